@@ -1,0 +1,143 @@
+"""ctypes mirror of include/h1v2_b200.h and the loader of the in-tree CUDA library.
+
+The library is the product: if it is missing or does not export a symbol the header declares, loading
+fails loudly -- there is no CPU or PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+NJ = 12
+NUM_REW = 20
+NUM_SLOT = 6
+OBS_TERM_DIM = 45
+MAX_HISTORY = 16
+LOG_DIM = 32
+
+REW_NAMES = [
+    "termination_penalty", "track_lin_vel_xy_exp", "track_ang_vel_z_exp", "feet_air_time", "feet_slide",
+    "dof_pos_limits", "joint_deviation_hip", "ang_vel_xy_l2", "dof_torques_l2", "dof_acc_l2", "action_rate_l2",
+    "flat_orientation_l2", "lin_vel_z_l2", "undesired_contacts", "track_lin_vel_xy_exp_base",
+    "track_ang_vel_z_exp_base", "feet_air_time_l2", "joint_vel_l2", "base_height_l2", "contact_forces",
+]
+LOG_COUNT, LOG_REW0, LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW = 0, 1, 21, 22, 23, 24
+LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS = 25, 26, 27
+
+f32, i32, u32, i64 = C.c_float, C.c_int32, C.c_uint32, C.c_int64
+
+
+class H1v2Config(C.Structure):
+    _fields_ = [
+        ("sim_dt", f32), ("decimation", i32), ("episode_length_s", f32),
+        ("action_scale", f32), ("default_joint_pos", f32 * NJ), ("joint_perm", i32 * NJ),
+        ("kp", f32 * NJ), ("kd", f32 * NJ), ("effort_limit", f32 * NJ), ("min_delay", i32), ("max_delay", i32),
+        ("gravity", f32), ("friction", f32),
+        ("dof_damping", f32 * 18), ("dof_armature", f32 * 18), ("dof_frictionloss", f32 * 18),
+        ("act_frc_limit", f32 * NJ), ("joint_range", (f32 * 2) * NJ),
+        ("contact_solref", f32 * 2), ("contact_solimp", f32 * 5),
+        ("floss_solref", f32 * 2), ("floss_solimp", f32 * 5),
+        ("limit_solref", f32 * 2), ("limit_solimp", f32 * 5),
+        ("solver_iterations", i32), ("solver_tolerance", f32),
+        ("history_length", i32), ("enable_corruption", i32),
+        ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_joint_pos", f32), ("noise_joint_vel", f32),
+        ("scale_ang_vel", f32), ("scale_gravity", f32), ("scale_cmd", f32), ("scale_joint_pos", f32),
+        ("scale_joint_vel", f32), ("scale_action", f32),
+        ("rew_weight", f32 * NUM_REW), ("track_std", f32), ("feet_air_threshold", f32),
+        ("contact_threshold", f32), ("soft_limit_factor", f32), ("base_height_target", f32),
+        ("mask_pos_limits", u32), ("mask_joint_dev", u32), ("mask_torques", u32), ("mask_undesired_slots", u32),
+        ("mask_illegal_slots", u32),
+        ("cmd_lin_x", f32 * 2), ("cmd_lin_y", f32 * 2), ("cmd_ang_z", f32 * 2), ("cmd_heading", f32 * 2),
+        ("cmd_resample_time", f32 * 2),
+        ("rel_standing_envs", f32), ("rel_heading_envs", f32), ("heading_stiffness", f32), ("heading_command", i32),
+        ("reset_pose_range", (f32 * 2) * 6), ("reset_vel_range", (f32 * 2) * 6),
+        ("reset_joint_pos_scale", f32 * 2), ("reset_joint_vel_scale", f32 * 2), ("init_root_height", f32),
+        ("push_enable", i32), ("push_interval_s", f32 * 2), ("push_vel_xy", f32 * 2),
+        ("mass_add_range", f32 * 2), ("friction_range", f32 * 2),
+        ("env_id_offset", i64), ("env_spacing", f32), ("reserved", i32 * 8),
+    ]
+
+    def copy(self) -> "H1v2Config":
+        out = H1v2Config()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(H1v2Config))
+        return out
+
+
+# (name, per-env element count as a function of history H, ctype)
+STATE_FIELDS = [
+    ("root_pos", 3, f32), ("root_quat", 4, f32), ("root_lin_vel", 3, f32), ("root_ang_vel", 3, f32),
+    ("joint_pos", NJ, f32), ("joint_vel", NJ, f32), ("last_action", NJ, f32), ("target_hist", 2 * NJ, f32),
+    ("lag", 1, i32), ("fresh", 1, i32), ("command", 3, f32), ("heading_target", 1, f32), ("time_left", 1, f32),
+    ("is_standing", 1, i32), ("is_heading", 1, i32), ("cmd_metrics", 2, f32), ("feet_timers", 8, f32),
+    ("episode_sums", NUM_REW, f32), ("obs_history", None, f32), ("friction", 1, f32), ("mass_add", 1, f32),
+    ("push_time_left", 1, f32),
+    ("slot_force", NUM_SLOT * 3, f32), ("slot_force_hist", NUM_SLOT * 3, f32), ("applied_torque", NJ, f32),
+    ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32),
+]
+READ_ONLY_STATE = {"slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel"}
+
+
+class H1v2State(C.Structure):
+    _fields_ = [(name, C.POINTER(ct)) for name, _, ct in STATE_FIELDS]
+
+
+def state_field_count(name: str, history: int) -> int:
+    for n, cnt, _ in STATE_FIELDS:
+        if n == name:
+            return history * OBS_TERM_DIM if cnt is None else cnt
+    raise KeyError(name)
+
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libh1v2_b200.so")
+
+_SYMBOLS = {
+    "h1v2_default_config": (C.c_int, [C.POINTER(H1v2Config)]),
+    "h1v2_create": (C.c_int, [C.POINTER(H1v2Config), i32, i32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "h1v2_destroy": (None, [C.c_void_p]),
+    "h1v2_last_error": (C.c_char_p, []),
+    "h1v2_obs_dim": (C.c_int, [C.c_void_p]),
+    "h1v2_num_envs": (C.c_int, [C.c_void_p]),
+    "h1v2_bind_episode_length": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "h1v2_reset": (C.c_int, [C.c_void_p, C.c_void_p, i32, C.c_void_p]),
+    "h1v2_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_get_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
+    "h1v2_set_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
+    "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "h1v2_get_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_launch_count": (i64, [C.c_void_p]),
+    "h1v2_random_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libh1v2_b200.so and bind every symbol of include/h1v2_b200.h; raises if anything is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: the CUDA extension is the product and there is no fallback. "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)."
+        )
+    lib = C.CDLL(p)
+    for name, (res, args) in _SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_config() -> H1v2Config:
+    cfg = H1v2Config()
+    rc = load_library().h1v2_default_config(C.byref(cfg))
+    if rc != 0:
+        raise RuntimeError("h1v2_default_config failed")
+    return cfg

@@ -1,0 +1,153 @@
+"""H1v2Sim: thin torch-facing wrapper over the C-ABI (include/h1v2_b200.h).
+
+PyTorch is used only for device memory and streams; all arithmetic of the step happens in the CUDA library.
+There is no fallback: constructing H1v2Sim without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import (H1v2Config, H1v2State, LOG_DIM, NJ, READ_ONLY_STATE, STATE_FIELDS, default_config, load_library,
+                    state_field_count)
+
+_TORCH_DT = {C.c_float: torch.float32, C.c_int32: torch.int32}
+
+
+class _DevPtr:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+class H1v2Sim:
+    def __init__(self, num_envs: int, cfg: H1v2Config | None = None, device: str | torch.device = "cuda:0",
+                 seed: int = 42, diagnostics: bool = False):
+        self._lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("H1v2Sim runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("H1v2Sim: no CUDA device visible; the CUDA kernels are the product, nothing to fall back to")
+        self.cfg = (cfg or default_config()).copy()
+        if diagnostics:
+            self.cfg.reserved[0] = 1
+        self.num_envs = int(num_envs)
+        self._h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(idx):
+            rc = self._lib.h1v2_create(C.byref(self.cfg), self.num_envs, idx, seed, C.byref(self._h))
+            if rc != 0:
+                raise RuntimeError("h1v2_create: " + self._lib.h1v2_last_error().decode())
+            self.obs_dim = self._lib.h1v2_obs_dim(self._h)
+            self.history = self.cfg.history_length
+            step_dt = self.cfg.sim_dt * self.cfg.decimation
+            import math
+            self.max_episode_length = int(math.ceil(self.cfg.episode_length_s / step_dt - 1e-9))
+            self.episode_length_buf = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+            self._check(self._lib.h1v2_bind_episode_length(self._h, self.episode_length_buf.data_ptr()))
+            p = C.c_void_p()
+            self._check(self._lib.h1v2_get_log(self._h, C.byref(p)))
+            self.log_buf = torch.as_tensor(_DevPtr(p.value, LOG_DIM), device=self.device)
+
+    # ------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(self._lib.h1v2_last_error().decode())
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.h1v2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def step(self, actions: torch.Tensor):
+        """One control step.  actions: float32 [N,12] on this device (external joint order)."""
+        a = actions
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
+            a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.shape != (self.num_envs, NJ):
+            raise ValueError(f"actions must be [{self.num_envs},{NJ}], got {tuple(a.shape)}")
+        obs = torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        rew = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        term = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        trunc = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._check(self._lib.h1v2_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(),
+                                        trunc.data_ptr(), self._stream()))
+        return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
+
+    def step_into(self, actions, obs, rew, term, trunc):
+        """Same as step() with caller-provided output tensors (no allocation; used by bench.py and CUDA graphs)."""
+        self._check(self._lib.h1v2_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(),
+                                        trunc.data_ptr(), self._stream()))
+
+    def step_host(self, actions, obs, rew, term, trunc):
+        """C-ABI call with HOST buffers (numpy or pinned CPU tensors); copies inside, synchronises."""
+        def ptr(x):
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        self._check(self._lib.h1v2_step_host(self._h, ptr(actions), ptr(obs), ptr(rew), ptr(term), ptr(trunc)))
+
+    def observe(self) -> torch.Tensor:
+        obs = torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        self._check(self._lib.h1v2_observe(self._h, obs.data_ptr(), self._stream()))
+        return obs
+
+    def reset(self, env_ids: torch.Tensor | None = None):
+        if env_ids is None:
+            self._check(self._lib.h1v2_reset(self._h, None, 0, self._stream()))
+        else:
+            ids = env_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            self._check(self._lib.h1v2_reset(self._h, ids.data_ptr(), ids.numel(), self._stream()))
+            self._keep = ids
+
+    def random_actions(self, step: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.num_envs, NJ), dtype=torch.float32, device=self.device)
+        self._check(self._lib.h1v2_random_actions(self._h, out.data_ptr(), step, self._stream()))
+        return out
+
+    # ------------------------------------------------------------------
+    def get_state(self, names=None) -> dict:
+        out, st = {}, H1v2State()
+        for name, _, ct in STATE_FIELDS:
+            if names is not None and name not in names:
+                continue
+            cnt = state_field_count(name, self.history)
+            t = torch.zeros((self.num_envs, cnt), dtype=_TORCH_DT[ct], device=self.device)
+            out[name] = t
+            setattr(st, name, C.cast(t.data_ptr(), C.POINTER(ct)))
+        self._check(self._lib.h1v2_get_state(self._h, C.byref(st), self._stream()))
+        return out
+
+    def set_state(self, state: dict):
+        st, keep = H1v2State(), []
+        for name, _, ct in STATE_FIELDS:
+            if name in state and name not in READ_ONLY_STATE:
+                cnt = state_field_count(name, self.history)
+                t = torch.as_tensor(state[name]).to(device=self.device, dtype=_TORCH_DT[ct]).reshape(self.num_envs, cnt).contiguous()
+                keep.append(t)
+                setattr(st, name, C.cast(t.data_ptr(), C.POINTER(ct)))
+        self._check(self._lib.h1v2_set_state(self._h, C.byref(st), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # keep the staging tensors alive until consumed
+
+    def log_host(self):
+        import numpy as np
+        out = np.zeros(LOG_DIM, np.float32)
+        self._check(self._lib.h1v2_get_log_host(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.h1v2_launch_count(self._h))

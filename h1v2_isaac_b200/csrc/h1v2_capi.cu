@@ -1,0 +1,509 @@
+// h1v2_capi.cu -- host side of the C-ABI declared in include/h1v2_b200.h.
+// Owns the device state, builds the kernel parameter block from H1v2Config + the compiled model tables,
+// launches the fused step kernel.  No torch types, no synchronisation except where the header says so.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/h1v2_model_h12.h"
+#include "h1v2_step.cuh"
+
+using namespace h1v2;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+struct H1v2Handle {
+  H1v2Config cfg;
+  KParams P;
+  KState S;
+  int n = 0, device = 0;
+  uint64_t seed = 0;
+  int64_t launches = 0;
+  std::vector<void*> allocs;
+  int64_t* own_ep_len = nullptr;
+  // staging for h1v2_step_host
+  float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+  uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  cudaStream_t host_stream = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// auxiliary kernels (not on the step path)
+// ------------------------------------------------------------------------------------------------------
+__global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, const int64_t* __restrict__ ids, int n_ids,
+                             int startup) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gtid >> 1, side = gtid & 1;
+  if (i >= n_ids) return;
+  const int env = ids ? (int)ids[i] : i;
+  if (env < 0 || env >= P.n) return;
+  const int N = P.n, N2 = 2 * P.n, lidx = 2 * env + side;
+  const int64_t gid = P.env_id_offset + env;
+  const unsigned long long step = S.counters[0];
+  float4 r3 = S.root[3 * N + env];
+  float mu = r3.y, mass_add = r3.z, push_left = r3.w;
+  (void)startup;
+  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
+  float4 tm;
+  CmdState cmd;
+  cmd.flags = 0; cmd.heading_target = 0.f;
+  reset_env(P, side, gid, step, rp, rq, rv, rw, q, qd, la, T1, T2, tm, cmd, push_left);
+  if (side == 0) {
+    S.root[env] = make_float4(rp[0], rp[1], rp[2], rq[0]);
+    S.root[N + env] = make_float4(rq[1], rq[2], rq[3], rv[0]);
+    S.root[2 * N + env] = make_float4(rv[1], rv[2], rw[0], rw[1]);
+    S.root[3 * N + env] = make_float4(rw[2], mu, mass_add, push_left);
+    S.cmd[env] = make_float4(cmd.c[0], cmd.c[1], cmd.c[2], cmd.heading_target);
+    S.cmd[N + env] = make_float4(cmd.time_left, 0.f, 0.f, __int_as_float(cmd.flags));
+    S.ep_len[env] = 0;
+    for (int k = 0; k < 5; k++) S.epsum[(size_t)k * N + env] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  S.leg[lidx] = make_float4(q[0], q[1], q[2], q[3]);
+  S.leg[N2 + lidx] = make_float4(q[4], q[5], qd[0], qd[1]);
+  S.leg[2 * N2 + lidx] = make_float4(qd[2], qd[3], qd[4], qd[5]);
+  for (int k = 0; k < 5; k++) S.act[(size_t)k * N2 + lidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  S.timers[lidx] = tm;
+}
+
+__global__ void startup_kernel(const __grid_constant__ KParams P, const KState S, float fr_lo, float fr_hi, float ma_lo, float ma_hi) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= P.n) return;
+  float u[4];
+  rng4(P.key0, P.env_id_offset + env, 0ull, STREAM_EVENT, 0, u);
+  S.root[3 * P.n + env] = make_float4(0.f, uni(u[0], fr_lo, fr_hi), uni(u[1], ma_lo, ma_hi), 0.f);
+}
+
+__global__ void random_actions_kernel(const __grid_constant__ KParams P, float* __restrict__ actions, unsigned long long step) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= P.n) return;
+  const int64_t gid = P.env_id_offset + env;
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    float u[4], z[4];
+    rng4(P.key0, gid, step, STREAM_ACTIONS, b, u);
+    // Box-Muller on (u0,u1) and (u2,u3); 1-u keeps the log argument in (0,1]
+    float r0 = sqrtf(-2.f * logf(1.f - u[0])), r1 = sqrtf(-2.f * logf(1.f - u[2]));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u[1], &s0, &c0);
+    sincospif(2.f * u[3], &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) actions[(size_t)env * 12 + 4 * b + k] = z[k];
+  }
+}
+
+// natural-layout state exchange; one thread per env
+__global__ void state_io_kernel(const __grid_constant__ KParams P, const KState S, const H1v2State st, int set) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= P.n) return;
+  const int N = P.n, N2 = 2 * P.n, H = P.H;
+  float4 r[4], c[2];
+  for (int k = 0; k < 4; k++) r[k] = S.root[(size_t)k * N + env];
+  for (int k = 0; k < 2; k++) c[k] = S.cmd[(size_t)k * N + env];
+  int flags = __float_as_int(c[1].w);
+  float root[16] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w, r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
+  float leg[2][12], act[2][20], tmr[2][4], es[20];
+  for (int s = 0; s < 2; s++) {
+    const int l = 2 * env + s;
+    for (int k = 0; k < 3; k++) { float4 v = S.leg[(size_t)k * N2 + l]; leg[s][4 * k] = v.x; leg[s][4 * k + 1] = v.y; leg[s][4 * k + 2] = v.z; leg[s][4 * k + 3] = v.w; }
+    for (int k = 0; k < 5; k++) { float4 v = S.act[(size_t)k * N2 + l]; act[s][4 * k] = v.x; act[s][4 * k + 1] = v.y; act[s][4 * k + 2] = v.z; act[s][4 * k + 3] = v.w; }
+    float4 t = S.timers[l]; tmr[s][0] = t.x; tmr[s][1] = t.y; tmr[s][2] = t.z; tmr[s][3] = t.w;
+  }
+  for (int k = 0; k < 5; k++) { float4 v = S.epsum[(size_t)k * N + env]; es[4 * k] = v.x; es[4 * k + 1] = v.y; es[4 * k + 2] = v.z; es[4 * k + 3] = v.w; }
+  const int head = (int)(S.counters[1] % (unsigned long long)H);
+  if (!set) {
+    if (st.root_pos) for (int k = 0; k < 3; k++) st.root_pos[env * 3 + k] = root[k];
+    if (st.root_quat) for (int k = 0; k < 4; k++) st.root_quat[env * 4 + k] = root[3 + k];
+    if (st.root_lin_vel) for (int k = 0; k < 3; k++) st.root_lin_vel[env * 3 + k] = root[7 + k];
+    if (st.root_ang_vel) for (int k = 0; k < 3; k++) st.root_ang_vel[env * 3 + k] = root[10 + k];
+    for (int s = 0; s < 2; s++)
+      for (int k = 0; k < 6; k++) {
+        const int j = 6 * s + k;
+        if (st.joint_pos) st.joint_pos[env * 12 + j] = leg[s][k];
+        if (st.joint_vel) st.joint_vel[env * 12 + j] = leg[s][6 + k];
+        if (st.last_action) st.last_action[env * 12 + P.inv_perm[j]] = act[s][k];
+        if (st.target_hist) { st.target_hist[env * 24 + j] = act[s][6 + k]; st.target_hist[env * 24 + 12 + j] = act[s][12 + k]; }
+      }
+    if (st.lag) st.lag[env] = (flags >> FLAG_LAG_SHIFT) & 7;
+    if (st.fresh) st.fresh[env] = flags & 3;
+    if (st.command) { st.command[env * 3] = c[0].x; st.command[env * 3 + 1] = c[0].y; st.command[env * 3 + 2] = c[0].z; }
+    if (st.heading_target) st.heading_target[env] = c[0].w;
+    if (st.time_left) st.time_left[env] = c[1].x;
+    if (st.is_standing) st.is_standing[env] = (flags & FLAG_STANDING) != 0;
+    if (st.is_heading) st.is_heading[env] = (flags & FLAG_HEADING) != 0;
+    if (st.cmd_metrics) { st.cmd_metrics[env * 2] = c[1].y; st.cmd_metrics[env * 2 + 1] = c[1].z; }
+    if (st.feet_timers) for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) st.feet_timers[env * 8 + 4 * s + k] = tmr[s][k];
+    if (st.episode_sums) for (int k = 0; k < 20; k++) st.episode_sums[env * 20 + k] = es[k];
+    if (st.obs_history)
+      for (int hh = 0; hh < H; hh++) {
+        int sl = (head + 1 + hh) % H;
+        for (int k = 0; k < 45; k++) st.obs_history[((size_t)env * H + hh) * 45 + k] = S.hist[((size_t)env * H + sl) * H1V2_HIST_STRIDE + k];
+      }
+    if (st.friction) st.friction[env] = root[13];
+    if (st.mass_add) st.mass_add[env] = root[14];
+    if (st.push_time_left) st.push_time_left[env] = root[15];
+    if (S.diag) {
+      const float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
+      if (st.slot_force) for (int k = 0; k < 18; k++) st.slot_force[env * 18 + k] = dg[k];
+      if (st.slot_force_hist) for (int k = 0; k < 18; k++) st.slot_force_hist[env * 18 + k] = dg[18 + k];
+      if (st.applied_torque) for (int k = 0; k < 12; k++) st.applied_torque[env * 12 + k] = dg[36 + k];
+      if (st.joint_acc) for (int k = 0; k < 12; k++) st.joint_acc[env * 12 + k] = dg[48 + k];
+      if (st.reward_terms) for (int k = 0; k < 20; k++) st.reward_terms[env * 20 + k] = dg[60 + k];
+      if (st.foot_vel) for (int k = 0; k < 6; k++) st.foot_vel[env * 6 + k] = dg[80 + k];
+    }
+    return;
+  }
+  // ---- set ----
+  if (st.root_pos) for (int k = 0; k < 3; k++) root[k] = st.root_pos[env * 3 + k];
+  if (st.root_quat) for (int k = 0; k < 4; k++) root[3 + k] = st.root_quat[env * 4 + k];
+  if (st.root_lin_vel) for (int k = 0; k < 3; k++) root[7 + k] = st.root_lin_vel[env * 3 + k];
+  if (st.root_ang_vel) for (int k = 0; k < 3; k++) root[10 + k] = st.root_ang_vel[env * 3 + k];
+  if (st.friction) root[13] = st.friction[env];
+  if (st.mass_add) root[14] = st.mass_add[env];
+  if (st.push_time_left) root[15] = st.push_time_left[env];
+  for (int s = 0; s < 2; s++)
+    for (int k = 0; k < 6; k++) {
+      const int j = 6 * s + k;
+      if (st.joint_pos) leg[s][k] = st.joint_pos[env * 12 + j];
+      if (st.joint_vel) leg[s][6 + k] = st.joint_vel[env * 12 + j];
+      if (st.last_action) act[s][k] = st.last_action[env * 12 + P.inv_perm[j]];
+      if (st.target_hist) { act[s][6 + k] = st.target_hist[env * 24 + j]; act[s][12 + k] = st.target_hist[env * 24 + 12 + j]; }
+    }
+  if (st.lag) flags = (flags & ~(7 << FLAG_LAG_SHIFT)) | ((st.lag[env] & 7) << FLAG_LAG_SHIFT);
+  if (st.fresh) flags = (flags & ~3) | (st.fresh[env] & 3);
+  if (st.is_standing) flags = (flags & ~FLAG_STANDING) | (st.is_standing[env] ? FLAG_STANDING : 0);
+  if (st.is_heading) flags = (flags & ~FLAG_HEADING) | (st.is_heading[env] ? FLAG_HEADING : 0);
+  if (st.command) { c[0].x = st.command[env * 3]; c[0].y = st.command[env * 3 + 1]; c[0].z = st.command[env * 3 + 2]; }
+  if (st.heading_target) c[0].w = st.heading_target[env];
+  if (st.time_left) c[1].x = st.time_left[env];
+  if (st.cmd_metrics) { c[1].y = st.cmd_metrics[env * 2]; c[1].z = st.cmd_metrics[env * 2 + 1]; }
+  c[1].w = __int_as_float(flags);
+  if (st.feet_timers) for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) tmr[s][k] = st.feet_timers[env * 8 + 4 * s + k];
+  if (st.episode_sums) for (int k = 0; k < 20; k++) es[k] = st.episode_sums[env * 20 + k];
+  if (st.obs_history)
+    for (int hh = 0; hh < H; hh++) {
+      int sl = (head + 1 + hh) % H;
+      for (int k = 0; k < 45; k++) S.hist[((size_t)env * H + sl) * H1V2_HIST_STRIDE + k] = st.obs_history[((size_t)env * H + hh) * 45 + k];
+    }
+  for (int k = 0; k < 4; k++) S.root[(size_t)k * N + env] = make_float4(root[4 * k], root[4 * k + 1], root[4 * k + 2], root[4 * k + 3]);
+  for (int k = 0; k < 2; k++) S.cmd[(size_t)k * N + env] = c[k];
+  for (int s = 0; s < 2; s++) {
+    const int l = 2 * env + s;
+    for (int k = 0; k < 3; k++) S.leg[(size_t)k * N2 + l] = make_float4(leg[s][4 * k], leg[s][4 * k + 1], leg[s][4 * k + 2], leg[s][4 * k + 3]);
+    for (int k = 0; k < 5; k++) S.act[(size_t)k * N2 + l] = make_float4(act[s][4 * k], act[s][4 * k + 1], act[s][4 * k + 2], act[s][4 * k + 3]);
+    S.timers[l] = make_float4(tmr[s][0], tmr[s][1], tmr[s][2], tmr[s][3]);
+  }
+  for (int k = 0; k < 5; k++) S.epsum[(size_t)k * N + env] = make_float4(es[4 * k], es[4 * k + 1], es[4 * k + 2], es[4 * k + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// parameter block
+// ------------------------------------------------------------------------------------------------------
+static double impedance_h(const float* solimp, double pos) {
+  double dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  auto cl = [](double v) { return v < 1e-4 ? 1e-4 : (v > 0.9999 ? 0.9999 : v); };
+  dmin = cl(dmin); dmax = cl(dmax); mid = cl(mid);
+  if (power < 1) power = 1;
+  if (dmin == dmax || width <= 1e-15) return 0.5 * (dmin + dmax);
+  double x = std::fabs(pos) / width;
+  if (x >= 1) return dmax;
+  if (x == 0) return dmin;
+  double y = power == 1 ? x : (x <= mid ? std::pow(x, power) / std::pow(mid, power - 1) : 1 - std::pow(1 - x, power) / std::pow(1 - mid, power - 1));
+  return dmin + y * (dmax - dmin);
+}
+static void kb_h(const float* solref, const float* solimp, double dt, float* K, float* B) {
+  double tc = solref[0], dr = solref[1], dmax = solimp[1];
+  dmax = dmax < 1e-4 ? 1e-4 : (dmax > 0.9999 ? 0.9999 : dmax);
+  if (tc < 2 * dt) tc = 2 * dt;  // refsafe
+  *K = (float)(1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr));
+  *B = (float)(2.0 / std::fmax(1e-15, dmax * tc));
+}
+
+static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
+  std::memset(&P, 0, sizeof(P));
+  static const int axis_expect[6] = {2, 1, 0, 1, 1, 0};
+  for (int s = 0; s < 2; s++)
+    for (int i = 0; i < 6; i++) {
+      const int b = 1 + 6 * s + i;
+      if (h1v2_body_parent[b] != (i == 0 ? 0 : b - 1)) return fail("model: unexpected kinematic tree");
+      for (int k = 0; k < 3; k++)
+        if (h1v2_jnt_axis[b - 1][k] != (k == axis_expect[i] ? 1.0 : 0.0)) return fail("model: unexpected joint axis pattern");
+      KLeg& L = P.leg[s];
+      for (int k = 0; k < 3; k++) { L.pos[i][k] = (float)h1v2_body_pos[b][k]; L.ipos[i][k] = (float)h1v2_body_ipos[b][k]; }
+      const double* I = h1v2_body_inertia[b];
+      const double six[6] = {I[0], I[4], I[8], I[1], I[2], I[5]};
+      for (int k = 0; k < 6; k++) L.inertia[i][k] = (float)six[k];
+      L.mass[i] = (float)h1v2_body_mass[b];
+    }
+  {
+    int nf[2] = {0, 0}, ns[2] = {0, 0}, nr = 0;
+    for (int r = 0; r < H1V2_NCOLL; r++) {
+      const double* row = h1v2_coll[r];
+      const int b = (int)row[0], slot = (int)row[5];
+      if (slot < 2) { float* d = P.leg[slot].foot_pt[nf[slot]++]; d[0] = (float)row[1]; d[1] = (float)row[2]; d[2] = (float)row[3]; }
+      else if (slot < 4) { float* d = P.leg[slot - 2].shin_pt[ns[slot - 2]++]; d[0] = (float)row[1]; d[1] = (float)row[2]; d[2] = (float)row[3]; P.leg[slot - 2].shin_rad = (float)row[4]; }
+      else { float* d = P.root_pt[nr]; d[0] = (float)row[1]; d[1] = (float)row[2]; d[2] = (float)row[3]; P.root_rad[nr++] = (float)row[4]; }
+      (void)b;
+    }
+    if (nf[0] != 4 || nf[1] != 4 || ns[0] != 2 || ns[1] != 2 || nr != 9) return fail("model: unexpected collider table");
+  }
+  P.root_mass = (float)h1v2_body_mass[0];
+  for (int k = 0; k < 3; k++) P.root_ipos[k] = (float)h1v2_body_ipos[0][k];
+  {
+    const double* I = h1v2_body_inertia[0];
+    const double six[6] = {I[0], I[4], I[8], I[1], I[2], I[5]};
+    for (int k = 0; k < 6; k++) P.root_inertia[k] = (float)six[k];
+  }
+  P.h = c.sim_dt; P.decimation = c.decimation; P.step_dt = c.sim_dt * (float)c.decimation;
+  P.max_episode_length = (int64_t)std::ceil((double)c.episode_length_s / ((double)c.sim_dt * c.decimation) - 1e-9);
+  P.max_episode_length_s = c.episode_length_s;
+  P.action_scale = c.action_scale;
+  bool seen[12] = {false};
+  for (int i = 0; i < 12; i++) {
+    P.q0[i] = c.default_joint_pos[i]; P.kp[i] = c.kp[i]; P.kd[i] = c.kd[i]; P.effort[i] = c.effort_limit[i]; P.frc[i] = c.act_frc_limit[i];
+    const int j = c.joint_perm[i];
+    if (j < 0 || j >= 12 || seen[j]) return fail("config: joint_perm is not a permutation");
+    seen[j] = true;
+    P.perm[i] = j; P.inv_perm[j] = i;
+    P.range_lo[i] = c.joint_range[i][0]; P.range_hi[i] = c.joint_range[i][1];
+    const double mid = 0.5 * ((double)c.joint_range[i][0] + c.joint_range[i][1]), half = 0.5 * ((double)c.joint_range[i][1] - c.joint_range[i][0]) * c.soft_limit_factor;
+    P.soft_lo[i] = (float)(mid - half); P.soft_hi[i] = (float)(mid + half);
+    P.limit_invw[i] = (float)h1v2_dof_invweight0[6 + i];
+  }
+  if (c.min_delay < 0 || c.max_delay > 7 || c.max_delay < c.min_delay) return fail("config: delays must satisfy 0 <= min <= max <= 7");
+  if (c.max_delay > 2 * c.decimation) return fail("config: max_delay exceeds two control steps");
+  P.min_delay = c.min_delay; P.max_delay = c.max_delay;
+  P.gravity = c.gravity;
+  float Kf, Bf;
+  kb_h(c.floss_solref, c.floss_solimp, c.sim_dt, &Kf, &Bf);
+  P.floss_B = Bf;
+  const double imp0 = impedance_h(c.floss_solimp, 0.0);
+  for (int d = 0; d < 18; d++) {
+    P.damping[d] = c.dof_damping[d]; P.armature[d] = c.dof_armature[d]; P.floss[d] = c.dof_frictionloss[d];
+    const double R = std::fmax(1e-15, (1 - imp0) * h1v2_dof_invweight0[d] / imp0);
+    P.floss_D[d] = c.dof_frictionloss[d] > 0 ? (float)(1.0 / R) : 0.f;
+    P.floss_lim[d] = (float)(R * c.dof_frictionloss[d]);
+  }
+  kb_h(c.limit_solref, c.limit_solimp, c.sim_dt, &P.limit_K, &P.limit_B);
+  kb_h(c.contact_solref, c.contact_solimp, c.sim_dt, &P.contact_K, &P.contact_B);
+  for (int k = 0; k < 5; k++) { P.limit_imp[k] = c.limit_solimp[k]; P.contact_imp[k] = c.contact_solimp[k]; }
+  for (int s = 0; s < 6; s++) P.slot_tran[s] = (float)h1v2_slot_invweight_tran[s];
+  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance;
+  P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
+  if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
+  P.H = c.history_length; P.obs_dim = c.history_length * H1V2_OBS_TERM_DIM; P.corrupt = c.enable_corruption;
+  P.n_av = c.noise_ang_vel; P.n_g = c.noise_gravity; P.n_q = c.noise_joint_pos; P.n_v = c.noise_joint_vel;
+  P.s_av = c.scale_ang_vel; P.s_g = c.scale_gravity; P.s_cmd = c.scale_cmd; P.s_q = c.scale_joint_pos; P.s_v = c.scale_joint_vel; P.s_a = c.scale_action;
+  for (int t = 0; t < H1V2_NUM_REW; t++) P.w[t] = c.rew_weight[t];
+  P.inv_std2 = 1.f / (c.track_std * c.track_std); P.air_thr = c.feet_air_threshold; P.contact_thr = c.contact_threshold; P.base_h = c.base_height_target;
+  P.m_poslim = c.mask_pos_limits; P.m_dev = c.mask_joint_dev; P.m_tau = c.mask_torques; P.m_undesired = c.mask_undesired_slots; P.m_illegal = c.mask_illegal_slots;
+  for (int k = 0; k < 2; k++) {
+    P.c_lx[k] = c.cmd_lin_x[k]; P.c_ly[k] = c.cmd_lin_y[k]; P.c_wz[k] = c.cmd_ang_z[k]; P.c_hd[k] = c.cmd_heading[k]; P.c_rt[k] = c.cmd_resample_time[k];
+    P.rjp[k] = c.reset_joint_pos_scale[k]; P.rjv[k] = c.reset_joint_vel_scale[k]; P.push_int[k] = c.push_interval_s[k]; P.push_v[k] = c.push_vel_xy[k];
+    for (int a = 0; a < 6; a++) { P.rp[a][k] = c.reset_pose_range[a][k]; P.rv[a][k] = c.reset_vel_range[a][k]; }
+  }
+  P.rel_standing = c.rel_standing_envs; P.rel_heading = c.rel_heading_envs; P.k_heading = c.heading_stiffness; P.heading_cmd = c.heading_command;
+  P.max_command_step = c.cmd_resample_time[1] / P.step_dt;
+  P.init_h = c.init_root_height; P.push_enable = c.push_enable;
+  P.key0 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+  P.env_id_offset = c.env_id_offset;
+  P.n = n;
+  return 0;
+}
+
+template <typename T>
+static int dalloc(H1v2Handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(q, 0, count * sizeof(T));
+  if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* h1v2_last_error(void) { return g_err.c_str(); }
+
+int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t seed, H1v2Handle** out) {
+  if (!cfg || !out || n_envs <= 0) return fail("h1v2_create: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("h1v2_create: no CUDA device (the CUDA path is the product; there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  H1v2Handle* h = new H1v2Handle();
+  h->cfg = *cfg; h->n = n_envs; h->device = device; h->seed = seed;
+  if (build_params(*cfg, n_envs, seed, h->P) != 0) { delete h; return -1; }
+  const size_t N = (size_t)n_envs;
+  KState& S = h->S;
+  int rc = 0;
+  rc |= dalloc(h, &S.root, 4 * N);
+  rc |= dalloc(h, &S.leg, 3 * 2 * N);
+  rc |= dalloc(h, &S.act, 5 * 2 * N);
+  rc |= dalloc(h, &S.cmd, 2 * N);
+  rc |= dalloc(h, &S.timers, 2 * N);
+  rc |= dalloc(h, &S.epsum, 5 * N);
+  rc |= dalloc(h, &S.hist, N * (size_t)h->P.H * H1V2_HIST_STRIDE);
+  rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM);
+  rc |= dalloc(h, &S.log, (size_t)H1V2_LOG_DIM);
+  rc |= dalloc(h, &S.counters, (size_t)2);
+  rc |= dalloc(h, &h->own_ep_len, N);
+  int* lut_d = nullptr;
+  rc |= dalloc(h, &lut_d, (size_t)h->P.obs_dim);
+  if (cfg->reserved[0]) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);
+  if (rc != 0) { h1v2_destroy(h); return -1; }
+  S.ep_len = h->own_ep_len;
+  {
+    std::vector<int> lut(h->P.obs_dim);
+    static const int off[7] = {0, 3, 6, 9, 21, 33, 45};
+    int w = 0;
+    for (int t = 0; t < 6; t++)
+      for (int hh = 0; hh < h->P.H; hh++)
+        for (int k = off[t]; k < off[t + 1]; k++) lut[w++] = (hh << 8) | k;
+    CK(cudaMemcpy(lut_d, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
+    S.lut = lut_d;
+  }
+  CK(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
+  reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, 0);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+void h1v2_destroy(H1v2Handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  for (void* p : {(void*)h->d_act, (void*)h->d_obs, (void*)h->d_rew, (void*)h->d_term, (void*)h->d_trunc})
+    if (p) cudaFree(p);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+}
+
+int h1v2_obs_dim(const H1v2Handle* h) { return h ? h->P.obs_dim : -1; }
+int h1v2_num_envs(const H1v2Handle* h) { return h ? h->n : -1; }
+int64_t h1v2_launch_count(const H1v2Handle* h) { return h ? h->launches : -1; }
+
+int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length) {
+  if (!h) return fail("null handle");
+  if (episode_length) {
+    CK(cudaMemcpy(episode_length, h->S.ep_len, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice));
+    h->S.ep_len = episode_length;
+  } else {
+    h->S.ep_len = h->own_ep_len;
+  }
+  return 0;
+}
+
+int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int cnt = env_ids ? n : h->n;
+  if (cnt <= 0) return 0;
+  reset_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(h->P, h->S, env_ids, cnt, 0);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st) {
+  const int threads = 64, lanes = 2 * h->n;
+  const int blocks = (lanes + threads - 1) / threads;
+  if (do_step)
+    step_kernel<true><<<blocks, threads, 0, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
+  else
+    step_kernel<false><<<blocks, threads, 0, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
+  finalize_kernel<<<1, 32, 0, st>>>(h->S, do_step ? 1 : 0);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int h1v2_observe(H1v2Handle* h, float* obs, void* cuda_stream) {
+  if (!h || !obs) return fail("h1v2_observe: bad arguments");
+  return launch_step(h, false, nullptr, obs, nullptr, nullptr, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int h1v2_step(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated, void* cuda_stream) {
+  if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step: bad arguments");
+  return launch_step(h, true, actions, obs, rew, terminated, truncated, (cudaStream_t)cuda_stream);
+}
+
+int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated) {
+  if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step_host: bad arguments");
+  const size_t N = (size_t)h->n, od = (size_t)h->P.obs_dim;
+  if (!h->d_act) {
+    CK(cudaMalloc(&h->d_act, N * 12 * sizeof(float)));
+    CK(cudaMalloc(&h->d_obs, N * od * sizeof(float)));
+    CK(cudaMalloc(&h->d_rew, N * sizeof(float)));
+    CK(cudaMalloc(&h->d_term, N));
+    CK(cudaMalloc(&h->d_trunc, N));
+  }
+  cudaStream_t st = h->host_stream;
+  CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (launch_step(h, true, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, st) != 0) return -1;
+  CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
+  if (!h || !dst) return fail("h1v2_get_state: bad arguments");
+  state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *dst, 0);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream) {
+  if (!h || !src) return fail("h1v2_set_state: bad arguments");
+  state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *src, 1);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+int h1v2_get_log(H1v2Handle* h, const float** log_dev) {
+  if (!h || !log_dev) return fail("h1v2_get_log: bad arguments");
+  *log_dev = h->S.log;
+  return 0;
+}
+int h1v2_get_log_host(H1v2Handle* h, float* log_host) {
+  if (!h || !log_host) return fail("h1v2_get_log_host: bad arguments");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(log_host, h->S.log, sizeof(float) * H1V2_LOG_DIM, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream) {
+  if (!h || !actions) return fail("h1v2_random_actions: bad arguments");
+  random_actions_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(h->P, actions, step);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

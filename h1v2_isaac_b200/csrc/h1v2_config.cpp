@@ -1,0 +1,114 @@
+// h1v2_config.cpp -- resolved configuration of Isaac-Velocity-Flat-H12_12dof-v0 as a POD (host only).
+//
+// Every number cites where the reference pins it (paths relative to the reference root):
+//   V  = packages/biped_tasks/biped_tasks/tasks/locomotion/velocity
+//   C12= V/config/h12_12dof ;  A = packages/biped_assets/biped_assets
+#include <cmath>
+#include <cstring>
+
+#include "../../include/h1v2_b200.h"
+#include "../../include/h1v2_model_h12.h"
+
+extern "C" int h1v2_default_config(H1v2Config* c) {
+  if (!c) return -1;
+  std::memset(c, 0, sizeof(*c));
+  // timing: V/velocity_env_cfg.py:302-305
+  c->sim_dt = 0.005f;
+  c->decimation = 4;
+  c->episode_length_s = 20.0f;
+  // action: V/velocity_env_cfg.py:111 ; default pose A/robots/h12.py:38-53 == h12_12dof.xml:362-368
+  c->action_scale = 0.5f;
+  for (int j = 0; j < H1V2_NJ; j++) c->default_joint_pos[j] = (float)h1v2_key_qpos[7 + j];
+  // joint_names=[".*"] without preserve_order -> PhysX breadth-first order, L/R interleaved
+  static const int perm[12] = {0, 6, 1, 7, 2, 8, 3, 9, 4, 10, 5, 11};
+  for (int i = 0; i < H1V2_NJ; i++) c->joint_perm[i] = perm[i];
+  // actuators: A/robots/h12.py:58-113 (MJCF order: yaw pitch roll knee ankle_pitch ankle_roll)
+  static const float kp6[6] = {200, 200, 200, 300, 40, 40}, kd6[6] = {2.5f, 2.5f, 2.5f, 4, 2, 2};
+  static const float ef6[6] = {220, 220, 220, 360, 45, 45};
+  for (int j = 0; j < H1V2_NJ; j++) {
+    c->kp[j] = kp6[j % 6];
+    c->kd[j] = kd6[j % 6];
+    c->effort_limit[j] = ef6[j % 6];
+  }
+  c->min_delay = 0;
+  c->max_delay = 5;
+  // physics: h12_12dof.xml:4-7 defaults, :73..134 ranges; MuJoCo defaults for solref/solimp;
+  // contact solref = equal-weight mix of the robot geoms (0.005 1) and the floor (default 0.02 1)
+  c->gravity = 9.81f;
+  c->friction = 0.8f;  // robot static 0.8 x ground 1.0, "multiply": V/velocity_env_cfg.py:40-51,153-163
+  for (int d = 0; d < 18; d++) {
+    c->dof_damping[d] = (float)h1v2_dof_damping[d];
+    c->dof_armature[d] = (float)h1v2_dof_armature[d];
+    c->dof_frictionloss[d] = (float)h1v2_dof_frictionloss[d];
+  }
+  for (int j = 0; j < H1V2_NJ; j++) {
+    c->act_frc_limit[j] = (float)h1v2_jnt_frcrange[j];
+    c->joint_range[j][0] = (float)h1v2_jnt_range[j][0];
+    c->joint_range[j][1] = (float)h1v2_jnt_range[j][1];
+  }
+  c->contact_solref[0] = 0.5f * (0.005f + 0.02f);
+  c->contact_solref[1] = 1.0f;
+  static const float solimp[5] = {0.9f, 0.95f, 0.001f, 0.5f, 2.0f};
+  std::memcpy(c->contact_solimp, solimp, sizeof(solimp));
+  std::memcpy(c->floss_solimp, solimp, sizeof(solimp));
+  std::memcpy(c->limit_solimp, solimp, sizeof(solimp));
+  c->floss_solref[0] = 0.02f; c->floss_solref[1] = 1.0f;
+  c->limit_solref[0] = 0.02f; c->limit_solref[1] = 1.0f;
+  c->solver_iterations = 8;
+  c->solver_tolerance = 1e-6f;
+  // observations: V/velocity_env_cfg.py:123-132 ; C12/flat_env_cfg.py:25-27
+  c->history_length = 10;
+  c->enable_corruption = 1;
+  c->noise_ang_vel = 0.2f;
+  c->noise_gravity = 0.05f;
+  c->noise_joint_pos = 0.01f;
+  c->noise_joint_vel = 1.5f;
+  c->scale_ang_vel = c->scale_gravity = c->scale_cmd = c->scale_joint_pos = c->scale_joint_vel = c->scale_action = 1.0f;
+  // rewards: C12/rough_env_cfg.py:18-62,112-120 ; C12/flat_env_cfg.py:35-44 ; V/velocity_env_cfg.py:225-257
+  c->rew_weight[H1V2_REW_TERMINATION] = -200.0f;
+  c->rew_weight[H1V2_REW_TRACK_LIN_XY_YAW] = 1.0f;
+  c->rew_weight[H1V2_REW_TRACK_ANG_Z_WORLD] = 1.0f;
+  c->rew_weight[H1V2_REW_FEET_AIR_BIPED] = 0.75f;
+  c->rew_weight[H1V2_REW_FEET_SLIDE] = -0.25f;
+  c->rew_weight[H1V2_REW_DOF_POS_LIMITS] = -1.0f;
+  c->rew_weight[H1V2_REW_JOINT_DEV_HIP] = -0.2f;
+  c->rew_weight[H1V2_REW_ANG_VEL_XY] = -0.05f;
+  c->rew_weight[H1V2_REW_TORQUES] = -2.0e-6f;
+  c->rew_weight[H1V2_REW_DOF_ACC] = -1.0e-7f;
+  c->rew_weight[H1V2_REW_ACTION_RATE] = -0.005f;
+  c->rew_weight[H1V2_REW_FLAT_ORI] = -1.0f;
+  c->track_std = 0.5f;
+  c->feet_air_threshold = 0.4f;
+  c->contact_threshold = 1.0f;
+  c->soft_limit_factor = 0.9f;  // A/robots/h12.py:56
+  c->base_height_target = 0.98f;
+  c->mask_pos_limits = (1u << 4) | (1u << 5) | (1u << 10) | (1u << 11);
+  c->mask_joint_dev = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8);
+  c->mask_torques = 0xFFFu;
+  c->mask_undesired_slots = (1u << 2) | (1u << 3);
+  // terminations: C12/rough_env_cfg.py:95-109 (bodies with colliders: knee links, torso, pelvis)
+  c->mask_illegal_slots = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 5);
+  // commands: V/velocity_env_cfg.py:90-104 ; C12/flat_env_cfg.py:46-48
+  c->cmd_lin_x[0] = 0.0f; c->cmd_lin_x[1] = 1.0f;
+  c->cmd_lin_y[0] = -0.5f; c->cmd_lin_y[1] = 0.5f;
+  c->cmd_ang_z[0] = -1.0f; c->cmd_ang_z[1] = 1.0f;
+  c->cmd_heading[0] = -(float)M_PI; c->cmd_heading[1] = (float)M_PI;
+  c->cmd_resample_time[0] = c->cmd_resample_time[1] = 10.0f;
+  c->rel_standing_envs = 0.02f;
+  c->rel_heading_envs = 1.0f;
+  c->heading_stiffness = 0.5f;
+  c->heading_command = 1;
+  // reset events: C12/rough_env_cfg.py:78-92 ; V/velocity_env_cfg.py:200-209
+  c->reset_pose_range[0][0] = -0.5f; c->reset_pose_range[0][1] = 0.5f;
+  c->reset_pose_range[1][0] = -0.5f; c->reset_pose_range[1][1] = 0.5f;
+  c->reset_pose_range[5][0] = -3.14f; c->reset_pose_range[5][1] = 3.14f;
+  c->reset_joint_pos_scale[0] = c->reset_joint_pos_scale[1] = 1.0f;
+  c->init_root_height = 1.05f;  // A/robots/h12.py:38
+  c->push_enable = 0;           // C12/rough_env_cfg.py:78
+  c->push_interval_s[0] = 10.0f; c->push_interval_s[1] = 15.0f;  // V/velocity_env_cfg.py:212-217
+  c->push_vel_xy[0] = -0.5f; c->push_vel_xy[1] = 0.5f;
+  c->friction_range[0] = c->friction_range[1] = c->friction;
+  c->env_id_offset = 0;
+  c->env_spacing = 2.5f;
+  return 0;
+}

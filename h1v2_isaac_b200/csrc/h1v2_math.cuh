@@ -1,0 +1,173 @@
+// h1v2_math.cuh -- small fixed-size math used by the step kernel (device only, everything inlined/unrolled).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace h1v2 {
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  return mk3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ V3 fma3(V3 a, float s, V3 b) { return mk3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
+__device__ __forceinline__ V3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+struct M3 {  // columns
+  V3 cx, cy, cz;
+};
+__device__ __forceinline__ V3 mulv(const M3& R, V3 v) { return fma3(R.cx, v.x, fma3(R.cy, v.y, R.cz * v.z)); }
+__device__ __forceinline__ V3 mulTv(const M3& R, V3 v) { return mk3(dot(R.cx, v), dot(R.cy, v), dot(R.cz, v)); }
+__device__ __forceinline__ M3 quat2mat(float w, float x, float y, float z) {
+  M3 R;
+  R.cx = mk3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
+  R.cy = mk3(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
+  R.cz = mk3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+  return R;
+}
+// R <- R * Rot(axis, th), axis in {0:x, 1:y, 2:z}
+template <int AXIS>
+__device__ __forceinline__ void rotate(M3& R, float th) {
+  float s, c;
+  sincosf(th, &s, &c);
+  if (AXIS == 2) {
+    V3 X = fma3(R.cx, c, R.cy * s), Y = fma3(R.cy, c, R.cx * (-s));
+    R.cx = X; R.cy = Y;
+  } else if (AXIS == 1) {
+    V3 X = fma3(R.cx, c, R.cz * (-s)), Z = fma3(R.cz, c, R.cx * s);
+    R.cx = X; R.cz = Z;
+  } else {
+    V3 Y = fma3(R.cy, c, R.cz * s), Z = fma3(R.cz, c, R.cy * (-s));
+    R.cy = Y; R.cz = Z;
+  }
+}
+template <int AXIS>
+__device__ __forceinline__ V3 axis_col(const M3& R) { return AXIS == 0 ? R.cx : (AXIS == 1 ? R.cy : R.cz); }
+
+// rigid spatial inertia about the reference point O, world axes: mass, mass*com, rotational inertia about O
+struct RI {
+  float m;
+  V3 mc;
+  float xx, yy, zz, xy, xz, yz;
+};
+__device__ __forceinline__ RI operator+(const RI& a, const RI& b) {
+  RI r;
+  r.m = a.m + b.m; r.mc = a.mc + b.mc;
+  r.xx = a.xx + b.xx; r.yy = a.yy + b.yy; r.zz = a.zz + b.zz;
+  r.xy = a.xy + b.xy; r.xz = a.xz + b.xz; r.yz = a.yz + b.yz;
+  return r;
+}
+__device__ __forceinline__ V3 rot_inertia_mul(const RI& I, V3 w) {
+  return mk3(fmaf(I.xx, w.x, fmaf(I.xy, w.y, I.xz * w.z)), fmaf(I.xy, w.x, fmaf(I.yy, w.y, I.yz * w.z)),
+             fmaf(I.xz, w.x, fmaf(I.yz, w.y, I.zz * w.z)));
+}
+// (n,l) = I * (w,u)
+__device__ __forceinline__ void ri_apply(const RI& I, V3 w, V3 u, V3& n, V3& l) {
+  n = rot_inertia_mul(I, w) + cross(I.mc, u);
+  l = fma3(u, I.m, cross(w, I.mc));
+}
+// world inertia of a body: rotation R, COM c (relative to O), mass m, body-frame inertia ib = xx yy zz xy xz yz
+__device__ __forceinline__ RI body_inertia(const M3& R, V3 c, float m, const float* ib, float iscale) {
+  V3 t0 = mulv(R, mk3(ib[0], ib[3], ib[4])) * iscale;
+  V3 t1 = mulv(R, mk3(ib[3], ib[1], ib[5])) * iscale;
+  V3 t2 = mulv(R, mk3(ib[4], ib[5], ib[2])) * iscale;
+  RI I;
+  I.m = m;
+  I.mc = c * m;
+  float cc = dot(c, c);
+  // Iw(i,j) = sum_k t_k[i] * Rcol_k[j]
+  I.xx = fmaf(t0.x, R.cx.x, fmaf(t1.x, R.cy.x, t2.x * R.cz.x)) + m * (cc - c.x * c.x);
+  I.yy = fmaf(t0.y, R.cx.y, fmaf(t1.y, R.cy.y, t2.y * R.cz.y)) + m * (cc - c.y * c.y);
+  I.zz = fmaf(t0.z, R.cx.z, fmaf(t1.z, R.cy.z, t2.z * R.cz.z)) + m * (cc - c.z * c.z);
+  I.xy = fmaf(t0.x, R.cx.y, fmaf(t1.x, R.cy.y, t2.x * R.cz.y)) - m * c.x * c.y;
+  I.xz = fmaf(t0.x, R.cx.z, fmaf(t1.x, R.cy.z, t2.x * R.cz.z)) - m * c.x * c.z;
+  I.yz = fmaf(t0.y, R.cx.z, fmaf(t1.y, R.cy.z, t2.y * R.cz.z)) - m * c.y * c.z;
+  return I;
+}
+
+// packed lower-triangular index
+#define TI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// in-place Cholesky of a packed symmetric 6x6 (lower); invd = 1/diag(L)
+__device__ __forceinline__ void chol6(float (&A)[21], float (&invd)[6]) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    float d = A[TI(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d = fmaf(-A[TI(j, k)], A[TI(j, k)], d);
+    d = fmaxf(d, 1e-12f);
+    float r = rsqrtf(d);
+    invd[j] = r;
+    A[TI(j, j)] = d * r;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      float s = A[TI(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s = fmaf(-A[TI(i, k)], A[TI(j, k)], s);
+      A[TI(i, j)] = s * r;
+    }
+  }
+}
+__device__ __forceinline__ void fwd6(const float (&L)[21], const float (&invd)[6], float (&b)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = fmaf(-L[TI(i, k)], b[k], s);
+    b[i] = s * invd[i];
+  }
+}
+__device__ __forceinline__ void bwd6(const float (&L)[21], const float (&invd)[6], float (&b)[6]) {
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s = fmaf(-L[TI(k, i)], b[k], s);
+    b[i] = s * invd[i];
+  }
+}
+
+// ---------------- Philox4x32-10, same stream contract as the oracle (SURVEY 8(a) RNG note) ----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+#define STREAM_OBS 0u
+#define STREAM_RESET 1u
+#define STREAM_CMD 2u
+#define STREAM_EVENT 3u
+#define STREAM_ACTIONS 7u
+__device__ __forceinline__ void rng4(uint32_t key0, int64_t gid, unsigned long long step, uint32_t stream, uint32_t block,
+                                     float (&u)[4]) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), stream, block, key0, (uint32_t)gid, o);
+#pragma unroll
+  for (int i = 0; i < 4; i++) u[i] = (float)(o[i] >> 8) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float uni(float u, float lo, float hi) { return lo + (hi - lo) * u; }
+
+__device__ __forceinline__ float wrap_to_pi(float a) {
+  const float PI = 3.14159265358979323846f, TWO_PI = 2.0f * 3.14159265358979323846f;
+  float w = fmodf(a + PI, TWO_PI);
+  if (w < 0.f) w += TWO_PI;
+  if (w == 0.0f && a > 0.0f) return PI;
+  return w - PI;
+}
+
+}  // namespace h1v2

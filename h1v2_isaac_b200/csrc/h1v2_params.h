@@ -1,0 +1,96 @@
+// h1v2_params.h -- kernel-side parameter block (passed as a __grid_constant__ kernel argument) and the
+// internal HBM layout of the per-env state.  Host code (h1v2_capi.cu) fills both.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/h1v2_b200.h"
+
+#define H1V2_HIST_STRIDE 48  // floats per history slot (45 used; 192 B = 6 sectors)
+
+// --- rigid-body constants of one leg (MJCF order: hip_yaw, hip_pitch, hip_roll, knee, ankle_pitch, ankle_roll) ---
+struct KLeg {
+  float pos[6][3];      // body offset in the parent frame        (h12_12dof.xml:71,76,81,86,91,96 / :107..)
+  float ipos[6][3];     // COM in the body frame
+  float inertia[6][6];  // xx yy zz xy xz yz about the COM, body frame
+  float mass[6];
+  float foot_pt[4][3];  // sole corners in the ankle_roll frame
+  float shin_pt[2][3];  // shin capsule end centres in the knee_link frame
+  float shin_rad;
+};
+
+struct KParams {
+  KLeg leg[2];
+  float root_mass, root_ipos[3], root_inertia[6];
+  float root_pt[9][3];  // torso box corners 0..7, pelvis sphere centre 8
+  float root_rad[9];
+  // timing
+  float h;              // physics dt
+  int decimation;
+  float step_dt;
+  int64_t max_episode_length;
+  float max_episode_length_s;
+  // action / actuator
+  float action_scale;
+  float q0[12], kp[12], kd[12], effort[12], frc[12];
+  int perm[12];      // external -> MJCF
+  int inv_perm[12];  // MJCF -> external
+  int min_delay, max_delay;
+  // physics
+  float gravity;
+  float damping[18], armature[18];
+  float floss[18], floss_D[18], floss_lim[18], floss_B;  // lim = R*frictionloss
+  float range_lo[12], range_hi[12], limit_invw[12], limit_K, limit_B, limit_imp[5];
+  float contact_K, contact_B, contact_imp[5];
+  float slot_tran[6];
+  int max_iters;
+  float tol;  // on |grad| * scale
+  float grad_scale;
+  // observations
+  int H, obs_dim, corrupt;
+  float n_av, n_g, n_q, n_v;
+  float s_av, s_g, s_cmd, s_q, s_v, s_a;
+  // rewards
+  float w[H1V2_NUM_REW];
+  float inv_std2, air_thr, contact_thr, base_h;
+  float soft_lo[12], soft_hi[12];
+  uint32_t m_poslim, m_dev, m_tau, m_undesired, m_illegal;
+  // commands
+  float c_lx[2], c_ly[2], c_wz[2], c_hd[2], c_rt[2];
+  float rel_standing, rel_heading, k_heading;
+  int heading_cmd;
+  float max_command_step;
+  // events
+  float rp[6][2], rv[6][2], rjp[2], rjv[2], init_h;
+  int push_enable;
+  float push_int[2], push_v[2];
+  // rng
+  uint32_t key0;
+  int64_t env_id_offset;
+  int n;
+};
+
+// --- internal state, SoA of float4 so that every lane issues coalesced 128-bit accesses ---
+//   lane index l = 2*env + side (side 0 = left leg, 1 = right leg)
+struct KState {
+  float4* root;    // [4][N]   (px,py,pz,qw) (qx,qy,qz,vx) (vy,vz,wx,wy) (wz,friction,mass_add,push_left)
+  float4* leg;     // [3][2N]  (q0..q3) (q4,q5,qd0,qd1) (qd2..qd5)
+  float4* act;     // [5][2N]  last_action[6] | T1[6] | T2[6] | pad2   (MJCF order within the leg)
+  float4* cmd;     // [2][N]   (cx,cy,cz,heading_target) (time_left,err_xy,err_yaw,flags)
+  float4* timers;  // [2N]     cur_air,last_air,cur_contact,last_contact of the lane's foot
+  float4* epsum;   // [5][N]   episode sums of the 20 reward slots
+  float* hist;     // [N][H][48]
+  const int* lut;  // [obs_dim] (history index << 8) | offset in the 45-float sample, for the term-major flatten
+  int64_t* ep_len; // [N] bound, owned by the caller
+  float* diag;     // [N][H1V2_DIAG_DIM] or NULL
+  float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
+  float* log;      // [H1V2_LOG_DIM] published log vector
+  unsigned long long* counters;  // [0] global step counter, [1] history head
+};
+#define H1V2_DIAG_DIM 96
+// diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | reward_terms 60..79
+//              | foot_vel 80..85 | newton iters 86 | cap hit 87
+#define FLAG_DELAY_FRESH 1
+#define FLAG_HIST_FRESH 2
+#define FLAG_LAG_SHIFT 2
+#define FLAG_STANDING 32
+#define FLAG_HEADING 64

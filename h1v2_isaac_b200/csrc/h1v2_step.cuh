@@ -1,0 +1,521 @@
+// h1v2_step.cuh -- the fused control-step kernel: action -> 4 x (PD actuator + physics substep + contact sensor)
+// -> terminations -> rewards -> reset -> command -> observation, one launch, no host sync.
+// Step order follows packages/biped_tasks/biped_tasks/utils/cat/cat_env.py:95-193 (vendored ManagerBasedRLEnv.step).
+#pragma once
+#include "h1v2_physics.cuh"
+
+namespace h1v2 {
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+struct RootDerived {
+  M3 R;
+  V3 vb, wb, ww, g;
+  float heading;
+};
+__device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const float (&rv)[3], const float (&rw)[3]) {
+  RootDerived d;
+  d.R = quat2mat(rq[0], rq[1], rq[2], rq[3]);
+  d.vb = mulTv(d.R, mk3(rv[0], rv[1], rv[2]));
+  d.wb = mk3(rw[0], rw[1], rw[2]);
+  d.ww = mulv(d.R, d.wb);
+  d.g = mk3(-d.R.cx.z, -d.R.cy.z, -d.R.cz.z);  // R^T (0,0,-1)
+  d.heading = atan2f(d.R.cx.y, d.R.cx.x);
+  return d;
+}
+
+// world linear velocity of the ankle_roll_link origin of this lane's leg
+__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6]) {
+  M3 R = R0;
+  V3 x = mk3(0.f, 0.f, 0.f), om = om0, vo = v0;
+#define FV_JOINT(i, AX)                     \
+  {                                         \
+    x = x + mulv(R, ld3(LG.pos[i]));        \
+    V3 wi = axis_col<AX>(R);                \
+    om = fma3(wi, qd[i], om);               \
+    vo = fma3(cross(x, wi), qd[i], vo);     \
+    rotate<AX>(R, q[i]);                    \
+  }
+  FV_JOINT(0, 2) FV_JOINT(1, 1) FV_JOINT(2, 0) FV_JOINT(3, 1) FV_JOINT(4, 1) FV_JOINT(5, 0)
+#undef FV_JOINT
+  return vo + cross(om, x);
+}
+
+struct CmdState {
+  float c[3], heading_target, time_left, m_xy, m_yaw;
+  int flags;
+};
+__device__ __forceinline__ void resample_command(const KParams& P, CmdState& c, int64_t gid, unsigned long long step, uint32_t block0) {
+  float u[4], v[4];
+  rng4(P.key0, gid, step, STREAM_CMD, block0, u);
+  rng4(P.key0, gid, step, STREAM_CMD, block0 + 1, v);
+  c.time_left = uni(v[2], P.c_rt[0], P.c_rt[1]);
+  c.c[0] = uni(u[0], P.c_lx[0], P.c_lx[1]);
+  c.c[1] = uni(u[1], P.c_ly[0], P.c_ly[1]);
+  c.c[2] = uni(u[2], P.c_wz[0], P.c_wz[1]);
+  if (P.heading_cmd) {
+    c.heading_target = uni(u[3], P.c_hd[0], P.c_hd[1]);
+    c.flags = (c.flags & ~FLAG_HEADING) | (v[0] <= P.rel_heading ? FLAG_HEADING : 0);
+  }
+  c.flags = (c.flags & ~FLAG_STANDING) | (v[1] <= P.rel_standing ? FLAG_STANDING : 0);
+}
+
+// reset of one env (reset_root_state_uniform, reset_joints_by_scale, manager resets); both lanes compute the root
+__device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
+                                          float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
+                                          float (&la)[6], float (&T1)[6], float (&T2)[6], float4& timers, CmdState& cmd,
+                                          float& push_left) {
+  float u0[4], u1[4], u2[4], u3[4];
+  rng4(P.key0, gid, step, STREAM_RESET, 0, u0);
+  rng4(P.key0, gid, step, STREAM_RESET, 1, u1);
+  rng4(P.key0, gid, step, STREAM_RESET, 2, u2);
+  rng4(P.key0, gid, step, STREAM_RESET, 3, u3);
+  int lag = P.min_delay + (int)(u1[2] * (float)(P.max_delay - P.min_delay + 1));
+  lag = min(lag, P.max_delay);
+  cmd.flags = FLAG_DELAY_FRESH | FLAG_HIST_FRESH | (lag << FLAG_LAG_SHIFT);
+  timers = make_float4(0.f, 0.f, 0.f, 0.f);
+  rp[0] = uni(u0[0], P.rp[0][0], P.rp[0][1]);
+  rp[1] = uni(u0[1], P.rp[1][0], P.rp[1][1]);
+  rp[2] = P.init_h + uni(u0[3], P.rp[2][0], P.rp[2][1]);
+  float roll = uni(u1[0], P.rp[3][0], P.rp[3][1]), pitch = uni(u1[1], P.rp[4][0], P.rp[4][1]);
+  float yaw = uni(u0[2], P.rp[5][0], P.rp[5][1]);
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(0.5f * roll, &sr, &cr); sincosf(0.5f * pitch, &sp, &cp); sincosf(0.5f * yaw, &sy, &cy);
+  rq[0] = cy * cr * cp + sy * sr * sp;
+  rq[1] = cy * sr * cp - sy * cr * sp;
+  rq[2] = cy * cr * sp + sy * sr * cp;
+  rq[3] = sy * cr * cp - cy * sr * sp;
+  V3 vw = mk3(uni(u2[0], P.rv[0][0], P.rv[0][1]), uni(u2[1], P.rv[1][0], P.rv[1][1]), uni(u2[2], P.rv[2][0], P.rv[2][1]));
+  V3 ww = mk3(uni(u3[0], P.rv[3][0], P.rv[3][1]), uni(u3[1], P.rv[4][0], P.rv[4][1]), uni(u3[2], P.rv[5][0], P.rv[5][1]));
+  M3 R = quat2mat(rq[0], rq[1], rq[2], rq[3]);
+  V3 wb = mulTv(R, ww);
+  rv[0] = vw.x; rv[1] = vw.y; rv[2] = vw.z;
+  rw[0] = wb.x; rw[1] = wb.y; rw[2] = wb.z;
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    float uj[4];
+    rng4(P.key0, gid, step, STREAM_RESET, 4 + 3 * side + b, uj);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int k = 2 * b + e, j = 6 * side + k;
+      float spos = uni(uj[2 * e], P.rjp[0], P.rjp[1]);
+      float qq = P.q0[j] * spos;
+      q[k] = fminf(fmaxf(qq, P.soft_lo[j]), P.soft_hi[j]);
+      qd[k] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) la[k] = T1[k] = T2[k] = 0.f;
+  cmd.m_xy = cmd.m_yaw = 0.f;
+  resample_command(P, cmd, gid, step, 0);
+  if (P.push_enable) {
+    float up[4];
+    rng4(P.key0, gid, step, STREAM_EVENT, 1, up);
+    push_left = uni(up[0], P.push_int[0], P.push_int[1]);
+  }
+}
+
+// CommandTerm.compute(dt) of UniformVelocityCommand (V/velocity_env_cfg.py:90-104; T/utils/mdp/commands.py:47-59)
+__device__ __forceinline__ void update_command(const KParams& P, CmdState& c, const RootDerived& rd, int64_t gid,
+                                               unsigned long long step) {
+  float ex = c.c[0] - rd.vb.x, ey = c.c[1] - rd.vb.y;
+  c.m_xy += sqrtf(ex * ex + ey * ey) / P.max_command_step;
+  c.m_yaw += fabsf(c.c[2] - rd.wb.z) / P.max_command_step;
+  c.time_left -= P.step_dt;
+  if (c.time_left <= 0.0f) resample_command(P, c, gid, step, 2);
+  if (P.heading_cmd && (c.flags & FLAG_HEADING)) {
+    float err = wrap_to_pi(c.heading_target - rd.heading);
+    c.c[2] = fminf(fmaxf(P.k_heading * err, P.c_wz[0]), P.c_wz[1]);
+  }
+  if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
+}
+
+// observation sample of this step -> history ring slot `head`; then the warp cooperatively emits the flattened rows
+__device__ __forceinline__ void emit_observation(const KParams& P, const KState& S, int env, int side, bool valid, int64_t gid,
+                                                 unsigned long long step, int head, const RootDerived& rd, const CmdState& cmd,
+                                                 const float (&q)[6], const float (&qd)[6], const float (&la)[6], float* obs) {
+  const int H = P.H;
+  float* slot = S.hist + ((size_t)env * H + head) * H1V2_HIST_STRIDE;
+  float nq[6] = {0, 0, 0, 0, 0, 0}, nv[6] = {0, 0, 0, 0, 0, 0};
+  if (P.corrupt) {
+    float a[4], b[4], d[4];
+    rng4(P.key0, gid, step, STREAM_OBS, 2 + 4 * side, a);
+    rng4(P.key0, gid, step, STREAM_OBS, 3 + 4 * side, b);
+    rng4(P.key0, gid, step, STREAM_OBS, 4 + 4 * side, d);
+    nq[0] = a[0]; nq[1] = a[1]; nq[2] = a[2]; nq[3] = a[3]; nq[4] = b[0]; nq[5] = b[1];
+    nv[0] = b[2]; nv[1] = b[3]; nv[2] = d[0]; nv[3] = d[1]; nv[4] = d[2]; nv[5] = d[3];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { nq[k] = uni(nq[k], -P.n_q, P.n_q); nv[k] = uni(nv[k], -P.n_v, P.n_v); }
+  }
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int j = 6 * side + k, i = P.inv_perm[j];
+      slot[9 + i] = (q[k] - P.q0[j] + nq[k]) * P.s_q;
+      slot[21 + i] = (qd[k] + nv[k]) * P.s_v;
+      slot[33 + i] = la[k] * P.s_a;
+    }
+    if (side == 0) {
+      float n0[3] = {0, 0, 0}, n1[3] = {0, 0, 0};
+      if (P.corrupt) {
+        float b0[4], b1[4];
+        rng4(P.key0, gid, step, STREAM_OBS, 0, b0);
+        rng4(P.key0, gid, step, STREAM_OBS, 1, b1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { n0[i] = uni(b0[i], -P.n_av, P.n_av); n1[i] = uni(b1[i], -P.n_g, P.n_g); }
+      }
+      slot[0] = (rd.wb.x + n0[0]) * P.s_av; slot[1] = (rd.wb.y + n0[1]) * P.s_av; slot[2] = (rd.wb.z + n0[2]) * P.s_av;
+      slot[3] = (rd.g.x + n1[0]) * P.s_g; slot[4] = (rd.g.y + n1[1]) * P.s_g; slot[5] = (rd.g.z + n1[2]) * P.s_g;
+      slot[6] = cmd.c[0] * P.s_cmd; slot[7] = cmd.c[1] * P.s_cmd; slot[8] = cmd.c[2] * P.s_cmd;
+    }
+  }
+  __syncwarp();
+  // cooperative flatten: term-major, oldest -> newest inside each term block
+  // (packages/biped_tasks/biped_tasks/utils/history/observation_manager.py:335-355, circular_buffer.py:79-87,131-135)
+  const int lane = threadIdx.x & 31;
+  const int warp_env0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 1;
+  for (int e = 0; e < 16; e++) {
+    const int env_e = warp_env0 + e;
+    const int fl = __shfl_sync(0xffffffffu, cmd.flags, 2 * e);
+    if (env_e >= P.n) break;
+    const bool fresh = (fl & FLAG_HIST_FRESH) != 0;
+    float* hbase = S.hist + (size_t)env_e * H * H1V2_HIST_STRIDE;
+    for (int idx = lane; idx < P.obs_dim; idx += 32) {
+      const int hk = __ldg(S.lut + idx);
+      const int hh = hk >> 8, k = hk & 255;
+      int sl = head + 1 + hh;
+      sl = sl >= H ? sl - H : sl;
+      if (fresh) sl = head;
+      const float v = __ldcg(hbase + sl * H1V2_HIST_STRIDE + k);
+      if (obs) obs[(size_t)env_e * P.obs_dim + idx] = v;
+      if (fresh) hbase[hh * H1V2_HIST_STRIDE + k] = v;
+    }
+  }
+}
+
+template <bool DO_STEP>
+__global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
+                                                  float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
+                                                  uint8_t* __restrict__ trunc) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = gtid & 1;
+  const bool valid = (gtid >> 1) < P.n;
+  const int env = valid ? (gtid >> 1) : P.n - 1;
+  const int lidx = 2 * env + side;
+  const unsigned pm = 3u << (threadIdx.x & 30);
+  const int N = P.n, N2 = 2 * P.n;
+  const int64_t gid = P.env_id_offset + env;
+  const unsigned long long step = S.counters[0] + (DO_STEP ? 1ull : 0ull);
+  const int head = (int)((S.counters[1] + 1ull) % (unsigned long long)P.H);
+
+  // ---- load state (coalesced 128-bit) ----
+  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
+  float mu, mass_add, push_left;
+  CmdState cmd;
+  {
+    float4 r0 = S.root[env], r1 = S.root[N + env], r2 = S.root[2 * N + env], r3 = S.root[3 * N + env];
+    rp[0] = r0.x; rp[1] = r0.y; rp[2] = r0.z; rq[0] = r0.w; rq[1] = r1.x; rq[2] = r1.y; rq[3] = r1.z;
+    rv[0] = r1.w; rv[1] = r2.x; rv[2] = r2.y; rw[0] = r2.z; rw[1] = r2.w; rw[2] = r3.x;
+    mu = r3.y; mass_add = r3.z; push_left = r3.w;
+    float4 l0 = S.leg[lidx], l1 = S.leg[N2 + lidx], l2 = S.leg[2 * N2 + lidx];
+    q[0] = l0.x; q[1] = l0.y; q[2] = l0.z; q[3] = l0.w; q[4] = l1.x; q[5] = l1.y;
+    qd[0] = l1.z; qd[1] = l1.w; qd[2] = l2.x; qd[3] = l2.y; qd[4] = l2.z; qd[5] = l2.w;
+    float4 a0 = S.act[lidx], a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx], a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
+    la[0] = a0.x; la[1] = a0.y; la[2] = a0.z; la[3] = a0.w; la[4] = a1.x; la[5] = a1.y;
+    T1[0] = a1.z; T1[1] = a1.w; T1[2] = a2.x; T1[3] = a2.y; T1[4] = a2.z; T1[5] = a2.w;
+    T2[0] = a3.x; T2[1] = a3.y; T2[2] = a3.z; T2[3] = a3.w; T2[4] = a4.x; T2[5] = a4.y;
+    float4 c0 = S.cmd[env], c1 = S.cmd[N + env];
+    cmd.c[0] = c0.x; cmd.c[1] = c0.y; cmd.c[2] = c0.z; cmd.heading_target = c0.w;
+    cmd.time_left = c1.x; cmd.m_xy = c1.y; cmd.m_yaw = c1.z; cmd.flags = __float_as_int(c1.w);
+  }
+  float4 tm = S.timers[lidx];
+
+  if (DO_STEP) {
+    // ---- action manager: process_action (JointPositionAction, V/velocity_env_cfg.py:111) ----
+    float prev[6], T0[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int j = 6 * side + k;
+      prev[k] = la[k];
+      la[k] = actions[(size_t)env * 12 + P.inv_perm[j]];
+      T0[k] = fmaf(P.action_scale, la[k], P.q0[j]);
+    }
+    if (cmd.flags & FLAG_DELAY_FRESH) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) T1[k] = T2[k] = T0[k];
+    }
+    const int lag = (cmd.flags >> FLAG_LAG_SHIFT) & 7;
+    // ---- physics loop: DelayedPD actuator (A/robots/h12.py:58-113) + substep + ContactSensor at sim dt ----
+    float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
+    float tau[6];
+    SubOut so;
+    int max_it = 0, ncap = 0;
+#pragma unroll 1
+    for (int k = 0; k < P.decimation; k++) {
+      const int age = lag - k;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const int j = 6 * side + i;
+        float T = age <= 0 ? T0[i] : (age <= P.decimation ? T1[i] : T2[i]);
+        float t = P.kp[j] * (T - q[i]) + P.kd[j] * (0.f - qd[i]);
+        tau[i] = fminf(fmaxf(t, -P.effort[j]), P.effort[j]);
+      }
+      substep(P, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, so);
+      max_it = max(max_it, so.iters); ncap += so.capped;
+      float nf = sqrtf(dot(so.F_foot, so.F_foot));
+      h_foot[0] = h_foot[1]; h_foot[1] = h_foot[2]; h_foot[2] = nf;
+      h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = sqrtf(dot(so.F_shin, so.F_shin));
+      h_torso[0] = h_torso[1]; h_torso[1] = h_torso[2]; h_torso[2] = sqrtf(dot(so.F_torso, so.F_torso));
+      h_pelvis[0] = h_pelvis[1]; h_pelvis[1] = h_pelvis[2]; h_pelvis[2] = sqrtf(dot(so.F_pelvis, so.F_pelvis));
+      {  // air / contact timers of the lane's foot (ContactSensor)
+        const float el = P.h;
+        const bool is_c = nf > P.contact_thr;
+        const bool first_c = (tm.x > 0.f) && is_c, first_d = (tm.z > 0.f) && !is_c;
+        tm.y = first_c ? tm.x + el : tm.y;
+        tm.x = is_c ? 0.f : tm.x + el;
+        tm.w = first_d ? tm.z + el : tm.w;
+        tm.z = is_c ? tm.z + el : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { T2[k] = T1[k]; T1[k] = T0[k]; }
+    cmd.flags &= ~FLAG_DELAY_FRESH;
+
+    // ---- non-finite guard ----
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !isfinite(qd[k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !isfinite(rv[k]) || !isfinite(rw[k]);
+    bad |= !isfinite(rq[0]) || !isfinite(rq[1]) || !isfinite(rq[2]) || !isfinite(rq[3]);
+    bad = (__shfl_xor_sync(pm, (int)bad, 1) | (int)bad) != 0;
+
+    // ---- counters and terminations (C12/rough_env_cfg.py:95-109) ----
+    int64_t ep_len = S.ep_len[env] + 1;
+    const bool time_out = ep_len >= P.max_episode_length;
+    const float C_foot = fmaxf(h_foot[0], fmaxf(h_foot[1], h_foot[2]));
+    const float C_shin = fmaxf(h_shin[0], fmaxf(h_shin[1], h_shin[2]));
+    const float C_torso = fmaxf(h_torso[0], fmaxf(h_torso[1], h_torso[2]));
+    const float C_pelvis = fmaxf(h_pelvis[0], fmaxf(h_pelvis[1], h_pelvis[2]));
+    int contact = (((P.m_illegal >> side) & 1u) && C_foot > P.contact_thr) || (((P.m_illegal >> (2 + side)) & 1u) && C_shin > P.contact_thr) ||
+                  (((P.m_illegal >> 4) & 1u) && C_torso > P.contact_thr) || (((P.m_illegal >> 5) & 1u) && C_pelvis > P.contact_thr);
+    contact = (__shfl_xor_sync(pm, contact, 1) | contact) | (int)bad;
+    const bool reset = contact || time_out;
+
+    // ---- rewards on the pre-reset state ----
+    const RootDerived rd = root_derived(rq, rv, rw);
+    const V3 fv = foot_velocity(P.leg[side], rd.R, rd.ww, mk3(rv[0], rv[1], rv[2]), q, qd);
+    float r[H1V2_NUM_REW];
+#pragma unroll
+    for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;
+    {
+      float s_lim = 0.f, s_dev = 0.f, s_tau = 0.f, s_acc = 0.f, s_vel = 0.f, s_da = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int j = 6 * side + k;
+        if ((P.m_poslim >> j) & 1u) s_lim += -fminf(q[k] - P.soft_lo[j], 0.f) + fmaxf(q[k] - P.soft_hi[j], 0.f);
+        if ((P.m_dev >> j) & 1u) s_dev += fabsf(q[k] - P.q0[j]);
+        if ((P.m_tau >> j) & 1u) s_tau = fmaf(tau[k], tau[k], s_tau);
+        s_acc = fmaf(so.qacc[k], so.qacc[k], s_acc);
+        s_vel = fmaf(qd[k], qd[k], s_vel);
+        float da = la[k] - prev[k];
+        s_da = fmaf(da, da, s_da);
+      }
+      r[H1V2_REW_DOF_POS_LIMITS] = pair_sum(s_lim, pm);
+      r[H1V2_REW_JOINT_DEV_HIP] = pair_sum(s_dev, pm);
+      r[H1V2_REW_TORQUES] = pair_sum(s_tau, pm);
+      r[H1V2_REW_DOF_ACC] = pair_sum(s_acc, pm);
+      r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel, pm);
+      r[H1V2_REW_ACTION_RATE] = pair_sum(s_da, pm);
+      r[H1V2_REW_TERMINATION] = contact ? 1.f : 0.f;
+      const float ch = cosf(rd.heading), sh = sinf(rd.heading);
+      float ex = cmd.c[0] - (ch * rv[0] + sh * rv[1]), ey = cmd.c[1] - (-sh * rv[0] + ch * rv[1]);
+      r[H1V2_REW_TRACK_LIN_XY_YAW] = expf(-(ex * ex + ey * ey) * P.inv_std2);
+      float ez = cmd.c[2] - rd.ww.z;
+      r[H1V2_REW_TRACK_ANG_Z_WORLD] = expf(-(ez * ez) * P.inv_std2);
+      ex = cmd.c[0] - rd.vb.x; ey = cmd.c[1] - rd.vb.y;
+      r[H1V2_REW_TRACK_LIN_XY_BASE] = expf(-(ex * ex + ey * ey) * P.inv_std2);
+      ez = cmd.c[2] - rd.wb.z;
+      r[H1V2_REW_TRACK_ANG_Z_BASE] = expf(-(ez * ez) * P.inv_std2);
+      const bool moving = sqrtf(cmd.c[0] * cmd.c[0] + cmd.c[1] * cmd.c[1]) > 0.1f;
+      // feet_air_time_positive_biped (V/mdp/rewards.py:38-62) and feet_air_time (:13-35)
+      const int inc = tm.z > 0.f;
+      const float mode_t = inc ? tm.z : tm.x;
+      const int inc_p = __shfl_xor_sync(pm, inc, 1);
+      const float mode_p = __shfl_xor_sync(pm, mode_t, 1);
+      const bool single = (inc + inc_p) == 1;
+      float mn = fminf(single ? mode_t : 0.f, single ? mode_p : 0.f);
+      mn = fminf(mn, P.air_thr);
+      r[H1V2_REW_FEET_AIR_BIPED] = moving ? mn : 0.f;
+      const bool first = (tm.z > 0.f) && (tm.z < P.step_dt + 1e-8f);
+      float l2 = first ? (tm.y - P.air_thr) : 0.f;
+      l2 = pair_sum(l2, pm);
+      r[H1V2_REW_FEET_AIR_L2] = moving ? l2 : 0.f;
+      float slide = (C_foot > P.contact_thr) ? sqrtf(fv.x * fv.x + fv.y * fv.y) : 0.f;
+      r[H1V2_REW_FEET_SLIDE] = pair_sum(slide, pm);
+      r[H1V2_REW_ANG_VEL_XY] = rd.wb.x * rd.wb.x + rd.wb.y * rd.wb.y;
+      r[H1V2_REW_FLAT_ORI] = rd.g.x * rd.g.x + rd.g.y * rd.g.y;
+      r[H1V2_REW_LIN_VEL_Z] = rd.vb.z * rd.vb.z;
+      r[H1V2_REW_BASE_HEIGHT] = (rp[2] - P.base_h) * (rp[2] - P.base_h);
+      float und = 0.f, cf = 0.f;
+      if ((P.m_undesired >> side) & 1u) { und += C_foot > P.contact_thr; cf += fmaxf(C_foot - P.contact_thr, 0.f); }
+      if ((P.m_undesired >> (2 + side)) & 1u) { und += C_shin > P.contact_thr; cf += fmaxf(C_shin - P.contact_thr, 0.f); }
+      if (side == 0) {
+        if ((P.m_undesired >> 4) & 1u) { und += C_torso > P.contact_thr; cf += fmaxf(C_torso - P.contact_thr, 0.f); }
+        if ((P.m_undesired >> 5) & 1u) { und += C_pelvis > P.contact_thr; cf += fmaxf(C_pelvis - P.contact_thr, 0.f); }
+      }
+      r[H1V2_REW_UNDESIRED_CONTACTS] = pair_sum(und, pm);
+      r[H1V2_REW_CONTACT_FORCES] = pair_sum(cf, pm);
+    }
+    float total = 0.f;
+#pragma unroll
+    for (int t = 0; t < H1V2_NUM_REW; t++) {
+      float v = (P.w[t] == 0.f || bad) ? 0.f : P.w[t] * r[t] * P.step_dt;
+      r[t] = v;
+      total += v;
+    }
+    // episode sums: lane 0 owns float4 0..2 (terms 0..11), lane 1 owns float4 3..4 (terms 12..19)
+    float es[12];
+    const int ef0 = side == 0 ? 0 : 3, enf4 = side == 0 ? 3 : 2;
+    {
+      float rsel[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) rsel[i] = side == 0 ? r[i] : (i < 8 ? r[12 + (i & 7)] : 0.f);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < enf4) e4 = S.epsum[(size_t)(ef0 + i) * N + env];
+        es[4 * i + 0] = e4.x + rsel[4 * i + 0]; es[4 * i + 1] = e4.y + rsel[4 * i + 1];
+        es[4 * i + 2] = e4.z + rsel[4 * i + 2]; es[4 * i + 3] = e4.w + rsel[4 * i + 3];
+      }
+    }
+    if (valid && side == 0) {
+      rew[env] = total;
+      term[env] = (uint8_t)(contact != 0);
+      trunc[env] = (uint8_t)time_out;
+    }
+    if (S.diag && valid) {
+      float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
+      dg[3 * side + 0] = so.F_foot.x; dg[3 * side + 1] = so.F_foot.y; dg[3 * side + 2] = so.F_foot.z;
+      dg[6 + 3 * side + 0] = so.F_shin.x; dg[6 + 3 * side + 1] = so.F_shin.y; dg[6 + 3 * side + 2] = so.F_shin.z;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { dg[18 + 3 * side + i] = h_foot[i]; dg[24 + 3 * side + i] = h_shin[i]; }
+#pragma unroll
+      for (int k = 0; k < 6; k++) { dg[36 + 6 * side + k] = tau[k]; dg[48 + 6 * side + k] = so.qacc[k]; }
+      dg[80 + 3 * side + 0] = fv.x; dg[80 + 3 * side + 1] = fv.y; dg[80 + 3 * side + 2] = fv.z;
+      if (side == 0) {
+        dg[12] = so.F_torso.x; dg[13] = so.F_torso.y; dg[14] = so.F_torso.z;
+        dg[15] = so.F_pelvis.x; dg[16] = so.F_pelvis.y; dg[17] = so.F_pelvis.z;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { dg[30 + i] = h_torso[i]; dg[33 + i] = h_pelvis[i]; }
+#pragma unroll
+        for (int t = 0; t < H1V2_NUM_REW; t++) dg[60 + t] = r[t];
+        dg[86] = (float)max_it; dg[87] = (float)ncap;
+      }
+    }
+    // solver statistics
+    {
+      int wm = __reduce_max_sync(0xffffffffu, valid ? max_it : 0);
+      int wc = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? ncap : 0);
+      if ((threadIdx.x & 31) == 0) {
+        atomicMax((int*)(S.acc + H1V2_LOG_MAX_ITERS), wm);
+        if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (float)wc);
+      }
+    }
+    // ---- reset (T/utils/cat/cat_env.py:195-248): log, then new state ----
+    if (reset) {
+      if (valid) {
+        const float inv = 1.f / P.max_episode_length_s;
+        const int f0 = side == 0 ? 0 : 12, cnt = side == 0 ? 12 : 8;
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+          if (i < cnt) atomicAdd(S.acc + H1V2_LOG_REW0 + f0 + i, es[i] * inv);
+        if (side == 0) {
+          atomicAdd(S.acc + H1V2_LOG_COUNT, 1.f);
+          if (time_out) atomicAdd(S.acc + H1V2_LOG_TERM_TIMEOUT, 1.f);
+          if (contact) atomicAdd(S.acc + H1V2_LOG_TERM_CONTACT, 1.f);
+          atomicAdd(S.acc + H1V2_LOG_ERR_XY, cmd.m_xy);
+          atomicAdd(S.acc + H1V2_LOG_ERR_YAW, cmd.m_yaw);
+          if (bad) atomicAdd(S.acc + H1V2_LOG_NAN_RESETS, 1.f);
+        }
+      }
+      reset_env(P, side, gid, step, rp, rq, rv, rw, q, qd, la, T1, T2, tm, cmd, push_left);
+#pragma unroll
+      for (int i = 0; i < 12; i++) es[i] = 0.f;
+      ep_len = 0;
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (i < enf4) S.epsum[(size_t)(ef0 + i) * N + env] = make_float4(es[4 * i], es[4 * i + 1], es[4 * i + 2], es[4 * i + 3]);
+      if (side == 0) S.ep_len[env] = ep_len;
+    }
+  }
+
+  // ---- command manager, interval events, observation (on the post-reset state) ----
+  RootDerived rd = root_derived(rq, rv, rw);
+  if (DO_STEP) {
+    update_command(P, cmd, rd, gid, step);
+    if (P.push_enable) {  // push_by_setting_velocity (V/velocity_env_cfg.py:212-217)
+      push_left -= P.step_dt;
+      if (push_left < 1e-6f) {
+        float u[4];
+        rng4(P.key0, gid, step, STREAM_EVENT, 2, u);
+        push_left = uni(u[2], P.push_int[0], P.push_int[1]);
+        rv[0] += uni(u[0], P.push_v[0], P.push_v[1]);
+        rv[1] += uni(u[1], P.push_v[0], P.push_v[1]);
+        rd = root_derived(rq, rv, rw);
+      }
+    }
+  }
+  emit_observation(P, S, env, side, valid, gid, step, head, rd, cmd, q, qd, la, obs);
+  cmd.flags &= ~FLAG_HIST_FRESH;
+
+  // ---- store state ----
+  if (valid) {
+    if (side == 0) {
+      S.root[env] = make_float4(rp[0], rp[1], rp[2], rq[0]);
+      S.root[N + env] = make_float4(rq[1], rq[2], rq[3], rv[0]);
+      S.root[2 * N + env] = make_float4(rv[1], rv[2], rw[0], rw[1]);
+      S.root[3 * N + env] = make_float4(rw[2], mu, mass_add, push_left);
+      S.cmd[env] = make_float4(cmd.c[0], cmd.c[1], cmd.c[2], cmd.heading_target);
+      S.cmd[N + env] = make_float4(cmd.time_left, cmd.m_xy, cmd.m_yaw, __int_as_float(cmd.flags));
+    }
+    S.leg[lidx] = make_float4(q[0], q[1], q[2], q[3]);
+    S.leg[N2 + lidx] = make_float4(q[4], q[5], qd[0], qd[1]);
+    S.leg[2 * N2 + lidx] = make_float4(qd[2], qd[3], qd[4], qd[5]);
+    S.act[lidx] = make_float4(la[0], la[1], la[2], la[3]);
+    S.act[N2 + lidx] = make_float4(la[4], la[5], T1[0], T1[1]);
+    S.act[2 * N2 + lidx] = make_float4(T1[2], T1[3], T1[4], T1[5]);
+    S.act[3 * N2 + lidx] = make_float4(T2[0], T2[1], T2[2], T2[3]);
+    S.act[4 * N2 + lidx] = make_float4(T2[4], T2[5], 0.f, 0.f);
+    S.timers[lidx] = tm;
+  }
+}
+
+// publishes the log vector, clears the accumulators, advances the step counter and the history head
+__global__ void finalize_kernel(const KState S, int do_step) {
+  const int t = threadIdx.x;
+  if (do_step) {
+    const float cnt = S.acc[H1V2_LOG_COUNT];
+    if (t < H1V2_LOG_DIM) {
+      float a = S.acc[t];
+      if (t == H1V2_LOG_COUNT) S.log[t] = a;
+      else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
+      else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
+      else if (t == H1V2_LOG_CAP_HITS) S.log[t] = a;
+      else if (cnt > 0.f) {
+        const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
+        S.log[t] = mean ? a / cnt : a;
+      }
+    }
+    __syncthreads();
+    if (t < H1V2_LOG_DIM) S.acc[t] = 0.f;
+  }
+  if (t == 0) {
+    if (do_step) S.counters[0] += 1ull;
+    S.counters[1] += 1ull;
+  }
+}
+
+}  // namespace h1v2

@@ -1,0 +1,223 @@
+/*
+ * h1v2_b200.h -- C-ABI of the B200-native batched simulation backend for the Unitree H1-2
+ * velocity-tracking task  Isaac-Velocity-Flat-H12_12dof-v0.
+ *
+ * The reference (olivier-stasse/h1v2-Isaac) has no FFI of its own: its seam is the Python
+ * ManagerBasedRLEnv.step contract.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root):
+ *
+ *   h1v2_create        <- gym.make(task, cfg=env_cfg)            scripts/rsl_rl/train.py:102
+ *                         -> ManagerBasedRLEnv.__init__ / load_managers
+ *                            packages/biped_tasks/biped_tasks/utils/cat/cat_env.py:31-93
+ *   h1v2_default_config<- resolved cfg of the Flat id
+ *                            .../velocity/config/h12_12dof/flat_env_cfg.py:13-48,
+ *                            .../velocity/config/h12_12dof/rough_env_cfg.py:18-125,
+ *                            .../velocity/velocity_env_cfg.py:86-324,
+ *                            packages/biped_assets/biped_assets/robots/h12.py:18-114
+ *   h1v2_step          <- ManagerBasedRLEnv.step(action)         utils/cat/cat_env.py:95-193
+ *   h1v2_step_host     <- same call with HOST buffers (what a non-torch caller binds; used for e2e timing)
+ *   h1v2_reset         <- ManagerBasedRLEnv.reset / _reset_idx   utils/cat/cat_env.py:195-248
+ *   h1v2_get_state /
+ *   h1v2_set_state     <- robot.data.* reads, write_root_*_to_sim / write_joint_state_to_sim (upstream
+ *                         isaaclab; needed for identical-state parity tests)
+ *   h1v2_get_log       <- extras["log"] filled in _reset_idx     utils/cat/cat_env.py:217-245
+ *   h1v2_bind_episode_length <- env.episode_length_buf (assignable LongTensor; train.py:141
+ *                         learn(init_at_random_ep_len=True))
+ *
+ * Conventions: plain pointers and sizes only; every device pointer is borrowed for the duration of the
+ * call; persistent state is owned by the handle; calls enqueue work on the given CUDA stream and never
+ * synchronise (except *_host and get_log_host, which must); return 0 on success, negative on error with a
+ * thread-local message from h1v2_last_error().  One handle per process per GPU.
+ */
+#ifndef H1V2_B200_H
+#define H1V2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H1V2_NJ 12           /* actuated joints */
+#define H1V2_NUM_REW 20      /* reward-term slots (union of the cfgs) */
+#define H1V2_NUM_SLOT 6      /* contact-sensor bodies: 0,1 feet L/R; 2,3 knee_link L/R; 4 torso_link; 5 pelvis */
+#define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
+#define H1V2_MAX_HISTORY 16
+#define H1V2_LOG_DIM 32      /* see h1v2_get_log */
+
+/* reward term slots; weights[i]==0 means "term not in the cfg" (RewardManager skips zero weights) */
+enum {
+  H1V2_REW_TERMINATION = 0,        /* is_terminated                               rough_env_cfg.py:22 */
+  H1V2_REW_TRACK_LIN_XY_YAW = 1,   /* track_lin_vel_xy_yaw_frame_exp              rough_env_cfg.py:24-28 */
+  H1V2_REW_TRACK_ANG_Z_WORLD = 2,  /* track_ang_vel_z_world_exp                   rough_env_cfg.py:29-33 */
+  H1V2_REW_FEET_AIR_BIPED = 3,     /* feet_air_time_positive_biped                mdp/rewards.py:38-62 */
+  H1V2_REW_FEET_SLIDE = 4,         /* feet_slide                                  rough_env_cfg.py:43-50 */
+  H1V2_REW_DOF_POS_LIMITS = 5,     /* joint_pos_limits (ankles)                   rough_env_cfg.py:52-56 */
+  H1V2_REW_JOINT_DEV_HIP = 6,      /* joint_deviation_l1 (hip yaw+roll)           rough_env_cfg.py:58-62 */
+  H1V2_REW_ANG_VEL_XY = 7,         /* ang_vel_xy_l2                               velocity_env_cfg.py:238 */
+  H1V2_REW_TORQUES = 8,            /* joint_torques_l2                            velocity_env_cfg.py:239 */
+  H1V2_REW_DOF_ACC = 9,            /* joint_acc_l2                                velocity_env_cfg.py:240 */
+  H1V2_REW_ACTION_RATE = 10,       /* action_rate_l2                              velocity_env_cfg.py:241 */
+  H1V2_REW_FLAT_ORI = 11,          /* flat_orientation_l2                         velocity_env_cfg.py:256 */
+  H1V2_REW_LIN_VEL_Z = 12,         /* lin_vel_z_l2                                velocity_env_cfg.py:237 */
+  H1V2_REW_UNDESIRED_CONTACTS = 13,/* undesired_contacts (knee links)             velocity_env_cfg.py:251-255 */
+  H1V2_REW_TRACK_LIN_XY_BASE = 14, /* track_lin_vel_xy_exp (base frame)           velocity_env_cfg.py:226-230 */
+  H1V2_REW_TRACK_ANG_Z_BASE = 15,  /* track_ang_vel_z_exp (base frame)            velocity_env_cfg.py:231-235 */
+  H1V2_REW_FEET_AIR_L2 = 16,       /* feet_air_time                               mdp/rewards.py:13-35 */
+  H1V2_REW_JOINT_VEL = 17,         /* joint_vel_l2        (Rsl variant)           rsl_env_cfg.py */
+  H1V2_REW_BASE_HEIGHT = 18,       /* base_height_l2      (Rsl variant)           rsl_env_cfg.py */
+  H1V2_REW_CONTACT_FORCES = 19     /* contact_forces      (Rsl variant)           rsl_env_cfg.py */
+};
+
+/* layout of the log vector returned by h1v2_get_log (all float):
+ *   [0]                 number of envs reset in the last step that reset anything (count)
+ *   [1 .. NUM_REW]      Episode_Reward/<term>   = mean over reset envs of episode_sum / max_episode_length_s
+ *   [21], [22]          Episode_Termination/time_out, /base_contact  (counts, as upstream's count_nonzero)
+ *   [23], [24]          Metrics/base_velocity/error_vel_xy, error_vel_yaw (mean over reset envs)
+ *   [25]                number of envs force-reset by the non-finite-state guard (cumulative)
+ *   [26]                max Newton iterations used by any env in the last step
+ *   [27]                number of (env,substep) solves that hit the iteration cap in the last step
+ */
+#define H1V2_LOG_COUNT 0
+#define H1V2_LOG_REW0 1
+#define H1V2_LOG_TERM_TIMEOUT 21
+#define H1V2_LOG_TERM_CONTACT 22
+#define H1V2_LOG_ERR_XY 23
+#define H1V2_LOG_ERR_YAW 24
+#define H1V2_LOG_NAN_RESETS 25
+#define H1V2_LOG_MAX_ITERS 26
+#define H1V2_LOG_CAP_HITS 27
+
+typedef struct H1v2Config {
+  /* ---- timing (velocity_env_cfg.py:302-305) ---- */
+  float sim_dt;            /* 0.005 */
+  int32_t decimation;      /* 4 */
+  float episode_length_s;  /* 20 -> max_episode_length = ceil(20/0.02) = 1000 */
+  /* ---- action: JointPositionAction (velocity_env_cfg.py:111) ---- */
+  float action_scale;                  /* 0.5 */
+  float default_joint_pos[H1V2_NJ];    /* MJCF (leg-major) order; h12.py:38-53 */
+  int32_t joint_perm[H1V2_NJ];         /* external joint i  ->  MJCF index joint_perm[i] */
+  /* ---- actuator: DelayedPDActuatorCfg (h12.py:58-113), MJCF order ---- */
+  float kp[H1V2_NJ], kd[H1V2_NJ], effort_limit[H1V2_NJ];
+  int32_t min_delay, max_delay;        /* physics steps, 0..5 */
+  /* ---- physics model (MuJoCo semantics of h12_12dof.xml) ---- */
+  float gravity;                       /* 9.81 */
+  float friction;                      /* tangential Coulomb coefficient of every robot-floor contact */
+  float dof_damping[18], dof_armature[18], dof_frictionloss[18];
+  float act_frc_limit[H1V2_NJ];        /* joint actuatorfrcrange */
+  float joint_range[H1V2_NJ][2];
+  float contact_solref[2];             /* (timeconst, dampratio) after geom mixing */
+  float contact_solimp[5];
+  float floss_solref[2], floss_solimp[5];
+  float limit_solref[2], limit_solimp[5];
+  int32_t solver_iterations;           /* Newton iteration cap */
+  float solver_tolerance;              /* on scaled gradient norm */
+  /* ---- observations (velocity_env_cfg.py:123-142, flat_env_cfg.py:25-27) ---- */
+  int32_t history_length;              /* 10 */
+  int32_t enable_corruption;           /* 1 */
+  float noise_ang_vel, noise_gravity, noise_joint_pos, noise_joint_vel; /* half-widths of Unoise */
+  float scale_ang_vel, scale_gravity, scale_cmd, scale_joint_pos, scale_joint_vel, scale_action; /* 1 */
+  /* ---- rewards ---- */
+  float rew_weight[H1V2_NUM_REW];
+  float track_std;                     /* 0.5 */
+  float feet_air_threshold;            /* 0.4 */
+  float contact_threshold;             /* 1.0 N, ContactSensor force_threshold and term thresholds */
+  float soft_limit_factor;             /* 0.9 */
+  float base_height_target;
+  uint32_t mask_pos_limits, mask_joint_dev, mask_torques; /* bit j = MJCF joint j */
+  uint32_t mask_undesired_slots;       /* bit s = sensor slot s */
+  /* ---- terminations (rough_env_cfg.py:95-109) ---- */
+  uint32_t mask_illegal_slots;
+  /* ---- commands (velocity_env_cfg.py:90-104, flat_env_cfg.py:46-48) ---- */
+  float cmd_lin_x[2], cmd_lin_y[2], cmd_ang_z[2], cmd_heading[2];
+  float cmd_resample_time[2];
+  float rel_standing_envs, rel_heading_envs, heading_stiffness;
+  int32_t heading_command;
+  /* ---- events ---- */
+  float reset_pose_range[6][2];        /* x y z roll pitch yaw (rough_env_cfg.py:80-92) */
+  float reset_vel_range[6][2];
+  float reset_joint_pos_scale[2], reset_joint_vel_scale[2];
+  float init_root_height;              /* 1.05 */
+  int32_t push_enable;                 /* interval event push_by_setting_velocity (velocity_env_cfg.py:212-217) */
+  float push_interval_s[2], push_vel_xy[2];
+  float mass_add_range[2];             /* startup randomize_rigid_body_mass on the base (kg) */
+  float friction_range[2];             /* startup per-env friction; lo==hi -> constant */
+  /* ---- sharding ---- */
+  int64_t env_id_offset;               /* global id of local env 0 (rank * n_envs) for the Philox key */
+  float env_spacing;                   /* 2.5 m grid (velocity_env_cfg.py:288) */
+  int32_t reserved[8];
+} H1v2Config;
+
+/* Natural-layout state exchange (row-major, env-major).  NULL members are skipped.
+ * Joint-indexed arrays are in MJCF order.  Device pointers for the product, host pointers for the oracle. */
+typedef struct H1v2State {
+  float* root_pos;      /* [N,3] relative to the env origin */
+  float* root_quat;     /* [N,4] w,x,y,z */
+  float* root_lin_vel;  /* [N,3] world frame, of the pelvis origin */
+  float* root_ang_vel;  /* [N,3] body frame */
+  float* joint_pos;     /* [N,12] */
+  float* joint_vel;     /* [N,12] */
+  float* last_action;   /* [N,12] external order, as passed to step */
+  float* target_hist;   /* [N,2,12] processed joint targets of the previous two control steps */
+  int32_t* lag;         /* [N] actuator delay in physics steps */
+  int32_t* fresh;       /* [N] 1 = no step since reset (delay line and obs history will back-fill) */
+  float* command;       /* [N,3] */
+  float* heading_target;/* [N] */
+  float* time_left;     /* [N] */
+  int32_t* is_standing; /* [N] */
+  int32_t* is_heading;  /* [N] */
+  float* cmd_metrics;   /* [N,2] */
+  float* feet_timers;   /* [N,2,4] cur_air,last_air,cur_contact,last_contact */
+  float* episode_sums;  /* [N,NUM_REW] */
+  float* obs_history;   /* [N,H,45] oldest -> newest */
+  float* friction;      /* [N] */
+  float* mass_add;      /* [N] */
+  float* push_time_left;/* [N] */
+  /* read-only diagnostics of the last step (get only) */
+  float* slot_force;    /* [N,NUM_SLOT,3] net contact force of the last substep, world */
+  float* slot_force_hist; /* [N,NUM_SLOT,3] |F| of the last three substeps, oldest -> newest */
+  float* applied_torque;/* [N,12] last substep, after the effort-limit clip */
+  float* joint_acc;     /* [N,12] last substep */
+  float* reward_terms;  /* [N,NUM_REW] weighted*dt value of every term in the last step */
+  float* foot_vel;      /* [N,2,3] world linear velocity of the ankle_roll_link origins */
+} H1v2State;
+
+typedef struct H1v2Handle H1v2Handle;
+
+int h1v2_default_config(H1v2Config* cfg);
+int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t seed, H1v2Handle** out);
+void h1v2_destroy(H1v2Handle* h);
+const char* h1v2_last_error(void);
+int h1v2_obs_dim(const H1v2Handle* h);
+int h1v2_num_envs(const H1v2Handle* h);
+
+/* episode_length_buf: int64[N] device buffer owned by the caller, read and written by every step */
+int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length);
+
+/* Reset envs.  env_ids == NULL resets all.  No observation is produced (use h1v2_observe). */
+int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stream);
+/* Compute observations for the current state WITHOUT stepping (ManagerBasedRLEnv.reset's obs);
+ * appends to the history exactly like observation_manager.compute(). */
+int h1v2_observe(H1v2Handle* h, float* obs, void* cuda_stream);
+
+/* One control step (decimation physics substeps + managers).  All pointers are device pointers. */
+int h1v2_step(H1v2Handle* h, const float* actions /*[N,12]*/, float* obs /*[N,obs_dim]*/, float* rew /*[N]*/,
+              uint8_t* terminated /*[N]*/, uint8_t* truncated /*[N]*/, void* cuda_stream);
+/* Same with HOST buffers (pinned or pageable): H2D of actions and D2H of all outputs inside, synchronises. */
+int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
+                   uint8_t* truncated);
+
+int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
+int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);
+/* device pointer to the float[H1V2_LOG_DIM] log vector (valid for the handle's lifetime, updated by step) */
+int h1v2_get_log(H1v2Handle* h, const float** log_dev);
+int h1v2_get_log_host(H1v2Handle* h, float* log_host /*[H1V2_LOG_DIM]*/);
+/* number of kernels launched by this handle since creation (for bench.py's gpu_launches) */
+int64_t h1v2_launch_count(const H1v2Handle* h);
+/* fill actions[N,12] with N(0,1) draws: Philox(seed, stream 7), counter = step */
+int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
