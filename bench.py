@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the fused control step (physics + obs + reward + termination + reset), B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line on rank 0.
+  * ours:      one H1v2Sim per rank (envs shard with no data-path collective -> "scaling": "weak"), K timed control
+               steps on synthetic N(0,1) actions resident in HBM, per-step CUDA events, L2 flushed between steps,
+               max over ranks.  `e2e` is the same metric through h1v2_step_host (HOST buffers, copies inside).
+  * reference: the reference's CPU path restated (oracle/h1v2_oracle.c, float64, MuJoCo-semantics physics at the Isaac
+               timing 5 ms x 4) on all host cores; a bounded sample of the same workload per step.
+Workload = BASELINE.json configs[1]: Isaac-Velocity-Flat-H12_12dof-v0 step, 4096 envs, random actions (--envs overrides).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec"
+# algorithmic HBM bytes per env-step of the fused kernel: action 48, root r+w 128, leg 192,
+# actuator line 320, command 64, timers 64, warm start 192, episode sums 160, episode length 16,
+# history read 9x180=1620 + write 180, obs write 1800, reward+flags 6
+ALGO_BYTES_PER_ENV_STEP = 4790
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1] = 4096; configs[3] = 32768)")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(cfg, seed: int, target_s: float = 12.0, steps: int | None = None, warmup: int = 2):
+    """Time the CPU restatement of the reference path on all host cores; bounded sample of the same workload."""
+    import numpy as np
+    from oracle.oracle import Oracle
+
+    cores = os.cpu_count() or 1
+    n = 64 * cores
+    orc = Oracle(cfg, n, seed=seed, threads=cores)
+    orc.observe()
+    rng = np.random.default_rng(0)
+    acts = [rng.normal(size=(n, 12)).astype(np.float32) for _ in range(4)]
+    for i in range(warmup):
+        orc.step(acts[i % 4])
+    t0 = time.perf_counter()
+    orc.step(acts[0])
+    one = time.perf_counter() - t0
+    k = steps if steps is not None else max(3, int(target_s / max(one, 1e-6)))
+    t0 = time.perf_counter()
+    for i in range(k):
+        orc.step(acts[i % 4])
+    dt = time.perf_counter() - t0
+    return {"value": n * k / dt, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"{n} envs x {k} control steps (4 x 5 ms MuJoCo-semantics substeps + managers), float64 C oracle, {cores} pthreads",
+            "ms_per_step": dt / k * 1e3, "n_envs": n, "steps": k}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from h1v2_isaac_b200._capi import default_config
+    cfg = default_config()
+    cb = cpu_baseline(cfg, args.seed, steps=max(1, args.steps) if args.steps <= 50 else None, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": cb["steps"],
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Isaac-Velocity-Flat-H12_12dof-v0 physics+obs+reward step, random actions, CPU restatement of the MuJoCo sim2sim path (bounded sample)",
+                   "envs_per_step": cb["n_envs"], "decimation": 4, "sim_dt": 0.005},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from h1v2_isaac_b200._capi import default_config, load_library
+    from h1v2_isaac_b200.backend import H1v2Sim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    cfg = default_config()
+    cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
+    sim = H1v2Sim(n, cfg, device=dev, seed=args.seed)
+    sim.observe()
+    pool = [sim.random_actions(i) for i in range(16)]  # synthetic N(0,1) actions, resident in HBM
+    obs = torch.empty((n, sim.obs_dim), device=dev)
+    rew = torch.empty(n, device=dev)
+    term = torch.empty(n, dtype=torch.uint8, device=dev)
+    trunc = torch.empty(n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        sim.step_into(pool[i % 16], obs, rew, term, trunc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        ev[i][0].record()
+        sim.step_into(pool[i % 16], obs, rew, term, trunc)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = sim.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * n * K / (total_ms * 1e-3)
+    logv = sim.log_host()
+
+    # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        ha = [p.cpu().pin_memory() for p in pool[:4]]
+        hobs = torch.empty((n, sim.obs_dim), dtype=torch.float32).pin_memory()
+        hrew = torch.empty(n, dtype=torch.float32).pin_memory()
+        hterm = torch.empty(n, dtype=torch.uint8).pin_memory()
+        htrunc = torch.empty(n, dtype=torch.uint8).pin_memory()
+        Ke = max(10, min(K, 100))
+        for i in range(3):
+            sim.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            sim.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)  # synchronises inside
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * Ke / float(td.item()), "unit": METRIC, "h2d_bytes_per_step": n * 12 * 4,
+               "d2h_bytes_per_step": n * (sim.obs_dim * 4 + 4 + 1 + 1), "steps": Ke, "timer": "host wall clock around synchronous h1v2_step_host calls"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = ALGO_BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
+    import ctypes as C
+    fp = C.c_float(0.0)
+    load_library().h1v2_measure_fp32_peak(local, C.byref(fp))
+    rf_path = os.path.join(ROOT, "profiles", "roofline.json")
+    flops_per_env_step = json.load(open(rf_path)).get("fp32_flops_per_env_step") if os.path.exists(rf_path) else None
+    line = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Isaac-Velocity-Flat-H12_12dof-v0 physics+obs+reward step, {n} envs/GPU, random N(0,1) actions (BASELINE configs[1] when 4096)",
+                   "envs_per_gpu": n, "decimation": 4, "sim_dt": 0.005, "history": 10, "obs_dim": sim.obs_dim, "parallelism": f"env-shard x{world}",
+                   "l2": "flushed between timed steps (256 MiB write, untimed); per-step CUDA events summed"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "note": "the step kernel is FP32-issue bound, not HBM bound (SURVEY 8(d)); see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32", "peak": float(fp.value), "unit": "TFLOP/s", "peak_source": "h1v2_measure_fp32_peak (FFMA micro-benchmark, this run)",
+                          "flops_per_env_step": flops_per_env_step,
+                          "achieved": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12) if flops_per_env_step else None,
+                          "frac": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None},
+        "solver": {"mean_newton_iters_per_substep": float(logv[28]) / (4.0 * n), "max_iters_last_step": float(logv[26]), "cap_hits_last_step": float(logv[27]),
+                   "nan_resets": float(logv[25])},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb = cpu_baseline(cfg, args.seed)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the checker library missing must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

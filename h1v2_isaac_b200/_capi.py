@@ -22,7 +22,7 @@ REW_NAMES = [
     "track_ang_vel_z_exp_base", "feet_air_time_l2", "joint_vel_l2", "base_height_l2", "contact_forces",
 ]
 LOG_COUNT, LOG_REW0, LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW = 0, 1, 21, 22, 23, 24
-LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS = 25, 26, 27
+LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS, LOG_SUM_ITERS = 25, 26, 27, 28
 
 f32, i32, u32, i64 = C.c_float, C.c_int32, C.c_uint32, C.c_int64
 
@@ -38,7 +38,7 @@ class H1v2Config(C.Structure):
         ("contact_solref", f32 * 2), ("contact_solimp", f32 * 5),
         ("floss_solref", f32 * 2), ("floss_solimp", f32 * 5),
         ("limit_solref", f32 * 2), ("limit_solimp", f32 * 5),
-        ("solver_iterations", i32), ("solver_tolerance", f32),
+        ("solver_iterations", i32), ("solver_tolerance", f32), ("solver_step_tolerance", f32),
         ("history_length", i32), ("enable_corruption", i32),
         ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_joint_pos", f32), ("noise_joint_vel", f32),
         ("scale_ang_vel", f32), ("scale_gravity", f32), ("scale_cmd", f32), ("scale_joint_pos", f32),
@@ -108,6 +108,7 @@ _SYMBOLS = {
     "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "h1v2_get_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_launch_count": (i64, [C.c_void_p]),
+    "h1v2_measure_fp32_peak": (C.c_int, [i32, C.POINTER(f32)]),
     "h1v2_random_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
 }
 

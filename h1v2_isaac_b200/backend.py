@@ -46,7 +46,7 @@ class H1v2Sim:
             self.history = self.cfg.history_length
             step_dt = self.cfg.sim_dt * self.cfg.decimation
             import math
-            self.max_episode_length = int(math.ceil(self.cfg.episode_length_s / step_dt - 1e-9))
+            self.max_episode_length = int(math.ceil(self.cfg.episode_length_s / step_dt * (1.0 - 1e-6)))
             self.episode_length_buf = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
             self._check(self._lib.h1v2_bind_episode_length(self._h, self.episode_length_buf.data_ptr()))
             p = C.c_void_p()

@@ -77,6 +77,7 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
   S.leg[2 * N2 + lidx] = make_float4(qd[2], qd[3], qd[4], qd[5]);
   for (int k = 0; k < 5; k++) S.act[(size_t)k * N2 + lidx] = make_float4(0.f, 0.f, 0.f, 0.f);
   S.timers[lidx] = tm;
+  for (int k = 0; k < 3; k++) S.warm[(size_t)k * N2 + lidx] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void startup_kernel(const __grid_constant__ KParams P, const KState S, float fr_lo, float fr_hi, float ma_lo, float ma_hi) {
@@ -104,6 +105,17 @@ __global__ void random_actions_kernel(const __grid_constant__ KParams P, float* 
 #pragma unroll
     for (int k = 0; k < 4; k++) actions[(size_t)env * 12 + 4 * b + k] = z[k];
   }
+}
+
+// FP32 FMA peak micro-benchmark (denominator of the FP32 roofline; MEASURED_PEAKS.json has no FP32 entry)
+__global__ void fma_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; i++) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 // natural-layout state exchange; one thread per env
@@ -269,7 +281,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
     for (int k = 0; k < 6; k++) P.root_inertia[k] = (float)six[k];
   }
   P.h = c.sim_dt; P.decimation = c.decimation; P.step_dt = c.sim_dt * (float)c.decimation;
-  P.max_episode_length = (int64_t)std::ceil((double)c.episode_length_s / ((double)c.sim_dt * c.decimation) - 1e-9);
+  P.max_episode_length = (int64_t)std::ceil((double)c.episode_length_s / ((double)c.sim_dt * c.decimation) * (1.0 - 1e-6));
   P.max_episode_length_s = c.episode_length_s;
   P.action_scale = c.action_scale;
   bool seen[12] = {false};
@@ -302,7 +314,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   kb_h(c.contact_solref, c.contact_solimp, c.sim_dt, &P.contact_K, &P.contact_B);
   for (int k = 0; k < 5; k++) { P.limit_imp[k] = c.limit_solimp[k]; P.contact_imp[k] = c.contact_solimp[k]; }
   for (int s = 0; s < 6; s++) P.slot_tran[s] = (float)h1v2_slot_invweight_tran[s];
-  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance;
+  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance;
   P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
   if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
   P.H = c.history_length; P.obs_dim = c.history_length * H1V2_OBS_TERM_DIM; P.corrupt = c.enable_corruption;
@@ -361,6 +373,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &S.act, 5 * 2 * N);
   rc |= dalloc(h, &S.cmd, 2 * N);
   rc |= dalloc(h, &S.timers, 2 * N);
+  rc |= dalloc(h, &S.warm, 3 * 2 * N);
   rc |= dalloc(h, &S.epsum, 5 * N);
   rc |= dalloc(h, &S.hist, N * (size_t)h->P.H * H1V2_HIST_STRIDE);
   rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM);
@@ -498,6 +511,32 @@ int h1v2_get_log_host(H1v2Handle* h, float* log_host) {
   CK(cudaMemcpy(log_host, h->S.log, sizeof(float) * H1V2_LOG_DIM, cudaMemcpyDeviceToHost));
   return 0;
 }
+int h1v2_measure_fp32_peak(int32_t device, float* tflops) {
+  if (!tflops) return fail("h1v2_measure_fp32_peak: bad arguments");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  float* buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(float) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 6; rep++) {
+    CK(cudaEventRecord(e0));
+    fma_peak_kernel<<<blocks, threads>>>(buf, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = fmaxf(best, (float)(fl / (ms * 1e-3) / 1e12));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops = best;
+  return 0;
+}
+
 int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream) {
   if (!h || !actions) return fail("h1v2_random_actions: bad arguments");
   random_actions_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(h->P, actions, step);

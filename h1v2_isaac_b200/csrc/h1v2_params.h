@@ -44,6 +44,7 @@ struct KParams {
   float slot_tran[6];
   int max_iters;
   float tol;  // on |grad| * scale
+  float step_tol;
   float grad_scale;
   // observations
   int H, obs_dim, corrupt;
@@ -77,6 +78,7 @@ struct KState {
   float4* act;     // [5][2N]  last_action[6] | T1[6] | T2[6] | pad2   (MJCF order within the leg)
   float4* cmd;     // [2][N]   (cx,cy,cz,heading_target) (time_left,err_xy,err_yaw,flags)
   float4* timers;  // [2N]     cur_air,last_air,cur_contact,last_contact of the lane's foot
+  float4* warm;    // [3][2N]  solver warm start: qacc of the last substep (leg 6 | root 6)
   float4* epsum;   // [5][N]   episode sums of the 20 reward slots
   float* hist;     // [N][H][48]
   const int* lut;  // [obs_dim] (history index << 8) | offset in the 45-float sample, for the term-major flatten

@@ -227,7 +227,8 @@ struct SubOut {
 // ----------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void substep(const KParams& P, const int side, const unsigned pm, float (&rp)[3], float (&rq)[4],
                                      float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6], const float (&tau)[6],
-                                     const float mu, const float mass_add, SubOut& out) {
+                                     const float mu, const float mass_add, float (&wl)[6], float (&wr)[6], const bool use_warm,
+                                     SubOut& out) {
   const KLeg& LG = P.leg[side];
   const float h = P.h;
   // ---- root frame ----
@@ -398,7 +399,6 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
 
   // ---- solve: phase 0 smooth acceleration, phases 1.. Newton, last phase implicit update ----
   float xl[6], xr[6];        // iterate qacc (leg own, root replicated)
-  float xsl[6], xsr[6];      // qacc_smooth
   float Mal[6], Mar[6];      // M (x - x_smooth)
   float jl[6], jr[6];        // J' f at the last evaluation (leg own; root: sum over both lanes)
   V3 F_foot = mk3(0, 0, 0), F_shin = F_foot, F_torso = F_foot, F_pelvis = F_foot;
@@ -554,7 +554,13 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
     solve(F, rl, rr, pm);
     if (mode == 0) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) { xl[i] = xsl[i] = rl[i]; xr[i] = xsr[i] = rr[i]; Mal[i] = 0.f; Mar[i] = 0.f; jl[i] = 0.f; jr[i] = 0.f; }
+      for (int i = 0; i < 6; i++) { xl[i] = rl[i]; xr[i] = rr[i]; Mal[i] = 0.f; Mar[i] = 0.f; jl[i] = 0.f; jr[i] = 0.f; }
+      if (use_warm) {  // warm start from the previous substep's acceleration: Ma = M (x_w - x_smooth)
+        float dl[6], dr[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { dl[i] = wl[i] - xl[i]; dr[i] = wr[i] - xr[i]; xl[i] = wl[i]; xr[i] = wr[i]; }
+        matvec(M, dl, dr, Mal, Mar, pm);
+      }
       mode = 1;
       continue;
     }
@@ -562,6 +568,15 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
 #pragma unroll
       for (int i = 0; i < 6; i++) { xl[i] = rl[i]; xr[i] = rr[i]; }
       break;
+    }
+    {  // the Newton step no longer moves the acceleration: accept the iterate (J'f of this evaluation is current)
+      float smax = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rl[i]));
+      smax = fmaxf(smax, __shfl_xor_sync(pm, smax, 1));
+#pragma unroll
+      for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rr[i]));
+      if (smax < P.step_tol) { mode = 2; continue; }
     }
     // ---- exact line search along (rl, rr) ----
     float Msl[6], Msr[6];
@@ -618,8 +633,9 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
       if (d1 < 0.f) lo = alpha; else hi = alpha;
       float nx = alpha - d1 / d2;
       if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
-      if (nx == alpha) break;
+      const bool tiny = fabsf(nx - alpha) <= 1e-4f * alpha;
       alpha = nx;
+      if (tiny) break;
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -629,7 +645,7 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
   }
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----
 #pragma unroll
-  for (int j = 0; j < 6; j++) { out.qacc[j] = xl[j]; qd[j] = fmaf(h, xl[j], qd[j]); q[j] = fmaf(h, qd[j], q[j]); }
+  for (int j = 0; j < 6; j++) { out.qacc[j] = xl[j]; wl[j] = xl[j]; wr[j] = xr[j]; qd[j] = fmaf(h, xl[j], qd[j]); q[j] = fmaf(h, qd[j], q[j]); }
 #pragma unroll
   for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, xr[k], rv[k]); rw[k] = fmaf(h, xr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
   {

@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
     cmd.time_left = c1.x; cmd.m_xy = c1.y; cmd.m_yaw = c1.z; cmd.flags = __float_as_int(c1.w);
   }
   float4 tm = S.timers[lidx];
+  float wl[6], wr[6];
+  {
+    float4 w0 = S.warm[lidx], w1 = S.warm[N2 + lidx], w2 = S.warm[2 * N2 + lidx];
+    wl[0] = w0.x; wl[1] = w0.y; wl[2] = w0.z; wl[3] = w0.w; wl[4] = w1.x; wl[5] = w1.y;
+    wr[0] = w1.z; wr[1] = w1.w; wr[2] = w2.x; wr[3] = w2.y; wr[4] = w2.z; wr[5] = w2.w;
+  }
 
   if (DO_STEP) {
     // ---- action manager: process_action (JointPositionAction, V/velocity_env_cfg.py:111) ----
@@ -249,7 +255,8 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
     float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
     float tau[6];
     SubOut so;
-    int max_it = 0, ncap = 0;
+    int max_it = 0, ncap = 0, sum_it = 0;
+    bool use_warm = !(cmd.flags & FLAG_DELAY_FRESH);
 #pragma unroll 1
     for (int k = 0; k < P.decimation; k++) {
       const int age = lag - k;
@@ -260,8 +267,9 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
         float t = P.kp[j] * (T - q[i]) + P.kd[j] * (0.f - qd[i]);
         tau[i] = fminf(fmaxf(t, -P.effort[j]), P.effort[j]);
       }
-      substep(P, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, so);
-      max_it = max(max_it, so.iters); ncap += so.capped;
+      substep(P, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
+      use_warm = true;
+      max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters;
       float nf = sqrtf(dot(so.F_foot, so.F_foot));
       h_foot[0] = h_foot[1]; h_foot[1] = h_foot[2]; h_foot[2] = nf;
       h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = sqrtf(dot(so.F_shin, so.F_shin));
@@ -417,9 +425,11 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
     {
       int wm = __reduce_max_sync(0xffffffffu, valid ? max_it : 0);
       int wc = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? ncap : 0);
+      int ws = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? sum_it : 0);
       if ((threadIdx.x & 31) == 0) {
         atomicMax((int*)(S.acc + H1V2_LOG_MAX_ITERS), wm);
         if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (float)wc);
+        atomicAdd(S.acc + H1V2_LOG_SUM_ITERS, (float)ws);
       }
     }
     // ---- reset (T/utils/cat/cat_env.py:195-248): log, then new state ----
@@ -490,6 +500,9 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
     S.act[3 * N2 + lidx] = make_float4(T2[0], T2[1], T2[2], T2[3]);
     S.act[4 * N2 + lidx] = make_float4(T2[4], T2[5], 0.f, 0.f);
     S.timers[lidx] = tm;
+    S.warm[lidx] = make_float4(wl[0], wl[1], wl[2], wl[3]);
+    S.warm[N2 + lidx] = make_float4(wl[4], wl[5], wr[0], wr[1]);
+    S.warm[2 * N2 + lidx] = make_float4(wr[2], wr[3], wr[4], wr[5]);
   }
 }
 
@@ -503,7 +516,7 @@ __global__ void finalize_kernel(const KState S, int do_step) {
       if (t == H1V2_LOG_COUNT) S.log[t] = a;
       else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
       else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
-      else if (t == H1V2_LOG_CAP_HITS) S.log[t] = a;
+      else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS) S.log[t] = a;
       else if (cnt > 0.f) {
         const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
         S.log[t] = mean ? a / cnt : a;

@@ -77,6 +77,7 @@ enum {
  *   [25]                number of envs force-reset by the non-finite-state guard (cumulative)
  *   [26]                max Newton iterations used by any env in the last step
  *   [27]                number of (env,substep) solves that hit the iteration cap in the last step
+ *   [28]                total Newton iterations over all (env,substep) solves of the last step
  */
 #define H1V2_LOG_COUNT 0
 #define H1V2_LOG_REW0 1
@@ -87,6 +88,7 @@ enum {
 #define H1V2_LOG_NAN_RESETS 25
 #define H1V2_LOG_MAX_ITERS 26
 #define H1V2_LOG_CAP_HITS 27
+#define H1V2_LOG_SUM_ITERS 28
 
 typedef struct H1v2Config {
   /* ---- timing (velocity_env_cfg.py:302-305) ---- */
@@ -112,6 +114,7 @@ typedef struct H1v2Config {
   float limit_solref[2], limit_solimp[5];
   int32_t solver_iterations;           /* Newton iteration cap */
   float solver_tolerance;              /* on scaled gradient norm */
+  float solver_step_tolerance;         /* stop when the Newton step max|dqacc| falls below this (rad/s^2) */
   /* ---- observations (velocity_env_cfg.py:123-142, flat_env_cfg.py:25-27) ---- */
   int32_t history_length;              /* 10 */
   int32_t enable_corruption;           /* 1 */
@@ -214,6 +217,8 @@ int h1v2_get_log(H1v2Handle* h, const float** log_dev);
 int h1v2_get_log_host(H1v2Handle* h, float* log_host /*[H1V2_LOG_DIM]*/);
 /* number of kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t h1v2_launch_count(const H1v2Handle* h);
+/* FP32 FMA throughput of the device (TFLOP/s, best of 6): the measured denominator of the FP32 roofline */
+int h1v2_measure_fp32_peak(int32_t device, float* tflops);
 /* fill actions[N,12] with N(0,1) draws: Philox(seed, stream 7), counter = step */
 int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream);
 

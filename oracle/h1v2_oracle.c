@@ -986,7 +986,7 @@ int h1v2o_create(const H1v2Config* cfg, int32_t n_envs, uint64_t seed, H1v2Oracl
   o->max_newton_iters = 100;
   o->nthreads = 1;
   double step_dt = (double)cfg->sim_dt * cfg->decimation;
-  o->max_episode_length = (int64_t)ceil((double)cfg->episode_length_s / step_dt - 1e-9);
+  o->max_episode_length = (int64_t)ceil((double)cfg->episode_length_s / step_dt * (1.0 - 1e-6)); /* float dt: 0.005f*4 is not 0.02 */
   for (int j = 0; j < NJ; j++) {
     double lo = cfg->joint_range[j][0], hi = cfg->joint_range[j][1];
     double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo) * cfg->soft_limit_factor;
