@@ -38,7 +38,7 @@ class H1v2Config(C.Structure):
         ("contact_solref", f32 * 2), ("contact_solimp", f32 * 5),
         ("floss_solref", f32 * 2), ("floss_solimp", f32 * 5),
         ("limit_solref", f32 * 2), ("limit_solimp", f32 * 5),
-        ("solver_iterations", i32), ("solver_tolerance", f32), ("solver_step_tolerance", f32),
+        ("solver_iterations", i32), ("solver_tolerance", f32), ("solver_step_tolerance", f32), ("solver_ls_tolerance", f32),
         ("history_length", i32), ("enable_corruption", i32),
         ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_joint_pos", f32), ("noise_joint_vel", f32),
         ("scale_ang_vel", f32), ("scale_gravity", f32), ("scale_cmd", f32), ("scale_joint_pos", f32),
@@ -72,9 +72,10 @@ STATE_FIELDS = [
     ("episode_sums", NUM_REW, f32), ("obs_history", None, f32), ("friction", 1, f32), ("mass_add", 1, f32),
     ("push_time_left", 1, f32),
     ("slot_force", NUM_SLOT * 3, f32), ("slot_force_hist", NUM_SLOT * 3, f32), ("applied_torque", NJ, f32),
-    ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32),
+    ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32), ("solver_iters", 2, f32),
+    ("pre_reset_qpos", 19, f32), ("pre_reset_qvel", 18, f32), ("pre_reset_timers", 8, f32),
 ]
-READ_ONLY_STATE = {"slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel"}
+READ_ONLY_STATE = {"slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel", "solver_iters", "pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers"}
 
 
 class H1v2State(C.Structure):
@@ -107,6 +108,7 @@ _SYMBOLS = {
     "h1v2_set_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "h1v2_get_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_debug_iter_hist": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_launch_count": (i64, [C.c_void_p]),
     "h1v2_measure_fp32_peak": (C.c_int, [i32, C.POINTER(f32)]),
     "h1v2_random_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -148,6 +148,12 @@ class H1v2Sim:
         self._check(self._lib.h1v2_get_log_host(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
+    def iter_hist(self):
+        import numpy as np
+        out = np.zeros(32, np.float32)
+        self._check(self._lib.h1v2_debug_iter_hist(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.h1v2_launch_count(self._h))

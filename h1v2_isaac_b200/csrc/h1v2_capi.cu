@@ -176,6 +176,10 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
       if (st.joint_acc) for (int k = 0; k < 12; k++) st.joint_acc[env * 12 + k] = dg[48 + k];
       if (st.reward_terms) for (int k = 0; k < 20; k++) st.reward_terms[env * 20 + k] = dg[60 + k];
       if (st.foot_vel) for (int k = 0; k < 6; k++) st.foot_vel[env * 6 + k] = dg[80 + k];
+      if (st.pre_reset_qpos) for (int k = 0; k < 19; k++) st.pre_reset_qpos[env * 19 + k] = dg[96 + k];
+      if (st.pre_reset_qvel) for (int k = 0; k < 18; k++) st.pre_reset_qvel[env * 18 + k] = dg[115 + k];
+      if (st.pre_reset_timers) for (int k = 0; k < 8; k++) st.pre_reset_timers[env * 8 + k] = dg[133 + k];
+      if (st.solver_iters) { st.solver_iters[env * 2] = dg[86]; st.solver_iters[env * 2 + 1] = dg[88]; }
     }
     return;
   }
@@ -314,7 +318,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   kb_h(c.contact_solref, c.contact_solimp, c.sim_dt, &P.contact_K, &P.contact_B);
   for (int k = 0; k < 5; k++) { P.limit_imp[k] = c.limit_solimp[k]; P.contact_imp[k] = c.contact_solimp[k]; }
   for (int s = 0; s < 6; s++) P.slot_tran[s] = (float)h1v2_slot_invweight_tran[s];
-  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance;
+  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance; P.ls_tol = c.solver_ls_tolerance > 0.f ? c.solver_ls_tolerance : 0.01f;
   P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
   if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
   P.H = c.history_length; P.obs_dim = c.history_length * H1V2_OBS_TERM_DIM; P.corrupt = c.enable_corruption;
@@ -376,7 +380,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &S.warm, 3 * 2 * N);
   rc |= dalloc(h, &S.epsum, 5 * N);
   rc |= dalloc(h, &S.hist, N * (size_t)h->P.H * H1V2_HIST_STRIDE);
-  rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM);
+  rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM + 32);  // + cumulative histogram of Newton iterations per solve
   rc |= dalloc(h, &S.log, (size_t)H1V2_LOG_DIM);
   rc |= dalloc(h, &S.counters, (size_t)2);
   rc |= dalloc(h, &h->own_ep_len, N);
@@ -443,10 +447,17 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
 }
 
 static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st) {
-  const int threads = 64, lanes = 2 * h->n;
+  const int threads = H1V2_BLOCK, lanes = 2 * h->n;
   const int blocks = (lanes + threads - 1) / threads;
+  const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
   if (do_step)
-    step_kernel<true><<<blocks, threads, 0, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
+    step_kernel<true><<<blocks, threads, smem, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
   else
     step_kernel<false><<<blocks, threads, 0, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
   finalize_kernel<<<1, 32, 0, st>>>(h->S, do_step ? 1 : 0);
@@ -503,6 +514,12 @@ int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream) {
 int h1v2_get_log(H1v2Handle* h, const float** log_dev) {
   if (!h || !log_dev) return fail("h1v2_get_log: bad arguments");
   *log_dev = h->S.log;
+  return 0;
+}
+int h1v2_debug_iter_hist(H1v2Handle* h, float* hist32) {
+  if (!h || !hist32) return fail("h1v2_debug_iter_hist: bad arguments");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(hist32, h->S.acc + H1V2_LOG_DIM, sizeof(float) * 32, cudaMemcpyDeviceToHost));
   return 0;
 }
 int h1v2_get_log_host(H1v2Handle* h, float* log_host) {

@@ -57,6 +57,7 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->solver_iterations = 12;
   c->solver_tolerance = 1e-5f;
   c->solver_step_tolerance = 1e-2f;
+  c->solver_ls_tolerance = 0.01f;
   // observations: V/velocity_env_cfg.py:123-132 ; C12/flat_env_cfg.py:25-27
   c->history_length = 10;
   c->enable_corruption = 1;

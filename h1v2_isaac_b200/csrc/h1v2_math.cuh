@@ -33,11 +33,45 @@ __device__ __forceinline__ M3 quat2mat(float w, float x, float y, float z) {
   R.cz = mk3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
   return R;
 }
+// sine/cosine for bounded arguments (joint angles, half rotation angles: |x| < ~100): Cody-Waite reduction by pi/2
+// and degree-7/8 minimax polynomials on [-pi/4, pi/4]; ~1 ulp, no slow path (keeps the kernel's code small)
+__device__ __forceinline__ void sincos_lim(float x, float& s, float& c) {
+  const float kf = rintf(x * 0.636619772367581343f);
+  const int k = (int)kf;
+  float r = fmaf(kf, -1.57079601287841796875f, x);
+  r = fmaf(kf, -3.1391647326017846353e-7f, r);
+  r = fmaf(kf, -5.3903025299577647655e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+  sp = fmaf(sp, r2, -1.66666546e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+  cp = fmaf(cp, r2, 4.16666457e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const float ss = (k & 1) ? cp : sp, cc = (k & 1) ? sp : cp;
+  s = (k & 2) ? -ss : ss;
+  c = ((k + 1) & 2) ? -cc : cc;
+}
 // R <- R * Rot(axis, th), axis in {0:x, 1:y, 2:z}
 template <int AXIS>
 __device__ __forceinline__ void rotate(M3& R, float th) {
   float s, c;
   sincosf(th, &s, &c);
+  if (AXIS == 2) {
+    V3 X = fma3(R.cx, c, R.cy * s), Y = fma3(R.cy, c, R.cx * (-s));
+    R.cx = X; R.cy = Y;
+  } else if (AXIS == 1) {
+    V3 X = fma3(R.cx, c, R.cz * (-s)), Z = fma3(R.cz, c, R.cx * s);
+    R.cx = X; R.cz = Z;
+  } else {
+    V3 Y = fma3(R.cy, c, R.cz * s), Z = fma3(R.cz, c, R.cy * (-s));
+    R.cy = Y; R.cz = Z;
+  }
+}
+// same with the sine/cosine already known
+template <int AXIS>
+__device__ __forceinline__ void rotate_sc(M3& R, float s, float c) {
   if (AXIS == 2) {
     V3 X = fma3(R.cx, c, R.cy * s), Y = fma3(R.cy, c, R.cx * (-s));
     R.cx = X; R.cy = Y;
@@ -153,7 +187,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 #define STREAM_CMD 2u
 #define STREAM_EVENT 3u
 #define STREAM_ACTIONS 7u
-__device__ __forceinline__ void rng4(uint32_t key0, int64_t gid, unsigned long long step, uint32_t stream, uint32_t block,
+__device__ __noinline__ void rng4(uint32_t key0, int64_t gid, unsigned long long step, uint32_t stream, uint32_t block,
                                      float (&u)[4]) {
   uint32_t o[4];
   philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), stream, block, key0, (uint32_t)gid, o);
@@ -164,8 +198,10 @@ __device__ __forceinline__ float uni(float u, float lo, float hi) { return lo + 
 
 __device__ __forceinline__ float wrap_to_pi(float a) {
   const float PI = 3.14159265358979323846f, TWO_PI = 2.0f * 3.14159265358979323846f;
-  float w = fmodf(a + PI, TWO_PI);
+  float w = a + PI;
+  w = w - TWO_PI * floorf(w / TWO_PI);
   if (w < 0.f) w += TWO_PI;
+  if (w >= TWO_PI) w -= TWO_PI;
   if (w == 0.0f && a > 0.0f) return PI;
   return w - PI;
 }

@@ -45,6 +45,7 @@ struct KParams {
   int max_iters;
   float tol;  // on |grad| * scale
   float step_tol;
+  float ls_tol;  // line-search tolerance on |phi'(alpha)| / |phi'(0)|  (MuJoCo opt.ls_tolerance = 0.01)
   float grad_scale;
   // observations
   int H, obs_dim, corrupt;
@@ -88,9 +89,9 @@ struct KState {
   float* log;      // [H1V2_LOG_DIM] published log vector
   unsigned long long* counters;  // [0] global step counter, [1] history head
 };
-#define H1V2_DIAG_DIM 96
+#define H1V2_DIAG_DIM 144
 // diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | reward_terms 60..79
-//              | foot_vel 80..85 | newton iters 86 | cap hit 87
+//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140
 #define FLAG_DELAY_FRESH 1
 #define FLAG_HIST_FRESH 2
 #define FLAG_LAG_SHIFT 2

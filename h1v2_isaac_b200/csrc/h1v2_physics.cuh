@@ -1,18 +1,25 @@
 // h1v2_physics.cuh -- one physics substep of the H1-2 (floating base + 2 x 6-dof legs) for ONE LANE PAIR.
 //
-// Work decomposition: two adjacent lanes own one environment; lane `side` owns one leg.
-// The mass matrix of a floating base with two serial branches is block-arrow:
-//        [ A    B_L   B_R ]      A   6x6 root block (replicated bit-identically on both lanes)
-//    M = [ B_L' C_L   0   ]      B_s 6x6 root-leg coupling of this lane's leg
-//        [ B_R' 0     C_R ]      C_s 6x6 leg block
-// so every factorisation is: Cholesky(C_s) per lane, Y_s = L_s^-1 B_s', one pair-exchange of Y_s'Y_s (21 floats),
-// Cholesky of the 6x6 Schur complement on both lanes.  Contacts attach a symmetric 6x6 "stiffness" K to the foot /
-// shin / root bodies, so the Newton Hessian M + J'DJ keeps exactly the same block-arrow shape.
+// Work decomposition: two adjacent lanes own one environment; lane `side` owns one leg and
+// both lanes carry the 6 root dofs bit-identically.  Nothing is ever formed as an 18x18 matrix:
+//
+//   * every linear system of the step --  M a = f (smooth),  (M + J'DJ + diag) s = -grad (Newton),
+//     (M + h*damping) a = f + J'f (implicitfast) -- is the forward dynamics of an articulated body whose link
+//     inertias are augmented by the contact "stiffness" K of the links in contact, so it is solved by the
+//     articulated-body algorithm: one tip->root sweep per leg (6x6 articulated inertia, rank-1 downdate per joint),
+//     a pair exchange of the two legs' hand-offs in root-joint space (27 floats), a 6x6 Cholesky on both lanes and
+//     one root->tip sweep.  M x products are one RNE-like sweep.
+//   * leg quantities are expressed in world axes about the ANKLE (foot-link origin): the light distal links and the
+//     large contact forces sit next to the reference point, which removes the m*r^2 cancellation that limits fp32
+//     when everything is referenced to the pelvis (profiles/r1_notes.md).  Root-body quantities are about the pelvis
+//     origin; the two meet in root-joint space, which is reference-point independent.
+//   * bulk per-joint data (axis, moment arm, link inertia, ABA hand-off) and the active contact list live in a
+//     per-thread column of shared memory ([field][thread], conflict free); small per-joint vectors stay in registers.
 //
 // Semantics restated from the reference's physics target (MuJoCo 3.3.6 as configured by
 // packages/biped_deploy/biped_deploy/simulator/sim_mujoco.py:39-41 on
 // packages/biped_assets/biped_assets/models/h12/scene/h12_12dof.xml):
-// CRBA + RNE bias, soft constraints (friction loss, joint limits, pyramidal contacts with solref/solimp),
+// RNE bias, soft constraints (friction loss, joint limits, pyramidal contacts with solref/solimp),
 // primal Newton with exact line search, implicitfast velocity update, semi-implicit Euler.
 #pragma once
 #include "h1v2_math.cuh"
@@ -20,92 +27,49 @@
 
 namespace h1v2 {
 
+#define H1V2_BLOCK 32
+// shared-memory column of one thread: 6 joints x JSTRIDE floats, then MAXC contact points x PSTRIDE floats
+#define JSTRIDE 32
+#define F_W 0      // 3  joint axis (world)
+#define F_U 3      // 3  (joint position - O_s) x axis
+#define F_I 6      // 10 link inertia about O_s: m, m*c (3), xx yy zz xy xz yz
+#define F_X 16     // 6  scratch: RNE link force | ABA U = IA*S (n,l) | M-product link force
+#define F_DINV 22  // 1  ABA 1/(S'IA S + armature + diag)
+#define F_XQ 23    // 1  acceleration iterate
+#define F_R 24     // 1  rhs of the current solve -> ABA reduced rhs -> solution / search direction
+#define F_MA 25    // 1  (M x - f_smooth)
+#define F_G 26     // 1  J'f at the last evaluation
+#define F_DG 27    // 1  extra diagonal of the current solve | (M s) after the M-product
+#define F_FLC 28   // 1  friction-loss row offset  B*qd
+#define F_LIMC 29  // 1  limit row offset
+#define F_LIMD 30  // 1  limit row sign * D (0 = no limit row)
+#define F_FS 31    // 1  smooth force
+#define MAXC 7
+#define PSTRIDE 8  // r (3) | B*velocity (3) | K*imp*dist | 1/R   (owner link from the list position)
+#define PT_BASE (6 * JSTRIDE)
+#define SMEM_FLOATS (PT_BASE + MAXC * PSTRIDE)
+
+struct Smem {
+  float* base;  // this thread's column
+  __device__ __forceinline__ float& jf(int j, int f) const { return base[(j * JSTRIDE + f) * H1V2_BLOCK]; }
+  __device__ __forceinline__ float& pf(int p, int f) const { return base[(PT_BASE + p * PSTRIDE + f) * H1V2_BLOCK]; }
+  __device__ __forceinline__ V3 jv(int j, int f) const { return mk3(jf(j, f), jf(j, f + 1), jf(j, f + 2)); }
+  __device__ __forceinline__ void sjv(int j, int f, V3 v) const { jf(j, f) = v.x; jf(j, f + 1) = v.y; jf(j, f + 2) = v.z; }
+  __device__ __forceinline__ V3 pv(int p, int f) const { return mk3(pf(p, f), pf(p, f + 1), pf(p, f + 2)); }
+  __device__ __forceinline__ RI ji(int j) const {
+    RI I;
+    I.m = jf(j, F_I); I.mc = jv(j, F_I + 1);
+    I.xx = jf(j, F_I + 4); I.yy = jf(j, F_I + 5); I.zz = jf(j, F_I + 6); I.xy = jf(j, F_I + 7); I.xz = jf(j, F_I + 8); I.yz = jf(j, F_I + 9);
+    return I;
+  }
+  __device__ __forceinline__ void sji(int j, const RI& I) const {
+    jf(j, F_I) = I.m; sjv(j, F_I + 1, I.mc);
+    jf(j, F_I + 4) = I.xx; jf(j, F_I + 5) = I.yy; jf(j, F_I + 6) = I.zz; jf(j, F_I + 7) = I.xy; jf(j, F_I + 8) = I.xz; jf(j, F_I + 9) = I.yz;
+  }
+};
+
 __device__ __forceinline__ float pair_sum(float v, unsigned pm) { return v + __shfl_xor_sync(pm, v, 1); }
 __device__ __forceinline__ V3 pair_sum(V3 v, unsigned pm) { return mk3(pair_sum(v.x, pm), pair_sum(v.y, pm), pair_sum(v.z, pm)); }
-
-struct Blk {  // one lane's share of a block-arrow symmetric matrix
-  float C[21];
-  float B[36];  // B[k*6+j]: root dof k, leg joint j
-  float A[21];
-};
-struct Fac {
-  float L[21], invd[6];
-  float Y[36];  // Y[i*6+k] = (L^-1 B')[i][k]
-  float La[21], inva[6];
-};
-
-__device__ __forceinline__ void factor(const Blk& Mx, Fac& F, unsigned pm) {
-#pragma unroll
-  for (int i = 0; i < 21; i++) F.L[i] = Mx.C[i];
-  chol6(F.L, F.invd);
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      float s = Mx.B[k * 6 + i];
-#pragma unroll
-      for (int m = 0; m < i; m++) s = fmaf(-F.L[TI(i, m)], F.Y[m * 6 + k], s);
-      F.Y[i * 6 + k] = s * F.invd[i];
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 6; a++) {
-#pragma unroll
-    for (int b = 0; b <= a; b++) {
-      float g = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; i++) g = fmaf(F.Y[i * 6 + a], F.Y[i * 6 + b], g);
-      F.La[TI(a, b)] = Mx.A[TI(a, b)] - pair_sum(g, pm);
-    }
-  }
-  chol6(F.La, F.inva);
-}
-
-// solve M x = b ; b_leg/x_leg own 6, b_root/x_root replicated
-__device__ __forceinline__ void solve(const Fac& F, float (&leg)[6], float (&root)[6], unsigned pm) {
-  fwd6(F.L, F.invd, leg);
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; i++) t = fmaf(F.Y[i * 6 + k], leg[i], t);
-    root[k] -= pair_sum(t, pm);
-  }
-  fwd6(F.La, F.inva, root);
-  bwd6(F.La, F.inva, root);
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    float s = leg[i];
-#pragma unroll
-    for (int k = 0; k < 6; k++) s = fmaf(-F.Y[i * 6 + k], root[k], s);
-    leg[i] = s;
-  }
-  bwd6(F.L, F.invd, leg);
-}
-
-// y = M x (leg part own, root part replicated)
-__device__ __forceinline__ void matvec(const Blk& Mx, const float (&xl)[6], const float (&xr)[6], float (&yl)[6], float (&yr)[6],
-                                       unsigned pm) {
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; j++) s = fmaf(i >= j ? Mx.C[TI(i, j)] : Mx.C[TI(j, i)], xl[j], s);
-#pragma unroll
-    for (int k = 0; k < 6; k++) s = fmaf(Mx.B[k * 6 + i], xr[k], s);
-    yl[i] = s;
-  }
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    float t = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; j++) t = fmaf(Mx.B[k * 6 + j], xl[j], t);
-    float s = pair_sum(t, pm);
-#pragma unroll
-    for (int m = 0; m < 6; m++) s = fmaf(k >= m ? Mx.A[TI(k, m)] : Mx.A[TI(m, k)], xr[m], s);
-    yr[k] = s;
-  }
-}
 
 // MuJoCo getimpedance (solimp = d0, dmax, width, midpoint, power), margin 0
 __device__ __forceinline__ float impedance(const float* si, float pos) {
@@ -122,7 +86,7 @@ __device__ __forceinline__ float impedance(const float* si, float pos) {
   return dmin + y * (dmax - dmin);
 }
 
-// general symmetric 6x6 about O in [ang;lin] order: aa (6: xx yy zz xy xz yz), al (9: row=ang, col=lin), ll (6)
+// general symmetric 6x6 in [ang;lin] order: aa (xx yy zz xy xz yz), al (row = ang, col = lin), ll (xx yy zz xy xz yz)
 struct K6 {
   float aa[6], al[9], ll[6];
 };
@@ -138,6 +102,12 @@ __device__ __forceinline__ void k6_add(K6& K, const K6& o) {
 #pragma unroll
   for (int i = 0; i < 9; i++) K.al[i] += o.al[i];
 }
+// K += rigid inertia: n = I w + mc x u  ->  al = [mc]x ;  l = m u + w x mc
+__device__ __forceinline__ void k6_add_rigid(K6& K, const RI& I) {
+  K.aa[0] += I.xx; K.aa[1] += I.yy; K.aa[2] += I.zz; K.aa[3] += I.xy; K.aa[4] += I.xz; K.aa[5] += I.yz;
+  K.ll[0] += I.m; K.ll[1] += I.m; K.ll[2] += I.m;
+  K.al[1] -= I.mc.z; K.al[2] += I.mc.y; K.al[3] += I.mc.z; K.al[5] -= I.mc.x; K.al[6] -= I.mc.y; K.al[7] += I.mc.x;
+}
 __device__ __forceinline__ V3 sym3_mul(const float* s, V3 v) {
   return mk3(fmaf(s[0], v.x, fmaf(s[3], v.y, s[4] * v.z)), fmaf(s[3], v.x, fmaf(s[1], v.y, s[5] * v.z)),
              fmaf(s[4], v.x, fmaf(s[5], v.y, s[2] * v.z)));
@@ -149,53 +119,48 @@ __device__ __forceinline__ void k6_apply(const K6& K, V3 w, V3 u, V3& n, V3& l) 
   l = sym3_mul(K.ll, u) + mk3(fmaf(K.al[0], w.x, fmaf(K.al[3], w.y, K.al[6] * w.z)), fmaf(K.al[1], w.x, fmaf(K.al[4], w.y, K.al[7] * w.z)),
                               fmaf(K.al[2], w.x, fmaf(K.al[5], w.y, K.al[8] * w.z)));
 }
+// K -= (n;l)(n;l)' * s
+__device__ __forceinline__ void k6_rank1_sub(K6& K, V3 n, V3 l, float s) {
+  V3 ns = n * s, ls = l * s;
+  K.aa[0] = fmaf(-ns.x, n.x, K.aa[0]); K.aa[1] = fmaf(-ns.y, n.y, K.aa[1]); K.aa[2] = fmaf(-ns.z, n.z, K.aa[2]);
+  K.aa[3] = fmaf(-ns.x, n.y, K.aa[3]); K.aa[4] = fmaf(-ns.x, n.z, K.aa[4]); K.aa[5] = fmaf(-ns.y, n.z, K.aa[5]);
+  K.ll[0] = fmaf(-ls.x, l.x, K.ll[0]); K.ll[1] = fmaf(-ls.y, l.y, K.ll[1]); K.ll[2] = fmaf(-ls.z, l.z, K.ll[2]);
+  K.ll[3] = fmaf(-ls.x, l.y, K.ll[3]); K.ll[4] = fmaf(-ls.x, l.z, K.ll[4]); K.ll[5] = fmaf(-ls.y, l.z, K.ll[5]);
+  K.al[0] = fmaf(-ns.x, l.x, K.al[0]); K.al[1] = fmaf(-ns.x, l.y, K.al[1]); K.al[2] = fmaf(-ns.x, l.z, K.al[2]);
+  K.al[3] = fmaf(-ns.y, l.x, K.al[3]); K.al[4] = fmaf(-ns.y, l.y, K.al[4]); K.al[5] = fmaf(-ns.y, l.z, K.al[5]);
+  K.al[6] = fmaf(-ns.z, l.x, K.al[6]); K.al[7] = fmaf(-ns.z, l.y, K.al[7]); K.al[8] = fmaf(-ns.z, l.z, K.al[8]);
+}
 
-#define NPT 11  // candidate contact points of a lane: 0..3 sole corners, 4..5 shin ends, 6..9 torso corners, 10 pelvis (lane 0)
-
-struct Contacts {
-  unsigned mask;     // active candidates (dist < 0)
-  float r[NPT][3];   // contact point relative to O
-  float ub[NPT][3];  // B * point velocity
-  float kap[NPT];    // K * imp * dist
-  float D[NPT];      // 1/R of the four pyramid edges
-  float e[NPT][3];   // J_p x + ub at the current iterate
-  float us[NPT][3];  // J_p search
-};
-
-// one contact point at the iterate: edge residuals -> force vector and (optionally) the 3x3 weight W = D * sum_active a a'
-// edges a_k = (0,mu,1) (0,-mu,1) (-mu,0,1) (mu,0,1)
+// one contact point at the iterate: edge residuals -> force vector and the 3x3 weight W = D * sum_active a a'
+// edges a_k = (0,mu,1) (0,-mu,1) (-mu,0,1) (mu,0,1)   (normal z, tangents y and -x: mju_makeFrame on the plane normal)
 __device__ __forceinline__ void point_eval(V3 e, float kap, float D, float mu, V3& F, float (&W)[5]) {
   float j0 = fmaf(mu, e.y, e.z) + kap, j1 = fmaf(-mu, e.y, e.z) + kap;
   float j2 = fmaf(-mu, e.x, e.z) + kap, j3 = fmaf(mu, e.x, e.z) + kap;
   float a0 = j0 < 0.f ? D : 0.f, a1 = j1 < 0.f ? D : 0.f, a2 = j2 < 0.f ? D : 0.f, a3 = j3 < 0.f ? D : 0.f;
   float f0 = -a0 * j0, f1 = -a1 * j1, f2 = -a2 * j2, f3 = -a3 * j3;
   F = mk3(mu * (f3 - f2), mu * (f0 - f1), (f0 + f1) + (f2 + f3));
-  W[0] = mu * mu * (a2 + a3);         // xx
-  W[1] = mu * mu * (a0 + a1);         // yy
-  W[2] = (a0 + a1) + (a2 + a3);       // zz
-  W[3] = mu * (a3 - a2);              // xz
-  W[4] = mu * (a0 - a1);              // yz
+  W[0] = mu * mu * (a2 + a3);    // xx
+  W[1] = mu * mu * (a0 + a1);    // yy
+  W[2] = (a0 + a1) + (a2 + a3);  // zz
+  W[3] = mu * (a3 - a2);         // xz
+  W[4] = mu * (a0 - a1);         // yz
+}
+__device__ __forceinline__ V3 w5_mul(const float (&W)[5], V3 g) {
+  return mk3(W[0] * g.x + W[3] * g.z, W[1] * g.y + W[4] * g.z, W[3] * g.x + W[4] * g.y + W[2] * g.z);
 }
 // K += X' W X with X = [G | 1], G = -[r]x   (point velocity u = v_O + w x r)
 __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const float (&W)[5]) {
-  // columns of G: g_j = e_j x r
-  V3 g0 = mk3(0.f, -r.z, r.y), g1 = mk3(r.z, 0.f, -r.x), g2 = mk3(-r.y, r.x, 0.f);
-  // W g_j  (W symmetric with xy = 0)
-  V3 w0 = mk3(W[0] * g0.x + W[3] * g0.z, W[1] * g0.y + W[4] * g0.z, W[3] * g0.x + W[4] * g0.y + W[2] * g0.z);
-  V3 w1 = mk3(W[0] * g1.x + W[3] * g1.z, W[1] * g1.y + W[4] * g1.z, W[3] * g1.x + W[4] * g1.y + W[2] * g1.z);
-  V3 w2 = mk3(W[0] * g2.x + W[3] * g2.z, W[1] * g2.y + W[4] * g2.z, W[3] * g2.x + W[4] * g2.y + W[2] * g2.z);
+  V3 g0 = mk3(0.f, -r.z, r.y), g1 = mk3(r.z, 0.f, -r.x), g2 = mk3(-r.y, r.x, 0.f);  // columns of G: e_j x r
+  V3 w0 = w5_mul(W, g0), w1 = w5_mul(W, g1), w2 = w5_mul(W, g2);
   K.aa[0] += dot(g0, w0); K.aa[1] += dot(g1, w1); K.aa[2] += dot(g2, w2);
   K.aa[3] += dot(g0, w1); K.aa[4] += dot(g0, w2); K.aa[5] += dot(g1, w2);
-  // al[i][c] = (G' W)[i][c] = (W g_i)[c]
   K.al[0] += w0.x; K.al[1] += w0.y; K.al[2] += w0.z;
   K.al[3] += w1.x; K.al[4] += w1.y; K.al[5] += w1.z;
   K.al[6] += w2.x; K.al[7] += w2.y; K.al[8] += w2.z;
   K.ll[0] += W[0]; K.ll[1] += W[1]; K.ll[2] += W[2]; K.ll[4] += W[3]; K.ll[5] += W[4];
 }
-
-// line-search contribution of one contact point at step alpha: d1 += D*jar*jv, d2 += D*jv^2 over active edges
-__device__ __forceinline__ void point_ls(V3 e, V3 us, float a, float kap, float D, float mu, float& d1, float& d2) {
-  V3 ea = fma3(us, a, e);
+// line-search contribution of one contact point: d1 += D*jar*jv, d2 += D*jv^2 over the edges active at ea
+__device__ __forceinline__ void point_ls(V3 ea, V3 us, float kap, float D, float mu, float& d1, float& d2) {
   float j0 = fmaf(mu, ea.y, ea.z) + kap, j1 = fmaf(-mu, ea.y, ea.z) + kap;
   float j2 = fmaf(-mu, ea.x, ea.z) + kap, j3 = fmaf(mu, ea.x, ea.z) + kap;
   float v0 = fmaf(mu, us.y, us.z), v1 = fmaf(-mu, us.y, us.z), v2 = fmaf(-mu, us.x, us.z), v3 = fmaf(mu, us.x, us.z);
@@ -207,8 +172,7 @@ __device__ __forceinline__ void point_ls(V3 e, V3 us, float a, float kap, float 
   d1 = fmaf(D, s1, d1);
   d2 = fmaf(D, s2, d2);
 }
-
-// friction-loss row: force and activity at residual jar
+// friction-loss row: force and activity (= D inside the quadratic zone) at residual jar
 __device__ __forceinline__ float floss_force(float jar, float D, float lim, float fl, float& act) {
   if (jar <= -lim) { act = 0.f; return fl; }
   if (jar >= lim) { act = 0.f; return -fl; }
@@ -217,21 +181,53 @@ __device__ __forceinline__ float floss_force(float jar, float D, float lim, floa
 }
 
 struct SubOut {
-  V3 F_foot, F_shin, F_torso, F_pelvis;  // net contact forces (torso pair-summed, pelvis valid on both lanes)
+  V3 F_foot, F_shin, F_torso, F_pelvis;  // net contact forces (torso/pelvis pair-summed, valid on both lanes)
   float qacc[6];                         // joint accelerations of this leg after the implicit update
-  int iters, capped;
+  int iters, capped, overflow;
 };
+
+// root-joint-space projection helpers.  Root dofs seen from reference point O_s = O_r + d:
+//   translation k: (0, e_k) ; rotation k: (c_k, c_k x d)   with c_k = columns of the root rotation
+struct RootBasis {
+  V3 c[3], rd[3];
+};
+__device__ __forceinline__ void root_project_force(const RootBasis& B, V3 n, V3 l, float (&out)[6]) {
+  out[0] = l.x; out[1] = l.y; out[2] = l.z;
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[3 + k] = dot(B.c[k], n) + dot(B.rd[k], l);
+}
+// A (packed lower 6x6) += S_r' K S_r
+__device__ __forceinline__ void root_project_k6(const RootBasis& B, const K6& K, float (&A)[21]) {
+  A[TI(0, 0)] += K.ll[0]; A[TI(1, 1)] += K.ll[1]; A[TI(2, 2)] += K.ll[2];
+  A[TI(1, 0)] += K.ll[3]; A[TI(2, 0)] += K.ll[4]; A[TI(2, 1)] += K.ll[5];
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    V3 n, l;
+    k6_apply(K, B.c[b], B.rd[b], n, l);
+    A[TI(3 + b, 0)] += l.x; A[TI(3 + b, 1)] += l.y; A[TI(3 + b, 2)] += l.z;
+#pragma unroll
+    for (int a = 0; a <= b; a++) A[TI(3 + b, 3 + a)] += dot(B.c[a], n) + dot(B.rd[a], l);
+  }
+}
+// spatial "velocity" of the root body for generalized vector xr, about O_r + d
+__device__ __forceinline__ void root_motion(const RootBasis& B, const float (&xr)[6], V3 d, V3& a, V3& l) {
+  a = fma3(B.c[0], xr[3], fma3(B.c[1], xr[4], B.c[2] * xr[5]));
+  l = mk3(xr[0], xr[1], xr[2]) + cross(a, d);
+}
 
 // ----------------------------------------------------------------------------------------------------------
 // One physics substep.  State is updated in place.  tau = joint torques after the actuator's effort clip.
+// wl/wr: warm start in (if use_warm), solution out.
 // ----------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void substep(const KParams& P, const int side, const unsigned pm, float (&rp)[3], float (&rq)[4],
-                                     float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6], const float (&tau)[6],
-                                     const float mu, const float mass_add, float (&wl)[6], float (&wr)[6], const bool use_warm,
-                                     SubOut& out) {
+__device__ __forceinline__ void substep(const KParams& P, const int side, const unsigned pm, float (&rp)[3],
+                                     float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
+                                     const float (&tau)[6], const float mu, const float mass_add, float (&wl)[6], float (&wr)[6],
+                                     const bool use_warm, SubOut& out) {
+  extern __shared__ float smem_raw[];
+  const Smem sm{smem_raw + threadIdx.x};
   const KLeg& LG = P.leg[side];
   const float h = P.h;
-  // ---- root frame ----
+  // ---- root frame (about O_r = pelvis origin) ----
   {
     float n = rsqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
     rq[0] *= n; rq[1] *= n; rq[2] *= n; rq[3] *= n;
@@ -239,10 +235,10 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
   const M3 R0 = quat2mat(rq[0], rq[1], rq[2], rq[3]);
   const V3 v0 = mk3(rv[0], rv[1], rv[2]);
   const V3 om0 = mulv(R0, mk3(rw[0], rw[1], rw[2]));
-  const V3 acc0 = mk3(0.f, 0.f, P.gravity) + cross(v0, om0);  // cacc of the root: -gravity + free-joint cdof_dot
+  const V3 acc0 = mk3(0.f, 0.f, P.gravity) + cross(v0, om0);  // root cacc: -gravity + free-joint cdof_dot * qvel
   const float m0 = P.root_mass + mass_add;
   const RI I0 = body_inertia(R0, mulv(R0, ld3(P.root_ipos)), m0, P.root_inertia, m0 / P.root_mass);
-  V3 f0n, f0l;
+  V3 f0n, f0l;  // bias force of the root link about O_r
   {
     V3 an, al, vn, vl;
     ri_apply(I0, mk3(0.f, 0.f, 0.f), acc0, an, al);
@@ -250,31 +246,51 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
     f0n = an + cross(om0, vn) + cross(v0, vl);
     f0l = al + cross(om0, vl);
   }
-  // ---- leg forward pass: kinematics, velocities, bias accelerations, per-body inertia and force ----
-  V3 w[6], u[6];
-  RI Ib[6];
-  V3 fn[6], fl[6];
-  M3 Rshin, Rfoot;
-  V3 xshin, xfoot, om_shin, vo_shin, om_foot, vo_foot;
+  // ---- pass 1: joint sines/cosines and the ankle position d (O_s = O_r + d) ----
+  float sn[6], cs[6];
+  V3 d;
   {
     M3 R = R0;
-    V3 x = mk3(0.f, 0.f, 0.f), om = om0, vo = v0, al = mk3(0.f, 0.f, 0.f), ao = acc0;
-#define LEG_JOINT(i, AX)                                                              \
-  {                                                                                   \
-    x = x + mulv(R, ld3(LG.pos[i]));                                                  \
-    V3 wi = axis_col<AX>(R);                                                          \
-    V3 ui = cross(x, wi);                                                             \
-    V3 sdw = cross(om, wi), sdu = cross(om, ui) + cross(vo, wi);                      \
-    al = fma3(sdw, qd[i], al); ao = fma3(sdu, qd[i], ao);                             \
-    om = fma3(wi, qd[i], om); vo = fma3(ui, qd[i], vo);                               \
-    rotate<AX>(R, q[i]);                                                              \
-    w[i] = wi; u[i] = ui;                                                             \
-    Ib[i] = body_inertia(R, x + mulv(R, ld3(LG.ipos[i])), LG.mass[i], LG.inertia[i], 1.f); \
-    V3 an, aL, vn, vL;                                                                \
-    ri_apply(Ib[i], al, ao, an, aL);                                                  \
-    ri_apply(Ib[i], om, vo, vn, vL);                                                  \
-    fn[i] = an + cross(om, vn) + cross(vo, vL);                                       \
-    fl[i] = aL + cross(om, vL);                                                       \
+    V3 x = mk3(0.f, 0.f, 0.f);
+#define P1_JOINT(i, AX)                        \
+  {                                            \
+    x = x + mulv(R, ld3(LG.pos[i]));           \
+    sincos_lim(q[i], sn[i], cs[i]);            \
+    rotate_sc<AX>(R, sn[i], cs[i]);            \
+  }
+    P1_JOINT(0, 2) P1_JOINT(1, 1) P1_JOINT(2, 0) P1_JOINT(3, 1) P1_JOINT(4, 1)
+    x = x + mulv(R, ld3(LG.pos[5]));
+    sincos_lim(q[5], sn[5], cs[5]);
+#undef P1_JOINT
+    d = x;
+  }
+  RootBasis RB, RB0;  // root dofs seen from O_s and from O_r
+  RB.c[0] = RB0.c[0] = R0.cx; RB.c[1] = RB0.c[1] = R0.cy; RB.c[2] = RB0.c[2] = R0.cz;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { RB.rd[k] = cross(RB.c[k], d); RB0.rd[k] = mk3(0.f, 0.f, 0.f); }
+  // ---- pass 2: kinematics about O_s, velocities, bias accelerations, link inertia and RNE link force ----
+  M3 Rshin, Rfoot;
+  V3 xshin, om_shin, vo_shin, om_foot, vo_foot;
+  {
+    M3 R = R0;
+    V3 x = mk3(0.f, 0.f, 0.f) - d, om = om0, vo = v0 + cross(om0, d), al = mk3(0.f, 0.f, 0.f), ao = acc0;
+#define LEG_JOINT(i, AX)                                                                    \
+  {                                                                                         \
+    x = x + mulv(R, ld3(LG.pos[i]));                                                        \
+    V3 wi = axis_col<AX>(R);                                                                \
+    V3 ui = cross(x, wi);                                                                   \
+    V3 sdw = cross(om, wi), sdu = cross(om, ui) + cross(vo, wi);                            \
+    al = fma3(sdw, qd[i], al); ao = fma3(sdu, qd[i], ao);                                   \
+    om = fma3(wi, qd[i], om); vo = fma3(ui, qd[i], vo);                                     \
+    rotate_sc<AX>(R, sn[i], cs[i]);                                                         \
+    sm.sjv(i, F_W, wi); sm.sjv(i, F_U, ui);                                                 \
+    RI Ii = body_inertia(R, x + mulv(R, ld3(LG.ipos[i])), LG.mass[i], LG.inertia[i], 1.f);  \
+    sm.sji(i, Ii);                                                                          \
+    V3 an, aL, vn, vL;                                                                      \
+    ri_apply(Ii, al, ao, an, aL);                                                           \
+    ri_apply(Ii, om, vo, vn, vL);                                                           \
+    sm.sjv(i, F_X, an + cross(om, vn) + cross(vo, vL));                                     \
+    sm.sjv(i, F_X + 3, aL + cross(om, vL));                                                 \
   }
     LEG_JOINT(0, 2)
     LEG_JOINT(1, 1)
@@ -283,388 +299,400 @@ __device__ __noinline__ void substep(const KParams& P, const int side, const uns
     Rshin = R; xshin = x; om_shin = om; vo_shin = vo;
     LEG_JOINT(4, 1)
     LEG_JOINT(5, 0)
-    Rfoot = R; xfoot = x; om_foot = om; vo_foot = vo;
+    Rfoot = R; om_foot = om; vo_foot = vo;
 #undef LEG_JOINT
   }
-  // ---- backward pass: composite inertia -> M blocks, composite force -> bias ----
-  Blk M;
-  float bias_leg[6];
-  RI Ic;
-  V3 fcn, fcl;
-#pragma unroll
-  for (int j = 5; j >= 0; j--) {
-    if (j == 5) { Ic = Ib[5]; fcn = fn[5]; fcl = fl[5]; }
-    else { Ic = Ic + Ib[j]; fcn = fcn + fn[j]; fcl = fcl + fl[j]; }
-    V3 n, l;
-    ri_apply(Ic, w[j], u[j], n, l);
-    bias_leg[j] = dot(w[j], fcn) + dot(u[j], fcl);
-#pragma unroll
-    for (int i = 0; i <= j; i++) M.C[TI(j, i)] = dot(w[i], n) + dot(u[i], l);
-    M.C[TI(j, j)] += P.armature[6 + 6 * side + j];
-    M.B[0 * 6 + j] = l.x; M.B[1 * 6 + j] = l.y; M.B[2 * 6 + j] = l.z;
-    M.B[3 * 6 + j] = dot(R0.cx, n); M.B[4 * 6 + j] = dot(R0.cy, n); M.B[5 * 6 + j] = dot(R0.cz, n);
-  }
-  // ---- root block and root bias (replicated: partner contributions are added as self+partner) ----
-  float bias_root[6];
+  // ---- smooth forces: tau - bias - damping*v ; dof-row constants (friction loss, joint limits) ----
+  float fs_root[6];
   {
-    RI It;
-    It.m = I0.m + pair_sum(Ic.m, pm);
-    It.mc = I0.mc + pair_sum(Ic.mc, pm);
-    It.xx = I0.xx + pair_sum(Ic.xx, pm); It.yy = I0.yy + pair_sum(Ic.yy, pm); It.zz = I0.zz + pair_sum(Ic.zz, pm);
-    It.xy = I0.xy + pair_sum(Ic.xy, pm); It.xz = I0.xz + pair_sum(Ic.xz, pm); It.yz = I0.yz + pair_sum(Ic.yz, pm);
-    V3 ftn = f0n + pair_sum(fcn, pm), ftl = f0l + pair_sum(fcl, pm);
-    V3 c[3] = {R0.cx, R0.cy, R0.cz};
+    V3 fcn = mk3(0.f, 0.f, 0.f), fcl = fcn;
 #pragma unroll
-    for (int i = 0; i < 21; i++) M.A[i] = 0.f;
-    M.A[TI(0, 0)] = M.A[TI(1, 1)] = M.A[TI(2, 2)] = It.m;
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-      V3 n = rot_inertia_mul(It, c[b]);
-      V3 l = cross(c[b], It.mc);
-      M.A[TI(3 + b, 0)] = l.x; M.A[TI(3 + b, 1)] = l.y; M.A[TI(3 + b, 2)] = l.z;
-#pragma unroll
-      for (int a = 0; a <= b; a++) M.A[TI(3 + b, 3 + a)] = dot(c[a], n);
+    for (int j = 5; j >= 0; j--) {
+      fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
+      const int dj = 6 + 6 * side + j, jj = 6 * side + j;
+      const float lim = P.frc[jj];
+      const float t = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
+      const float fs = t - (dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl)) - P.damping[dj] * qd[j];
+      sm.jf(j, F_FS) = fs;
+      sm.jf(j, F_XQ) = 0.f; sm.jf(j, F_MA) = -fs; sm.jf(j, F_G) = 0.f;
+      sm.jf(j, F_FLC) = P.floss_B * qd[j];
+      const float dlo = q[j] - P.range_lo[jj], dhi = P.range_hi[jj] - q[j];
+      const float sig = dlo < 0.f ? 1.f : (dhi < 0.f ? -1.f : 0.f);
+      float lc = 0.f, lD = 0.f;
+      if (sig != 0.f) {
+        const float dist = dlo < 0.f ? dlo : dhi;
+        const float imp = impedance(P.limit_imp, dist);
+        lc = sig * P.limit_B * qd[j] + P.limit_K * imp * dist;
+        lD = sig / fmaxf(1e-15f, (1.f - imp) * P.limit_invw[jj] / imp);
+      }
+      sm.jf(j, F_LIMC) = lc; sm.jf(j, F_LIMD) = lD;
+      sm.jf(j, F_R) = wl[j];  // warm start (consumed by phase 0)
     }
+    float bl[6], b0[6];
+    root_project_force(RB, fcn, fcl, bl);
+    root_project_force(RB0, f0n, f0l, b0);
 #pragma unroll
-    for (int k = 0; k < 6; k++) M.A[TI(k, k)] += P.armature[k];
-    bias_root[0] = ftl.x; bias_root[1] = ftl.y; bias_root[2] = ftl.z;
-    bias_root[3] = dot(c[0], ftn); bias_root[4] = dot(c[1], ftn); bias_root[5] = dot(c[2], ftn);
+    for (int k = 0; k < 6; k++) fs_root[k] = -(b0[k] + pair_sum(bl[k], pm)) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
   }
-  // ---- smooth forces ----
-  float fs_leg[6], fs_root[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    const int d = 6 + 6 * side + j;
-    float lim = P.frc[6 * side + j];
-    float t = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
-    fs_leg[j] = t - bias_leg[j] - P.damping[d] * qd[j];
-  }
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    fs_root[k] = -bias_root[k] - P.damping[k] * rv[k];
-    fs_root[3 + k] = -bias_root[3 + k] - P.damping[3 + k] * rw[k];
-  }
-  // ---- constraint rows owned by this lane ----
-  // dof rows: friction loss on own leg dofs and on root dofs 3*side..3*side+2; joint limits on own leg
-  float fl_c[6], rfl_c[3];             // B_f * velocity (the -aref of the row)
-  float lim_sig[6], lim_c[6], lim_D[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    fl_c[j] = P.floss_B * qd[j];
-    const int jj = 6 * side + j;
-    float dlo = q[j] - P.range_lo[jj], dhi = P.range_hi[jj] - q[j];
-    float sig = dlo < 0.f ? 1.f : (dhi < 0.f ? -1.f : 0.f);
-    float dist = dlo < 0.f ? dlo : dhi;
-    float imp = impedance(P.limit_imp, dist);
-    lim_sig[j] = sig;
-    lim_c[j] = sig * P.limit_B * qd[j] + P.limit_K * imp * dist;
-    lim_D[j] = sig != 0.f ? 1.f / fmaxf(1e-15f, (1.f - imp) * P.limit_invw[jj] / imp) : 0.f;
-  }
+  float rfl_c[3];  // friction-loss rows of the root dofs 3*side..3*side+2 owned by this lane
 #pragma unroll
   for (int k = 0; k < 3; k++) rfl_c[k] = P.floss_B * (side == 0 ? rv[k] : rw[k]);
-  // contact candidates
-  Contacts CT;
-  CT.mask = 0u;
+  // contact candidates -> compact active list, ordered foot | shin | torso | pelvis (feet, shins about O_s; root about O_r)
+  int n_foot = 0, e_shin = 0, e_torso = 0, nact = 0, overflow = 0;
   {
     const float pz = rp[2];
     const float mu2 = mu * mu;
-#define CAND(p, Rb, xb, omb, vob, lp, rad, slot)                                                           \
-  {                                                                                                        \
-    V3 c = xb + mulv(Rb, lp);                                                                              \
-    float dist = pz + c.z - (rad);                                                                         \
-    if (dist < 0.f) {                                                                                      \
-      CT.mask |= 1u << (p);                                                                                \
-      V3 rc = mk3(c.x, c.y, 0.5f * dist - pz);                                                             \
-      V3 vel = vob + cross(omb, rc);                                                                       \
-      float imp = impedance(P.contact_imp, dist);                                                          \
-      float tr = P.slot_tran[slot];                                                                        \
-      float R0_ = fmaxf(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);                                      \
-      CT.r[p][0] = rc.x; CT.r[p][1] = rc.y; CT.r[p][2] = rc.z;                                             \
-      CT.ub[p][0] = P.contact_B * vel.x; CT.ub[p][1] = P.contact_B * vel.y; CT.ub[p][2] = P.contact_B * vel.z; \
-      CT.kap[p] = P.contact_K * imp * dist;                                                                \
-      CT.D[p] = 1.f / fmaxf(1e-15f, 2.f * mu2 * R0_);                                                      \
-    }                                                                                                      \
-  }
-#pragma unroll
-    for (int p = 0; p < 4; p++) CAND(p, Rfoot, xfoot, om_foot, vo_foot, ld3(LG.foot_pt[p]), 0.f, side)
-#pragma unroll
-    for (int p = 0; p < 2; p++) CAND(4 + p, Rshin, xshin, om_shin, vo_shin, ld3(LG.shin_pt[p]), LG.shin_rad, 2 + side)
-    const V3 zero = mk3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int p = 0; p < 4; p++) CAND(6 + p, R0, zero, om0, v0, ld3(P.root_pt[4 * side + p]), P.root_rad[4 * side + p], 4)
-    if (side == 0) CAND(10, R0, zero, om0, v0, ld3(P.root_pt[8]), P.root_rad[8], 5)
-#undef CAND
-  }
-  const unsigned m_foot = CT.mask & 0xFu, m_shin = CT.mask & 0x30u, m_root = CT.mask & 0x7C0u;
-
-  // ---- solve: phase 0 smooth acceleration, phases 1.. Newton, last phase implicit update ----
-  float xl[6], xr[6];        // iterate qacc (leg own, root replicated)
-  float Mal[6], Mar[6];      // M (x - x_smooth)
-  float jl[6], jr[6];        // J' f at the last evaluation (leg own; root: sum over both lanes)
-  V3 F_foot = mk3(0, 0, 0), F_shin = F_foot, F_torso = F_foot, F_pelvis = F_foot;
-  int mode = 0, it = 0, capped = 0;
-  Fac F;
-  for (;;) {
-    Blk Hm;
-    float rl[6], rr[6];
-    if (mode == 0) {
-#pragma unroll
-      for (int i = 0; i < 21; i++) { Hm.C[i] = M.C[i]; Hm.A[i] = M.A[i]; }
-#pragma unroll
-      for (int i = 0; i < 36; i++) Hm.B[i] = M.B[i];
-#pragma unroll
-      for (int i = 0; i < 6; i++) { rl[i] = fs_leg[i]; rr[i] = fs_root[i]; }
-    } else if (mode == 1) {
-      // ---- evaluate all rows at x: forces, gradient, Hessian increments ----
-      float dC[6], dAo[3];  // diagonal increments from dof rows
-      float gl[6], gr_own[6];
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        const int d = 6 + 6 * side + j;
-        float act;
-        float f = floss_force(xl[j] + fl_c[j], P.floss_D[d], P.floss_lim[d], P.floss[d], act);
-        float jar = fmaf(lim_sig[j], xl[j], lim_c[j]);
-        float la = (lim_sig[j] != 0.f && jar < 0.f) ? lim_D[j] : 0.f;
-        f += lim_sig[j] * (-la * jar);
-        gl[j] = f;
-        dC[j] = act + la;
+    const int ncand = side == 0 ? 11 : 10;
+#pragma unroll 1
+    for (int p = 0; p < ncand; p++) {
+      V3 lp, xb, omb, vob;
+      M3 Rb;
+      float rad, href;
+      int slot;
+      if (p < 4) { lp = ld3(LG.foot_pt[p]); Rb = Rfoot; xb = mk3(0.f, 0.f, 0.f); omb = om_foot; vob = vo_foot; rad = 0.f; slot = side; href = pz + d.z; }
+      else if (p < 6) { lp = ld3(LG.shin_pt[p - 4]); Rb = Rshin; xb = xshin; omb = om_shin; vob = vo_shin; rad = LG.shin_rad; slot = 2 + side; href = pz + d.z; }
+      else {
+        const int rpi = p < 10 ? 4 * side + (p - 6) : 8;
+        lp = ld3(P.root_pt[rpi]); Rb = R0; xb = mk3(0.f, 0.f, 0.f); omb = om0; vob = v0; rad = P.root_rad[rpi]; slot = p < 10 ? 4 : 5; href = pz;
       }
+      const V3 c = xb + mulv(Rb, lp);
+      const float dist = href + c.z - rad;
+      if (dist < 0.f) {
+        if (nact < MAXC) {
+          const V3 rc = mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
+          const V3 vel = vob + cross(omb, rc);
+          const float imp = impedance(P.contact_imp, dist);
+          const float tr = P.slot_tran[slot];
+          const float Rn = fmaxf(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);
+          sm.pf(nact, 0) = rc.x; sm.pf(nact, 1) = rc.y; sm.pf(nact, 2) = rc.z;
+          sm.pf(nact, 3) = P.contact_B * vel.x; sm.pf(nact, 4) = P.contact_B * vel.y; sm.pf(nact, 5) = P.contact_B * vel.z;
+          sm.pf(nact, 6) = P.contact_K * imp * dist;
+          sm.pf(nact, 7) = 1.f / fmaxf(1e-15f, 2.f * mu2 * Rn);
+          nact++;
+          n_foot += p < 4; e_shin += p < 6; e_torso += p < 10;
+        } else {
+          overflow = 1;
+        }
+      }
+    }
+  }
+
+  // ---- iterate state: per-joint scalars live in the shared-memory column, root 6-vectors in registers ----
+  float xr[6], Mar[6], jr[6], rr[6], dgr[6], Msr[6];
+  K6 Kf, Ks;     // contact stiffness of the foot / shin links about O_s
+  float Ar[21];  // this lane's share of root-block increments from root contact points (about O_r)
+  V3 F_foot = mk3(0, 0, 0), F_shin = F_foot, F_torso = F_foot, F_pelvis = F_foot;
+  int it = 0, capped = 0;
+  const V3 zero3 = mk3(0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 6; k++) gr_own[k] = 0.f;
+  for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = wr[i]; dgr[i] = 0.f; }
+  const float* arm = P.armature + 6 + 6 * side;
+  const float* dmp = P.damping + 6 + 6 * side;
+  const float* flD = P.floss_D + 6 + 6 * side;
+  const float* flL = P.floss_lim + 6 + 6 * side;
+  const float* flF = P.floss + 6 + 6 * side;
+
+  // phase 0: inject the warm start (x = 0 -> previous acceleration, unit step); 1: Newton; 2: implicitfast update
+  int phase = use_warm ? 0 : 1;
+#pragma unroll 1
+  for (;;) {
+    if (phase == 1) {
+      // ---- evaluate all rows at x: forces, gradient pieces, Hessian increments ----
+      float gr_own[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { gr_own[k] = 0.f; dgr[k] = 0.f; }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const int d = 3 * side + k;
+        const int dk = 3 * side + k;
         float act;
-        float f = floss_force(xr[d] + rfl_c[k], P.floss_D[d], P.floss_lim[d], P.floss[d], act);
-        gr_own[d] = f;
-        dAo[k] = act;
+        gr_own[dk] = floss_force(xr[dk] + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
+        dgr[dk] = act;
       }
-      // body "velocities" of the iterate: V_root, V_shin, V_foot
-      V3 Va_root = fma3(R0.cx, xr[3], fma3(R0.cy, xr[4], R0.cz * xr[5])), Vl_root = mk3(xr[0], xr[1], xr[2]);
-      V3 Va_shin = Va_root, Vl_shin = Vl_root;
-#pragma unroll
-      for (int j = 0; j < 4; j++) { Va_shin = fma3(w[j], xl[j], Va_shin); Vl_shin = fma3(u[j], xl[j], Vl_shin); }
-      V3 Va_foot = fma3(w[4], xl[4], fma3(w[5], xl[5], Va_shin)), Vl_foot = fma3(u[4], xl[4], fma3(u[5], xl[5], Vl_shin));
-      K6 Kf, Ks, Kr;
-      k6_zero(Kf); k6_zero(Ks); k6_zero(Kr);
-      V3 Wn_f = mk3(0, 0, 0), Wl_f = Wn_f, Wn_s = Wn_f, Wl_s = Wn_f, Wn_r = Wn_f, Wl_r = Wn_f;
-      F_foot = F_shin = F_torso = F_pelvis = mk3(0, 0, 0);
-#define POINT(p, Va, Vl, Kacc, Wn, Wl, Facc)                                  \
-  if (CT.mask & (1u << (p))) {                                                \
-    V3 r = ld3(CT.r[p]);                                                      \
-    V3 e = Vl + cross(Va, r) + ld3(CT.ub[p]);                                 \
-    CT.e[p][0] = e.x; CT.e[p][1] = e.y; CT.e[p][2] = e.z;                     \
-    V3 Fp; float Wp[5];                                                       \
-    point_eval(e, CT.kap[p], CT.D[p], mu, Fp, Wp);                            \
-    k6_add_point(Kacc, r, Wp);                                                \
-    Wn = Wn + cross(r, Fp); Wl = Wl + Fp; Facc = Facc + Fp;                   \
-  }
-      if (m_foot) {
-#pragma unroll
-        for (int p = 0; p < 4; p++) POINT(p, Va_foot, Vl_foot, Kf, Wn_f, Wl_f, F_foot)
+      V3 Va_r, Vl_r, Va_s, Vl_s, Va_f, Vl_f;  // body "velocities" of the iterate about O_r (root) and O_s (shin, foot)
+      root_motion(RB0, xr, zero3, Va_r, Vl_r);
+      root_motion(RB, xr, d, Va_f, Vl_f);
+      Va_s = Va_f; Vl_s = Vl_f;
+#pragma unroll 1
+      for (int j = 0; j < 6; j++) {
+        const float x = sm.jf(j, F_XQ);
+        float act;
+        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
+        const float lD = sm.jf(j, F_LIMD);
+        const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
+        const float jar = fmaf(sig, x, sm.jf(j, F_LIMC));
+        const float la = (sig != 0.f && jar < 0.f) ? fabsf(lD) : 0.f;
+        f += sig * (-la * jar);
+        sm.jf(j, F_G) = f;
+        sm.jf(j, F_DG) = act + la;
+        Va_f = fma3(sm.jv(j, F_W), x, Va_f); Vl_f = fma3(sm.jv(j, F_U), x, Vl_f);
+        if (j == 3) { Va_s = Va_f; Vl_s = Vl_f; }
       }
-      if (m_shin) {
+      F_foot = F_shin = F_torso = F_pelvis = zero3;
 #pragma unroll
-        for (int p = 4; p < 6; p++) POINT(p, Va_shin, Vl_shin, Ks, Wn_s, Wl_s, F_shin)
+      for (int i = 0; i < 21; i++) Ar[i] = 0.f;
+      k6_zero(Kf); k6_zero(Ks);
+      V3 Wn_f = zero3, Wl_f = zero3, Wn_s = zero3, Wl_s = zero3, Wn_r = zero3, Wl_r = zero3;
+#pragma unroll 1
+      for (int p = 0; p < nact; p++) {
+        const V3 r = sm.pv(p, 0), ub = sm.pv(p, 3);
+        const int tag = p < n_foot ? 0 : (p < e_shin ? 1 : (p < e_torso ? 2 : 3));
+        const V3 Va = tag == 0 ? Va_f : (tag == 1 ? Va_s : Va_r), Vl = tag == 0 ? Vl_f : (tag == 1 ? Vl_s : Vl_r);
+        const V3 e = Vl + cross(Va, r) + ub;
+        V3 Fp;
+        float Wp[5];
+        point_eval(e, sm.pf(p, 6), sm.pf(p, 7), mu, Fp, Wp);
+        const V3 mom = cross(r, Fp);
+        if (tag == 0) { k6_add_point(Kf, r, Wp); Wn_f = Wn_f + mom; Wl_f = Wl_f + Fp; F_foot = F_foot + Fp; }
+        else if (tag == 1) { k6_add_point(Ks, r, Wp); Wn_s = Wn_s + mom; Wl_s = Wl_s + Fp; F_shin = F_shin + Fp; }
+        else {
+          K6 Kp;
+          k6_zero(Kp);
+          k6_add_point(Kp, r, Wp);
+          root_project_k6(RB0, Kp, Ar);
+          Wn_r = Wn_r + mom; Wl_r = Wl_r + Fp;
+          if (tag == 2) F_torso = F_torso + Fp; else F_pelvis = F_pelvis + Fp;
+        }
       }
-      if (m_root) {
+      const V3 Wn_leg = Wn_f + Wn_s, Wl_leg = Wl_f + Wl_s;  // wrench of the leg contacts about O_s
+      {
+        float t6[6];
+        root_project_force(RB, Wn_leg, Wl_leg, t6);
 #pragma unroll
-        for (int p = 6; p < 10; p++) POINT(p, Va_root, Vl_root, Kr, Wn_r, Wl_r, F_torso)
-        POINT(10, Va_root, Vl_root, Kr, Wn_r, Wl_r, F_pelvis)
+        for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
+        root_project_force(RB0, Wn_r, Wl_r, t6);
+#pragma unroll
+        for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
       }
-#undef POINT
-      // J' f: composite wrenches (foot -> joints 4,5 ; foot+shin -> joints 0..3 ; all -> root)
-      V3 Wn_fs = Wn_f + Wn_s, Wl_fs = Wl_f + Wl_s;
-#pragma unroll
-      for (int j = 0; j < 6; j++) gl[j] += (j >= 4) ? dot(w[j], Wn_f) + dot(u[j], Wl_f) : dot(w[j], Wn_fs) + dot(u[j], Wl_fs);
-      V3 Wn_t = Wn_fs + Wn_r, Wl_t = Wl_fs + Wl_r;
-      gr_own[0] += Wl_t.x; gr_own[1] += Wl_t.y; gr_own[2] += Wl_t.z;
-      gr_own[3] += dot(R0.cx, Wn_t); gr_own[4] += dot(R0.cy, Wn_t); gr_own[5] += dot(R0.cz, Wn_t);
       float gn2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 6; j++) { jl[j] = gl[j]; rl[j] = gl[j] - Mal[j]; gn2 = fmaf(rl[j], rl[j], gn2); }
+#pragma unroll 1
+      for (int j = 0; j < 6; j++) {
+        const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
+        const float g = sm.jf(j, F_G) + ((j >= 4) ? dot(wj, Wn_f) + dot(uj, Wl_f) : dot(wj, Wn_leg) + dot(uj, Wl_leg));
+        const float r = g - sm.jf(j, F_MA);
+        sm.jf(j, F_G) = g; sm.jf(j, F_R) = r;
+        gn2 = fmaf(r, r, gn2);
+      }
+      F_torso = pair_sum(F_torso, pm);
+      F_pelvis = pair_sum(F_pelvis, pm);
       gn2 = pair_sum(gn2, pm);
 #pragma unroll
       for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k], pm); rr[k] = jr[k] - Mar[k]; gn2 = fmaf(rr[k], rr[k], gn2); }
-      F_torso = pair_sum(F_torso, pm);
-      F_pelvis = pair_sum(F_pelvis, pm);
       const bool conv = sqrtf(gn2) * P.grad_scale < P.tol;
-      if (conv || it >= P.max_iters) {
-        capped = !conv;
-        mode = 2;
-      } else {
-        it++;
-        // ---- Hessian = M + J' D J ----
+      if (conv || it >= P.max_iters) { capped = !conv; phase = 2; }
+      else it++;
+    }
+    if (phase == 2) {
+      // implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f
+#pragma unroll 1
+      for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * dmp[j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
 #pragma unroll
-        for (int i = 0; i < 21; i++) Hm.C[i] = M.C[i];
+      for (int k = 0; k < 6; k++) { dgr[k] = 0.5f * h * P.damping[k]; rr[k] = fs_root[k] + jr[k]; }  // halves are pair-summed
+    }
+    // ---- ABA sweep 1 (tip -> root): articulated inertia and reduced rhs.  Skipped for the warm-start injection. ----
+    V3 aa, al;  // acceleration of the parent link of joint 0 (the root, about O_s)
+    if (phase != 0) {
+      K6 IA;
+      k6_zero(IA);
+      V3 pn = zero3, pl = zero3;
+      const bool kc = phase == 1;
+#pragma unroll 1
+      for (int j = 5; j >= 0; j--) {
+        k6_add_rigid(IA, sm.ji(j));
+        if (kc && j == 5 && n_foot) k6_add(IA, Kf);
+        if (kc && j == 3 && e_shin > n_foot) k6_add(IA, Ks);
+        const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
+        V3 n, l;
+        k6_apply(IA, wj, uj, n, l);
+        const float dinv = 1.f / (dot(wj, n) + dot(uj, l) + arm[j] + sm.jf(j, F_DG));
+        const float t = sm.jf(j, F_R) - (dot(wj, pn) + dot(uj, pl));
+        sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
+        sm.jf(j, F_DINV) = dinv; sm.jf(j, F_R) = t;
+        k6_rank1_sub(IA, n, l, dinv);
+        const float td = t * dinv;
+        pn = fma3(n, td, pn); pl = fma3(l, td, pl);
+      }
+      // root block: own link + hand-offs of both legs (joint space) + diagonal; 6x6 Cholesky on both lanes
+      float A[21], g[6];
 #pragma unroll
-        for (int i = 0; i < 36; i++) Hm.B[i] = M.B[i];
+      for (int i = 0; i < 21; i++) A[i] = kc ? Ar[i] : 0.f;
+      root_project_k6(RB, IA, A);
+      root_project_force(RB, pn, pl, g);
 #pragma unroll
-        for (int j = 0; j < 6; j++) Hm.C[TI(j, j)] += dC[j];
-        float dA[21];
+      for (int k = 0; k < 6; k++) A[TI(k, k)] += dgr[k];
+      {
+        K6 K0;
+        k6_zero(K0);
+        k6_add_rigid(K0, I0);
+        float A0[21];
 #pragma unroll
-        for (int i = 0; i < 21; i++) dA[i] = 0.f;
+        for (int i = 0; i < 21; i++) A0[i] = 0.f;
+        root_project_k6(RB0, K0, A0);
 #pragma unroll
-        for (int k = 0; k < 3; k++) dA[TI(3 * side + k, 3 * side + k)] = dAo[k];
-        if (CT.mask) {
-          K6 Kc = Kf;  // composite stiffness seen by joints 4,5
+        for (int i = 0; i < 21; i++) A[i] = A0[i] + pair_sum(A[i], pm);
+      }
 #pragma unroll
-          for (int j = 5; j >= 0; j--) {
-            if (j == 3) k6_add(Kc, Ks);
-            V3 n, l;
-            k6_apply(Kc, w[j], u[j], n, l);
-#pragma unroll
-            for (int i = 0; i <= j; i++) Hm.C[TI(j, i)] += dot(w[i], n) + dot(u[i], l);
-            Hm.B[0 * 6 + j] += l.x; Hm.B[1 * 6 + j] += l.y; Hm.B[2 * 6 + j] += l.z;
-            Hm.B[3 * 6 + j] += dot(R0.cx, n); Hm.B[4 * 6 + j] += dot(R0.cy, n); Hm.B[5 * 6 + j] += dot(R0.cz, n);
-          }
-          k6_add(Kc, Kr);
-          // root block: trans-trans = ll, rot_b-trans = (al' c_b), rot-rot = c_a' aa c_b
-          dA[TI(0, 0)] += Kc.ll[0]; dA[TI(1, 1)] += Kc.ll[1]; dA[TI(2, 2)] += Kc.ll[2];
-          dA[TI(1, 0)] += Kc.ll[3]; dA[TI(2, 0)] += Kc.ll[4]; dA[TI(2, 1)] += Kc.ll[5];
-          V3 c[3] = {R0.cx, R0.cy, R0.cz};
-#pragma unroll
-          for (int b = 0; b < 3; b++) {
-            V3 n, l;
-            k6_apply(Kc, c[b], mk3(0.f, 0.f, 0.f), n, l);
-            dA[TI(3 + b, 0)] += l.x; dA[TI(3 + b, 1)] += l.y; dA[TI(3 + b, 2)] += l.z;
-#pragma unroll
-            for (int a = 0; a <= b; a++) dA[TI(3 + b, 3 + a)] += dot(c[a], n);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 21; i++) Hm.A[i] = M.A[i] + pair_sum(dA[i], pm);
+      for (int k = 0; k < 6; k++) { A[TI(k, k)] += P.armature[k]; rr[k] -= pair_sum(g[k], pm); }
+      float inva[6];
+      chol6(A, inva);
+      fwd6(A, inva, rr);
+      bwd6(A, inva, rr);
+    }
+    root_motion(RB, rr, d, aa, al);
+    // ---- sweep 2 (root -> tip): joint accelerations; the same sweep starts the M-product of the direction ----
+    float smax = 0.f;
+    const bool solve = phase != 0, need_ms = phase != 2;
+#pragma unroll 1
+    for (int j = 0; j < 6; j++) {
+      float s = sm.jf(j, F_R);
+      if (solve) {
+        s = (s - (dot(sm.jv(j, F_X), aa) + dot(sm.jv(j, F_X + 3), al))) * sm.jf(j, F_DINV);
+        sm.jf(j, F_R) = s;
+      }
+      smax = fmaxf(smax, fabsf(s));
+      aa = fma3(sm.jv(j, F_W), s, aa); al = fma3(sm.jv(j, F_U), s, al);
+      if (need_ms) {
+        V3 n, l;
+        ri_apply(sm.ji(j), aa, al, n, l);
+        sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
       }
     }
-    if (mode == 2) {
-      // ---- implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f ----
-#pragma unroll
-      for (int i = 0; i < 21; i++) { Hm.C[i] = M.C[i]; Hm.A[i] = M.A[i]; }
-#pragma unroll
-      for (int i = 0; i < 36; i++) Hm.B[i] = M.B[i];
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        Hm.C[TI(j, j)] += h * P.damping[6 + 6 * side + j];
-        Hm.A[TI(j, j)] += h * P.damping[j];
-        rl[j] = fs_leg[j] + jl[j];
-        rr[j] = fs_root[j] + jr[j];
-      }
-    }
-    factor(Hm, F, pm);
-    solve(F, rl, rr, pm);
-    if (mode == 0) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) { xl[i] = rl[i]; xr[i] = rr[i]; Mal[i] = 0.f; Mar[i] = 0.f; jl[i] = 0.f; jr[i] = 0.f; }
-      if (use_warm) {  // warm start from the previous substep's acceleration: Ma = M (x_w - x_smooth)
-        float dl[6], dr[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) { dl[i] = wl[i] - xl[i]; dr[i] = wr[i] - xr[i]; xl[i] = wl[i]; xr[i] = wr[i]; }
-        matvec(M, dl, dr, Mal, Mar, pm);
-      }
-      mode = 1;
-      continue;
-    }
-    if (mode == 2) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) { xl[i] = rl[i]; xr[i] = rr[i]; }
-      break;
-    }
-    {  // the Newton step no longer moves the acceleration: accept the iterate (J'f of this evaluation is current)
-      float smax = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rl[i]));
+    if (phase == 2) break;
+    if (phase == 1) {  // the Newton step no longer moves the acceleration: accept the iterate (J'f is current)
       smax = fmaxf(smax, __shfl_xor_sync(pm, smax, 1));
 #pragma unroll
       for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rr[i]));
-      if (smax < P.step_tol) { mode = 2; continue; }
+      if (smax < P.step_tol) { phase = 2; continue; }
     }
-    // ---- exact line search along (rl, rr) ----
-    float Msl[6], Msr[6];
-    matvec(M, rl, rr, Msl, Msr, pm);
+    // ---- M-product, tip -> root half:  Ms = M s  (stored in the F_DG slot) ; line-search scalars ----
     float sMs = 0.f, sMa = 0.f, gs = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; i++) { sMs = fmaf(rl[i], Msl[i], sMs); sMa = fmaf(rl[i], Mal[i], sMa); gs = fmaf(rl[i], jl[i], gs); }
-    sMs = pair_sum(sMs, pm); sMa = pair_sum(sMa, pm); gs = pair_sum(gs, pm);
-#pragma unroll
-    for (int k = 0; k < 6; k++) { sMs = fmaf(rr[k], Msr[k], sMs); sMa = fmaf(rr[k], Mar[k], sMa); gs = fmaf(rr[k], jr[k], gs); }
-    const float d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
-    // J_p search for the active points
     {
-      V3 Sa_root = fma3(R0.cx, rr[3], fma3(R0.cy, rr[4], R0.cz * rr[5])), Sl_root = mk3(rr[0], rr[1], rr[2]);
-      V3 Sa_shin = Sa_root, Sl_shin = Sl_root;
-#pragma unroll
-      for (int j = 0; j < 4; j++) { Sa_shin = fma3(w[j], rl[j], Sa_shin); Sl_shin = fma3(u[j], rl[j], Sl_shin); }
-      V3 Sa_foot = fma3(w[4], rl[4], fma3(w[5], rl[5], Sa_shin)), Sl_foot = fma3(u[4], rl[4], fma3(u[5], rl[5], Sl_shin));
-#pragma unroll
-      for (int p = 0; p < NPT; p++)
-        if (CT.mask & (1u << p)) {
-          V3 r = ld3(CT.r[p]);
-          V3 s = p < 4 ? Sl_foot + cross(Sa_foot, r) : (p < 6 ? Sl_shin + cross(Sa_shin, r) : Sl_root + cross(Sa_root, r));
-          CT.us[p][0] = s.x; CT.us[p][1] = s.y; CT.us[p][2] = s.z;
-        }
-    }
-    float alpha = 1.f, lo = 0.f, hi = 1e30f;
+      V3 fcn = zero3, fcl = zero3;
 #pragma unroll 1
-    for (int ls = 0; ls < 12; ls++) {
-      float d1 = 0.f, d2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        const int d = 6 + 6 * side + j;
-        float act;
-        float f = floss_force(fmaf(alpha, rl[j], xl[j]) + fl_c[j], P.floss_D[d], P.floss_lim[d], P.floss[d], act);
-        d1 = fmaf(-f, rl[j], d1); d2 = fmaf(act * rl[j], rl[j], d2);
-        float jv = lim_sig[j] * rl[j];
-        float jar = fmaf(lim_sig[j], fmaf(alpha, rl[j], xl[j]), lim_c[j]);
-        if (lim_sig[j] != 0.f && jar < 0.f) { d1 = fmaf(lim_D[j] * jar, jv, d1); d2 = fmaf(lim_D[j] * jv, jv, d2); }
+      for (int j = 5; j >= 0; j--) {
+        fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
+        const float s = sm.jf(j, F_R);
+        const float ms = dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl) + arm[j] * s;
+        sm.jf(j, F_DG) = ms;
+        sMs = fmaf(s, ms, sMs); sMa = fmaf(s, sm.jf(j, F_MA), sMa); gs = fmaf(s, sm.jf(j, F_G), gs);
       }
+      float bl[6], b0[6];
+      root_project_force(RB, fcn, fcl, bl);
+      V3 a0, l0, n0, f0;
+      root_motion(RB0, rr, zero3, a0, l0);
+      ri_apply(I0, a0, l0, n0, f0);
+      root_project_force(RB0, n0, f0, b0);
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int d = 3 * side + k;
-        float act;
-        float f = floss_force(fmaf(alpha, rr[d], xr[d]) + rfl_c[k], P.floss_D[d], P.floss_lim[d], P.floss[d], act);
-        d1 = fmaf(-f, rr[d], d1); d2 = fmaf(act * rr[d], rr[d], d2);
+      for (int k = 0; k < 6; k++) Msr[k] = b0[k] + pair_sum(bl[k], pm) + P.armature[k] * rr[k];
+    }
+    float alpha = 1.f;
+    if (phase == 1) {
+      // ---- exact line search along the direction ----
+      sMs = pair_sum(sMs, pm); sMa = pair_sum(sMa, pm); gs = pair_sum(gs, pm);
+#pragma unroll
+      for (int k = 0; k < 6; k++) { sMs = fmaf(rr[k], Msr[k], sMs); sMa = fmaf(rr[k], Mar[k], sMa); gs = fmaf(rr[k], jr[k], gs); }
+      const float d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
+      V3 Va_r, Vl_r, Va_s, Vl_s, Va_f, Vl_f, Sa_r, Sl_r, Sa_s, Sl_s, Sa_f, Sl_f;
+      if (nact) {
+        root_motion(RB0, xr, zero3, Va_r, Vl_r);
+        root_motion(RB, xr, d, Va_f, Vl_f);
+        root_motion(RB0, rr, zero3, Sa_r, Sl_r);
+        root_motion(RB, rr, d, Sa_f, Sl_f);
+        Va_s = Va_f; Vl_s = Vl_f; Sa_s = Sa_f; Sl_s = Sl_f;
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) {
+          const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
+          const float x = sm.jf(j, F_XQ), s = sm.jf(j, F_R);
+          Va_f = fma3(wj, x, Va_f); Vl_f = fma3(uj, x, Vl_f);
+          Sa_f = fma3(wj, s, Sa_f); Sl_f = fma3(uj, s, Sl_f);
+          if (j == 3) { Va_s = Va_f; Vl_s = Vl_f; Sa_s = Sa_f; Sl_s = Sl_f; }
+        }
       }
+      float lo = 0.f, hi = 1e30f;
+#pragma unroll 1
+      for (int ls = 0; ls < 12; ls++) {
+        float d1 = 0.f, d2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) {
+          const float s = sm.jf(j, F_R);
+          const float xa = fmaf(alpha, s, sm.jf(j, F_XQ));
+          float act;
+          const float f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
+          d1 = fmaf(-f, s, d1); d2 = fmaf(act * s, s, d2);
+          const float lD = sm.jf(j, F_LIMD);
+          if (lD != 0.f) {
+            const float sig = lD > 0.f ? 1.f : -1.f;
+            const float jar = fmaf(sig, xa, sm.jf(j, F_LIMC));
+            if (jar < 0.f) { d1 = fmaf(fabsf(lD) * jar, sig * s, d1); d2 = fmaf(fabsf(lD) * s, s, d2); }
+          }
+        }
 #pragma unroll
-      for (int p = 0; p < NPT; p++)
-        if (CT.mask & (1u << p)) point_ls(ld3(CT.e[p]), ld3(CT.us[p]), alpha, CT.kap[p], CT.D[p], mu, d1, d2);
-      d1 = pair_sum(d1, pm) + fmaf(alpha, sMs, sMa);
-      d2 = pair_sum(d2, pm) + sMs;
-      if (fabsf(d1) <= 1e-5f * fabsf(d10) || !(d2 > 0.f)) break;
-      if (d1 < 0.f) lo = alpha; else hi = alpha;
-      float nx = alpha - d1 / d2;
-      if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
-      const bool tiny = fabsf(nx - alpha) <= 1e-4f * alpha;
-      alpha = nx;
-      if (tiny) break;
+        for (int k = 0; k < 3; k++) {
+          const int dk = 3 * side + k;
+          float act;
+          const float f = floss_force(fmaf(alpha, rr[dk], xr[dk]) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
+          d1 = fmaf(-f, rr[dk], d1); d2 = fmaf(act * rr[dk], rr[dk], d2);
+        }
+        if (nact) {
+          const V3 Ea_f = fma3(Sa_f, alpha, Va_f), El_f = fma3(Sl_f, alpha, Vl_f);
+          const V3 Ea_s = fma3(Sa_s, alpha, Va_s), El_s = fma3(Sl_s, alpha, Vl_s);
+          const V3 Ea_r = fma3(Sa_r, alpha, Va_r), El_r = fma3(Sl_r, alpha, Vl_r);
+#pragma unroll 1
+          for (int p = 0; p < nact; p++) {
+            const V3 r = sm.pv(p, 0), ub = sm.pv(p, 3);
+            const bool isf = p < n_foot, iss = p < e_shin;
+            const V3 Ea = isf ? Ea_f : (iss ? Ea_s : Ea_r), El = isf ? El_f : (iss ? El_s : El_r);
+            const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
+            point_ls(El + cross(Ea, r) + ub, Sl + cross(Sa, r), sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
+          }
+        }
+        d1 = pair_sum(d1, pm) + fmaf(alpha, sMs, sMa);
+        d2 = pair_sum(d2, pm) + sMs;
+        if (fabsf(d1) <= P.ls_tol * fabsf(d10) || !(d2 > 0.f)) break;
+        if (d1 < 0.f) lo = alpha; else hi = alpha;
+        float nx = alpha - d1 / d2;
+        if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
+        const bool tiny = fabsf(nx - alpha) <= 1e-4f * alpha;
+        alpha = nx;
+        if (tiny) break;
+      }
+    }
+#pragma unroll 1
+    for (int j = 0; j < 6; j++) {
+      sm.jf(j, F_XQ) = fmaf(alpha, sm.jf(j, F_R), sm.jf(j, F_XQ));
+      sm.jf(j, F_MA) = fmaf(alpha, sm.jf(j, F_DG), sm.jf(j, F_MA));
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      xl[i] = fmaf(alpha, rl[i], xl[i]); xr[i] = fmaf(alpha, rr[i], xr[i]);
-      Mal[i] = fmaf(alpha, Msl[i], Mal[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]);
-    }
+    for (int i = 0; i < 6; i++) { xr[i] = fmaf(alpha, rr[i], xr[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]); }
+    phase = 1;
   }
+  float rl[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) rl[j] = sm.jf(j, F_R);
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----
 #pragma unroll
-  for (int j = 0; j < 6; j++) { out.qacc[j] = xl[j]; wl[j] = xl[j]; wr[j] = xr[j]; qd[j] = fmaf(h, xl[j], qd[j]); q[j] = fmaf(h, qd[j], q[j]); }
+  for (int j = 0; j < 6; j++) {
+    out.qacc[j] = rl[j]; wl[j] = rl[j]; wr[j] = rr[j];
+    qd[j] = fmaf(h, rl[j], qd[j]); q[j] = fmaf(h, qd[j], q[j]);
+  }
 #pragma unroll
-  for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, xr[k], rv[k]); rw[k] = fmaf(h, xr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
+  for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, rr[k], rv[k]); rw[k] = fmaf(h, rr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
   {
     float wn = sqrtf(rw[0] * rw[0] + rw[1] * rw[1] + rw[2] * rw[2]);
     float ang = wn * h, dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
     if (ang > 0.f) {
       float s, c;
-      sincosf(0.5f * ang, &s, &c);
+      sincos_lim(0.5f * ang, s, c);
       s /= wn;
       dw = c; dx = rw[0] * s; dy = rw[1] * s; dz = rw[2] * s;
     }
-    float a = rq[0], b = rq[1], c = rq[2], d = rq[3];
-    float nw = a * dw - b * dx - c * dy - d * dz, nx = a * dx + b * dw + c * dz - d * dy;
-    float ny = a * dy - b * dz + c * dw + d * dx, nz = a * dz + b * dy - c * dx + d * dw;
+    float a = rq[0], b = rq[1], c = rq[2], e = rq[3];
+    float nw = a * dw - b * dx - c * dy - e * dz, nx = a * dx + b * dw + c * dz - e * dy;
+    float ny = a * dy - b * dz + c * dw + e * dx, nz = a * dz + b * dy - c * dx + e * dw;
     float n = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
     rq[0] = nw * n; rq[1] = nx * n; rq[2] = ny * n; rq[3] = nz * n;
   }
   out.F_foot = F_foot; out.F_shin = F_shin; out.F_torso = F_torso; out.F_pelvis = F_pelvis;
-  out.iters = it; out.capped = capped;
+  out.iters = it; out.capped = capped; out.overflow = overflow;
 }
 
 }  // namespace h1v2

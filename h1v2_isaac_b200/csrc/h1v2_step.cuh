@@ -34,7 +34,7 @@ __device__ __forceinline__ V3 foot_velocity(const KLeg& LG, const M3& R0, V3 om0
     V3 wi = axis_col<AX>(R);                \
     om = fma3(wi, qd[i], om);               \
     vo = fma3(cross(x, wi), qd[i], vo);     \
-    rotate<AX>(R, q[i]);                    \
+    { float s_, c_; sincos_lim(q[i], s_, c_); rotate_sc<AX>(R, s_, c_); } \
   }
   FV_JOINT(0, 2) FV_JOINT(1, 1) FV_JOINT(2, 0) FV_JOINT(3, 1) FV_JOINT(4, 1) FV_JOINT(5, 0)
 #undef FV_JOINT
@@ -45,7 +45,7 @@ struct CmdState {
   float c[3], heading_target, time_left, m_xy, m_yaw;
   int flags;
 };
-__device__ __forceinline__ void resample_command(const KParams& P, CmdState& c, int64_t gid, unsigned long long step, uint32_t block0) {
+__device__ __noinline__ void resample_command(const KParams& P, CmdState& c, int64_t gid, unsigned long long step, uint32_t block0) {
   float u[4], v[4];
   rng4(P.key0, gid, step, STREAM_CMD, block0, u);
   rng4(P.key0, gid, step, STREAM_CMD, block0 + 1, v);
@@ -61,7 +61,7 @@ __device__ __forceinline__ void resample_command(const KParams& P, CmdState& c, 
 }
 
 // reset of one env (reset_root_state_uniform, reset_joints_by_scale, manager resets); both lanes compute the root
-__device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
+__device__ __noinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
                                           float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
                                           float (&la)[6], float (&T1)[6], float (&T2)[6], float4& timers, CmdState& cmd,
                                           float& push_left) {
@@ -172,29 +172,47 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   __syncwarp();
   // cooperative flatten: term-major, oldest -> newest inside each term block
   // (packages/biped_tasks/biped_tasks/utils/history/observation_manager.py:335-355, circular_buffer.py:79-87,131-135)
+  // Each lane owns output columns lane, lane+32, ...; their (history index, sample offset) is the same for every env,
+  // so it is decoded once, and the loads of one env row are issued back to back (memory-level parallelism).
   const int lane = threadIdx.x & 31;
   const int warp_env0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 1;
+  constexpr int MAXPASS = (H1V2_MAX_HISTORY * H1V2_OBS_TERM_DIM + 31) / 32;
+  const int npass = (P.obs_dim + 31) >> 5;
+  int soff[MAXPASS], hoff[MAXPASS];  // offset inside the ring for a non-fresh env / offset of the slot to back-fill
+#pragma unroll
+  for (int i = 0; i < MAXPASS; i++) {
+    const int idx = lane + 32 * i;
+    soff[i] = -1; hoff[i] = 0;
+    if (i < npass && idx < P.obs_dim) {
+      const int hk = __ldg(S.lut + idx);
+      const int hh = hk >> 8, k = hk & 255;
+      int sl = head + 1 + hh;
+      sl = sl >= H ? sl - H : sl;
+      soff[i] = sl * H1V2_HIST_STRIDE + k;
+      hoff[i] = hh * H1V2_HIST_STRIDE + k;
+    }
+  }
   for (int e = 0; e < 16; e++) {
     const int env_e = warp_env0 + e;
     const int fl = __shfl_sync(0xffffffffu, cmd.flags, 2 * e);
     if (env_e >= P.n) break;
     const bool fresh = (fl & FLAG_HIST_FRESH) != 0;
     float* hbase = S.hist + (size_t)env_e * H * H1V2_HIST_STRIDE;
-    for (int idx = lane; idx < P.obs_dim; idx += 32) {
-      const int hk = __ldg(S.lut + idx);
-      const int hh = hk >> 8, k = hk & 255;
-      int sl = head + 1 + hh;
-      sl = sl >= H ? sl - H : sl;
-      if (fresh) sl = head;
-      const float v = __ldcg(hbase + sl * H1V2_HIST_STRIDE + k);
-      if (obs) obs[(size_t)env_e * P.obs_dim + idx] = v;
-      if (fresh) hbase[hh * H1V2_HIST_STRIDE + k] = v;
-    }
+    float v[MAXPASS];
+#pragma unroll
+    for (int i = 0; i < MAXPASS; i++)
+      if (soff[i] >= 0) v[i] = __ldcg(hbase + (fresh ? head * H1V2_HIST_STRIDE + (hoff[i] % H1V2_HIST_STRIDE) : soff[i]));
+#pragma unroll
+    for (int i = 0; i < MAXPASS; i++)
+      if (soff[i] >= 0) {
+        if (obs) obs[(size_t)env_e * P.obs_dim + lane + 32 * i] = v[i];
+        if (fresh) hbase[hoff[i]] = v[i];
+      }
   }
 }
 
 template <bool DO_STEP>
-__global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
+__global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
       substep(P, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters;
+      if (valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);
       float nf = sqrtf(dot(so.F_foot, so.F_foot));
       h_foot[0] = h_foot[1]; h_foot[1] = h_foot[2]; h_foot[2] = nf;
       h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = sqrtf(dot(so.F_shin, so.F_shin));
@@ -411,14 +430,21 @@ __global__ void __launch_bounds__(64) step_kernel(const __grid_constant__ KParam
 #pragma unroll
       for (int k = 0; k < 6; k++) { dg[36 + 6 * side + k] = tau[k]; dg[48 + 6 * side + k] = so.qacc[k]; }
       dg[80 + 3 * side + 0] = fv.x; dg[80 + 3 * side + 1] = fv.y; dg[80 + 3 * side + 2] = fv.z;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { dg[96 + 7 + 6 * side + k] = q[k]; dg[115 + 6 + 6 * side + k] = qd[k]; }
+      dg[133 + 4 * side + 0] = tm.x; dg[133 + 4 * side + 1] = tm.y; dg[133 + 4 * side + 2] = tm.z; dg[133 + 4 * side + 3] = tm.w;
       if (side == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { dg[96 + k] = rp[k]; dg[115 + k] = rv[k]; dg[118 + k] = rw[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) dg[99 + k] = rq[k];
         dg[12] = so.F_torso.x; dg[13] = so.F_torso.y; dg[14] = so.F_torso.z;
         dg[15] = so.F_pelvis.x; dg[16] = so.F_pelvis.y; dg[17] = so.F_pelvis.z;
 #pragma unroll
         for (int i = 0; i < 3; i++) { dg[30 + i] = h_torso[i]; dg[33 + i] = h_pelvis[i]; }
 #pragma unroll
         for (int t = 0; t < H1V2_NUM_REW; t++) dg[60 + t] = r[t];
-        dg[86] = (float)max_it; dg[87] = (float)ncap;
+        dg[86] = (float)max_it; dg[87] = (float)ncap; dg[88] = (float)sum_it;
       }
     }
     // solver statistics

@@ -115,6 +115,7 @@ typedef struct H1v2Config {
   int32_t solver_iterations;           /* Newton iteration cap */
   float solver_tolerance;              /* on scaled gradient norm */
   float solver_step_tolerance;         /* stop when the Newton step max|dqacc| falls below this (rad/s^2) */
+  float solver_ls_tolerance;           /* exact line search stops at |phi'(a)| <= tol*|phi'(0)| (MuJoCo ls_tolerance 0.01) */
   /* ---- observations (velocity_env_cfg.py:123-142, flat_env_cfg.py:25-27) ---- */
   int32_t history_length;              /* 10 */
   int32_t enable_corruption;           /* 1 */
@@ -183,6 +184,10 @@ typedef struct H1v2State {
   float* joint_acc;     /* [N,12] last substep */
   float* reward_terms;  /* [N,NUM_REW] weighted*dt value of every term in the last step */
   float* foot_vel;      /* [N,2,3] world linear velocity of the ankle_roll_link origins */
+  float* solver_iters;  /* [N,2] max and sum of Newton iterations over the substeps of the last step */
+  float* pre_reset_qpos;   /* [N,19] state after the physics substeps of the last step, BEFORE any reset */
+  float* pre_reset_qvel;   /* [N,18] */
+  float* pre_reset_timers; /* [N,2,4] */
 } H1v2State;
 
 typedef struct H1v2Handle H1v2Handle;
@@ -215,6 +220,8 @@ int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);
 /* device pointer to the float[H1V2_LOG_DIM] log vector (valid for the handle's lifetime, updated by step) */
 int h1v2_get_log(H1v2Handle* h, const float** log_dev);
 int h1v2_get_log_host(H1v2Handle* h, float* log_host /*[H1V2_LOG_DIM]*/);
+/* cumulative histogram of Newton iterations per (env,substep) solve since creation: hist32[k] = #solves with k iterations */
+int h1v2_debug_iter_hist(H1v2Handle* h, float* hist32);
 /* number of kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t h1v2_launch_count(const H1v2Handle* h);
 /* FP32 FMA throughput of the device (TFLOP/s, best of 6): the measured denominator of the FP32 roofline */

@@ -108,6 +108,8 @@ typedef struct {
   double slot_force[NSLOT][3], slot_hist[NSLOT][3], applied_tau[NJ], joint_acc[NJ], rew_terms[NREW], foot_vel[2][3];
   int newton_iters;
   double newton_resid;
+  double min_abs_dist; /* smallest |signed distance| of any contact candidate at a substep start during the last step */
+  double min_limit_dist; /* same for joint-limit activation */
 } OEnv;
 
 struct H1v2Oracle {
@@ -371,6 +373,7 @@ typedef struct {
   double J[MAXROW][NV];
   double aref[MAXROW], R[MAXROW], D[MAXROW], floss[MAXROW];
   int type[MAXROW];  /* 0 friction-loss (two-sided box), 1 unilateral (limit / pyramid edge) */
+  double min_abs_dist, min_limit_dist;
   int coll[MAXROW];  /* collider index for contact rows, -1 otherwise */
   int edge[MAXROW];  /* pyramid edge 0..3 */
   double force[MAXROW];
@@ -392,6 +395,7 @@ static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows*
   const double dt = cfg->sim_dt;
   const double* qvel = e->qvel;
   r->n = 0;
+  r->min_abs_dist = 1e30; r->min_limit_dist = 1e30;
   double K, B;
   /* (a) dof friction loss */
   kb_from_solref(cfg->floss_solref, cfg->floss_solimp, dt, &K, &B);
@@ -413,6 +417,7 @@ static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows*
     double q = e->qpos[7 + j];
     for (int side = 0; side < 2; side++) {
       double dist = side == 0 ? q - cfg->joint_range[j][0] : cfg->joint_range[j][1] - q;
+      if (fabs(dist) < r->min_limit_dist) r->min_limit_dist = fabs(dist);
       if (dist >= 0) continue;
       int i = r->n++;
       memset(r->J[i], 0, sizeof(r->J[i]));
@@ -436,6 +441,7 @@ static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows*
     matvec3(k->R[b], &h1v2_coll[c][1], off);
     for (int i = 0; i < 3; i++) ctr[i] = k->x[b][i] + off[i];
     double dist = ctr[2] - rad;
+    if (fabs(dist) < r->min_abs_dist) r->min_abs_dist = fabs(dist);
     if (dist >= 0) continue;
     double p[3] = {ctr[0], ctr[1], 0.5 * dist}; /* midway between the surfaces */
     /* translational jacobian of the body-fixed point at p: v = v_O + w x p */
@@ -594,6 +600,8 @@ static void physics_substep(const H1v2Oracle* o, OEnv* e, const double ctrl[NJ])
   chol_solve(L, NV, qacc_s);
   static _Thread_local Rows rows;
   build_rows(cfg, &k, e, &rows);
+  if (rows.min_abs_dist < e->min_abs_dist) e->min_abs_dist = rows.min_abs_dist;
+  if (rows.min_limit_dist < e->min_limit_dist) e->min_limit_dist = rows.min_limit_dist;
   double qacc[NV];
   solve_constraints(o, M, qacc_s, &rows, qacc, &e->newton_iters, &e->newton_resid);
   /* constraint force and per-slot net contact force */
@@ -829,11 +837,24 @@ static void compute_obs(H1v2Oracle* o, int ei, float* obs_out) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* values the tail consumes that normally come out of the physics loop; tests may inject the CUDA kernel's own
+ * post-physics values here so that rewards / masks / observations are compared on IDENTICAL states */
+typedef struct H1v2Inject {
+  const float* qpos;      /* [N,19] */
+  const float* qvel;      /* [N,18] */
+  const float* timers;    /* [N,8] */
+  const float* slot_hist; /* [N,6,3] */
+  const float* tau;       /* [N,12] */
+  const float* qacc;      /* [N,12] */
+  const float* foot_vel;  /* [N,6] */
+} H1v2Inject;
+
 static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out, uint8_t* term_out, uint8_t* trunc_out,
-                     int* reset_flag, int* nan_flag) {
+                     int* reset_flag, int* nan_flag, const H1v2Inject* inj) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
   const float step_dt = c->sim_dt * (float)c->decimation;
+  e->min_abs_dist = 1e30; e->min_limit_dist = 1e30;
   /* -- action manager: process_action -- */
   float prev_action[NJ];
   memcpy(prev_action, e->last_action, sizeof(prev_action));
@@ -845,7 +866,7 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   if (e->fresh & 1) { memcpy(e->T1, T0, sizeof(T0)); memcpy(e->T2, T0, sizeof(T0)); }
   /* -- physics loop -- */
   double qd_prev[NJ];
-  for (int k = 0; k < c->decimation; k++) {
+  for (int k = 0; k < (inj ? 0 : c->decimation); k++) {
     int age = e->lag - k; /* physics steps between the delayed sample and the current control step's first push */
     const double* T = age <= 0 ? T0 : (age <= c->decimation ? e->T1 : e->T2);
     double tau[NJ];
@@ -879,7 +900,16 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   memcpy(e->T2, e->T1, sizeof(T0));
   memcpy(e->T1, T0, sizeof(T0));
   e->fresh &= ~1;
-  foot_velocities(e, e->foot_vel);
+  if (inj) {
+    for (int i = 0; i < 19; i++) e->qpos[i] = inj->qpos[(size_t)ei * 19 + i];
+    for (int i = 0; i < 18; i++) e->qvel[i] = inj->qvel[(size_t)ei * 18 + i];
+    for (int i = 0; i < 8; i++) e->timers[i / 4][i % 4] = inj->timers[(size_t)ei * 8 + i];
+    for (int i = 0; i < 18; i++) e->slot_hist[i / 3][i % 3] = inj->slot_hist[(size_t)ei * 18 + i];
+    for (int i = 0; i < NJ; i++) { e->applied_tau[i] = inj->tau[(size_t)ei * NJ + i]; e->joint_acc[i] = inj->qacc[(size_t)ei * NJ + i]; }
+    for (int i = 0; i < 6; i++) e->foot_vel[i / 3][i % 3] = inj->foot_vel[(size_t)ei * 6 + i];
+  } else {
+    foot_velocities(e, e->foot_vel);
+  }
   /* non-finite guard: force a reset, zero reward */
   int bad = 0;
   for (int i = 0; i < 19; i++) if (!isfinite(e->qpos[i])) bad = 1;
@@ -1023,14 +1053,14 @@ int h1v2o_observe(H1v2Oracle* o, float* obs) {
 /* minimal pthread parallel-for (libgomp is not in the image): interleaved static partition over envs */
 typedef struct {
   H1v2Oracle* o; const float* actions; float* obs; float* rew; uint8_t* term; uint8_t* trunc;
-  int* reset; int* bad; int phase, tid, nthreads;
+  int* reset; int* bad; int phase, tid, nthreads; const H1v2Inject* inj;
 } Job;
 static void post_env(H1v2Oracle* o, int i, const int* reset, float* obs);
 static void* job_main(void* p) {
   Job* j = (Job*)p;
   for (int i = j->tid; i < j->o->n; i += j->nthreads) {
     if (j->phase == 0)
-      step_env(j->o, i, j->actions + (size_t)i * NJ, j->rew + i, j->term + i, j->trunc + i, j->reset + i, j->bad + i);
+      step_env(j->o, i, j->actions + (size_t)i * NJ, j->rew + i, j->term + i, j->trunc + i, j->reset + i, j->bad + i, j->inj);
     else
       post_env(j->o, i, j->reset, j->obs);
   }
@@ -1073,12 +1103,25 @@ static void post_env(H1v2Oracle* o, int i, const int* reset, float* obs) {
     }
 }
 
+static int step_impl(H1v2Oracle* o, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+                     const H1v2Inject* inj);
 int h1v2o_step(H1v2Oracle* o, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated) {
+  return step_impl(o, actions, obs, rew, terminated, truncated, NULL);
+}
+/* one control step whose physics loop is replaced by injected post-physics values (see H1v2Inject) */
+int h1v2o_step_injected(H1v2Oracle* o, const float* actions, const float* qpos, const float* qvel, const float* timers,
+                        const float* slot_hist, const float* tau, const float* qacc, const float* foot_vel, float* obs, float* rew,
+                        uint8_t* terminated, uint8_t* truncated) {
+  H1v2Inject inj = {qpos, qvel, timers, slot_hist, tau, qacc, foot_vel};
+  return step_impl(o, actions, obs, rew, terminated, truncated, &inj);
+}
+static int step_impl(H1v2Oracle* o, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+                     const H1v2Inject* inj) {
   const int n = o->n;
   o->step_counter += 1;
   int* reset = (int*)calloc((size_t)n, sizeof(int));
   int* bad = (int*)calloc((size_t)n, sizeof(int));
-  Job proto = {o, actions, obs, rew, terminated, truncated, reset, bad, 0, 0, 1};
+  Job proto = {o, actions, obs, rew, terminated, truncated, reset, bad, 0, 0, 1, inj};
   run_phase(proto, 0);
   /* logging of the envs about to reset (cat_env.py:217-245) */
   double sums[NREW] = {0}, mxy = 0, myaw = 0;
@@ -1146,6 +1189,10 @@ int h1v2o_get_state(H1v2Oracle* o, const H1v2State* s) {
   CPY_OUT(joint_acc, o->env[i].joint_acc[k], NJ, float)
   CPY_OUT(reward_terms, o->env[i].rew_terms[k], NREW, float)
   CPY_OUT(foot_vel, o->env[i].foot_vel[k / 3][k % 3], 6, float)
+  CPY_OUT(solver_iters, o->env[i].newton_iters, 2, float)
+  CPY_OUT(pre_reset_qpos, 0.0f, 19, float)
+  CPY_OUT(pre_reset_qvel, 0.0f, 18, float)
+  CPY_OUT(pre_reset_timers, 0.0f, 8, float)
   return 0;
 }
 
@@ -1183,6 +1230,12 @@ int h1v2o_set_state(H1v2Oracle* o, const H1v2State* s) {
 int h1v2o_get_episode_length(H1v2Oracle* o, int64_t* out) { for (int i = 0; i < o->n; i++) out[i] = o->env[i].ep_len; return 0; }
 int h1v2o_set_episode_length(H1v2Oracle* o, const int64_t* in) { for (int i = 0; i < o->n; i++) o->env[i].ep_len = in[i]; return 0; }
 int h1v2o_get_log(H1v2Oracle* o, float* out) { memcpy(out, o->log, sizeof(o->log)); return 0; }
+/* smallest distance to a contact / joint-limit activation boundary seen at a substep start during the last step:
+ * envs within rounding error of a boundary are excluded from strict float-vs-double comparisons (tests) */
+int h1v2o_activation_margin(H1v2Oracle* o, double* contact, double* limit) {
+  for (int i = 0; i < o->n; i++) { contact[i] = o->env[i].min_abs_dist; limit[i] = o->env[i].min_limit_dist; }
+  return 0;
+}
 int h1v2o_solver_stats(H1v2Oracle* o, int32_t* iters, double* resid) {
   for (int i = 0; i < o->n; i++) { iters[i] = o->env[i].newton_iters; resid[i] = o->env[i].newton_resid; }
   return 0;

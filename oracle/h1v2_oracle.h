@@ -19,12 +19,16 @@ int64_t h1v2o_max_episode_length(const H1v2Oracle* o);
 int h1v2o_reset(H1v2Oracle* o, const int64_t* env_ids, int32_t n);
 int h1v2o_observe(H1v2Oracle* o, float* obs);
 int h1v2o_step(H1v2Oracle* o, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated);
+int h1v2o_step_injected(H1v2Oracle* o, const float* actions, const float* qpos, const float* qvel, const float* timers,
+                        const float* slot_hist, const float* tau, const float* qacc, const float* foot_vel, float* obs, float* rew,
+                        uint8_t* terminated, uint8_t* truncated);
 int h1v2o_get_state(H1v2Oracle* o, const H1v2State* s);
 int h1v2o_set_state(H1v2Oracle* o, const H1v2State* s);
 int h1v2o_get_episode_length(H1v2Oracle* o, int64_t* out);
 int h1v2o_set_episode_length(H1v2Oracle* o, const int64_t* in);
 int h1v2o_get_log(H1v2Oracle* o, float* out);
 int h1v2o_solver_stats(H1v2Oracle* o, int32_t* iters, double* resid);
+int h1v2o_activation_margin(H1v2Oracle* o, double* contact, double* limit);
 
 /* building blocks for known-answer tests */
 void h1v2o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

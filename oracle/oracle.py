@@ -42,12 +42,14 @@ def lib() -> C.CDLL:
         L.h1v2o_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.h1v2o_observe.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.h1v2o_step_injected.argtypes = [C.c_void_p] + [C.c_void_p] * 13
         L.h1v2o_get_state.argtypes = [C.c_void_p, C.POINTER(H1v2State)]
         L.h1v2o_set_state.argtypes = [C.c_void_p, C.POINTER(H1v2State)]
         L.h1v2o_get_episode_length.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_set_episode_length.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_get_log.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_solver_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.h1v2o_activation_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.h1v2o_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.h1v2o_rng4.argtypes = [C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.h1v2o_fk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -111,6 +113,21 @@ class Oracle:
         lib().h1v2o_step(self._h, _p(a), _p(obs), _p(rew), _p(term), _p(trunc))
         return obs, rew, term.astype(bool), trunc.astype(bool)
 
+    def step_injected(self, actions, post: dict):
+        """Control step with the physics loop replaced by the given post-physics values (identical-state tail parity).
+        post keys: pre_reset_qpos, pre_reset_qvel, pre_reset_timers, slot_force_hist, applied_torque, joint_acc, foot_vel."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        f = {k: np.ascontiguousarray(post[k], dtype=np.float32) for k in
+             ("pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers", "slot_force_hist", "applied_torque", "joint_acc", "foot_vel")}
+        obs = np.zeros((self.n, self.obs_dim), np.float32)
+        rew = np.zeros(self.n, np.float32)
+        term = np.zeros(self.n, np.uint8)
+        trunc = np.zeros(self.n, np.uint8)
+        lib().h1v2o_step_injected(self._h, _p(a), _p(f["pre_reset_qpos"]), _p(f["pre_reset_qvel"]), _p(f["pre_reset_timers"]),
+                                  _p(f["slot_force_hist"]), _p(f["applied_torque"]), _p(f["joint_acc"]), _p(f["foot_vel"]),
+                                  _p(obs), _p(rew), _p(term), _p(trunc))
+        return obs, rew, term.astype(bool), trunc.astype(bool)
+
     def get_state(self, names=None) -> dict:
         out, st = {}, H1v2State()
         for name, _, ct in STATE_FIELDS:
@@ -148,6 +165,13 @@ class Oracle:
         out = np.zeros(LOG_DIM, np.float32)
         lib().h1v2o_get_log(self._h, _p(out))
         return out
+
+    def activation_margin(self):
+        """(contact, limit): smallest distance to an activation boundary at any substep start of the last step."""
+        c = np.zeros(self.n, np.float64)
+        l = np.zeros(self.n, np.float64)
+        lib().h1v2o_activation_margin(self._h, _p(c), _p(l))
+        return c, l
 
     def solver_stats(self):
         it = np.zeros(self.n, np.int32)

@@ -1,68 +1,246 @@
-"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on identical
-seeded states and actions.  Tolerances are BASELINE.json's: 1e-4 rad / 1e-3 rad/s for one control step of
-physics, bit-exact masks."""
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on identical seeded
+states and actions (BASELINE.json north_star (a)(b)(c)):
+  (a) reward and observation terms within 1e-5 relative on IDENTICAL post-physics states,
+  (b) termination / reset masks and command-resample masks bit-exact,
+  (c) physics within 1e-4 rad / 1e-3 rad/s for one physics step, bounded divergence over 1000 steps,
+plus size-independent properties at BASELINE's full sizes (4096 / 32768 envs).
+"""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
-PHYS_FIELDS = ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"]
-SYNC_FIELDS = PHYS_FIELDS + ["last_action", "target_hist", "lag", "fresh", "command", "heading_target", "time_left",
-                             "is_standing", "is_heading", "cmd_metrics", "feet_timers", "episode_sums", "obs_history",
-                             "friction", "mass_add", "push_time_left"]
+PHYS = ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"]
+SYNC = PHYS + ["last_action", "target_hist", "lag", "fresh", "command", "heading_target", "time_left", "is_standing",
+               "is_heading", "cmd_metrics", "feet_timers", "episode_sums", "obs_history", "friction", "mass_add",
+               "push_time_left"]
+POST = ["pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers", "slot_force_hist", "applied_torque", "joint_acc", "foot_vel"]
 
 
-def _mk(cfg, n, seed, **kw):
+def _mk(cfg, n, seed):
     import torch
     from h1v2_isaac_b200.backend import H1v2Sim
     from oracle.oracle import Oracle
-    sim = H1v2Sim(n, cfg, device="cuda:0", seed=seed, diagnostics=True)
-    orc = Oracle(cfg, n, seed=seed, threads=8)
-    return torch, sim, orc
+    return torch, H1v2Sim(n, cfg, device="cuda:0", seed=seed, diagnostics=True), Oracle(cfg, n, seed=seed, threads=16)
 
 
 def _np(d):
     return {k: v.detach().cpu().numpy() for k, v in d.items()}
 
 
+def _resync(sim, orc, g):
+    orc.set_state({k: g[k] for k in SYNC})
+    orc.episode_length = sim.episode_length_buf.cpu().numpy()
+
+
 def test_reset_state_matches_oracle(cfg):
+    """create/reset: Philox draws, root pose, joint pose, lag, command resample -- all from the same counter-based stream."""
     torch, sim, orc = _mk(cfg, 512, 11)
-    g, o = _np(sim.get_state(SYNC_FIELDS)), orc.get_state(SYNC_FIELDS)
-    for k in SYNC_FIELDS:
+    g, o = _np(sim.get_state(SYNC)), orc.get_state(SYNC)
+    for k in SYNC:
         if g[k].dtype.kind == "i":
             assert np.array_equal(g[k], o[k]), k
         else:
             np.testing.assert_allclose(g[k], o[k], rtol=0, atol=2e-6, err_msg=k)
-    go, oo = sim.observe().cpu().numpy(), orc.observe()
-    np.testing.assert_allclose(go, oo, rtol=0, atol=3e-6)
+    np.testing.assert_allclose(sim.observe().cpu().numpy(), orc.observe(), rtol=0, atol=3e-6)
+    # partial reset through the API
+    ids = np.array([3, 77, 500], np.int64)
+    sim.reset(torch.from_numpy(ids).cuda()); orc.reset(ids)
+    g, o = _np(sim.get_state(SYNC)), orc.get_state(SYNC)
+    for k in ("root_pos", "root_quat", "joint_pos", "command", "lag", "fresh"):
+        np.testing.assert_allclose(g[k], o[k], rtol=0, atol=2e-6, err_msg=k)
 
 
-def test_single_step_physics_parity(cfg):
-    """Each control step starts from the SAME state on both sides (the oracle is re-synchronised to the GPU state)."""
-    torch, sim, orc = _mk(cfg, 1024, 3)
+@pytest.mark.parametrize("decimation,tol_q,tol_v", [(1, 1e-4, 1e-3), (4, 1e-4, 4e-3)])
+def test_physics_parity_from_identical_states(cfg, decimation, tol_q, tol_v):
+    """(c): every control step starts from the SAME state on both sides (oracle re-synchronised to the GPU state).
+    decimation=1 is the single physics step of the north star (1e-4 rad, 1e-3 rad/s on EVERY env);
+    decimation=4 is a whole control step (4 chained substeps, fp32): 99.9 % within 1e-3 rad/s, all within 4e-3.
+    Envs within 2e-6 m of a contact (2e-6 rad of a joint-limit) activation boundary at a substep start are skipped:
+    MuJoCo's soft contact switches on discontinuously at dist = 0, so float-vs-double rounding decides those."""
+    c = cfg.copy()
+    c.decimation = decimation
+    c.max_delay = min(c.max_delay, 2 * decimation)
+    n = 2048
+    torch, sim, orc = _mk(c, n, 3)
     sim.observe(); orc.observe()
     rng = np.random.default_rng(0)
-    worst = {"joint_pos": 0.0, "joint_vel": 0.0, "root_pos": 0.0, "root_lin_vel": 0.0, "root_ang_vel": 0.0}
-    n_checked = 0
-    for step in range(40):
-        a = rng.normal(size=(1024, 12)).astype(np.float32)
-        obs_g, rew_g, term_g, trunc_g = sim.step(torch.from_numpy(a).cuda())
-        obs_o, rew_o, term_o, trunc_o = orc.step(a)
-        g = _np(sim.get_state(SYNC_FIELDS + ["slot_force_hist"]))
-        o = orc.get_state(SYNC_FIELDS + ["slot_force_hist"])
-        term_g, trunc_g = term_g.cpu().numpy(), trunc_g.cpu().numpy()
-        # masks: bit-exact except where a contact force sits within 1e-3 of the 1 N threshold
-        C = np.maximum(o["slot_force_hist"].reshape(-1, 6, 3).max(-1), 0)
-        near = (np.abs(C - cfg.contact_threshold) < 2e-2).any(-1)
-        assert np.array_equal(term_g[~near], term_o[~near]), f"terminated mask differs at step {step}"
-        assert np.array_equal(trunc_g, trunc_o)
-        keep = ~(term_o | trunc_o | term_g | near)  # envs that did not reset: compare the post-physics state
-        n_checked += int(keep.sum())
-        for k, tol in (("joint_pos", 1e-4), ("joint_vel", 1e-3), ("root_pos", 1e-4), ("root_lin_vel", 1e-3), ("root_ang_vel", 1e-3)):
-            err = np.abs(g[k][keep] - o[k][keep]).max() if keep.any() else 0.0
-            worst[k] = max(worst[k], float(err))
-            assert err < tol, f"{k} error {err} at step {step}"
-        orc.set_state(g)
-        orc.episode_length = sim.episode_length_buf.cpu().numpy()
-    print("worst single-step errors", worst, "env-steps checked", n_checked)
-    assert n_checked > 20000
+    errs = {k: [] for k in PHYS}
+    for step in range(24 * (4 // decimation)):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        _, _, to, uo = orc.step(a)
+        g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS)
+        mc, ml = orc.activation_margin()
+        keep = ~(to | uo | tg.cpu().numpy()) & (mc > 2e-6) & (ml > 2e-6)
+        for k in PHYS:
+            errs[k].append(np.abs(g[k][keep] - o[k][keep]).max(axis=1))
+        _resync(sim, orc, g)
+    e = {k: np.concatenate(v) for k, v in errs.items()}
+    print({k: (float(v.max()), float(np.quantile(v, 0.999))) for k, v in e.items()}, "env-steps", len(e["joint_pos"]))
+    assert len(e["joint_pos"]) > 0.8 * n * 24
+    for k in ("joint_pos", "root_pos", "root_quat"):
+        assert e[k].max() < tol_q, k
+    for k in ("joint_vel", "root_lin_vel", "root_ang_vel"):
+        assert e[k].max() < tol_v, k
+        assert np.quantile(e[k], 0.999) < 2e-3 and np.quantile(e[k], 0.99) < 1e-3, k
+
+
+def test_tail_parity_on_identical_states(cfg):
+    """(a)+(b): the oracle's physics loop is replaced by the kernel's own post-physics values, so everything after the
+    physics -- contact-sensor logic, terminations, 20 reward terms, reset, command resampling, noisy observation with
+    history -- is compared on identical inputs: masks bit-exact, values to 1e-5."""
+    n = 4096
+    torch, sim, orc = _mk(cfg, n, 21)
+    sim.observe(); orc.observe()
+    ep = np.random.default_rng(1).integers(0, 1000, n)  # rsl_rl's init_at_random_ep_len: exercises time-outs
+    sim.episode_length_buf.copy_(torch.from_numpy(ep).cuda()); orc.episode_length = ep
+    rng = np.random.default_rng(2)
+    n_term = n_trunc = n_resample = 0
+    for step in range(60):
+        a = (rng.normal(size=(n, 12)) * (0.3 if step % 3 else 1.0)).astype(np.float32)
+        og, rg, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        g = _np(sim.get_state(SYNC + POST + ["reward_terms"]))
+        oo, ro, to, uo = orc.step_injected(a, g)
+        o = orc.get_state(SYNC + ["reward_terms"])
+        tg, ug, og, rg = tg.cpu().numpy(), ug.cpu().numpy(), og.cpu().numpy(), rg.cpu().numpy()
+        # (b) masks bit-exact
+        assert np.array_equal(tg, to), f"terminated mask, step {step}"
+        assert np.array_equal(ug, uo), f"truncated mask, step {step}"
+        for k in ("is_standing", "is_heading", "lag", "fresh"):
+            assert np.array_equal(g[k], o[k]), f"{k}, step {step}"
+        assert np.array_equal(g["time_left"], o["time_left"]), "command resample mask (time_left is float32 on both sides)"
+        assert np.array_equal(sim.episode_length_buf.cpu().numpy(), orc.episode_length)
+        assert np.array_equal(g["feet_timers"], o["feet_timers"]), "contact-sensor air/contact timers"
+        # (a) values
+        np.testing.assert_allclose(g["reward_terms"], o["reward_terms"], rtol=1e-5, atol=2e-7, err_msg=f"reward terms, step {step}")
+        np.testing.assert_allclose(rg, ro, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(og, oo, rtol=1e-5, atol=2e-6, err_msg=f"observation, step {step}")
+        for k in ("command", "heading_target", "cmd_metrics", "episode_sums", "root_pos", "root_quat", "joint_pos", "target_hist"):
+            np.testing.assert_allclose(g[k], o[k], rtol=1e-5, atol=2e-6, err_msg=f"{k}, step {step}")
+        n_term += int(to.sum()); n_trunc += int(uo.sum()); n_resample += int((g["time_left"] > 9.97).sum())
+        lg, lo = sim.log_host(), orc.log()
+        assert lg[0] == lo[0] and lg[21] == lo[21] and lg[22] == lo[22]  # reset / time_out / base_contact counts
+        if lo[0] > 0:
+            np.testing.assert_allclose(lg[1:21], lo[1:21], rtol=2e-4, atol=1e-6)  # Episode_Reward/* (float atomics)
+            np.testing.assert_allclose(lg[23:25], lo[23:25], rtol=2e-4, atol=1e-6)
+        _resync(sim, orc, g)
+    print(f"terminated {n_term}, truncated {n_trunc}, command resamples {n_resample}")
+    assert n_term > 100 and n_trunc > 100 and n_resample > 100
+
+
+def test_bounded_divergence_over_1000_steps(cfg):
+    """(c) free-running: 1000 control steps of both implementations under a stabilising (zero) action stay statistically
+    together and finite; individual trajectories are allowed to separate (contact dynamics are chaotic)."""
+    n = 256
+    c = cfg.copy()
+    c.enable_corruption = 0
+    torch, sim, orc = _mk(c, n, 9)
+    sim.observe(); orc.observe()
+    a = np.zeros((n, 12), np.float32)
+    at = torch.from_numpy(a).cuda()
+    rg_sum, ro_sum, dq = 0.0, 0.0, []
+    for step in range(1000):
+        _, rg, tg, _ = sim.step(at)
+        _, ro, to, _ = orc.step(a)
+        rg_sum += float(rg.mean()); ro_sum += float(ro.mean())
+        if step in (0, 4, 24, 99):
+            g, o = _np(sim.get_state(["joint_pos"])), orc.get_state(["joint_pos"])
+            dq.append(float(np.median(np.abs(g["joint_pos"] - o["joint_pos"]).max(1))))
+    g = _np(sim.get_state(PHYS))
+    assert all(np.isfinite(v).all() for v in g.values())
+    assert sim.log_host()[25] == 0  # no non-finite force-resets
+    print("median max-joint divergence after 1/5/25/100 steps:", dq, " mean reward/step gpu", rg_sum / 1000, "oracle", ro_sum / 1000)
+    assert dq[0] < 1e-5 and dq[1] < 1e-4
+    assert abs(rg_sum - ro_sum) / 1000 < 0.05 * max(abs(ro_sum) / 1000, 0.01) + 0.02
+
+
+def test_flight_conserves_momentum_and_matches_oracle(cfg):
+    """No contacts, no dissipation: the horizontal momentum is conserved and float tracks double to 1e-6."""
+    c = cfg.copy()
+    for d in range(18):
+        c.dof_damping[d] = 0.0
+        c.dof_frictionloss[d] = 0.0
+    c.init_root_height = 20.0
+    c.decimation = 1
+    c.max_delay = 0
+    n = 256
+    torch, sim, orc = _mk(c, n, 5)
+    sim.observe(); orc.observe()
+    rng = np.random.default_rng(0)
+    st = _np(sim.get_state(PHYS))
+    st["root_lin_vel"] = rng.normal(size=(n, 3)).astype(np.float32)
+    st["root_ang_vel"] = rng.normal(size=(n, 3)).astype(np.float32)
+    st["joint_vel"] = rng.normal(size=(n, 12)).astype(np.float32) * 2
+    sim.set_state(st); orc.set_state(st)
+    for step in range(10):
+        a = (rng.normal(size=(n, 12)) * 0.2).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda()); orc.step(a)
+        g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS)
+        for k, tol in (("joint_pos", 2e-6), ("joint_vel", 2e-4), ("root_lin_vel", 2e-5), ("root_ang_vel", 1e-4)):
+            assert np.abs(g[k] - o[k]).max() < tol, (k, step, np.abs(g[k] - o[k]).max())
+        _resync(sim, orc, g)
+
+
+@pytest.mark.parametrize("n", [4096, 32768])
+def test_full_size_properties(cfg, n):
+    """Size-independent properties at BASELINE's env counts: determinism (same seed -> bit-identical run), finite
+    outputs, history shift property of the observation, episode counters, sharding invariance of the Philox key."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    H = cfg.history_length
+
+    def run(offset, count, steps=12):
+        c = cfg.copy()
+        c.env_id_offset = offset
+        sim = H1v2Sim(count, c, device="cuda:0", seed=123)
+        obs = [sim.observe().clone()]
+        rews = []
+        for i in range(steps):
+            act = sim.random_actions(i)
+            o, r, t, u = sim.step(act)
+            obs.append(o.clone()); rews.append(r.clone())
+        ep = sim.episode_length_buf.clone()
+        lg = sim.log_host()
+        sim.close()
+        return obs, rews, ep, lg
+
+    obs_a, rew_a, ep_a, lg = run(0, n)
+    obs_b, rew_b, ep_b, _ = run(0, n)
+    assert all(torch.equal(x, y) for x, y in zip(obs_a, obs_b)) and all(torch.equal(x, y) for x, y in zip(rew_a, rew_b))
+    assert all(torch.isfinite(x).all() for x in obs_a) and all(torch.isfinite(x).all() for x in rew_a)
+    assert lg[25] == 0
+    # history shift: for envs that did not reset, block[h] at step t+1 equals block[h+1] at step t
+    off = [0, 3, 6, 9, 21, 33, 45]
+    alive = ep_a > 1
+    o0, o1 = obs_a[-2][alive], obs_a[-1][alive]
+    for t in range(6):
+        d = off[t + 1] - off[t]
+        b0 = o0[:, off[t] * H: off[t + 1] * H].reshape(-1, H, d)
+        b1 = o1[:, off[t] * H: off[t + 1] * H].reshape(-1, H, d)
+        assert torch.equal(b1[:, :-1], b0[:, 1:])
+    assert int(ep_a.max()) <= 12
+    # sharding: the second half of the envs simulated on its own (rank 1 of 2) reproduces the same trajectories
+    half = n // 2
+    obs_h, rew_h, _, _ = run(half, half, steps=3)
+    assert torch.equal(obs_h[0], obs_a[0][half:])
+    # actions are drawn from the global env id as well, so the whole rollout is identical
+    for k in range(1, 4):
+        assert torch.equal(obs_h[k], obs_a[k][half:]), k
+
+
+def test_step_host_matches_device_path(cfg):
+    """The HOST-buffer entry point (what a non-torch caller binds) gives exactly the device path's results."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 1024
+    s1, s2 = H1v2Sim(n, cfg, seed=4), H1v2Sim(n, cfg, seed=4)
+    s1.observe(); s2.observe()
+    hobs = torch.empty((n, s1.obs_dim)).pin_memory(); hrew = torch.empty(n).pin_memory()
+    ht = torch.empty(n, dtype=torch.uint8).pin_memory(); hu = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for i in range(5):
+        a = s1.random_actions(i)
+        o, r, t, u = s1.step(a)
+        s2.step_host(a.cpu().pin_memory(), hobs, hrew, ht, hu)
+        assert torch.equal(o.cpu(), hobs) and torch.equal(r.cpu(), hrew) and torch.equal(t.cpu().to(torch.uint8), ht)
+    s1.close(); s2.close()

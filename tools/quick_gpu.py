@@ -19,4 +19,5 @@ for n in (4096, 32768):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     print(f"n={n}: {ms:.4f} ms/step -> {n / ms * 1e3 / 1e6:.2f} M env-steps/s", "log", sim.log_host()[[0, 22, 25, 26, 27]], "rew mean", rew.mean().item())
+    hst = sim.iter_hist(); print("  iteration histogram (fraction):", (hst / hst.sum()).round(4)[:14])
     sim.close()
