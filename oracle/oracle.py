@@ -42,7 +42,7 @@ def lib() -> C.CDLL:
         L.h1v2o_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.h1v2o_observe.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
-        L.h1v2o_step_injected.argtypes = [C.c_void_p] + [C.c_void_p] * 13
+        L.h1v2o_step_injected.argtypes = [C.c_void_p] + [C.c_void_p] * 12
         L.h1v2o_get_state.argtypes = [C.c_void_p, C.POINTER(H1v2State)]
         L.h1v2o_set_state.argtypes = [C.c_void_p, C.POINTER(H1v2State)]
         L.h1v2o_get_episode_length.argtypes = [C.c_void_p, C.c_void_p]
