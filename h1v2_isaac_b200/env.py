@@ -1,0 +1,452 @@
+"""H1v2ManagerBasedRLEnv: the ManagerBasedRLEnv contract of the reference, backed by the fused B200 step kernel.
+
+Drop-in seam: `gym.make("Isaac-Velocity-Flat-H12_12dof-v0", cfg=env_cfg)` in the reference's
+scripts/rsl_rl/train.py:102 constructs this class (through the shimmed `isaaclab.envs:ManagerBasedRLEnv` entry point
+of packages/biped_tasks/.../config/h12_12dof/__init__.py:40-49, or through a real isaaclab install that points the
+entry point here).  The step order is packages/biped_tasks/biped_tasks/utils/cat/cat_env.py:95-193; all of it runs
+inside ONE kernel launch (h1v2_step), nothing on the host except this thin wrapper.
+
+`flatten_cfg` turns the reference's resolved @configclass tree into the POD `H1v2Config` the C-ABI consumes.  It reads
+term lists, weights, scales, noise, ranges, gains and limits from the tree -- nothing about the task is hard-coded here;
+what the tree does not hold (the MJCF rigid-body model and MuJoCo solver parameters) comes from h1v2_default_config.
+Anything in the tree the kernel cannot express raises NotImplementedError naming the offending entry.
+"""
+from __future__ import annotations
+
+import math
+import re
+from typing import Any
+
+from ._capi import H1v2Config, LOG_COUNT, LOG_ERR_XY, LOG_ERR_YAW, LOG_REW0, LOG_TERM_CONTACT, LOG_TERM_TIMEOUT, NJ, REW_NAMES, default_config
+
+# MJCF (leg-major) joint order of h12_12dof.xml:71-132 == A/robots/h12.py:40-53
+JOINT_NAMES = [f"{s}_{j}_joint" for s in ("left", "right") for j in ("hip_yaw", "hip_pitch", "hip_roll", "knee", "ankle_pitch", "ankle_roll")]
+# PhysX breadth-first order used by joint_names=[".*"] without preserve_order
+BREADTH_FIRST = [0, 6, 1, 7, 2, 8, 3, 9, 4, 10, 5, 11]
+# contact-sensor slots of the kernel: bodies that own colliders in the PhysX asset (h12_12dof.urdf:116-121,168-191,387-392)
+SLOT_BODIES = ["left_ankle_roll_link", "right_ankle_roll_link", "left_knee_link", "right_knee_link", "torso_link", "pelvis"]
+# every rigid body of the articulation (names a body regex may legitimately match without owning a collider)
+ALL_BODIES = SLOT_BODIES + [f"{s}_{j}_link" for s in ("left", "right") for j in (
+    "hip_yaw", "hip_pitch", "hip_roll", "ankle_pitch", "shoulder_pitch", "shoulder_roll", "shoulder_yaw", "elbow", "wrist_roll", "wrist_pitch", "wrist_yaw")]
+
+# reward function name -> kernel slot (include/h1v2_b200.h enum)
+REW_FUNC_SLOT = {
+    "is_terminated": 0, "track_lin_vel_xy_yaw_frame_exp": 1, "track_ang_vel_z_world_exp": 2, "feet_air_time_positive_biped": 3,
+    "feet_slide": 4, "joint_pos_limits": 5, "joint_deviation_l1": 6, "ang_vel_xy_l2": 7, "joint_torques_l2": 8, "joint_acc_l2": 9,
+    "action_rate_l2": 10, "flat_orientation_l2": 11, "lin_vel_z_l2": 12, "undesired_contacts": 13, "track_lin_vel_xy_exp": 14,
+    "track_ang_vel_z_exp": 15, "feet_air_time": 16, "joint_vel_l2": 17, "base_height_l2": 18, "contact_forces": 19,
+}
+OBS_LAYOUT = ["base_ang_vel", "projected_gravity", "generated_commands", "joint_pos_rel", "joint_vel_rel", "last_action"]
+
+
+def _get(obj, name, default=None):
+    if obj is None:
+        return default
+    if isinstance(obj, dict):
+        return obj.get(name, default)
+    v = getattr(obj, name, default)
+    return default if v is None else v
+
+
+def _fname(func) -> str:
+    return getattr(func, "__name__", str(func)).split(".")[-1]
+
+
+def _match(patterns, names) -> list[int]:
+    """isaaclab string_utils.resolve_matching_names semantics: full-match regexes, indices in `names` order."""
+    if patterns is None:
+        return list(range(len(names)))
+    if isinstance(patterns, str):
+        patterns = [patterns]
+    return [i for i, n in enumerate(names) if any(re.fullmatch(p, n) for p in patterns)]
+
+
+def _per_joint(value, default: float) -> list[float]:
+    """float | {regex: float} -> 12 values in MJCF order."""
+    out = [default] * NJ
+    if value is None:
+        return out
+    if isinstance(value, dict):
+        for pat, v in value.items():
+            for i in _match(pat, JOINT_NAMES):
+                out[i] = float(v)
+        return out
+    return [float(value)] * NJ
+
+
+def _terms(group) -> list[tuple[str, Any]]:
+    if group is None:
+        return []
+    names = group.__configclass_fields__() if hasattr(group, "__configclass_fields__") else [k for k in vars(group) if not k.startswith("_")]
+    return [(n, getattr(group, n)) for n in names if getattr(group, n, None) is not None and hasattr(getattr(group, n), "func")]
+
+
+def _joint_mask(params, key="asset_cfg") -> int:
+    cfg = _get(params, key)
+    ids = _match(_get(cfg, "joint_names"), JOINT_NAMES)
+    return sum(1 << i for i in ids)
+
+
+def _slot_mask(params, key="sensor_cfg") -> int:
+    cfg = _get(params, key)
+    pats = _get(cfg, "body_names")
+    if pats in ("base", ["base"]):  # the upstream default names a body the H1-2 does not have; the H1-2 cfg overrides it
+        return 0
+    return sum(1 << s for s in _match(pats, SLOT_BODIES))
+
+
+def flatten_cfg(cfg) -> H1v2Config:
+    """Resolved ManagerBasedRLEnvCfg tree (reference: config/h12_12dof/flat_env_cfg.py:13-48 and parents) -> H1v2Config."""
+    c = default_config()  # rigid-body model, MuJoCo solver parameters; everything below is overwritten from the tree
+    c.sim_dt = float(cfg.sim.dt)
+    c.decimation = int(cfg.decimation)
+    c.episode_length_s = float(cfg.episode_length_s)
+    g = _get(cfg.sim, "gravity", (0.0, 0.0, -9.81))
+    c.gravity = float(-g[2])
+    c.env_spacing = float(_get(cfg.scene, "env_spacing", 2.5))
+
+    # ---- robot articulation (A/robots/h12.py:18-114) ----
+    robot = cfg.scene.robot
+    c.init_root_height = float(robot.init_state.pos[2])
+    q0 = _per_joint(robot.init_state.joint_pos, 0.0)
+    c.soft_limit_factor = float(_get(robot, "soft_joint_pos_limit_factor", 1.0))
+    kp, kd, ef = [None] * NJ, [None] * NJ, [None] * NJ
+    delays = set()
+    for name, act in robot.actuators.items():
+        ids = _match(act.joint_names_expr, JOINT_NAMES)
+        st, dm = _per_joint(act.stiffness, float("nan")), _per_joint(act.damping, float("nan"))
+        el = _per_joint(_get(act, "effort_limit"), float("inf"))
+        arm = _get(act, "armature")
+        for i in ids:
+            kp[i], kd[i], ef[i] = st[i], dm[i], el[i]
+            if arm is not None:
+                c.dof_armature[6 + i] = _per_joint(arm, 0.0)[i]
+        delays.add((int(_get(act, "min_delay", 0)), int(_get(act, "max_delay", 0))))
+    if any(v is None or (isinstance(v, float) and math.isnan(v)) for v in kp + kd):
+        raise NotImplementedError("actuators: every one of the 12 leg joints needs stiffness and damping")
+    if len(delays) != 1:
+        raise NotImplementedError(f"actuators: all groups must share one (min_delay, max_delay); got {sorted(delays)}")
+    c.min_delay, c.max_delay = delays.pop()
+    for i in range(NJ):
+        c.default_joint_pos[i], c.kp[i], c.kd[i] = q0[i], kp[i], kd[i]
+        c.effort_limit[i] = ef[i] if math.isfinite(ef[i]) else 1e9
+
+    # ---- actions (V/velocity_env_cfg.py:111) ----
+    acts = [(n, getattr(cfg.actions, n)) for n in cfg.actions.__configclass_fields__() if getattr(cfg.actions, n) is not None]
+    if len(acts) != 1 or not hasattr(acts[0][1], "joint_names"):
+        raise NotImplementedError("actions: exactly one JointPositionAction term is supported")
+    a = acts[0][1]
+    if not _get(a, "use_default_offset", True):
+        raise NotImplementedError("actions: use_default_offset=False is not supported")
+    if isinstance(a.scale, dict):
+        raise NotImplementedError("actions: per-joint scale dict is not supported")
+    c.action_scale = float(a.scale)
+    if _get(a, "preserve_order", False):
+        order = []
+        for pat in a.joint_names:
+            order += [i for i in _match(pat, JOINT_NAMES) if i not in order]
+    else:
+        sel = set(_match(a.joint_names, JOINT_NAMES))
+        order = [i for i in BREADTH_FIRST if i in sel]
+    if sorted(order) != list(range(NJ)):
+        raise NotImplementedError("actions: joint_names must select all 12 leg joints")
+    for i in range(NJ):
+        c.joint_perm[i] = order[i]
+
+    # ---- observations (V/velocity_env_cfg.py:123-142; flat_env_cfg.py:22-27) ----
+    pol = cfg.observations.policy
+    terms = _terms(pol)
+    got = [_fname(t.func) for _, t in terms]
+    if got != OBS_LAYOUT:
+        raise NotImplementedError(f"observations.policy: the fused kernel emits {OBS_LAYOUT}; the cfg asks for {got}")
+    if not _get(pol, "concatenate_terms", True):
+        raise NotImplementedError("observations.policy.concatenate_terms=False is not supported")
+    c.history_length = int(_get(pol, "history_length", 0) or 1)
+    c.enable_corruption = int(bool(_get(pol, "enable_corruption", False)))
+    noise, scale = [], []
+    for n, t in terms:
+        nz = _get(t, "noise")
+        if nz is None:
+            noise.append(0.0)
+        else:
+            lo, hi = float(nz.n_min), float(nz.n_max)
+            if abs(lo + hi) > 1e-12:
+                raise NotImplementedError(f"observations.policy.{n}: only symmetric additive uniform noise is supported")
+            noise.append(hi)
+        if _get(t, "clip") is not None:
+            raise NotImplementedError(f"observations.policy.{n}.clip is not supported")
+        sc = _get(t, "scale")
+        scale.append(1.0 if sc is None else float(sc))
+    if noise[2] or noise[5]:
+        raise NotImplementedError("observations.policy: noise on commands / last_action is not supported")
+    c.noise_ang_vel, c.noise_gravity, c.noise_joint_pos, c.noise_joint_vel = noise[0], noise[1], noise[3], noise[4]
+    c.scale_ang_vel, c.scale_gravity, c.scale_cmd, c.scale_joint_pos, c.scale_joint_vel, c.scale_action = scale
+
+    # ---- rewards (rough_env_cfg.py:18-62,112-120; flat_env_cfg.py:35-44; V/velocity_env_cfg.py:225-257) ----
+    for i in range(len(REW_NAMES)):
+        c.rew_weight[i] = 0.0
+    std = None
+    for n, t in _terms(cfg.rewards):
+        w = float(t.weight)
+        if w == 0.0:
+            continue  # RewardManager skips zero-weight terms
+        f = _fname(t.func)
+        if f not in REW_FUNC_SLOT:
+            raise NotImplementedError(f"rewards.{n}: mdp.{f} is not implemented in the fused kernel")
+        slot, p = REW_FUNC_SLOT[f], (t.params or {})
+        if c.rew_weight[slot] != 0.0:
+            raise NotImplementedError(f"rewards.{n}: mdp.{f} appears twice")
+        c.rew_weight[slot] = w
+        if "std" in p:
+            if std is not None and abs(std - float(p["std"])) > 1e-9:
+                raise NotImplementedError("rewards: tracking terms must share one std")
+            std = float(p["std"])
+        if f in ("feet_air_time", "feet_air_time_positive_biped"):
+            c.feet_air_threshold = float(p["threshold"])
+            if _slot_mask(p) != 0b11:
+                raise NotImplementedError(f"rewards.{n}: sensor bodies must be the two ankle_roll links")
+        elif f == "feet_slide" and _slot_mask(p) != 0b11:
+            raise NotImplementedError(f"rewards.{n}: sensor bodies must be the two ankle_roll links")
+        elif f == "joint_pos_limits":
+            c.mask_pos_limits = _joint_mask(p)
+        elif f == "joint_deviation_l1":
+            c.mask_joint_dev = _joint_mask(p)
+        elif f == "joint_torques_l2":
+            c.mask_torques = _joint_mask(p)
+        elif f in ("undesired_contacts", "contact_forces"):
+            c.mask_undesired_slots = _slot_mask(p)
+            if abs(float(p.get("threshold", 1.0)) - 1.0) > 1e-9:
+                raise NotImplementedError(f"rewards.{n}: threshold must equal the contact threshold 1.0")
+        elif f == "base_height_l2":
+            c.base_height_target = float(p["target_height"])
+    if std is not None:
+        c.track_std = std
+
+    # ---- terminations (V/velocity_env_cfg.py:264-268; rough_env_cfg.py:95-109) ----
+    c.mask_illegal_slots = 0
+    have_timeout = False
+    for n, t in _terms(cfg.terminations):
+        f = _fname(t.func)
+        if f == "time_out":
+            have_timeout = bool(_get(t, "time_out", False))
+        elif f == "illegal_contact":
+            c.mask_illegal_slots = _slot_mask(t.params)
+            c.contact_threshold = float(t.params.get("threshold", 1.0))
+        else:
+            raise NotImplementedError(f"terminations.{n}: mdp.{f} is not implemented in the fused kernel")
+    if not have_timeout:
+        raise NotImplementedError("terminations: a time_out term (time_out=True) is required")
+
+    # ---- commands (V/velocity_env_cfg.py:90-104; flat_env_cfg.py:46-48) ----
+    cmd = cfg.commands.base_velocity
+    r = cmd.ranges
+    for dst, src in ((c.cmd_lin_x, r.lin_vel_x), (c.cmd_lin_y, r.lin_vel_y), (c.cmd_ang_z, r.ang_vel_z), (c.cmd_resample_time, cmd.resampling_time_range)):
+        dst[0], dst[1] = float(src[0]), float(src[1])
+    c.heading_command = int(bool(_get(cmd, "heading_command", False)))
+    if c.heading_command:
+        h = r.heading
+        c.cmd_heading[0], c.cmd_heading[1] = float(h[0]), float(h[1])
+    c.heading_stiffness = float(_get(cmd, "heading_control_stiffness", 1.0))
+    c.rel_standing_envs = float(_get(cmd, "rel_standing_envs", 0.0))
+    c.rel_heading_envs = float(_get(cmd, "rel_heading_envs", 1.0))
+
+    # ---- events (V/velocity_env_cfg.py:153-217; rough_env_cfg.py:78-92) ----
+    ground_mu = float(_get(_get(_get(cfg.scene, "terrain"), "physics_material"), "static_friction", 1.0))
+    c.push_enable = 0
+    c.mass_add_range[0] = c.mass_add_range[1] = 0.0
+    for i in range(6):
+        c.reset_pose_range[i][0] = c.reset_pose_range[i][1] = 0.0
+        c.reset_vel_range[i][0] = c.reset_vel_range[i][1] = 0.0
+    axes = ["x", "y", "z", "roll", "pitch", "yaw"]
+    for n, t in _terms(cfg.events):
+        f, p = _fname(t.func), (t.params or {})
+        if f == "randomize_rigid_body_material":
+            lo, hi = p["static_friction_range"]
+            # "multiply" combine with the ground material (V/velocity_env_cfg.py:40-51)
+            c.friction_range[0], c.friction_range[1] = float(lo) * ground_mu, float(hi) * ground_mu
+            c.friction = 0.5 * (c.friction_range[0] + c.friction_range[1])
+        elif f == "randomize_rigid_body_mass":
+            if p.get("operation", "add") != "add":
+                raise NotImplementedError(f"events.{n}: only operation='add' is supported")
+            c.mass_add_range[0], c.mass_add_range[1] = map(float, p["mass_distribution_params"])
+        elif f == "apply_external_force_torque":
+            if any(abs(float(v)) > 0 for v in tuple(p["force_range"]) + tuple(p["torque_range"])):
+                raise NotImplementedError(f"events.{n}: non-zero external wrench is not supported")
+        elif f == "reset_root_state_uniform":
+            for i, ax in enumerate(axes):
+                lo, hi = p.get("pose_range", {}).get(ax, (0.0, 0.0))
+                c.reset_pose_range[i][0], c.reset_pose_range[i][1] = float(lo), float(hi)
+                lo, hi = p.get("velocity_range", {}).get(ax, (0.0, 0.0))
+                c.reset_vel_range[i][0], c.reset_vel_range[i][1] = float(lo), float(hi)
+        elif f == "reset_joints_by_scale":
+            c.reset_joint_pos_scale[0], c.reset_joint_pos_scale[1] = map(float, p["position_range"])
+            c.reset_joint_vel_scale[0], c.reset_joint_vel_scale[1] = map(float, p["velocity_range"])
+        elif f == "push_by_setting_velocity":
+            vr = p["velocity_range"]
+            if set(vr) - {"x", "y"} or tuple(vr.get("x", (0, 0))) != tuple(vr.get("y", (0, 0))):
+                raise NotImplementedError(f"events.{n}: pushes must be one range on x and y")
+            c.push_enable = 1
+            c.push_interval_s[0], c.push_interval_s[1] = map(float, t.interval_range_s)
+            c.push_vel_xy[0], c.push_vel_xy[1] = map(float, vr["x"])
+        else:
+            raise NotImplementedError(f"events.{n}: mdp.{f} is not implemented in the fused kernel")
+    return c
+
+
+def config_to_dict(c: H1v2Config) -> dict:
+    """Plain-python view of an H1v2Config (golden fixtures, yaml dumps)."""
+    def conv(v):
+        if hasattr(v, "__len__"):
+            return [conv(x) for x in v]
+        return v
+    return {name: conv(getattr(c, name)) for name, _ in c._fields_ if name != "reserved"}
+
+
+class _ActionManagerView:
+    def __init__(self, env):
+        self._env = env
+        self.total_action_dim = NJ
+        self.active_terms = ["joint_pos"]
+
+    @property
+    def action(self):
+        return self._env._last_action
+
+    @property
+    def prev_action(self):
+        return self._env._prev_action
+
+
+class _ObservationManagerView:
+    def __init__(self, env):
+        self._env = env
+        self.group_obs_dim = {"policy": (env.sim.obs_dim,)}
+        self.active_terms = {"policy": ["base_ang_vel", "projected_gravity", "velocity_commands", "joint_pos", "joint_vel", "actions"]}
+
+    def compute(self):
+        """ObservationManager.compute(): appends to the history like upstream (observation_manager.py:318-355)."""
+        return {"policy": self._env.sim.observe()}
+
+
+class _NamesView:
+    def __init__(self, names):
+        self.active_terms = list(names)
+
+
+class H1v2ManagerBasedRLEnv:
+    """ManagerBasedRLEnv drop-in.  step(action) -> (obs_dict, rew, terminated, truncated, extras), all device tensors."""
+
+    is_vector_env = True
+    metadata = {"render_modes": [None, "human", "rgb_array"], "isaac_sim_version": "B200-native backend (no Isaac Sim)"}
+
+    def __init__(self, cfg, render_mode: str | None = None, **kwargs):
+        import torch
+
+        from .backend import H1v2Sim
+        if hasattr(cfg, "validate"):
+            cfg.validate()
+        self.cfg = cfg
+        self.render_mode = render_mode
+        self.kernel_cfg = flatten_cfg(cfg)
+        seed = _get(cfg, "seed")
+        self._seed = 42 if seed is None else int(seed)
+        rank, world = self._dist_info()
+        n = int(cfg.scene.num_envs)
+        self.kernel_cfg.env_id_offset = rank * n  # envs shard by rank; the Philox key uses the global env id
+        dev = torch.device(_get(cfg.sim, "device", "cuda:0"))
+        self.sim = H1v2Sim(n, self.kernel_cfg, device=dev, seed=self._seed)
+        self.num_envs, self.device = n, self.sim.device
+        self.physics_dt = float(cfg.sim.dt)
+        self.step_dt = self.physics_dt * int(cfg.decimation)
+        self.max_episode_length_s = float(cfg.episode_length_s)
+        self.max_episode_length = self.sim.max_episode_length
+        self.cfg_is_finite_horizon = bool(_get(cfg, "is_finite_horizon", False))
+        self.common_step_counter = 0
+        self.extras: dict = {}
+        self._last_action = torch.zeros((n, NJ), device=self.device)
+        self._prev_action = torch.zeros((n, NJ), device=self.device)
+        self.action_manager = _ActionManagerView(self)
+        self.observation_manager = _ObservationManagerView(self)
+        self.reward_manager = _NamesView([REW_NAMES[i] for i in range(len(REW_NAMES)) if self.kernel_cfg.rew_weight[i] != 0.0])
+        self.termination_manager = _NamesView(["time_out", "base_contact"])
+        self.command_manager = _NamesView(["base_velocity"])
+        self._rew_names = [n for n, t in _terms(cfg.rewards) if float(t.weight) != 0.0]
+        self._rew_slots = [REW_FUNC_SLOT[_fname(getattr(cfg.rewards, n).func)] for n in self._rew_names]
+        self._configure_gym_env_spaces()
+        self.obs_buf = {"policy": self.sim.observe()}
+        print(f"[INFO]: B200-native environment: {n} envs on {self.device}, step_dt {self.step_dt:.3f} s, obs {self.sim.obs_dim}, seed {self._seed}"
+              + (f", rank {rank}/{world}" if world > 1 else ""))
+
+    @staticmethod
+    def _dist_info():
+        import os
+        return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ---- gym surface (T/utils/cat/cat_env.py:250-275) ----
+    def _configure_gym_env_spaces(self):
+        import gymnasium as gym
+        import numpy as np
+        od = self.sim.obs_dim
+        self.single_observation_space = gym.spaces.Dict({"policy": gym.spaces.Box(low=-np.inf, high=np.inf, shape=(od,))})
+        self.single_action_space = gym.spaces.Box(low=-np.inf, high=np.inf, shape=(NJ,))
+        self.observation_space = gym.vector.utils.batch_space(self.single_observation_space, self.num_envs)
+        self.action_space = gym.vector.utils.batch_space(self.single_action_space, self.num_envs)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def episode_length_buf(self):
+        return self.sim.episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        # assignable (scripts/rsl_rl/train.py:141 learn(init_at_random_ep_len=True)); the kernel keeps its bound buffer
+        self.sim.episode_length_buf.copy_(value.to(self.sim.episode_length_buf.dtype))
+
+    def seed(self, seed: int = -1) -> int:
+        return self._seed
+
+    # ---- MDP ----
+    def reset(self, seed: int | None = None, options: dict | None = None):
+        self.sim.reset(None)
+        self._last_action.zero_(); self._prev_action.zero_()
+        self.sim.episode_length_buf.zero_()
+        self.obs_buf = {"policy": self.sim.observe()}
+        self.extras = {}
+        return self.obs_buf, self.extras
+
+    def step(self, action):
+        obs, rew, terminated, truncated = self.sim.step(action)
+        self._prev_action, self._last_action = self._last_action, action
+        self.common_step_counter += 1
+        self.obs_buf = {"policy": obs}
+        self.reward_buf, self.reset_terminated, self.reset_time_outs = rew, terminated, truncated
+        self.reset_buf = terminated | truncated
+        self.extras = {"log": self._log_dict()}
+        return self.obs_buf, rew, terminated, truncated, self.extras
+
+    def _log_dict(self) -> dict:
+        """extras["log"] (T/utils/cat/cat_env.py:217-245): 0-d device tensors, no host sync.  Values are those of the
+        most recent step in which any env reset (upstream only writes the keys on such steps)."""
+        lg = self.sim.log_buf
+        d = {f"Episode_Reward/{n}": lg[LOG_REW0 + s] for n, s in zip(self._rew_names, self._rew_slots)}
+        d["Episode_Termination/time_out"] = lg[LOG_TERM_TIMEOUT]
+        d["Episode_Termination/base_contact"] = lg[LOG_TERM_CONTACT]
+        d["Metrics/base_velocity/error_vel_xy"] = lg[LOG_ERR_XY]
+        d["Metrics/base_velocity/error_vel_yaw"] = lg[LOG_ERR_YAW]
+        return d
+
+    def render(self, recompute: bool = False):
+        return None
+
+    def close(self):
+        if getattr(self, "sim", None) is not None:
+            self.sim.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

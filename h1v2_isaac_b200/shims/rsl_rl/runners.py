@@ -1,0 +1,409 @@
+"""OnPolicyRunner / PPO / ActorCritic with rsl-rl-lib 2.3.3 semantics:
+24-step rollouts, GAE(gamma, lam) with time-out bootstrapping, clipped surrogate + clipped value loss, entropy bonus,
+adaptive-KL learning rate, num_learning_epochs x num_mini_batches updates, grad-norm clipping.  Multi-GPU (WORLD_SIZE>1):
+parameters broadcast from rank 0 once, gradients all-reduced (mean) every mini-batch, KL all-reduced for the LR schedule,
+rollout statistics reduced to rank 0 once per iteration (north star)."""
+from __future__ import annotations
+
+import os
+import statistics
+import time
+from collections import deque
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def _act(name: str):
+    return {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}[name]()
+
+
+def _mlp(i, hidden, o, act):
+    layers, d = [], i
+    for h in hidden:
+        layers += [nn.Linear(d, h), _act(act)]
+        d = h
+    layers.append(nn.Linear(d, o))
+    return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+    is_recurrent = False
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256), critic_hidden_dims=(256, 256, 256),
+                 activation="elu", init_noise_std=1.0, noise_std_type="scalar", **kwargs):
+        super().__init__()
+        self.actor = _mlp(num_actor_obs, actor_hidden_dims, num_actions, activation)
+        self.critic = _mlp(num_critic_obs, critic_hidden_dims, 1, activation)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.distribution = None
+        torch.distributions.Normal.set_default_validate_args(False)
+
+    def reset(self, dones=None):
+        pass
+
+    def update_distribution(self, obs):
+        mean = self.actor(obs)
+        self.distribution = torch.distributions.Normal(mean, self.std.expand_as(mean))
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
+    def act(self, obs, **kw):
+        self.update_distribution(obs)
+        return self.distribution.sample()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    def act_inference(self, obs):
+        return self.actor(obs)
+
+    def evaluate(self, critic_obs, **kw):
+        return self.critic(critic_obs)
+
+
+class EmpiricalNormalization(nn.Module):
+    def __init__(self, shape, eps=1e-2, until=None):
+        super().__init__()
+        self.eps, self.until = eps, until
+        self.register_buffer("_mean", torch.zeros(shape).unsqueeze(0))
+        self.register_buffer("_var", torch.ones(shape).unsqueeze(0))
+        self.register_buffer("_std", torch.ones(shape).unsqueeze(0))
+        self.register_buffer("count", torch.tensor(0, dtype=torch.long))
+
+    def forward(self, x):
+        if self.training:
+            self.update(x)
+        return (x - self._mean) / (self._std + self.eps)
+
+    @torch.jit.unused
+    def update(self, x):
+        if self.until is not None and self.count >= self.until:
+            return
+        n = x.shape[0]
+        self.count += n
+        rate = n / self.count
+        var_x, mean_x = torch.var(x, dim=0, unbiased=False, keepdim=True), torch.mean(x, dim=0, keepdim=True)
+        delta = mean_x - self._mean
+        self._mean += rate * delta
+        self._var += rate * (var_x - self._var + delta * (mean_x - self._mean))
+        self._std = torch.sqrt(self._var)
+
+
+class RolloutStorage:
+    def __init__(self, num_envs, T, obs_shape, critic_shape, act_shape, device):
+        z = lambda *s: torch.zeros(T, num_envs, *s, device=device)  # noqa: E731
+        self.obs, self.critic_obs, self.actions = z(*obs_shape), z(*critic_shape), z(*act_shape)
+        self.rewards, self.dones, self.values, self.logp = z(1), z(1).byte(), z(1), z(1)
+        self.mu, self.sigma = z(*act_shape), z(*act_shape)
+        self.returns, self.adv = z(1), z(1)
+        self.T, self.num_envs, self.step = T, num_envs, 0
+
+    def add(self, obs, critic_obs, actions, rewards, dones, values, logp, mu, sigma):
+        t = self.step
+        self.obs[t].copy_(obs); self.critic_obs[t].copy_(critic_obs); self.actions[t].copy_(actions)
+        self.rewards[t].copy_(rewards.view(-1, 1)); self.dones[t].copy_(dones.view(-1, 1)); self.values[t].copy_(values)
+        self.logp[t].copy_(logp.view(-1, 1)); self.mu[t].copy_(mu); self.sigma[t].copy_(sigma)
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam, normalize=True):
+        adv = 0
+        for t in reversed(range(self.T)):
+            nv = last_values if t == self.T - 1 else self.values[t + 1]
+            nt = 1.0 - self.dones[t].float()
+            delta = self.rewards[t] + nt * gamma * nv - self.values[t]
+            adv = delta + nt * gamma * lam * adv
+            self.returns[t] = adv + self.values[t]
+        self.adv = self.returns - self.values
+        if normalize:
+            self.adv = (self.adv - self.adv.mean()) / (self.adv.std() + 1e-8)
+
+    def mini_batches(self, num_mini_batches, num_epochs):
+        B = self.T * self.num_envs
+        mb = B // num_mini_batches
+        flat = lambda x: x.flatten(0, 1)  # noqa: E731
+        obs, cobs, act, val, ret, logp, adv, mu, sig = map(flat, (self.obs, self.critic_obs, self.actions, self.values, self.returns, self.logp,
+                                                                  self.adv, self.mu, self.sigma))
+        for _ in range(num_epochs):
+            idx = torch.randperm(num_mini_batches * mb, device=obs.device)
+            for i in range(num_mini_batches):
+                b = idx[i * mb:(i + 1) * mb]
+                yield obs[b], cobs[b], act[b], val[b], adv[b], ret[b], logp[b], mu[b], sig[b]
+
+
+class PPO:
+    def __init__(self, policy, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95, value_loss_coef=1.0,
+                 entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01,
+                 device="cpu", normalize_advantage_per_mini_batch=False, multi_gpu_cfg=None, **kwargs):
+        self.policy, self.device = policy.to(device), device
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate)
+        self.epochs, self.nmb, self.clip, self.gamma, self.lam = num_learning_epochs, num_mini_batches, clip_param, gamma, lam
+        self.vcoef, self.ecoef, self.lr, self.max_grad_norm = value_loss_coef, entropy_coef, learning_rate, max_grad_norm
+        self.clip_v, self.schedule, self.desired_kl = use_clipped_value_loss, schedule, desired_kl
+        self.multi_gpu = multi_gpu_cfg
+        self.storage = None
+        self._tr = {}
+
+    def init_storage(self, num_envs, T, obs_shape, critic_shape, act_shape):
+        self.storage = RolloutStorage(num_envs, T, obs_shape, critic_shape, act_shape, self.device)
+
+    def act(self, obs, critic_obs):
+        a = self.policy.act(obs).detach()
+        self._tr = dict(obs=obs, critic_obs=critic_obs, actions=a, values=self.policy.evaluate(critic_obs).detach(),
+                        logp=self.policy.get_actions_log_prob(a).detach(), mu=self.policy.action_mean.detach(), sigma=self.policy.action_std.detach())
+        return a
+
+    def process_env_step(self, rewards, dones, infos):
+        r = rewards.clone()
+        if "time_outs" in infos:  # bootstrap on time-outs
+            r += self.gamma * (self._tr["values"].squeeze(1) * infos["time_outs"].to(self.device).float())
+        t = self._tr
+        self.storage.add(t["obs"], t["critic_obs"], t["actions"], r, dones, t["values"], t["logp"], t["mu"], t["sigma"])
+        self._tr = {}
+
+    def compute_returns(self, last_critic_obs):
+        self.storage.compute_returns(self.policy.evaluate(last_critic_obs).detach(), self.gamma, self.lam)
+
+    def broadcast_parameters(self):
+        for p in self.policy.parameters():
+            dist.broadcast(p.data, src=0)
+
+    def reduce_parameters(self):
+        grads = [p.grad.view(-1) for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= self.multi_gpu["world_size"]
+        off = 0
+        for p in self.policy.parameters():
+            if p.grad is not None:
+                n = p.numel()
+                p.grad.data.copy_(flat[off:off + n].view_as(p.grad.data))
+                off += n
+
+    def update(self):
+        mv = ms = me = 0.0
+        n = 0
+        for obs, cobs, act, val, adv, ret, old_logp, old_mu, old_sigma in self.storage.mini_batches(self.nmb, self.epochs):
+            self.policy.act(obs)
+            logp = self.policy.get_actions_log_prob(act)
+            value = self.policy.evaluate(cobs)
+            mu, sigma, ent = self.policy.action_mean, self.policy.action_std, self.policy.entropy
+            if self.desired_kl is not None and self.schedule == "adaptive":
+                with torch.inference_mode():
+                    kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * sigma.square()) - 0.5, dim=-1)
+                    kl_mean = kl.mean()
+                    if self.multi_gpu:
+                        dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
+                        kl_mean /= self.multi_gpu["world_size"]
+                    if kl_mean > self.desired_kl * 2.0:
+                        self.lr = max(1e-5, self.lr / 1.5)
+                    elif 0.0 < kl_mean < self.desired_kl / 2.0:
+                        self.lr = min(1e-2, self.lr * 1.5)
+                    for g in self.opt.param_groups:
+                        g["lr"] = self.lr
+            ratio = torch.exp(logp - old_logp.squeeze(1))
+            a = adv.squeeze(1)
+            surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip, 1.0 + self.clip)).mean()
+            if self.clip_v:
+                vc = val + (value - val).clamp(-self.clip, self.clip)
+                vloss = torch.max((value - ret).square(), (vc - ret).square()).mean()
+            else:
+                vloss = (ret - value).square().mean()
+            loss = surrogate + self.vcoef * vloss - self.ecoef * ent.mean()
+            self.opt.zero_grad()
+            loss.backward()
+            if self.multi_gpu:
+                self.reduce_parameters()
+            nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+            self.opt.step()
+            mv += vloss.item(); ms += surrogate.item(); me += ent.mean().item(); n += 1
+        self.storage.clear()
+        return {"value_function": mv / n, "surrogate": ms / n, "entropy": me / n}
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg: dict, log_dir: str | None = None, device="cpu"):
+        self.cfg, self.alg_cfg, self.policy_cfg = train_cfg, dict(train_cfg["algorithm"]), dict(train_cfg["policy"])
+        self.device, self.env, self.log_dir = device, env, log_dir
+        self._configure_multi_gpu()
+        obs, extras = self.env.get_observations()
+        num_obs = obs.shape[1]
+        num_critic = extras["observations"]["critic"].shape[1] if "critic" in extras["observations"] else num_obs
+        self.privileged = "critic" if "critic" in extras["observations"] else None
+        self.policy_cfg.pop("class_name", None); self.alg_cfg.pop("class_name", None)
+        for k in ("symmetry_cfg", "rnd_cfg"):
+            self.alg_cfg.pop(k, None)
+        policy = ActorCritic(num_obs, num_critic, self.env.num_actions, **self.policy_cfg).to(self.device)
+        self.alg = PPO(policy, device=self.device, multi_gpu_cfg=self.multi_gpu_cfg, **self.alg_cfg)
+        self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
+        self.empirical_normalization = self.cfg.get("empirical_normalization", False)
+        if self.empirical_normalization:
+            self.obs_normalizer = EmpiricalNormalization([num_obs], until=1.0e8).to(self.device)
+            self.critic_obs_normalizer = EmpiricalNormalization([num_critic], until=1.0e8).to(self.device)
+        else:
+            self.obs_normalizer = self.critic_obs_normalizer = nn.Identity().to(self.device)
+        self.alg.init_storage(self.env.num_envs, self.num_steps_per_env, [num_obs], [num_critic], [self.env.num_actions])
+        self.disable_logs = self.is_distributed and self.gpu_global_rank != 0
+        self.writer, self.tot_timesteps, self.tot_time, self.current_learning_iteration, self.git_status_repos = None, 0, 0.0, 0, []
+        self.stats = {}
+
+    def _configure_multi_gpu(self):
+        self.gpu_world_size = int(os.getenv("WORLD_SIZE", "1"))
+        self.is_distributed = self.gpu_world_size > 1
+        if not self.is_distributed:
+            self.gpu_local_rank = self.gpu_global_rank = 0
+            self.multi_gpu_cfg = None
+            return
+        self.gpu_local_rank, self.gpu_global_rank = int(os.getenv("LOCAL_RANK", "0")), int(os.getenv("RANK", "0"))
+        self.multi_gpu_cfg = {"global_rank": self.gpu_global_rank, "local_rank": self.gpu_local_rank, "world_size": self.gpu_world_size}
+        if str(self.device).startswith("cuda") and self.device != f"cuda:{self.gpu_local_rank}":
+            raise ValueError(f"Device '{self.device}' does not match expected device for local rank '{self.gpu_local_rank}'.")
+        if not dist.is_initialized():
+            dist.init_process_group(backend="nccl" if str(self.device).startswith("cuda") else "gloo", rank=self.gpu_global_rank, world_size=self.gpu_world_size)
+        if str(self.device).startswith("cuda"):
+            torch.cuda.set_device(self.gpu_local_rank)
+
+    def add_git_repo_to_log(self, repo_file_path):
+        self.git_status_repos.append(repo_file_path)
+
+    def _init_writer(self):
+        if self.log_dir is None or self.disable_logs or self.writer is not None:
+            return
+        os.makedirs(self.log_dir, exist_ok=True)
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)
+        except Exception:
+            self.writer = None
+
+    def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
+        self._init_writer()
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        obs, extras = self.env.get_observations()
+        critic_obs = extras["observations"].get(self.privileged, obs) if self.privileged else obs
+        obs, critic_obs = obs.to(self.device), critic_obs.to(self.device)
+        self.train_mode()
+        ep_infos, rewbuffer, lenbuffer = [], deque(maxlen=100), deque(maxlen=100)
+        cur_rew = torch.zeros(self.env.num_envs, device=self.device)
+        cur_len = torch.zeros(self.env.num_envs, device=self.device)
+        if self.is_distributed:
+            self.alg.broadcast_parameters()
+        start = self.current_learning_iteration
+        tot = start + num_learning_iterations
+        for it in range(start, tot):
+            t0 = time.time()
+            with torch.inference_mode():
+                for _ in range(self.num_steps_per_env):
+                    actions = self.alg.act(obs, critic_obs)
+                    obs, rewards, dones, infos = self.env.step(actions.to(self.env.device))
+                    obs, rewards, dones = obs.to(self.device), rewards.to(self.device), dones.to(self.device)
+                    obs = self.obs_normalizer(obs)
+                    critic_obs = self.critic_obs_normalizer(infos["observations"][self.privileged].to(self.device)) if self.privileged else obs
+                    self.alg.process_env_step(rewards, dones, infos)
+                    if self.log_dir is not None:
+                        if "episode" in infos:
+                            ep_infos.append(infos["episode"])
+                        elif "log" in infos:
+                            ep_infos.append(infos["log"])
+                        cur_rew += rewards
+                        cur_len += 1
+                        new_ids = (dones > 0).nonzero(as_tuple=False)
+                        rewbuffer.extend(cur_rew[new_ids][:, 0].cpu().numpy().tolist())
+                        lenbuffer.extend(cur_len[new_ids][:, 0].cpu().numpy().tolist())
+                        cur_rew[new_ids] = 0
+                        cur_len[new_ids] = 0
+                t1 = time.time()
+                self.alg.compute_returns(critic_obs)
+            loss = self.alg.update()
+            t2 = time.time()
+            self.current_learning_iteration = it
+            self._log(it, tot, t1 - t0, t2 - t1, loss, ep_infos, rewbuffer, lenbuffer)
+            ep_infos.clear()
+            if self.log_dir is not None and not self.disable_logs and it % self.save_interval == 0:
+                self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
+        if self.log_dir is not None and not self.disable_logs:
+            self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+
+    def _log(self, it, tot, collection_time, learn_time, loss, ep_infos, rewbuffer, lenbuffer):
+        steps = self.num_steps_per_env * self.env.num_envs * self.gpu_world_size
+        self.tot_timesteps += steps
+        self.tot_time += collection_time + learn_time
+        fps = int(steps / (collection_time + learn_time))
+        stats = {"iteration": it, "fps": fps, "collection_time": collection_time, "learn_time": learn_time, **{f"loss/{k}": v for k, v in loss.items()},
+                 "mean_noise_std": self.alg.policy.action_std.mean().item() if self.alg.policy.distribution is not None else float("nan"),
+                 "lr": self.alg.lr}
+        if len(rewbuffer) > 0:
+            mr, ml = statistics.mean(rewbuffer), statistics.mean(lenbuffer)
+            if self.is_distributed:  # rollout statistics reduced over ranks once per iteration (north star)
+                t = torch.tensor([mr, ml, 1.0], device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                mr, ml = (t[0] / t[2]).item(), (t[1] / t[2]).item()
+            stats["mean_reward"], stats["mean_episode_length"] = mr, ml
+        ep = {}
+        if ep_infos:
+            for key in ep_infos[0]:
+                vals = [torch.as_tensor(e[key], dtype=torch.float32, device=self.device).reshape(-1) for e in ep_infos if key in e]
+                if vals:
+                    ep[key] = torch.cat(vals).mean().item()
+        self.stats = {**stats, **{f"episode/{k}": v for k, v in ep.items()}}
+        if self.disable_logs:
+            return
+        if self.writer is not None:
+            for k, v in self.stats.items():
+                if isinstance(v, (int, float)):
+                    self.writer.add_scalar(k, v, it)
+        print(f"[rsl_rl shim] it {it + 1}/{tot}  steps/s {fps}  collect {collection_time:.3f}s learn {learn_time:.3f}s  "
+              f"reward {stats.get('mean_reward', float('nan')):.3f}  len {stats.get('mean_episode_length', float('nan')):.1f}  "
+              f"vloss {loss['value_function']:.4f}  lr {self.alg.lr:.2e}", flush=True)
+
+    def save(self, path: str, infos=None):
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save({"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": self.alg.opt.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos,
+                    **({"obs_norm_state_dict": self.obs_normalizer.state_dict(), "critic_obs_norm_state_dict": self.critic_obs_normalizer.state_dict()}
+                       if self.empirical_normalization else {})}, path)
+
+    def load(self, path: str, load_optimizer: bool = True):
+        d = torch.load(path, weights_only=False, map_location=self.device)
+        self.alg.policy.load_state_dict(d["model_state_dict"])
+        if self.empirical_normalization and "obs_norm_state_dict" in d:
+            self.obs_normalizer.load_state_dict(d["obs_norm_state_dict"])
+            self.critic_obs_normalizer.load_state_dict(d["critic_obs_norm_state_dict"])
+        if load_optimizer:
+            self.alg.opt.load_state_dict(d["optimizer_state_dict"])
+        self.current_learning_iteration = d["iter"]
+        return d.get("infos")
+
+    def get_inference_policy(self, device=None):
+        self.eval_mode()
+        if device is not None:
+            self.alg.policy.to(device)
+        if self.empirical_normalization:
+            norm = self.obs_normalizer.to(device) if device is not None else self.obs_normalizer
+            return lambda x: self.alg.policy.act_inference(norm(x))
+        return self.alg.policy.act_inference
+
+    def train_mode(self):
+        self.alg.policy.train()
+        if self.empirical_normalization:
+            self.obs_normalizer.train(); self.critic_obs_normalizer.train()
+
+    def eval_mode(self):
+        self.alg.policy.eval()
+        if self.empirical_normalization:
+            self.obs_normalizer.eval(); self.critic_obs_normalizer.eval()
