@@ -131,19 +131,34 @@ __device__ __forceinline__ void k6_rank1_sub(K6& K, V3 n, V3 l, float s) {
   K.al[6] = fmaf(-ns.z, l.x, K.al[6]); K.al[7] = fmaf(-ns.z, l.y, K.al[7]); K.al[8] = fmaf(-ns.z, l.z, K.al[8]);
 }
 
-// one contact point at the iterate: edge residuals -> force vector and the 3x3 weight W = D * sum_active a a'
-// edges a_k = (0,mu,1) (0,-mu,1) (-mu,0,1) (mu,0,1)   (normal z, tangents y and -x: mju_makeFrame on the plane normal)
-__device__ __forceinline__ void point_eval(V3 e, float kap, float D, float mu, V3& F, float (&W)[5]) {
-  float j0 = fmaf(mu, e.y, e.z) + kap, j1 = fmaf(-mu, e.y, e.z) + kap;
-  float j2 = fmaf(-mu, e.x, e.z) + kap, j3 = fmaf(mu, e.x, e.z) + kap;
-  float a0 = j0 < 0.f ? D : 0.f, a1 = j1 < 0.f ? D : 0.f, a2 = j2 < 0.f ? D : 0.f, a3 = j3 < 0.f ? D : 0.f;
-  float f0 = -a0 * j0, f1 = -a1 * j1, f2 = -a2 * j2, f3 = -a3 * j3;
-  F = mk3(mu * (f3 - f2), mu * (f0 - f1), (f0 + f1) + (f2 + f3));
-  W[0] = mu * mu * (a2 + a3);    // xx
-  W[1] = mu * mu * (a0 + a1);    // yy
-  W[2] = (a0 + a1) + (a2 + a3);  // zz
-  W[3] = mu * (a3 - a2);         // xz
-  W[4] = mu * (a0 - a1);         // yz
+// one contact point at the iterate.  Edge residuals j_k = a_k . e + kappa over the four pyramid edges
+// a_k = (0,mu,1) (0,-mu,1) (-mu,0,1) (mu,0,1)   (normal z, tangents y and -x: mju_makeFrame on the plane normal);
+// an edge is active where j_k < 0, with force -D*j_k along a_k.
+struct Edges {
+  float j0, j1, j2, j3;
+};
+__device__ __forceinline__ Edges point_edges(V3 e, float kap, float mu) {
+  Edges E;
+  E.j0 = fmaf(mu, e.y, e.z) + kap; E.j1 = fmaf(-mu, e.y, e.z) + kap;
+  E.j2 = fmaf(-mu, e.x, e.z) + kap; E.j3 = fmaf(mu, e.x, e.z) + kap;
+  return E;
+}
+// contact force of the point (world axes)
+__device__ __forceinline__ V3 point_force(V3 e, float kap, float D, float mu) {
+  const Edges E = point_edges(e, kap, mu);
+  const float f0 = E.j0 < 0.f ? -D * E.j0 : 0.f, f1 = E.j1 < 0.f ? -D * E.j1 : 0.f;
+  const float f2 = E.j2 < 0.f ? -D * E.j2 : 0.f, f3 = E.j3 < 0.f ? -D * E.j3 : 0.f;
+  return mk3(mu * (f3 - f2), mu * (f0 - f1), (f0 + f1) + (f2 + f3));
+}
+// 3x3 weight W = D * sum_active a a'  as  xx yy zz xz yz
+__device__ __forceinline__ void point_weight(V3 e, float kap, float D, float mu, float (&W)[5]) {
+  const Edges E = point_edges(e, kap, mu);
+  const float a0 = E.j0 < 0.f ? D : 0.f, a1 = E.j1 < 0.f ? D : 0.f, a2 = E.j2 < 0.f ? D : 0.f, a3 = E.j3 < 0.f ? D : 0.f;
+  W[0] = mu * mu * (a2 + a3);
+  W[1] = mu * mu * (a0 + a1);
+  W[2] = (a0 + a1) + (a2 + a3);
+  W[3] = mu * (a3 - a2);
+  W[4] = mu * (a0 - a1);
 }
 __device__ __forceinline__ V3 w5_mul(const float (&W)[5], V3 g) {
   return mk3(W[0] * g.x + W[3] * g.z, W[1] * g.y + W[4] * g.z, W[3] * g.x + W[4] * g.y + W[2] * g.z);
@@ -161,14 +176,13 @@ __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const float (&W)[5]) {
 }
 // line-search contribution of one contact point: d1 += D*jar*jv, d2 += D*jv^2 over the edges active at ea
 __device__ __forceinline__ void point_ls(V3 ea, V3 us, float kap, float D, float mu, float& d1, float& d2) {
-  float j0 = fmaf(mu, ea.y, ea.z) + kap, j1 = fmaf(-mu, ea.y, ea.z) + kap;
-  float j2 = fmaf(-mu, ea.x, ea.z) + kap, j3 = fmaf(mu, ea.x, ea.z) + kap;
-  float v0 = fmaf(mu, us.y, us.z), v1 = fmaf(-mu, us.y, us.z), v2 = fmaf(-mu, us.x, us.z), v3 = fmaf(mu, us.x, us.z);
+  const Edges E = point_edges(ea, kap, mu);
+  const float v0 = fmaf(mu, us.y, us.z), v1 = fmaf(-mu, us.y, us.z), v2 = fmaf(-mu, us.x, us.z), v3 = fmaf(mu, us.x, us.z);
   float s1 = 0.f, s2 = 0.f;
-  if (j0 < 0.f) { s1 = fmaf(j0, v0, s1); s2 = fmaf(v0, v0, s2); }
-  if (j1 < 0.f) { s1 = fmaf(j1, v1, s1); s2 = fmaf(v1, v1, s2); }
-  if (j2 < 0.f) { s1 = fmaf(j2, v2, s1); s2 = fmaf(v2, v2, s2); }
-  if (j3 < 0.f) { s1 = fmaf(j3, v3, s1); s2 = fmaf(v3, v3, s2); }
+  if (E.j0 < 0.f) { s1 = fmaf(E.j0, v0, s1); s2 = fmaf(v0, v0, s2); }
+  if (E.j1 < 0.f) { s1 = fmaf(E.j1, v1, s1); s2 = fmaf(v1, v1, s2); }
+  if (E.j2 < 0.f) { s1 = fmaf(E.j2, v2, s1); s2 = fmaf(v2, v2, s2); }
+  if (E.j3 < 0.f) { s1 = fmaf(E.j3, v3, s1); s2 = fmaf(v3, v3, s2); }
   d1 = fmaf(D, s1, d1);
   d2 = fmaf(D, s2, d2);
 }
@@ -215,9 +229,47 @@ __device__ __forceinline__ void root_motion(const RootBasis& B, const float (&xr
   l = mk3(xr[0], xr[1], xr[2]) + cross(a, d);
 }
 
+// same about the pelvis origin itself (d = 0): rotation k is (c_k, 0)
+__device__ __forceinline__ void root_project_force0(const V3 (&c)[3], V3 n, V3 l, float (&out)[6]) {
+  out[0] = l.x; out[1] = l.y; out[2] = l.z;
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[3 + k] = dot(c[k], n);
+}
+__device__ __forceinline__ void root_project_k60(const V3 (&c)[3], const K6& K, float (&A)[21]) {
+  A[TI(0, 0)] += K.ll[0]; A[TI(1, 1)] += K.ll[1]; A[TI(2, 2)] += K.ll[2];
+  A[TI(1, 0)] += K.ll[3]; A[TI(2, 0)] += K.ll[4]; A[TI(2, 1)] += K.ll[5];
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    const V3 n = sym3_mul(K.aa, c[b]);
+    const V3 l = mk3(fmaf(K.al[0], c[b].x, fmaf(K.al[3], c[b].y, K.al[6] * c[b].z)), fmaf(K.al[1], c[b].x, fmaf(K.al[4], c[b].y, K.al[7] * c[b].z)),
+                     fmaf(K.al[2], c[b].x, fmaf(K.al[5], c[b].y, K.al[8] * c[b].z)));
+    A[TI(3 + b, 0)] += l.x; A[TI(3 + b, 1)] += l.y; A[TI(3 + b, 2)] += l.z;
+#pragma unroll
+    for (int a = 0; a <= b; a++) A[TI(3 + b, 3 + a)] += dot(c[a], n);
+  }
+}
+
+// joint axis in the link frame: hip_yaw z, hip_pitch y, hip_roll x, knee y, ankle_pitch y, ankle_roll x (h12_12dof.xml:71-96);
+// checked against the compiled model by build_params.  The index is warp-uniform, so the branches below do not diverge.
+__device__ __forceinline__ int joint_axis(int i) { return (0x146 >> (2 * i)) & 3; }
+__device__ __forceinline__ void rotate_rt(M3& R, int ax, float s, float c) {
+  if (ax == 2) rotate_sc<2>(R, s, c);
+  else if (ax == 1) rotate_sc<1>(R, s, c);
+  else rotate_sc<0>(R, s, c);
+}
+__device__ __forceinline__ V3 axis_rt(const M3& R, int ax) { return ax == 0 ? R.cx : (ax == 1 ? R.cy : R.cz); }
+__device__ __noinline__ float impedance_call(const float* si, float pos) { return impedance(si, pos); }
+
 // ----------------------------------------------------------------------------------------------------------
 // One physics substep.  State is updated in place.  tau = joint torques after the actuator's effort clip.
 // wl/wr: warm start in (if use_warm), solution out.
+//
+// Code-size discipline (profiles/r1d: the first version was instruction-fetch bound -- 242 KB of SASS, 65 % hit rate
+// in the SM instruction cache, the GPC instruction cache at 74 % of its request rate): every loop over joints or
+// contact points is rolled, per-joint inputs are staged in the shared-memory column so that rolled loops can index
+// them, each helper has one call site inside the Newton loop, and nothing is kept in registers between the
+// "evaluate" and "solve" halves of an iteration that can be re-derived from the contact list (the contact
+// stiffness is accumulated straight into the articulated inertia during the tip->root sweep).
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void substep(const KParams& P, const int side, const unsigned pm, float (&rp)[3],
                                      float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
@@ -227,6 +279,16 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
   const Smem sm{smem_raw + threadIdx.x};
   const KLeg& LG = P.leg[side];
   const float h = P.h;
+  const int j0 = 6 * side;
+  const V3 zero3 = mk3(0.f, 0.f, 0.f);
+  // ---- stage the per-joint inputs in the column: q -> F_XQ, qd -> F_FLC, tau -> F_FS, warm start -> F_R ----
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const float lim = P.frc[j0 + j];
+    sm.jf(j, F_XQ) = q[j]; sm.jf(j, F_FLC) = qd[j];
+    sm.jf(j, F_FS) = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
+    sm.jf(j, F_R) = wl[j];
+  }
   // ---- root frame (about O_r = pelvis origin) ----
   {
     float n = rsqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
@@ -238,106 +300,95 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
   const V3 acc0 = mk3(0.f, 0.f, P.gravity) + cross(v0, om0);  // root cacc: -gravity + free-joint cdof_dot * qvel
   const float m0 = P.root_mass + mass_add;
   const RI I0 = body_inertia(R0, mulv(R0, ld3(P.root_ipos)), m0, P.root_inertia, m0 / P.root_mass);
-  V3 f0n, f0l;  // bias force of the root link about O_r
+  float fs_root[6];  // first the bias force of the root link about O_r, then the smooth force of the root dofs
   {
     V3 an, al, vn, vl;
-    ri_apply(I0, mk3(0.f, 0.f, 0.f), acc0, an, al);
+    ri_apply(I0, zero3, acc0, an, al);
     ri_apply(I0, om0, v0, vn, vl);
-    f0n = an + cross(om0, vn) + cross(v0, vl);
-    f0l = al + cross(om0, vl);
+    const V3 c3[3] = {R0.cx, R0.cy, R0.cz};
+    root_project_force0(c3, an + cross(om0, vn) + cross(v0, vl), al + cross(om0, vl), fs_root);
   }
-  // ---- pass 1: joint sines/cosines and the ankle position d (O_s = O_r + d) ----
-  float sn[6], cs[6];
+  // ---- pass 1: joint sines/cosines (-> F_G, F_DG) and the ankle position d (O_s = O_r + d) ----
   V3 d;
   {
     M3 R = R0;
-    V3 x = mk3(0.f, 0.f, 0.f);
-#define P1_JOINT(i, AX)                        \
-  {                                            \
-    x = x + mulv(R, ld3(LG.pos[i]));           \
-    sincos_lim(q[i], sn[i], cs[i]);            \
-    rotate_sc<AX>(R, sn[i], cs[i]);            \
-  }
-    P1_JOINT(0, 2) P1_JOINT(1, 1) P1_JOINT(2, 0) P1_JOINT(3, 1) P1_JOINT(4, 1)
-    x = x + mulv(R, ld3(LG.pos[5]));
-    sincos_lim(q[5], sn[5], cs[5]);
-#undef P1_JOINT
+    V3 x = zero3;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+      x = x + mulv(R, ld3(LG.pos[i]));
+      float s, c;
+      sincos_lim(sm.jf(i, F_XQ), s, c);
+      sm.jf(i, F_G) = s; sm.jf(i, F_DG) = c;
+      rotate_rt(R, joint_axis(i), s, c);
+    }
     d = x;
   }
-  RootBasis RB, RB0;  // root dofs seen from O_s and from O_r
-  RB.c[0] = RB0.c[0] = R0.cx; RB.c[1] = RB0.c[1] = R0.cy; RB.c[2] = RB0.c[2] = R0.cz;
+  RootBasis RB;  // root dofs seen from O_s
+  RB.c[0] = R0.cx; RB.c[1] = R0.cy; RB.c[2] = R0.cz;
 #pragma unroll
-  for (int k = 0; k < 3; k++) { RB.rd[k] = cross(RB.c[k], d); RB0.rd[k] = mk3(0.f, 0.f, 0.f); }
+  for (int k = 0; k < 3; k++) RB.rd[k] = cross(RB.c[k], d);
   // ---- pass 2: kinematics about O_s, velocities, bias accelerations, link inertia and RNE link force ----
   M3 Rshin, Rfoot;
   V3 xshin, om_shin, vo_shin, om_foot, vo_foot;
   {
     M3 R = R0;
-    V3 x = mk3(0.f, 0.f, 0.f) - d, om = om0, vo = v0 + cross(om0, d), al = mk3(0.f, 0.f, 0.f), ao = acc0;
-#define LEG_JOINT(i, AX)                                                                    \
-  {                                                                                         \
-    x = x + mulv(R, ld3(LG.pos[i]));                                                        \
-    V3 wi = axis_col<AX>(R);                                                                \
-    V3 ui = cross(x, wi);                                                                   \
-    V3 sdw = cross(om, wi), sdu = cross(om, ui) + cross(vo, wi);                            \
-    al = fma3(sdw, qd[i], al); ao = fma3(sdu, qd[i], ao);                                   \
-    om = fma3(wi, qd[i], om); vo = fma3(ui, qd[i], vo);                                     \
-    rotate_sc<AX>(R, sn[i], cs[i]);                                                         \
-    sm.sjv(i, F_W, wi); sm.sjv(i, F_U, ui);                                                 \
-    RI Ii = body_inertia(R, x + mulv(R, ld3(LG.ipos[i])), LG.mass[i], LG.inertia[i], 1.f);  \
-    sm.sji(i, Ii);                                                                          \
-    V3 an, aL, vn, vL;                                                                      \
-    ri_apply(Ii, al, ao, an, aL);                                                           \
-    ri_apply(Ii, om, vo, vn, vL);                                                           \
-    sm.sjv(i, F_X, an + cross(om, vn) + cross(vo, vL));                                     \
-    sm.sjv(i, F_X + 3, aL + cross(om, vL));                                                 \
-  }
-    LEG_JOINT(0, 2)
-    LEG_JOINT(1, 1)
-    LEG_JOINT(2, 0)
-    LEG_JOINT(3, 1)
-    Rshin = R; xshin = x; om_shin = om; vo_shin = vo;
-    LEG_JOINT(4, 1)
-    LEG_JOINT(5, 0)
+    V3 x = zero3 - d, om = om0, vo = v0 + cross(om0, d), al = zero3, ao = acc0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+      const int ax = joint_axis(i);
+      const float qdi = sm.jf(i, F_FLC);
+      x = x + mulv(R, ld3(LG.pos[i]));
+      const V3 wi = axis_rt(R, ax);
+      const V3 ui = cross(x, wi);
+      const V3 sdw = cross(om, wi), sdu = cross(om, ui) + cross(vo, wi);
+      al = fma3(sdw, qdi, al); ao = fma3(sdu, qdi, ao);
+      om = fma3(wi, qdi, om); vo = fma3(ui, qdi, vo);
+      rotate_rt(R, ax, sm.jf(i, F_G), sm.jf(i, F_DG));
+      sm.sjv(i, F_W, wi); sm.sjv(i, F_U, ui);
+      const RI Ii = body_inertia(R, x + mulv(R, ld3(LG.ipos[i])), LG.mass[i], LG.inertia[i], 1.f);
+      sm.sji(i, Ii);
+      V3 an, aL, vn, vL;
+      ri_apply(Ii, al, ao, an, aL);
+      ri_apply(Ii, om, vo, vn, vL);
+      sm.sjv(i, F_X, an + cross(om, vn) + cross(vo, vL));
+      sm.sjv(i, F_X + 3, aL + cross(om, vL));
+      if (i == 3) { Rshin = R; xshin = x; om_shin = om; vo_shin = vo; }
+    }
     Rfoot = R; om_foot = om; vo_foot = vo;
-#undef LEG_JOINT
   }
   // ---- smooth forces: tau - bias - damping*v ; dof-row constants (friction loss, joint limits) ----
-  float fs_root[6];
   {
-    V3 fcn = mk3(0.f, 0.f, 0.f), fcl = fcn;
-#pragma unroll
+    V3 fcn = zero3, fcl = zero3;
+#pragma unroll 1
     for (int j = 5; j >= 0; j--) {
       fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
-      const int dj = 6 + 6 * side + j, jj = 6 * side + j;
-      const float lim = P.frc[jj];
-      const float t = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
-      const float fs = t - (dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl)) - P.damping[dj] * qd[j];
+      const int jj = j0 + j;
+      const float qj = sm.jf(j, F_XQ), qdj = sm.jf(j, F_FLC);
+      const float fs = sm.jf(j, F_FS) - (dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl)) - P.damping[6 + jj] * qdj;
       sm.jf(j, F_FS) = fs;
       sm.jf(j, F_XQ) = 0.f; sm.jf(j, F_MA) = -fs; sm.jf(j, F_G) = 0.f;
-      sm.jf(j, F_FLC) = P.floss_B * qd[j];
-      const float dlo = q[j] - P.range_lo[jj], dhi = P.range_hi[jj] - q[j];
+      sm.jf(j, F_FLC) = P.floss_B * qdj;
+      const float dlo = qj - P.range_lo[jj], dhi = P.range_hi[jj] - qj;
       const float sig = dlo < 0.f ? 1.f : (dhi < 0.f ? -1.f : 0.f);
       float lc = 0.f, lD = 0.f;
       if (sig != 0.f) {
         const float dist = dlo < 0.f ? dlo : dhi;
-        const float imp = impedance(P.limit_imp, dist);
-        lc = sig * P.limit_B * qd[j] + P.limit_K * imp * dist;
+        const float imp = impedance_call(P.limit_imp, dist);
+        lc = sig * P.limit_B * qdj + P.limit_K * imp * dist;
         lD = sig / fmaxf(1e-15f, (1.f - imp) * P.limit_invw[jj] / imp);
       }
       sm.jf(j, F_LIMC) = lc; sm.jf(j, F_LIMD) = lD;
-      sm.jf(j, F_R) = wl[j];  // warm start (consumed by phase 0)
     }
-    float bl[6], b0[6];
+    float bl[6];
     root_project_force(RB, fcn, fcl, bl);
-    root_project_force(RB0, f0n, f0l, b0);
 #pragma unroll
-    for (int k = 0; k < 6; k++) fs_root[k] = -(b0[k] + pair_sum(bl[k], pm)) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
+    for (int k = 0; k < 6; k++) fs_root[k] = -(fs_root[k] + pair_sum(bl[k], pm)) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
   }
-  float rfl_c[3];  // friction-loss rows of the root dofs 3*side..3*side+2 owned by this lane
+  float rfl_c[3];  // friction-loss row offsets of the root dofs 3*side..3*side+2 owned by this lane
 #pragma unroll
   for (int k = 0; k < 3; k++) rfl_c[k] = P.floss_B * (side == 0 ? rv[k] : rw[k]);
-  // contact candidates -> compact active list, ordered foot | shin | torso | pelvis (feet, shins about O_s; root about O_r)
+  // ---- contact candidates -> compact active list, ordered foot | shin | torso | pelvis (feet, shins about O_s; root about O_r).
+  //      Slot 3..5 of a point holds the row residual e = J x + B*velocity at the current iterate x (x = 0 here). ----
   int n_foot = 0, e_shin = 0, e_torso = 0, nact = 0, overflow = 0;
   {
     const float pz = rp[2];
@@ -349,11 +400,11 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
       M3 Rb;
       float rad, href;
       int slot;
-      if (p < 4) { lp = ld3(LG.foot_pt[p]); Rb = Rfoot; xb = mk3(0.f, 0.f, 0.f); omb = om_foot; vob = vo_foot; rad = 0.f; slot = side; href = pz + d.z; }
+      if (p < 4) { lp = ld3(LG.foot_pt[p]); Rb = Rfoot; xb = zero3; omb = om_foot; vob = vo_foot; rad = 0.f; slot = side; href = pz + d.z; }
       else if (p < 6) { lp = ld3(LG.shin_pt[p - 4]); Rb = Rshin; xb = xshin; omb = om_shin; vob = vo_shin; rad = LG.shin_rad; slot = 2 + side; href = pz + d.z; }
       else {
         const int rpi = p < 10 ? 4 * side + (p - 6) : 8;
-        lp = ld3(P.root_pt[rpi]); Rb = R0; xb = mk3(0.f, 0.f, 0.f); omb = om0; vob = v0; rad = P.root_rad[rpi]; slot = p < 10 ? 4 : 5; href = pz;
+        lp = ld3(P.root_pt[rpi]); Rb = R0; xb = zero3; omb = om0; vob = v0; rad = P.root_rad[rpi]; slot = p < 10 ? 4 : 5; href = pz;
       }
       const V3 c = xb + mulv(Rb, lp);
       const float dist = href + c.z - rad;
@@ -361,7 +412,7 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
         if (nact < MAXC) {
           const V3 rc = mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
           const V3 vel = vob + cross(omb, rc);
-          const float imp = impedance(P.contact_imp, dist);
+          const float imp = impedance_call(P.contact_imp, dist);
           const float tr = P.slot_tran[slot];
           const float Rn = fmaxf(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);
           sm.pf(nact, 0) = rc.x; sm.pf(nact, 1) = rc.y; sm.pf(nact, 2) = rc.z;
@@ -378,40 +429,33 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
   }
 
   // ---- iterate state: per-joint scalars live in the shared-memory column, root 6-vectors in registers ----
-  float xr[6], Mar[6], jr[6], rr[6], dgr[6], Msr[6];
-  K6 Kf, Ks;     // contact stiffness of the foot / shin links about O_s
-  float Ar[21];  // this lane's share of root-block increments from root contact points (about O_r)
-  V3 F_foot = mk3(0, 0, 0), F_shin = F_foot, F_torso = F_foot, F_pelvis = F_foot;
+  float xr[6], Mar[6], jr[6], rr[6], Msr[6];
+  V3 Wl_f = zero3, Wl_s = zero3, F_torso = zero3, F_pelvis = zero3;  // net contact forces per body at the last evaluation
   int it = 0, capped = 0;
-  const V3 zero3 = mk3(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = wr[i]; dgr[i] = 0.f; }
-  const float* arm = P.armature + 6 + 6 * side;
-  const float* dmp = P.damping + 6 + 6 * side;
-  const float* flD = P.floss_D + 6 + 6 * side;
-  const float* flL = P.floss_lim + 6 + 6 * side;
-  const float* flF = P.floss + 6 + 6 * side;
+  for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = wr[i]; }
+  const float* arm = P.armature + 6 + j0;
+  const float* flD = P.floss_D + 6 + j0;
+  const float* flL = P.floss_lim + 6 + j0;
+  const float* flF = P.floss + 6 + j0;
+  const V3 c3[3] = {R0.cx, R0.cy, R0.cz};
 
   // phase 0: inject the warm start (x = 0 -> previous acceleration, unit step); 1: Newton; 2: implicitfast update
   int phase = use_warm ? 0 : 1;
 #pragma unroll 1
   for (;;) {
+    float dg_own[3] = {0.f, 0.f, 0.f};  // extra Hessian diagonal of this lane's three root rows
     if (phase == 1) {
-      // ---- evaluate all rows at x: forces, gradient pieces, Hessian increments ----
+      // ---- evaluate all rows at x: forces and gradient ----
       float gr_own[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { gr_own[k] = 0.f; dgr[k] = 0.f; }
+      for (int k = 0; k < 6; k++) gr_own[k] = 0.f;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const int dk = 3 * side + k;
-        float act;
-        gr_own[dk] = floss_force(xr[dk] + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
-        dgr[dk] = act;
+        const float f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], dg_own[k]);
+        if (side == 0) gr_own[k] = f; else gr_own[3 + k] = f;
       }
-      V3 Va_r, Vl_r, Va_s, Vl_s, Va_f, Vl_f;  // body "velocities" of the iterate about O_r (root) and O_s (shin, foot)
-      root_motion(RB0, xr, zero3, Va_r, Vl_r);
-      root_motion(RB, xr, d, Va_f, Vl_f);
-      Va_s = Va_f; Vl_s = Vl_f;
 #pragma unroll 1
       for (int j = 0; j < 6; j++) {
         const float x = sm.jf(j, F_XQ);
@@ -424,42 +468,29 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
         f += sig * (-la * jar);
         sm.jf(j, F_G) = f;
         sm.jf(j, F_DG) = act + la;
-        Va_f = fma3(sm.jv(j, F_W), x, Va_f); Vl_f = fma3(sm.jv(j, F_U), x, Vl_f);
-        if (j == 3) { Va_s = Va_f; Vl_s = Vl_f; }
       }
-      F_foot = F_shin = F_torso = F_pelvis = zero3;
-#pragma unroll
-      for (int i = 0; i < 21; i++) Ar[i] = 0.f;
-      k6_zero(Kf); k6_zero(Ks);
-      V3 Wn_f = zero3, Wl_f = zero3, Wn_s = zero3, Wl_s = zero3, Wn_r = zero3, Wl_r = zero3;
+      V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
+      Wl_f = Wl_s = F_torso = F_pelvis = zero3;
 #pragma unroll 1
       for (int p = 0; p < nact; p++) {
-        const V3 r = sm.pv(p, 0), ub = sm.pv(p, 3);
-        const int tag = p < n_foot ? 0 : (p < e_shin ? 1 : (p < e_torso ? 2 : 3));
-        const V3 Va = tag == 0 ? Va_f : (tag == 1 ? Va_s : Va_r), Vl = tag == 0 ? Vl_f : (tag == 1 ? Vl_s : Vl_r);
-        const V3 e = Vl + cross(Va, r) + ub;
-        V3 Fp;
-        float Wp[5];
-        point_eval(e, sm.pf(p, 6), sm.pf(p, 7), mu, Fp, Wp);
+        const V3 r = sm.pv(p, 0);
+        const V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
         const V3 mom = cross(r, Fp);
-        if (tag == 0) { k6_add_point(Kf, r, Wp); Wn_f = Wn_f + mom; Wl_f = Wl_f + Fp; F_foot = F_foot + Fp; }
-        else if (tag == 1) { k6_add_point(Ks, r, Wp); Wn_s = Wn_s + mom; Wl_s = Wl_s + Fp; F_shin = F_shin + Fp; }
-        else {
-          K6 Kp;
-          k6_zero(Kp);
-          k6_add_point(Kp, r, Wp);
-          root_project_k6(RB0, Kp, Ar);
-          Wn_r = Wn_r + mom; Wl_r = Wl_r + Fp;
-          if (tag == 2) F_torso = F_torso + Fp; else F_pelvis = F_pelvis + Fp;
-        }
+        const float isf = p < n_foot ? 1.f : 0.f, iss = (p >= n_foot && p < e_shin) ? 1.f : 0.f, isr = p >= e_shin ? 1.f : 0.f;
+        const float ist = (p >= e_shin && p < e_torso) ? 1.f : 0.f;
+        Wn_f = fma3(mom, isf, Wn_f); Wl_f = fma3(Fp, isf, Wl_f);
+        Wn_s = fma3(mom, iss, Wn_s); Wl_s = fma3(Fp, iss, Wl_s);
+        Wn_r = fma3(mom, isr, Wn_r); Wl_r = fma3(Fp, isr, Wl_r);
+        F_torso = fma3(Fp, ist, F_torso);
       }
+      F_pelvis = Wl_r - F_torso;
       const V3 Wn_leg = Wn_f + Wn_s, Wl_leg = Wl_f + Wl_s;  // wrench of the leg contacts about O_s
       {
         float t6[6];
         root_project_force(RB, Wn_leg, Wl_leg, t6);
 #pragma unroll
         for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
-        root_project_force(RB0, Wn_r, Wl_r, t6);
+        root_project_force0(c3, Wn_r, Wl_r, t6);
 #pragma unroll
         for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
       }
@@ -484,12 +515,11 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
     if (phase == 2) {
       // implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f
 #pragma unroll 1
-      for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * dmp[j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
+      for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * P.damping[6 + j0 + j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
 #pragma unroll
-      for (int k = 0; k < 6; k++) { dgr[k] = 0.5f * h * P.damping[k]; rr[k] = fs_root[k] + jr[k]; }  // halves are pair-summed
+      for (int k = 0; k < 6; k++) rr[k] = fs_root[k] + jr[k];
     }
     // ---- ABA sweep 1 (tip -> root): articulated inertia and reduced rhs.  Skipped for the warm-start injection. ----
-    V3 aa, al;  // acceleration of the parent link of joint 0 (the root, about O_s)
     if (phase != 0) {
       K6 IA;
       k6_zero(IA);
@@ -498,8 +528,15 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
 #pragma unroll 1
       for (int j = 5; j >= 0; j--) {
         k6_add_rigid(IA, sm.ji(j));
-        if (kc && j == 5 && n_foot) k6_add(IA, Kf);
-        if (kc && j == 3 && e_shin > n_foot) k6_add(IA, Ks);
+        if (kc && (j == 5 || j == 3)) {  // contact stiffness of the foot / shin link, straight into the articulated inertia
+          const int p1 = j == 5 ? n_foot : e_shin;
+#pragma unroll 1
+          for (int p = j == 5 ? 0 : n_foot; p < p1; p++) {
+            float Wp[5];
+            point_weight(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu, Wp);
+            k6_add_point(IA, sm.pv(p, 0), Wp);
+          }
+        }
         const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
         V3 n, l;
         k6_apply(IA, wj, uj, n, l);
@@ -511,48 +548,66 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
         const float td = t * dinv;
         pn = fma3(n, td, pn); pl = fma3(l, td, pl);
       }
-      // root block: own link + hand-offs of both legs (joint space) + diagonal; 6x6 Cholesky on both lanes
+      // root block: hand-offs of both legs (joint space) + own link + root contact points + diagonal; 6x6 Cholesky on both lanes
       float A[21], g[6];
 #pragma unroll
-      for (int i = 0; i < 21; i++) A[i] = kc ? Ar[i] : 0.f;
+      for (int i = 0; i < 21; i++) A[i] = 0.f;
       root_project_k6(RB, IA, A);
       root_project_force(RB, pn, pl, g);
-#pragma unroll
-      for (int k = 0; k < 6; k++) A[TI(k, k)] += dgr[k];
       {
-        K6 K0;
-        k6_zero(K0);
-        k6_add_rigid(K0, I0);
-        float A0[21];
-#pragma unroll
-        for (int i = 0; i < 21; i++) A0[i] = 0.f;
-        root_project_k6(RB0, K0, A0);
-#pragma unroll
-        for (int i = 0; i < 21; i++) A[i] = A0[i] + pair_sum(A[i], pm);
+        RI Ih = I0;  // half of the root link on each lane: the pair sum below restores it exactly
+        Ih.m *= 0.5f; Ih.mc = Ih.mc * 0.5f;
+        Ih.xx *= 0.5f; Ih.yy *= 0.5f; Ih.zz *= 0.5f; Ih.xy *= 0.5f; Ih.xz *= 0.5f; Ih.yz *= 0.5f;
+        k6_zero(IA);
+        k6_add_rigid(IA, Ih);
+        if (kc) {
+#pragma unroll 1
+          for (int p = e_shin; p < nact; p++) {
+            float Wp[5];
+            point_weight(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu, Wp);
+            k6_add_point(IA, sm.pv(p, 0), Wp);
+          }
+        }
+        root_project_k60(c3, IA, A);
+      }
+      if (phase == 1) {
+        if (side == 0) { A[TI(0, 0)] += dg_own[0]; A[TI(1, 1)] += dg_own[1]; A[TI(2, 2)] += dg_own[2]; }
+        else { A[TI(3, 3)] += dg_own[0]; A[TI(4, 4)] += dg_own[1]; A[TI(5, 5)] += dg_own[2]; }
       }
 #pragma unroll
-      for (int k = 0; k < 6; k++) { A[TI(k, k)] += P.armature[k]; rr[k] -= pair_sum(g[k], pm); }
+      for (int i = 0; i < 21; i++) A[i] = pair_sum(A[i], pm);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        A[TI(k, k)] += P.armature[k] + (phase == 2 ? h * P.damping[k] : 0.f);
+        rr[k] -= pair_sum(g[k], pm);
+      }
       float inva[6];
       chol6(A, inva);
       fwd6(A, inva, rr);
       bwd6(A, inva, rr);
     }
-    root_motion(RB, rr, d, aa, al);
-    // ---- sweep 2 (root -> tip): joint accelerations; the same sweep starts the M-product of the direction ----
+    // ---- sweep 2 (root -> tip): joint accelerations; the same sweep starts the M-product of the direction and
+    //      leaves the direction's body accelerations (root about O_r; shin, foot about O_s) for the line search ----
+    V3 Sa_r, Sl_r, Sa_s, Sl_s, Sa_f, Sl_f;
+    Sa_r = fma3(c3[0], rr[3], fma3(c3[1], rr[4], c3[2] * rr[5]));
+    Sl_r = mk3(rr[0], rr[1], rr[2]);
+    Sa_f = Sa_r; Sl_f = Sl_r + cross(Sa_r, d);
+    Sa_s = Sa_f; Sl_s = Sl_f;
     float smax = 0.f;
     const bool solve = phase != 0, need_ms = phase != 2;
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {
       float s = sm.jf(j, F_R);
       if (solve) {
-        s = (s - (dot(sm.jv(j, F_X), aa) + dot(sm.jv(j, F_X + 3), al))) * sm.jf(j, F_DINV);
+        s = (s - (dot(sm.jv(j, F_X), Sa_f) + dot(sm.jv(j, F_X + 3), Sl_f))) * sm.jf(j, F_DINV);
         sm.jf(j, F_R) = s;
       }
       smax = fmaxf(smax, fabsf(s));
-      aa = fma3(sm.jv(j, F_W), s, aa); al = fma3(sm.jv(j, F_U), s, al);
+      Sa_f = fma3(sm.jv(j, F_W), s, Sa_f); Sl_f = fma3(sm.jv(j, F_U), s, Sl_f);
+      if (j == 3) { Sa_s = Sa_f; Sl_s = Sl_f; }
       if (need_ms) {
         V3 n, l;
-        ri_apply(sm.ji(j), aa, al, n, l);
+        ri_apply(sm.ji(j), Sa_f, Sl_f, n, l);
         sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
       }
     }
@@ -577,10 +632,9 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
       }
       float bl[6], b0[6];
       root_project_force(RB, fcn, fcl, bl);
-      V3 a0, l0, n0, f0;
-      root_motion(RB0, rr, zero3, a0, l0);
-      ri_apply(I0, a0, l0, n0, f0);
-      root_project_force(RB0, n0, f0, b0);
+      V3 n0, f0;
+      ri_apply(I0, Sa_r, Sl_r, n0, f0);
+      root_project_force0(c3, n0, f0, b0);
 #pragma unroll
       for (int k = 0; k < 6; k++) Msr[k] = b0[k] + pair_sum(bl[k], pm) + P.armature[k] * rr[k];
     }
@@ -591,22 +645,6 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
 #pragma unroll
       for (int k = 0; k < 6; k++) { sMs = fmaf(rr[k], Msr[k], sMs); sMa = fmaf(rr[k], Mar[k], sMa); gs = fmaf(rr[k], jr[k], gs); }
       const float d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
-      V3 Va_r, Vl_r, Va_s, Vl_s, Va_f, Vl_f, Sa_r, Sl_r, Sa_s, Sl_s, Sa_f, Sl_f;
-      if (nact) {
-        root_motion(RB0, xr, zero3, Va_r, Vl_r);
-        root_motion(RB, xr, d, Va_f, Vl_f);
-        root_motion(RB0, rr, zero3, Sa_r, Sl_r);
-        root_motion(RB, rr, d, Sa_f, Sl_f);
-        Va_s = Va_f; Vl_s = Vl_f; Sa_s = Sa_f; Sl_s = Sl_f;
-#pragma unroll 1
-        for (int j = 0; j < 6; j++) {
-          const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
-          const float x = sm.jf(j, F_XQ), s = sm.jf(j, F_R);
-          Va_f = fma3(wj, x, Va_f); Vl_f = fma3(uj, x, Vl_f);
-          Sa_f = fma3(wj, s, Sa_f); Sl_f = fma3(uj, s, Sl_f);
-          if (j == 3) { Va_s = Va_f; Vl_s = Vl_f; Sa_s = Sa_f; Sl_s = Sl_f; }
-        }
-      }
       float lo = 0.f, hi = 1e30f;
 #pragma unroll 1
       for (int ls = 0; ls < 12; ls++) {
@@ -628,22 +666,18 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           const int dk = 3 * side + k;
+          const float sk = side == 0 ? rr[k] : rr[3 + k], xk = side == 0 ? xr[k] : xr[3 + k];
           float act;
-          const float f = floss_force(fmaf(alpha, rr[dk], xr[dk]) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
-          d1 = fmaf(-f, rr[dk], d1); d2 = fmaf(act * rr[dk], rr[dk], d2);
+          const float f = floss_force(fmaf(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
+          d1 = fmaf(-f, sk, d1); d2 = fmaf(act * sk, sk, d2);
         }
-        if (nact) {
-          const V3 Ea_f = fma3(Sa_f, alpha, Va_f), El_f = fma3(Sl_f, alpha, Vl_f);
-          const V3 Ea_s = fma3(Sa_s, alpha, Va_s), El_s = fma3(Sl_s, alpha, Vl_s);
-          const V3 Ea_r = fma3(Sa_r, alpha, Va_r), El_r = fma3(Sl_r, alpha, Vl_r);
 #pragma unroll 1
-          for (int p = 0; p < nact; p++) {
-            const V3 r = sm.pv(p, 0), ub = sm.pv(p, 3);
-            const bool isf = p < n_foot, iss = p < e_shin;
-            const V3 Ea = isf ? Ea_f : (iss ? Ea_s : Ea_r), El = isf ? El_f : (iss ? El_s : El_r);
-            const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
-            point_ls(El + cross(Ea, r) + ub, Sl + cross(Sa, r), sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
-          }
+        for (int p = 0; p < nact; p++) {
+          const V3 r = sm.pv(p, 0);
+          const bool isf = p < n_foot, iss = p < e_shin;
+          const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
+          const V3 us = Sl + cross(Sa, r);
+          point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
         d1 = pair_sum(d1, pm) + fmaf(alpha, sMs, sMa);
         d2 = pair_sum(d2, pm) + sMs;
@@ -656,6 +690,7 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
         if (tiny) break;
       }
     }
+    // ---- take the step: x += alpha s ; M x - f += alpha M s ; row residuals of the contact points += alpha J s ----
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {
       sm.jf(j, F_XQ) = fmaf(alpha, sm.jf(j, F_R), sm.jf(j, F_XQ));
@@ -663,16 +698,22 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) { xr[i] = fmaf(alpha, rr[i], xr[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]); }
+#pragma unroll 1
+    for (int p = 0; p < nact; p++) {
+      const V3 r = sm.pv(p, 0);
+      const bool isf = p < n_foot, iss = p < e_shin;
+      const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
+      const V3 e = fma3(Sl + cross(Sa, r), alpha, sm.pv(p, 3));
+      sm.pf(p, 3) = e.x; sm.pf(p, 4) = e.y; sm.pf(p, 5) = e.z;
+    }
     phase = 1;
   }
-  float rl[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) rl[j] = sm.jf(j, F_R);
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    out.qacc[j] = rl[j]; wl[j] = rl[j]; wr[j] = rr[j];
-    qd[j] = fmaf(h, rl[j], qd[j]); q[j] = fmaf(h, qd[j], q[j]);
+    const float a = sm.jf(j, F_R);
+    out.qacc[j] = a; wl[j] = a; wr[j] = rr[j];
+    qd[j] = fmaf(h, a, qd[j]); q[j] = fmaf(h, qd[j], q[j]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, rr[k], rv[k]); rw[k] = fmaf(h, rr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
@@ -691,7 +732,7 @@ __device__ __forceinline__ void substep(const KParams& P, const int side, const 
     float n = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
     rq[0] = nw * n; rq[1] = nx * n; rq[2] = ny * n; rq[3] = nz * n;
   }
-  out.F_foot = F_foot; out.F_shin = F_shin; out.F_torso = F_torso; out.F_pelvis = F_pelvis;
+  out.F_foot = Wl_f; out.F_shin = Wl_s; out.F_torso = F_torso; out.F_pelvis = F_pelvis;
   out.iters = it; out.capped = capped; out.overflow = overflow;
 }
 

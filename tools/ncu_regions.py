@@ -4,10 +4,10 @@ usage: python tools/ncu_regions.py <rep> <libh1v2_b200.so>"""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, so = sys.argv[1], sys.argv[2]
-PHYS = [(222, 248, "root frame"), (249, 266, "pass1 sincos/ankle"), (267, 304, "pass2 kinematics+RNE"), (305, 339, "smooth forces/rows"),
-        (340, 378, "contact candidates"), (379, 398, "iterate init"), (399, 483, "newton: evaluate rows"), (484, 490, "phase2 rhs"),
-        (491, 513, "ABA sweep1"), (514, 539, "root 6x6"), (540, 558, "ABA sweep2"), (559, 565, "step-tol exit"), (566, 586, "M-product"),
-        (587, 658, "line search"), (659, 667, "iterate update"), (668, 696, "integrate")]
+PHYS = [(274, 310, "stage+root frame"), (311, 329, "pass1 sincos/ankle"), (330, 358, "pass2 kinematics+RNE"), (359, 389, "smooth forces/rows"),
+        (390, 430, "contact candidates"), (431, 447, "iterate init"), (448, 514, "newton: evaluate rows"), (515, 521, "phase2 rhs"),
+        (522, 555, "ABA sweep1"), (556, 588, "root 6x6"), (589, 614, "ABA sweep2"), (615, 620, "step-tol exit"), (621, 640, "M-product"),
+        (641, 692, "line search"), (693, 710, "iterate update"), (711, 740, "integrate")]
 STEP = [(134, 171, "obs: sample+noise"), (172, 212, "obs: flatten/emit"), (214, 256, "load state"), (257, 271, "action"),
         (272, 306, "PD+sensor loop"), (307, 331, "guards/terminations"), (332, 403, "rewards"), (404, 460, "epsum/diag/stats"),
         (461, 489, "reset"), (490, 509, "command/push"), (510, 533, "store state")]
@@ -16,7 +16,7 @@ STEP = [(134, 171, "obs: sample+noise"), (172, 212, "obs: flatten/emit"), (214, 
 def region(chain):
     # chain: innermost -> outermost list of (file, line)
     for f, ln in reversed(chain):
-        if f == "h1v2_physics.cuh" and ln >= 222:
+        if f == "h1v2_physics.cuh" and ln >= 274:
             for a, b, n in PHYS:
                 if a <= ln <= b:
                     return "phys: " + n
@@ -59,6 +59,11 @@ for l in dis:
 static = collections.Counter()
 for a, ch in amap.items():
     static[region(ch)] += 16
+if rep == "-":
+    print(f"static SASS {sum(static.values()):,} B")
+    for k, v in sorted(static.items(), key=lambda kv: -kv[1]):
+        print(f"{k:34s} {v:11,d}")
+    sys.exit(0)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
