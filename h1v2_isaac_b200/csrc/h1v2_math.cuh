@@ -187,12 +187,17 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 #define STREAM_CMD 2u
 #define STREAM_EVENT 3u
 #define STREAM_ACTIONS 7u
-__device__ __noinline__ void rng4(uint32_t key0, int64_t gid, unsigned long long step, uint32_t stream, uint32_t block,
-                                     float (&u)[4]) {
+// out-of-line (one copy of the 10 Philox rounds), result returned by value so that no caller array has its address taken
+__device__ __noinline__ float4 rng4v(uint32_t key0, uint32_t gid, uint32_t step_lo, uint32_t step_hi, uint32_t stream, uint32_t block) {
   uint32_t o[4];
-  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), stream, block, key0, (uint32_t)gid, o);
-#pragma unroll
-  for (int i = 0; i < 4; i++) u[i] = (float)(o[i] >> 8) * (1.0f / 16777216.0f);
+  philox4x32_10(step_lo, step_hi, stream, block, key0, gid, o);
+  const float k = 1.0f / 16777216.0f;
+  return make_float4((float)(o[0] >> 8) * k, (float)(o[1] >> 8) * k, (float)(o[2] >> 8) * k, (float)(o[3] >> 8) * k);
+}
+__device__ __forceinline__ void rng4(uint32_t key0, int64_t gid, unsigned long long step, uint32_t stream, uint32_t block,
+                                     float (&u)[4]) {
+  const float4 r = rng4v(key0, (uint32_t)gid, (uint32_t)step, (uint32_t)(step >> 32), stream, block);
+  u[0] = r.x; u[1] = r.y; u[2] = r.z; u[3] = r.w;
 }
 __device__ __forceinline__ float uni(float u, float lo, float hi) { return lo + (hi - lo) * u; }
 

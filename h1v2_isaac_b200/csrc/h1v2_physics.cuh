@@ -271,12 +271,12 @@ __device__ __noinline__ float impedance_call(const float* si, float pos) { retur
 // "evaluate" and "solve" halves of an iteration that can be re-derived from the contact list (the contact
 // stiffness is accumulated straight into the articulated inertia during the tip->root sweep).
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void substep(const KParams& P, const int side, const unsigned pm, float (&rp)[3],
+__device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, const unsigned pm, float (&rp)[3],
                                      float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
                                      const float (&tau)[6], const float mu, const float mass_add, float (&wl)[6], float (&wr)[6],
                                      const bool use_warm, SubOut& out) {
   extern __shared__ float smem_raw[];
-  const Smem sm{smem_raw + threadIdx.x};
+  const Smem sm{smem_raw + tid};
   const KLeg& LG = P.leg[side];
   const float h = P.h;
   const int j0 = 6 * side;

@@ -45,7 +45,7 @@ struct CmdState {
   float c[3], heading_target, time_left, m_xy, m_yaw;
   int flags;
 };
-__device__ __noinline__ void resample_command(const KParams& P, CmdState& c, int64_t gid, unsigned long long step, uint32_t block0) {
+__device__ __forceinline__ void resample_command(const KParams& P, CmdState& c, int64_t gid, unsigned long long step, uint32_t block0) {
   float u[4], v[4];
   rng4(P.key0, gid, step, STREAM_CMD, block0, u);
   rng4(P.key0, gid, step, STREAM_CMD, block0 + 1, v);
@@ -61,7 +61,7 @@ __device__ __noinline__ void resample_command(const KParams& P, CmdState& c, int
 }
 
 // reset of one env (reset_root_state_uniform, reset_joints_by_scale, manager resets); both lanes compute the root
-__device__ __noinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
+__device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
                                           float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
                                           float (&la)[6], float (&T1)[6], float (&T2)[6], float4& timers, CmdState& cmd,
                                           float& push_left) {
@@ -131,7 +131,7 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
 }
 
 // observation sample of this step -> history ring slot `head`; then the warp cooperatively emits the flattened rows
-__device__ __forceinline__ void emit_observation(const KParams& P, const KState& S, int env, int side, bool valid, int64_t gid,
+__device__ __forceinline__ void emit_observation(const KParams& P, const KState& S, unsigned tid, unsigned bid, int env, int side, bool valid, int64_t gid,
                                                  unsigned long long step, int head, const RootDerived& rd, const CmdState& cmd,
                                                  const float (&q)[6], const float (&qd)[6], const float (&la)[6], float* obs) {
   const int H = P.H;
@@ -172,41 +172,42 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   __syncwarp();
   // cooperative flatten: term-major, oldest -> newest inside each term block
   // (packages/biped_tasks/biped_tasks/utils/history/observation_manager.py:335-355, circular_buffer.py:79-87,131-135)
-  // Each lane owns output columns lane, lane+32, ...; their (history index, sample offset) is the same for every env,
-  // so it is decoded once, and the loads of one env row are issued back to back (memory-level parallelism).
-  const int lane = threadIdx.x & 31;
-  const int warp_env0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 1;
+  // Each lane owns output columns lane, lane+32, ...; their source offset inside an env's ring is the same for every env,
+  // so it is decoded once; the loads of one env row are issued back to back (memory-level parallelism).
+  const int lane = tid & 31;
+  const int warp_env0 = (bid * H1V2_BLOCK + (tid & ~31u)) >> 1;
   constexpr int MAXPASS = (H1V2_MAX_HISTORY * H1V2_OBS_TERM_DIM + 31) / 32;
   const int npass = (P.obs_dim + 31) >> 5;
-  int soff[MAXPASS], hoff[MAXPASS];  // offset inside the ring for a non-fresh env / offset of the slot to back-fill
+  int soff[MAXPASS], foff[MAXPASS];  // source offset in the ring: regular env / fresh env (every slot reads the newest sample)
 #pragma unroll
   for (int i = 0; i < MAXPASS; i++) {
     const int idx = lane + 32 * i;
-    soff[i] = -1; hoff[i] = 0;
+    soff[i] = -1; foff[i] = 0;
     if (i < npass && idx < P.obs_dim) {
       const int hk = __ldg(S.lut + idx);
       const int hh = hk >> 8, k = hk & 255;
       int sl = head + 1 + hh;
       sl = sl >= H ? sl - H : sl;
       soff[i] = sl * H1V2_HIST_STRIDE + k;
-      hoff[i] = hh * H1V2_HIST_STRIDE + k;
+      foff[i] = head * H1V2_HIST_STRIDE + k;
     }
   }
-  for (int e = 0; e < 16; e++) {
+  const int nenv = min(16, P.n - warp_env0);
+#pragma unroll 1
+  for (int e = 0; e < nenv; e++) {
     const int env_e = warp_env0 + e;
-    const int fl = __shfl_sync(0xffffffffu, cmd.flags, 2 * e);
-    if (env_e >= P.n) break;
-    const bool fresh = (fl & FLAG_HIST_FRESH) != 0;
+    const bool fresh = (__shfl_sync(0xffffffffu, cmd.flags, 2 * e) & FLAG_HIST_FRESH) != 0;
     float* hbase = S.hist + (size_t)env_e * H * H1V2_HIST_STRIDE;
+    float* orow = obs + (size_t)env_e * P.obs_dim + lane;
     float v[MAXPASS];
 #pragma unroll
     for (int i = 0; i < MAXPASS; i++)
-      if (soff[i] >= 0) v[i] = __ldcg(hbase + (fresh ? head * H1V2_HIST_STRIDE + (hoff[i] % H1V2_HIST_STRIDE) : soff[i]));
+      if (soff[i] >= 0) v[i] = __ldcg(hbase + (fresh ? foff[i] : soff[i]));
 #pragma unroll
     for (int i = 0; i < MAXPASS; i++)
       if (soff[i] >= 0) {
-        if (obs) obs[(size_t)env_e * P.obs_dim + lane + 32 * i] = v[i];
-        if (fresh) hbase[hoff[i]] = v[i];
+        if (obs) orow[32 * i] = v[i];
+        if (fresh) hbase[soff[i]] = v[i];  // back-fill: the whole ring holds the first sample (circular_buffer.py:131-135)
       }
   }
 }
@@ -215,21 +216,27 @@ template <bool DO_STEP>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  // thread / block index through volatile asm: under register pressure ptxas otherwise re-reads the special registers
+  // (S2R, ~20 cycles each) all over the Newton loop instead of keeping one value alive (profiles/r1e: 7 % of all instructions)
+  unsigned tid, bid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
+  const int gtid = bid * H1V2_BLOCK + tid;
   const int side = gtid & 1;
   const bool valid = (gtid >> 1) < P.n;
   const int env = valid ? (gtid >> 1) : P.n - 1;
   const int lidx = 2 * env + side;
-  const unsigned pm = 3u << (threadIdx.x & 30);
+  const unsigned pm = 3u << (tid & 30);
   const int N = P.n, N2 = 2 * P.n;
   const int64_t gid = P.env_id_offset + env;
   const unsigned long long step = S.counters[0] + (DO_STEP ? 1ull : 0ull);
   const int head = (int)((S.counters[1] + 1ull) % (unsigned long long)P.H);
 
-  // ---- load state (coalesced 128-bit) ----
-  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
+  // ---- load the physics state (coalesced 128-bit).  The actuator line and the command state are read AFTER the
+  //      physics loop: whatever is live across substep() costs registers inside the Newton iteration. ----
+  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6];
   float mu, mass_add, push_left;
-  CmdState cmd;
+  int flags0;
   {
     float4 r0 = S.root[env], r1 = S.root[N + env], r2 = S.root[2 * N + env], r3 = S.root[3 * N + env];
     rp[0] = r0.x; rp[1] = r0.y; rp[2] = r0.z; rq[0] = r0.w; rq[1] = r1.x; rq[2] = r1.y; rq[3] = r1.z;
@@ -238,13 +245,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     float4 l0 = S.leg[lidx], l1 = S.leg[N2 + lidx], l2 = S.leg[2 * N2 + lidx];
     q[0] = l0.x; q[1] = l0.y; q[2] = l0.z; q[3] = l0.w; q[4] = l1.x; q[5] = l1.y;
     qd[0] = l1.z; qd[1] = l1.w; qd[2] = l2.x; qd[3] = l2.y; qd[4] = l2.z; qd[5] = l2.w;
-    float4 a0 = S.act[lidx], a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx], a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
-    la[0] = a0.x; la[1] = a0.y; la[2] = a0.z; la[3] = a0.w; la[4] = a1.x; la[5] = a1.y;
-    T1[0] = a1.z; T1[1] = a1.w; T1[2] = a2.x; T1[3] = a2.y; T1[4] = a2.z; T1[5] = a2.w;
-    T2[0] = a3.x; T2[1] = a3.y; T2[2] = a3.z; T2[3] = a3.w; T2[4] = a4.x; T2[5] = a4.y;
-    float4 c0 = S.cmd[env], c1 = S.cmd[N + env];
-    cmd.c[0] = c0.x; cmd.c[1] = c0.y; cmd.c[2] = c0.z; cmd.heading_target = c0.w;
-    cmd.time_left = c1.x; cmd.m_xy = c1.y; cmd.m_yaw = c1.z; cmd.flags = __float_as_int(c1.w);
+    flags0 = __float_as_int(S.cmd[N + env].w);
   }
   float4 tm = S.timers[lidx];
   float wl[6], wr[6];
@@ -253,42 +254,62 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     wl[0] = w0.x; wl[1] = w0.y; wl[2] = w0.z; wl[3] = w0.w; wl[4] = w1.x; wl[5] = w1.y;
     wr[0] = w1.z; wr[1] = w1.w; wr[2] = w2.x; wr[3] = w2.y; wr[4] = w2.z; wr[5] = w2.w;
   }
+  float la[6], T1[6], T2[6];
+  CmdState cmd;
+  float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
+  float s_tau = 0.f, s_acc = 0.f;
+  SubOut so;
+  int max_it = 0, ncap = 0, sum_it = 0;
 
   if (DO_STEP) {
-    // ---- action manager: process_action (JointPositionAction, V/velocity_env_cfg.py:111) ----
-    float prev[6], T0[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      const int j = 6 * side + k;
-      prev[k] = la[k];
-      la[k] = actions[(size_t)env * 12 + P.inv_perm[j]];
-      T0[k] = fmaf(P.action_scale, la[k], P.q0[j]);
-    }
-    if (cmd.flags & FLAG_DELAY_FRESH) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) T1[k] = T2[k] = T0[k];
-    }
-    const int lag = (cmd.flags >> FLAG_LAG_SHIFT) & 7;
     // ---- physics loop: DelayedPD actuator (A/robots/h12.py:58-113) + substep + ContactSensor at sim dt ----
-    float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
-    float tau[6];
-    SubOut so;
-    int max_it = 0, ncap = 0, sum_it = 0;
-    bool use_warm = !(cmd.flags & FLAG_DELAY_FRESH);
+    // process_action (JointPositionAction, V/velocity_env_cfg.py:111): target = scale * a + q0; the delay line holds the
+    // targets of the previous two control steps.  Targets are re-read per substep (L1/L2 hits) instead of held in registers.
+    const int lag = (flags0 >> FLAG_LAG_SHIFT) & 7;
+    const bool line_fresh = (flags0 & FLAG_DELAY_FRESH) != 0;
+    bool use_warm = !line_fresh;
 #pragma unroll 1
     for (int k = 0; k < P.decimation; k++) {
       const int age = lag - k;
+      float tau[6];
+      {
+        float T[6];
+        if (age <= 0 || line_fresh) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const int j = 6 * side + i;
-        float T = age <= 0 ? T0[i] : (age <= P.decimation ? T1[i] : T2[i]);
-        float t = P.kp[j] * (T - q[i]) + P.kd[j] * (0.f - qd[i]);
-        tau[i] = fminf(fmaxf(t, -P.effort[j]), P.effort[j]);
+          for (int i = 0; i < 6; i++) T[i] = fmaf(P.action_scale, __ldg(actions + (size_t)env * 12 + P.inv_perm[6 * side + i]), P.q0[6 * side + i]);
+        } else if (age <= P.decimation) {
+          const float4 a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx];
+          T[0] = a1.z; T[1] = a1.w; T[2] = a2.x; T[3] = a2.y; T[4] = a2.z; T[5] = a2.w;
+        } else {
+          const float4 a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
+          T[0] = a3.x; T[1] = a3.y; T[2] = a3.z; T[3] = a3.w; T[4] = a4.x; T[5] = a4.y;
+        }
+        s_tau = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          const int j = 6 * side + i;
+          const float t = P.kp[j] * (T[i] - q[i]) + P.kd[j] * (0.f - qd[i]);
+          tau[i] = fminf(fmaxf(t, -P.effort[j]), P.effort[j]);
+          if ((P.m_tau >> j) & 1u) s_tau = fmaf(tau[i], tau[i], s_tau);
+        }
+        if (S.diag && valid) {
+          float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
+#pragma unroll
+          for (int i = 0; i < 6; i++) dg[36 + 6 * side + i] = tau[i];
+        }
       }
-      substep(P, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
+      substep(P, tid, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters;
       if (valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);
+      s_acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; i++) s_acc = fmaf(so.qacc[i], so.qacc[i], s_acc);
+      if (S.diag && valid) {
+        float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dg[48 + 6 * side + i] = so.qacc[i];
+      }
       float nf = sqrtf(dot(so.F_foot, so.F_foot));
       h_foot[0] = h_foot[1]; h_foot[1] = h_foot[2]; h_foot[2] = nf;
       h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = sqrtf(dot(so.F_shin, so.F_shin));
@@ -304,9 +325,33 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         tm.z = is_c ? tm.z + el : 0.f;
       }
     }
+  }
+  // ---- actuator line and command state ----
+  {
+    float4 a0 = S.act[lidx], a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx], a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
+    la[0] = a0.x; la[1] = a0.y; la[2] = a0.z; la[3] = a0.w; la[4] = a1.x; la[5] = a1.y;
+    T1[0] = a1.z; T1[1] = a1.w; T1[2] = a2.x; T1[3] = a2.y; T1[4] = a2.z; T1[5] = a2.w;
+    T2[0] = a3.x; T2[1] = a3.y; T2[2] = a3.z; T2[3] = a3.w; T2[4] = a4.x; T2[5] = a4.y;
+    float4 c0 = S.cmd[env], c1 = S.cmd[N + env];
+    cmd.c[0] = c0.x; cmd.c[1] = c0.y; cmd.c[2] = c0.z; cmd.heading_target = c0.w;
+    cmd.time_left = c1.x; cmd.m_xy = c1.y; cmd.m_yaw = c1.z; cmd.flags = __float_as_int(c1.w);
+  }
+  if (DO_STEP) {
+    // action manager bookkeeping: prev_action <- action ; action <- a ; shift the delay line
+    float prev[6];
+    {
+      const bool line_fresh = (cmd.flags & FLAG_DELAY_FRESH) != 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { T2[k] = T1[k]; T1[k] = T0[k]; }
-    cmd.flags &= ~FLAG_DELAY_FRESH;
+      for (int k = 0; k < 6; k++) {
+        const int j = 6 * side + k;
+        prev[k] = la[k];
+        la[k] = __ldg(actions + (size_t)env * 12 + P.inv_perm[j]);
+        const float T0 = fmaf(P.action_scale, la[k], P.q0[j]);
+        T2[k] = line_fresh ? T0 : T1[k];
+        T1[k] = T0;
+      }
+      cmd.flags &= ~FLAG_DELAY_FRESH;
+    }
 
     // ---- non-finite guard ----
     bool bad = false;
@@ -336,14 +381,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;
     {
-      float s_lim = 0.f, s_dev = 0.f, s_tau = 0.f, s_acc = 0.f, s_vel = 0.f, s_da = 0.f;
+      float s_lim = 0.f, s_dev = 0.f, s_vel = 0.f, s_da = 0.f;
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const int j = 6 * side + k;
         if ((P.m_poslim >> j) & 1u) s_lim += -fminf(q[k] - P.soft_lo[j], 0.f) + fmaxf(q[k] - P.soft_hi[j], 0.f);
         if ((P.m_dev >> j) & 1u) s_dev += fabsf(q[k] - P.q0[j]);
-        if ((P.m_tau >> j) & 1u) s_tau = fmaf(tau[k], tau[k], s_tau);
-        s_acc = fmaf(so.qacc[k], so.qacc[k], s_acc);
         s_vel = fmaf(qd[k], qd[k], s_vel);
         float da = la[k] - prev[k];
         s_da = fmaf(da, da, s_da);
@@ -427,8 +470,6 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       dg[6 + 3 * side + 0] = so.F_shin.x; dg[6 + 3 * side + 1] = so.F_shin.y; dg[6 + 3 * side + 2] = so.F_shin.z;
 #pragma unroll
       for (int i = 0; i < 3; i++) { dg[18 + 3 * side + i] = h_foot[i]; dg[24 + 3 * side + i] = h_shin[i]; }
-#pragma unroll
-      for (int k = 0; k < 6; k++) { dg[36 + 6 * side + k] = tau[k]; dg[48 + 6 * side + k] = so.qacc[k]; }
       dg[80 + 3 * side + 0] = fv.x; dg[80 + 3 * side + 1] = fv.y; dg[80 + 3 * side + 2] = fv.z;
 #pragma unroll
       for (int k = 0; k < 6; k++) { dg[96 + 7 + 6 * side + k] = q[k]; dg[115 + 6 + 6 * side + k] = qd[k]; }
@@ -452,7 +493,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       int wm = __reduce_max_sync(0xffffffffu, valid ? max_it : 0);
       int wc = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? ncap : 0);
       int ws = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? sum_it : 0);
-      if ((threadIdx.x & 31) == 0) {
+      if ((tid & 31) == 0) {
         atomicMax((int*)(S.acc + H1V2_LOG_MAX_ITERS), wm);
         if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (float)wc);
         atomicAdd(S.acc + H1V2_LOG_SUM_ITERS, (float)ws);
@@ -504,7 +545,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
     }
   }
-  emit_observation(P, S, env, side, valid, gid, step, head, rd, cmd, q, qd, la, obs);
+  emit_observation(P, S, tid, bid, env, side, valid, gid, step, head, rd, cmd, q, qd, la, obs);
   cmd.flags &= ~FLAG_HIST_FRESH;
 
   // ---- store state ----
