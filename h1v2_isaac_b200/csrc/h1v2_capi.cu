@@ -319,6 +319,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   for (int k = 0; k < 5; k++) { P.limit_imp[k] = c.limit_solimp[k]; P.contact_imp[k] = c.contact_solimp[k]; }
   for (int s = 0; s < 6; s++) P.slot_tran[s] = (float)h1v2_slot_invweight_tran[s];
   P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance; P.ls_tol = c.solver_ls_tolerance > 0.f ? c.solver_ls_tolerance : 0.01f;
+  P.ls_max = c.reserved[1] > 0 ? c.reserved[1] : 6;  // reserved[1]: tuning knob for the line-search trip cap
   P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
   if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
   P.H = c.history_length; P.obs_dim = c.history_length * H1V2_OBS_TERM_DIM; P.corrupt = c.enable_corruption;

@@ -68,8 +68,13 @@ struct Smem {
   }
 };
 
-__device__ __forceinline__ float pair_sum(float v, unsigned pm) { return v + __shfl_xor_sync(pm, v, 1); }
-__device__ __forceinline__ V3 pair_sum(V3 v, unsigned pm) { return mk3(pair_sum(v.x, pm), pair_sum(v.y, pm), pair_sum(v.z, pm)); }
+// Sum over the two lanes of an env.  ALWAYS executed by the whole, converged warp with the constant full mask: a shuffle
+// with a per-pair register mask compiles to a BSSY / WARPSYNC.COLLECTIVE / SHFL / ENDCOLLECTIVE / BSYNC sequence through
+// fixed registers (~13 instructions and spills, profiles/r1g), the constant-mask one to a single SHFL.  The Newton loop
+// below is therefore warp-synchronous: every lane runs every trip, lanes whose solve is finished are masked by selects.
+#define FULL_MASK 0xffffffffu
+__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(FULL_MASK, v, 1); }
+__device__ __forceinline__ V3 pair_sum(V3 v) { return mk3(pair_sum(v.x), pair_sum(v.y), pair_sum(v.z)); }
 
 // MuJoCo getimpedance (solimp = d0, dmax, width, midpoint, power), margin 0
 __device__ __forceinline__ float impedance(const float* si, float pos) {
@@ -129,6 +134,19 @@ __device__ __forceinline__ void k6_rank1_sub(K6& K, V3 n, V3 l, float s) {
   K.al[0] = fmaf(-ns.x, l.x, K.al[0]); K.al[1] = fmaf(-ns.x, l.y, K.al[1]); K.al[2] = fmaf(-ns.x, l.z, K.al[2]);
   K.al[3] = fmaf(-ns.y, l.x, K.al[3]); K.al[4] = fmaf(-ns.y, l.y, K.al[4]); K.al[5] = fmaf(-ns.y, l.z, K.al[5]);
   K.al[6] = fmaf(-ns.z, l.x, K.al[6]); K.al[7] = fmaf(-ns.z, l.y, K.al[7]); K.al[8] = fmaf(-ns.z, l.z, K.al[8]);
+}
+
+// K about O_s  ->  K about O_r, with O_s = O_r + d  (motion at O_s: u_s = u_r + w x d):  K_r = X' K_s X, X = [[1,0],[-[d]x,1]]
+//   ll_r = ll ;  al_r = al + [d]x ll ;  aa_r = aa - al_r [d]x + [d]x al'
+__device__ __forceinline__ void k6_shift(K6& K, V3 d) {
+  const V3 c0 = cross(d, mk3(K.ll[0], K.ll[3], K.ll[4])), c1 = cross(d, mk3(K.ll[3], K.ll[1], K.ll[5])), c2 = cross(d, mk3(K.ll[4], K.ll[5], K.ll[2]));
+  const V3 b0 = mk3(K.al[0], K.al[1], K.al[2]), b1 = mk3(K.al[3], K.al[4], K.al[5]), b2 = mk3(K.al[6], K.al[7], K.al[8]);
+  const V3 r0 = b0 + mk3(c0.x, c1.x, c2.x), r1 = b1 + mk3(c0.y, c1.y, c2.y), r2 = b2 + mk3(c0.z, c1.z, c2.z);
+  const V3 p0 = cross(d, r0), p1 = cross(d, r1), p2 = cross(d, r2);
+  const V3 q0 = cross(d, b0), q1 = cross(d, b1), q2 = cross(d, b2);
+  K.aa[0] += p0.x + q0.x; K.aa[1] += p1.y + q1.y; K.aa[2] += p2.z + q2.z;
+  K.aa[3] += p0.y + q1.x; K.aa[4] += p0.z + q2.x; K.aa[5] += p1.z + q2.y;
+  K.al[0] = r0.x; K.al[1] = r0.y; K.al[2] = r0.z; K.al[3] = r1.x; K.al[4] = r1.y; K.al[5] = r1.z; K.al[6] = r2.x; K.al[7] = r2.y; K.al[8] = r2.z;
 }
 
 // one contact point at the iterate.  Edge residuals j_k = a_k . e + kappa over the four pyramid edges
@@ -287,7 +305,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
     const float lim = P.frc[j0 + j];
     sm.jf(j, F_XQ) = q[j]; sm.jf(j, F_FLC) = qd[j];
     sm.jf(j, F_FS) = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
-    sm.jf(j, F_R) = wl[j];
+    sm.jf(j, F_R) = use_warm ? wl[j] : 0.f;
   }
   // ---- root frame (about O_r = pelvis origin) ----
   {
@@ -382,7 +400,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
     float bl[6];
     root_project_force(RB, fcn, fcl, bl);
 #pragma unroll
-    for (int k = 0; k < 6; k++) fs_root[k] = -(fs_root[k] + pair_sum(bl[k], pm)) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
+    for (int k = 0; k < 6; k++) fs_root[k] = -(fs_root[k] + pair_sum(bl[k])) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
   }
   float rfl_c[3];  // friction-loss row offsets of the root dofs 3*side..3*side+2 owned by this lane
 #pragma unroll
@@ -433,19 +451,25 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   V3 Wl_f = zero3, Wl_s = zero3, F_torso = zero3, F_pelvis = zero3;  // net contact forces per body at the last evaluation
   int it = 0, capped = 0;
 #pragma unroll
-  for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = wr[i]; }
+  for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = use_warm ? wr[i] : 0.f; }
   const float* arm = P.armature + 6 + j0;
   const float* flD = P.floss_D + 6 + j0;
   const float* flL = P.floss_lim + 6 + j0;
   const float* flF = P.floss + 6 + j0;
   const V3 c3[3] = {R0.cx, R0.cy, R0.cz};
 
-  // phase 0: inject the warm start (x = 0 -> previous acceleration, unit step); 1: Newton; 2: implicitfast update
-  int phase = use_warm ? 0 : 1;
+  // Warp-synchronous loop.  Trip 0 injects the warm start (x = 0 -> previous acceleration, unit step, no solve; a fresh
+  // env injects zero).  Every later trip evaluates the rows at x, then solves: a lane in MODE_NEWTON takes a Newton step
+  // with exact line search, a lane whose iterate has converged takes the implicitfast update (MODE_FINAL) in the same
+  // trip and is MODE_DONE afterwards; done lanes keep running on frozen state (all their writes are selects).
+  enum { MODE_NEWTON = 1, MODE_FINAL = 2, MODE_DONE = 3 };
+  int mode = MODE_NEWTON;
 #pragma unroll 1
-  for (;;) {
+  for (int trip = 0;; trip++) {
+    const bool first = trip == 0;
     float dg_own[3] = {0.f, 0.f, 0.f};  // extra Hessian diagonal of this lane's three root rows
-    if (phase == 1) {
+    bool final_trip = false;            // this trip's solve is the lane's implicitfast update
+    if (!first) {
       // ---- evaluate all rows at x: forces and gradient ----
       float gr_own[6];
 #pragma unroll
@@ -456,21 +480,8 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
         const float f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], dg_own[k]);
         if (side == 0) gr_own[k] = f; else gr_own[3 + k] = f;
       }
-#pragma unroll 1
-      for (int j = 0; j < 6; j++) {
-        const float x = sm.jf(j, F_XQ);
-        float act;
-        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
-        const float lD = sm.jf(j, F_LIMD);
-        const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
-        const float jar = fmaf(sig, x, sm.jf(j, F_LIMC));
-        const float la = (sig != 0.f && jar < 0.f) ? fabsf(lD) : 0.f;
-        f += sig * (-la * jar);
-        sm.jf(j, F_G) = f;
-        sm.jf(j, F_DG) = act + la;
-      }
       V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
-      Wl_f = Wl_s = F_torso = F_pelvis = zero3;
+      Wl_f = Wl_s = F_torso = zero3;
 #pragma unroll 1
       for (int p = 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
@@ -496,44 +507,54 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
       }
       float gn2 = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < 6; j++) {
+      for (int j = 0; j < 6; j++) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
+        const float x = sm.jf(j, F_XQ);
+        float act;
+        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
+        const float lD = sm.jf(j, F_LIMD);
+        const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
+        const float jar = fmaf(sig, x, sm.jf(j, F_LIMC));
+        const float la = (sig != 0.f && jar < 0.f) ? fabsf(lD) : 0.f;
+        f += sig * (-la * jar);
         const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
-        const float g = sm.jf(j, F_G) + ((j >= 4) ? dot(wj, Wn_f) + dot(uj, Wl_f) : dot(wj, Wn_leg) + dot(uj, Wl_leg));
+        const float g = f + ((j >= 4) ? dot(wj, Wn_f) + dot(uj, Wl_f) : dot(wj, Wn_leg) + dot(uj, Wl_leg));
         const float r = g - sm.jf(j, F_MA);
-        sm.jf(j, F_G) = g; sm.jf(j, F_R) = r;
+        sm.jf(j, F_G) = g; sm.jf(j, F_R) = r; sm.jf(j, F_DG) = act + la;
         gn2 = fmaf(r, r, gn2);
       }
-      F_torso = pair_sum(F_torso, pm);
-      F_pelvis = pair_sum(F_pelvis, pm);
-      gn2 = pair_sum(gn2, pm);
+      F_torso = pair_sum(F_torso);
+      F_pelvis = pair_sum(F_pelvis);
+      gn2 = pair_sum(gn2);
 #pragma unroll
-      for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k], pm); rr[k] = jr[k] - Mar[k]; gn2 = fmaf(rr[k], rr[k], gn2); }
-      const bool conv = sqrtf(gn2) * P.grad_scale < P.tol;
-      if (conv || it >= P.max_iters) { capped = !conv; phase = 2; }
-      else it++;
-    }
-    if (phase == 2) {
-      // implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f
+      for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k]); rr[k] = jr[k] - Mar[k]; gn2 = fmaf(rr[k], rr[k], gn2); }
+      if (mode == MODE_NEWTON) {
+        const bool conv = sqrtf(gn2) * P.grad_scale < P.tol;
+        if (conv || it >= P.max_iters) { capped = !conv; mode = MODE_FINAL; }
+        else it++;
+      }
+      const bool newton = mode == MODE_NEWTON;
+      final_trip = mode == MODE_FINAL;
+      if (!newton) {
+        // implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f   (a done lane repeats this harmlessly)
 #pragma unroll 1
-      for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * P.damping[6 + j0 + j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
+        for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * P.damping[6 + j0 + j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
 #pragma unroll
-      for (int k = 0; k < 6; k++) rr[k] = fs_root[k] + jr[k];
-    }
-    // ---- ABA sweep 1 (tip -> root): articulated inertia and reduced rhs.  Skipped for the warm-start injection. ----
-    if (phase != 0) {
+        for (int k = 0; k < 6; k++) rr[k] = fs_root[k] + jr[k];
+      }
+      // ---- ABA sweep 1 (tip -> root): articulated inertia and reduced rhs ----
       K6 IA;
       k6_zero(IA);
       V3 pn = zero3, pl = zero3;
-      const bool kc = phase == 1;
+      const float Dk = newton ? 1.f : 0.f;  // contact stiffness enters the Newton Hessian only
 #pragma unroll 1
       for (int j = 5; j >= 0; j--) {
         k6_add_rigid(IA, sm.ji(j));
-        if (kc && (j == 5 || j == 3)) {  // contact stiffness of the foot / shin link, straight into the articulated inertia
+        if (j == 5 || j == 3) {  // contact stiffness of the foot / shin link, straight into the articulated inertia
           const int p1 = j == 5 ? n_foot : e_shin;
 #pragma unroll 1
           for (int p = j == 5 ? 0 : n_foot; p < p1; p++) {
             float Wp[5];
-            point_weight(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu, Wp);
+            point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
             k6_add_point(IA, sm.pv(p, 0), Wp);
           }
         }
@@ -548,43 +569,45 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
         const float td = t * dinv;
         pn = fma3(n, td, pn); pl = fma3(l, td, pl);
       }
-      // root block: hand-offs of both legs (joint space) + own link + root contact points + diagonal; 6x6 Cholesky on both lanes
-      float A[21], g[6];
-#pragma unroll
-      for (int i = 0; i < 21; i++) A[i] = 0.f;
-      root_project_k6(RB, IA, A);
-      root_project_force(RB, pn, pl, g);
+      // ---- root block: both legs' hand-offs moved to the pelvis origin + own link + root contact points; 6x6 Cholesky on both lanes ----
       {
+        k6_shift(IA, d);
+        pn = pn + cross(d, pl);
         RI Ih = I0;  // half of the root link on each lane: the pair sum below restores it exactly
         Ih.m *= 0.5f; Ih.mc = Ih.mc * 0.5f;
         Ih.xx *= 0.5f; Ih.yy *= 0.5f; Ih.zz *= 0.5f; Ih.xy *= 0.5f; Ih.xz *= 0.5f; Ih.yz *= 0.5f;
-        k6_zero(IA);
         k6_add_rigid(IA, Ih);
-        if (kc) {
 #pragma unroll 1
-          for (int p = e_shin; p < nact; p++) {
-            float Wp[5];
-            point_weight(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu, Wp);
-            k6_add_point(IA, sm.pv(p, 0), Wp);
-          }
+        for (int p = e_shin; p < nact; p++) {
+          float Wp[5];
+          point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
+          k6_add_point(IA, sm.pv(p, 0), Wp);
         }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { IA.aa[i] = pair_sum(IA.aa[i]); IA.ll[i] = pair_sum(IA.ll[i]); }
+#pragma unroll
+        for (int i = 0; i < 9; i++) IA.al[i] = pair_sum(IA.al[i]);
+        pn = pair_sum(pn); pl = pair_sum(pl);
+        float A[21], g[6];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = 0.f;
         root_project_k60(c3, IA, A);
-      }
-      if (phase == 1) {
-        if (side == 0) { A[TI(0, 0)] += dg_own[0]; A[TI(1, 1)] += dg_own[1]; A[TI(2, 2)] += dg_own[2]; }
-        else { A[TI(3, 3)] += dg_own[0]; A[TI(4, 4)] += dg_own[1]; A[TI(5, 5)] += dg_own[2]; }
-      }
+        root_project_force0(c3, pn, pl, g);
+        // diagonal: armature, friction-loss curvature of the root rows (Newton) or h*damping (implicit update)
+        const float o0 = newton ? dg_own[0] : 0.f, o1 = newton ? dg_own[1] : 0.f, o2 = newton ? dg_own[2] : 0.f;
+        const float e0 = pair_sum(side == 0 ? o0 : 0.f), e1 = pair_sum(side == 0 ? o1 : 0.f), e2 = pair_sum(side == 0 ? o2 : 0.f);
+        const float e3 = pair_sum(side == 0 ? 0.f : o0), e4 = pair_sum(side == 0 ? 0.f : o1), e5 = pair_sum(side == 0 ? 0.f : o2);
+        const float ex[6] = {e0, e1, e2, e3, e4, e5};
 #pragma unroll
-      for (int i = 0; i < 21; i++) A[i] = pair_sum(A[i], pm);
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        A[TI(k, k)] += P.armature[k] + (phase == 2 ? h * P.damping[k] : 0.f);
-        rr[k] -= pair_sum(g[k], pm);
+        for (int k = 0; k < 6; k++) {
+          A[TI(k, k)] += P.armature[k] + (newton ? ex[k] : h * P.damping[k]);
+          rr[k] -= g[k];
+        }
+        float inva[6];
+        chol6(A, inva);
+        fwd6(A, inva, rr);
+        bwd6(A, inva, rr);
       }
-      float inva[6];
-      chol6(A, inva);
-      fwd6(A, inva, rr);
-      bwd6(A, inva, rr);
     }
     // ---- sweep 2 (root -> tip): joint accelerations; the same sweep starts the M-product of the direction and
     //      leaves the direction's body accelerations (root about O_r; shin, foot about O_s) for the line search ----
@@ -594,30 +617,27 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
     Sa_f = Sa_r; Sl_f = Sl_r + cross(Sa_r, d);
     Sa_s = Sa_f; Sl_s = Sl_f;
     float smax = 0.f;
-    const bool solve = phase != 0, need_ms = phase != 2;
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {
       float s = sm.jf(j, F_R);
-      if (solve) {
+      if (!first) {
         s = (s - (dot(sm.jv(j, F_X), Sa_f) + dot(sm.jv(j, F_X + 3), Sl_f))) * sm.jf(j, F_DINV);
         sm.jf(j, F_R) = s;
       }
       smax = fmaxf(smax, fabsf(s));
       Sa_f = fma3(sm.jv(j, F_W), s, Sa_f); Sl_f = fma3(sm.jv(j, F_U), s, Sl_f);
       if (j == 3) { Sa_s = Sa_f; Sl_s = Sl_f; }
-      if (need_ms) {
-        V3 n, l;
-        ri_apply(sm.ji(j), Sa_f, Sl_f, n, l);
-        sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
-      }
+      V3 n, l;
+      ri_apply(sm.ji(j), Sa_f, Sl_f, n, l);
+      sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
     }
-    if (phase == 2) break;
-    if (phase == 1) {  // the Newton step no longer moves the acceleration: accept the iterate (J'f is current)
-      smax = fmaxf(smax, __shfl_xor_sync(pm, smax, 1));
+    smax = fmaxf(smax, __shfl_xor_sync(FULL_MASK, smax, 1));
 #pragma unroll
-      for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rr[i]));
-      if (smax < P.step_tol) { phase = 2; continue; }
-    }
+    for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rr[i]));
+    // what this lane does with the direction: Newton step with line search | unit step (trip 0) | nothing.
+    // A Newton step that no longer moves the acceleration is dropped and the iterate accepted (J'f is current).
+    bool search = !first && mode == MODE_NEWTON;
+    if (search && smax < P.step_tol) { search = false; mode = MODE_FINAL; }
     // ---- M-product, tip -> root half:  Ms = M s  (stored in the F_DG slot) ; line-search scalars ----
     float sMs = 0.f, sMa = 0.f, gs = 0.f;
     {
@@ -636,18 +656,19 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
       ri_apply(I0, Sa_r, Sl_r, n0, f0);
       root_project_force0(c3, n0, f0, b0);
 #pragma unroll
-      for (int k = 0; k < 6; k++) Msr[k] = b0[k] + pair_sum(bl[k], pm) + P.armature[k] * rr[k];
+      for (int k = 0; k < 6; k++) Msr[k] = b0[k] + pair_sum(bl[k]) + P.armature[k] * rr[k];
     }
-    float alpha = 1.f;
-    if (phase == 1) {
-      // ---- exact line search along the direction ----
-      sMs = pair_sum(sMs, pm); sMa = pair_sum(sMa, pm); gs = pair_sum(gs, pm);
+    float alpha = first ? 1.f : 0.f;
+    {
+      // ---- exact line search along the direction (all lanes run the trips; only searching lanes move alpha) ----
+      sMs = pair_sum(sMs); sMa = pair_sum(sMa); gs = pair_sum(gs);
 #pragma unroll
       for (int k = 0; k < 6; k++) { sMs = fmaf(rr[k], Msr[k], sMs); sMa = fmaf(rr[k], Mar[k], sMa); gs = fmaf(rr[k], jr[k], gs); }
       const float d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
-      float lo = 0.f, hi = 1e30f;
+      float lo = 0.f, hi = 1e30f, dlo = d10, dhi = 0.f;  // bracket of the minimiser and phi' at its ends
+      if (search) alpha = 1.f;
 #pragma unroll 1
-      for (int ls = 0; ls < 12; ls++) {
+      for (int ls = 0; __any_sync(FULL_MASK, search); ls++) {
         float d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 6; j++) {
@@ -679,44 +700,64 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
           const V3 us = Sl + cross(Sa, r);
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
-        d1 = pair_sum(d1, pm) + fmaf(alpha, sMs, sMa);
-        d2 = pair_sum(d2, pm) + sMs;
-        if (fabsf(d1) <= P.ls_tol * fabsf(d10) || !(d2 > 0.f)) break;
-        if (d1 < 0.f) lo = alpha; else hi = alpha;
-        float nx = alpha - d1 / d2;
-        if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
-        const bool tiny = fabsf(nx - alpha) <= 1e-4f * alpha;
-        alpha = nx;
-        if (tiny) break;
+        d1 = pair_sum(d1) + fmaf(alpha, sMs, sMa);
+        d2 = pair_sum(d2) + sMs;
+        if (search) {
+          if (fabsf(d1) <= P.ls_tol * fabsf(d10) || !(d2 > 0.f)) search = false;
+          else {
+            if (d1 < 0.f) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+            if (ls + 1 >= P.ls_max) {  // out of trips: phi' is monotone, take the secant root inside the bracket (regula falsi)
+              if (hi < 1e29f) alpha = lo + (hi - lo) * (-dlo / (dhi - dlo));
+              search = false;
+            } else {
+              float nx = alpha - d1 / d2;
+              if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
+              if (fabsf(nx - alpha) <= 1e-4f * alpha) search = false;
+              alpha = nx;
+            }
+          }
+        }
       }
     }
-    // ---- take the step: x += alpha s ; M x - f += alpha M s ; row residuals of the contact points += alpha J s ----
+    // ---- take the step: x += alpha s ; M x - f += alpha M s ; row residuals of the contact points += alpha J s.
+    //      A lane that just took its implicit update keeps the result: qacc -> F_FS, root part -> wr. ----
+    const bool move = alpha != 0.f;
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {
-      sm.jf(j, F_XQ) = fmaf(alpha, sm.jf(j, F_R), sm.jf(j, F_XQ));
-      sm.jf(j, F_MA) = fmaf(alpha, sm.jf(j, F_DG), sm.jf(j, F_MA));
+      const float s = sm.jf(j, F_R);
+      if (move) {
+        sm.jf(j, F_XQ) = fmaf(alpha, s, sm.jf(j, F_XQ));
+        sm.jf(j, F_MA) = fmaf(alpha, sm.jf(j, F_DG), sm.jf(j, F_MA));
+      }
+      if (final_trip) sm.jf(j, F_FS) = s;
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) { xr[i] = fmaf(alpha, rr[i], xr[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]); }
-#pragma unroll 1
-    for (int p = 0; p < nact; p++) {
-      const V3 r = sm.pv(p, 0);
-      const bool isf = p < n_foot, iss = p < e_shin;
-      const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
-      const V3 e = fma3(Sl + cross(Sa, r), alpha, sm.pv(p, 3));
-      sm.pf(p, 3) = e.x; sm.pf(p, 4) = e.y; sm.pf(p, 5) = e.z;
+    for (int i = 0; i < 6; i++) {
+      if (move) { xr[i] = fmaf(alpha, rr[i], xr[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]); }
+      if (final_trip) wr[i] = rr[i];
     }
-    phase = 1;
+    if (move) {
+#pragma unroll 1
+      for (int p = 0; p < nact; p++) {
+        const V3 r = sm.pv(p, 0);
+        const bool isf = p < n_foot, iss = p < e_shin;
+        const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
+        const V3 e = fma3(Sl + cross(Sa, r), alpha, sm.pv(p, 3));
+        sm.pf(p, 3) = e.x; sm.pf(p, 4) = e.y; sm.pf(p, 5) = e.z;
+      }
+    }
+    if (final_trip) mode = MODE_DONE;
+    if (__all_sync(FULL_MASK, mode == MODE_DONE)) break;
   }
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const float a = sm.jf(j, F_R);
-    out.qacc[j] = a; wl[j] = a; wr[j] = rr[j];
+    const float a = sm.jf(j, F_FS);
+    out.qacc[j] = a; wl[j] = a;
     qd[j] = fmaf(h, a, qd[j]); q[j] = fmaf(h, qd[j], q[j]);
   }
 #pragma unroll
-  for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, rr[k], rv[k]); rw[k] = fmaf(h, rr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
+  for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, wr[k], rv[k]); rw[k] = fmaf(h, wr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
   {
     float wn = sqrtf(rw[0] * rw[0] + rw[1] * rw[1] + rw[2] * rw[2]);
     float ang = wn * h, dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;

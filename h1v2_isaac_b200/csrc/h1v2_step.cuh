@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
     for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !isfinite(rv[k]) || !isfinite(rw[k]);
     bad |= !isfinite(rq[0]) || !isfinite(rq[1]) || !isfinite(rq[2]) || !isfinite(rq[3]);
-    bad = (__shfl_xor_sync(pm, (int)bad, 1) | (int)bad) != 0;
+    bad = (__shfl_xor_sync(FULL_MASK, (int)bad, 1) | (int)bad) != 0;
 
     // ---- counters and terminations (C12/rough_env_cfg.py:95-109) ----
     int64_t ep_len = S.ep_len[env] + 1;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     const float C_pelvis = fmaxf(h_pelvis[0], fmaxf(h_pelvis[1], h_pelvis[2]));
     int contact = (((P.m_illegal >> side) & 1u) && C_foot > P.contact_thr) || (((P.m_illegal >> (2 + side)) & 1u) && C_shin > P.contact_thr) ||
                   (((P.m_illegal >> 4) & 1u) && C_torso > P.contact_thr) || (((P.m_illegal >> 5) & 1u) && C_pelvis > P.contact_thr);
-    contact = (__shfl_xor_sync(pm, contact, 1) | contact) | (int)bad;
+    contact = (__shfl_xor_sync(FULL_MASK, contact, 1) | contact) | (int)bad;
     const bool reset = contact || time_out;
 
     // ---- rewards on the pre-reset state ----
@@ -391,12 +391,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         float da = la[k] - prev[k];
         s_da = fmaf(da, da, s_da);
       }
-      r[H1V2_REW_DOF_POS_LIMITS] = pair_sum(s_lim, pm);
-      r[H1V2_REW_JOINT_DEV_HIP] = pair_sum(s_dev, pm);
-      r[H1V2_REW_TORQUES] = pair_sum(s_tau, pm);
-      r[H1V2_REW_DOF_ACC] = pair_sum(s_acc, pm);
-      r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel, pm);
-      r[H1V2_REW_ACTION_RATE] = pair_sum(s_da, pm);
+      r[H1V2_REW_DOF_POS_LIMITS] = pair_sum(s_lim);
+      r[H1V2_REW_JOINT_DEV_HIP] = pair_sum(s_dev);
+      r[H1V2_REW_TORQUES] = pair_sum(s_tau);
+      r[H1V2_REW_DOF_ACC] = pair_sum(s_acc);
+      r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel);
+      r[H1V2_REW_ACTION_RATE] = pair_sum(s_da);
       r[H1V2_REW_TERMINATION] = contact ? 1.f : 0.f;
       const float ch = cosf(rd.heading), sh = sinf(rd.heading);
       float ex = cmd.c[0] - (ch * rv[0] + sh * rv[1]), ey = cmd.c[1] - (-sh * rv[0] + ch * rv[1]);
@@ -411,18 +411,18 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       // feet_air_time_positive_biped (V/mdp/rewards.py:38-62) and feet_air_time (:13-35)
       const int inc = tm.z > 0.f;
       const float mode_t = inc ? tm.z : tm.x;
-      const int inc_p = __shfl_xor_sync(pm, inc, 1);
-      const float mode_p = __shfl_xor_sync(pm, mode_t, 1);
+      const int inc_p = __shfl_xor_sync(FULL_MASK, inc, 1);
+      const float mode_p = __shfl_xor_sync(FULL_MASK, mode_t, 1);
       const bool single = (inc + inc_p) == 1;
       float mn = fminf(single ? mode_t : 0.f, single ? mode_p : 0.f);
       mn = fminf(mn, P.air_thr);
       r[H1V2_REW_FEET_AIR_BIPED] = moving ? mn : 0.f;
       const bool first = (tm.z > 0.f) && (tm.z < P.step_dt + 1e-8f);
       float l2 = first ? (tm.y - P.air_thr) : 0.f;
-      l2 = pair_sum(l2, pm);
+      l2 = pair_sum(l2);
       r[H1V2_REW_FEET_AIR_L2] = moving ? l2 : 0.f;
       float slide = (C_foot > P.contact_thr) ? sqrtf(fv.x * fv.x + fv.y * fv.y) : 0.f;
-      r[H1V2_REW_FEET_SLIDE] = pair_sum(slide, pm);
+      r[H1V2_REW_FEET_SLIDE] = pair_sum(slide);
       r[H1V2_REW_ANG_VEL_XY] = rd.wb.x * rd.wb.x + rd.wb.y * rd.wb.y;
       r[H1V2_REW_FLAT_ORI] = rd.g.x * rd.g.x + rd.g.y * rd.g.y;
       r[H1V2_REW_LIN_VEL_Z] = rd.vb.z * rd.vb.z;
@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         if ((P.m_undesired >> 4) & 1u) { und += C_torso > P.contact_thr; cf += fmaxf(C_torso - P.contact_thr, 0.f); }
         if ((P.m_undesired >> 5) & 1u) { und += C_pelvis > P.contact_thr; cf += fmaxf(C_pelvis - P.contact_thr, 0.f); }
       }
-      r[H1V2_REW_UNDESIRED_CONTACTS] = pair_sum(und, pm);
-      r[H1V2_REW_CONTACT_FORCES] = pair_sum(cf, pm);
+      r[H1V2_REW_UNDESIRED_CONTACTS] = pair_sum(und);
+      r[H1V2_REW_CONTACT_FORCES] = pair_sum(cf);
     }
     float total = 0.f;
 #pragma unroll

@@ -4,34 +4,44 @@ usage: python tools/ncu_regions.py <rep> <libh1v2_b200.so>"""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, so = sys.argv[1], sys.argv[2]
-PHYS = [(274, 310, "stage+root frame"), (311, 329, "pass1 sincos/ankle"), (330, 358, "pass2 kinematics+RNE"), (359, 389, "smooth forces/rows"),
-        (390, 430, "contact candidates"), (431, 447, "iterate init"), (448, 514, "newton: evaluate rows"), (515, 521, "phase2 rhs"),
-        (522, 555, "ABA sweep1"), (556, 588, "root 6x6"), (589, 614, "ABA sweep2"), (615, 620, "step-tol exit"), (621, 640, "M-product"),
-        (641, 692, "line search"), (693, 710, "iterate update"), (711, 740, "integrate")]
-STEP = [(134, 171, "obs: sample+noise"), (172, 212, "obs: flatten/emit"), (214, 256, "load state"), (257, 271, "action"),
-        (272, 306, "PD+sensor loop"), (307, 331, "guards/terminations"), (332, 403, "rewards"), (404, 460, "epsum/diag/stats"),
-        (461, 489, "reset"), (490, 509, "command/push"), (510, 533, "store state")]
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "h1v2_isaac_b200", "csrc")
+
+
+def sections(fname, start_pat):
+    """Regions = the '// ---- title' section comments of the source, from the function matching start_pat to its end."""
+    out, on, lines = [], False, open(os.path.join(CSRC, fname)).read().split("\n")
+    for i, l in enumerate(lines, 1):
+        if re.search(start_pat, l):
+            on = True
+            out.append([i, None, "prologue"])
+        m = re.match(r"\s*// ---- (.*?)( ----)?$", l)
+        if on and m:
+            out[-1][1] = i - 1
+            out.append([i, None, m.group(1)[:44]])
+    if out:
+        out[-1][1] = len(lines)
+    return out
+
+
+PHYS = sections("h1v2_physics.cuh", r"void substep\(")
+STEP = sections("h1v2_step.cuh", r"step_kernel\(const")
+EMIT = sections("h1v2_step.cuh", r"void emit_observation\(")
+PHYS0 = PHYS[0][0]
 
 
 def region(chain):
-    # chain: innermost -> outermost list of (file, line)
+    # chain: innermost -> outermost list of (file, line); attribute to the OUTERMOST frame inside substep(), else step_kernel()
     for f, ln in reversed(chain):
-        if f == "h1v2_physics.cuh" and ln >= 274:
+        if f == "h1v2_physics.cuh" and ln >= PHYS0:
             for a, b, n in PHYS:
                 if a <= ln <= b:
                     return "phys: " + n
-        if f == "h1v2_step.cuh":
-            hit = None
-            for a, b, n in STEP:
-                if a <= ln <= b:
-                    hit = "step: " + n
-            if hit and not (ln == 288):
-                return hit
     for f, ln in reversed(chain):
         if f == "h1v2_step.cuh":
             for a, b, n in STEP:
                 if a <= ln <= b:
                     return "step: " + n
+            return "step: helpers (obs/reset/command)"
     return "other: " + (chain[-1][0] if chain else "?")
 
 
@@ -68,6 +78,9 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ia, ie, isamp, ithr = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+STALLS = ["stall_no_inst", "stall_wait", "stall_short_sb", "stall_long_sb", "stall_branch_resolving", "stall_selected", "stall_math", "stall_mio", "stall_lg", "stall_dispatch"]
+isx = [hdr.index(c) for c in STALLS]
+stall = collections.defaultdict(lambda: [0] * len(STALLS))
 base, agg, tot = None, collections.defaultdict(lambda: [0, 0, 0]), [0, 0, 0]
 for r in rows[2:]:
     try:
@@ -79,8 +92,12 @@ for r in rows[2:]:
     k = region(amap.get(a - base, []))
     e, s, t = int(r[ie] or 0), int(r[isamp] or 0), int(r[ithr] or 0)
     agg[k][0] += e; agg[k][1] += s; agg[k][2] += t
+    for q, ix in enumerate(isx):
+        stall[k][q] += int(r[ix] or 0)
     tot[0] += e; tot[1] += s; tot[2] += t
 print(f"total warp-instr {tot[0]:,}  samples {tot[1]:,}  avg threads {tot[2]/max(tot[0],1):.1f}  static SASS {sum(static.values()):,} B")
 print(f"{'region':34s} {'instr%':>7s} {'samples%':>9s} {'thr/inst':>9s} {'SASS bytes':>11s}")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:34s} {100*v[0]/tot[0]:7.1f} {100*v[1]/tot[1]:9.1f} {v[2]/max(v[0],1):9.1f} {static[k]:11,d}")
+    top = sorted(zip(stall[k], STALLS), reverse=True)[:3]
+    ts = " ".join(f"{n[6:]}={100*c/max(v[1],1):.0f}%" for c, n in top)
+    print(f"{k[:34]:34s} {100*v[0]/tot[0]:7.1f} {100*v[1]/tot[1]:9.1f} {v[2]/max(v[0],1):9.1f} {static[k]:11,d}  {ts}")
