@@ -455,12 +455,13 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
   if (!attr_set) {
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
-  else
-    step_kernel<false><<<blocks, threads, 0, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
+  else  // the observe-only launch stages the history rings in the same shared-memory window
+    step_kernel<false><<<blocks, threads, smem, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
   finalize_kernel<<<1, 32, 0, st>>>(h->S, do_step ? 1 : 0);
   h->launches += 2;
   CK(cudaGetLastError());

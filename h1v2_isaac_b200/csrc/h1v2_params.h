@@ -5,6 +5,7 @@
 
 #include "../../include/h1v2_b200.h"
 
+#define H1V2_OBS_MAXPASS ((H1V2_MAX_HISTORY * H1V2_OBS_TERM_DIM + 31) / 32)  // 32-column passes over one observation row
 #define H1V2_HIST_STRIDE 48  // floats per history slot (45 used; 192 B = 6 sectors)
 
 // --- rigid-body constants of one leg (MJCF order: hip_yaw, hip_pitch, hip_roll, knee, ankle_pitch, ankle_roll) ---

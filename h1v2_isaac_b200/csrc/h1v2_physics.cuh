@@ -293,7 +293,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
                                      float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
                                      const float (&tau)[6], const float mu, const float mass_add, float (&wl)[6], float (&wr)[6],
                                      const bool use_warm, SubOut& out) {
-  extern __shared__ float smem_raw[];
+  extern __shared__ __align__(16) float smem_raw[];
   const Smem sm{smem_raw + tid};
   const KLeg& LG = P.leg[side];
   const float h = P.h;

@@ -130,85 +130,139 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
   if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
 }
 
+// ---- history rings of the warp's 16 envs: global -> shared memory, asynchronously ----
+// The rings of consecutive envs are contiguous in HBM ([N][H][48] floats), so the warp's block is ONE contiguous range;
+// every lane issues 16-byte cp.async copies that need no registers and are all in flight at once.  The copy is started
+// right after the physics (the per-thread columns are dead by then) and awaited only when the observation is emitted,
+// so the HBM latency hides behind the reward / termination / reset / command code (profiles/r1k: with register-staged
+// loads the emission was 27 % of the step, 76 % of it long-scoreboard stalls).
+__device__ __forceinline__ int hist_envs_per_chunk(int H) { return min(16, (SMEM_FLOATS * H1V2_BLOCK) / (H * H1V2_HIST_STRIDE)); }
+__device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S, unsigned tid, unsigned bid, int e0) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int lane = tid & 31;
+  const int warp_env0 = (bid * H1V2_BLOCK + (tid & ~31u)) >> 1;
+  const int ne = min(hist_envs_per_chunk(P.H), min(16, P.n - warp_env0) - e0);
+  const int nchunk = ne * P.H * (H1V2_HIST_STRIDE / 4);  // 16-byte pieces
+  const float* src = S.hist + (size_t)(warp_env0 + e0) * P.H * H1V2_HIST_STRIDE;
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
+#pragma unroll 4
+  for (int c = lane; c < nchunk; c += 32)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 4 * c) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // observation sample of this step -> history ring slot `head`; then the warp cooperatively emits the flattened rows
 __device__ __forceinline__ void emit_observation(const KParams& P, const KState& S, unsigned tid, unsigned bid, int env, int side, bool valid, int64_t gid,
                                                  unsigned long long step, int head, const RootDerived& rd, const CmdState& cmd,
                                                  const float (&q)[6], const float (&qd)[6], const float (&la)[6], float* obs) {
+  extern __shared__ __align__(16) float smem_raw[];
   const int H = P.H;
-  float* slot = S.hist + ((size_t)env * H + head) * H1V2_HIST_STRIDE;
-  float nq[6] = {0, 0, 0, 0, 0, 0}, nv[6] = {0, 0, 0, 0, 0, 0};
-  if (P.corrupt) {
-    float a[4], b[4], d[4];
-    rng4(P.key0, gid, step, STREAM_OBS, 2 + 4 * side, a);
-    rng4(P.key0, gid, step, STREAM_OBS, 3 + 4 * side, b);
-    rng4(P.key0, gid, step, STREAM_OBS, 4 + 4 * side, d);
-    nq[0] = a[0]; nq[1] = a[1]; nq[2] = a[2]; nq[3] = a[3]; nq[4] = b[0]; nq[5] = b[1];
-    nv[0] = b[2]; nv[1] = b[3]; nv[2] = d[0]; nv[3] = d[1]; nv[4] = d[2]; nv[5] = d[3];
+  // ---- the sample: 18 values of this lane's leg, 9 root values on the env's first lane (noise: V/velocity_env_cfg.py:124-131) ----
+  float sv[18], s9[9];
+  {
+    float nq[6] = {0, 0, 0, 0, 0, 0}, nv[6] = {0, 0, 0, 0, 0, 0};
+    if (P.corrupt) {
+      float a[4], b[4], d[4];
+      rng4(P.key0, gid, step, STREAM_OBS, 2 + 4 * side, a);
+      rng4(P.key0, gid, step, STREAM_OBS, 3 + 4 * side, b);
+      rng4(P.key0, gid, step, STREAM_OBS, 4 + 4 * side, d);
+      nq[0] = a[0]; nq[1] = a[1]; nq[2] = a[2]; nq[3] = a[3]; nq[4] = b[0]; nq[5] = b[1];
+      nv[0] = b[2]; nv[1] = b[3]; nv[2] = d[0]; nv[3] = d[1]; nv[4] = d[2]; nv[5] = d[3];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { nq[k] = uni(nq[k], -P.n_q, P.n_q); nv[k] = uni(nv[k], -P.n_v, P.n_v); }
-  }
-  if (valid) {
+      for (int k = 0; k < 6; k++) { nq[k] = uni(nq[k], -P.n_q, P.n_q); nv[k] = uni(nv[k], -P.n_v, P.n_v); }
+    }
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      const int j = 6 * side + k, i = P.inv_perm[j];
-      slot[9 + i] = (q[k] - P.q0[j] + nq[k]) * P.s_q;
-      slot[21 + i] = (qd[k] + nv[k]) * P.s_v;
-      slot[33 + i] = la[k] * P.s_a;
+      const int j = 6 * side + k;
+      sv[k] = (q[k] - P.q0[j] + nq[k]) * P.s_q;
+      sv[6 + k] = (qd[k] + nv[k]) * P.s_v;
+      sv[12 + k] = la[k] * P.s_a;
+    }
+    float n0[3] = {0, 0, 0}, n1[3] = {0, 0, 0};
+    if (P.corrupt && side == 0) {
+      float b0[4], b1[4];
+      rng4(P.key0, gid, step, STREAM_OBS, 0, b0);
+      rng4(P.key0, gid, step, STREAM_OBS, 1, b1);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { n0[i] = uni(b0[i], -P.n_av, P.n_av); n1[i] = uni(b1[i], -P.n_g, P.n_g); }
+    }
+    s9[0] = (rd.wb.x + n0[0]) * P.s_av; s9[1] = (rd.wb.y + n0[1]) * P.s_av; s9[2] = (rd.wb.z + n0[2]) * P.s_av;
+    s9[3] = (rd.g.x + n1[0]) * P.s_g; s9[4] = (rd.g.y + n1[1]) * P.s_g; s9[5] = (rd.g.z + n1[2]) * P.s_g;
+    s9[6] = cmd.c[0] * P.s_cmd; s9[7] = cmd.c[1] * P.s_cmd; s9[8] = cmd.c[2] * P.s_cmd;
+  }
+  if (valid) {  // ring slot `head` in HBM
+    float* slot = S.hist + ((size_t)env * H + head) * H1V2_HIST_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int i = P.inv_perm[6 * side + k];
+      slot[9 + i] = sv[k]; slot[21 + i] = sv[6 + k]; slot[33 + i] = sv[12 + k];
     }
     if (side == 0) {
-      float n0[3] = {0, 0, 0}, n1[3] = {0, 0, 0};
-      if (P.corrupt) {
-        float b0[4], b1[4];
-        rng4(P.key0, gid, step, STREAM_OBS, 0, b0);
-        rng4(P.key0, gid, step, STREAM_OBS, 1, b1);
 #pragma unroll
-        for (int i = 0; i < 3; i++) { n0[i] = uni(b0[i], -P.n_av, P.n_av); n1[i] = uni(b1[i], -P.n_g, P.n_g); }
-      }
-      slot[0] = (rd.wb.x + n0[0]) * P.s_av; slot[1] = (rd.wb.y + n0[1]) * P.s_av; slot[2] = (rd.wb.z + n0[2]) * P.s_av;
-      slot[3] = (rd.g.x + n1[0]) * P.s_g; slot[4] = (rd.g.y + n1[1]) * P.s_g; slot[5] = (rd.g.z + n1[2]) * P.s_g;
-      slot[6] = cmd.c[0] * P.s_cmd; slot[7] = cmd.c[1] * P.s_cmd; slot[8] = cmd.c[2] * P.s_cmd;
+      for (int k = 0; k < 9; k++) slot[k] = s9[k];
     }
   }
-  __syncwarp();
-  // cooperative flatten: term-major, oldest -> newest inside each term block
-  // (packages/biped_tasks/biped_tasks/utils/history/observation_manager.py:335-355, circular_buffer.py:79-87,131-135)
-  // Each lane owns output columns lane, lane+32, ...; their source offset inside an env's ring is the same for every env,
-  // so it is decoded once; the loads of one env row are issued back to back (memory-level parallelism).
+  // ---- cooperative flatten from the shared-memory copy: term-major, oldest -> newest inside each term block
+  // (packages/biped_tasks/biped_tasks/utils/history/observation_manager.py:335-355, circular_buffer.py:79-87,131-135).
+  // Each lane owns output columns lane, lane+32, ...; their source offset inside an env's ring is the same for every
+  // env, so it is decoded once (packed: regular offset | offset in the newest slot << 16; -1 = beyond obs_dim). ----
   const int lane = tid & 31;
   const int warp_env0 = (bid * H1V2_BLOCK + (tid & ~31u)) >> 1;
-  constexpr int MAXPASS = (H1V2_MAX_HISTORY * H1V2_OBS_TERM_DIM + 31) / 32;
   const int npass = (P.obs_dim + 31) >> 5;
-  int soff[MAXPASS], foff[MAXPASS];  // source offset in the ring: regular env / fresh env (every slot reads the newest sample)
+  int off[H1V2_OBS_MAXPASS];
 #pragma unroll
-  for (int i = 0; i < MAXPASS; i++) {
+  for (int i = 0; i < H1V2_OBS_MAXPASS; i++) {
     const int idx = lane + 32 * i;
-    soff[i] = -1; foff[i] = 0;
+    off[i] = -1;
     if (i < npass && idx < P.obs_dim) {
       const int hk = __ldg(S.lut + idx);
       const int hh = hk >> 8, k = hk & 255;
       int sl = head + 1 + hh;
       sl = sl >= H ? sl - H : sl;
-      soff[i] = sl * H1V2_HIST_STRIDE + k;
-      foff[i] = head * H1V2_HIST_STRIDE + k;
+      off[i] = (sl * H1V2_HIST_STRIDE + k) | ((head * H1V2_HIST_STRIDE + k) << 16);
     }
   }
-  const int nenv = min(16, P.n - warp_env0);
+  const int nenv = min(16, P.n - warp_env0), epc = hist_envs_per_chunk(H), ring = H * H1V2_HIST_STRIDE;
+  const int my_e = (int)(lane >> 1);
 #pragma unroll 1
-  for (int e = 0; e < nenv; e++) {
-    const int env_e = warp_env0 + e;
-    const bool fresh = (__shfl_sync(0xffffffffu, cmd.flags, 2 * e) & FLAG_HIST_FRESH) != 0;
-    float* hbase = S.hist + (size_t)env_e * H * H1V2_HIST_STRIDE;
-    float* orow = obs + (size_t)env_e * P.obs_dim + lane;
-    float v[MAXPASS];
+  for (int e0 = 0; e0 < nenv; e0 += epc) {
+    if (e0 > 0) { __syncwarp(); hist_prefetch(P, S, tid, bid, e0); }  // H > 10 only: the rings do not fit at once
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (my_e >= e0 && my_e < e0 + epc) {  // the new sample replaces the stale slot `head` of this env's copy
+      float* sl = smem_raw + (my_e - e0) * ring + head * H1V2_HIST_STRIDE;
 #pragma unroll
-    for (int i = 0; i < MAXPASS; i++)
-      if (soff[i] >= 0) v[i] = __ldcg(hbase + (fresh ? foff[i] : soff[i]));
-#pragma unroll
-    for (int i = 0; i < MAXPASS; i++)
-      if (soff[i] >= 0) {
-        if (obs) orow[32 * i] = v[i];
-        if (fresh) hbase[soff[i]] = v[i];  // back-fill: the whole ring holds the first sample (circular_buffer.py:131-135)
+      for (int k = 0; k < 6; k++) {
+        const int i = P.inv_perm[6 * side + k];
+        sl[9 + i] = sv[k]; sl[21 + i] = sv[6 + k]; sl[33 + i] = sv[12 + k];
       }
+      if (side == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) sl[k] = s9[k];
+      }
+    }
+    __syncwarp();
+    const int e1 = min(nenv, e0 + epc);
+#pragma unroll 1
+    for (int e = e0; e < e1; e++) {
+      const int env_e = warp_env0 + e;
+      const bool fresh = (__shfl_sync(0xffffffffu, cmd.flags, 2 * e) & FLAG_HIST_FRESH) != 0;  // warp-uniform
+      const float* hsm = smem_raw + (e - e0) * ring;
+      float* orow = obs + (size_t)env_e * P.obs_dim + lane;
+      const int sh = fresh ? 16 : 0;
+#pragma unroll
+      for (int i = 0; i < H1V2_OBS_MAXPASS; i++)
+        if (off[i] >= 0) {
+          const float v = hsm[(off[i] >> sh) & 0xffff];
+          if (obs) orow[32 * i] = v;
+        }
+      if (fresh) {  // back-fill: the whole ring holds the first sample (circular_buffer.py:131-135)
+        float* hbase = S.hist + (size_t)env_e * ring;
+#pragma unroll
+        for (int i = 0; i < H1V2_OBS_MAXPASS; i++)
+          if (off[i] >= 0) hbase[off[i] & 0xffff] = hsm[(off[i] >> 16) & 0xffff];
+      }
+    }
   }
 }
 
@@ -326,6 +380,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
     }
   }
+  hist_prefetch(P, S, tid, bid, 0);
   // ---- actuator line and command state ----
   {
     float4 a0 = S.act[lidx], a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx], a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
