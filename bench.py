@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-big", action="store_true", help="skip the extra 32768-envs/GPU measurement")
     return ap.parse_args()
 
 
@@ -141,41 +142,45 @@ def run_ours(args):
     n = args.envs
     cfg = default_config()
     cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
-    sim = H1v2Sim(n, cfg, device=dev, seed=args.seed)
-    sim.observe()
-    pool = [sim.random_actions(i) for i in range(16)]  # synthetic N(0,1) actions, resident in HBM
-    obs = torch.empty((n, sim.obs_dim), device=dev)
-    rew = torch.empty(n, device=dev)
-    term = torch.empty(n, dtype=torch.uint8, device=dev)
-    trunc = torch.empty(n, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
     W, K = max(args.warmup, 3), args.steps
-    for i in range(W):
-        sim.step_into(pool[i % 16], obs, rew, term, trunc)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+
+    def timed(n_envs, steps):
+        """K timed control steps of one H1v2Sim: per-step CUDA events, L2 flushed (untimed) between steps, max over ranks."""
+        c = cfg.copy()
+        c.env_id_offset = rank * n_envs
+        sim = H1v2Sim(n_envs, c, device=dev, seed=args.seed)
+        sim.observe()
+        pool = [sim.random_actions(i) for i in range(16)]  # synthetic N(0,1) actions, resident in HBM
+        obs = torch.empty((n_envs, sim.obs_dim), device=dev)
+        rew = torch.empty(n_envs, device=dev)
+        term = torch.empty(n_envs, dtype=torch.uint8, device=dev)
+        trunc = torch.empty(n_envs, dtype=torch.uint8, device=dev)
+        for i in range(W):
+            sim.step_into(pool[i % 16], obs, rew, term, trunc)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = sim.launch_count
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (not timed)
+            ev[i][0].record()
+            sim.step_into(pool[i % 16], obs, rew, term, trunc)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return sim, pool, float(t.item()), sim.launch_count - l0
+
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = sim.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for i in range(K):
-        flush.zero_()  # L2 flush between timed iterations (not timed)
-        ev[i][0].record()
-        sim.step_into(pool[i % 16], obs, rew, term, trunc)
-        ev[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches = sim.launch_count - l0
+    sim, pool, total_ms, launches = timed(n, K)
     clocks = sampler.stop() if sampler else None
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     ms_per_step = total_ms / K
     value = world * n * K / (total_ms * 1e-3)
     logv = sim.log_host()
@@ -203,6 +208,13 @@ def run_ours(args):
         e2e = {"value": world * n * Ke / float(td.item()), "unit": METRIC, "h2d_bytes_per_step": n * 12 * 4,
                "d2h_bytes_per_step": n * (sim.obs_dim * 4 + 4 + 1 + 1), "steps": Ke, "timer": "host wall clock around synchronous h1v2_step_host calls"}
 
+    big = None
+    if n != 32768 and not args.no_big:  # the north-star target is quoted at 32768 envs/GPU: report it beside configs[1]
+        sim.close()
+        sim_b, _, ms_b, _ = timed(32768, max(20, K // 3))
+        kb = max(20, K // 3)
+        big = {"envs_per_gpu": 32768, "value": world * 32768 * kb / (ms_b * 1e-3), "unit": METRIC, "ms_per_step": ms_b / kb, "steps": kb}
+        sim_b.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -217,7 +229,9 @@ def run_ours(args):
     fp = C.c_float(0.0)
     load_library().h1v2_measure_fp32_peak(local, C.byref(fp))
     rf_path = os.path.join(ROOT, "profiles", "roofline.json")
-    flops_per_env_step = json.load(open(rf_path)).get("fp32_flops_per_env_step") if os.path.exists(rf_path) else None
+    rf = json.load(open(rf_path)) if os.path.exists(rf_path) else {}
+    flops_per_env_step = rf.get("fp32_flops_per_env_step")
+    traffic = rf.get("dram_bytes_per_launch", {}).get(str(n))  # ncu dram read+write of one launch at this env count, else null
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -227,13 +241,16 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                      "note": "the step kernel is FP32-issue bound, not HBM bound (SURVEY 8(d)); see roofline_fp32"},
         "roofline_fp32": {"bound": "fp32", "peak": float(fp.value), "unit": "TFLOP/s", "peak_source": "h1v2_measure_fp32_peak (FFMA micro-benchmark, this run)",
                           "flops_per_env_step": flops_per_env_step,
                           "achieved": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12) if flops_per_env_step else None,
                           "frac": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None},
+        "at_32768_envs_per_gpu": (dict(big, roofline_hbm_frac=ALGO_BYTES_PER_ENV_STEP * 32768 / (big["ms_per_step"] * 1e-3) / 1e9 / hbm_peak,
+                                       roofline_fp32_frac=(flops_per_env_step * 32768 / (big["ms_per_step"] * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None)
+                                  if big else None),
         "solver": {"mean_newton_iters_per_substep": float(logv[28]) / (4.0 * n), "max_iters_last_step": float(logv[26]), "cap_hits_last_step": float(logv[27]),
                    "nan_resets": float(logv[25])},
     }

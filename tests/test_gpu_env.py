@@ -58,3 +58,23 @@ def test_rsl_rl_ppo_runs_on_the_backend(tmp_path):
         assert torch.isfinite(p).all()
     assert runner.current_learning_iteration >= 1
     env.close()
+
+
+def test_rank_shards_are_slices_of_one_job(cfg):
+    """Multi-GPU sharding rule: a handle created with env_id_offset = r*n reproduces envs
+    [r*n, (r+1)*n) of a single 2n-env handle bit for bit -- reset draws, noise, resamples -- with no exchange."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 256
+    whole = H1v2Sim(2 * n, cfg, device="cuda:0", seed=42)
+    c1 = cfg.copy(); c1.env_id_offset = n
+    shard = H1v2Sim(n, c1, device="cuda:0", seed=42)
+    o_w, o_s = whole.observe(), shard.observe()
+    assert torch.equal(o_w[n:], o_s)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(8):
+        a = torch.randn((2 * n, 12), device="cuda", generator=g)
+        o_w, r_w, t_w, u_w = whole.step(a)
+        o_s, r_s, t_s, u_s = shard.step(a[n:].contiguous())
+        assert torch.equal(o_w[n:], o_s) and torch.equal(r_w[n:], r_s) and torch.equal(t_w[n:], t_s) and torch.equal(u_w[n:], u_s)
+    whole.close(); shard.close()
