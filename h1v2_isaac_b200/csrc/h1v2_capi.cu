@@ -354,6 +354,15 @@ static int dalloc(H1v2Handle* h, T** p, size_t count) {
   return 0;
 }
 
+// device-visible alias of a host pointer when it is pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory), else NULL
+template <typename T>
+static T* mapped_alias(T* host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return (T*)a.devicePointer;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------------
@@ -489,12 +498,21 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
     CK(cudaMalloc(&h->d_trunc, N));
   }
   cudaStream_t st = h->host_stream;
-  CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (launch_step(h, true, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, st) != 0) return -1;
-  CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+  // Pinned caller buffers are written by the kernel itself (zero-copy over PCIe): the 1.8 KB observation row of an env
+  // leaves the GPU as soon as its warp has emitted it, overlapping the transfer with the rest of the step instead of
+  // serialising a 450-float-per-env D2H copy behind the kernel.  Pageable buffers take the staged path.
+  float* obs_dev = mapped_alias(obs);
+  float* rew_dev = mapped_alias(rew);
+  uint8_t* term_dev = mapped_alias(terminated);
+  uint8_t* trunc_dev = mapped_alias(truncated);
+  const float* act_dev = mapped_alias(const_cast<float*>(actions));
+  if (!act_dev) { CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st)); act_dev = h->d_act; }
+  if (launch_step(h, true, act_dev, obs_dev ? obs_dev : h->d_obs, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term,
+                  trunc_dev ? trunc_dev : h->d_trunc, st) != 0) return -1;
+  if (!obs_dev) CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
+  if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -233,18 +233,22 @@ def test_full_size_properties(cfg, n):
         assert torch.equal(obs_h[k], obs_a[k][half:]), k
 
 
-def test_step_host_matches_device_path(cfg):
-    """The HOST-buffer entry point (what a non-torch caller binds) gives exactly the device path's results."""
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_matches_device_path(cfg, pinned):
+    """The HOST-buffer entry point (what a non-torch caller binds) gives exactly the device path's results, both through
+    the zero-copy path (pinned buffers, written by the kernel over PCIe) and the staged one (pageable numpy buffers)."""
     import torch
     from h1v2_isaac_b200.backend import H1v2Sim
     n = 1024
     s1, s2 = H1v2Sim(n, cfg, seed=4), H1v2Sim(n, cfg, seed=4)
     s1.observe(); s2.observe()
-    hobs = torch.empty((n, s1.obs_dim)).pin_memory(); hrew = torch.empty(n).pin_memory()
-    ht = torch.empty(n, dtype=torch.uint8).pin_memory(); hu = torch.empty(n, dtype=torch.uint8).pin_memory()
+    pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
+    hobs = pin(torch.empty((n, s1.obs_dim))); hrew = pin(torch.empty(n))
+    ht = pin(torch.empty(n, dtype=torch.uint8)); hu = pin(torch.empty(n, dtype=torch.uint8))
     for i in range(5):
         a = s1.random_actions(i)
         o, r, t, u = s1.step(a)
-        s2.step_host(a.cpu().pin_memory(), hobs, hrew, ht, hu)
+        s2.step_host(pin(a.cpu()), hobs, hrew, ht, hu)
         assert torch.equal(o.cpu(), hobs) and torch.equal(r.cpu(), hrew) and torch.equal(t.cpu().to(torch.uint8), ht)
+        assert torch.equal(u.cpu().to(torch.uint8), hu)
     s1.close(); s2.close()
