@@ -54,7 +54,7 @@ class H1v2Config(C.Structure):
         ("reset_joint_pos_scale", f32 * 2), ("reset_joint_vel_scale", f32 * 2), ("init_root_height", f32),
         ("push_enable", i32), ("push_interval_s", f32 * 2), ("push_vel_xy", f32 * 2),
         ("mass_add_range", f32 * 2), ("friction_range", f32 * 2),
-        ("env_id_offset", i64), ("env_spacing", f32), ("reserved", i32 * 8),
+        ("env_id_offset", i64), ("env_spacing", f32), ("joint_vel_limit", f32), ("runaway_vel", f32), ("reserved", i32 * 8),
     ]
 
     def copy(self) -> "H1v2Config":

@@ -304,6 +304,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   if (c.max_delay > 2 * c.decimation) return fail("config: max_delay exceeds two control steps");
   P.min_delay = c.min_delay; P.max_delay = c.max_delay;
   P.gravity = c.gravity;
+  P.vel_limit = c.joint_vel_limit; P.runaway_vel = c.runaway_vel > 0.f ? c.runaway_vel : 3.0e38f;
   float Kf, Bf;
   kb_h(c.floss_solref, c.floss_solimp, c.sim_dt, &Kf, &Bf);
   P.floss_B = Bf;

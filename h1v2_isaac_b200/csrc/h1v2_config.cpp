@@ -112,5 +112,7 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->friction_range[0] = c->friction_range[1] = c->friction;
   c->env_id_offset = 0;
   c->env_spacing = 2.5f;
+  c->joint_vel_limit = 100.0f;  // A/robots/h12.py:66,89,103 velocity_limit
+  c->runaway_vel = 1000.0f;     // A/robots/h12.py:27-28 max_linear_velocity / max_angular_velocity
   return 0;
 }

@@ -38,6 +38,7 @@ struct KParams {
   int min_delay, max_delay;
   // physics
   float gravity;
+  float vel_limit, runaway_vel;  // joint velocity clamp (<= 0: off); runaway-state guard
   float damping[18], armature[18];
   float floss[18], floss_D[18], floss_lim[18], floss_B;  // lim = R*frictionloss
   float range_lo[12], range_hi[12], limit_invw[12], limit_K, limit_B, limit_imp[5];

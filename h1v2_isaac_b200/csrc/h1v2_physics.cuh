@@ -754,7 +754,9 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   for (int j = 0; j < 6; j++) {
     const float a = sm.jf(j, F_FS);
     out.qacc[j] = a; wl[j] = a;
-    qd[j] = fmaf(h, a, qd[j]); q[j] = fmaf(h, qd[j], q[j]);
+    qd[j] = fmaf(h, a, qd[j]);
+    if (P.vel_limit > 0.f) qd[j] = fminf(fmaxf(qd[j], -P.vel_limit), P.vel_limit);  // actuator velocity_limit (A/robots/h12.py:66)
+    q[j] = fmaf(h, qd[j], q[j]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, wr[k], rv[k]); rw[k] = fmaf(h, wr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }

@@ -408,12 +408,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       cmd.flags &= ~FLAG_DELAY_FRESH;
     }
 
-    // ---- non-finite guard ----
+    // ---- non-finite / runaway guard ----
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !isfinite(qd[k]);
+    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !(fabsf(qd[k]) <= P.runaway_vel);
 #pragma unroll
-    for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !isfinite(rv[k]) || !isfinite(rw[k]);
+    for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !(fabsf(rv[k]) <= P.runaway_vel) || !(fabsf(rw[k]) <= P.runaway_vel);
     bad |= !isfinite(rq[0]) || !isfinite(rq[1]) || !isfinite(rq[2]) || !isfinite(rq[3]);
     bad = (__shfl_xor_sync(FULL_MASK, (int)bad, 1) | (int)bad) != 0;
 

@@ -111,7 +111,7 @@ def flatten_cfg(cfg) -> H1v2Config:
     q0 = _per_joint(robot.init_state.joint_pos, 0.0)
     c.soft_limit_factor = float(_get(robot, "soft_joint_pos_limit_factor", 1.0))
     kp, kd, ef = [None] * NJ, [None] * NJ, [None] * NJ
-    delays = set()
+    delays, vlims = set(), set()
     for name, act in robot.actuators.items():
         ids = _match(act.joint_names_expr, JOINT_NAMES)
         st, dm = _per_joint(act.stiffness, float("nan")), _per_joint(act.damping, float("nan"))
@@ -122,11 +122,17 @@ def flatten_cfg(cfg) -> H1v2Config:
             if arm is not None:
                 c.dof_armature[6 + i] = _per_joint(arm, 0.0)[i]
         delays.add((int(_get(act, "min_delay", 0)), int(_get(act, "max_delay", 0))))
+        vl = _get(act, "velocity_limit")
+        vlims.add(None if vl is None else float(vl))
     if any(v is None or (isinstance(v, float) and math.isnan(v)) for v in kp + kd):
         raise NotImplementedError("actuators: every one of the 12 leg joints needs stiffness and damping")
     if len(delays) != 1:
         raise NotImplementedError(f"actuators: all groups must share one (min_delay, max_delay); got {sorted(delays)}")
     c.min_delay, c.max_delay = delays.pop()
+    if len(vlims) != 1:
+        raise NotImplementedError(f"actuators: all groups must share one velocity_limit; got {sorted(map(str, vlims))}")
+    vl = vlims.pop()
+    c.joint_vel_limit = 0.0 if vl is None else vl
     for i in range(NJ):
         c.default_joint_pos[i], c.kp[i], c.kd[i] = q0[i], kp[i], kd[i]
         c.effort_limit[i] = ef[i] if math.isfinite(ef[i]) else 1e9

@@ -48,7 +48,7 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
     groups = {"legs": [0, 1, 2, 6, 7, 8], "knees": [3, 9], "feet": [4, 5, 10, 11]}
     actuators = {
         g: DelayedPDActuatorCfg(joint_names_expr=[JOINT_NAMES[i] for i in ids], effort_limit={JOINT_NAMES[i]: c.effort_limit[i] for i in ids},
-                                velocity_limit=100.0, stiffness={JOINT_NAMES[i]: c.kp[i] for i in ids}, damping={JOINT_NAMES[i]: c.kd[i] for i in ids},
+                                velocity_limit=(c.joint_vel_limit if c.joint_vel_limit > 0 else None), stiffness={JOINT_NAMES[i]: c.kp[i] for i in ids}, damping={JOINT_NAMES[i]: c.kd[i] for i in ids},
                                 armature=c.dof_armature[6 + ids[0]], friction=0.0, min_delay=c.min_delay, max_delay=c.max_delay)
         for g, ids in groups.items()}
     robot = ArticulationCfg(prim_path="{ENV_REGEX_NS}/Robot", init_state=ArticulationCfg.InitialStateCfg(

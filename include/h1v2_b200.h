@@ -149,6 +149,10 @@ typedef struct H1v2Config {
   /* ---- sharding ---- */
   int64_t env_id_offset;               /* global id of local env 0 (rank * n_envs) for the Philox key */
   float env_spacing;                   /* 2.5 m grid (velocity_env_cfg.py:288) */
+  float joint_vel_limit;               /* actuator velocity_limit (rad/s, robots/h12.py:66,89,103): joint velocities are clamped
+                                          to it after every physics step, as PhysX does; <= 0 disables */
+  float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
+                                          non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
   int32_t reserved[8];
 } H1v2Config;
 

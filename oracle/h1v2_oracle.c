@@ -626,6 +626,8 @@ static void physics_substep(const H1v2Oracle* o, OEnv* e, const double ctrl[NJ])
   chol_solve(A, NV, rhs);
   for (int j = 0; j < NJ; j++) e->joint_acc[j] = rhs[6 + j];
   for (int d = 0; d < NV; d++) e->qvel[d] += h * rhs[d];
+  if (cfg->joint_vel_limit > 0.f) /* actuator velocity_limit (A/robots/h12.py:66,89,103), PhysX joint velocity clamp */
+    for (int j = 0; j < NJ; j++) e->qvel[6 + j] = fmin(fmax(e->qvel[6 + j], -(double)cfg->joint_vel_limit), (double)cfg->joint_vel_limit);
   for (int i = 0; i < 3; i++) e->qpos[i] += h * e->qvel[i];
   quat_integrate(e->qpos + 3, e->qvel + 3, h);
   for (int j = 0; j < NJ; j++) e->qpos[7 + j] += h * e->qvel[6 + j];
@@ -913,7 +915,8 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   /* non-finite guard: force a reset, zero reward */
   int bad = 0;
   for (int i = 0; i < 19; i++) if (!isfinite(e->qpos[i])) bad = 1;
-  for (int i = 0; i < 18; i++) if (!isfinite(e->qvel[i])) bad = 1;
+  const double runaway = c->runaway_vel > 0.f ? (double)c->runaway_vel : 3.0e38;
+  for (int i = 0; i < 18; i++) if (!(fabs((double)(float)e->qvel[i]) <= runaway)) bad = 1;
   *nan_flag = bad;
   /* -- counters, terminations -- */
   e->ep_len += 1;
