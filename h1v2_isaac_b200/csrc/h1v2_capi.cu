@@ -340,6 +340,17 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.key0 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
   P.env_id_offset = c.env_id_offset;
   P.n = n;
+  // envs per warp: 16 fills the lanes; with few envs, fewer per warp shorten every warp's Newton loop (it runs as long as
+  // its slowest env).  Measured on B200 (tools/diag_epw.py): best is the smallest group that keeps the grid within ~3.5
+  // warps per SM (4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16).  reserved[2] overrides.
+  {
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int epw = 1;
+    while (epw < 16 && 2 * ((n + epw - 1) / epw) > 7 * sms) epw *= 2;
+    if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) epw = c.reserved[2];
+    P.epw = epw;
+  }
   return 0;
 }
 
@@ -458,8 +469,8 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
 }
 
 static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st) {
-  const int threads = H1V2_BLOCK, lanes = 2 * h->n;
-  const int blocks = (lanes + threads - 1) / threads;
+  const int threads = H1V2_BLOCK;
+  const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
   const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

@@ -72,6 +72,7 @@ struct KParams {
   uint32_t key0;
   int64_t env_id_offset;
   int n;
+  int epw;  // envs per warp (1,2,4,8,16): lanes 2*epw..31 shadow the warp's first env (small-N mapping)
 };
 
 // --- internal state, SoA of float4 so that every lane issues coalesced 128-bit accesses ---

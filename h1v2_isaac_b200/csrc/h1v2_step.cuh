@@ -136,12 +136,12 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
 // right after the physics (the per-thread columns are dead by then) and awaited only when the observation is emitted,
 // so the HBM latency hides behind the reward / termination / reset / command code (profiles/r1k: with register-staged
 // loads the emission was 27 % of the step, 76 % of it long-scoreboard stalls).
-__device__ __forceinline__ int hist_envs_per_chunk(int H) { return min(16, (SMEM_FLOATS * H1V2_BLOCK) / (H * H1V2_HIST_STRIDE)); }
+__device__ __forceinline__ int hist_envs_per_chunk(int H, int epw) { return min(epw, (SMEM_FLOATS * H1V2_BLOCK) / (H * H1V2_HIST_STRIDE)); }
 __device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S, unsigned tid, unsigned bid, int e0) {
   extern __shared__ __align__(16) float smem_raw[];
   const int lane = tid & 31;
-  const int warp_env0 = (bid * H1V2_BLOCK + (tid & ~31u)) >> 1;
-  const int ne = min(hist_envs_per_chunk(P.H), min(16, P.n - warp_env0) - e0);
+  const int warp_env0 = (int)bid * P.epw;
+  const int ne = min(hist_envs_per_chunk(P.H, P.epw), min(P.epw, P.n - warp_env0) - e0);
   const int nchunk = ne * P.H * (H1V2_HIST_STRIDE / 4);  // 16-byte pieces
   const float* src = S.hist + (size_t)(warp_env0 + e0) * P.H * H1V2_HIST_STRIDE;
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -207,7 +207,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   // Each lane owns output columns lane, lane+32, ...; their source offset inside an env's ring is the same for every
   // env, so it is decoded once (packed: regular offset | offset in the newest slot << 16; -1 = beyond obs_dim). ----
   const int lane = tid & 31;
-  const int warp_env0 = (bid * H1V2_BLOCK + (tid & ~31u)) >> 1;
+  const int warp_env0 = (int)bid * P.epw;
   const int npass = (P.obs_dim + 31) >> 5;
   int off[H1V2_OBS_MAXPASS];
 #pragma unroll
@@ -222,7 +222,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
       off[i] = (sl * H1V2_HIST_STRIDE + k) | ((head * H1V2_HIST_STRIDE + k) << 16);
     }
   }
-  const int nenv = min(16, P.n - warp_env0), epc = hist_envs_per_chunk(H), ring = H * H1V2_HIST_STRIDE;
+  const int nenv = min(P.epw, P.n - warp_env0), epc = hist_envs_per_chunk(H, P.epw), ring = H * H1V2_HIST_STRIDE;
   const int my_e = (int)(lane >> 1);
 #pragma unroll 1
   for (int e0 = 0; e0 < nenv; e0 += epc) {
@@ -275,10 +275,14 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   unsigned tid, bid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
+  // lane pair p of warp w owns env w*epw + p for p < epw; the remaining lanes shadow the warp's first env (their work is
+  // bit-identical to it, so they never lengthen the warp's Newton loop) and store nothing
   const int gtid = bid * H1V2_BLOCK + tid;
-  const int side = gtid & 1;
-  const bool valid = (gtid >> 1) < P.n;
-  const int env = valid ? (gtid >> 1) : P.n - 1;
+  const int side = tid & 1;
+  const int slot = (int)(tid >> 1);
+  const int warp_env0 = (int)bid * P.epw;
+  const bool valid = slot < P.epw && warp_env0 + slot < P.n;
+  const int env = valid ? warp_env0 + slot : min(warp_env0, P.n - 1);
   const int lidx = 2 * env + side;
   const unsigned pm = 3u << (tid & 30);
   const int N = P.n, N2 = 2 * P.n;

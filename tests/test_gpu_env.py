@@ -78,3 +78,31 @@ def test_rank_shards_are_slices_of_one_job(cfg):
         o_s, r_s, t_s, u_s = shard.step(a[n:].contiguous())
         assert torch.equal(o_w[n:], o_s) and torch.equal(r_w[n:], r_s) and torch.equal(t_w[n:], t_s) and torch.equal(u_w[n:], u_s)
     whole.close(); shard.close()
+
+
+def test_envs_per_warp_mapping_is_bit_identical(cfg):
+    """The small-N mapping (fewer envs per warp, spare lanes shadowing the warp's first env) must not change a single bit
+    of any env's trajectory: same arithmetic per env, only the grouping into warps differs."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 200  # not a multiple of any group size: exercises the ragged last warp
+    sims = []
+    for epw in (16, 8, 4, 1):
+        c = cfg.copy(); c.reserved[2] = epw
+        sims.append(H1v2Sim(n, c, device="cuda:0", seed=9))
+    obs0 = [s.observe() for s in sims]
+    for o in obs0[1:]:
+        assert torch.equal(obs0[0], o)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(12):
+        a = torch.randn((n, 12), device="cuda", generator=g)
+        outs = [s.step(a) for s in sims]
+        for o in outs[1:]:
+            for x, y in zip(outs[0], o):
+                assert torch.equal(x, y)
+    st = [s.get_state(["joint_pos", "root_quat", "episode_sums", "feet_timers"]) for s in sims]
+    for other in st[1:]:
+        for k in st[0]:
+            assert torch.equal(st[0][k], other[k]), k
+    for s in sims:
+        s.close()
