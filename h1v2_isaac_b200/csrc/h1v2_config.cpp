@@ -57,7 +57,7 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->solver_iterations = 12;
   c->solver_tolerance = 1e-5f;  // on the scaled gradient norm; the fp32 noise floor of that norm is ~3e-6 (profiles/r1_notes.md), below it iterations only chase rounding
   c->solver_step_tolerance = 1e-3f;
-  c->solver_ls_tolerance = 0.01f;
+  c->solver_ls_tolerance = 0.3f;  // MuJoCo default 0.01; 0.01..0.3 give the same Newton iteration histogram and parity on B200 (tools/diag_lstol.py), 0.3 is 5 % faster
   // observations: V/velocity_env_cfg.py:123-132 ; C12/flat_env_cfg.py:25-27
   c->history_length = 10;
   c->enable_corruption = 1;

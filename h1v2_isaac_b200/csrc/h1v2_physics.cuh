@@ -28,6 +28,24 @@
 namespace h1v2 {
 
 #define H1V2_BLOCK 32
+// unroll factors of the joint loops inside the Newton trip (tuned on B200, tools/diag_unroll.sh; 1 = rolled)
+#define H1V2_PRAGMA(x) _Pragma(#x)
+#define UNROLL(n) H1V2_PRAGMA(unroll n)
+#ifndef U_SWEEP1
+#define U_SWEEP1 1
+#endif
+#ifndef U_SWEEP2
+#define U_SWEEP2 1
+#endif
+#ifndef U_MPROD
+#define U_MPROD 1
+#endif
+#ifndef U_LSJ
+#define U_LSJ 1
+#endif
+#ifndef U_EVJ
+#define U_EVJ 1
+#endif
 // shared-memory column of one thread: 6 joints x JSTRIDE floats, then MAXC contact points x PSTRIDE floats
 #define JSTRIDE 32
 #define F_W 0      // 3  joint axis (world)
@@ -506,7 +524,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
         for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
       }
       float gn2 = 0.f;
-#pragma unroll 1
+UNROLL(U_EVJ)
       for (int j = 0; j < 6; j++) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
         const float x = sm.jf(j, F_XQ);
         float act;
@@ -546,7 +564,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
       k6_zero(IA);
       V3 pn = zero3, pl = zero3;
       const float Dk = newton ? 1.f : 0.f;  // contact stiffness enters the Newton Hessian only
-#pragma unroll 1
+UNROLL(U_SWEEP1)
       for (int j = 5; j >= 0; j--) {
         k6_add_rigid(IA, sm.ji(j));
         if (j == 5 || j == 3) {  // contact stiffness of the foot / shin link, straight into the articulated inertia
@@ -617,7 +635,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
     Sa_f = Sa_r; Sl_f = Sl_r + cross(Sa_r, d);
     Sa_s = Sa_f; Sl_s = Sl_f;
     float smax = 0.f;
-#pragma unroll 1
+UNROLL(U_SWEEP2)
     for (int j = 0; j < 6; j++) {
       float s = sm.jf(j, F_R);
       if (!first) {
@@ -642,7 +660,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
     float sMs = 0.f, sMa = 0.f, gs = 0.f;
     {
       V3 fcn = zero3, fcl = zero3;
-#pragma unroll 1
+UNROLL(U_MPROD)
       for (int j = 5; j >= 0; j--) {
         fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
         const float s = sm.jf(j, F_R);
@@ -670,7 +688,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
 #pragma unroll 1
       for (int ls = 0; __any_sync(FULL_MASK, search); ls++) {
         float d1 = 0.f, d2 = 0.f;
-#pragma unroll 1
+UNROLL(U_LSJ)
         for (int j = 0; j < 6; j++) {
           const float s = sm.jf(j, F_R);
           const float xa = fmaf(alpha, s, sm.jf(j, F_XQ));
