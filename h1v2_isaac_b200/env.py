@@ -98,6 +98,12 @@ def _slot_mask(params, key="sensor_cfg") -> int:
 def flatten_cfg(cfg) -> H1v2Config:
     """Resolved ManagerBasedRLEnvCfg tree (reference: config/h12_12dof/flat_env_cfg.py:13-48 and parents) -> H1v2Config."""
     c = default_config()  # rigid-body model, MuJoCo solver parameters; everything below is overwritten from the tree
+    # managers the fused kernel does not have: refuse rather than silently drop them
+    if _get(cfg, "constraints") is not None:
+        raise NotImplementedError("constraints: the Constraints-as-Terminations manager (utils/cat) is not implemented in the fused kernel")
+    cur = [n for n, t in _terms(_get(cfg, "curriculum"))]
+    if cur:
+        raise NotImplementedError(f"curriculum: terms {cur} are not implemented (the Flat id sets terrain_levels=None and has no other)")
     c.sim_dt = float(cfg.sim.dt)
     c.decimation = int(cfg.decimation)
     c.episode_length_s = float(cfg.episode_length_s)

@@ -5,7 +5,7 @@ from h1v2_isaac_b200.backend import H1v2Sim
 from h1v2_isaac_b200._capi import default_config
 from oracle.oracle import Oracle
 from test_gpu_parity import PHYS, SYNC, _np, _resync
-for lstol in (0.01, 0.03, 0.1, 0.3):
+for lstol in (0.3, 0.5, 0.7, 1.0, 2.0):
     cfg = default_config(); cfg.solver_ls_tolerance = lstol
     n = 32768
     sim = H1v2Sim(n, cfg, seed=1); sim.observe()
