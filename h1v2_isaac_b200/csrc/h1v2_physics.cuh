@@ -294,7 +294,19 @@ __device__ __forceinline__ void rotate_rt(M3& R, int ax, float s, float c) {
   else rotate_sc<0>(R, s, c);
 }
 __device__ __forceinline__ V3 axis_rt(const M3& R, int ax) { return ax == 0 ? R.cx : (ax == 1 ? R.cy : R.cz); }
-__device__ __noinline__ float impedance_call(const float* si, float pos) { return impedance(si, pos); }
+__device__ __noinline__ float impedance_general(const float* si, float pos) { return impedance(si, pos); }
+// MuJoCo's default solimp (power 2, every geom and joint of h12_12dof.xml) inline; anything else out of line (powf paths)
+__device__ __forceinline__ float impedance_call(const float* si, float pos) {
+  if (si[4] != 2.f || si[2] <= 1e-15f) return impedance_general(si, pos);
+  const float dmin = fminf(fmaxf(si[0], 1e-4f), 0.9999f), dmax = fminf(fmaxf(si[1], 1e-4f), 0.9999f);
+  const float mid = fminf(fmaxf(si[3], 1e-4f), 0.9999f);
+  if (dmin == dmax) return 0.5f * (dmin + dmax);
+  const float x = fabsf(pos) / si[2];
+  if (x >= 1.f) return dmax;
+  if (x == 0.f) return dmin;
+  const float y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  return dmin + y * (dmax - dmin);
+}
 
 // ----------------------------------------------------------------------------------------------------------
 // One physics substep.  State is updated in place.  tau = joint torques after the actuator's effort clip.

@@ -306,6 +306,13 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     flags0 = __float_as_int(S.cmd[N + env].w);
   }
   float4 tm = S.timers[lidx];
+  if (DO_STEP) {  // warm the L1 with the actuator line and this env's action row: the PD loop re-reads them every substep
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.act + N2 + lidx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.act + 2 * N2 + lidx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.act + 3 * N2 + lidx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.act + 4 * N2 + lidx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)env * 12 + 6 * side));
+  }
   float wl[6], wr[6];
   {
     float4 w0 = S.warm[lidx], w1 = S.warm[N2 + lidx], w2 = S.warm[2 * N2 + lidx];
