@@ -252,3 +252,100 @@ def test_step_host_matches_device_path(cfg, pinned):
         assert torch.equal(o.cpu(), hobs) and torch.equal(r.cpu(), hrew) and torch.equal(t.cpu().to(torch.uint8), ht)
         assert torch.equal(u.cpu().to(torch.uint8), hu)
     s1.close(); s2.close()
+
+
+def _randomised(cfg, mu_lo=0.3):
+    """BASELINE configs[4]: push events, base-mass and friction randomisation on (V/velocity_env_cfg.py:153-173,212-217;
+    friction range of C12/rsl_env_cfg.py:213-223); the push interval is shortened so that pushes fire inside the test.
+    The strict physics bounds are asserted for mu >= 0.3; below that the fp32 primal Newton loses convergence in a small
+    fraction of solves (MuJoCo's pyramidal regulariser makes the normal contact stiffness grow as 1/mu^2: 64x at mu = 0.1,
+    which puts stiffness/inertia past 1/eps of fp32) -- measured and bounded in test_low_friction_is_bounded."""
+    c = cfg.copy()
+    c.push_enable = 1
+    c.push_interval_s[0], c.push_interval_s[1] = 0.06, 0.3
+    c.push_vel_xy[0], c.push_vel_xy[1] = -0.5, 0.5
+    c.mass_add_range[0], c.mass_add_range[1] = -5.0, 5.0
+    c.friction_range[0], c.friction_range[1] = mu_lo, 1.25
+    return c
+
+
+def test_randomised_events_parity(cfg):
+    """Startup randomisation (per-env friction and base mass), interval pushes: draws bit-identical to the oracle's,
+    physics from identical states within the same bounds as the nominal task, push velocities / timers on identical
+    post-physics states to 1e-6."""
+    c = _randomised(cfg)
+    n = 2048
+    torch, sim, orc = _mk(c, n, 17)
+    g, o = _np(sim.get_state(SYNC)), orc.get_state(SYNC)
+    for k in ("friction", "mass_add", "push_time_left"):
+        np.testing.assert_allclose(g[k], o[k], rtol=0, atol=1e-6, err_msg=k)
+    assert g["friction"].min() < 0.35 and g["friction"].max() > 1.0 and g["mass_add"].min() < -4 and g["mass_add"].max() > 4
+    sim.observe(); orc.observe()
+    rng = np.random.default_rng(5)
+    errs = {k: [] for k in PHYS}
+    n_push = 0
+    for step in range(16):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        # (1) physics with randomised mass / friction from identical states
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        g = _np(sim.get_state(SYNC + POST))
+        before = orc.get_state(["push_time_left"])["push_time_left"][:, 0]
+        # (2) the tail on identical post-physics states: push draw, push timer, reset
+        _, _, to, uo = orc.step_injected(a, g)
+        o = orc.get_state(SYNC)
+        assert np.array_equal(tg.cpu().numpy(), to) and np.array_equal(ug.cpu().numpy(), uo)
+        for k in ("root_lin_vel", "push_time_left", "friction", "mass_add", "root_pos", "joint_pos"):
+            np.testing.assert_allclose(g[k], o[k], rtol=1e-5, atol=2e-6, err_msg=f"{k}, step {step}")
+        fired = (o["push_time_left"][:, 0] > before) & ~(to | uo)
+        n_push += int(fired.sum())
+        _resync(sim, orc, g)
+    assert n_push > 500, n_push
+    # free physics comparison (oracle runs its own substeps) on the randomised model
+    for step in range(12):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        _, _, to, uo = orc.step(a)
+        g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS + ["push_time_left"])
+        mc, ml = orc.activation_margin()
+        pushed = np.abs(g["push_time_left"][:, 0] - o["push_time_left"][:, 0]) > 1e-6
+        keep = ~(to | uo | tg.cpu().numpy()) & (mc > 2e-6) & (ml > 2e-6) & ~pushed
+        for k in PHYS:
+            errs[k].append(np.abs(g[k][keep] - o[k][keep]).max(axis=1))
+        _resync(sim, orc, g)
+    e = {k: np.concatenate(v) for k, v in errs.items()}
+    print({k: (float(v.max()), float(np.quantile(v, 0.999))) for k, v in e.items()})
+    # same quantile bounds as the nominal task; the absolute worst case is not asserted at 5e-3 here because the low end
+    # of the friction range (0.3..0.5) already shows ~1e-5 of solves that stop at the Newton cap (tools/diag_rand2.py)
+    for k in ("joint_pos", "root_pos", "root_quat"):
+        assert np.quantile(e[k], 0.9995) < 1e-4 and e[k].max() < 1e-2, k
+    for k in ("joint_vel", "root_lin_vel", "root_ang_vel"):
+        assert np.quantile(e[k], 0.99) < 5e-4 and np.quantile(e[k], 0.999) < 1.5e-3 and float((e[k] > 5e-3).mean()) < 3e-4, k
+
+
+def test_low_friction_is_bounded(cfg):
+    """Known fp32 limit: at mu in [0.1, 0.3) a small fraction of contact solves does not converge
+    within the Newton cap.  This pins how small: >= 99.5 % of env-steps stay within 5e-3 rad/s of the oracle at mu ~ 0.1,
+    every state stays finite, and nothing is force-reset by the runaway guard."""
+    c = _randomised(cfg, mu_lo=0.1)
+    c.friction_range[1] = 0.12
+    c.push_enable = 0
+    n = 4096
+    torch, sim, orc = _mk(c, n, 17)
+    sim.observe(); orc.observe()
+    rng = np.random.default_rng(5)
+    errs = []
+    for step in range(20):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        _, _, to, uo = orc.step(a)
+        g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS)
+        mc, ml = orc.activation_margin()
+        keep = ~(to | uo | tg.cpu().numpy()) & (mc > 2e-6) & (ml > 2e-6)
+        errs.append(np.abs(g["joint_vel"][keep] - o["joint_vel"][keep]).max(axis=1))
+        assert all(np.isfinite(v).all() for v in g.values() if v.dtype.kind == "f")
+        _resync(sim, orc, g)
+    e = np.concatenate(errs)
+    frac = float((e > 5e-3).mean())
+    print(f"mu~0.1: {len(e)} env-steps, {100 * frac:.3f} % beyond 5e-3 rad/s, q99 {np.quantile(e, 0.99):.2e}")
+    assert frac < 5e-3 and np.quantile(e, 0.99) < 5e-3
+    assert sim.log_host()[25] == 0
