@@ -54,7 +54,9 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   std::memcpy(c->limit_solimp, solimp, sizeof(solimp));
   c->floss_solref[0] = 0.02f; c->floss_solref[1] = 1.0f;
   c->limit_solref[0] = 0.02f; c->limit_solref[1] = 1.0f;
-  c->solver_iterations = 12;
+  c->solver_iterations = 12;  // Newton cap (MuJoCo: 100).  Enough at the task's mu = 0.8 (< 1e-5 of solves reach it); the kernel ends when its
+                              // slowest warp does, so a larger cap costs ~9 % even when almost no solve uses it.  flatten_cfg raises it to
+                              // 30 when the friction range reaches below 0.3 (10x fewer non-converged solves at mu ~ 0.1, tools/diag_rand3.py)
   c->solver_tolerance = 1e-5f;  // on the scaled gradient norm; the fp32 noise floor of that norm is ~3e-6 (profiles/r1_notes.md), below it iterations only chase rounding
   c->solver_step_tolerance = 1e-3f;
   c->solver_ls_tolerance = 0.3f;  // MuJoCo default 0.01; 0.01..0.3 give the same Newton iteration histogram and parity on B200 (tools/diag_lstol.py), 0.3 is 5 % faster

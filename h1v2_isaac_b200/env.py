@@ -277,6 +277,8 @@ def flatten_cfg(cfg) -> H1v2Config:
             # "multiply" combine with the ground material (V/velocity_env_cfg.py:40-51)
             c.friction_range[0], c.friction_range[1] = float(lo) * ground_mu, float(hi) * ground_mu
             c.friction = 0.5 * (c.friction_range[0] + c.friction_range[1])
+            if c.friction_range[0] < 0.3:  # stiff regime of the pyramidal regulariser (1/mu^2): give the fp32 Newton more iterations
+                c.solver_iterations = max(c.solver_iterations, 30)
         elif f == "randomize_rigid_body_mass":
             if p.get("operation", "add") != "add":
                 raise NotImplementedError(f"events.{n}: only operation='add' is supported")

@@ -266,6 +266,8 @@ def _randomised(cfg, mu_lo=0.3):
     c.push_vel_xy[0], c.push_vel_xy[1] = -0.5, 0.5
     c.mass_add_range[0], c.mass_add_range[1] = -5.0, 5.0
     c.friction_range[0], c.friction_range[1] = mu_lo, 1.25
+    if mu_lo < 0.3:
+        c.solver_iterations = 30  # what env.flatten_cfg selects for such a friction range
     return c
 
 
@@ -347,5 +349,5 @@ def test_low_friction_is_bounded(cfg):
     e = np.concatenate(errs)
     frac = float((e > 5e-3).mean())
     print(f"mu~0.1: {len(e)} env-steps, {100 * frac:.3f} % beyond 5e-3 rad/s, q99 {np.quantile(e, 0.99):.2e}")
-    assert frac < 5e-3 and np.quantile(e, 0.99) < 5e-3
+    assert frac < 1e-3 and np.quantile(e, 0.99) < 5e-3  # measured 2e-4 with the 30-iteration cap (1.8e-3 with 12)
     assert sim.log_host()[25] == 0
