@@ -46,24 +46,28 @@ namespace h1v2 {
 #ifndef U_EVJ
 #define U_EVJ 1
 #endif
-// shared-memory column of one thread: 6 joints x JSTRIDE floats, then MAXC contact points x PSTRIDE floats
-#define JSTRIDE 32
+// shared-memory column of one thread: 6 joints x JSTRIDE floats, then MAXC contact points x PSTRIDE floats.
+// 220 floats per thread = 28160 B per warp: 8 warps per SM ((28160 + 1024 reserved) * 8 = 228 KB exactly).  Measured on
+// B200: throughput still grows linearly with resident warps at 7 per SM (tools: H1V2_SMEM_PAD experiment, profiles/r1_notes.md),
+// so every float here is worth keeping out: the link mass comes from the parameter block, the ABA 1/D shares a slot
+// with the extra-diagonal / M-product scratch, and the active contact list holds 5 points.
+#define JSTRIDE 30
 #define F_W 0      // 3  joint axis (world)
 #define F_U 3      // 3  (joint position - O_s) x axis
-#define F_I 6      // 10 link inertia about O_s: m, m*c (3), xx yy zz xy xz yz
-#define F_X 16     // 6  scratch: RNE link force | ABA U = IA*S (n,l) | M-product link force
-#define F_DINV 22  // 1  ABA 1/(S'IA S + armature + diag)
-#define F_XQ 23    // 1  acceleration iterate
-#define F_R 24     // 1  rhs of the current solve -> ABA reduced rhs -> solution / search direction
-#define F_MA 25    // 1  (M x - f_smooth)
-#define F_G 26     // 1  J'f at the last evaluation
-#define F_DG 27    // 1  extra diagonal of the current solve | (M s) after the M-product
-#define F_FLC 28   // 1  friction-loss row offset  B*qd
-#define F_LIMC 29  // 1  limit row offset
-#define F_LIMD 30  // 1  limit row sign * D (0 = no limit row)
-#define F_FS 31    // 1  smooth force
-#define MAXC 7
-#define PSTRIDE 8  // r (3) | B*velocity (3) | K*imp*dist | 1/R   (owner link from the list position)
+#define F_I 6      // 9  link inertia about O_s: m*c (3) xx yy zz xy xz yz   (the mass itself is KLeg::mass)
+#define F_X 15     // 6  scratch: RNE link force | ABA U = IA*S (n,l) | M-product link force
+#define F_DG 21    // 1  extra diagonal of the current solve -> ABA 1/(S'IA S + armature + diag) -> (M s) after the M-product
+#define F_DINV F_DG
+#define F_XQ 22    // 1  acceleration iterate
+#define F_R 23     // 1  rhs of the current solve -> ABA reduced rhs -> solution / search direction
+#define F_MA 24    // 1  (M x - f_smooth)
+#define F_G 25     // 1  J'f at the last evaluation
+#define F_FLC 26   // 1  friction-loss row offset  B*qd
+#define F_LIMC 27  // 1  limit row offset
+#define F_LIMD 28  // 1  limit row sign * D (0 = no limit row)
+#define F_FS 29    // 1  smooth force
+#define MAXC 5     // 4 sole corners + 1: any further point means shin / torso / pelvis on the ground, i.e. the env terminates this step
+#define PSTRIDE 8  // r (3) | row residual e (3) | K*imp*dist | 1/R   (owner link from the list position)
 #define PT_BASE (6 * JSTRIDE)
 #define SMEM_FLOATS (PT_BASE + MAXC * PSTRIDE)
 
@@ -74,15 +78,15 @@ struct Smem {
   __device__ __forceinline__ V3 jv(int j, int f) const { return mk3(jf(j, f), jf(j, f + 1), jf(j, f + 2)); }
   __device__ __forceinline__ void sjv(int j, int f, V3 v) const { jf(j, f) = v.x; jf(j, f + 1) = v.y; jf(j, f + 2) = v.z; }
   __device__ __forceinline__ V3 pv(int p, int f) const { return mk3(pf(p, f), pf(p, f + 1), pf(p, f + 2)); }
-  __device__ __forceinline__ RI ji(int j) const {
+  __device__ __forceinline__ RI ji(int j, float m) const {
     RI I;
-    I.m = jf(j, F_I); I.mc = jv(j, F_I + 1);
-    I.xx = jf(j, F_I + 4); I.yy = jf(j, F_I + 5); I.zz = jf(j, F_I + 6); I.xy = jf(j, F_I + 7); I.xz = jf(j, F_I + 8); I.yz = jf(j, F_I + 9);
+    I.m = m; I.mc = jv(j, F_I);
+    I.xx = jf(j, F_I + 3); I.yy = jf(j, F_I + 4); I.zz = jf(j, F_I + 5); I.xy = jf(j, F_I + 6); I.xz = jf(j, F_I + 7); I.yz = jf(j, F_I + 8);
     return I;
   }
   __device__ __forceinline__ void sji(int j, const RI& I) const {
-    jf(j, F_I) = I.m; sjv(j, F_I + 1, I.mc);
-    jf(j, F_I + 4) = I.xx; jf(j, F_I + 5) = I.yy; jf(j, F_I + 6) = I.zz; jf(j, F_I + 7) = I.xy; jf(j, F_I + 8) = I.xz; jf(j, F_I + 9) = I.yz;
+    sjv(j, F_I, I.mc);
+    jf(j, F_I + 3) = I.xx; jf(j, F_I + 4) = I.yy; jf(j, F_I + 5) = I.zz; jf(j, F_I + 6) = I.xy; jf(j, F_I + 7) = I.xz; jf(j, F_I + 8) = I.yz;
   }
 };
 
@@ -578,7 +582,7 @@ UNROLL(U_EVJ)
       const float Dk = newton ? 1.f : 0.f;  // contact stiffness enters the Newton Hessian only
 UNROLL(U_SWEEP1)
       for (int j = 5; j >= 0; j--) {
-        k6_add_rigid(IA, sm.ji(j));
+        k6_add_rigid(IA, sm.ji(j, LG.mass[j]));
         if (j == 5 || j == 3) {  // contact stiffness of the foot / shin link, straight into the articulated inertia
           const int p1 = j == 5 ? n_foot : e_shin;
 #pragma unroll 1
@@ -658,7 +662,7 @@ UNROLL(U_SWEEP2)
       Sa_f = fma3(sm.jv(j, F_W), s, Sa_f); Sl_f = fma3(sm.jv(j, F_U), s, Sl_f);
       if (j == 3) { Sa_s = Sa_f; Sl_s = Sl_f; }
       V3 n, l;
-      ri_apply(sm.ji(j), Sa_f, Sl_f, n, l);
+      ri_apply(sm.ji(j, LG.mass[j]), Sa_f, Sl_f, n, l);
       sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
     }
     smax = fmaxf(smax, __shfl_xor_sync(FULL_MASK, smax, 1));
