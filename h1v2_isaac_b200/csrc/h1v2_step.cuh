@@ -11,7 +11,7 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 struct RootDerived {
   M3 R;
   V3 vb, wb, ww, g;
-  float heading;
+  float hx, hy;  // forward axis of the base projected on the ground, unnormalised: heading = atan2(hy, hx)
 };
 __device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const float (&rv)[3], const float (&rw)[3]) {
   RootDerived d;
@@ -20,7 +20,7 @@ __device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const 
   d.wb = mk3(rw[0], rw[1], rw[2]);
   d.ww = mulv(d.R, d.wb);
   d.g = mk3(-d.R.cx.z, -d.R.cy.z, -d.R.cz.z);  // R^T (0,0,-1)
-  d.heading = atan2f(d.R.cx.y, d.R.cx.x);
+  d.hx = d.R.cx.x; d.hy = d.R.cx.y;
   return d;
 }
 
@@ -80,7 +80,7 @@ __device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gi
   float roll = uni(u1[0], P.rp[3][0], P.rp[3][1]), pitch = uni(u1[1], P.rp[4][0], P.rp[4][1]);
   float yaw = uni(u0[2], P.rp[5][0], P.rp[5][1]);
   float sr, cr, sp, cp, sy, cy;
-  sincosf(0.5f * roll, &sr, &cr); sincosf(0.5f * pitch, &sp, &cp); sincosf(0.5f * yaw, &sy, &cy);
+  sincos_lim(0.5f * roll, sr, cr); sincos_lim(0.5f * pitch, sp, cp); sincos_lim(0.5f * yaw, sy, cy);
   rq[0] = cy * cr * cp + sy * sr * sp;
   rq[1] = cy * sr * cp - sy * cr * sp;
   rq[2] = cy * cr * sp + sy * sr * cp;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
   c.time_left -= P.step_dt;
   if (c.time_left <= 0.0f) resample_command(P, c, gid, step, 2);
   if (P.heading_cmd && (c.flags & FLAG_HEADING)) {
-    float err = wrap_to_pi(c.heading_target - rd.heading);
+    float err = wrap_to_pi(c.heading_target - atan2f(rd.hy, rd.hx));
     c.c[2] = fminf(fmaxf(P.k_heading * err, P.c_wz[0]), P.c_wz[1]);
   }
   if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
@@ -464,7 +464,8 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel);
       r[H1V2_REW_ACTION_RATE] = pair_sum(s_da);
       r[H1V2_REW_TERMINATION] = contact ? 1.f : 0.f;
-      const float ch = cosf(rd.heading), sh = sinf(rd.heading);
+      const float hn = rsqrtf(fmaxf(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));  // cos / sin of the heading without the angle itself
+      const float ch = rd.hx * hn, sh = rd.hy * hn;
       float ex = cmd.c[0] - (ch * rv[0] + sh * rv[1]), ey = cmd.c[1] - (-sh * rv[0] + ch * rv[1]);
       r[H1V2_REW_TRACK_LIN_XY_YAW] = expf(-(ex * ex + ey * ey) * P.inv_std2);
       float ez = cmd.c[2] - rd.ww.z;
