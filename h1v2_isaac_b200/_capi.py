@@ -12,7 +12,7 @@ NJ = 12
 NUM_REW = 20
 NUM_SLOT = 6
 OBS_TERM_DIM = 45
-MAX_HISTORY = 16
+MAX_HISTORY = 10
 LOG_DIM = 32
 
 REW_NAMES = [

@@ -24,20 +24,28 @@ __device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const 
   return d;
 }
 
-// world linear velocity of the ankle_roll_link origin of this lane's leg
-__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6]) {
+// world linear velocity of the ankle_roll_link origin of this lane's leg (body_lin_vel_w of the foot, feet_slide).
+// Rolled over the joints with q / qd staged in the lane's shared-memory column: call it while the column is free
+// (after the physics loop, before the history prefetch).
+__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6]) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const Smem sm{smem_raw + tid};
+#pragma unroll
+  for (int j = 0; j < 6; j++) { sm.jf(j, F_XQ) = q[j]; sm.jf(j, F_FLC) = qd[j]; }
   M3 R = R0;
   V3 x = mk3(0.f, 0.f, 0.f), om = om0, vo = v0;
-#define FV_JOINT(i, AX)                     \
-  {                                         \
-    x = x + mulv(R, ld3(LG.pos[i]));        \
-    V3 wi = axis_col<AX>(R);                \
-    om = fma3(wi, qd[i], om);               \
-    vo = fma3(cross(x, wi), qd[i], vo);     \
-    { float s_, c_; sincos_lim(q[i], s_, c_); rotate_sc<AX>(R, s_, c_); } \
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) {
+    const int ax = joint_axis(i);
+    const float qdi = sm.jf(i, F_FLC);
+    x = x + mulv(R, ld3(LG.pos[i]));
+    const V3 wi = axis_rt(R, ax);
+    om = fma3(wi, qdi, om);
+    vo = fma3(cross(x, wi), qdi, vo);
+    float s_, c_;
+    sincos_lim(sm.jf(i, F_XQ), s_, c_);
+    rotate_rt(R, ax, s_, c_);
   }
-  FV_JOINT(0, 2) FV_JOINT(1, 1) FV_JOINT(2, 0) FV_JOINT(3, 1) FV_JOINT(4, 1) FV_JOINT(5, 0)
-#undef FV_JOINT
   return vo + cross(om, x);
 }
 
@@ -391,6 +399,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
     }
   }
+  V3 fv = mk3(0.f, 0.f, 0.f);
+  if (DO_STEP) {
+    const M3 Rn = quat2mat(rq[0], rq[1], rq[2], rq[3]);
+    fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd);
+    __syncwarp();  // every lane is done with its column before the asynchronous copy lands in it
+  }
   hist_prefetch(P, S, tid, bid, 0);
   // ---- actuator line and command state ----
   {
@@ -442,7 +456,6 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 
     // ---- rewards on the pre-reset state ----
     const RootDerived rd = root_derived(rq, rv, rw);
-    const V3 fv = foot_velocity(P.leg[side], rd.R, rd.ww, mk3(rv[0], rv[1], rv[2]), q, qd);
     float r[H1V2_NUM_REW];
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;

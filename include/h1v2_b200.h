@@ -42,7 +42,7 @@ extern "C" {
 #define H1V2_NUM_REW 20      /* reward-term slots (union of the cfgs) */
 #define H1V2_NUM_SLOT 6      /* contact-sensor bodies: 0,1 feet L/R; 2,3 knee_link L/R; 4 torso_link; 5 pelvis */
 #define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
-#define H1V2_MAX_HISTORY 16
+#define H1V2_MAX_HISTORY 10 /* the reference tasks use 10 (Flat), 6 (Rsl) and 1 (deploy) */
 #define H1V2_LOG_DIM 32      /* see h1v2_get_log */
 
 /* reward term slots; weights[i]==0 means "term not in the cfg" (RewardManager skips zero weights) */
