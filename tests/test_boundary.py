@@ -95,3 +95,41 @@ def test_unmodified_train_py_reaches_the_backend(tmp_path):
     else:
         assert "H1v2ManagerBasedRLEnv" in out.stderr or "h1v2_isaac_b200/env.py" in out.stderr
         assert "no CUDA device visible" in out.stderr
+
+
+@pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
+def test_reference_variants_are_accepted_or_refused_by_name():
+    """Which of the reference's H1-2 12-dof ids the backend takes: Flat and Flat-Play flatten, also with the
+    H12_12DOF_IDEAL robot (IdealPD -> no delay line); CaT (constraint manager), Rsl (reward-weight curriculum) and Rough
+    (height scan, base_lin_vel) are refused with the name of the offending cfg entry, never approximated."""
+    code = r'''
+import gymnasium as gym
+import biped_tasks.tasks
+from isaaclab_tasks.utils import load_cfg_from_registry
+from biped_assets.robots.h12 import H12_12DOF_IDEAL
+from h1v2_isaac_b200.env import flatten_cfg
+out = {}
+for tid in ("Isaac-Velocity-Flat-H12_12dof-v0", "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-v0",
+            "Isaac-Velocity-Rsl-H12_12dof-v0", "Isaac-Velocity-Rough-H12_12dof-v0"):
+    cfg = load_cfg_from_registry(tid, "env_cfg_entry_point")
+    try:
+        c = flatten_cfg(cfg); out[tid] = "ok corruption=%d" % c.enable_corruption
+    except NotImplementedError as e:
+        out[tid] = "refused: " + str(e)[:40]
+cfg = load_cfg_from_registry("Isaac-Velocity-Flat-H12_12dof-v0", "env_cfg_entry_point")
+cfg.scene.robot = H12_12DOF_IDEAL.replace(prim_path="{ENV_REGEX_NS}/Robot")
+c = flatten_cfg(cfg); out["ideal"] = "ok delays %d %d" % (c.min_delay, c.max_delay)
+import json; print("RESULT" + json.dumps(out))
+'''
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "h1v2_isaac_b200", "shims"), ROOT, os.path.join(REF, "packages", "biped_tasks"),
+                                         os.path.join(REF, "packages", "biped_assets")])
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.split("RESULT")[1])
+    assert res["Isaac-Velocity-Flat-H12_12dof-v0"] == "ok corruption=1"
+    assert res["Isaac-Velocity-Flat-H12_12dof-Play-v0"] == "ok corruption=0"
+    assert res["ideal"] == "ok delays 0 0"
+    assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"].startswith("refused: constraints")
+    assert res["Isaac-Velocity-Rsl-H12_12dof-v0"].startswith("refused: curriculum")
+    assert res["Isaac-Velocity-Rough-H12_12dof-v0"].startswith("refused: ")  # terrain curriculum, height scan, base_lin_vel

@@ -94,14 +94,33 @@ def test_tail_parity_on_identical_states(cfg):
     """(a)+(b): the oracle's physics loop is replaced by the kernel's own post-physics values, so everything after the
     physics -- contact-sensor logic, terminations, 20 reward terms, reset, command resampling, noisy observation with
     history -- is compared on identical inputs: masks bit-exact, values to 1e-5."""
-    n = 4096
+    _tail_parity(cfg, 4096, 60, 100)
+
+
+def test_tail_parity_ideal_pd_and_union_rewards(cfg):
+    """Same check on the H12_12DOF_IDEAL actuator variant (IdealPD: no delay line, A/robots/h12.py:117-206) with every
+    one of the 20 reward slots switched on (the union of the H1-2 cfgs), history 6 and the Rsl observation
+    scales (C12/rsl_env_cfg.py) -- the configuration space flatten_cfg can produce beyond the Flat id's defaults."""
+    c = cfg.copy()
+    c.min_delay = c.max_delay = 0
+    for t in range(20):
+        if c.rew_weight[t] == 0.0:
+            c.rew_weight[t] = -0.01 * (t + 1)
+    c.history_length = 6
+    c.scale_ang_vel, c.scale_joint_vel, c.action_scale = 0.25, 0.05, 0.25
+    for i in range(12):
+        c.joint_perm[i] = i
+    _tail_parity(c, 2048, 30, 30, min_term=0)  # action scale 0.25: nobody falls within 30 steps
+
+
+def _tail_parity(cfg, n, steps, min_events, min_term=None):
     torch, sim, orc = _mk(cfg, n, 21)
     sim.observe(); orc.observe()
     ep = np.random.default_rng(1).integers(0, 1000, n)  # rsl_rl's init_at_random_ep_len: exercises time-outs
     sim.episode_length_buf.copy_(torch.from_numpy(ep).cuda()); orc.episode_length = ep
     rng = np.random.default_rng(2)
     n_term = n_trunc = n_resample = 0
-    for step in range(60):
+    for step in range(steps):
         a = (rng.normal(size=(n, 12)) * (0.3 if step % 3 else 1.0)).astype(np.float32)
         og, rg, tg, ug = sim.step(torch.from_numpy(a).cuda())
         g = _np(sim.get_state(SYNC + POST + ["reward_terms"]))
@@ -130,7 +149,7 @@ def test_tail_parity_on_identical_states(cfg):
             np.testing.assert_allclose(lg[23:25], lo[23:25], rtol=2e-4, atol=1e-6)
         _resync(sim, orc, g)
     print(f"terminated {n_term}, truncated {n_trunc}, command resamples {n_resample}")
-    assert n_term > 100 and n_trunc > 100 and n_resample > 100
+    assert n_term >= (min_events if min_term is None else min_term) and n_trunc > min_events and n_resample > min_events
 
 
 def test_bounded_divergence_over_1000_steps(cfg):
