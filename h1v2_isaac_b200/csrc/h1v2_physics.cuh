@@ -226,12 +226,12 @@ __device__ __forceinline__ void point_ls(V3 ea, V3 us, float kap, float D, float
   d1 = fmaf(D, s1, d1);
   d2 = fmaf(D, s2, d2);
 }
-// friction-loss row: force and activity (= D inside the quadratic zone) at residual jar
-__device__ __forceinline__ float floss_force(float jar, float D, float lim, float fl, float& act) {
-  if (jar <= -lim) { act = 0.f; return fl; }
-  if (jar >= lim) { act = 0.f; return -fl; }
-  act = D;
-  return -D * jar;
+// friction-loss row: force and activity (= D inside the quadratic zone) at residual jar.  The zone boundary R*fl is where
+// the linear force -D*jar reaches +-fl (D = 1/R), so the row is a clamp: no branches and no third constant.
+__device__ __forceinline__ float floss_force(float jar, float D, float fl, float& act) {
+  const float f = -D * jar;
+  act = fabsf(f) < fl ? D : 0.f;
+  return fminf(fmaxf(f, -fl), fl);
 }
 
 struct SubOut {
@@ -488,7 +488,6 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   for (int i = 0; i < 6; i++) { xr[i] = 0.f; Mar[i] = -fs_root[i]; jr[i] = 0.f; rr[i] = use_warm ? wr[i] : 0.f; }
   const float* arm = P.armature + 6 + j0;
   const float* flD = P.floss_D + 6 + j0;
-  const float* flL = P.floss_lim + 6 + j0;
   const float* flF = P.floss + 6 + j0;
   const V3 c3[3] = {R0.cx, R0.cy, R0.cz};
 
@@ -511,7 +510,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const int dk = 3 * side + k;
-        const float f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], dg_own[k]);
+        const float f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss[dk], dg_own[k]);
         if (side == 0) gr_own[k] = f; else gr_own[3 + k] = f;
       }
       V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
@@ -544,7 +543,7 @@ UNROLL(U_EVJ)
       for (int j = 0; j < 6; j++) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
         const float x = sm.jf(j, F_XQ);
         float act;
-        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
+        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flF[j], act);
         const float lD = sm.jf(j, F_LIMD);
         const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
         const float jar = fmaf(sig, x, sm.jf(j, F_LIMC));
@@ -709,7 +708,7 @@ UNROLL(U_LSJ)
           const float s = sm.jf(j, F_R);
           const float xa = fmaf(alpha, s, sm.jf(j, F_XQ));
           float act;
-          const float f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flL[j], flF[j], act);
+          const float f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flF[j], act);
           d1 = fmaf(-f, s, d1); d2 = fmaf(act * s, s, d2);
           const float lD = sm.jf(j, F_LIMD);
           if (lD != 0.f) {
@@ -723,7 +722,7 @@ UNROLL(U_LSJ)
           const int dk = 3 * side + k;
           const float sk = side == 0 ? rr[k] : rr[3 + k], xk = side == 0 ? xr[k] : xr[3 + k];
           float act;
-          const float f = floss_force(fmaf(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss_lim[dk], P.floss[dk], act);
+          const float f = floss_force(fmaf(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss[dk], act);
           d1 = fmaf(-f, sk, d1); d2 = fmaf(act * sk, sk, d2);
         }
 #pragma unroll 1
