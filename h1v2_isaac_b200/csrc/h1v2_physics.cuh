@@ -218,11 +218,10 @@ __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const float (&W)[5]) {
 __device__ __forceinline__ void point_ls(V3 ea, V3 us, float kap, float D, float mu, float& d1, float& d2) {
   const Edges E = point_edges(ea, kap, mu);
   const float v0 = fmaf(mu, us.y, us.z), v1 = fmaf(-mu, us.y, us.z), v2 = fmaf(-mu, us.x, us.z), v3 = fmaf(mu, us.x, us.z);
-  float s1 = 0.f, s2 = 0.f;
-  if (E.j0 < 0.f) { s1 = fmaf(E.j0, v0, s1); s2 = fmaf(v0, v0, s2); }
-  if (E.j1 < 0.f) { s1 = fmaf(E.j1, v1, s1); s2 = fmaf(v1, v1, s2); }
-  if (E.j2 < 0.f) { s1 = fmaf(E.j2, v2, s1); s2 = fmaf(v2, v2, s2); }
-  if (E.j3 < 0.f) { s1 = fmaf(E.j3, v3, s1); s2 = fmaf(v3, v3, s2); }
+  // branch-free: an inactive edge contributes min(j,0) = 0 to the first sum and a zeroed velocity to the second
+  const float w0 = E.j0 < 0.f ? v0 : 0.f, w1 = E.j1 < 0.f ? v1 : 0.f, w2 = E.j2 < 0.f ? v2 : 0.f, w3 = E.j3 < 0.f ? v3 : 0.f;
+  const float s1 = fmaf(E.j0, w0, fmaf(E.j1, w1, fmaf(E.j2, w2, E.j3 * w3)));
+  const float s2 = fmaf(w0, w0, fmaf(w1, w1, fmaf(w2, w2, w3 * w3)));
   d1 = fmaf(D, s1, d1);
   d2 = fmaf(D, s2, d2);
 }
@@ -710,12 +709,11 @@ UNROLL(U_LSJ)
           float act;
           const float f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flF[j], act);
           d1 = fmaf(-f, s, d1); d2 = fmaf(act * s, s, d2);
-          const float lD = sm.jf(j, F_LIMD);
-          if (lD != 0.f) {
-            const float sig = lD > 0.f ? 1.f : -1.f;
-            const float jar = fmaf(sig, xa, sm.jf(j, F_LIMC));
-            if (jar < 0.f) { d1 = fmaf(fabsf(lD) * jar, sig * s, d1); d2 = fmaf(fabsf(lD) * s, s, d2); }
-          }
+          const float lD = sm.jf(j, F_LIMD);  // limit row, branch-free: lD = 0 (no row) or an inactive row weigh nothing
+          const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
+          const float jar = fmaf(sig, xa, sm.jf(j, F_LIMC));
+          const float lw = jar < 0.f ? fabsf(lD) : 0.f;
+          d1 = fmaf(lw * jar, sig * s, d1); d2 = fmaf(lw * s, s, d2);
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
