@@ -322,7 +322,7 @@ __device__ __forceinline__ float impedance_call(const float* si, float pos) {
 // "evaluate" and "solve" halves of an iteration that can be re-derived from the contact list (the contact
 // stiffness is accumulated straight into the articulated inertia during the tip->root sweep).
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, const unsigned pm, float (&rp)[3],
+__device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, float (&rp)[3],
                                      float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
                                      const float (&tau)[6], const float mu, const float mass_add, float (&wl)[6], float (&wr)[6],
                                      const bool use_warm, SubOut& out) {

@@ -285,14 +285,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
   // lane pair p of warp w owns env w*epw + p for p < epw; the remaining lanes shadow the warp's first env (their work is
   // bit-identical to it, so they never lengthen the warp's Newton loop) and store nothing
-  const int gtid = bid * H1V2_BLOCK + tid;
   const int side = tid & 1;
   const int slot = (int)(tid >> 1);
   const int warp_env0 = (int)bid * P.epw;
   const bool valid = slot < P.epw && warp_env0 + slot < P.n;
   const int env = valid ? warp_env0 + slot : min(warp_env0, P.n - 1);
   const int lidx = 2 * env + side;
-  const unsigned pm = 3u << (tid & 30);
   const int N = P.n, N2 = 2 * P.n;
   const int64_t gid = P.env_id_offset + env;
   const unsigned long long step = S.counters[0] + (DO_STEP ? 1ull : 0ull);
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           for (int i = 0; i < 6; i++) dg[36 + 6 * side + i] = tau[i];
         }
       }
-      substep(P, tid, side, pm, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
+      substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters;
       if (valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);

@@ -153,7 +153,9 @@ typedef struct H1v2Config {
                                           to it after every physics step, as PhysX does; <= 0 disables */
   float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
                                           non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
-  int32_t reserved[8];
+  int32_t reserved[8];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
+                                          [1] > 0: line-search evaluations per Newton iteration (default 6);
+                                          [2] in {1,2,4,8,16}: envs per warp (default: chosen from n_envs); rest 0 */
 } H1v2Config;
 
 /* Natural-layout state exchange (row-major, env-major).  NULL members are skipped.
