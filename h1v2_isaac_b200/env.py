@@ -251,6 +251,9 @@ def flatten_cfg(cfg) -> H1v2Config:
 
     # ---- commands (V/velocity_env_cfg.py:90-104; flat_env_cfg.py:46-48) ----
     cmd = cfg.commands.base_velocity
+    ctype = getattr(_get(cmd, "class_type"), "__name__", "UniformVelocityCommand")
+    if ctype != "UniformVelocityCommand":  # e.g. utils/mdp/commands.py:19 UniformVelocityCommandWithDeadzone: cross-env balancing
+        raise NotImplementedError(f"commands.base_velocity: command class {ctype} is not implemented in the fused kernel")
     r = cmd.ranges
     for dst, src in ((c.cmd_lin_x, r.lin_vel_x), (c.cmd_lin_y, r.lin_vel_y), (c.cmd_ang_z, r.ang_vel_z), (c.cmd_resample_time, cmd.resampling_time_range)):
         dst[0], dst[1] = float(src[0]), float(src[1])
