@@ -104,6 +104,33 @@ def cpu_baseline(cfg, seed: int, target_s: float = 12.0, steps: int | None = Non
             "ms_per_step": dt / k * 1e3, "n_envs": n, "steps": k}
 
 
+def cpu_baseline_sim2sim(cfg, seed: int, target_s: float = 4.0):
+    """BASELINE.md B0 -- the reference's literal CPU configuration (scripts/deploy/sim2sim.py:46-54, deploy/config.yaml:7-8):
+    ONE env on ONE core, MuJoCo-semantics step at 1 ms x 20 substeps per 50 Hz control step, PD in the loop, random-init
+    450->512->256->128->12 ELU policy on torch-CPU.  Engine: the float64 C oracle (mujoco is not installable here)."""
+    import numpy as np
+    import torch
+    from oracle.oracle import Oracle
+
+    c = cfg.copy()
+    c.sim_dt, c.decimation = 0.001, 20
+    orc = Oracle(c, 1, seed=seed, threads=1)
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    pi = torch.nn.Sequential(torch.nn.Linear(450, 512), torch.nn.ELU(), torch.nn.Linear(512, 256), torch.nn.ELU(),
+                             torch.nn.Linear(256, 128), torch.nn.ELU(), torch.nn.Linear(128, 12))
+    obs = orc.observe()
+    k, t0 = 0, time.perf_counter()
+    with torch.inference_mode():
+        while time.perf_counter() - t0 < target_s:
+            a = pi(torch.from_numpy(obs)).numpy().astype(np.float32)
+            obs, _, _, _ = orc.step(a)
+            k += 1
+    dt = time.perf_counter() - t0
+    return {"value": k / dt, "unit": METRIC, "cores": 1, "kind": "port", "physics_steps_per_s": 20 * k / dt,
+            "sample": f"1 env x {k} control steps (20 x 1 ms MuJoCo-semantics substeps + PD + torch-CPU MLP policy), float64 C oracle, 1 thread"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -258,6 +285,7 @@ def run_ours(args):
         try:
             cb = cpu_baseline(cfg, args.seed)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline_sim2sim_1core"] = cpu_baseline_sim2sim(cfg, args.seed)
         except Exception as e:  # the checker library missing must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
     print(json.dumps(line), flush=True)
