@@ -405,6 +405,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM + 32);  // + cumulative histogram of Newton iterations per solve
   rc |= dalloc(h, &S.log, (size_t)H1V2_LOG_DIM);
   rc |= dalloc(h, &S.counters, (size_t)2);
+  rc |= dalloc(h, &S.done, (size_t)1);
   rc |= dalloc(h, &h->own_ep_len, N);
   int* lut_d = nullptr;
   rc |= dalloc(h, &lut_d, (size_t)h->P.obs_dim);
@@ -483,8 +484,7 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
   else  // the observe-only launch stages the history rings in the same shared-memory window
     step_kernel<false><<<blocks, threads, smem, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
-  finalize_kernel<<<1, 32, 0, st>>>(h->S, do_step ? 1 : 0);
-  h->launches += 2;
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }

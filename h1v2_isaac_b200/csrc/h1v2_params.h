@@ -92,6 +92,7 @@ struct KState {
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector
   unsigned long long* counters;  // [0] global step counter, [1] history head
+  unsigned* done;                // blocks of the current launch that have finished (the last one publishes the log, advances the counters)
 };
 #define H1V2_DIAG_DIM 144
 // diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | reward_terms 60..79

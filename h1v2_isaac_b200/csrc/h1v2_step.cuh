@@ -274,6 +274,30 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   }
 }
 
+// publishes the log vector, clears the accumulators, advances the step counter and the history head.
+// Run by the 32 lanes of the LAST block of a step launch to finish (ticket counter S.done): one launch per control step.
+__device__ __forceinline__ void finalize_step(const KState& S, bool do_step, unsigned t) {
+  if (do_step) {
+    const float cnt = __ldcg(S.acc + H1V2_LOG_COUNT);
+    const float a = __ldcg(S.acc + t);  // t < 32 == H1V2_LOG_DIM
+    if (t == H1V2_LOG_COUNT) S.log[t] = a;
+    else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
+    else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
+    else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS) S.log[t] = a;
+    else if (cnt > 0.f) {
+      const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
+      S.log[t] = mean ? a / cnt : a;
+    }
+    __syncwarp();
+    S.acc[t] = 0.f;
+  }
+  if (t == 0) {
+    if (do_step) S.counters[0] += 1ull;
+    S.counters[1] += 1ull;
+    *S.done = 0u;
+  }
+}
+
 template <bool DO_STEP>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
@@ -649,30 +673,14 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     S.warm[N2 + lidx] = make_float4(wl[4], wl[5], wr[0], wr[1]);
     S.warm[2 * N2 + lidx] = make_float4(wr[2], wr[3], wr[4], wr[5]);
   }
-}
-
-// publishes the log vector, clears the accumulators, advances the step counter and the history head
-__global__ void finalize_kernel(const KState S, int do_step) {
-  const int t = threadIdx.x;
-  if (do_step) {
-    const float cnt = S.acc[H1V2_LOG_COUNT];
-    if (t < H1V2_LOG_DIM) {
-      float a = S.acc[t];
-      if (t == H1V2_LOG_COUNT) S.log[t] = a;
-      else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
-      else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
-      else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS) S.log[t] = a;
-      else if (cnt > 0.f) {
-        const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
-        S.log[t] = mean ? a / cnt : a;
-      }
-    }
-    __syncthreads();
-    if (t < H1V2_LOG_DIM) S.acc[t] = 0.f;
-  }
-  if (t == 0) {
-    if (do_step) S.counters[0] += 1ull;
-    S.counters[1] += 1ull;
+  // ---- the last block to get here finalizes the step ----
+  __threadfence();
+  unsigned ticket = 0;
+  if (tid == 0) ticket = atomicAdd(S.done, 1u);
+  ticket = __shfl_sync(FULL_MASK, ticket, 0);
+  if (ticket == gridDim.x - 1) {
+    __threadfence();
+    finalize_step(S, DO_STEP, tid);
   }
 }
 
