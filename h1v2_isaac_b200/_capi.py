@@ -22,7 +22,7 @@ REW_NAMES = [
     "track_ang_vel_z_exp_base", "feet_air_time_l2", "joint_vel_l2", "base_height_l2", "contact_forces",
 ]
 LOG_COUNT, LOG_REW0, LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW = 0, 1, 21, 22, 23, 24
-LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS, LOG_SUM_ITERS = 25, 26, 27, 28
+LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS, LOG_SUM_ITERS, LOG_CONTACT_OVERFLOW = 25, 26, 27, 28, 29
 
 f32, i32, u32, i64 = C.c_float, C.c_int32, C.c_uint32, C.c_int64
 

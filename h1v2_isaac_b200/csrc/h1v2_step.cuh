@@ -283,7 +283,7 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, uns
     if (t == H1V2_LOG_COUNT) S.log[t] = a;
     else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
     else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
-    else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS) S.log[t] = a;
+    else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS || t == H1V2_LOG_CONTACT_OVERFLOW) S.log[t] = a;
     else if (cnt > 0.f) {
       const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
       S.log[t] = mean ? a / cnt : a;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
   float s_tau = 0.f, s_acc = 0.f;
   SubOut so;
-  int max_it = 0, ncap = 0, sum_it = 0;
+  int max_it = 0, ncap = 0, sum_it = 0, novf = 0;
 
   if (DO_STEP) {
     // ---- physics loop: DelayedPD actuator (A/robots/h12.py:58-113) + substep + ContactSensor at sim dt ----
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
       substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
-      max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters;
+      max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters; novf += so.overflow;
       if (valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);
       s_acc = 0.f;
 #pragma unroll
@@ -595,10 +595,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       int wm = __reduce_max_sync(0xffffffffu, valid ? max_it : 0);
       int wc = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? ncap : 0);
       int ws = __reduce_add_sync(0xffffffffu, (valid && side == 0) ? sum_it : 0);
+      int wo = __reduce_add_sync(0xffffffffu, valid ? novf : 0);  // per leg: each lane owns its own contact list
       if ((tid & 31) == 0) {
         atomicMax((int*)(S.acc + H1V2_LOG_MAX_ITERS), wm);
         if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (float)wc);
         atomicAdd(S.acc + H1V2_LOG_SUM_ITERS, (float)ws);
+        if (wo) atomicAdd(S.acc + H1V2_LOG_CONTACT_OVERFLOW, (float)wo);
       }
     }
     // ---- reset (T/utils/cat/cat_env.py:195-248): log, then new state ----

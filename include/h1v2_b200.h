@@ -78,6 +78,8 @@ enum {
  *   [26]                max Newton iterations used by any env in the last step
  *   [27]                number of (env,substep) solves that hit the iteration cap in the last step
  *   [28]                total Newton iterations over all (env,substep) solves of the last step
+ *   [29]                (leg,substep) pairs of the last step whose contact list overflowed (points beyond 5 are dropped;
+ *                       only reachable with shin / torso / pelvis on the ground, i.e. in the step that terminates the env)
  */
 #define H1V2_LOG_COUNT 0
 #define H1V2_LOG_REW0 1
@@ -89,6 +91,7 @@ enum {
 #define H1V2_LOG_MAX_ITERS 26
 #define H1V2_LOG_CAP_HITS 27
 #define H1V2_LOG_SUM_ITERS 28
+#define H1V2_LOG_CONTACT_OVERFLOW 29 /* (leg,substep) pairs of the last step with more penetrating points than the 5-slot list holds */
 
 typedef struct H1v2Config {
   /* ---- timing (velocity_env_cfg.py:302-305) ---- */

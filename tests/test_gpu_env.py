@@ -106,3 +106,21 @@ def test_envs_per_warp_mapping_is_bit_identical(cfg):
             assert torch.equal(st[0][k], other[k]), k
     for s in sims:
         s.close()
+
+
+def test_contact_list_overflow_is_reported(cfg):
+    """Robots pushed into the ground put more than 5 points of a leg in contact: the kernel keeps the first 5 and
+    reports the event in log[29] instead of hiding it."""
+    import torch
+    from h1v2_isaac_b200._capi import LOG_CONTACT_OVERFLOW
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 64
+    sim = H1v2Sim(n, cfg, device="cuda:0", seed=2)
+    sim.observe()
+    st = sim.get_state(["root_pos", "root_quat", "joint_pos"])
+    st["root_pos"][:, 2] = 0.35                      # pelvis far too low for straight legs:
+    st["joint_pos"][:] = 0.0                          # 4 sole corners + 2 shin capsule ends of each leg are below the plane
+    sim.set_state(st)
+    sim.step(torch.zeros((n, 12), device="cuda"))
+    assert sim.log_host()[LOG_CONTACT_OVERFLOW] >= 2 * n  # both legs of every env, at least in the first substep
+    sim.close()
