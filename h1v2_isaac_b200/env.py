@@ -380,6 +380,7 @@ class H1v2ManagerBasedRLEnv:
         self.cfg_is_finite_horizon = bool(_get(cfg, "is_finite_horizon", False))
         self.common_step_counter = 0
         self.extras: dict = {}
+        self._log_keys = None
         self._last_action = torch.zeros((n, NJ), device=self.device)
         self._prev_action = torch.zeros((n, NJ), device=self.device)
         self.action_manager = _ActionManagerView(self)
@@ -446,14 +447,16 @@ class H1v2ManagerBasedRLEnv:
 
     def _log_dict(self) -> dict:
         """extras["log"] (T/utils/cat/cat_env.py:217-245): 0-d device tensors, no host sync.  Values are those of the
-        most recent step in which any env reset (upstream only writes the keys on such steps)."""
-        lg = self.sim.log_buf
-        d = {f"Episode_Reward/{n}": lg[LOG_REW0 + s] for n, s in zip(self._rew_names, self._rew_slots)}
-        d["Episode_Termination/time_out"] = lg[LOG_TERM_TIMEOUT]
-        d["Episode_Termination/base_contact"] = lg[LOG_TERM_CONTACT]
-        d["Metrics/base_velocity/error_vel_xy"] = lg[LOG_ERR_XY]
-        d["Metrics/base_velocity/error_vel_yaw"] = lg[LOG_ERR_YAW]
-        return d
+        most recent step in which any env reset (upstream only writes the keys on such steps).  One gather per step: the
+        entries are a snapshot, they do not change when the kernel updates its log vector later."""
+        if self._log_keys is None:
+            import torch
+            self._log_keys = [f"Episode_Reward/{n}" for n in self._rew_names] + [
+                "Episode_Termination/time_out", "Episode_Termination/base_contact",
+                "Metrics/base_velocity/error_vel_xy", "Metrics/base_velocity/error_vel_yaw"]
+            idx = [LOG_REW0 + s for s in self._rew_slots] + [LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW]
+            self._log_index = torch.tensor(idx, dtype=torch.long, device=self.device)
+        return dict(zip(self._log_keys, self.sim.log_buf[self._log_index].unbind(0)))
 
     def render(self, recompute: bool = False):
         return None
