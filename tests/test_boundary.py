@@ -133,3 +133,36 @@ import json; print("RESULT" + json.dumps(out))
     assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"].startswith("refused: constraints")
     assert res["Isaac-Velocity-Rsl-H12_12dof-v0"].startswith("refused: curriculum")
     assert res["Isaac-Velocity-Rough-H12_12dof-v0"].startswith("refused: ")  # terrain curriculum, height scan, base_lin_vel
+
+
+@pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
+def test_reference_deploy_exporter_on_shim_cfg_matches_shipped_yaml():
+    """Train -> deploy wire format: the reference's own get_deploy_config (utils/mdp/config_exporter.py:27-58)
+    runs unmodified on a cfg tree built from the shim classes and reproduces the env.yaml the reference ships for its deployed
+    policy (scripts/deploy/policies/demo_rsl/env.yaml): control rate, history, action scale, observation list with scales,
+    per-joint kp / kd / default pose."""
+    code = r'''
+import json, yaml
+import gymnasium as gym
+import biped_tasks.tasks
+from isaaclab_tasks.utils import load_cfg_from_registry
+from biped_tasks.utils.mdp.config_exporter import get_deploy_config
+d = get_deploy_config(load_cfg_from_registry("Isaac-Velocity-CaT-Flat-H12_12dof-v0", "env_cfg_entry_point"))
+y = yaml.load(open("/root/reference/scripts/deploy/policies/demo_rsl/env.yaml"), Loader=yaml.UnsafeLoader)
+print("RESULT" + json.dumps({"mine": d, "shipped": y}))
+'''
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "h1v2_isaac_b200", "shims"), ROOT, os.path.join(REF, "packages", "biped_tasks"),
+                                         os.path.join(REF, "packages", "biped_assets")])
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.split("RESULT")[1])
+    mine, shipped = r["mine"], r["shipped"]
+    for k in ("control_dt", "history_length", "history_step", "action_scale", "command_ranges"):
+        assert mine[k] == shipped[k], k
+    assert [(o["name"], o.get("scale") or 1) for o in mine["observations"]] == [(o["name"], o.get("scale") or 1) for o in shipped["observations"]]
+    ship_j = {j["name"]: j for j in shipped["joints"]}
+    assert len(mine["joints"]) == 12
+    for j in mine["joints"]:
+        s = ship_j[j["name"]]
+        assert (j["kp"], j["kd"], j["default_joint_pos"]) == (s["kp"], s["kd"], s["default_joint_pos"]), j["name"]
