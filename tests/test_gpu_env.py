@@ -106,6 +106,16 @@ def test_envs_per_warp_mapping_is_bit_identical(cfg):
             assert torch.equal(st[0][k], other[k]), k
     for s in sims:
         s.close()
+    # tiny batches take the same per-env path: a 3-env handle reproduces envs 0..2 of the 200-env one
+    big, tiny = H1v2Sim(n, cfg, device="cuda:0", seed=9), H1v2Sim(3, cfg, device="cuda:0", seed=9)
+    assert torch.equal(big.observe()[:3], tiny.observe())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(6):
+        a = torch.randn((n, 12), device="cuda", generator=g)
+        ob, rb, tb, ub = big.step(a)
+        ot, rt, tt, ut = tiny.step(a[:3].contiguous())
+        assert torch.equal(ob[:3], ot) and torch.equal(rb[:3], rt) and torch.equal(tb[:3], tt) and torch.equal(ub[:3], ut)
+    big.close(); tiny.close()
 
 
 def test_contact_list_overflow_is_reported(cfg):
