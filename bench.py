@@ -165,7 +165,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT at communicator creation when NCCL_DEBUG is set on the box; the contract
+        # is ONE JSON line on stdout, so the banner is sent to stderr (fd-level: it comes from the C library).
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n = args.envs
     cfg = default_config()
     cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
