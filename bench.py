@@ -287,6 +287,12 @@ def run_ours(args):
                           "flops_per_env_step": flops_per_env_step,
                           "achieved": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12) if flops_per_env_step else None,
                           "frac": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None},
+        "roofline_issue": (lambda wi, clk: {"bound": "warp-instruction issue", "unit": "G warp-instr/s", "peak": 148 * 4 * clk * 1e-3,
+                                             "achieved": wi * n / (ms_per_step * 1e-3) / 1e9, "frac": wi * n / (ms_per_step * 1e-3) / 1e9 / (148 * 4 * clk * 1e-3),
+                                             "warp_instructions_per_env_step": wi,
+                                             "note": "instruction count per env-step from the ncu capture at 32768 envs (profiles/roofline.json); peak = 148 SMs x 4 schedulers x SM clock"}
+                           )(rf.get("warp_instructions_per_env_step", {}).get("32768"), (clocks or {}).get("sm_mhz") or 1965.0)
+                          if rf.get("warp_instructions_per_env_step", {}).get("32768") else None,
         "at_32768_envs_per_gpu": (dict(big, roofline_hbm_frac=ALGO_BYTES_PER_ENV_STEP * 32768 / (big["ms_per_step"] * 1e-3) / 1e9 / hbm_peak,
                                        roofline_fp32_frac=(flops_per_env_step * 32768 / (big["ms_per_step"] * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None)
                                   if big else None),
