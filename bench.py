@@ -156,6 +156,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from h1v2_isaac_b200 import _capi
     from h1v2_isaac_b200._capi import default_config, load_library
     from h1v2_isaac_b200.backend import H1v2Sim
 
@@ -296,8 +297,8 @@ def run_ours(args):
         "at_32768_envs_per_gpu": (dict(big, roofline_hbm_frac=ALGO_BYTES_PER_ENV_STEP * 32768 / (big["ms_per_step"] * 1e-3) / 1e9 / hbm_peak,
                                        roofline_fp32_frac=(flops_per_env_step * 32768 / (big["ms_per_step"] * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None)
                                   if big else None),
-        "solver": {"mean_newton_iters_per_substep": float(logv[28]) / (4.0 * n), "max_iters_last_step": float(logv[26]), "cap_hits_last_step": float(logv[27]),
-                   "nan_resets": float(logv[25])},
+        "solver": {"mean_newton_iters_per_substep": float(logv[_capi.LOG_SUM_ITERS]) / (4.0 * n), "max_iters_last_step": float(logv[_capi.LOG_MAX_ITERS]),
+                   "cap_hits_last_step": float(logv[_capi.LOG_CAP_HITS]), "nan_resets": float(logv[_capi.LOG_NAN_RESETS])},
     }
     if not args.no_cpu_baseline and world == 1:
         try:

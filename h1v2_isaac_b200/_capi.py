@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 NJ = 12
-NUM_REW = 20
+NUM_REW = 22
 NUM_SLOT = 6
 OBS_TERM_DIM = 45
 MAX_HISTORY = 10
@@ -20,9 +20,10 @@ REW_NAMES = [
     "dof_pos_limits", "joint_deviation_hip", "ang_vel_xy_l2", "dof_torques_l2", "dof_acc_l2", "action_rate_l2",
     "flat_orientation_l2", "lin_vel_z_l2", "undesired_contacts", "track_lin_vel_xy_exp_base",
     "track_ang_vel_z_exp_base", "feet_air_time_l2", "joint_vel_l2", "base_height_l2", "contact_forces",
+    "dof_pos_limits_b", "joint_deviation_b",
 ]
-LOG_COUNT, LOG_REW0, LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW = 0, 1, 21, 22, 23, 24
-LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS, LOG_SUM_ITERS, LOG_CONTACT_OVERFLOW = 25, 26, 27, 28, 29
+LOG_COUNT, LOG_REW0, LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW = 0, 1, 23, 24, 25, 26
+LOG_NAN_RESETS, LOG_MAX_ITERS, LOG_CAP_HITS, LOG_SUM_ITERS, LOG_CONTACT_OVERFLOW = 27, 28, 29, 30, 31
 
 f32, i32, u32, i64 = C.c_float, C.c_int32, C.c_uint32, C.c_int64
 
@@ -54,7 +55,10 @@ class H1v2Config(C.Structure):
         ("reset_joint_pos_scale", f32 * 2), ("reset_joint_vel_scale", f32 * 2), ("init_root_height", f32),
         ("push_enable", i32), ("push_interval_s", f32 * 2), ("push_vel_xy", f32 * 2),
         ("mass_add_range", f32 * 2), ("friction_range", f32 * 2),
-        ("env_id_offset", i64), ("env_spacing", f32), ("joint_vel_limit", f32), ("runaway_vel", f32), ("reserved", i32 * 8),
+        ("env_id_offset", i64), ("env_spacing", f32), ("joint_vel_limit", f32),
+        ("mask_pos_limits_b", u32), ("mask_joint_dev_b", u32), ("mask_contact_forces_slots", u32), ("contact_forces_threshold", f32),
+        ("command_class", i32), ("velocity_deadzone", f32), ("ang_vel_flip_prob", f32),
+        ("runaway_vel", f32), ("reserved", i32 * 8),
     ]
 
     def copy(self) -> "H1v2Config":
@@ -94,6 +98,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libh1v2_b200.so")
 
 _SYMBOLS = {
     "h1v2_default_config": (C.c_int, [C.POINTER(H1v2Config)]),
+    "h1v2_rsl_config": (C.c_int, [C.POINTER(H1v2Config)]),
     "h1v2_create": (C.c_int, [C.POINTER(H1v2Config), i32, i32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "h1v2_destroy": (None, [C.c_void_p]),
     "h1v2_last_error": (C.c_char_p, []),
@@ -104,6 +109,7 @@ _SYMBOLS = {
     "h1v2_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_set_reward_weights": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_get_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_set_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -143,4 +149,13 @@ def default_config() -> H1v2Config:
     rc = load_library().h1v2_default_config(C.byref(cfg))
     if rc != 0:
         raise RuntimeError("h1v2_default_config failed")
+    return cfg
+
+
+def rsl_config() -> H1v2Config:
+    """Resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (config/h12_12dof/rsl_env_cfg.py)."""
+    cfg = H1v2Config()
+    rc = load_library().h1v2_rsl_config(C.byref(cfg))
+    if rc != 0:
+        raise RuntimeError("h1v2_rsl_config failed")
     return cfg

@@ -142,6 +142,16 @@ class H1v2Sim:
         self._check(self._lib.h1v2_set_state(self._h, C.byref(st), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # keep the staging tensors alive until consumed
 
+    def set_reward_weights(self, weights) -> None:
+        """CurriculumManager's modify_reward_weight: new weights for the kernel's reward slots, effective from the next step."""
+        import numpy as np
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        if w.size != len(self.cfg.rew_weight):
+            raise ValueError(f"expected {len(self.cfg.rew_weight)} weights, got {w.size}")
+        self._check(self._lib.h1v2_set_reward_weights(self._h, w.ctypes.data_as(C.POINTER(C.c_float))))
+        for i in range(w.size):
+            self.cfg.rew_weight[i] = float(w[i])
+
     def log_host(self):
         import numpy as np
         out = np.zeros(LOG_DIM, np.float32)

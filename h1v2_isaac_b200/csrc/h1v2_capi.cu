@@ -70,7 +70,7 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
     S.cmd[env] = make_float4(cmd.c[0], cmd.c[1], cmd.c[2], cmd.heading_target);
     S.cmd[N + env] = make_float4(cmd.time_left, 0.f, 0.f, __int_as_float(cmd.flags));
     S.ep_len[env] = 0;
-    for (int k = 0; k < 5; k++) S.epsum[(size_t)k * N + env] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < H1V2_EPSUM_F4; k++) S.epsum[(size_t)k * N + env] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   S.leg[lidx] = make_float4(q[0], q[1], q[2], q[3]);
   S.leg[N2 + lidx] = make_float4(q[4], q[5], qd[0], qd[1]);
@@ -128,14 +128,14 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
   for (int k = 0; k < 2; k++) c[k] = S.cmd[(size_t)k * N + env];
   int flags = __float_as_int(c[1].w);
   float root[16] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w, r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
-  float leg[2][12], act[2][20], tmr[2][4], es[20];
+  float leg[2][12], act[2][20], tmr[2][4], es[4 * H1V2_EPSUM_F4];
   for (int s = 0; s < 2; s++) {
     const int l = 2 * env + s;
     for (int k = 0; k < 3; k++) { float4 v = S.leg[(size_t)k * N2 + l]; leg[s][4 * k] = v.x; leg[s][4 * k + 1] = v.y; leg[s][4 * k + 2] = v.z; leg[s][4 * k + 3] = v.w; }
     for (int k = 0; k < 5; k++) { float4 v = S.act[(size_t)k * N2 + l]; act[s][4 * k] = v.x; act[s][4 * k + 1] = v.y; act[s][4 * k + 2] = v.z; act[s][4 * k + 3] = v.w; }
     float4 t = S.timers[l]; tmr[s][0] = t.x; tmr[s][1] = t.y; tmr[s][2] = t.z; tmr[s][3] = t.w;
   }
-  for (int k = 0; k < 5; k++) { float4 v = S.epsum[(size_t)k * N + env]; es[4 * k] = v.x; es[4 * k + 1] = v.y; es[4 * k + 2] = v.z; es[4 * k + 3] = v.w; }
+  for (int k = 0; k < H1V2_EPSUM_F4; k++) { float4 v = S.epsum[(size_t)k * N + env]; es[4 * k] = v.x; es[4 * k + 1] = v.y; es[4 * k + 2] = v.z; es[4 * k + 3] = v.w; }
   const int head = (int)(S.counters[1] % (unsigned long long)H);
   if (!set) {
     if (st.root_pos) for (int k = 0; k < 3; k++) st.root_pos[env * 3 + k] = root[k];
@@ -159,7 +159,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
     if (st.is_heading) st.is_heading[env] = (flags & FLAG_HEADING) != 0;
     if (st.cmd_metrics) { st.cmd_metrics[env * 2] = c[1].y; st.cmd_metrics[env * 2 + 1] = c[1].z; }
     if (st.feet_timers) for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) st.feet_timers[env * 8 + 4 * s + k] = tmr[s][k];
-    if (st.episode_sums) for (int k = 0; k < 20; k++) st.episode_sums[env * 20 + k] = es[k];
+    if (st.episode_sums) for (int k = 0; k < H1V2_NUM_REW; k++) st.episode_sums[env * H1V2_NUM_REW + k] = es[k];
     if (st.obs_history)
       for (int hh = 0; hh < H; hh++) {
         int sl = (head + 1 + hh) % H;
@@ -174,7 +174,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
       if (st.slot_force_hist) for (int k = 0; k < 18; k++) st.slot_force_hist[env * 18 + k] = dg[18 + k];
       if (st.applied_torque) for (int k = 0; k < 12; k++) st.applied_torque[env * 12 + k] = dg[36 + k];
       if (st.joint_acc) for (int k = 0; k < 12; k++) st.joint_acc[env * 12 + k] = dg[48 + k];
-      if (st.reward_terms) for (int k = 0; k < 20; k++) st.reward_terms[env * 20 + k] = dg[60 + k];
+      if (st.reward_terms) for (int k = 0; k < H1V2_NUM_REW; k++) st.reward_terms[env * H1V2_NUM_REW + k] = dg[H1V2_DIAG_REW0 + k];
       if (st.foot_vel) for (int k = 0; k < 6; k++) st.foot_vel[env * 6 + k] = dg[80 + k];
       if (st.pre_reset_qpos) for (int k = 0; k < 19; k++) st.pre_reset_qpos[env * 19 + k] = dg[96 + k];
       if (st.pre_reset_qvel) for (int k = 0; k < 18; k++) st.pre_reset_qvel[env * 18 + k] = dg[115 + k];
@@ -209,7 +209,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
   if (st.cmd_metrics) { c[1].y = st.cmd_metrics[env * 2]; c[1].z = st.cmd_metrics[env * 2 + 1]; }
   c[1].w = __int_as_float(flags);
   if (st.feet_timers) for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) tmr[s][k] = st.feet_timers[env * 8 + 4 * s + k];
-  if (st.episode_sums) for (int k = 0; k < 20; k++) es[k] = st.episode_sums[env * 20 + k];
+  if (st.episode_sums) for (int k = 0; k < H1V2_NUM_REW; k++) es[k] = st.episode_sums[env * H1V2_NUM_REW + k];
   if (st.obs_history)
     for (int hh = 0; hh < H; hh++) {
       int sl = (head + 1 + hh) % H;
@@ -223,7 +223,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
     for (int k = 0; k < 5; k++) S.act[(size_t)k * N2 + l] = make_float4(act[s][4 * k], act[s][4 * k + 1], act[s][4 * k + 2], act[s][4 * k + 3]);
     S.timers[l] = make_float4(tmr[s][0], tmr[s][1], tmr[s][2], tmr[s][3]);
   }
-  for (int k = 0; k < 5; k++) S.epsum[(size_t)k * N + env] = make_float4(es[4 * k], es[4 * k + 1], es[4 * k + 2], es[4 * k + 3]);
+  for (int k = 0; k < H1V2_EPSUM_F4; k++) S.epsum[(size_t)k * N + env] = make_float4(es[4 * k], es[4 * k + 1], es[4 * k + 2], es[4 * k + 3]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -328,7 +328,9 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.s_av = c.scale_ang_vel; P.s_g = c.scale_gravity; P.s_cmd = c.scale_cmd; P.s_q = c.scale_joint_pos; P.s_v = c.scale_joint_vel; P.s_a = c.scale_action;
   for (int t = 0; t < H1V2_NUM_REW; t++) P.w[t] = c.rew_weight[t];
   P.inv_std2 = 1.f / (c.track_std * c.track_std); P.air_thr = c.feet_air_threshold; P.contact_thr = c.contact_threshold; P.base_h = c.base_height_target;
-  P.m_poslim = c.mask_pos_limits; P.m_dev = c.mask_joint_dev; P.m_tau = c.mask_torques; P.m_undesired = c.mask_undesired_slots; P.m_illegal = c.mask_illegal_slots;
+  P.m_poslim = c.mask_pos_limits; P.m_dev = c.mask_joint_dev; P.m_poslim_b = c.mask_pos_limits_b; P.m_dev_b = c.mask_joint_dev_b;
+  P.m_cforce = c.mask_contact_forces_slots; P.cforce_thr = c.contact_forces_threshold;
+  P.m_tau = c.mask_torques; P.m_undesired = c.mask_undesired_slots; P.m_illegal = c.mask_illegal_slots;
   for (int k = 0; k < 2; k++) {
     P.c_lx[k] = c.cmd_lin_x[k]; P.c_ly[k] = c.cmd_lin_y[k]; P.c_wz[k] = c.cmd_ang_z[k]; P.c_hd[k] = c.cmd_heading[k]; P.c_rt[k] = c.cmd_resample_time[k];
     P.rjp[k] = c.reset_joint_pos_scale[k]; P.rjv[k] = c.reset_joint_vel_scale[k]; P.push_int[k] = c.push_interval_s[k]; P.push_v[k] = c.push_vel_xy[k];
@@ -336,6 +338,13 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   }
   P.rel_standing = c.rel_standing_envs; P.rel_heading = c.rel_heading_envs; P.k_heading = c.heading_stiffness; P.heading_cmd = c.heading_command;
   P.max_command_step = c.cmd_resample_time[1] / P.step_dt;
+  if (c.command_class != 0 && c.command_class != 1) return fail("config: command_class must be 0 (UniformVelocityCommand) or 1 (UniformVelocityCommandWithDeadzone)");
+  if (c.command_class == 1 && c.velocity_deadzone != 0.f)
+    return fail("config: UniformVelocityCommandWithDeadzone is implemented for velocity_deadzone == 0 only (rsl_env_cfg.py:98); a positive dead zone balances a per-process count of envs");
+  P.cmd_class = c.command_class;
+  // commands.py:62-76 with no env ever inside the dead zone: randperm(n)[: n // 2] of ALL envs get xy = 0, i.e. each env with probability (n // 2) / n
+  P.dz_prob = (float)(n / 2) / (float)n;
+  P.flip_prob = c.ang_vel_flip_prob;
   P.init_h = c.init_root_height; P.push_enable = c.push_enable;
   P.key0 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
   P.env_id_offset = c.env_id_offset;
@@ -400,7 +409,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &S.cmd, 2 * N);
   rc |= dalloc(h, &S.timers, 2 * N);
   rc |= dalloc(h, &S.warm, 3 * 2 * N);
-  rc |= dalloc(h, &S.epsum, 5 * N);
+  rc |= dalloc(h, &S.epsum, H1V2_EPSUM_F4 * N);
   rc |= dalloc(h, &S.hist, N * (size_t)h->P.H * H1V2_HIST_STRIDE);
   rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM + 32);  // + cumulative histogram of Newton iterations per solve
   rc |= dalloc(h, &S.log, (size_t)H1V2_LOG_DIM);
@@ -529,6 +538,15 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
   return 0;
 }
 
+int h1v2_set_reward_weights(H1v2Handle* h, const float* weights) {
+  if (!h || !weights) return fail("h1v2_set_reward_weights: bad arguments");
+  for (int t = 0; t < H1V2_NUM_REW; t++) {
+    if (!std::isfinite(weights[t])) return fail("h1v2_set_reward_weights: non-finite weight");
+    h->cfg.rew_weight[t] = weights[t];
+    h->P.w[t] = weights[t];  // the parameter block travels by value with every launch
+  }
+  return 0;
+}
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
   if (!h || !dst) return fail("h1v2_get_state: bad arguments");
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *dst, 0);

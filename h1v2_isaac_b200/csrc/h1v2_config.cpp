@@ -90,6 +90,11 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->mask_joint_dev = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8);
   c->mask_torques = 0xFFFu;
   c->mask_undesired_slots = (1u << 2) | (1u << 3);
+  // second-instance terms and contact_forces of the Rsl cfg (C12/rsl_env_cfg.py:353-401): present, weight 0 by default
+  c->mask_pos_limits_b = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8);
+  c->mask_joint_dev_b = (1u << 4) | (1u << 5) | (1u << 10) | (1u << 11);
+  c->mask_contact_forces_slots = 0x3u;
+  c->contact_forces_threshold = 800.0f;
   // terminations: C12/rough_env_cfg.py:95-109 (bodies with colliders: knee links, torso, pelvis)
   c->mask_illegal_slots = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 5);
   // commands: V/velocity_env_cfg.py:90-104 ; C12/flat_env_cfg.py:46-48
@@ -102,6 +107,9 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->rel_heading_envs = 1.0f;
   c->heading_stiffness = 0.5f;
   c->heading_command = 1;
+  c->command_class = 0;
+  c->velocity_deadzone = 0.0f;
+  c->ang_vel_flip_prob = 0.005f / 20.0f;  // T/utils/mdp/commands.py:86 physics_dt / max_episode_length_s
   // reset events: C12/rough_env_cfg.py:78-92 ; V/velocity_env_cfg.py:200-209
   c->reset_pose_range[0][0] = -0.5f; c->reset_pose_range[0][1] = 0.5f;
   c->reset_pose_range[1][0] = -0.5f; c->reset_pose_range[1][1] = 0.5f;
@@ -116,5 +124,63 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->env_spacing = 2.5f;
   c->joint_vel_limit = 100.0f;  // A/robots/h12.py:66,89,103 velocity_limit
   c->runaway_vel = 1000.0f;     // A/robots/h12.py:27-28 max_linear_velocity / max_angular_velocity
+  return 0;
+}
+
+// Resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (C12/__init__.py:85-93 -> C12/rsl_env_cfg.py:503-540 H12_12dof_EnvCfg), the task
+// the reference's deployed policies were trained on.  Same robot model and solver as the Flat id.
+extern "C" int h1v2_rsl_config(H1v2Config* c) {
+  if (h1v2_default_config(c) != 0) return -1;
+  // actions: C12/rsl_env_cfg.py:104-127 (scale 0.25, preserve_order over the MJCF joint list)
+  c->action_scale = 0.25f;
+  for (int i = 0; i < H1V2_NJ; i++) c->joint_perm[i] = i;
+  // robot: A/robots/h12.py:117-206 H12_12DOF_IDEAL -- IdealPDActuatorCfg, same gains and limits, no delay line
+  c->min_delay = c->max_delay = 0;
+  // observations: C12/rsl_env_cfg.py:133-203 (history 6, gyro x0.25, joint velocity x0.05)
+  c->history_length = 6;
+  c->scale_ang_vel = 0.25f;
+  c->scale_joint_vel = 0.05f;
+  // rewards: C12/rsl_env_cfg.py:278-407
+  for (int t = 0; t < H1V2_NUM_REW; t++) c->rew_weight[t] = 0.0f;
+  c->rew_weight[H1V2_REW_TRACK_LIN_XY_BASE] = 1.0f;      // :283-287 track_lin_vel_xy_exp, base frame
+  c->rew_weight[H1V2_REW_TRACK_ANG_Z_BASE] = 0.5f;       // :288-292
+  c->rew_weight[H1V2_REW_FEET_AIR_BIPED] = 0.75f;        // :295-305
+  c->rew_weight[H1V2_REW_FEET_SLIDE] = -0.25f;           // :306-315
+  c->rew_weight[H1V2_REW_FLAT_ORI] = -1.0f;              // :318-321
+  c->rew_weight[H1V2_REW_BASE_HEIGHT] = -0.2f;           // :322-328
+  c->base_height_target = 1.0f;
+  c->rew_weight[H1V2_REW_TORQUES] = -1.0e-5f;            // :331-334 (all joints)
+  c->rew_weight[H1V2_REW_JOINT_VEL] = -1.0e-3f;          // :335-338
+  c->rew_weight[H1V2_REW_DOF_ACC] = -1.0e-7f;            // :339-342
+  c->rew_weight[H1V2_REW_JOINT_DEV_HIP] = -0.2f;         // :343-357 hip yaw + roll
+  c->mask_joint_dev = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8);
+  c->rew_weight[H1V2_REW_JOINT_DEV_B] = -0.2f;           // :358-372 ankle roll + pitch
+  c->mask_joint_dev_b = (1u << 4) | (1u << 5) | (1u << 10) | (1u << 11);
+  c->rew_weight[H1V2_REW_DOF_POS_LIMITS] = -0.2f;        // :373-379 ankles
+  c->mask_pos_limits = (1u << 4) | (1u << 5) | (1u << 10) | (1u << 11);
+  c->rew_weight[H1V2_REW_DOF_POS_LIMITS_B] = -0.2f;      // :380-386 hip yaw + roll
+  c->mask_pos_limits_b = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8);
+  c->rew_weight[H1V2_REW_ACTION_RATE] = -0.01f;          // :389-392
+  c->rew_weight[H1V2_REW_CONTACT_FORCES] = -1.0e-3f;     // :395-404 feet, 800 N
+  c->mask_contact_forces_slots = 0x3u;
+  c->contact_forces_threshold = 800.0f;
+  c->rew_weight[H1V2_REW_TERMINATION] = -200.0f;         // :407
+  // commands: C12/rsl_env_cfg.py:82-99 UniformVelocityCommandWithDeadzoneCfg, no heading control
+  c->command_class = 1;
+  c->velocity_deadzone = 0.0f;
+  c->ang_vel_flip_prob = 0.005f / 20.0f;
+  c->cmd_lin_x[0] = -1.0f; c->cmd_lin_x[1] = 1.0f;
+  c->cmd_lin_y[0] = -1.0f; c->cmd_lin_y[1] = 1.0f;
+  c->cmd_resample_time[0] = 5.0f; c->cmd_resample_time[1] = 8.0f;
+  c->heading_command = 0;
+  c->heading_stiffness = 1.0f;
+  // events: C12/rsl_env_cfg.py:208-272 (friction 0.1..1.25 x ground 1.0, pushes every U(5,8) s of +-1 m/s)
+  c->friction_range[0] = 0.1f; c->friction_range[1] = 1.25f;
+  c->friction = 0.5f * (c->friction_range[0] + c->friction_range[1]);
+  c->solver_iterations = 30;  // friction below 0.3: the stiff regime of the pyramidal regulariser
+  c->reset_joint_vel_scale[0] = c->reset_joint_vel_scale[1] = 1.0f;
+  c->push_enable = 1;
+  c->push_interval_s[0] = 5.0f; c->push_interval_s[1] = 8.0f;
+  c->push_vel_xy[0] = -1.0f; c->push_vel_xy[1] = 1.0f;
   return 0;
 }

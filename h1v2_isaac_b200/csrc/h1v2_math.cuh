@@ -199,7 +199,8 @@ __device__ __forceinline__ void rng4(uint32_t key0, int64_t gid, unsigned long l
   const float4 r = rng4v(key0, (uint32_t)gid, (uint32_t)step, (uint32_t)(step >> 32), stream, block);
   u[0] = r.x; u[1] = r.y; u[2] = r.z; u[3] = r.w;
 }
-__device__ __forceinline__ float uni(float u, float lo, float hi) { return lo + (hi - lo) * u; }
+// one rounding (fused multiply-add) on both sides: the oracle calls fmaf too, so every uniform draw is bit-identical to it
+__device__ __forceinline__ float uni(float u, float lo, float hi) { return fmaf(hi - lo, u, lo); }
 
 __device__ __forceinline__ float wrap_to_pi(float a) {
   const float PI = 3.14159265358979323846f, TWO_PI = 2.0f * 3.14159265358979323846f;

@@ -6,6 +6,7 @@
 #include "../../include/h1v2_b200.h"
 
 #define H1V2_OBS_MAXPASS ((H1V2_MAX_HISTORY * H1V2_OBS_TERM_DIM + 31) / 32)  // 32-column passes over one observation row
+#define H1V2_EPSUM_F4 ((H1V2_NUM_REW + 3) / 4)  // float4 rows of the episode sums
 #define H1V2_HIST_STRIDE 48  // floats per history slot (45 used; 192 B = 6 sectors)
 
 // --- rigid-body constants of one leg (MJCF order: hip_yaw, hip_pitch, hip_roll, knee, ankle_pitch, ankle_roll) ---
@@ -58,11 +59,14 @@ struct KParams {
   float w[H1V2_NUM_REW];
   float inv_std2, air_thr, contact_thr, base_h;
   float soft_lo[12], soft_hi[12];
-  uint32_t m_poslim, m_dev, m_tau, m_undesired, m_illegal;
+  uint32_t m_poslim, m_dev, m_tau, m_undesired, m_illegal, m_poslim_b, m_dev_b, m_cforce;
+  float cforce_thr;
   // commands
   float c_lx[2], c_ly[2], c_wz[2], c_hd[2], c_rt[2];
   float rel_standing, rel_heading, k_heading;
   int heading_cmd;
+  int cmd_class;          // 1: UniformVelocityCommandWithDeadzone (T/utils/mdp/commands.py:19-96), dead zone 0
+  float dz_prob, flip_prob;
   float max_command_step;
   // events
   float rp[6][2], rv[6][2], rjp[2], rjv[2], init_h;
@@ -84,7 +88,7 @@ struct KState {
   float4* cmd;     // [2][N]   (cx,cy,cz,heading_target) (time_left,err_xy,err_yaw,flags)
   float4* timers;  // [2N]     cur_air,last_air,cur_contact,last_contact of the lane's foot
   float4* warm;    // [3][2N]  solver warm start: qacc of the last substep (leg 6 | root 6)
-  float4* epsum;   // [5][N]   episode sums of the 20 reward slots
+  float4* epsum;   // [6][N]   episode sums of the 22 reward slots (2 pad)
   float* hist;     // [N][H][48]
   const int* lut;  // [obs_dim] (history index << 8) | offset in the 45-float sample, for the term-major flatten
   int64_t* ep_len; // [N] bound, owned by the caller
@@ -94,9 +98,10 @@ struct KState {
   unsigned long long* counters;  // [0] global step counter, [1] history head
   unsigned* done;                // blocks of the current launch that have finished (the last one publishes the log, advances the counters)
 };
-#define H1V2_DIAG_DIM 144
-// diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | reward_terms 60..79
-//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140
+#define H1V2_DIAG_DIM 168
+#define H1V2_DIAG_REW0 144
+// diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | (free 60..79)
+//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140 | reward_terms 144..165
 #define FLAG_DELAY_FRESH 1
 #define FLAG_HIST_FRESH 2
 #define FLAG_LAG_SHIFT 2

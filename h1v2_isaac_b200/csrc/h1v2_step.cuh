@@ -135,7 +135,18 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
     float err = wrap_to_pi(c.heading_target - atan2f(rd.hy, rd.hx));
     c.c[2] = fminf(fmaxf(P.k_heading * err, P.c_wz[0]), P.c_wz[1]);
   }
-  if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
+  if (P.cmd_class == 0) {
+    if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
+  } else {
+    // UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96) with velocity_deadzone == 0: the
+    // override never zeroes standing envs; |cmd_xy| < 0 holds for no env, so the balancing branch zeroes the xy command of
+    // n // 2 envs drawn uniformly from ALL envs on every step (per env: probability (n // 2) / n, drawn independently here);
+    // then the yaw-rate command flips sign with probability physics_dt / max_episode_length_s.
+    float u[4];
+    rng4(P.key0, gid, step, STREAM_CMD, 4, u);
+    if (u[0] < P.dz_prob) c.c[0] = c.c[1] = 0.f;
+    if (u[1] < P.flip_prob) c.c[2] = -c.c[2];
+  }
 }
 
 // ---- history rings of the warp's 16 envs: global -> shared memory, asynchronously ----
@@ -482,18 +493,23 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;
     {
-      float s_lim = 0.f, s_dev = 0.f, s_vel = 0.f, s_da = 0.f;
+      float s_lim = 0.f, s_dev = 0.f, s_lim_b = 0.f, s_dev_b = 0.f, s_vel = 0.f, s_da = 0.f;
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const int j = 6 * side + k;
-        if ((P.m_poslim >> j) & 1u) s_lim += -fminf(q[k] - P.soft_lo[j], 0.f) + fmaxf(q[k] - P.soft_hi[j], 0.f);
-        if ((P.m_dev >> j) & 1u) s_dev += fabsf(q[k] - P.q0[j]);
+        const float lim = -fminf(q[k] - P.soft_lo[j], 0.f) + fmaxf(q[k] - P.soft_hi[j], 0.f), dev = fabsf(q[k] - P.q0[j]);
+        if ((P.m_poslim >> j) & 1u) s_lim += lim;
+        if ((P.m_dev >> j) & 1u) s_dev += dev;
+        if ((P.m_poslim_b >> j) & 1u) s_lim_b += lim;
+        if ((P.m_dev_b >> j) & 1u) s_dev_b += dev;
         s_vel = fmaf(qd[k], qd[k], s_vel);
         float da = la[k] - prev[k];
         s_da = fmaf(da, da, s_da);
       }
       r[H1V2_REW_DOF_POS_LIMITS] = pair_sum(s_lim);
       r[H1V2_REW_JOINT_DEV_HIP] = pair_sum(s_dev);
+      r[H1V2_REW_DOF_POS_LIMITS_B] = pair_sum(s_lim_b);
+      r[H1V2_REW_JOINT_DEV_B] = pair_sum(s_dev_b);
       r[H1V2_REW_TORQUES] = pair_sum(s_tau);
       r[H1V2_REW_DOF_ACC] = pair_sum(s_acc);
       r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel);
@@ -530,11 +546,17 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       r[H1V2_REW_LIN_VEL_Z] = rd.vb.z * rd.vb.z;
       r[H1V2_REW_BASE_HEIGHT] = (rp[2] - P.base_h) * (rp[2] - P.base_h);
       float und = 0.f, cf = 0.f;
-      if ((P.m_undesired >> side) & 1u) { und += C_foot > P.contact_thr; cf += fmaxf(C_foot - P.contact_thr, 0.f); }
-      if ((P.m_undesired >> (2 + side)) & 1u) { und += C_shin > P.contact_thr; cf += fmaxf(C_shin - P.contact_thr, 0.f); }
+      // undesired_contacts counts bodies above the sensor threshold; contact_forces (C12/rsl_env_cfg.py:395-404) sums the
+      // excess of max_h |F| over its own threshold on its own bodies
+      if ((P.m_undesired >> side) & 1u) und += C_foot > P.contact_thr;
+      if ((P.m_undesired >> (2 + side)) & 1u) und += C_shin > P.contact_thr;
+      if ((P.m_cforce >> side) & 1u) cf += fmaxf(C_foot - P.cforce_thr, 0.f);
+      if ((P.m_cforce >> (2 + side)) & 1u) cf += fmaxf(C_shin - P.cforce_thr, 0.f);
       if (side == 0) {
-        if ((P.m_undesired >> 4) & 1u) { und += C_torso > P.contact_thr; cf += fmaxf(C_torso - P.contact_thr, 0.f); }
-        if ((P.m_undesired >> 5) & 1u) { und += C_pelvis > P.contact_thr; cf += fmaxf(C_pelvis - P.contact_thr, 0.f); }
+        if ((P.m_undesired >> 4) & 1u) und += C_torso > P.contact_thr;
+        if ((P.m_undesired >> 5) & 1u) und += C_pelvis > P.contact_thr;
+        if ((P.m_cforce >> 4) & 1u) cf += fmaxf(C_torso - P.cforce_thr, 0.f);
+        if ((P.m_cforce >> 5) & 1u) cf += fmaxf(C_pelvis - P.cforce_thr, 0.f);
       }
       r[H1V2_REW_UNDESIRED_CONTACTS] = pair_sum(und);
       r[H1V2_REW_CONTACT_FORCES] = pair_sum(cf);
@@ -546,13 +568,13 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       r[t] = v;
       total += v;
     }
-    // episode sums: lane 0 owns float4 0..2 (terms 0..11), lane 1 owns float4 3..4 (terms 12..19)
+    // episode sums: lane 0 owns float4 0..2 (terms 0..11), lane 1 owns float4 3..5 (terms 12..21 and two pads)
     float es[12];
-    const int ef0 = side == 0 ? 0 : 3, enf4 = side == 0 ? 3 : 2;
+    const int ef0 = side == 0 ? 0 : 3, enf4 = 3;
     {
       float rsel[12];
 #pragma unroll
-      for (int i = 0; i < 12; i++) rsel[i] = side == 0 ? r[i] : (i < 8 ? r[12 + (i & 7)] : 0.f);
+      for (int i = 0; i < 12; i++) rsel[i] = side == 0 ? r[i] : (12 + i < H1V2_NUM_REW ? r[12 + i < H1V2_NUM_REW ? 12 + i : 0] : 0.f);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -586,7 +608,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 3; i++) { dg[30 + i] = h_torso[i]; dg[33 + i] = h_pelvis[i]; }
 #pragma unroll
-        for (int t = 0; t < H1V2_NUM_REW; t++) dg[60 + t] = r[t];
+        for (int t = 0; t < H1V2_NUM_REW; t++) dg[H1V2_DIAG_REW0 + t] = r[t];
         dg[86] = (float)max_it; dg[87] = (float)ncap; dg[88] = (float)sum_it;
       }
     }
@@ -607,7 +629,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     if (reset) {
       if (valid) {
         const float inv = 1.f / P.max_episode_length_s;
-        const int f0 = side == 0 ? 0 : 12, cnt = side == 0 ? 12 : 8;
+        const int f0 = side == 0 ? 0 : 12, cnt = side == 0 ? 12 : H1V2_NUM_REW - 12;
 #pragma unroll
         for (int i = 0; i < 12; i++)
           if (i < cnt) atomicAdd(S.acc + H1V2_LOG_REW0 + f0 + i, es[i] * inv);

@@ -36,6 +36,9 @@ REW_FUNC_SLOT = {
     "action_rate_l2": 10, "flat_orientation_l2": 11, "lin_vel_z_l2": 12, "undesired_contacts": 13, "track_lin_vel_xy_exp": 14,
     "track_ang_vel_z_exp": 15, "feet_air_time": 16, "joint_vel_l2": 17, "base_height_l2": 18, "contact_forces": 19,
 }
+# functions a cfg may use twice (C12/rsl_env_cfg.py:343-386 has joint_deviation_l1 and joint_pos_limits on two joint sets each):
+# the second term of the cfg goes to the kernel's second slot of that function
+REW_FUNC_SLOT_B = {"joint_pos_limits": 20, "joint_deviation_l1": 21}
 OBS_LAYOUT = ["base_ang_vel", "projected_gravity", "generated_commands", "joint_pos_rel", "joint_vel_rel", "last_action"]
 
 
@@ -95,15 +98,48 @@ def _slot_mask(params, key="sensor_cfg") -> int:
     return sum(1 << s for s in _match(pats, SLOT_BODIES))
 
 
+def reward_slots(cfg) -> dict[str, int]:
+    """cfg reward term name -> kernel slot, in cfg order.  Zero-weight terms get a slot when one is free (a curriculum may raise
+    them later); a non-zero-weight term without a slot raises."""
+    used, out = set(), {}
+    for n, t in _terms(cfg.rewards):
+        f, w = _fname(t.func), float(t.weight)
+        slot = REW_FUNC_SLOT.get(f)
+        if slot in used:
+            slot = REW_FUNC_SLOT_B.get(f)
+        if slot is None or slot in used:
+            if w == 0.0:
+                continue  # RewardManager skips zero-weight terms
+            if f not in REW_FUNC_SLOT:
+                raise NotImplementedError(f"rewards.{n}: mdp.{f} is not implemented in the fused kernel")
+            raise NotImplementedError(f"rewards.{n}: mdp.{f} appears more often than the kernel has slots for it")
+        used.add(slot)
+        out[n] = slot
+    return out
+
+
+def curriculum_schedule(cfg) -> list[tuple[int, float, int]]:
+    """CurriculumManager terms -> [(reward slot, weight, num_steps)].  Only mdp.modify_reward_weight is implemented
+    (C12/rsl_env_cfg.py:447-497): once common_step_counter > num_steps the term's weight becomes `weight`."""
+    out, slots = [], reward_slots(cfg)
+    for n, t in _terms(_get(cfg, "curriculum")):
+        f, p = _fname(t.func), (t.params or {})
+        if f != "modify_reward_weight":
+            raise NotImplementedError(f"curriculum.{n}: mdp.{f} is not implemented (only modify_reward_weight is)")
+        if p["term_name"] not in slots:
+            raise NotImplementedError(f"curriculum.{n}: reward term {p['term_name']!r} has no kernel slot")
+        out.append((slots[p["term_name"]], float(p["weight"]), int(p["num_steps"])))
+    return out
+
+
 def flatten_cfg(cfg) -> H1v2Config:
-    """Resolved ManagerBasedRLEnvCfg tree (reference: config/h12_12dof/flat_env_cfg.py:13-48 and parents) -> H1v2Config."""
+    """Resolved ManagerBasedRLEnvCfg tree (reference: config/h12_12dof/flat_env_cfg.py:13-48 and parents, or
+    config/h12_12dof/rsl_env_cfg.py:44-540) -> H1v2Config."""
     c = default_config()  # rigid-body model, MuJoCo solver parameters; everything below is overwritten from the tree
     # managers the fused kernel does not have: refuse rather than silently drop them
     if _get(cfg, "constraints") is not None:
         raise NotImplementedError("constraints: the Constraints-as-Terminations manager (utils/cat) is not implemented in the fused kernel")
-    cur = [n for n, t in _terms(_get(cfg, "curriculum"))]
-    if cur:
-        raise NotImplementedError(f"curriculum: terms {cur} are not implemented (the Flat id sets terrain_levels=None and has no other)")
+    curriculum_schedule(cfg)  # raises on anything but modify_reward_weight; the schedule itself is applied by the env, host side
     c.sim_dt = float(cfg.sim.dt)
     c.decimation = int(cfg.decimation)
     c.episode_length_s = float(cfg.episode_length_s)
@@ -189,6 +225,20 @@ def flatten_cfg(cfg) -> H1v2Config:
             raise NotImplementedError(f"observations.policy.{n}.clip is not supported")
         sc = _get(t, "scale")
         scale.append(1.0 if sc is None else float(sc))
+    for n, t in terms:  # joint-indexed terms must list the joints in the action's order (one permutation in the kernel)
+        ac = _get(_get(t, "params"), "asset_cfg")
+        names = _get(ac, "joint_names")
+        if names is None:
+            jo = BREADTH_FIRST
+        elif _get(ac, "preserve_order", False):
+            jo = []
+            for pat in ([names] if isinstance(names, str) else names):
+                jo += [i for i in _match(pat, JOINT_NAMES) if i not in jo]
+        else:
+            sel = set(_match(names, JOINT_NAMES))
+            jo = [i for i in BREADTH_FIRST if i in sel]
+        if _fname(t.func) in ("joint_pos_rel", "joint_vel_rel") and list(jo) != list(order):
+            raise NotImplementedError(f"observations.policy.{n}: joint order differs from the action term's")
     if noise[2] or noise[5]:
         raise NotImplementedError("observations.policy: noise on commands / last_action is not supported")
     c.noise_ang_vel, c.noise_gravity, c.noise_joint_pos, c.noise_joint_vel = noise[0], noise[1], noise[3], noise[4]
@@ -198,16 +248,11 @@ def flatten_cfg(cfg) -> H1v2Config:
     for i in range(len(REW_NAMES)):
         c.rew_weight[i] = 0.0
     std = None
+    slots = reward_slots(cfg)
     for n, t in _terms(cfg.rewards):
-        w = float(t.weight)
-        if w == 0.0:
-            continue  # RewardManager skips zero-weight terms
-        f = _fname(t.func)
-        if f not in REW_FUNC_SLOT:
-            raise NotImplementedError(f"rewards.{n}: mdp.{f} is not implemented in the fused kernel")
-        slot, p = REW_FUNC_SLOT[f], (t.params or {})
-        if c.rew_weight[slot] != 0.0:
-            raise NotImplementedError(f"rewards.{n}: mdp.{f} appears twice")
+        if n not in slots:
+            continue
+        w, f, slot, p = float(t.weight), _fname(t.func), slots[n], (t.params or {})
         c.rew_weight[slot] = w
         if "std" in p:
             if std is not None and abs(std - float(p["std"])) > 1e-9:
@@ -220,15 +265,24 @@ def flatten_cfg(cfg) -> H1v2Config:
         elif f == "feet_slide" and _slot_mask(p) != 0b11:
             raise NotImplementedError(f"rewards.{n}: sensor bodies must be the two ankle_roll links")
         elif f == "joint_pos_limits":
-            c.mask_pos_limits = _joint_mask(p)
+            if slot == REW_FUNC_SLOT[f]:
+                c.mask_pos_limits = _joint_mask(p)
+            else:
+                c.mask_pos_limits_b = _joint_mask(p)
         elif f == "joint_deviation_l1":
-            c.mask_joint_dev = _joint_mask(p)
+            if slot == REW_FUNC_SLOT[f]:
+                c.mask_joint_dev = _joint_mask(p)
+            else:
+                c.mask_joint_dev_b = _joint_mask(p)
         elif f == "joint_torques_l2":
             c.mask_torques = _joint_mask(p)
-        elif f in ("undesired_contacts", "contact_forces"):
+        elif f == "undesired_contacts":
             c.mask_undesired_slots = _slot_mask(p)
             if abs(float(p.get("threshold", 1.0)) - 1.0) > 1e-9:
                 raise NotImplementedError(f"rewards.{n}: threshold must equal the contact threshold 1.0")
+        elif f == "contact_forces":
+            c.mask_contact_forces_slots = _slot_mask(p)
+            c.contact_forces_threshold = float(p["threshold"])
         elif f == "base_height_l2":
             c.base_height_target = float(p["target_height"])
     if std is not None:
@@ -252,7 +306,15 @@ def flatten_cfg(cfg) -> H1v2Config:
     # ---- commands (V/velocity_env_cfg.py:90-104; flat_env_cfg.py:46-48) ----
     cmd = cfg.commands.base_velocity
     ctype = getattr(_get(cmd, "class_type"), "__name__", "UniformVelocityCommand")
-    if ctype != "UniformVelocityCommand":  # e.g. utils/mdp/commands.py:19 UniformVelocityCommandWithDeadzone: cross-env balancing
+    if ctype == "UniformVelocityCommandWithDeadzone":  # T/utils/mdp/commands.py:19-96
+        c.command_class = 1
+        c.velocity_deadzone = float(_get(cmd, "velocity_deadzone", 0.1))
+        if c.velocity_deadzone != 0.0:  # a positive dead zone balances a per-process COUNT of envs inside it (commands.py:62-83)
+            raise NotImplementedError("commands.base_velocity.velocity_deadzone: only 0.0 (C12/rsl_env_cfg.py:98) is implemented in the fused kernel")
+        c.ang_vel_flip_prob = c.sim_dt / c.episode_length_s  # commands.py:37-38,86 (from the fp32 values the kernel holds)
+    elif ctype == "UniformVelocityCommand":
+        c.command_class = 0
+    else:
         raise NotImplementedError(f"commands.base_velocity: command class {ctype} is not implemented in the fused kernel")
     r = cmd.ranges
     for dst, src in ((c.cmd_lin_x, r.lin_vel_x), (c.cmd_lin_y, r.lin_vel_y), (c.cmd_ang_z, r.ang_vel_z), (c.cmd_resample_time, cmd.resampling_time_range)):
@@ -385,11 +447,14 @@ class H1v2ManagerBasedRLEnv:
         self._prev_action = torch.zeros((n, NJ), device=self.device)
         self.action_manager = _ActionManagerView(self)
         self.observation_manager = _ObservationManagerView(self)
-        self.reward_manager = _NamesView([REW_NAMES[i] for i in range(len(REW_NAMES)) if self.kernel_cfg.rew_weight[i] != 0.0])
+        self.reward_manager = _NamesView([n for n, t in _terms(cfg.rewards) if float(t.weight) != 0.0])
         self.termination_manager = _NamesView(["time_out", "base_contact"])
         self.command_manager = _NamesView(["base_velocity"])
-        self._rew_names = [n for n, t in _terms(cfg.rewards) if float(t.weight) != 0.0]
-        self._rew_slots = [REW_FUNC_SLOT[_fname(getattr(cfg.rewards, n).func)] for n in self._rew_names]
+        slots = reward_slots(cfg)
+        self._rew_names = list(slots)  # every term that owns a slot is logged, like upstream's Episode_Reward/<term> (0 for weight 0)
+        self._rew_slots = [slots[n] for n in self._rew_names]
+        # CurriculumManager (modify_reward_weight only): pending (slot, weight, num_steps), applied once the counter passes num_steps
+        self._curriculum = curriculum_schedule(cfg)
         self._configure_gym_env_spaces()
         self.obs_buf = {"policy": self.sim.observe()}
         print(f"[INFO]: B200-native environment: {n} envs on {self.device}, step_dt {self.step_dt:.3f} s, obs {self.sim.obs_dim}, seed {self._seed}"
@@ -439,11 +504,26 @@ class H1v2ManagerBasedRLEnv:
         obs, rew, terminated, truncated = self.sim.step(action)
         self._prev_action, self._last_action = self._last_action, action
         self.common_step_counter += 1
+        if self._curriculum:
+            self._apply_curriculum()
         self.obs_buf = {"policy": obs}
         self.reward_buf, self.reset_terminated, self.reset_time_outs = rew, terminated, truncated
         self.reset_buf = terminated | truncated
         self.extras = {"log": self._log_dict()}
         return self.obs_buf, rew, terminated, truncated, self.extras
+
+    def _apply_curriculum(self) -> None:
+        """mdp.modify_reward_weight (C12/rsl_env_cfg.py:447-497): `if env.common_step_counter > num_steps: weight = w`.  Upstream
+        evaluates it inside _reset_idx, i.e. in any step with a reset; at thousands of envs that is every step.  Host integers only."""
+        due = [t for t in self._curriculum if self.common_step_counter > t[2]]
+        if not due:
+            return
+        w = list(self.sim.cfg.rew_weight)
+        for slot, weight, _ in due:
+            w[slot] = weight
+        if w != list(self.sim.cfg.rew_weight):
+            self.sim.set_reward_weights(w)
+        self._curriculum = [t for t in self._curriculum if t not in due]
 
     def _log_dict(self) -> dict:
         """extras["log"] (T/utils/cat/cat_env.py:217-245): 0-d device tensors, no host sync.  Values are those of the

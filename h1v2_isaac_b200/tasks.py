@@ -1,31 +1,53 @@
-"""Self-contained registration of the Flat H1-2 task for machines that have neither the reference's `biped_tasks`
-package nor isaaclab (the GPU test box): the same gym id, the same entry-point kwargs, a cfg tree of the same shape.
+"""Self-contained registration of the Flat and Rsl H1-2 tasks for machines that have neither the reference's `biped_tasks`
+package nor isaaclab (the GPU test box): the same gym ids, the same entry-point kwargs, cfg trees of the same shape.
 
-The tree is generated FROM the kernel's resolved default (`h1v2_default_config`, every value of which cites the reference
-line that pins it) by inverting `env.flatten_cfg`, so `flatten_cfg(default_env_cfg()) == default_config()` by
-construction and is asserted in tests/test_boundary.py.  When `biped_tasks` is importable its own registration
-(packages/biped_tasks/.../config/h12_12dof/__init__.py:40-49) wins and this module does nothing.
+The trees are generated FROM the kernel's resolved configs (`h1v2_default_config`, `h1v2_rsl_config`, every value of which
+cites the reference line that pins it) by inverting `env.flatten_cfg`, so `flatten_cfg(default_env_cfg()) == default_config()`
+(and the same for Rsl) by construction; asserted in tests/test_boundary.py.  When `biped_tasks` is importable its own
+registration (packages/biped_tasks/.../config/h12_12dof/__init__.py:40-49,85-93) wins and this module does nothing.
 """
 from __future__ import annotations
 
 TASK_ID = "Isaac-Velocity-Flat-H12_12dof-v0"
+RSL_TASK_ID = "Isaac-Velocity-Rsl-H12_12dof-v0"
+# reward term names of C12/rsl_env_cfg.py:278-407 by kernel slot (the Flat tree uses _capi.REW_NAMES)
+RSL_REW_NAMES = {14: "track_lin_vel_xy_exp", 15: "track_ang_vel_z_exp", 3: "feet_air_time", 4: "feet_slide", 11: "flat_orientation",
+                 18: "base_height_l2", 8: "joint_torques_l2", 17: "joint_vel_l2", 9: "dof_acc_l2", 6: "joint_deviation_hip",
+                 21: "joint_deviation_ankle", 5: "joint_pos_limits_ankle", 20: "joint_pos_limits_hip", 10: "action_rate_l2",
+                 19: "contact_forces", 0: "termination_penalty"}
+# C12/rsl_env_cfg.py:447-497: modify_reward_weight on these terms after 24 * 5000 steps, to the weight they already have
+RSL_CURRICULUM = ["flat_orientation", "joint_torques_l2", "joint_vel_l2", "dof_acc_l2", "joint_deviation_hip", "joint_deviation_ankle",
+                  "joint_pos_limits_ankle", "joint_pos_limits_hip", "contact_forces", "feet_air_time", "feet_slide", "base_height_l2"]
+
+
+class UniformVelocityCommandWithDeadzone:
+    """Name-only stand-in for T/utils/mdp/commands.py:19 (flatten_cfg keys on class_type.__name__; the logic is in the kernel)."""
 
 
 def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
+    from ._capi import default_config
+    return env_cfg_from_config(default_config(), num_envs, device)
+
+
+def rsl_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
+    from ._capi import rsl_config
+    return env_cfg_from_config(rsl_config(), num_envs, device, rew_names=RSL_REW_NAMES, curriculum=RSL_CURRICULUM, curriculum_steps=24 * 5000)
+
+
+def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_names=None, curriculum=(), curriculum_steps=0):
+    """Inverse of env.flatten_cfg: an H1v2Config -> a ManagerBasedRLEnvCfg-shaped tree built from the shim cfg classes."""
     from . import shims
     shims.install()
     import isaaclab.envs as ienvs
-    from isaaclab.actuators import DelayedPDActuatorCfg
+    from isaaclab.actuators import DelayedPDActuatorCfg, IdealPDActuatorCfg
     from isaaclab.assets import ArticulationCfg
     from isaaclab.managers import EventTermCfg, ObservationGroupCfg, ObservationTermCfg, RewardTermCfg, SceneEntityCfg, TerminationTermCfg
     from isaaclab.scene import InteractiveSceneCfg
     from isaaclab.utils.noise import AdditiveUniformNoiseCfg as Unoise
 
-    from ._capi import default_config
-    from .env import JOINT_NAMES, REW_FUNC_SLOT, SLOT_BODIES
+    from .env import JOINT_NAMES, REW_FUNC_SLOT, REW_FUNC_SLOT_B, SLOT_BODIES
     from .shims._lenient import Placeholder
 
-    c = default_config()
     mdp = ienvs.mdp
     import isaaclab_tasks  # noqa: F401  (builds the locomotion mdp namespace)
     import isaaclab_tasks.manager_based.locomotion.velocity.mdp as lmdp
@@ -46,10 +68,12 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
             return {k: (v.to_dict() if hasattr(v, "to_dict") else v) for k, v in self.__dict__.items()}
 
     groups = {"legs": [0, 1, 2, 6, 7, 8], "knees": [3, 9], "feet": [4, 5, 10, 11]}
+    delayed = c.max_delay > 0  # A/robots/h12.py:18-114 DelayedPDActuatorCfg (Flat) vs :117-206 IdealPDActuatorCfg (Rsl)
     actuators = {
-        g: DelayedPDActuatorCfg(joint_names_expr=[JOINT_NAMES[i] for i in ids], effort_limit={JOINT_NAMES[i]: c.effort_limit[i] for i in ids},
-                                velocity_limit=(c.joint_vel_limit if c.joint_vel_limit > 0 else None), stiffness={JOINT_NAMES[i]: c.kp[i] for i in ids}, damping={JOINT_NAMES[i]: c.kd[i] for i in ids},
-                                armature=c.dof_armature[6 + ids[0]], friction=0.0, min_delay=c.min_delay, max_delay=c.max_delay)
+        g: (DelayedPDActuatorCfg if delayed else IdealPDActuatorCfg)(
+            joint_names_expr=[JOINT_NAMES[i] for i in ids], effort_limit={JOINT_NAMES[i]: c.effort_limit[i] for i in ids},
+            velocity_limit=(c.joint_vel_limit if c.joint_vel_limit > 0 else None), stiffness={JOINT_NAMES[i]: c.kp[i] for i in ids}, damping={JOINT_NAMES[i]: c.kd[i] for i in ids},
+            armature=c.dof_armature[6 + ids[0]], friction=0.0, **({"min_delay": c.min_delay, "max_delay": c.max_delay} if delayed else {}))
         for g, ids in groups.items()}
     robot = ArticulationCfg(prim_path="{ENV_REGEX_NS}/Robot", init_state=ArticulationCfg.InitialStateCfg(
         pos=(0.0, 0.0, c.init_root_height), joint_pos={JOINT_NAMES[i]: c.default_joint_pos[i] for i in range(12)}, joint_vel={".*": 0.0}),
@@ -58,15 +82,18 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
     object.__setattr__(scene, "robot", robot)
     object.__setattr__(scene, "terrain", Placeholder(terrain_type="plane", physics_material=Placeholder(static_friction=1.0, dynamic_friction=1.0)))
 
-    def obs(func, n=0.0, s=1.0):
-        return ObservationTermCfg(func=func, noise=Unoise(n_min=-n, n_max=n) if n else None, scale=None if s == 1.0 else s)
+    def obs(func, n=0.0, s=1.0, joints=False):
+        t = ObservationTermCfg(func=func, noise=Unoise(n_min=-n, n_max=n) if n else None, scale=None if s == 1.0 else s)
+        if joints and list(c.joint_perm) != [0, 6, 1, 7, 2, 8, 3, 9, 4, 10, 5, 11]:  # not the articulation's own order: name it (C12/rsl_env_cfg.py:148-192)
+            t.params = {"asset_cfg": SceneEntityCfg("robot", joint_names=[JOINT_NAMES[j] for j in c.joint_perm], preserve_order=True)}
+        return t
 
     policy = ObservationGroupCfg(concatenate_terms=True, enable_corruption=bool(c.enable_corruption), history_length=c.history_length)
     for k, v in (("base_ang_vel", obs(mdp.base_ang_vel, c.noise_ang_vel, c.scale_ang_vel)),
                  ("projected_gravity", obs(mdp.projected_gravity, c.noise_gravity, c.scale_gravity)),
                  ("velocity_commands", obs(mdp.generated_commands, 0.0, c.scale_cmd)),
-                 ("joint_pos", obs(mdp.joint_pos_rel, c.noise_joint_pos, c.scale_joint_pos)),
-                 ("joint_vel", obs(mdp.joint_vel_rel, c.noise_joint_vel, c.scale_joint_vel)),
+                 ("joint_pos", obs(mdp.joint_pos_rel, c.noise_joint_pos, c.scale_joint_pos, True)),
+                 ("joint_vel", obs(mdp.joint_vel_rel, c.noise_joint_vel, c.scale_joint_vel, True)),
                  ("actions", obs(mdp.last_action, 0.0, c.scale_action))):
         object.__setattr__(policy, k, v)
     policy.__configclass_fields__ = lambda: ["concatenate_terms", "enable_corruption", "history_length", "base_ang_vel", "projected_gravity",
@@ -85,17 +112,24 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
         "joint_deviation_l1": {"asset_cfg": SceneEntityCfg("robot", joint_names=names(c.mask_joint_dev, JOINT_NAMES))},
         "joint_torques_l2": {"asset_cfg": SceneEntityCfg("robot", joint_names=names(c.mask_torques, JOINT_NAMES))},
         "undesired_contacts": {"sensor_cfg": SceneEntityCfg("contact_forces", body_names=names(c.mask_undesired_slots, SLOT_BODIES)), "threshold": 1.0},
-        "contact_forces": {"sensor_cfg": SceneEntityCfg("contact_forces", body_names=names(c.mask_undesired_slots, SLOT_BODIES)), "threshold": 1.0},
+        "contact_forces": {"sensor_cfg": SceneEntityCfg("contact_forces", body_names=names(c.mask_contact_forces_slots, SLOT_BODIES)), "threshold": c.contact_forces_threshold},
         "base_height_l2": {"target_height": c.base_height_target},
     }
-    slot_func = {s: f for f, s in REW_FUNC_SLOT.items()}
+    rew_params_b = {
+        "joint_pos_limits": {"asset_cfg": SceneEntityCfg("robot", joint_names=names(c.mask_pos_limits_b, JOINT_NAMES))},
+        "joint_deviation_l1": {"asset_cfg": SceneEntityCfg("robot", joint_names=names(c.mask_joint_dev_b, JOINT_NAMES))},
+    }
+    slot_func = {s: (f, rew_params) for f, s in REW_FUNC_SLOT.items()}
+    slot_func.update({s: (f, rew_params_b) for f, s in REW_FUNC_SLOT_B.items()})
     from ._capi import REW_NAMES
     rew = {}
-    for s, w in enumerate(c.rew_weight):
+    for s, w in enumerate(c.rew_weight):  # ascending slots: a function's first slot precedes its second, as reward_slots assigns them
         if w != 0.0:
-            f = slot_func[s]
-            rew[REW_NAMES[s]] = RewardTermCfg(func=getattr(lmdp, f), weight=w, params=rew_params.get(f, {}))
+            f, params = slot_func[s]
+            rew[(rew_names or {}).get(s, REW_NAMES[s])] = RewardTermCfg(func=getattr(lmdp, f), weight=w, params=params.get(f, {}))
     rewards = bag(**rew)
+    cur = bag(**{n: ienvs_managers().CurriculumTermCfg(func=mdp.modify_reward_weight, params={
+        "term_name": n, "weight": rew[n].weight, "num_steps": curriculum_steps}) for n in curriculum}) if curriculum else None
 
     terminations = bag(
         time_out=TerminationTermCfg(func=mdp.time_out, time_out=True),
@@ -103,9 +137,13 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
             "sensor_cfg": SceneEntityCfg("contact_forces", body_names=names(c.mask_illegal_slots, SLOT_BODIES)), "threshold": c.contact_threshold}))
     ranges = ienvs.UniformVelocityCommandCfg.Ranges(lin_vel_x=tuple(c.cmd_lin_x), lin_vel_y=tuple(c.cmd_lin_y), ang_vel_z=tuple(c.cmd_ang_z),
                                                     heading=tuple(c.cmd_heading))
-    commands = bag(base_velocity=ienvs.UniformVelocityCommandCfg(
+    base_velocity = ienvs.UniformVelocityCommandCfg(
         asset_name="robot", resampling_time_range=tuple(c.cmd_resample_time), rel_standing_envs=c.rel_standing_envs, rel_heading_envs=c.rel_heading_envs,
-        heading_command=bool(c.heading_command), heading_control_stiffness=c.heading_stiffness, ranges=ranges))
+        heading_command=bool(c.heading_command), heading_control_stiffness=c.heading_stiffness, ranges=ranges)
+    if c.command_class == 1:  # C12/rsl_env_cfg.py:86-99 UniformVelocityCommandWithDeadzoneCfg
+        object.__setattr__(base_velocity, "class_type", UniformVelocityCommandWithDeadzone)
+        object.__setattr__(base_velocity, "velocity_deadzone", c.velocity_deadzone)
+    commands = bag(base_velocity=base_velocity)
     axes = ["x", "y", "z", "roll", "pitch", "yaw"]
     ev = dict(
         physics_material=EventTermCfg(func=mdp.randomize_rigid_body_material, mode="startup", params={
@@ -126,7 +164,7 @@ def default_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
                                           use_default_offset=True, preserve_order=True)
     cfg = ienvs.ManagerBasedRLEnvCfg(decimation=c.decimation, episode_length_s=c.episode_length_s, scene=scene,
                                      observations=bag(policy=policy), actions=bag(joint_pos=action), rewards=rewards,
-                                     terminations=terminations, commands=commands, events=bag(**ev), curriculum=None)
+                                     terminations=terminations, commands=commands, events=bag(**ev), curriculum=cur)
     cfg.sim.dt = c.sim_dt
     cfg.sim.device = device
     cfg.sim.gravity = (0.0, 0.0, -c.gravity)
@@ -146,16 +184,25 @@ def default_agent_cfg():
                                        max_grad_norm=1.0))
 
 
+def ienvs_managers():
+    import isaaclab.managers as m
+    return m
+
+
 def register() -> bool:
-    """gym.register the Flat id with this package's own entry points unless something registered it already."""
+    """gym.register the Flat and Rsl ids with this package's own entry points unless something registered them already."""
     from . import shims
     shims.install()
     import gymnasium as gym
-    try:
-        gym.spec(TASK_ID)
-        return False
-    except Exception:
-        pass
-    gym.register(id=TASK_ID, entry_point="h1v2_isaac_b200.env:H1v2ManagerBasedRLEnv", disable_env_checker=True,
-                 kwargs={"env_cfg_entry_point": "h1v2_isaac_b200.tasks:default_env_cfg", "rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})
-    return True
+    done = False
+    for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg")):
+        try:
+            gym.spec(tid)
+            continue
+        except Exception:
+            pass
+        # both ids use the same runner cfg (C12/__init__.py:47,91: rsl_rl_ppo_cfg:H12_12dof_FlatPPORunnerCfg)
+        gym.register(id=tid, entry_point="h1v2_isaac_b200.env:H1v2ManagerBasedRLEnv", disable_env_checker=True,
+                     kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}", "rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})
+        done = True
+    return done

@@ -1,6 +1,6 @@
 /*
  * h1v2_b200.h -- C-ABI of the B200-native batched simulation backend for the Unitree H1-2
- * velocity-tracking task  Isaac-Velocity-Flat-H12_12dof-v0.
+ * velocity-tracking tasks  Isaac-Velocity-Flat-H12_12dof-v0  and  Isaac-Velocity-Rsl-H12_12dof-v0.
  *
  * The reference (olivier-stasse/h1v2-Isaac) has no FFI of its own: its seam is the Python
  * ManagerBasedRLEnv.step contract.  Each entry point below names the reference interface it replaces
@@ -14,6 +14,9 @@
  *                            .../velocity/config/h12_12dof/rough_env_cfg.py:18-125,
  *                            .../velocity/velocity_env_cfg.py:86-324,
  *                            packages/biped_assets/biped_assets/robots/h12.py:18-114
+ *   h1v2_rsl_config    <- resolved cfg of the Rsl id
+ *                            .../velocity/config/h12_12dof/rsl_env_cfg.py:44-540, robots/h12.py:117-206
+ *   h1v2_set_reward_weights <- CurriculumManager: mdp.modify_reward_weight   rsl_env_cfg.py:447-497
  *   h1v2_step          <- ManagerBasedRLEnv.step(action)         utils/cat/cat_env.py:95-193
  *   h1v2_step_host     <- same call with HOST buffers (what a non-torch caller binds; used for e2e timing)
  *   h1v2_reset         <- ManagerBasedRLEnv.reset / _reset_idx   utils/cat/cat_env.py:195-248
@@ -39,7 +42,7 @@ extern "C" {
 #endif
 
 #define H1V2_NJ 12           /* actuated joints */
-#define H1V2_NUM_REW 20      /* reward-term slots (union of the cfgs) */
+#define H1V2_NUM_REW 22      /* reward-term slots (union of the Flat / base / Rsl cfgs) */
 #define H1V2_NUM_SLOT 6      /* contact-sensor bodies: 0,1 feet L/R; 2,3 knee_link L/R; 4 torso_link; 5 pelvis */
 #define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
 #define H1V2_MAX_HISTORY 10 /* the reference tasks use 10 (Flat), 6 (Rsl) and 1 (deploy) */
@@ -64,34 +67,36 @@ enum {
   H1V2_REW_TRACK_LIN_XY_BASE = 14, /* track_lin_vel_xy_exp (base frame)           velocity_env_cfg.py:226-230 */
   H1V2_REW_TRACK_ANG_Z_BASE = 15,  /* track_ang_vel_z_exp (base frame)            velocity_env_cfg.py:231-235 */
   H1V2_REW_FEET_AIR_L2 = 16,       /* feet_air_time                               mdp/rewards.py:13-35 */
-  H1V2_REW_JOINT_VEL = 17,         /* joint_vel_l2        (Rsl variant)           rsl_env_cfg.py */
-  H1V2_REW_BASE_HEIGHT = 18,       /* base_height_l2      (Rsl variant)           rsl_env_cfg.py */
-  H1V2_REW_CONTACT_FORCES = 19     /* contact_forces      (Rsl variant)           rsl_env_cfg.py */
+  H1V2_REW_JOINT_VEL = 17,         /* joint_vel_l2                                rsl_env_cfg.py:335-338 */
+  H1V2_REW_BASE_HEIGHT = 18,       /* base_height_l2                              rsl_env_cfg.py:322-328 */
+  H1V2_REW_CONTACT_FORCES = 19,    /* contact_forces (own threshold and bodies)   rsl_env_cfg.py:395-404 */
+  H1V2_REW_DOF_POS_LIMITS_B = 20,  /* second joint_pos_limits term (hips)         rsl_env_cfg.py:380-386 */
+  H1V2_REW_JOINT_DEV_B = 21        /* second joint_deviation_l1 term (ankles)     rsl_env_cfg.py:358-372 */
 };
 
 /* layout of the log vector returned by h1v2_get_log (all float):
  *   [0]                 number of envs reset in the last step that reset anything (count)
  *   [1 .. NUM_REW]      Episode_Reward/<term>   = mean over reset envs of episode_sum / max_episode_length_s
- *   [21], [22]          Episode_Termination/time_out, /base_contact  (counts, as upstream's count_nonzero)
- *   [23], [24]          Metrics/base_velocity/error_vel_xy, error_vel_yaw (mean over reset envs)
- *   [25]                number of envs force-reset by the non-finite-state guard (cumulative)
- *   [26]                max Newton iterations used by any env in the last step
- *   [27]                number of (env,substep) solves that hit the iteration cap in the last step
- *   [28]                total Newton iterations over all (env,substep) solves of the last step
- *   [29]                (leg,substep) pairs of the last step whose contact list overflowed (points beyond 5 are dropped;
+ *   [23], [24]          Episode_Termination/time_out, /base_contact  (counts, as upstream's count_nonzero)
+ *   [25], [26]          Metrics/base_velocity/error_vel_xy, error_vel_yaw (mean over reset envs)
+ *   [27]                number of envs force-reset by the non-finite-state guard (cumulative)
+ *   [28]                max Newton iterations used by any env in the last step
+ *   [29]                number of (env,substep) solves that hit the iteration cap in the last step
+ *   [30]                total Newton iterations over all (env,substep) solves of the last step
+ *   [31]                (leg,substep) pairs of the last step whose contact list overflowed (points beyond 5 are dropped;
  *                       only reachable with shin / torso / pelvis on the ground, i.e. in the step that terminates the env)
  */
 #define H1V2_LOG_COUNT 0
 #define H1V2_LOG_REW0 1
-#define H1V2_LOG_TERM_TIMEOUT 21
-#define H1V2_LOG_TERM_CONTACT 22
-#define H1V2_LOG_ERR_XY 23
-#define H1V2_LOG_ERR_YAW 24
-#define H1V2_LOG_NAN_RESETS 25
-#define H1V2_LOG_MAX_ITERS 26
-#define H1V2_LOG_CAP_HITS 27
-#define H1V2_LOG_SUM_ITERS 28
-#define H1V2_LOG_CONTACT_OVERFLOW 29 /* (leg,substep) pairs of the last step with more penetrating points than the 5-slot list holds */
+#define H1V2_LOG_TERM_TIMEOUT 23
+#define H1V2_LOG_TERM_CONTACT 24
+#define H1V2_LOG_ERR_XY 25
+#define H1V2_LOG_ERR_YAW 26
+#define H1V2_LOG_NAN_RESETS 27
+#define H1V2_LOG_MAX_ITERS 28
+#define H1V2_LOG_CAP_HITS 29
+#define H1V2_LOG_SUM_ITERS 30
+#define H1V2_LOG_CONTACT_OVERFLOW 31 /* (leg,substep) pairs of the last step with more penetrating points than the 5-slot list holds */
 
 typedef struct H1v2Config {
   /* ---- timing (velocity_env_cfg.py:302-305) ---- */
@@ -154,6 +159,15 @@ typedef struct H1v2Config {
   float env_spacing;                   /* 2.5 m grid (velocity_env_cfg.py:288) */
   float joint_vel_limit;               /* actuator velocity_limit (rad/s, robots/h12.py:66,89,103): joint velocities are clamped
                                           to it after every physics step, as PhysX does; <= 0 disables */
+  /* ---- second instances of reward terms a cfg may hold twice, and contact_forces' own parameters (rsl_env_cfg.py:343-404) ---- */
+  uint32_t mask_pos_limits_b, mask_joint_dev_b; /* bit j = MJCF joint j, for H1V2_REW_DOF_POS_LIMITS_B / H1V2_REW_JOINT_DEV_B */
+  uint32_t mask_contact_forces_slots;  /* bit s = sensor slot s */
+  float contact_forces_threshold;      /* N; sum over the bodies of max(0, max_h |F| - threshold) */
+  /* ---- command class (utils/mdp/commands.py:19-96) ---- */
+  int32_t command_class;               /* 0 = UniformVelocityCommand; 1 = UniformVelocityCommandWithDeadzone */
+  float velocity_deadzone;             /* only 0.0 is implemented for class 1 (rsl_env_cfg.py:98): no env is ever "in the dead zone",
+                                          so every step n_envs/2 uniformly chosen envs get their xy command zeroed */
+  float ang_vel_flip_prob;             /* per-step probability of negating the yaw-rate command (commands.py:85-96): physics_dt / episode_length_s */
   float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
                                           non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
   int32_t reserved[8];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
@@ -201,7 +215,8 @@ typedef struct H1v2State {
 
 typedef struct H1v2Handle H1v2Handle;
 
-int h1v2_default_config(H1v2Config* cfg);
+int h1v2_default_config(H1v2Config* cfg); /* resolved cfg of Isaac-Velocity-Flat-H12_12dof-v0 */
+int h1v2_rsl_config(H1v2Config* cfg);     /* resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (config/h12_12dof/rsl_env_cfg.py:503-540) */
 int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t seed, H1v2Handle** out);
 void h1v2_destroy(H1v2Handle* h);
 const char* h1v2_last_error(void);
@@ -223,6 +238,10 @@ int h1v2_step(H1v2Handle* h, const float* actions /*[N,12]*/, float* obs /*[N,ob
 /* Same with HOST buffers (pinned or pageable): H2D of actions and D2H of all outputs inside, synchronises. */
 int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                    uint8_t* truncated);
+
+/* Replace the reward weights (CurriculumManager's modify_reward_weight, rsl_env_cfg.py:447-497).  Host array of
+ * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises. */
+int h1v2_set_reward_weights(H1v2Handle* h, const float* weights);
 
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);

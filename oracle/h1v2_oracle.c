@@ -88,7 +88,7 @@ void h1v2o_rng4(uint64_t seed, int64_t env_gid, uint64_t step, uint32_t stream, 
 #define STREAM_EVENT 3u
 #define STREAM_ACTIONS 7u
 
-static inline float uni(float u, float lo, float hi) { return lo + (hi - lo) * u; }
+static inline float uni(float u, float lo, float hi) { return fmaf(hi - lo, u, lo); } /* fused, like the kernel: draws are bit-identical */
 
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -776,7 +776,20 @@ static void update_command(H1v2Oracle* o, int ei) {
     if (w > c->cmd_ang_z[1]) w = c->cmd_ang_z[1];
     e->cmd[2] = w;
   }
-  if (e->is_standing) e->cmd[0] = e->cmd[1] = e->cmd[2] = 0;
+  if (c->command_class == 0) {
+    if (e->is_standing) e->cmd[0] = e->cmd[1] = e->cmd[2] = 0;
+  } else {
+    /* UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96), velocity_deadzone == 0
+     * (C12/rsl_env_cfg.py:98): standing envs are not zeroed by the override; `norm(cmd_xy) < 0` is false for every env, so
+     * current_deadzone_count == 0 < n // 2 and randperm(n)[: n // 2] of all envs get cmd_xy = 0 on EVERY step (:62-70);
+     * restated per env as an independent draw with the same marginal probability (n // 2) / n.  Then the yaw-rate command
+     * changes sign with probability physics_dt / max_episode_length_s (:85-96). */
+    float u[4];
+    rng4(o->seed, c->env_id_offset + ei, o->step_counter, STREAM_CMD, 4, u);
+    const float dz_prob = (float)(o->n / 2) / (float)o->n;
+    if (u[0] < dz_prob) e->cmd[0] = e->cmd[1] = 0;
+    if (u[1] < c->ang_vel_flip_prob) e->cmd[2] = -e->cmd[2];
+  }
 }
 
 static void compute_obs(H1v2Oracle* o, int ei, float* obs_out) {
@@ -980,6 +993,11 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
       r[H1V2_REW_DOF_POS_LIMITS] += -(lo < 0 ? lo : 0) + (hi > 0 ? hi : 0);
     }
     if ((c->mask_joint_dev >> j) & 1u) r[H1V2_REW_JOINT_DEV_HIP] += fabs(q - c->default_joint_pos[j]);
+    if ((c->mask_pos_limits_b >> j) & 1u) { /* second joint_pos_limits term of a cfg (C12/rsl_env_cfg.py:380-386) */
+      double lo = q - o->soft_lo[j], hi = q - o->soft_hi[j];
+      r[H1V2_REW_DOF_POS_LIMITS_B] += -(lo < 0 ? lo : 0) + (hi > 0 ? hi : 0);
+    }
+    if ((c->mask_joint_dev_b >> j) & 1u) r[H1V2_REW_JOINT_DEV_B] += fabs(q - c->default_joint_pos[j]); /* rsl_env_cfg.py:358-372 */
     if ((c->mask_torques >> j) & 1u) r[H1V2_REW_TORQUES] += e->applied_tau[j] * e->applied_tau[j];
     r[H1V2_REW_DOF_ACC] += e->joint_acc[j] * e->joint_acc[j];
     r[H1V2_REW_JOINT_VEL] += qd * qd;
@@ -991,9 +1009,9 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   r[H1V2_REW_LIN_VEL_Z] = vb[2] * vb[2];
   r[H1V2_REW_BASE_HEIGHT] = (e->qpos[2] - c->base_height_target) * (e->qpos[2] - c->base_height_target);
   for (int s = 0; s < NSLOT; s++) {
-    if ((c->mask_undesired_slots >> s) & 1u) {
-      r[H1V2_REW_UNDESIRED_CONTACTS] += (float)Cmax[s] > c->contact_threshold;
-      double ex = Cmax[s] - c->contact_threshold;
+    if ((c->mask_undesired_slots >> s) & 1u) r[H1V2_REW_UNDESIRED_CONTACTS] += (float)Cmax[s] > c->contact_threshold;
+    if ((c->mask_contact_forces_slots >> s) & 1u) { /* contact_forces: sum_b clip(max_h |F_b| - threshold, min 0) (rsl_env_cfg.py:395-404) */
+      double ex = Cmax[s] - c->contact_forces_threshold;
       r[H1V2_REW_CONTACT_FORCES] += ex > 0 ? ex : 0;
     }
   }
@@ -1232,6 +1250,7 @@ int h1v2o_set_state(H1v2Oracle* o, const H1v2State* s) {
 }
 int h1v2o_get_episode_length(H1v2Oracle* o, int64_t* out) { for (int i = 0; i < o->n; i++) out[i] = o->env[i].ep_len; return 0; }
 int h1v2o_set_episode_length(H1v2Oracle* o, const int64_t* in) { for (int i = 0; i < o->n; i++) o->env[i].ep_len = in[i]; return 0; }
+int h1v2o_set_reward_weights(H1v2Oracle* o, const float* w) { for (int t = 0; t < NREW; t++) o->cfg.rew_weight[t] = w[t]; return 0; }
 int h1v2o_get_log(H1v2Oracle* o, float* out) { memcpy(out, o->log, sizeof(o->log)); return 0; }
 /* smallest distance to a contact / joint-limit activation boundary seen at a substep start during the last step:
  * envs within rounding error of a boundary are excluded from strict float-vs-double comparisons (tests) */

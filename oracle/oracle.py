@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         L.h1v2o_get_episode_length.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_set_episode_length.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_get_log.argtypes = [C.c_void_p, C.c_void_p]
+        L.h1v2o_set_reward_weights.argtypes = [C.c_void_p, C.c_void_p]
         L.h1v2o_solver_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.h1v2o_activation_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.h1v2o_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -160,6 +161,11 @@ class Oracle:
     def episode_length(self, v):
         a = np.ascontiguousarray(v, dtype=np.int64)
         lib().h1v2o_set_episode_length(self._h, _p(a))
+
+    def set_reward_weights(self, w):
+        a = np.ascontiguousarray(w, dtype=np.float32)
+        assert a.size == len(self.cfg.rew_weight)
+        lib().h1v2o_set_reward_weights(self._h, _p(a))
 
     def log(self) -> np.ndarray:
         out = np.zeros(LOG_DIM, np.float32)

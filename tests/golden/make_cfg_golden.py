@@ -1,6 +1,7 @@
-"""Generate tests/golden/flat_cfg_resolved.json: the reference's OWN resolved cfg tree of Isaac-Velocity-Flat-H12_12dof-v0
-(packages/biped_tasks/.../config/h12_12dof/flat_env_cfg.py:13-48 and parents, robot from biped_assets/robots/h12.py:18-114),
-imported from /root/reference through the isaaclab shims and flattened by h1v2_isaac_b200.env.flatten_cfg.
+"""Generate tests/golden/flat_cfg_resolved.json and rsl_cfg_resolved.json: the reference's OWN resolved cfg trees of
+Isaac-Velocity-Flat-H12_12dof-v0 (packages/biped_tasks/.../config/h12_12dof/flat_env_cfg.py:13-48 and parents, robot from
+biped_assets/robots/h12.py:18-114) and Isaac-Velocity-Rsl-H12_12dof-v0 (.../config/h12_12dof/rsl_env_cfg.py:44-540, robot
+h12.py:117-206), imported from /root/reference through the isaaclab shims and flattened by h1v2_isaac_b200.env.flatten_cfg.
 Run in the build container (the reference is not on the GPU box):  python tests/golden/make_cfg_golden.py"""
 import json
 import os
@@ -13,12 +14,13 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "h1v2_isaac_b200", "shims"), os.path.jo
 import biped_tasks.tasks  # noqa: E402,F401  (runs the reference's gym.register calls)
 from isaaclab_tasks.utils import load_cfg_from_registry  # noqa: E402
 
-from h1v2_isaac_b200.env import config_to_dict, flatten_cfg  # noqa: E402
+from h1v2_isaac_b200.env import config_to_dict, curriculum_schedule, flatten_cfg, reward_slots  # noqa: E402
 
-TASK = "Isaac-Velocity-Flat-H12_12dof-v0"
-env_cfg = load_cfg_from_registry(TASK, "env_cfg_entry_point")
-agent_cfg = load_cfg_from_registry(TASK, "rsl_rl_cfg_entry_point")
-out = {"task": TASK, "num_envs": env_cfg.scene.num_envs, "kernel_config": config_to_dict(flatten_cfg(env_cfg)), "agent": agent_cfg.to_dict()}
-with open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json"), "w") as f:
-    json.dump(out, f, indent=1, sort_keys=True)
-print("wrote flat_cfg_resolved.json")
+for TASK, name in (("Isaac-Velocity-Flat-H12_12dof-v0", "flat_cfg_resolved.json"), ("Isaac-Velocity-Rsl-H12_12dof-v0", "rsl_cfg_resolved.json")):
+    env_cfg = load_cfg_from_registry(TASK, "env_cfg_entry_point")
+    agent_cfg = load_cfg_from_registry(TASK, "rsl_rl_cfg_entry_point")
+    out = {"task": TASK, "num_envs": env_cfg.scene.num_envs, "kernel_config": config_to_dict(flatten_cfg(env_cfg)), "agent": agent_cfg.to_dict(),
+           "reward_slots": reward_slots(env_cfg), "curriculum": curriculum_schedule(env_cfg)}
+    with open(os.path.join(ROOT, "tests", "golden", name), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("wrote", name)

@@ -11,6 +11,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json")))
+GOLD_RSL = json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json")))
 has_ref = os.path.isdir(os.path.join(REF, "packages", "biped_tasks"))
 
 
@@ -28,6 +29,37 @@ def test_default_config_equals_reference_cfg_golden(cfg):
     assert set(mine) == set(gold)
     for k in gold:
         assert _close(mine[k], gold[k]), k
+
+
+def test_rsl_config_equals_reference_cfg_golden():
+    """h1v2_rsl_config (C restatement of config/h12_12dof/rsl_env_cfg.py:44-540) == the reference's Rsl cfg tree, value by value;
+    the 12 modify_reward_weight curriculum terms (:447-497) target the weights the terms already have."""
+    from h1v2_isaac_b200._capi import rsl_config
+    from h1v2_isaac_b200.env import config_to_dict
+    mine = config_to_dict(rsl_config())
+    gold = GOLD_RSL["kernel_config"]
+    assert set(mine) == set(gold)
+    for k in gold:
+        assert _close(mine[k], gold[k]), k
+    assert mine["history_length"] == 6 and mine["command_class"] == 1 and mine["max_delay"] == 0
+    assert len(GOLD_RSL["curriculum"]) == 12
+    for slot, weight, num_steps in GOLD_RSL["curriculum"]:
+        assert num_steps == 24 * 5000 and _close(weight, mine["rew_weight"][slot])
+
+
+def test_self_contained_rsl_task_roundtrip():
+    """tasks.rsl_env_cfg() inverts flatten_cfg on the Rsl config, with the reference's term names, slots and curriculum."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200._capi import rsl_config
+    from h1v2_isaac_b200.env import config_to_dict, curriculum_schedule, flatten_cfg, reward_slots
+    tree = tasks.rsl_env_cfg(32)
+    assert config_to_dict(flatten_cfg(tree)) == config_to_dict(rsl_config())
+    assert reward_slots(tree) == GOLD_RSL["reward_slots"]
+    mine, gold = sorted(map(list, curriculum_schedule(tree))), sorted(GOLD_RSL["curriculum"])
+    assert len(mine) == len(gold) and all(_close(a, b) for a, b in zip(mine, gold))
+    tasks.register()
+    import gymnasium as gym
+    assert gym.spec(tasks.RSL_TASK_ID).kwargs["env_cfg_entry_point"]
 
 
 def test_self_contained_task_roundtrip(cfg):
@@ -59,6 +91,18 @@ def test_unsupported_cfg_is_rejected_loudly():
     tree.scene.robot.actuators["knees"].max_delay = 2
     with pytest.raises(NotImplementedError, match="min_delay"):
         flatten_cfg(tree)
+    tree = tasks.rsl_env_cfg(8)
+    tree.commands.base_velocity.velocity_deadzone = 0.1  # a positive dead zone balances a per-process count of envs: not in the kernel
+    with pytest.raises(NotImplementedError, match="velocity_deadzone"):
+        flatten_cfg(tree)
+    tree = tasks.rsl_env_cfg(8)
+    tree.curriculum.feet_slide.func = tree.rewards.feet_slide.func  # anything but modify_reward_weight
+    with pytest.raises(NotImplementedError, match="curriculum.feet_slide"):
+        flatten_cfg(tree)
+    tree = tasks.rsl_env_cfg(8)
+    tree.observations.policy.joint_vel.params = {}  # articulation order while the action term preserves the MJCF order
+    with pytest.raises(NotImplementedError, match="joint order"):
+        flatten_cfg(tree)
 
 
 def test_env_fails_loudly_without_cuda():
@@ -78,6 +122,7 @@ def test_reference_cfg_tree_flattens_to_golden():
     assert out.returncode == 0, out.stderr[-2000:]
     again = json.load(open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json")))
     assert again == GOLD  # regenerating from the reference changes nothing
+    assert json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json"))) == GOLD_RSL
 
 
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
@@ -100,8 +145,9 @@ def test_unmodified_train_py_reaches_the_backend(tmp_path):
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
 def test_reference_variants_are_accepted_or_refused_by_name():
     """Which of the reference's H1-2 12-dof ids the backend takes: Flat and Flat-Play flatten, also with the
-    H12_12DOF_IDEAL robot (IdealPD -> no delay line); CaT (constraint manager), Rsl (reward-weight curriculum) and Rough
-    (height scan, base_lin_vel) are refused with the name of the offending cfg entry, never approximated."""
+    H12_12DOF_IDEAL robot (IdealPD -> no delay line), and so do Rsl and Rsl-Play (dead-zone command class, second joint-set
+    terms, modify_reward_weight curriculum); CaT (constraint manager) and Rough (height scan, base_lin_vel) are refused with
+    the name of the offending cfg entry, never approximated."""
     code = r'''
 import gymnasium as gym
 import biped_tasks.tasks
@@ -110,10 +156,10 @@ from biped_assets.robots.h12 import H12_12DOF_IDEAL
 from h1v2_isaac_b200.env import flatten_cfg
 out = {}
 for tid in ("Isaac-Velocity-Flat-H12_12dof-v0", "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-v0",
-            "Isaac-Velocity-Rsl-H12_12dof-v0", "Isaac-Velocity-Rough-H12_12dof-v0"):
+            "Isaac-Velocity-Rsl-H12_12dof-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-Rough-H12_12dof-v0"):
     cfg = load_cfg_from_registry(tid, "env_cfg_entry_point")
     try:
-        c = flatten_cfg(cfg); out[tid] = "ok corruption=%d" % c.enable_corruption
+        c = flatten_cfg(cfg); out[tid] = "ok corruption=%d" % c.enable_corruption + (" class=%d H=%d" % (c.command_class, c.history_length) if "Rsl" in tid else "")
     except NotImplementedError as e:
         out[tid] = "refused: " + str(e)[:40]
 cfg = load_cfg_from_registry("Isaac-Velocity-Flat-H12_12dof-v0", "env_cfg_entry_point")
@@ -131,7 +177,8 @@ import json; print("RESULT" + json.dumps(out))
     assert res["Isaac-Velocity-Flat-H12_12dof-Play-v0"] == "ok corruption=0"
     assert res["ideal"] == "ok delays 0 0"
     assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"].startswith("refused: constraints")
-    assert res["Isaac-Velocity-Rsl-H12_12dof-v0"].startswith("refused: curriculum")
+    assert res["Isaac-Velocity-Rsl-H12_12dof-v0"] == "ok corruption=1 class=1 H=6"
+    assert res["Isaac-Velocity-Rsl-H12_12dof-Play-v0"] == "ok corruption=0 class=1 H=6"
     assert res["Isaac-Velocity-Rough-H12_12dof-v0"].startswith("refused: ")  # terrain curriculum, height scan, base_lin_vel
 
 

@@ -41,6 +41,51 @@ def test_env_contract_matches_backend():
     env.close(); sim.close()
 
 
+def test_rsl_task_env_and_curriculum(tmp_path):
+    """Isaac-Velocity-Rsl-H12_12dof-v0 through gym.make: 6 x 45 observation, the reference's 16 reward
+    term names in extras["log"], PPO runs; a modify_reward_weight curriculum term (C12/rsl_env_cfg.py:447-497) changes the
+    kernel's weight exactly when common_step_counter passes num_steps, and the step reward follows it."""
+    import torch
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200._capi import REW_NAMES
+    tasks.register()
+    import gymnasium as gym
+    n = 256
+    tree = tasks.rsl_env_cfg(n)
+    tree.curriculum.base_height_l2.params.update(weight=-50.0, num_steps=3)  # the shipped terms re-set the weight they already have
+    env = gym.make(tasks.RSL_TASK_ID, cfg=tree)
+    twin = gym.make(tasks.RSL_TASK_ID, cfg=tasks.rsl_env_cfg(n))  # same seed, shipped (no-op) curriculum
+    obs, _ = env.reset(); twin.reset()
+    assert obs["policy"].shape == (n, 270) and env.single_observation_space["policy"].shape == (270,)
+    slot = REW_NAMES.index("base_height_l2")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(1, 7):
+        a = 0.3 * torch.randn((n, 12), device="cuda", generator=g)
+        _, r1, _, _, extras = env.step(a)
+        _, r2, _, _, _ = twin.step(a)
+        # counter k: `counter > 3` first holds after step 4, so steps 1..4 ran with the old weight and 5.. with the new one
+        assert env.sim.cfg.rew_weight[slot] == (-50.0 if k >= 4 else pytest.approx(-0.2))
+        if k <= 4:
+            assert torch.equal(r1, r2)
+        else:
+            assert (r1 < r2).float().mean() > 0.9  # (z - 1.0)^2 penalised 250x harder
+    names = {k.split("/", 1)[1] for k in extras["log"] if k.startswith("Episode_Reward/")}
+    assert names == {"track_lin_vel_xy_exp", "track_ang_vel_z_exp", "feet_air_time", "feet_slide", "flat_orientation", "base_height_l2",
+                     "joint_torques_l2", "joint_vel_l2", "dof_acc_l2", "joint_deviation_hip", "joint_deviation_ankle", "joint_pos_limits_ankle",
+                     "joint_pos_limits_hip", "action_rate_l2", "contact_forces", "termination_penalty"}
+    twin.close()
+    from isaaclab_rl.rsl_rl import RslRlVecEnvWrapper
+    from rsl_rl.runners import OnPolicyRunner
+    agent = tasks.default_agent_cfg()
+    wrapped = RslRlVecEnvWrapper(env)
+    assert wrapped.num_obs == 270
+    runner = OnPolicyRunner(wrapped, agent.to_dict(), log_dir=str(tmp_path), device="cuda:0")
+    runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+    for p in runner.alg.policy.parameters():
+        assert torch.isfinite(p).all()
+    env.close()
+
+
 def test_rsl_rl_ppo_runs_on_the_backend(tmp_path):
     """RslRlVecEnvWrapper(env) -> OnPolicyRunner.learn: 2 PPO iterations, finite losses, checkpoint written."""
     import torch
@@ -120,7 +165,7 @@ def test_envs_per_warp_mapping_is_bit_identical(cfg):
 
 def test_contact_list_overflow_is_reported(cfg):
     """Robots pushed into the ground put more than 5 points of a leg in contact: the kernel keeps the first 5 and
-    reports the event in log[29] instead of hiding it."""
+    reports the event in log[H1V2_LOG_CONTACT_OVERFLOW] instead of hiding it."""
     import torch
     from h1v2_isaac_b200._capi import LOG_CONTACT_OVERFLOW
     from h1v2_isaac_b200.backend import H1v2Sim

@@ -6,6 +6,7 @@ states and actions (BASELINE.json north_star (a)(b)(c)):
 plus size-independent properties at BASELINE's full sizes (4096 / 32768 envs).
 """
 import numpy as np
+from h1v2_isaac_b200._capi import LOG_NAN_RESETS
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -92,18 +93,18 @@ def test_physics_parity_from_identical_states(cfg, decimation, action_scale):
 
 def test_tail_parity_on_identical_states(cfg):
     """(a)+(b): the oracle's physics loop is replaced by the kernel's own post-physics values, so everything after the
-    physics -- contact-sensor logic, terminations, 20 reward terms, reset, command resampling, noisy observation with
+    physics -- contact-sensor logic, terminations, the reward terms, reset, command resampling, noisy observation with
     history -- is compared on identical inputs: masks bit-exact, values to 1e-5."""
     _tail_parity(cfg, 4096, 60, 100)
 
 
 def test_tail_parity_ideal_pd_and_union_rewards(cfg):
     """Same check on the H12_12DOF_IDEAL actuator variant (IdealPD: no delay line, A/robots/h12.py:117-206) with every
-    one of the 20 reward slots switched on (the union of the H1-2 cfgs), history 6 and the Rsl observation
+    one of the 22 reward slots switched on (the union of the H1-2 cfgs), history 6 and the Rsl observation
     scales (C12/rsl_env_cfg.py) -- the configuration space flatten_cfg can produce beyond the Flat id's defaults."""
     c = cfg.copy()
     c.min_delay = c.max_delay = 0
-    for t in range(20):
+    for t in range(len(c.rew_weight)):
         if c.rew_weight[t] == 0.0:
             c.rew_weight[t] = -0.01 * (t + 1)
     c.history_length = 6
@@ -113,14 +114,36 @@ def test_tail_parity_ideal_pd_and_union_rewards(cfg):
     _tail_parity(c, 2048, 30, 30, min_term=0)  # action scale 0.25: nobody falls within 30 steps
 
 
-def _tail_parity(cfg, n, steps, min_events, min_term=None):
+def test_tail_parity_rsl_task():
+    """the resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (C12/rsl_env_cfg.py:44-540; tests/golden/
+    rsl_cfg_resolved.json pins it to the reference's own cfg classes): IdealPD, action scale 0.25, history 6, scaled gyro / joint
+    velocity, 16 reward terms incl. the second joint-set instances and contact_forces at 800 N, per-env friction 0.1..1.25, and
+    the dead-zone command class (T/utils/mdp/commands.py:41-96) whose zeroing / sign-flip masks must be bit-exact.  Half way
+    through, the reward weights are replaced through h1v2_set_reward_weights (the curriculum's modify_reward_weight path)."""
+    from h1v2_isaac_b200._capi import rsl_config
+    c = rsl_config()
+    assert c.command_class == 1 and c.history_length == 6
+    w2 = [w * (1.5 if i % 2 else 0.5) for i, w in enumerate(c.rew_weight)]
+    stats = _tail_parity(c, 2048, 40, 20, min_term=0, reweight=(20, w2))
+    # C12/rsl_env_cfg.py:98 velocity_deadzone = 0.0: every step half of ALL envs lose their xy command, so a command survives
+    # k steps with probability 2^-k -- the task as configured is in-place stepping and turning
+    assert stats["xy_zero_frac"][0] > 0.4 and stats["xy_zero_frac"][5] > 0.95 and stats["xy_zero_frac"][-1] > 0.99
+    assert stats["yaw_flips"] > 0
+
+
+def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
+    from h1v2_isaac_b200._capi import LOG_ERR_XY, LOG_REW0, LOG_TERM_CONTACT, LOG_TERM_TIMEOUT, NUM_REW
     torch, sim, orc = _mk(cfg, n, 21)
     sim.observe(); orc.observe()
     ep = np.random.default_rng(1).integers(0, 1000, n)  # rsl_rl's init_at_random_ep_len: exercises time-outs
     sim.episode_length_buf.copy_(torch.from_numpy(ep).cuda()); orc.episode_length = ep
     rng = np.random.default_rng(2)
     n_term = n_trunc = n_resample = 0
+    stats = {"xy_zero_frac": [], "yaw_flips": 0}
+    prev = _np(sim.get_state(["time_left", "command"]))
     for step in range(steps):
+        if reweight is not None and step == reweight[0]:
+            sim.set_reward_weights(reweight[1]); orc.set_reward_weights(reweight[1])
         a = (rng.normal(size=(n, 12)) * (0.3 if step % 3 else 1.0)).astype(np.float32)
         og, rg, tg, ug = sim.step(torch.from_numpy(a).cuda())
         g = _np(sim.get_state(SYNC + POST + ["reward_terms"]))
@@ -141,15 +164,24 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None):
         np.testing.assert_allclose(og, oo, rtol=1e-5, atol=2e-6, err_msg=f"observation, step {step}")
         for k in ("command", "heading_target", "cmd_metrics", "episode_sums", "root_pos", "root_quat", "joint_pos", "target_hist"):
             np.testing.assert_allclose(g[k], o[k], rtol=1e-5, atol=2e-6, err_msg=f"{k}, step {step}")
-        n_term += int(to.sum()); n_trunc += int(uo.sum()); n_resample += int((g["time_left"] > 9.97).sum())
+        resampled = g["time_left"][:, 0] > prev["time_left"][:, 0]  # natural resamples and those of resets
+        n_term += int(to.sum()); n_trunc += int(uo.sum()); n_resample += int(resampled.sum())
+        if cfg.command_class == 1:  # dead-zone class: the zeroing and sign-flip draws are masks, compare them exactly
+            assert np.array_equal(g["command"], o["command"]), f"dead-zone command, step {step}"
+            stats["xy_zero_frac"].append(float(((g["command"][:, 0] == 0) & (g["command"][:, 1] == 0)).mean()))
+            same = ~(to | uo | resampled) & (prev["command"][:, 2] != 0)
+            stats["yaw_flips"] += int((g["command"][same, 2] == -prev["command"][same, 2]).sum())
+            assert np.all(np.abs(g["command"][same, 2]) == np.abs(prev["command"][same, 2]))
         lg, lo = sim.log_host(), orc.log()
-        assert lg[0] == lo[0] and lg[21] == lo[21] and lg[22] == lo[22]  # reset / time_out / base_contact counts
+        assert lg[0] == lo[0] and lg[LOG_TERM_TIMEOUT] == lo[LOG_TERM_TIMEOUT] and lg[LOG_TERM_CONTACT] == lo[LOG_TERM_CONTACT]  # reset counts
         if lo[0] > 0:
-            np.testing.assert_allclose(lg[1:21], lo[1:21], rtol=2e-4, atol=1e-6)  # Episode_Reward/* (float atomics)
-            np.testing.assert_allclose(lg[23:25], lo[23:25], rtol=2e-4, atol=1e-6)
+            np.testing.assert_allclose(lg[LOG_REW0:LOG_REW0 + NUM_REW], lo[LOG_REW0:LOG_REW0 + NUM_REW], rtol=2e-4, atol=1e-6)  # Episode_Reward/* (float atomics)
+            np.testing.assert_allclose(lg[LOG_ERR_XY:LOG_ERR_XY + 2], lo[LOG_ERR_XY:LOG_ERR_XY + 2], rtol=2e-4, atol=1e-6)
+        prev = {"time_left": g["time_left"], "command": g["command"]}
         _resync(sim, orc, g)
-    print(f"terminated {n_term}, truncated {n_trunc}, command resamples {n_resample}")
+    print(f"terminated {n_term}, truncated {n_trunc}, command resamples {n_resample}", {k: (v if not isinstance(v, list) else v[:8]) for k, v in stats.items()})
     assert n_term >= (min_events if min_term is None else min_term) and n_trunc > min_events and n_resample > min_events
+    return stats
 
 
 def test_bounded_divergence_over_1000_steps(cfg):
@@ -172,7 +204,7 @@ def test_bounded_divergence_over_1000_steps(cfg):
             dq.append(float(np.median(np.abs(g["joint_pos"] - o["joint_pos"]).max(1))))
     g = _np(sim.get_state(PHYS))
     assert all(np.isfinite(v).all() for v in g.values())
-    assert sim.log_host()[25] == 0  # no non-finite force-resets
+    assert sim.log_host()[LOG_NAN_RESETS] == 0  # no non-finite force-resets
     print("median max-joint divergence after 1/5/25/100 steps:", dq, " mean reward/step gpu", rg_sum / 1000, "oracle", ro_sum / 1000)
     assert dq[0] < 1e-5 and dq[1] < 1e-4
     assert abs(rg_sum - ro_sum) / 1000 < 0.05 * max(abs(ro_sum) / 1000, 0.01) + 0.02
@@ -232,7 +264,7 @@ def test_full_size_properties(cfg, n):
     obs_b, rew_b, ep_b, _ = run(0, n)
     assert all(torch.equal(x, y) for x, y in zip(obs_a, obs_b)) and all(torch.equal(x, y) for x, y in zip(rew_a, rew_b))
     assert all(torch.isfinite(x).all() for x in obs_a) and all(torch.isfinite(x).all() for x in rew_a)
-    assert lg[25] == 0
+    assert lg[LOG_NAN_RESETS] == 0
     # history shift: for envs that did not reset, block[h] at step t+1 equals block[h+1] at step t
     off = [0, 3, 6, 9, 21, 33, 45]
     alive = ep_a > 1
@@ -369,4 +401,4 @@ def test_low_friction_is_bounded(cfg):
     frac = float((e > 5e-3).mean())
     print(f"mu~0.1: {len(e)} env-steps, {100 * frac:.3f} % beyond 5e-3 rad/s, q99 {np.quantile(e, 0.99):.2e}")
     assert frac < 1e-3 and np.quantile(e, 0.99) < 5e-3  # measured 2e-4 with the 30-iteration cap (1.8e-3 with 12)
-    assert sim.log_host()[25] == 0
+    assert sim.log_host()[LOG_NAN_RESETS] == 0

@@ -14,4 +14,4 @@ for i in range(600):
     o, r, t, u = sim.step(a)
     bad += int((~torch.isfinite(o)).sum()) + int((~torch.isfinite(r)).sum())
     mx = max(mx, float(o[torch.isfinite(o)].abs().max())); rmin = min(rmin, float(r.min()))
-    if i % 100 == 99: print(i, "non-finite so far", bad, "max |obs|", mx, "min rew", rmin, "nan resets", sim.log_host()[25])
+    if i % 100 == 99: print(i, "non-finite so far", bad, "max |obs|", mx, "min rew", rmin, "nan resets", sim.log_host()[27])

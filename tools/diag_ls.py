@@ -19,5 +19,5 @@ for cap in (12, 6, 4, 3, 2):
     e1.record(); torch.cuda.synchronize()
     h = sim.iter_hist() - h0; frac = h / h.sum(); mean = (frac * np.arange(32)).sum()
     cdf = np.cumsum(frac); emax = ((cdf ** 16)[1:] - (cdf ** 16)[:-1]) @ np.arange(1, 32)
-    print(f"ls cap {cap:2d}: {e0.elapsed_time(e1)/100:.4f} ms/step  mean iters {mean:.3f}  E[max16] {emax:.2f}  cap hits {sim.log_host()[27]:.0f}  hist {frac[:9].round(3)}")
+    print(f"ls cap {cap:2d}: {e0.elapsed_time(e1)/100:.4f} ms/step  mean iters {mean:.3f}  E[max16] {emax:.2f}  cap hits {sim.log_host()[29]:.0f}  hist {frac[:9].round(3)}")
     sim.close()

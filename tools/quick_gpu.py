@@ -18,6 +18,6 @@ for n in (4096, 32768):
     for i in range(K): sim.step_into(acts[i % 8], obs, rew, term, trunc)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
-    print(f"n={n}: {ms:.4f} ms/step -> {n / ms * 1e3 / 1e6:.2f} M env-steps/s", "log", sim.log_host()[[0, 22, 25, 26, 27]], "rew mean", rew.mean().item())
+    print(f"n={n}: {ms:.4f} ms/step -> {n / ms * 1e3 / 1e6:.2f} M env-steps/s", "log", sim.log_host()[[0, 24, 27, 28, 29]], "rew mean", rew.mean().item())
     hst = sim.iter_hist(); print("  iteration histogram (fraction):", (hst / hst.sum()).round(4)[:14])
     sim.close()

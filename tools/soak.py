@@ -17,17 +17,17 @@ half = {}
 for i in range(steps):
     if i == steps // 2:
         torch.cuda.synchronize()
-        half = dict(bad=int(bad), nterm=int(nterm), resets=float(sim.log_host()[25]), cap=int(capsum), ovf=int(ovf))
+        half = dict(bad=int(bad), nterm=int(nterm), resets=float(sim.log_host()[27]), cap=int(capsum), ovf=int(ovf))
     a = pool[i % 64] * (3.0 if i >= steps // 2 else 1.0)
     sim.step_into(a, obs, rew, term, trunc)
     bad += (~torch.isfinite(obs)).sum() + (~torch.isfinite(rew)).sum()
     maxabs = torch.maximum(maxabs, obs.abs().max())
     nterm += term.sum(); ntrunc += trunc.sum()
-    capsum += sim.log_buf[27]; ovf += sim.log_buf[29]
+    capsum += sim.log_buf[29]; ovf += sim.log_buf[31]
 torch.cuda.synchronize()
 lg = sim.log_host()
 print(f"{steps} steps x {n} envs = {steps*n/1e6:.0f} M env-steps in {time.time()-t0:.1f} s (with per-step finiteness checks)")
 print(f"first half (N(0,1) actions): non-finite {half['bad']}, terminations {half['nterm']}, runaway resets {half['resets']:.0f}, Newton-cap hits {half['cap']} of {steps*n*2} solves, overflows {half['ovf']}")
 print(f"whole run (second half: 3x action scale) --")
 print(f"non-finite outputs: {int(bad)}  max |obs|: {float(maxabs):.1f}  terminations: {int(nterm)}  time-outs: {int(ntrunc)}")
-print(f"runaway/non-finite force-resets (cumulative): {lg[25]:.0f}  Newton-cap hits: {int(capsum)} of {steps*n*4} solves  contact-list overflows: {int(ovf)}")
+print(f"runaway/non-finite force-resets (cumulative): {lg[27]:.0f}  Newton-cap hits: {int(capsum)} of {steps*n*4} solves  contact-list overflows: {int(ovf)}")

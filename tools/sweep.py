@@ -31,7 +31,7 @@ for randomize in (False, True):
         ms = sum(a.elapsed_time(b) for a, b in ev) / K
         lg = sim.log_host()
         rows.append({"envs": n, "randomised": randomize, "ms_per_step": round(ms, 4), "env_steps_per_s": round(n / ms * 1e3),
-                     "mean_newton_iters": round(float(lg[28]) / (4 * n), 3), "nan_resets_total": float(lg[25])})
+                     "mean_newton_iters": round(float(lg[30]) / (4 * n), 3), "nan_resets_total": float(lg[27])})
         print(rows[-1], file=sys.stderr)
         sim.close()
 print(json.dumps({"gpu": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
