@@ -24,9 +24,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec"
 # algorithmic HBM bytes per env-step of the fused kernel: action 48, root r+w 128, leg 192,
-# actuator line 320, command 64, timers 64, warm start 192, episode sums 160, episode length 16,
-# history read 9x180=1620 + write 180, obs write 1800, reward+flags 6
-ALGO_BYTES_PER_ENV_STEP = 4790
+# actuator line 320, command 64, timers 64, warm start 192, episode sums 192, episode length 16, reward+flags 6 = 1222,
+# plus per history slot H: ring read (H-1)x180 + ring write 180 + observation write 180 H = 360 H  (H = 10: 4822)
+def algo_bytes_per_env_step(history: int) -> int:
+    return 1222 + 360 * history
+
+
+TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-H12_12dof-v0"}
 
 
 def parse():
@@ -36,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1] = 4096; configs[3] = 32768)")
+    ap.add_argument("--task", default="flat", choices=sorted(TASKS), help="flat = BASELINE's metric config (default); rsl = the SURVEY 8(f)1 variant, same kernel")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -135,14 +140,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from h1v2_isaac_b200._capi import default_config
-    cfg = default_config()
+    from h1v2_isaac_b200._capi import default_config, rsl_config
+    cfg = rsl_config() if args.task == "rsl" else default_config()
     cb = cpu_baseline(cfg, args.seed, steps=max(1, args.steps) if args.steps <= 50 else None, warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": cb["steps"],
         "warmup": max(1, min(args.warmup, 3)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Isaac-Velocity-Flat-H12_12dof-v0 physics+obs+reward step, random actions, CPU restatement of the MuJoCo sim2sim path (bounded sample)",
+        "config": {"workload": TASKS[args.task] + " physics+obs+reward step, random actions, CPU restatement of the MuJoCo sim2sim path (bounded sample)",
                    "envs_per_step": cb["n_envs"], "decimation": 4, "sim_dt": 0.005},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,7 +185,8 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     n = args.envs
-    cfg = default_config()
+    cfg = _capi.rsl_config() if args.task == "rsl" else default_config()
+    ALGO_BYTES_PER_ENV_STEP = algo_bytes_per_env_step(cfg.history_length)
     cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     W, K = max(args.warmup, 3), args.steps
@@ -275,8 +281,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Isaac-Velocity-Flat-H12_12dof-v0 physics+obs+reward step, {n} envs/GPU, random N(0,1) actions (BASELINE configs[1] when 4096)",
-                   "envs_per_gpu": n, "decimation": 4, "sim_dt": 0.005, "history": 10, "obs_dim": sim.obs_dim, "parallelism": f"env-shard x{world}",
+        "config": {"workload": f"{TASKS[args.task]} physics+obs+reward step, {n} envs/GPU, random N(0,1) actions" + (" (BASELINE configs[1] when 4096)" if args.task == "flat" else " (SURVEY 8(f)1 variant; not BASELINE's metric config)"),
+                   "envs_per_gpu": n, "decimation": 4, "sim_dt": 0.005, "history": int(cfg.history_length), "obs_dim": sim.obs_dim, "parallelism": f"env-shard x{world}",
                    "l2": "flushed between timed steps (256 MiB write, untimed); per-step CUDA events summed"},
         "clocks": clocks,
         "e2e": e2e,

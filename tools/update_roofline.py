@@ -13,8 +13,10 @@ rd = f("dram__bytes_read.sum") * scale[u["dram__bytes_read.sum"]]; wr = f("dram_
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 path = os.path.join(root, "profiles", "roofline.json")
 d = json.load(open(path))
+dram = dict(d.get("dram_bytes_per_launch", {})); dram[str(n)] = round(rd + wr)  # one entry per profiled env count
+wi = dict(d.get("warp_instructions_per_env_step", {})); wi[str(n)] = round(f("smsp__inst_executed.sum") / n, 1)
 d.update({"fp32_flops_executed_per_env_step": round((2 * ffma + fadd + fmul) / n), "profile": tag, "profile_n_envs": n,
-          "dram_bytes_per_launch": {str(n): round(rd + wr)}, "dram_read_write_MB": [round(rd / 1e6, 1), round(wr / 1e6, 1)],
+          "dram_bytes_per_launch": dram, "warp_instructions_per_env_step": wi, "dram_read_write_MB": [round(rd / 1e6, 1), round(wr / 1e6, 1)],
           "kernel_time_under_ncu_us": f("gpu__time_duration.sum") * (1e3 if u["gpu__time_duration.sum"] == "ms" else 1.0),
           "how_executed": "thread-level executed FFMA (x2) + FADD + FMUL of step_kernel<true> in the profiled launch (ncu --set full), per env. Since the "
                           "Newton loop became warp-synchronous (r1h) this count includes the masked trips of lanes whose solve has finished, so it is "
