@@ -25,6 +25,16 @@ static int fail(const std::string& m) {
     cudaError_t e_ = (call);                                                                          \
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
   } while (0)
+// inside h1v2_create, once the handle exists: release it on failure
+#define CKH(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      fail(std::string(#call) + ": " + cudaGetErrorString(e_));                                       \
+      h1v2_destroy(h);                                                                                \
+      return -1;                                                                                      \
+    }                                                                                                 \
+  } while (0)
 
 struct H1v2Handle {
   H1v2Config cfg;
@@ -33,6 +43,7 @@ struct H1v2Handle {
   int n = 0, device = 0;
   uint64_t seed = 0;
   int64_t launches = 0;
+  bool attr_set = false;
   std::vector<void*> allocs;
   int64_t* own_ep_len = nullptr;
   // staging for h1v2_step_host
@@ -428,15 +439,15 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
     for (int t = 0; t < 6; t++)
       for (int hh = 0; hh < h->P.H; hh++)
         for (int k = off[t]; k < off[t + 1]; k++) lut[w++] = (hh << 8) | k;
-    CK(cudaMemcpy(lut_d, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(lut_d, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
     S.lut = lut_d;
   }
-  CK(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  CKH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
   reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, 0);
   h->launches += 2;
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
+  CKH(cudaGetLastError());
+  CKH(cudaDeviceSynchronize());
   *out = h;
   return 0;
 }
@@ -482,12 +493,11 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
   const int threads = H1V2_BLOCK;
   const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
   const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_set) {  // function attributes are per device: keep the flag with the handle, not with the process
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    h->attr_set = true;
   }
   if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, h->S, actions, obs, rew, term, trunc);

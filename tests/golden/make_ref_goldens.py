@@ -102,3 +102,37 @@ for t in range(Td):
 np.savez_compressed(os.path.join(OUT, "deploy_obs.npz"), quat=d_quat, ang=d_ang, q=d_q, qd=d_qd, act=d_act, cmd_unit=d_cmd, obs=d_obs,
                     cmd_lower=np.array([0.0, -0.5, -1.0]), cmd_upper=np.array([1.0, 0.5, 1.0]))
 print("wrote feet_air_time.npz obs_history.npz deploy_obs.npz")
+
+# ------------------------------------------------------------------ dead-zone command class (Rsl id, velocity_deadzone = 0)
+# biped_tasks/utils/mdp/commands.py:41-96 UniformVelocityCommandWithDeadzone._update_command, the reference's own method, run on
+# an instance that holds exactly the attributes the method reads (no simulator): what survives of a command after k calls.
+import json  # noqa: E402
+
+from biped_tasks.utils.mdp import commands as ref_commands  # noqa: E402
+
+torch.manual_seed(20261018)
+ND, CALLS, PHYS_DT, EP_S = 4096, 12, 0.005, 20.0
+term = object.__new__(ref_commands.UniformVelocityCommandWithDeadzone)
+term.cfg = types.SimpleNamespace(heading_command=False, heading_control_stiffness=1.0, ranges=types.SimpleNamespace(ang_vel_z=(-1.0, 1.0)))
+term.velocity_deadzone = 0.0          # C12/rsl_env_cfg.py:98
+term.dt, term.max_episode_length_s = PHYS_DT, EP_S  # commands.py:37-38
+term.vel_command_b = torch.from_numpy(rng.uniform(-1, 1, (ND, 3)).astype(np.float32))
+term.is_standing_env = torch.zeros(ND, dtype=torch.bool); term.is_standing_env[:64] = True  # the override must NOT zero these
+first = term.vel_command_b.clone()
+zero_xy, flips = [], 0
+for _ in range(CALLS):
+    before = term.vel_command_b[:, 2].clone()
+    term._update_command()
+    zero_xy.append(int(((term.vel_command_b[:, 0] == 0) & (term.vel_command_b[:, 1] == 0)).sum()))
+    flips += int((term.vel_command_b[:, 2] == -before).sum())
+    assert torch.equal(term.vel_command_b[:, 2].abs(), before.abs())
+# long run for the flip probability (it is 2.5e-4 per call)
+for _ in range(2000):
+    before = term.vel_command_b[:, 2].clone()
+    term._update_command()
+    flips += int((term.vel_command_b[:, 2] == -before).sum())
+json.dump({"n_envs": ND, "calls": CALLS, "zero_xy_after_call": zero_xy, "yaw_flips": flips, "flip_trials": ND * (CALLS + 2000),
+           "standing_envs_yaw_untouched_by_zeroing": bool(torch.equal(term.vel_command_b[:64, 2].abs(), first[:64, 2].abs())),
+           "physics_dt": PHYS_DT, "max_episode_length_s": EP_S},
+          open(os.path.join(OUT, "deadzone_command.json"), "w"), indent=1)
+print("wrote deadzone_command.json", zero_xy, flips)

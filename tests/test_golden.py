@@ -2,6 +2,7 @@
   * feet_air_time / feet_air_time_positive_biped   (velocity/mdp/rewards.py:13-62)
   * CircularBuffer history + term-major flatten    (utils/history/circular_buffer.py, observation_manager.py:335-355)
   * deployment ObservationHandler                  (biped_deploy/controllers/rl.py:34-121)
+  * dead-zone command class, dead zone 0           (utils/mdp/commands.py:41-96; survival statistics of a command)
 The CPU oracle is pinned against them here; the CUDA path is checked against the same files in the gpu-marked tests."""
 import os
 
@@ -26,6 +27,13 @@ class _OracleBackend:
     def observe(self):
         return self.o.observe()
 
+    def step(self, a):
+        _, _, t, u = self.o.step(a)
+        return t | u
+
+    def get_state(self, names):
+        return self.o.get_state(names)
+
     def close(self):
         pass
 
@@ -44,6 +52,13 @@ class _GpuBackend:
 
     def observe(self):
         return self.s.observe().cpu().numpy()
+
+    def step(self, a):
+        _, _, t, u = self.s.step(self.torch.from_numpy(a).cuda())
+        return (t | u).cpu().numpy()
+
+    def get_state(self, names):
+        return {k: v.cpu().numpy() for k, v in self.s.get_state(names).items()}
 
     def close(self):
         self.s.close()
@@ -118,6 +133,56 @@ def test_oracle_feet_air_time_against_reference_functions(cfg, thr):
     np.testing.assert_allclose(r[:, 3] / (0.75 * dt), g[f"biped_thr{thr}"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(r[:, 16] / (1.0 * dt), g[f"l2_thr{thr}"], rtol=1e-5, atol=1e-6)
     assert (g[f"biped_thr{thr}"] > 0).sum() > 100 and (g[f"l2_thr{thr}"] != 0).sum() > 50  # the fixture exercises both branches
+
+
+def _deadzone_case(backend_cls, steps):
+    """The Rsl id's command class against statistics of the reference's own _update_command (tests/golden/deadzone_command.json):
+    with velocity_deadzone = 0 every call zeroes the xy command of half of ALL envs (reference: exactly n // 2 by randperm; here
+    an independent draw per env with the same probability), never touches |yaw| (standing envs included), and flips the sign
+    of the yaw-rate command with probability physics_dt / max_episode_length_s."""
+    import json
+    from h1v2_isaac_b200._capi import rsl_config
+    g = json.load(open(os.path.join(GOLD, "deadzone_command.json")))
+    n, calls = g["n_envs"], g["calls"]
+    assert g["zero_xy_after_call"][0] == n // 2 and g["standing_envs_yaw_untouched_by_zeroing"]  # what the reference does
+    b = backend_cls(rsl_config(), n, seed=3)
+    b.observe()
+    rng = np.random.default_rng(4)
+    cmd = rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32) * rng.choice([-1.0, 1.0], (n, 3)).astype(np.float32)
+    standing = np.zeros((n, 1), np.int32); standing[:64] = 1
+    b.set_state({"command": cmd, "is_standing": standing, "time_left": np.full((n, 1), 100.0, np.float32)})
+    a = np.zeros((n, 12), np.float32)
+    prev, flips, trials = cmd.copy(), 0, 0
+    alive = np.ones(n, bool)  # envs whose command has not been redrawn by a reset
+    for k in range(steps):
+        done = b.step(a)
+        c = b.get_state(["command"])["command"]
+        alive &= ~done
+        zero = ((c[:, 0] == 0) & (c[:, 1] == 0))[alive]
+        if k < calls:
+            q = 0.5 ** (k + 1)
+            sigma = np.sqrt(alive.sum() * q * (1 - q))
+            want = g["zero_xy_after_call"][k] * alive.sum() / n
+            assert abs(zero.sum() - want) <= 5 * sigma + 2, (k, int(zero.sum()), want)
+        assert np.array_equal(np.abs(c[alive, 2]), np.abs(cmd[alive, 2])), "|yaw-rate command| never changes between resamples"
+        flips += int((c[alive, 2] == -prev[alive, 2]).sum()); trials += int(alive.sum())
+        prev = c
+    b.close()
+    assert alive[:64].sum() > 32  # standing envs were part of the check
+    p_ref, p = g["yaw_flips"] / g["flip_trials"], flips / trials
+    assert abs(p_ref - g["physics_dt"] / g["max_episode_length_s"]) < 2e-5
+    assert abs(p - p_ref) <= 5 * np.sqrt(p_ref / trials) + 1e-6, (flips, trials, p_ref)
+    return flips, trials
+
+
+def test_oracle_deadzone_command_against_reference_statistics():
+    _deadzone_case(_OracleBackend, 14)
+
+
+@pytest.mark.gpu
+def test_cuda_deadzone_command_against_reference_statistics():
+    flips, trials = _deadzone_case(_GpuBackend, 600)
+    assert flips > 300 and trials > 1_500_000
 
 
 @pytest.mark.gpu
