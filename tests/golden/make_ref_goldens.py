@@ -136,3 +136,37 @@ json.dump({"n_envs": ND, "calls": CALLS, "zero_xy_after_call": zero_xy, "yaw_fli
            "physics_dt": PHYS_DT, "max_episode_length_s": EP_S},
           open(os.path.join(OUT, "deadzone_command.json"), "w"), indent=1)
 print("wrote deadzone_command.json", zero_xy, flips)
+
+# ------------------------------------------------------------------ contact / limit idioms (in-tree constraint functions)
+# biped_tasks/utils/cat/constraints.py holds in-tree bodies of the idioms the Flat / Rsl terms use upstream:
+#   contact (:86-99)                 any_b max_h |F_hb| > 1.0            == mdp.illegal_contact(threshold=1.0)     (termination)
+#   foot_contact_force (:161-168)    max_h |F_hb| - limit                == the per-body argument of mdp.contact_forces' clip
+#   joint_position_limits (:22-31)   max(lo - q, q - hi)                 == the per-joint argument of mdp.joint_pos_limits' clip
+# Evaluated on random sensor histories / joint positions through a stand-in env.
+from biped_tasks.utils.cat import constraints as ref_cstr  # noqa: E402
+
+NC = 2048
+Fh = rng.normal(size=(NC, 3, 6, 3)).astype(np.float32)               # net_forces_w_history [N, H=3, B=6 sensor slots, 3]
+scale = np.exp(rng.uniform(np.log(0.02), np.log(3000.0), (NC, 1, 6, 1))).astype(np.float32)
+Fh *= scale
+Fh[(rng.random((NC, 1, 6, 1)) < 0.75).repeat(3, 1).repeat(3, 3)] = 0.0            # bodies in the air
+near = rng.random((NC, 6)) < 0.1                                                   # norms right at the 1.0 N threshold
+Fh = Fh.transpose(0, 2, 1, 3).copy()                                               # [N, B, H, 3] to index by (env, body)
+Fh[near] = 0.0
+Fh[near, 2] = (np.array([1.0, 0.0, 0.0], np.float32) * (1.0 + rng.choice([-1e-4, 1e-4], (int(near.sum()), 1)))).astype(np.float32)
+Fh = Fh.transpose(0, 2, 1, 3).copy()
+lo = np.array([-0.43, -3.14, -0.43, -0.26, -0.897334, -0.261799, -0.43, -3.14, -3.14, -0.26, -0.897334, -0.261799])
+hi = np.array([0.43, 2.5, 3.14, 2.05, 0.523598, 0.261799, 0.43, 2.5, 0.43, 2.05, 0.523598, 0.261799])
+mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * 0.9                                   # A/robots/h12.py:56 soft_joint_pos_limit_factor
+soft = np.stack([mid - half, mid + half], -1).astype(np.float32)
+qj = (mid + rng.uniform(-1.15, 1.15, (NC, 12)) * half).astype(np.float32)           # some beyond the soft limits
+sensor = types.SimpleNamespace(data=types.SimpleNamespace(net_forces_w_history=torch.from_numpy(Fh)))
+robot = types.SimpleNamespace(data=types.SimpleNamespace(joint_pos=torch.from_numpy(qj), soft_joint_pos_limits=torch.from_numpy(soft)[None].repeat(NC, 1, 1)))
+cenv = types.SimpleNamespace(scene={"contact_forces": sensor, "robot": robot})
+ill = SceneEntityCfg("contact_forces"); ill.body_ids = [2, 3, 4, 5]
+feet = SceneEntityCfg("contact_forces"); feet.body_ids = [0, 1]
+jall = SceneEntityCfg("robot"); jall.joint_ids = list(range(12))
+np.savez_compressed(os.path.join(OUT, "contact_limit_idioms.npz"), force_hist=Fh, joint_pos=qj, soft_limits=soft,
+                    illegal=ref_cstr.contact(cenv, ill).numpy(), foot_force_800=ref_cstr.foot_contact_force(cenv, 800.0, feet).numpy(),
+                    pos_limit=ref_cstr.joint_position_limits(cenv, jall).numpy())
+print("wrote contact_limit_idioms.npz")

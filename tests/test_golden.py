@@ -3,6 +3,8 @@
   * CircularBuffer history + term-major flatten    (utils/history/circular_buffer.py, observation_manager.py:335-355)
   * deployment ObservationHandler                  (biped_deploy/controllers/rl.py:34-121)
   * dead-zone command class, dead zone 0           (utils/mdp/commands.py:41-96; survival statistics of a command)
+  * contact / limit idioms                         (utils/cat/constraints.py:22-31,86-99,161-168: in-tree bodies of the
+                                                    expressions inside illegal_contact, contact_forces, joint_pos_limits)
 The CPU oracle is pinned against them here; the CUDA path is checked against the same files in the gpu-marked tests."""
 import os
 
@@ -133,6 +135,34 @@ def test_oracle_feet_air_time_against_reference_functions(cfg, thr):
     np.testing.assert_allclose(r[:, 3] / (0.75 * dt), g[f"biped_thr{thr}"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(r[:, 16] / (1.0 * dt), g[f"l2_thr{thr}"], rtol=1e-5, atol=1e-6)
     assert (g[f"biped_thr{thr}"] > 0).sum() > 100 and (g[f"l2_thr{thr}"] != 0).sum() > 50  # the fixture exercises both branches
+
+
+def test_oracle_contact_and_limit_terms_against_reference_constraint_functions(cfg):
+    """illegal_contact (termination mask, bit-exact), contact_forces and joint_pos_limits (1e-5) against the in-tree functions
+    that hold the same expressions: any_b max_h |F| > 1.0, max_h |F| - limit, max(lo - q, q - hi) (clipped at 0 and summed by
+    the upstream reward terms)."""
+    from oracle.oracle import Oracle
+    g = np.load(os.path.join(GOLD, "contact_limit_idioms.npz"))
+    n = g["joint_pos"].shape[0]
+    c = cfg.copy()
+    c.mask_illegal_slots = 0b111100  # knee links, torso, pelvis: the bodies the fixture's `illegal` was evaluated on
+    c.rew_weight[19], c.mask_contact_forces_slots, c.contact_forces_threshold = -1.0e-3, 0b11, 800.0
+    c.rew_weight[5], c.mask_pos_limits = -1.0, 0xFFF
+    o = Oracle(c, n, seed=2, threads=8)
+    o.observe()
+    s = o.get_state(["root_pos", "root_quat"])
+    norms = np.linalg.norm(g["force_hist"].astype(np.float64), axis=-1).astype(np.float32)  # [N, H, B]
+    post = {"pre_reset_qpos": np.concatenate([s["root_pos"], s["root_quat"], g["joint_pos"]], axis=1), "pre_reset_qvel": np.zeros((n, 18)),
+            "pre_reset_timers": np.zeros((n, 8)), "slot_force_hist": norms.transpose(0, 2, 1).reshape(n, 18), "applied_torque": np.zeros((n, 12)),
+            "joint_acc": np.zeros((n, 12)), "foot_vel": np.zeros((n, 6))}
+    _, _, term, trunc = o.step_injected(np.zeros((n, 12), np.float32), post)
+    assert np.array_equal(term.astype(bool), g["illegal"]) and not trunc.any()
+    assert 0.3 < g["illegal"].mean() < 0.8
+    r = o.get_state(["reward_terms"])["reward_terms"]
+    dt = c.sim_dt * c.decimation
+    np.testing.assert_allclose(r[:, 19] / (-1.0e-3 * dt), np.clip(g["foot_force_800"], 0, None).sum(1), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(r[:, 5] / (-1.0 * dt), np.clip(g["pos_limit"], 0, None).sum(1), rtol=1e-5, atol=1e-6)
+    assert (g["foot_force_800"] > 0).sum() > 50 and (g["pos_limit"] > 0).sum() > 1000
 
 
 def _deadzone_case(backend_cls, steps):
