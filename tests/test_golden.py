@@ -182,23 +182,26 @@ def _deadzone_case(backend_cls, steps):
     standing = np.zeros((n, 1), np.int32); standing[:64] = 1
     b.set_state({"command": cmd, "is_standing": standing, "time_left": np.full((n, 1), 100.0, np.float32)})
     a = np.zeros((n, 12), np.float32)
-    prev, flips, trials = cmd.copy(), 0, 0
-    alive = np.ones(n, bool)  # envs whose command has not been redrawn by a reset
+    prev, prev_tl, flips, trials = cmd.copy(), np.full(n, 100.0, np.float32), 0, 0
+    alive = np.ones(n, bool)  # envs whose command has not been redrawn since the start (no reset, no resample)
     for k in range(steps):
         done = b.step(a)
-        c = b.get_state(["command"])["command"]
-        alive &= ~done
-        zero = ((c[:, 0] == 0) & (c[:, 1] == 0))[alive]
+        st = b.get_state(["command", "time_left"])
+        c, tl = st["command"], st["time_left"][:, 0]
+        same = ~done & (tl < prev_tl)  # this step neither reset nor resampled the env's command
+        alive &= same
         if k < calls:
+            zero = ((c[:, 0] == 0) & (c[:, 1] == 0))[alive]
             q = 0.5 ** (k + 1)
             sigma = np.sqrt(alive.sum() * q * (1 - q))
             want = g["zero_xy_after_call"][k] * alive.sum() / n
             assert abs(zero.sum() - want) <= 5 * sigma + 2, (k, int(zero.sum()), want)
-        assert np.array_equal(np.abs(c[alive, 2]), np.abs(cmd[alive, 2])), "|yaw-rate command| never changes between resamples"
-        flips += int((c[alive, 2] == -prev[alive, 2]).sum()); trials += int(alive.sum())
-        prev = c
+            assert alive[:64].sum() > 32  # standing envs are part of the next check: the override does not zero them
+            assert np.array_equal(np.abs(c[alive, 2]), np.abs(cmd[alive, 2])), "|yaw-rate command| never changes between resamples"
+        assert np.array_equal(np.abs(c[same, 2]), np.abs(prev[same, 2]))
+        flips += int(((c[same, 2] == -prev[same, 2]) & (prev[same, 2] != 0)).sum()); trials += int(same.sum())
+        prev, prev_tl = c, tl
     b.close()
-    assert alive[:64].sum() > 32  # standing envs were part of the check
     p_ref, p = g["yaw_flips"] / g["flip_trials"], flips / trials
     assert abs(p_ref - g["physics_dt"] / g["max_episode_length_s"]) < 2e-5
     assert abs(p - p_ref) <= 5 * np.sqrt(p_ref / trials) + 1e-6, (flips, trials, p_ref)
