@@ -210,6 +210,14 @@ def flatten_cfg(cfg) -> H1v2Config:
     if not _get(pol, "concatenate_terms", True):
         raise NotImplementedError("observations.policy.concatenate_terms=False is not supported")
     c.history_length = int(_get(pol, "history_length", 0) or 1)
+    if int(_get(pol, "history_step", 1) or 1) != 1:  # T/utils/history/observation_manager.py:441-451 (the CaT cfg sets 1)
+        raise NotImplementedError("observations.policy.history_step != 1 is not supported")
+    if _get(pol, "flatten_history_dim", True) is False:
+        raise NotImplementedError("observations.policy.flatten_history_dim=False is not supported")
+    for n, t in terms:
+        th = _get(t, "history_length")
+        if th not in (None, 0, c.history_length):
+            raise NotImplementedError(f"observations.policy.{n}.history_length differs from the group's")
     c.enable_corruption = int(bool(_get(pol, "enable_corruption", False)))
     noise, scale = [], []
     for n, t in terms:

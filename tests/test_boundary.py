@@ -92,6 +92,10 @@ def test_unsupported_cfg_is_rejected_loudly():
     with pytest.raises(NotImplementedError, match="min_delay"):
         flatten_cfg(tree)
     tree = tasks.rsl_env_cfg(8)
+    tree.observations.policy.history_step = 2
+    with pytest.raises(NotImplementedError, match="history_step"):
+        flatten_cfg(tree)
+    tree = tasks.rsl_env_cfg(8)
     tree.commands.base_velocity.velocity_deadzone = 0.1  # a positive dead zone balances a per-process count of envs: not in the kernel
     with pytest.raises(NotImplementedError, match="velocity_deadzone"):
         flatten_cfg(tree)

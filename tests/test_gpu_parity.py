@@ -237,12 +237,15 @@ def test_flight_conserves_momentum_and_matches_oracle(cfg):
         _resync(sim, orc, g)
 
 
-@pytest.mark.parametrize("n", [4096, 32768])
-def test_full_size_properties(cfg, n):
+@pytest.mark.parametrize("task,n", [("flat", 4096), ("flat", 32768), ("rsl", 32768)])
+def test_full_size_properties(cfg, task, n):
     """Size-independent properties at BASELINE's env counts: determinism (same seed -> bit-identical run), finite
     outputs, history shift property of the observation, episode counters, sharding invariance of the Philox key."""
     import torch
+    from h1v2_isaac_b200._capi import rsl_config
     from h1v2_isaac_b200.backend import H1v2Sim
+    if task == "rsl":  # SURVEY 8(f)1: history 6, per-env friction, pushes, dead-zone command class
+        cfg = rsl_config()
     H = cfg.history_length
 
     def run(offset, count, steps=12):
