@@ -58,6 +58,7 @@ class H1v2Config(C.Structure):
         ("env_id_offset", i64), ("env_spacing", f32), ("joint_vel_limit", f32),
         ("mask_pos_limits_b", u32), ("mask_joint_dev_b", u32), ("mask_contact_forces_slots", u32), ("contact_forces_threshold", f32),
         ("command_class", i32), ("velocity_deadzone", f32), ("ang_vel_flip_prob", f32),
+        ("root_link_com", f32 * 3), ("body_vel_at_com", i32),
         ("runaway_vel", f32), ("reserved", i32 * 8),
     ]
 

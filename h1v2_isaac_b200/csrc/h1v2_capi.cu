@@ -341,6 +341,8 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.inv_std2 = 1.f / (c.track_std * c.track_std); P.air_thr = c.feet_air_threshold; P.contact_thr = c.contact_threshold; P.base_h = c.base_height_target;
   P.m_poslim = c.mask_pos_limits; P.m_dev = c.mask_joint_dev; P.m_poslim_b = c.mask_pos_limits_b; P.m_dev_b = c.mask_joint_dev_b;
   P.m_cforce = c.mask_contact_forces_slots; P.cforce_thr = c.contact_forces_threshold;
+  for (int k = 0; k < 3; k++) P.root_com[k] = c.root_link_com[k];
+  P.foot_vel_com = c.body_vel_at_com;
   P.m_tau = c.mask_torques; P.m_undesired = c.mask_undesired_slots; P.m_illegal = c.mask_illegal_slots;
   for (int k = 0; k < 2; k++) {
     P.c_lx[k] = c.cmd_lin_x[k]; P.c_ly[k] = c.cmd_lin_y[k]; P.c_wz[k] = c.cmd_ang_z[k]; P.c_hd[k] = c.cmd_heading[k]; P.c_rt[k] = c.cmd_resample_time[k];

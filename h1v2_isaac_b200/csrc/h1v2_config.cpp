@@ -123,6 +123,9 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->env_id_offset = 0;
   c->env_spacing = 2.5f;
   c->joint_vel_limit = 100.0f;  // A/robots/h12.py:66,89,103 velocity_limit
+  // isaaclab 2.1.0 reports link velocities at the link's COM: pelvis link inertial origin, A/models/h12/h12_12dof.urdf:16 (== h12_12dof.xml:67)
+  c->root_link_com[0] = -0.0004f; c->root_link_com[1] = 3.7e-05f; c->root_link_com[2] = -0.046864f;
+  c->body_vel_at_com = 1;
   c->runaway_vel = 1000.0f;     // A/robots/h12.py:27-28 max_linear_velocity / max_angular_velocity
   return 0;
 }

@@ -58,6 +58,8 @@ struct KParams {
   // rewards
   float w[H1V2_NUM_REW];
   float inv_std2, air_thr, contact_thr, base_h;
+  float root_com[3];  // COM of the root link in the pelvis frame: the managers read root_lin_vel at it (isaaclab ArticulationData)
+  int foot_vel_com;   // feet_slide reads the ankle_roll_link COM velocity
   float soft_lo[12], soft_hi[12];
   uint32_t m_poslim, m_dev, m_tau, m_undesired, m_illegal, m_poslim_b, m_dev_b, m_cforce;
   float cforce_thr;

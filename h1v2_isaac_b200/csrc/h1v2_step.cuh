@@ -10,14 +10,16 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 struct RootDerived {
   M3 R;
-  V3 vb, wb, ww, g;
+  V3 vb, vw, wb, ww, g;  // vb / vw: velocity of the root link's COM (base / world frame), as isaaclab's root_lin_vel_b / _w
   float hx, hy;  // forward axis of the base projected on the ground, unnormalised: heading = atan2(hy, hx)
 };
-__device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const float (&rv)[3], const float (&rw)[3]) {
+__device__ __forceinline__ RootDerived root_derived(const KParams& P, const float (&rq)[4], const float (&rv)[3], const float (&rw)[3]) {
   RootDerived d;
   d.R = quat2mat(rq[0], rq[1], rq[2], rq[3]);
-  d.vb = mulTv(d.R, mk3(rv[0], rv[1], rv[2]));
   d.wb = mk3(rw[0], rw[1], rw[2]);
+  // the state holds the pelvis ORIGIN velocity (MuJoCo qvel); the managers read the root link's COM velocity: v + w x r
+  d.vb = mulTv(d.R, mk3(rv[0], rv[1], rv[2])) + cross(d.wb, mk3(P.root_com[0], P.root_com[1], P.root_com[2]));
+  d.vw = mulv(d.R, d.vb);
   d.ww = mulv(d.R, d.wb);
   d.g = mk3(-d.R.cx.z, -d.R.cy.z, -d.R.cz.z);  // R^T (0,0,-1)
   d.hx = d.R.cx.x; d.hy = d.R.cx.y;
@@ -27,7 +29,7 @@ __device__ __forceinline__ RootDerived root_derived(const float (&rq)[4], const 
 // world linear velocity of the ankle_roll_link origin of this lane's leg (body_lin_vel_w of the foot, feet_slide).
 // Rolled over the joints with q / qd staged in the lane's shared-memory column: call it while the column is free
 // (after the physics loop, before the history prefetch).
-__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6]) {
+__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6], bool at_com) {
   extern __shared__ __align__(16) float smem_raw[];
   const Smem sm{smem_raw + tid};
 #pragma unroll
@@ -46,6 +48,7 @@ __device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const 
     sincos_lim(sm.jf(i, F_XQ), s_, c_);
     rotate_rt(R, ax, s_, c_);
   }
+  if (at_com) x = x + mulv(R, ld3(LG.ipos[5]));  // body_lin_vel_w is the velocity of the link's COM (isaaclab ArticulationData)
   return vo + cross(om, x);
 }
 
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   V3 fv = mk3(0.f, 0.f, 0.f);
   if (DO_STEP) {
     const M3 Rn = quat2mat(rq[0], rq[1], rq[2], rq[3]);
-    fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd);
+    fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd, P.foot_vel_com != 0);
     __syncwarp();  // every lane is done with its column before the asynchronous copy lands in it
   }
   hist_prefetch(P, S, tid, bid, 0);
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     const bool reset = contact || time_out;
 
     // ---- rewards on the pre-reset state ----
-    const RootDerived rd = root_derived(rq, rv, rw);
+    const RootDerived rd = root_derived(P, rq, rv, rw);
     float r[H1V2_NUM_REW];
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       r[H1V2_REW_TERMINATION] = contact ? 1.f : 0.f;
       const float hn = rsqrtf(fmaxf(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));  // cos / sin of the heading without the angle itself
       const float ch = rd.hx * hn, sh = rd.hy * hn;
-      float ex = cmd.c[0] - (ch * rv[0] + sh * rv[1]), ey = cmd.c[1] - (-sh * rv[0] + ch * rv[1]);
+      float ex = cmd.c[0] - (ch * rd.vw.x + sh * rd.vw.y), ey = cmd.c[1] - (-sh * rd.vw.x + ch * rd.vw.y);
       r[H1V2_REW_TRACK_LIN_XY_YAW] = expf(-(ex * ex + ey * ey) * P.inv_std2);
       float ez = cmd.c[2] - rd.ww.z;
       r[H1V2_REW_TRACK_ANG_Z_WORLD] = expf(-(ez * ez) * P.inv_std2);
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   }
 
   // ---- command manager, interval events, observation (on the post-reset state) ----
-  RootDerived rd = root_derived(rq, rv, rw);
+  RootDerived rd = root_derived(P, rq, rv, rw);
   if (DO_STEP) {
     update_command(P, cmd, rd, gid, step);
     if (P.push_enable) {  // push_by_setting_velocity (V/velocity_env_cfg.py:212-217)
@@ -667,7 +670,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         push_left = uni(u[2], P.push_int[0], P.push_int[1]);
         rv[0] += uni(u[0], P.push_v[0], P.push_v[1]);
         rv[1] += uni(u[1], P.push_v[0], P.push_v[1]);
-        rd = root_derived(rq, rv, rw);
+        rd = root_derived(P, rq, rv, rw);
       }
     }
   }

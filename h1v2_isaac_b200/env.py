@@ -420,6 +420,18 @@ class _NamesView:
         self.active_terms = list(names)
 
 
+class _CommandManagerView(_NamesView):
+    def __init__(self, env):
+        super().__init__(["base_velocity"])
+        self._env = env
+
+    def get_command(self, name: str):
+        """CommandManager.get_command("base_velocity") -> Tensor[N,3] (v_x, v_y, w_z), as the mdp terms read it upstream."""
+        if name != "base_velocity":
+            raise KeyError(name)
+        return self._env.sim.get_state(["command"])["command"]
+
+
 class H1v2ManagerBasedRLEnv:
     """ManagerBasedRLEnv drop-in.  step(action) -> (obs_dict, rew, terminated, truncated, extras), all device tensors."""
 
@@ -457,7 +469,7 @@ class H1v2ManagerBasedRLEnv:
         self.observation_manager = _ObservationManagerView(self)
         self.reward_manager = _NamesView([n for n, t in _terms(cfg.rewards) if float(t.weight) != 0.0])
         self.termination_manager = _NamesView(["time_out", "base_contact"])
-        self.command_manager = _NamesView(["base_velocity"])
+        self.command_manager = _CommandManagerView(self)
         slots = reward_slots(cfg)
         self._rew_names = list(slots)  # every term that owns a slot is logged, like upstream's Episode_Reward/<term> (0 for weight 0)
         self._rew_slots = [slots[n] for n in self._rew_names]

@@ -168,6 +168,11 @@ typedef struct H1v2Config {
   float velocity_deadzone;             /* only 0.0 is implemented for class 1 (rsl_env_cfg.py:98): no env is ever "in the dead zone",
                                           so every step n_envs/2 uniformly chosen envs get their xy command zeroed */
   float ang_vel_flip_prob;             /* per-step probability of negating the yaw-rate command (commands.py:85-96): physics_dt / episode_length_s */
+  /* ---- velocity reference points of the managers (isaaclab 2.1.0 ArticulationData: poses are of the link frame, velocities of the
+   *      link's centre of mass; SURVEY App. A "State conventions").  The physics state stays MuJoCo's (pelvis ORIGIN velocity). ---- */
+  float root_link_com[3];              /* COM of the root LINK (pelvis alone, h12_12dof.urdf:16 == h12_12dof.xml:67) in the pelvis frame:
+                                          root_lin_vel_w/_b used by rewards and command metrics = v_origin + w x (R r) */
+  int32_t body_vel_at_com;             /* 1: feet_slide reads the ankle_roll_link COM velocity (body_lin_vel_w), 0: link origin */
   float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
                                           non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
   int32_t reserved[8];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);

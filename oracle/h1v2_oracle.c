@@ -633,8 +633,9 @@ static void physics_substep(const H1v2Oracle* o, OEnv* e, const double ctrl[NJ])
   for (int j = 0; j < NJ; j++) e->qpos[7 + j] += h * e->qvel[6 + j];
 }
 
-/* world velocity of the ankle_roll_link origins (body_lin_vel_w of the feet) */
-static void foot_velocities(const OEnv* e, double fv[2][3]) {
+/* world velocity of the ankle_roll_links (body_lin_vel_w of the feet): isaaclab 2.1.0 ArticulationData reports link velocities at
+ * the link's centre of mass (at_com), the MuJoCo-side convention would be the link origin */
+static void foot_velocities(const OEnv* e, int at_com, double fv[2][3]) {
   Kin k;
   kinematics(e->qpos, &k);
   static const int foot_body[2] = {6, 12};
@@ -644,8 +645,13 @@ static void foot_velocities(const OEnv* e, double fv[2][3]) {
     for (int d = 0; d < NV; d++)
       if (is_ancestor_or_self(body_of_dof[d], b))
         for (int i = 0; i < 6; i++) v[i] += k.S[d][i] * e->qvel[d];
-    double wxp[3];
-    cross3(v, k.x[b], wxp);
+    double wxp[3], p[3] = {k.x[b][0], k.x[b][1], k.x[b][2]};
+    if (at_com) {
+      double c[3];
+      matvec3(k.R[b], h1v2_body_ipos[b], c);
+      for (int i = 0; i < 3; i++) p[i] += c[i];
+    }
+    cross3(v, p, wxp);
     for (int i = 0; i < 3; i++) fv[f][i] = v[3 + i] + wxp[i];
   }
 }
@@ -744,12 +750,18 @@ static void reset_env(H1v2Oracle* o, int ei) {
   e->ep_len = 0;
 }
 
-static void root_derived(const OEnv* e, double R[9], double vb[3], double wb[3], double g[3], double* heading,
-                         double ww[3]) {
+/* vb / vw: velocity of the root LINK's centre of mass in the base / world frame (isaaclab 2.1.0 root_lin_vel_b / root_lin_vel_w,
+ * SURVEY App. A); the state itself holds MuJoCo's pelvis-origin velocity: v_com = v_origin + w x (R r_com) */
+static void root_derived(const H1v2Config* c, const OEnv* e, double R[9], double vb[3], double wb[3], double g[3], double* heading,
+                         double ww[3], double vw[3]) {
   double q[4] = {e->qpos[3], e->qpos[4], e->qpos[5], e->qpos[6]};
   quat2mat(q, R);
   mattvec3(R, e->qvel, vb);
   for (int i = 0; i < 3; i++) wb[i] = e->qvel[3 + i];
+  double rc[3] = {c->root_link_com[0], c->root_link_com[1], c->root_link_com[2]}, wxr[3];
+  cross3(wb, rc, wxr);
+  for (int i = 0; i < 3; i++) vb[i] += wxr[i];
+  matvec3(R, vb, vw);
   matvec3(R, wb, ww);
   g[0] = -R[6]; g[1] = -R[7]; g[2] = -R[8]; /* R^T (0,0,-1) */
   *heading = atan2(R[3], R[0]);
@@ -758,8 +770,8 @@ static void root_derived(const OEnv* e, double R[9], double vb[3], double wb[3],
 static void update_command(H1v2Oracle* o, int ei) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
-  double R[9], vb[3], wb[3], g[3], heading, ww[3];
-  root_derived(e, R, vb, wb, g, &heading, ww);
+  double R[9], vb[3], wb[3], g[3], heading, ww[3], vw[3];
+  root_derived(c, e, R, vb, wb, g, &heading, ww, vw);
   /* _update_metrics */
   float max_command_step = c->cmd_resample_time[1] / (c->sim_dt * (float)c->decimation);
   float ex = e->cmd[0] - (float)vb[0], ey = e->cmd[1] - (float)vb[1];
@@ -796,8 +808,8 @@ static void compute_obs(H1v2Oracle* o, int ei, float* obs_out) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
   const int H = c->history_length;
-  double R[9], vb[3], wb[3], g[3], heading, ww[3];
-  root_derived(e, R, vb, wb, g, &heading, ww);
+  double R[9], vb[3], wb[3], g[3], heading, ww[3], vw[3];
+  root_derived(c, e, R, vb, wb, g, &heading, ww, vw);
   float s[H1V2_OBS_TERM_DIM];
   float n_av[3] = {0}, n_g[3] = {0}, n_q[NJ] = {0}, n_v[NJ] = {0};
   if (c->enable_corruption) {
@@ -921,9 +933,12 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
     for (int i = 0; i < 8; i++) e->timers[i / 4][i % 4] = inj->timers[(size_t)ei * 8 + i];
     for (int i = 0; i < 18; i++) e->slot_hist[i / 3][i % 3] = inj->slot_hist[(size_t)ei * 18 + i];
     for (int i = 0; i < NJ; i++) { e->applied_tau[i] = inj->tau[(size_t)ei * NJ + i]; e->joint_acc[i] = inj->qacc[(size_t)ei * NJ + i]; }
-    for (int i = 0; i < 6; i++) e->foot_vel[i / 3][i % 3] = inj->foot_vel[(size_t)ei * 6 + i];
+    if (inj->foot_vel)
+      for (int i = 0; i < 6; i++) e->foot_vel[i / 3][i % 3] = inj->foot_vel[(size_t)ei * 6 + i];
+    else /* not injected: the oracle's own kinematics on the injected state (checks the kernel's foot velocity) */
+      foot_velocities(e, o->cfg.body_vel_at_com, e->foot_vel);
   } else {
-    foot_velocities(e, e->foot_vel);
+    foot_velocities(e, o->cfg.body_vel_at_com, e->foot_vel);
   }
   /* non-finite guard: force a reset, zero reward */
   int bad = 0;
@@ -945,13 +960,13 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   *trunc_out = (uint8_t)time_out;
   int reset = contact || time_out;
   /* -- rewards on the pre-reset state -- */
-  double R[9], vb[3], wb[3], g[3], heading, ww[3], r[NREW];
-  root_derived(e, R, vb, wb, g, &heading, ww);
+  double R[9], vb[3], wb[3], g[3], heading, ww[3], vw[3], r[NREW];
+  root_derived(c, e, R, vb, wb, g, &heading, ww, vw);
   memset(r, 0, sizeof(r));
   double std2 = (double)c->track_std * c->track_std;
   double cy = cos(heading), sy = sin(heading);
   /* yaw-frame velocity: yaw_quat(root_quat)^-1 * v_w */
-  double vyaw[2] = {cy * e->qvel[0] + sy * e->qvel[1], -sy * e->qvel[0] + cy * e->qvel[1]};
+  double vyaw[2] = {cy * vw[0] + sy * vw[1], -sy * vw[0] + cy * vw[1]};
   double cmdn = sqrt((double)e->cmd[0] * e->cmd[0] + (double)e->cmd[1] * e->cmd[1]);
   int moving = (float)sqrtf(e->cmd[0] * e->cmd[0] + e->cmd[1] * e->cmd[1]) > 0.1f;
   (void)cmdn;

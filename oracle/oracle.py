@@ -116,16 +116,17 @@ class Oracle:
 
     def step_injected(self, actions, post: dict):
         """Control step with the physics loop replaced by the given post-physics values (identical-state tail parity).
-        post keys: pre_reset_qpos, pre_reset_qvel, pre_reset_timers, slot_force_hist, applied_torque, joint_acc, foot_vel."""
+        post keys: pre_reset_qpos, pre_reset_qvel, pre_reset_timers, slot_force_hist, applied_torque, joint_acc and, optionally,
+        foot_vel (without it the oracle computes the foot velocities from the injected state with its own kinematics)."""
         a = np.ascontiguousarray(actions, dtype=np.float32)
         f = {k: np.ascontiguousarray(post[k], dtype=np.float32) for k in
-             ("pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers", "slot_force_hist", "applied_torque", "joint_acc", "foot_vel")}
+             ("pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers", "slot_force_hist", "applied_torque", "joint_acc", "foot_vel") if k in post}
         obs = np.zeros((self.n, self.obs_dim), np.float32)
         rew = np.zeros(self.n, np.float32)
         term = np.zeros(self.n, np.uint8)
         trunc = np.zeros(self.n, np.uint8)
         lib().h1v2o_step_injected(self._h, _p(a), _p(f["pre_reset_qpos"]), _p(f["pre_reset_qvel"]), _p(f["pre_reset_timers"]),
-                                  _p(f["slot_force_hist"]), _p(f["applied_torque"]), _p(f["joint_acc"]), _p(f["foot_vel"]),
+                                  _p(f["slot_force_hist"]), _p(f["applied_torque"]), _p(f["joint_acc"]), _p(f["foot_vel"]) if "foot_vel" in f else None,
                                   _p(obs), _p(rew), _p(term), _p(trunc))
         return obs, rew, term.astype(bool), trunc.astype(bool)
 

@@ -29,6 +29,9 @@ def test_env_contract_matches_backend():
         obs, rew, term, trunc, extras = env.step(a)
         o2, r2, t2, u2 = sim.step(a)
     assert rew.dtype == torch.float32 and term.dtype == torch.bool and trunc.dtype == torch.bool
+    cmd = env.command_manager.get_command("base_velocity")
+    assert cmd.shape == (n, 3)
+    assert torch.allclose(cmd, obs["policy"][:, 60:90].reshape(n, 10, 3)[:, -1])  # newest slot of the command block (no noise, scale 1)
     assert set(k.split("/")[0] for k in extras["log"]) == {"Episode_Reward", "Episode_Termination", "Metrics"}
     assert len([k for k in extras["log"] if k.startswith("Episode_Reward/")]) == 12
     # episode_length_buf is assignable (train.py:141 learn(init_at_random_ep_len=True)) and drives truncation

@@ -147,8 +147,10 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
         a = (rng.normal(size=(n, 12)) * (0.3 if step % 3 else 1.0)).astype(np.float32)
         og, rg, tg, ug = sim.step(torch.from_numpy(a).cuda())
         g = _np(sim.get_state(SYNC + POST + ["reward_terms"]))
-        oo, ro, to, uo = orc.step_injected(a, g)
-        o = orc.get_state(SYNC + ["reward_terms"])
+        # foot_vel is NOT injected: the oracle derives body_lin_vel_w of the feet from the injected state with its own kinematics
+        oo, ro, to, uo = orc.step_injected(a, {k: v for k, v in g.items() if k != "foot_vel"})
+        o = orc.get_state(SYNC + ["reward_terms", "foot_vel"])
+        np.testing.assert_allclose(g["foot_vel"], o["foot_vel"], rtol=1e-4, atol=2e-5, err_msg=f"foot velocity, step {step}")
         tg, ug, og, rg = tg.cpu().numpy(), ug.cpu().numpy(), og.cpu().numpy(), rg.cpu().numpy()
         # (b) masks bit-exact
         assert np.array_equal(tg, to), f"terminated mask, step {step}"

@@ -191,3 +191,35 @@ def test_episode_timeout_and_reset_semantics(cfg):
     st = orc.get_state(["last_action", "fresh", "joint_pos"])
     assert (st["fresh"][1:, 0] & 1).all()  # delay line empty after the reset; the observation history was refilled
     np.testing.assert_allclose(st["joint_pos"][1], np.array(c.default_joint_pos[:]), atol=1e-6)
+
+
+def test_manager_velocities_refer_to_the_link_centre_of_mass(cfg):
+    """isaaclab 2.1.0 ArticulationData: poses are of the link frame, velocities of the link's centre of mass.
+    A pelvis spinning about its own origin (origin velocity 0) therefore has root_lin_vel_b = w x r_com, with r_com the inertial
+    origin of the pelvis LINK (h12_12dof.urdf:16).  Checked through lin_vel_z_l2 and the base / yaw-frame tracking terms."""
+    c = cfg.copy()
+    for t in (1, 12, 14):  # track_lin_vel_xy_yaw_frame_exp, lin_vel_z_l2, track_lin_vel_xy_exp
+        c.rew_weight[t] = 1.0
+    n = 4
+    o = O.Oracle(c, n, seed=1)
+    o.observe()
+    s = o.get_state(["root_pos", "root_quat", "joint_pos"])
+    yaw = 0.7
+    quat = np.tile(np.array([np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)], np.float32), (n, 1))
+    w = np.array([[1.0, 0, 0], [0, 2.0, 0], [0, 0, 3.0], [1.0, -2.0, 0.5]])  # body-frame angular velocity
+    qvel = np.zeros((n, 18)); qvel[:, 3:6] = w
+    cmd = np.tile(np.array([0.3, -0.2, 0.1], np.float32), (n, 1))
+    o.set_state({"command": cmd})
+    post = {"pre_reset_qpos": np.concatenate([s["root_pos"], quat, s["joint_pos"]], axis=1), "pre_reset_qvel": qvel,
+            "pre_reset_timers": np.zeros((n, 8)), "slot_force_hist": np.zeros((n, 18)), "applied_torque": np.zeros((n, 12)),
+            "joint_acc": np.zeros((n, 12)), "foot_vel": np.zeros((n, 6))}
+    o.step_injected(np.zeros((n, 12), np.float32), post)
+    r = o.get_state(["reward_terms"])["reward_terms"] / (c.sim_dt * c.decimation)
+    rc = np.array(c.root_link_com[:], np.float64)
+    assert np.allclose(rc, [-0.0004, 3.7e-05, -0.046864], atol=1e-7)
+    vb = np.cross(w, rc)  # base frame; the yaw frame differs from it by the roll/pitch only, which are 0 here
+    np.testing.assert_allclose(r[:, 12], vb[:, 2] ** 2, rtol=1e-5, atol=1e-9)
+    want = np.exp(-((cmd[:, 0] - vb[:, 0]) ** 2 + (cmd[:, 1] - vb[:, 1]) ** 2) / c.track_std ** 2)
+    np.testing.assert_allclose(r[:, 14], want, rtol=1e-5)
+    np.testing.assert_allclose(r[:, 1], want, rtol=1e-5)
+    assert np.abs(vb[:, :2]).max() > 0.04  # the convention matters at the 5 cm/s level
