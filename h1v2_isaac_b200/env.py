@@ -355,6 +355,8 @@ def flatten_cfg(cfg) -> H1v2Config:
         elif f == "randomize_rigid_body_mass":
             if p.get("operation", "add") != "add":
                 raise NotImplementedError(f"events.{n}: only operation='add' is supported")
+            if p.get("recompute_inertia", True) is False:  # the kernel rescales the inertia with the mass (isaaclab 2.1.0 default)
+                raise NotImplementedError(f"events.{n}: recompute_inertia=False is not supported")
             c.mass_add_range[0], c.mass_add_range[1] = map(float, p["mass_distribution_params"])
         elif f == "apply_external_force_torque":
             if any(abs(float(v)) > 0 for v in tuple(p["force_range"]) + tuple(p["torque_range"])):
