@@ -4,9 +4,11 @@ import sys, time
 sys.path.insert(0, '/root/repo')
 import torch
 from h1v2_isaac_b200.backend import H1v2Sim
-from h1v2_isaac_b200._capi import default_config
+from h1v2_isaac_b200._capi import default_config, rsl_config
 n, steps = 4096, 60000
-sim = H1v2Sim(n, default_config(), seed=123); sim.observe()
+task = sys.argv[1] if len(sys.argv) > 1 else "flat"  # "rsl": the Rsl id (friction 0.1..1.25, pushes, dead-zone commands, scale 0.25)
+sim = H1v2Sim(n, rsl_config() if task == "rsl" else default_config(), seed=123); sim.observe()
+print("task", task)
 pool = [sim.random_actions(i) for i in range(64)]
 obs = torch.empty((n, sim.obs_dim), device='cuda'); rew = torch.empty(n, device='cuda')
 term = torch.empty(n, dtype=torch.uint8, device='cuda'); trunc = torch.empty(n, dtype=torch.uint8, device='cuda')
