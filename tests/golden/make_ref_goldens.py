@@ -101,7 +101,17 @@ for t in range(Td):
     d_obs[t] = handler.get_observations(state, d_act[t], d_cmd[t])
 np.savez_compressed(os.path.join(OUT, "deploy_obs.npz"), quat=d_quat, ang=d_ang, q=d_q, qd=d_qd, act=d_act, cmd_unit=d_cmd, obs=d_obs,
                     cmd_lower=np.array([0.0, -0.5, -1.0]), cmd_upper=np.array([1.0, 0.5, 1.0]))
-print("wrote feet_air_time.npz obs_history.npz deploy_obs.npz")
+# the same through the format of the Rsl id / the shipped env.yaml (scripts/deploy/policies/demo_rsl/env.yaml): history 6,
+# gyro x0.25, joint velocity x0.05, command ranges +-1
+H6 = 6
+handler6 = ObservationHandler(names, [0.25, 1.0, 1.0, 1.0, 0.05, 1.0], H6, q0, {"lower": np.array([-1.0, -1.0, -1.0]), "upper": np.array([1.0, 1.0, 1.0]), "velocity_deadzone": 0.0})
+d_obs6 = np.zeros((Td, 45 * H6), np.float32)
+for t in range(Td):
+    state = {"base_orientation": d_quat[t], "base_angular_vel": d_ang[t], "qpos": d_q[t], "qvel": d_qd[t]}
+    d_obs6[t] = handler6.get_observations(state, d_act[t], d_cmd[t])
+np.savez_compressed(os.path.join(OUT, "deploy_obs_rsl.npz"), quat=d_quat, ang=d_ang, q=d_q, qd=d_qd, act=d_act, cmd_unit=d_cmd, obs=d_obs6,
+                    cmd_lower=np.array([-1.0, -1.0, -1.0]), cmd_upper=np.array([1.0, 1.0, 1.0]))
+print("wrote feet_air_time.npz obs_history.npz deploy_obs.npz deploy_obs_rsl.npz")
 
 # ------------------------------------------------------------------ dead-zone command class (Rsl id, velocity_deadzone = 0)
 # biped_tasks/utils/mdp/commands.py:41-96 UniformVelocityCommandWithDeadzone._update_command, the reference's own method, run on

@@ -217,3 +217,37 @@ print("RESULT" + json.dumps({"mine": d, "shipped": y}))
     for j in mine["joints"]:
         s = ship_j[j["name"]]
         assert (j["kp"], j["kd"], j["default_joint_pos"]) == (s["kp"], s["kd"], s["default_joint_pos"]), j["name"]
+
+
+def test_deploy_config_of_the_rsl_task():
+    """h1v2_isaac_b200.deploy.deploy_config: the env.yaml document for a policy trained on the Rsl id (the reference's own exporter
+    raises AttributeError on that cfg: no history_step).  Structure and values; the Flat id (articulation joint order) is refused
+    like the reference's exporter refuses cfgs without preserve_order."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.deploy import deploy_config
+    d = deploy_config(tasks.rsl_env_cfg(8))
+    assert (d["control_dt"], d["history_length"], d["history_step"], d["action_scale"], d["velocity_deadzone"]) == (0.02, 6, 1, 0.25, 0.0)
+    assert d["command_ranges"] == {"lin_vel_x": [-1.0, 1.0], "lin_vel_y": [-1.0, 1.0], "ang_vel_z": [-1.0, 1.0]}
+    assert [(o["name"], o["scale"]) for o in d["observations"]] == [("base_ang_vel", 0.25), ("projected_gravity", 1), ("generated_commands", 1),
+                                                                   ("joint_pos_rel", 1), ("joint_vel_rel", 0.05), ("last_action", 1)]
+    assert [j["name"] for j in d["joints"]][:4] == ["left_hip_yaw_joint", "left_hip_pitch_joint", "left_hip_roll_joint", "left_knee_joint"]
+    assert d["joints"][3] == {"name": "left_knee_joint", "kp": 300.0, "kd": 4.0, "default_joint_pos": 0.36, "enabled": True}
+    with pytest.raises(ValueError, match="preserve_order"):
+        deploy_config(tasks.default_env_cfg(8))
+
+
+@pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
+def test_deploy_config_matches_the_env_yaml_the_reference_ships(tmp_path):
+    """... and it is the document the reference ships next to its Rsl-trained policy (scripts/deploy/policies/demo_rsl/env.yaml):
+    every key equal; the shipped file additionally lists the 15 disabled upper-body joints of the real robot."""
+    import yaml
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.deploy import write_deploy_config
+    mine = write_deploy_config(tasks.rsl_env_cfg(8), str(tmp_path / "env.yaml"))
+    assert yaml.safe_load(open(tmp_path / "env.yaml")) == mine
+    shipped = yaml.load(open(os.path.join(REF, "scripts", "deploy", "policies", "demo_rsl", "env.yaml")), Loader=yaml.UnsafeLoader)
+    for k in ("control_dt", "history_length", "history_step", "action_scale", "velocity_deadzone", "command_ranges"):
+        assert mine[k] == shipped[k], k
+    assert [(o["name"], o.get("scale") or 1) for o in mine["observations"]] == [(o["name"], o.get("scale") or 1) for o in shipped["observations"]]
+    assert mine["joints"] == shipped["joints"][:12]
+    assert all(not j["enabled"] for j in shipped["joints"][12:])

@@ -89,14 +89,19 @@ def _history_case(backend_cls, cfg):
     return worst
 
 
-def _deploy_case(backend_cls, cfg):
-    g = np.load(os.path.join(GOLD, "deploy_obs.npz"))
+def _deploy_case(backend_cls, cfg, fixture="deploy_obs.npz"):
+    g = np.load(os.path.join(GOLD, fixture))
+    if fixture == "deploy_obs_rsl.npz":  # the Rsl id's format == the env.yaml the reference ships (history 6, scaled gyro / joint velocity)
+        from h1v2_isaac_b200._capi import rsl_config
+        cfg = rsl_config()
     c = cfg.copy(); c.enable_corruption = 0
     for i in range(12):
         c.joint_perm[i] = i  # deployment / Rsl order: MJCF leg-major (robots/h12.py:40-53 "preserved order for sim2sim")
+    H = c.history_length
+    assert g["obs"].shape[1] == 45 * H
     b = backend_cls(c, 1)
     for t in range(g["obs"].shape[0]):
-        cmd = g["obs"][t][60 + 27:90]  # newest command of the golden row (ObservationHandler.generated_commands)
+        cmd = g["obs"][t][6 * H + 3 * (H - 1):9 * H]  # newest command of the golden row (ObservationHandler.generated_commands)
         expect = (g["cmd_unit"][t] + 1) / 2 * (g["cmd_upper"] - g["cmd_lower"]) + g["cmd_lower"]
         np.testing.assert_allclose(cmd, expect, atol=1e-6)
         b.set_state({"root_quat": g["quat"][t][None], "root_ang_vel": g["ang"][t][None], "command": cmd[None], "joint_pos": g["q"][t][None],
@@ -109,8 +114,9 @@ def test_oracle_history_against_reference_circular_buffer(cfg):
     assert _history_case(_OracleBackend, cfg) < 2e-6
 
 
-def test_oracle_against_reference_deploy_observation_handler(cfg):
-    _deploy_case(_OracleBackend, cfg)
+@pytest.mark.parametrize("fixture", ["deploy_obs.npz", "deploy_obs_rsl.npz"])
+def test_oracle_against_reference_deploy_observation_handler(cfg, fixture):
+    _deploy_case(_OracleBackend, cfg, fixture)
 
 
 @pytest.mark.parametrize("thr", [0.4, 0.5])
@@ -224,5 +230,6 @@ def test_cuda_history_against_reference_circular_buffer(cfg):
 
 
 @pytest.mark.gpu
-def test_cuda_against_reference_deploy_observation_handler(cfg):
-    _deploy_case(_GpuBackend, cfg)
+@pytest.mark.parametrize("fixture", ["deploy_obs.npz", "deploy_obs_rsl.npz"])
+def test_cuda_against_reference_deploy_observation_handler(cfg, fixture):
+    _deploy_case(_GpuBackend, cfg, fixture)
