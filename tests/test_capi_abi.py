@@ -29,10 +29,11 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_c(tmp_path):
     from h1v2_isaac_b200 import _capi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "h1v2_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(H1v2Config), sizeof(H1v2State), offsetof(H1v2Config, rew_weight), offsetof(H1v2Config, env_id_offset), offsetof(H1v2Config, history_length));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "h1v2_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(H1v2Config), sizeof(H1v2State), offsetof(H1v2Config, rew_weight), offsetof(H1v2Config, env_id_offset), offsetof(H1v2Config, history_length), offsetof(H1v2Config, command_class), offsetof(H1v2Config, root_link_com), offsetof(H1v2Config, reserved));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b, c, d, e = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c, d, e, f, g, h = map(int, subprocess.check_output([str(exe)]).split())
+    assert (_capi.H1v2Config.command_class.offset, _capi.H1v2Config.root_link_com.offset, _capi.H1v2Config.reserved.offset) == (f, g, h)
     assert C.sizeof(_capi.H1v2Config) == a and C.sizeof(_capi.H1v2State) == b
     assert _capi.H1v2Config.rew_weight.offset == c and _capi.H1v2Config.env_id_offset.offset == d
     assert _capi.H1v2Config.history_length.offset == e
