@@ -34,6 +34,30 @@ def rsl_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
     return env_cfg_from_config(rsl_config(), num_envs, device, rew_names=RSL_REW_NAMES, curriculum=RSL_CURRICULUM, curriculum_steps=24 * 5000)
 
 
+def flat_play_env_cfg(num_envs: int = 50, device: str = "cuda:0"):
+    """Isaac-Velocity-Flat-H12_12dof-Play-v0 (C12/flat_env_cfg.py:51-66): 50 envs, no observation noise, no pushes."""
+    from ._capi import default_config
+    c = default_config()
+    c.enable_corruption = 0
+    c.push_enable = 0
+    return env_cfg_from_config(c, num_envs, device)
+
+
+def rsl_play_env_cfg(num_envs: int = 100, device: str = "cuda:0"):
+    """Isaac-Velocity-Rsl-H12_12dof-Play-v0 (C12/rsl_env_cfg.py:543-564): 100 envs, no noise, no pushes, no friction
+    randomisation (the asset's own material), forward command 0.5 m/s."""
+    from ._capi import default_config, rsl_config
+    c, d = rsl_config(), default_config()
+    c.enable_corruption = 0
+    c.push_enable = 0
+    c.friction, c.solver_iterations = d.friction, d.solver_iterations
+    c.friction_range[0] = c.friction_range[1] = d.friction
+    c.cmd_lin_x[0] = c.cmd_lin_x[1] = 0.5
+    c.cmd_lin_y[0] = c.cmd_lin_y[1] = 0.0
+    c.cmd_ang_z[0] = c.cmd_ang_z[1] = 0.0
+    return env_cfg_from_config(c, num_envs, device, rew_names=RSL_REW_NAMES, curriculum=RSL_CURRICULUM, curriculum_steps=24 * 5000)
+
+
 def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_names=None, curriculum=(), curriculum_steps=0):
     """Inverse of env.flatten_cfg: an H1v2Config -> a ManagerBasedRLEnvCfg-shaped tree built from the shim cfg classes."""
     from . import shims
@@ -195,7 +219,8 @@ def register() -> bool:
     shims.install()
     import gymnasium as gym
     done = False
-    for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg")):
+    for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg"),
+                         (TASK_ID.replace("-v0", "-Play-v0"), "flat_play_env_cfg"), (RSL_TASK_ID.replace("-v0", "-Play-v0"), "rsl_play_env_cfg")):
         try:
             gym.spec(tid)
             continue

@@ -62,6 +62,25 @@ def test_self_contained_rsl_task_roundtrip():
     assert gym.spec(tasks.RSL_TASK_ID).kwargs["env_cfg_entry_point"]
 
 
+def test_self_contained_play_ids_equal_the_reference_play_cfgs():
+    """tasks.flat_play_env_cfg / rsl_play_env_cfg against the reference's own Play cfg classes (C12/flat_env_cfg.py:51-66,
+    C12/rsl_env_cfg.py:543-564), flattened in tests/golden/play_cfg_resolved.json: scene size, noise off, pushes and friction
+    randomisation off, fixed forward command for the Rsl one."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.env import config_to_dict, flatten_cfg
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))
+    tasks.register()
+    import gymnasium as gym
+    for tid, make in (("Isaac-Velocity-Flat-H12_12dof-Play-v0", tasks.flat_play_env_cfg), ("Isaac-Velocity-Rsl-H12_12dof-Play-v0", tasks.rsl_play_env_cfg)):
+        tree = make()
+        mine = config_to_dict(flatten_cfg(tree))
+        assert tree.scene.num_envs == gold[tid]["num_envs"]
+        for k, v in gold[tid]["kernel_config"].items():
+            assert _close(mine[k], v), (tid, k)
+        assert mine["enable_corruption"] == 0 and mine["push_enable"] == 0
+        assert gym.spec(tid).kwargs["env_cfg_entry_point"]
+
+
 def test_self_contained_task_roundtrip(cfg):
     """tasks.default_env_cfg() is flatten_cfg's inverse on the default; registration uses the reference's id and kwargs."""
     from h1v2_isaac_b200 import tasks
@@ -127,6 +146,8 @@ def test_reference_cfg_tree_flattens_to_golden():
     again = json.load(open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json")))
     assert again == GOLD  # regenerating from the reference changes nothing
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json"))) == GOLD_RSL
+    assert set(json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))) == {
+        "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0"}
 
 
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
