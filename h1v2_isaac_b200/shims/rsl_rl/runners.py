@@ -360,6 +360,14 @@ class OnPolicyRunner:
                 vals = [torch.as_tensor(e[key], dtype=torch.float32, device=self.device).reshape(-1) for e in ep_infos if key in e]
                 if vals:
                     ep[key] = torch.cat(vals).mean().item()
+        if self.is_distributed:  # the packed extras["log"] means, one small all-reduce per iteration (every rank logs the job's mean)
+            keys = sorted(ep)
+            n_keys = torch.tensor([len(keys), -len(keys)], device=self.device)
+            dist.all_reduce(n_keys, op=dist.ReduceOp.MAX)
+            if len(keys) > 0 and int(n_keys[0]) == len(keys) == -int(n_keys[1]):  # same key set on every rank (always, with this env)
+                t = torch.tensor([ep[k] for k in keys], dtype=torch.float32, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                ep = dict(zip(keys, (t / self.gpu_world_size).tolist()))
         self.stats = {**stats, **{f"episode/{k}": v for k, v in ep.items()}}
         if self.disable_logs:
             return

@@ -37,7 +37,10 @@ class OracleVecEnv:
     def step(self, a):
         obs, rew, term, trunc = self.o.step(a.numpy().astype(np.float32))
         self._obs = torch.from_numpy(obs)
-        return self._obs, torch.from_numpy(rew), torch.from_numpy(term | trunc).long(), {"time_outs": torch.from_numpy(trunc), "observations": {"policy": self._obs}}
+        rank, _ = H1v2ManagerBasedRLEnv._dist_info()
+        return self._obs, torch.from_numpy(rew), torch.from_numpy(term | trunc).long(), {
+            "time_outs": torch.from_numpy(trunc), "observations": {"policy": self._obs},
+            "log": {"Probe/rank_plus_one": torch.tensor(float(rank + 1))}}  # rank-dependent: the runner must log the mean over ranks
 
 
 def main():
@@ -51,11 +54,11 @@ def main():
            "algorithm": {"value_loss_coef": 1.0, "use_clipped_value_loss": True, "clip_param": 0.2, "entropy_coef": 0.0081, "num_learning_epochs": 2,
                          "num_mini_batches": 2, "learning_rate": 1e-3, "schedule": "adaptive", "gamma": 0.99, "lam": 0.95, "desired_kl": 0.01,
                          "max_grad_norm": 1.0}}
-    runner = OnPolicyRunner(env, cfg, log_dir=None, device="cpu")
+    runner = OnPolicyRunner(env, cfg, log_dir=os.path.join(os.path.dirname(out_path), "logs"), device="cpu")  # book-keeping needs a log dir
     runner.learn(2, init_at_random_ep_len=False)
     flat = torch.cat([p.detach().reshape(-1) for p in runner.alg.policy.parameters()])
     json.dump({"rank": rank, "world": runner.gpu_world_size, "param_sum": float(flat.double().sum()), "param_abs": float(flat.double().abs().sum()),
-               "lr": float(runner.alg.lr), "root_pos": first["root_pos"].tolist(), "command": first["command"].tolist()}, open(out_path, "w"))
+               "lr": float(runner.alg.lr), "probe": runner.stats.get("episode/Probe/rank_plus_one"), "root_pos": first["root_pos"].tolist(), "command": first["command"].tolist()}, open(out_path, "w"))
 
 
 if __name__ == "__main__":

@@ -9,6 +9,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -37,6 +38,8 @@ def test_world_size_2_gloo(tmp_path, cfg):
     assert abs(r[0]["param_sum"] - r[1]["param_sum"]) < 1e-6 * max(1.0, abs(r[0]["param_sum"]))
     assert abs(r[0]["param_abs"] - r[1]["param_abs"]) < 1e-6 * r[0]["param_abs"]
     assert r[0]["lr"] == r[1]["lr"]
+    # (3) rollout statistics: extras["log"] entries are reduced over ranks (rank r reports r + 1; both must log 1.5)
+    assert r[0]["probe"] == pytest.approx(1.5) and r[1]["probe"] == pytest.approx(1.5)
     # (1) the two shards are the two halves of one 32-env job
     from oracle.oracle import Oracle
     whole = Oracle(cfg, 32, seed=42, threads=2)
