@@ -2,8 +2,12 @@ import sys
 sys.path.insert(0, '/root/repo')
 import torch
 from h1v2_isaac_b200.backend import H1v2Sim
-from h1v2_isaac_b200._capi import default_config
-for n in (1024, 2048, 4096, 8192, 16384):
+from h1v2_isaac_b200._capi import default_config, rsl_config
+"""Step time vs envs per warp (reserved[2] override).  usage: python tools/diag_epw.py [flat|rsl]"""
+task = sys.argv[1] if len(sys.argv) > 1 else "flat"
+default_config = rsl_config if task == "rsl" else default_config
+print("task", task)
+for n in (1024, 2048, 4096, 8192, 16384, 32768):
     row = []
     for epw in (16, 8, 4, 2):
         cfg = default_config(); cfg.reserved[2] = epw
