@@ -114,6 +114,16 @@ def test_tail_parity_ideal_pd_and_union_rewards(cfg):
     _tail_parity(c, 2048, 30, 30, min_term=0)  # action scale 0.25: nobody falls within 30 steps
 
 
+@pytest.mark.parametrize("H", [1, 3])
+def test_tail_parity_short_histories(cfg, H):
+    """History 1 is the deployment format without stacking (D/controllers/rl.py with history_length 1, a 45-float observation: less
+    than two 32-column passes of the flatten), 3 an odd length: ring indexing, first-push back-fill and flatten must not depend on
+    the Flat id's 10."""
+    c = cfg.copy()
+    c.history_length = H
+    _tail_parity(c, 1024, 16, 0, min_term=0)
+
+
 def test_tail_parity_rsl_task():
     """the resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (C12/rsl_env_cfg.py:44-540; tests/golden/
     rsl_cfg_resolved.json pins it to the reference's own cfg classes): IdealPD, action scale 0.25, history 6, scaled gyro / joint
