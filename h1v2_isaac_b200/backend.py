@@ -109,6 +109,8 @@ class H1v2Sim:
             self._check(self._lib.h1v2_reset(self._h, None, 0, self._stream()))
         else:
             ids = env_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            if ids.numel() == 0:  # an empty tensor has a NULL data pointer, which the C ABI reads as "all envs"
+                return
             self._check(self._lib.h1v2_reset(self._h, ids.data_ptr(), ids.numel(), self._stream()))
             self._keep = ids
 

@@ -182,3 +182,49 @@ def test_contact_list_overflow_is_reported(cfg):
     sim.step(torch.zeros((n, 12), device="cuda"))
     assert sim.log_host()[LOG_CONTACT_OVERFLOW] >= 2 * n  # both legs of every env, at least in the first substep
     sim.close()
+
+
+def test_c_abi_edge_cases(cfg):
+    """Boundary behaviour of the C ABI: one env, empty and partial reset lists, refused configs and arguments with a message."""
+    import ctypes as C
+    import torch
+    from h1v2_isaac_b200 import _capi
+    from h1v2_isaac_b200.backend import H1v2Sim
+    lib = _capi.load_library()
+    one = H1v2Sim(1, cfg, device="cuda:0", seed=5)
+    o0 = one.observe()
+    assert o0.shape == (1, 450) and torch.isfinite(o0).all()
+    o, r, t, u = one.step(torch.zeros((1, 12), device="cuda"))
+    assert torch.isfinite(o).all() and torch.isfinite(r).all() and not t.any() and not u.any()
+    one.close()
+    n = 64
+    sim = H1v2Sim(n, cfg, device="cuda:0", seed=5)
+    sim.observe()
+    for _ in range(3):
+        sim.step(torch.randn((n, 12), device="cuda"))
+    before = sim.get_state(["joint_pos", "root_pos"])
+    sim.reset(torch.empty(0, dtype=torch.int64))  # empty id list: nothing happens
+    after = sim.get_state(["joint_pos", "root_pos"])
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    ids = torch.tensor([3, 17, 63])
+    sim.reset(ids)
+    st = sim.get_state(["joint_pos", "root_pos", "fresh"])
+    q0 = torch.tensor(list(cfg.default_joint_pos), device="cuda")
+    assert torch.allclose(st["joint_pos"][ids.cuda()], q0.expand(3, 12), atol=1e-6) and (st["root_pos"][ids.cuda(), 2] == cfg.init_root_height).all()
+    keep = torch.ones(n, dtype=torch.bool); keep[ids] = False
+    assert torch.equal(st["joint_pos"][keep.cuda()], before["joint_pos"][keep.cuda()])
+    assert (st["fresh"][ids.cuda(), 0] != 0).all() and (st["fresh"][keep.cuda(), 0] == 0).all()
+    # refused arguments: error code and a message, never a crash
+    w = (C.c_float * _capi.NUM_REW)(*([float("nan")] + [0.0] * (_capi.NUM_REW - 1)))
+    assert lib.h1v2_set_reward_weights(sim._h, w) != 0 and b"non-finite" in lib.h1v2_last_error()
+    assert lib.h1v2_step(sim._h, None, None, None, None, None, None) != 0 and b"bad arguments" in lib.h1v2_last_error()
+    sim.close()
+    h = C.c_void_p()
+    for field, value, msg in (("history_length", 0, b"history_length"), ("history_length", 11, b"history_length"), ("max_delay", 9, b"delays"),
+                              ("command_class", 2, b"command_class")):
+        c = cfg.copy(); setattr(c, field, value)
+        assert lib.h1v2_create(C.byref(c), 8, 0, 1, C.byref(h)) != 0 and msg in lib.h1v2_last_error(), field
+    c = _capi.rsl_config(); c.velocity_deadzone = 0.1
+    assert lib.h1v2_create(C.byref(c), 8, 0, 1, C.byref(h)) != 0 and b"velocity_deadzone" in lib.h1v2_last_error()
+    assert lib.h1v2_create(C.byref(cfg), 0, 0, 1, C.byref(h)) != 0
+    assert lib.h1v2_create(C.byref(cfg), 8, 99, 1, C.byref(h)) != 0  # no such device
