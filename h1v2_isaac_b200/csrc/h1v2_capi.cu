@@ -25,6 +25,17 @@ static int fail(const std::string& m) {
     cudaError_t e_ = (call);                                                                          \
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
   } while (0)
+// Every entry point runs on the handle's device whatever the caller's current device is, and leaves the caller's current
+// device as it found it (a process may hold handles on several GPUs, e.g. one trainer thread per GPU).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false, ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev) { ok = cudaSetDevice(dev) == cudaSuccess; changed = ok; }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
 // inside h1v2_create, once the handle exists: release it on failure
 #define CKH(call)                                                                                     \
   do {                                                                                                \
@@ -409,7 +420,9 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail("h1v2_create: no CUDA device (the CUDA path is the product; there is no CPU fallback)");
-  CK(cudaSetDevice(device));
+  if (device < 0 || device >= ndev) return fail("h1v2_create: no such CUDA device");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("h1v2_create: cudaSetDevice failed");
   H1v2Handle* h = new H1v2Handle();
   h->cfg = *cfg; h->n = n_envs; h->device = device; h->seed = seed;
   if (build_params(*cfg, n_envs, seed, h->P) != 0) { delete h; return -1; }
@@ -456,7 +469,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
 
 void h1v2_destroy(H1v2Handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : {(void*)h->d_act, (void*)h->d_obs, (void*)h->d_rew, (void*)h->d_term, (void*)h->d_trunc})
@@ -471,6 +484,7 @@ int64_t h1v2_launch_count(const H1v2Handle* h) { return h ? h->launches : -1; }
 
 int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length) {
   if (!h) return fail("null handle");
+  DeviceGuard guard(h->device);
   if (episode_length) {
     CK(cudaMemcpy(episode_length, h->S.ep_len, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice));
     h->S.ep_len = episode_length;
@@ -482,6 +496,7 @@ int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length) {
 
 int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stream) {
   if (!h) return fail("null handle");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int cnt = env_ids ? n : h->n;
   if (cnt <= 0) return 0;
@@ -492,6 +507,7 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
 }
 
 static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st) {
+  DeviceGuard guard(h->device);
   const int threads = H1V2_BLOCK;
   const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
   const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(float);
@@ -522,6 +538,7 @@ int h1v2_step(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8
 
 int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated) {
   if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step_host: bad arguments");
+  DeviceGuard guard(h->device);
   const size_t N = (size_t)h->n, od = (size_t)h->P.obs_dim;
   if (!h->d_act) {
     CK(cudaMalloc(&h->d_act, N * 12 * sizeof(float)));
@@ -561,6 +578,7 @@ int h1v2_set_reward_weights(H1v2Handle* h, const float* weights) {
 }
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
   if (!h || !dst) return fail("h1v2_get_state: bad arguments");
+  DeviceGuard guard(h->device);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *dst, 0);
   h->launches += 1;
   CK(cudaGetLastError());
@@ -568,6 +586,7 @@ int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
 }
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream) {
   if (!h || !src) return fail("h1v2_set_state: bad arguments");
+  DeviceGuard guard(h->device);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *src, 1);
   h->launches += 1;
   CK(cudaGetLastError());
@@ -580,19 +599,22 @@ int h1v2_get_log(H1v2Handle* h, const float** log_dev) {
 }
 int h1v2_debug_iter_hist(H1v2Handle* h, float* hist32) {
   if (!h || !hist32) return fail("h1v2_debug_iter_hist: bad arguments");
+  DeviceGuard guard(h->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(hist32, h->S.acc + H1V2_LOG_DIM, sizeof(float) * 32, cudaMemcpyDeviceToHost));
   return 0;
 }
 int h1v2_get_log_host(H1v2Handle* h, float* log_host) {
   if (!h || !log_host) return fail("h1v2_get_log_host: bad arguments");
+  DeviceGuard guard(h->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(log_host, h->S.log, sizeof(float) * H1V2_LOG_DIM, cudaMemcpyDeviceToHost));
   return 0;
 }
 int h1v2_measure_fp32_peak(int32_t device, float* tflops) {
   if (!tflops) return fail("h1v2_measure_fp32_peak: bad arguments");
-  CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("h1v2_measure_fp32_peak: no such CUDA device");
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
@@ -618,6 +640,7 @@ int h1v2_measure_fp32_peak(int32_t device, float* tflops) {
 
 int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream) {
   if (!h || !actions) return fail("h1v2_random_actions: bad arguments");
+  DeviceGuard guard(h->device);
   random_actions_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(h->P, actions, step);
   h->launches += 1;
   CK(cudaGetLastError());

@@ -30,7 +30,9 @@
  * Conventions: plain pointers and sizes only; every device pointer is borrowed for the duration of the
  * call; persistent state is owned by the handle; calls enqueue work on the given CUDA stream and never
  * synchronise (except *_host and get_log_host, which must); return 0 on success, negative on error with a
- * thread-local message from h1v2_last_error().  One handle per process per GPU.
+ * thread-local message from h1v2_last_error().  One handle per process per GPU is the intended use; a process that holds
+ * handles on several GPUs may call them with any current device (each call runs on its handle's device and restores the
+ * caller's).  env_ids / n of h1v2_reset: a NULL list means "all envs" whatever n is.
  */
 #ifndef H1V2_B200_H
 #define H1V2_B200_H

@@ -228,3 +228,27 @@ def test_c_abi_edge_cases(cfg):
     assert lib.h1v2_create(C.byref(c), 8, 0, 1, C.byref(h)) != 0 and b"velocity_deadzone" in lib.h1v2_last_error()
     assert lib.h1v2_create(C.byref(cfg), 0, 0, 1, C.byref(h)) != 0
     assert lib.h1v2_create(C.byref(cfg), 8, 99, 1, C.byref(h)) != 0  # no such device
+
+
+def test_handle_runs_on_its_own_device_whatever_the_current_device_is(cfg):
+    """A process may hold handles on several GPUs: every C-ABI call runs on the handle's device and leaves the caller's
+    current device alone.  Needs two GPUs (skipped on a one-GPU box)."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 256
+    a0, a1 = H1v2Sim(n, cfg, device="cuda:0", seed=3), H1v2Sim(n, cfg, device="cuda:1", seed=3)
+    assert torch.cuda.current_device() == 0
+    o0, o1 = a0.observe(), a1.observe()
+    assert o1.device.index == 1 and torch.equal(o0.cpu(), o1.cpu())
+    g = torch.Generator().manual_seed(1)
+    for _ in range(6):
+        a = torch.randn((n, 12), generator=g)
+        r0, r1 = a0.step(a.to("cuda:0")), a1.step(a.to("cuda:1"))
+        assert torch.cuda.current_device() == 0
+        for x, y in zip(r0, r1):
+            assert torch.equal(x.cpu(), y.cpu())
+    a1.reset(torch.tensor([1, 2, 3]))
+    assert a1.log_host().shape == a0.log_host().shape
+    a0.close(); a1.close()
