@@ -485,12 +485,12 @@ int64_t h1v2_launch_count(const H1v2Handle* h) { return h ? h->launches : -1; }
 int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length) {
   if (!h) return fail("null handle");
   DeviceGuard guard(h->device);
-  if (episode_length) {
-    CK(cudaMemcpy(episode_length, h->S.ep_len, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice));
-    h->S.ep_len = episode_length;
-  } else {
-    h->S.ep_len = h->own_ep_len;
-  }
+  // rare call: wait for every step in flight (on whatever stream), then move the counters to their new home
+  int64_t* to = episode_length ? episode_length : h->own_ep_len;
+  if (to == h->S.ep_len) return 0;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(to, h->S.ep_len, sizeof(int64_t) * h->n, cudaMemcpyDeviceToDevice));
+  h->S.ep_len = to;
   return 0;
 }
 

@@ -230,7 +230,8 @@ const char* h1v2_last_error(void);
 int h1v2_obs_dim(const H1v2Handle* h);
 int h1v2_num_envs(const H1v2Handle* h);
 
-/* episode_length_buf: int64[N] device buffer owned by the caller, read and written by every step */
+/* episode_length_buf: int64[N] device buffer owned by the caller, read and written by every step.  Binding copies the current
+ * counters into it; NULL un-binds (the counters move back into the handle).  Synchronises the device (rare call). */
 int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length);
 
 /* Reset envs.  env_ids == NULL resets all.  No observation is produced (use h1v2_observe). */

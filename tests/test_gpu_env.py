@@ -252,3 +252,46 @@ def test_handle_runs_on_its_own_device_whatever_the_current_device_is(cfg):
     a1.reset(torch.tensor([1, 2, 3]))
     assert a1.log_host().shape == a0.log_host().shape
     a0.close(); a1.close()
+
+
+def test_state_round_trip_and_streams(cfg):
+    """set_state(get_state()) is the identity (the run continues bit-identically to an untouched twin), calls on a side stream
+    give the same results as on the default stream, and un-binding the caller's episode_length buffer keeps the counters."""
+    import ctypes as C
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    from h1v2_isaac_b200._capi import READ_ONLY_STATE, STATE_FIELDS
+    n = 512
+    a, b, c = (H1v2Sim(n, cfg, device="cuda:0", seed=11) for _ in range(3))
+    for s in (a, b, c):
+        s.observe()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    acts = [torch.randn((n, 12), device="cuda", generator=g) for _ in range(12)]
+    side = torch.cuda.Stream()
+    for k in range(6):
+        ra, rb = a.step(acts[k]), b.step(acts[k])
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # everything of c is enqueued on the side stream
+            rc = c.step(acts[k])
+        side.synchronize()
+        for x, y, z in zip(ra, rb, rc):
+            assert torch.equal(x, y) and torch.equal(x, z)
+    names = [nm for nm, _, _ in STATE_FIELDS if nm not in READ_ONLY_STATE]
+    b.set_state(b.get_state(names))
+    for k in range(6, 12):
+        ra, rb = a.step(acts[k]), b.step(acts[k])
+        for x, y in zip(ra, rb):
+            assert torch.equal(x, y), k
+    # un-bind: the handle copies the counters back into its own buffer and keeps counting there
+    ep = a.episode_length_buf.clone()
+    assert a._lib.h1v2_bind_episode_length(a._h, None) == 0
+    a.episode_length_buf.fill_(-5)  # the caller's old buffer is no longer read or written
+    a.step(acts[0])
+    assert (a.episode_length_buf == -5).all()
+    own = torch.zeros(n, dtype=torch.int64, device="cuda")
+    assert a._lib.h1v2_bind_episode_length(a._h, C.c_void_p(own.data_ptr())) == 0  # re-bind: receives the current counters
+    torch.cuda.synchronize()
+    done = own == 0
+    assert torch.equal(own[~done], ep[~done] + 1)
+    for s in (a, b, c):
+        s.close()
