@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     // ---- non-finite / runaway guard ----
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !(fabsf(qd[k]) <= P.runaway_vel);
+    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !(fabsf(qd[k]) <= P.runaway_vel) || !(fabsf(la[k]) <= H1V2_ACTION_ABS_MAX);
 #pragma unroll
     for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !(fabsf(rv[k]) <= P.runaway_vel) || !(fabsf(rw[k]) <= P.runaway_vel);
     bad |= !isfinite(rq[0]) || !isfinite(rq[1]) || !isfinite(rq[2]) || !isfinite(rq[3]);

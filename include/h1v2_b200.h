@@ -49,6 +49,8 @@ extern "C" {
 #define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
 #define H1V2_MAX_HISTORY 10 /* the reference tasks use 10 (Flat), 6 (Rsl) and 1 (deploy) */
 #define H1V2_LOG_DIM 32      /* see h1v2_get_log */
+#define H1V2_ACTION_ABS_MAX 1.0e6f /* an env whose action is non-finite or larger than this in magnitude is force-reset in that step
+                                      (zero reward, terminated, counted in H1V2_LOG_NAN_RESETS), like a non-finite state */
 
 /* reward term slots; weights[i]==0 means "term not in the cfg" (RewardManager skips zero weights) */
 enum {

@@ -945,6 +945,9 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   for (int i = 0; i < 19; i++) if (!isfinite(e->qpos[i])) bad = 1;
   const double runaway = c->runaway_vel > 0.f ? (double)c->runaway_vel : 3.0e38;
   for (int i = 0; i < 18; i++) if (!(fabs((double)(float)e->qvel[i]) <= runaway)) bad = 1;
+  /* an action that is non-finite or absurdly large (|a| > H1V2_ACTION_ABS_MAX) is contained the same way: the effort clip keeps the
+   * physics finite, but last_action (an observation term) and action_rate_l2 would carry it on */
+  for (int j = 0; j < NJ; j++) if (!(fabsf(e->last_action[j]) <= H1V2_ACTION_ABS_MAX)) bad = 1;
   *nan_flag = bad;
   /* -- counters, terminations -- */
   e->ep_len += 1;

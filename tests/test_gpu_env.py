@@ -295,3 +295,36 @@ def test_state_round_trip_and_streams(cfg):
     assert torch.equal(own[~done], ep[~done] + 1)
     for s in (a, b, c):
         s.close()
+
+
+def test_non_finite_and_huge_actions_are_contained(cfg):
+    """A policy that emits NaN / Inf / 1e30 for some envs must not poison anything: those envs are force-reset in the same
+    step (terminated, zero reward, finite post-reset observation, counted in the log), every other env is bit-identical to a
+    twin run that never saw the bad actions."""
+    import torch
+    from h1v2_isaac_b200._capi import LOG_NAN_RESETS
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 256
+    a, b = H1v2Sim(n, cfg, device="cuda:0", seed=7), H1v2Sim(n, cfg, device="cuda:0", seed=7)
+    a.observe(); b.observe()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bad_ids = torch.tensor([0, 1, 2, 3, 100], device="cuda")
+    ok = torch.ones(n, dtype=torch.bool, device="cuda"); ok[bad_ids] = False
+    for k in range(6):
+        act = torch.randn((n, 12), device="cuda", generator=g)
+        poisoned = act.clone()
+        if k == 2:
+            poisoned[0, 3] = float("nan"); poisoned[1, :] = float("inf"); poisoned[2, 0] = 1e30; poisoned[3, 7] = -1e30; poisoned[100, :] = float("nan")
+        oa, ra, ta, ua = a.step(poisoned)
+        ob, rb, tb, ub = b.step(act)
+        assert torch.isfinite(oa).all() and torch.isfinite(ra).all(), k
+        if k < 2:
+            assert torch.equal(oa, ob) and torch.equal(ra, rb)
+        if k == 2:
+            assert ta[bad_ids].all() and (ra[bad_ids] == 0).all()
+            assert a.log_host()[LOG_NAN_RESETS] >= 5
+        if k >= 2:  # the healthy envs never notice
+            assert torch.equal(oa[ok], ob[ok]) and torch.equal(ra[ok], rb[ok]) and torch.equal(ta[ok], tb[ok])
+    st = a.get_state(["joint_pos", "joint_vel", "root_pos", "root_quat", "last_action"])
+    assert all(torch.isfinite(v).all() for v in st.values())
+    a.close(); b.close()
