@@ -250,7 +250,8 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
                    uint8_t* truncated);
 
 /* Replace the reward weights (CurriculumManager's modify_reward_weight, rsl_env_cfg.py:447-497).  Host array of
- * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises. */
+ * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises.  (h1v2_step is CUDA-graph
+ * capturable; a captured step keeps the parameter block of capture time, so re-capture after changing the weights.) */
 int h1v2_set_reward_weights(H1v2Handle* h, const float* weights);
 
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
