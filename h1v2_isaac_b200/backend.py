@@ -38,6 +38,7 @@ class H1v2Sim:
         self.num_envs = int(num_envs)
         self._h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)  # "cuda" without an index would never compare equal to a tensor's device
         with torch.cuda.device(idx):
             rc = self._lib.h1v2_create(C.byref(self.cfg), self.num_envs, idx, seed, C.byref(self._h))
             if rc != 0:
