@@ -124,6 +124,40 @@ def test_tail_parity_short_histories(cfg, H):
     _tail_parity(c, 1024, 16, 0, min_term=0)
 
 
+@pytest.mark.parametrize("task", ["flat", "rsl"])
+def test_natural_command_resample_parity(cfg, task):
+    """CommandTerm.compute's own resample (time_left <= 0, not a reset): the draws come from Philox blocks 2-3 of the command
+    stream, the new time_left from the cfg's range; masks and values must match the oracle bit for bit."""
+    from h1v2_isaac_b200._capi import rsl_config
+    c = rsl_config() if task == "rsl" else cfg
+    n = 1024
+    torch, sim, orc = _mk(c, n, 31)
+    sim.observe(); orc.observe()
+    tl = np.full((n, 1), 50.0, np.float32)
+    tl[::3] = 0.03; tl[1::7] = 0.05  # these run out in the 2nd and 3rd step
+    sim.set_state({"time_left": tl}); orc.set_state({"time_left": tl})
+    n_nat = 0
+    for step in range(4):
+        a = np.zeros((n, 12), np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        g = _np(sim.get_state(SYNC + POST))
+        _, _, to, uo = orc.step_injected(a, g)
+        o = orc.get_state(SYNC)
+        assert not to.any() and not uo.any() and not tg.any()
+        assert np.array_equal(g["time_left"], o["time_left"]) and np.array_equal(g["command"][:, :2], o["command"][:, :2])
+        if c.heading_command:  # the yaw-rate command is 0.5 * wrap(target - atan2(...)): float vs double atan2, not a draw
+            np.testing.assert_allclose(g["command"][:, 2], o["command"][:, 2], atol=2e-6)
+        else:
+            assert np.array_equal(g["command"][:, 2], o["command"][:, 2])
+        assert np.array_equal(g["is_standing"], o["is_standing"]) and np.array_equal(g["heading_target"], o["heading_target"])
+        n_nat += int((g["time_left"][:, 0] > tl[:, 0]).sum())
+        tl = g["time_left"].copy()
+        _resync(sim, orc, g)
+    lo = float(c.cmd_resample_time[0])
+    assert n_nat >= n // 3 and (tl[::3, 0] >= lo - 0.1).all()
+    sim.close()
+
+
 def test_tail_parity_rsl_task():
     """the resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (C12/rsl_env_cfg.py:44-540; tests/golden/
     rsl_cfg_resolved.json pins it to the reference's own cfg classes): IdealPD, action scale 0.25, history 6, scaled gyro / joint
