@@ -106,6 +106,7 @@ typedef struct {
   float push_left;
   /* diagnostics */
   double slot_force[NSLOT][3], slot_hist[NSLOT][3], applied_tau[NJ], joint_acc[NJ], rew_terms[NREW], foot_vel[2][3];
+  double slot_hist_diag[NSLOT][3]; /* slot_hist as the terminations / rewards of the last step saw it (before any reset cleared it) */
   int newton_iters;
   double newton_resid;
   double min_abs_dist; /* smallest |signed distance| of any contact candidate at a substep start during the last step */
@@ -956,6 +957,7 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   double Cmax[NSLOT];
   for (int s = 0; s < NSLOT; s++) {
     Cmax[s] = fmax(e->slot_hist[s][0], fmax(e->slot_hist[s][1], e->slot_hist[s][2]));
+    for (int h = 0; h < 3; h++) e->slot_hist_diag[s][h] = e->slot_hist[s][h];
     if (((c->mask_illegal_slots >> s) & 1u) && (float)Cmax[s] > c->contact_threshold) contact = 1;
   }
   if (bad) contact = 1;
@@ -1223,7 +1225,7 @@ int h1v2o_get_state(H1v2Oracle* o, const H1v2State* s) {
   CPY_OUT(mass_add, o->env[i].mass_add, 1, float)
   CPY_OUT(push_time_left, o->env[i].push_left, 1, float)
   CPY_OUT(slot_force, o->env[i].slot_force[k / 3][k % 3], NSLOT * 3, float)
-  CPY_OUT(slot_force_hist, o->env[i].slot_hist[k / 3][k % 3], NSLOT * 3, float)
+  CPY_OUT(slot_force_hist, o->env[i].slot_hist_diag[k / 3][k % 3], NSLOT * 3, float)
   CPY_OUT(applied_torque, o->env[i].applied_tau[k], NJ, float)
   CPY_OUT(joint_acc, o->env[i].joint_acc[k], NJ, float)
   CPY_OUT(reward_terms, o->env[i].rew_terms[k], NREW, float)

@@ -91,6 +91,43 @@ def test_physics_parity_from_identical_states(cfg, decimation, action_scale):
     assert np.median(e["joint_vel"]) < 1e-4
 
 
+def test_fall_contacts_and_termination_decisions_from_identical_states(cfg):
+    """The colliders that only matter when the robot falls (shin capsules, torso box, pelvis sphere; h12_12dof.urdf:116-121,
+    387-392) and the termination they trigger: from identical states the kernel's own physics must give the oracle's contact
+    forces on those bodies (1 % + 0.5 N, envs on an activation boundary excluded) and, but for forces right at the 1 N
+    threshold, the same termination decision."""
+    n = 2048
+    torch, sim, orc = _mk(cfg, n, 41)
+    sim.observe(); orc.observe()
+    rng = np.random.default_rng(8)
+    n_fall_contacts = n_term = n_mismatch = n_steps = 0
+    worst = 0.0
+    for step in range(48):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        _, _, to, uo = orc.step(a)
+        g = _np(sim.get_state(SYNC + ["slot_force", "slot_force_hist"]))
+        o = orc.get_state(["slot_force", "slot_force_hist"])
+        mc, ml = orc.activation_margin()
+        keep = (mc > 2e-6) & (ml > 2e-6)
+        tg = tg.cpu().numpy()
+        # the force history of the last three substeps on the fall bodies (slots 2..5), |F| per substep
+        hg, ho = g["slot_force_hist"].reshape(n, 6, 3)[keep][:, 2:], o["slot_force_hist"].reshape(n, 6, 3)[keep][:, 2:]
+        active = ho > 5.0
+        n_fall_contacts += int(active.sum())
+        if active.any():
+            rel = np.abs(hg - ho)[active] / (0.01 * ho[active] + 0.5)
+            worst = max(worst, float(rel.max()))
+        cmax = ho.max(axis=(1, 2))
+        decided = (cmax < 0.9) | (cmax > 1.1)  # not within 10 % of the 1 N threshold
+        n_mismatch += int((tg[keep] != to[keep])[decided].sum()); n_term += int(to.sum()); n_steps += int(keep.sum())
+        _resync(sim, orc, g)
+    print(f"fall-body force samples {n_fall_contacts}, worst error in units of (1 % + 0.5 N) {worst:.2f}, terminations {n_term}, decision mismatches {n_mismatch} of {n_steps}")
+    assert n_fall_contacts > 300 and n_term > 100
+    assert worst < 0.25  # measured 0.02: the fall-body forces agree to ~2e-4 relative
+    assert n_mismatch == 0
+
+
 def test_tail_parity_on_identical_states(cfg):
     """(a)+(b): the oracle's physics loop is replaced by the kernel's own post-physics values, so everything after the
     physics -- contact-sensor logic, terminations, the reward terms, reset, command resampling, noisy observation with
