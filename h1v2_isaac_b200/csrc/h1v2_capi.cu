@@ -363,11 +363,9 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.rel_standing = c.rel_standing_envs; P.rel_heading = c.rel_heading_envs; P.k_heading = c.heading_stiffness; P.heading_cmd = c.heading_command;
   P.max_command_step = c.cmd_resample_time[1] / P.step_dt;
   if (c.command_class != 0 && c.command_class != 1) return fail("config: command_class must be 0 (UniformVelocityCommand) or 1 (UniformVelocityCommandWithDeadzone)");
-  if (c.command_class == 1 && c.velocity_deadzone != 0.f)
-    return fail("config: UniformVelocityCommandWithDeadzone is implemented for velocity_deadzone == 0 only (rsl_env_cfg.py:98); a positive dead zone balances a per-process count of envs");
+  if (c.command_class == 1 && !(c.velocity_deadzone >= 0.f)) return fail("config: velocity_deadzone must be >= 0");
   P.cmd_class = c.command_class;
-  // commands.py:62-76 with no env ever inside the dead zone: randperm(n)[: n // 2] of ALL envs get xy = 0, i.e. each env with probability (n // 2) / n
-  P.dz_prob = (float)(n / 2) / (float)n;
+  P.deadzone = c.velocity_deadzone;
   P.flip_prob = c.ang_vel_flip_prob;
   P.init_h = c.init_root_height; P.push_enable = c.push_enable;
   P.key0 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
@@ -439,7 +437,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &S.hist, N * (size_t)h->P.H * H1V2_HIST_STRIDE);
   rc |= dalloc(h, &S.acc, (size_t)H1V2_LOG_DIM + 32);  // + cumulative histogram of Newton iterations per solve
   rc |= dalloc(h, &S.log, (size_t)H1V2_LOG_DIM);
-  rc |= dalloc(h, &S.counters, (size_t)2);
+  rc |= dalloc(h, &S.counters, (size_t)4);
   rc |= dalloc(h, &S.done, (size_t)1);
   rc |= dalloc(h, &h->own_ep_len, N);
   int* lut_d = nullptr;

@@ -68,7 +68,7 @@ struct KParams {
   float rel_standing, rel_heading, k_heading;
   int heading_cmd;
   int cmd_class;          // 1: UniformVelocityCommandWithDeadzone (T/utils/mdp/commands.py:19-96), dead zone 0
-  float dz_prob, flip_prob;
+  float deadzone, flip_prob;
   float max_command_step;
   // events
   float rp[6][2], rv[6][2], rjp[2], rjv[2], init_h;
@@ -97,7 +97,7 @@ struct KState {
   float* diag;     // [N][H1V2_DIAG_DIM] or NULL
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector
-  unsigned long long* counters;  // [0] global step counter, [1] history head
+  unsigned long long* counters;  // [0] global step counter, [1] history head, [2] dead-zone census being taken, [3] census of the last step
   unsigned* done;                // blocks of the current launch that have finished (the last one publishes the log, advances the counters)
 };
 #define H1V2_DIAG_DIM 168

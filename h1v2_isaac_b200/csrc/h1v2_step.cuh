@@ -127,8 +127,9 @@ __device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gi
 }
 
 // CommandTerm.compute(dt) of UniformVelocityCommand (V/velocity_env_cfg.py:90-104; T/utils/mdp/commands.py:47-59)
-__device__ __forceinline__ void update_command(const KParams& P, CmdState& c, const RootDerived& rd, int64_t gid,
-                                               unsigned long long step) {
+// Returns true when the env ends the step inside the command dead zone (class 1 only; counted for the next step's balancing).
+__device__ __forceinline__ bool update_command(const KParams& P, CmdState& c, const RootDerived& rd, int64_t gid,
+                                               unsigned long long step, unsigned dz_prev) {
   float ex = c.c[0] - rd.vb.x, ey = c.c[1] - rd.vb.y;
   c.m_xy += sqrtf(ex * ex + ey * ey) / P.max_command_step;
   c.m_yaw += fabsf(c.c[2] - rd.wb.z) / P.max_command_step;
@@ -140,16 +141,29 @@ __device__ __forceinline__ void update_command(const KParams& P, CmdState& c, co
   }
   if (P.cmd_class == 0) {
     if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
-  } else {
-    // UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96) with velocity_deadzone == 0: the
-    // override never zeroes standing envs; |cmd_xy| < 0 holds for no env, so the balancing branch zeroes the xy command of
-    // n // 2 envs drawn uniformly from ALL envs on every step (per env: probability (n // 2) / n, drawn independently here);
-    // then the yaw-rate command flips sign with probability physics_dt / max_episode_length_s.
-    float u[4];
-    rng4(P.key0, gid, step, STREAM_CMD, 4, u);
-    if (u[0] < P.dz_prob) c.c[0] = c.c[1] = 0.f;
-    if (u[1] < P.flip_prob) c.c[2] = -c.c[2];
+    return false;
   }
+  // UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96).  The override never zeroes standing
+  // envs.  Balancing (:62-83): the reference counts the envs whose |cmd_xy| is inside the dead zone and moves exactly
+  // |n // 2 - count| envs, picked by randperm, across it: active ones get cmd_xy = 0, dead-zone ones a fresh command
+  // (_resample: new command AND new time_left).  Here every env draws on its own with the probability that moves the same
+  // number in expectation, from the count published at the end of the PREVIOUS step (one launch per step: no grid-wide count
+  // inside it).  With velocity_deadzone == 0 (C12/rsl_env_cfg.py:98) no env is ever inside, the count is 0 and every env loses
+  // its xy command with probability (n // 2) / n on every step.  Then the yaw-rate command flips sign with probability
+  // physics_dt / max_episode_length_s (:85-96).
+  float u[4];
+  rng4(P.key0, gid, step, STREAM_CMD, 4, u);
+  const int target = P.n / 2, cur = (int)min(dz_prev, (unsigned)P.n);
+  // |cmd_xy| < dead zone, as one multiply + one fused multiply-add against the squared threshold: the oracle does the same, bit for bit
+  const float dz2 = __fmul_rn(P.deadzone, P.deadzone);
+  bool in_dz = __fmaf_rn(c.c[1], c.c[1], __fmul_rn(c.c[0], c.c[0])) < dz2;
+  if (cur < target) {
+    if (!in_dz && u[0] < __fdiv_rn((float)(target - cur), (float)(P.n - cur))) c.c[0] = c.c[1] = 0.f;
+  } else if (cur > target) {
+    if (in_dz && u[0] < __fdiv_rn((float)(cur - target), (float)cur)) resample_command(P, c, gid, step, 6);
+  }
+  if (u[1] < P.flip_prob) c.c[2] = -c.c[2];
+  return __fmaf_rn(c.c[1], c.c[1], __fmul_rn(c.c[0], c.c[0])) < dz2;
 }
 
 // ---- history rings of the warp's 16 envs: global -> shared memory, asynchronously ----
@@ -306,7 +320,11 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, uns
     S.acc[t] = 0.f;
   }
   if (t == 0) {
-    if (do_step) S.counters[0] += 1ull;
+    if (do_step) {
+      S.counters[0] += 1ull;
+      S.counters[3] = __ldcg(S.counters + 2);  // dead-zone census of this step, read by the next one
+      S.counters[2] = 0ull;
+    }
     S.counters[1] += 1ull;
     *S.done = 0u;
   }
@@ -661,7 +679,11 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   // ---- command manager, interval events, observation (on the post-reset state) ----
   RootDerived rd = root_derived(P, rq, rv, rw);
   if (DO_STEP) {
-    update_command(P, cmd, rd, gid, step);
+    const bool in_dz = update_command(P, cmd, rd, gid, step, (unsigned)S.counters[3]);
+    if (P.cmd_class == 1) {  // envs inside the dead zone at the end of this step, for the next step's balancing
+      const unsigned m = __ballot_sync(FULL_MASK, in_dz && valid && side == 0);
+      if ((tid & 31) == 0 && m) atomicAdd(S.counters + 2, (unsigned long long)__popc(m));
+    }
     if (P.push_enable) {  // push_by_setting_velocity (V/velocity_env_cfg.py:212-217)
       push_left -= P.step_dt;
       if (push_left < 1e-6f) {

@@ -317,8 +317,8 @@ def flatten_cfg(cfg) -> H1v2Config:
     if ctype == "UniformVelocityCommandWithDeadzone":  # T/utils/mdp/commands.py:19-96
         c.command_class = 1
         c.velocity_deadzone = float(_get(cmd, "velocity_deadzone", 0.1))
-        if c.velocity_deadzone != 0.0:  # a positive dead zone balances a per-process COUNT of envs inside it (commands.py:62-83)
-            raise NotImplementedError("commands.base_velocity.velocity_deadzone: only 0.0 (C12/rsl_env_cfg.py:98) is implemented in the fused kernel")
+        if c.velocity_deadzone < 0.0:
+            raise NotImplementedError("commands.base_velocity.velocity_deadzone must be >= 0")
         c.ang_vel_flip_prob = c.sim_dt / c.episode_length_s  # commands.py:37-38,86 (from the fp32 values the kernel holds)
     elif ctype == "UniformVelocityCommand":
         c.command_class = 0

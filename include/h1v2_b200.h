@@ -169,8 +169,10 @@ typedef struct H1v2Config {
   float contact_forces_threshold;      /* N; sum over the bodies of max(0, max_h |F| - threshold) */
   /* ---- command class (utils/mdp/commands.py:19-96) ---- */
   int32_t command_class;               /* 0 = UniformVelocityCommand; 1 = UniformVelocityCommandWithDeadzone */
-  float velocity_deadzone;             /* only 0.0 is implemented for class 1 (rsl_env_cfg.py:98): no env is ever "in the dead zone",
-                                          so every step n_envs/2 uniformly chosen envs get their xy command zeroed */
+  float velocity_deadzone;             /* class 1 keeps about half of the envs inside |cmd_xy| < dead zone: per step every env outside
+                                          (inside) moves across with the probability that balances the census of the previous step
+                                          (the reference moves an exact randperm-picked number, commands.py:62-83).  0 (rsl_env_cfg.py:98):
+                                          nobody is ever inside, every step n_envs/2 envs in expectation get their xy command zeroed */
   float ang_vel_flip_prob;             /* per-step probability of negating the yaw-rate command (commands.py:85-96): physics_dt / episode_length_s */
   /* ---- velocity reference points of the managers (isaaclab 2.1.0 ArticulationData: poses are of the link frame, velocities of the
    *      link's centre of mass; SURVEY App. A "State conventions").  The physics state stays MuJoCo's (pelvis ORIGIN velocity). ---- */

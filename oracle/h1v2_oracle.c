@@ -124,6 +124,7 @@ struct H1v2Oracle {
   double soft_lo[NJ], soft_hi[NJ];
   int max_newton_iters;
   int nthreads;
+  int dz_prev; /* envs inside the command dead zone at the end of the previous step (UniformVelocityCommandWithDeadzone balancing) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -768,6 +769,9 @@ static void root_derived(const H1v2Config* c, const OEnv* e, double R[9], double
   *heading = atan2(R[3], R[0]);
 }
 
+/* norm(cmd_xy) < dead zone (commands.py:62), compared on the squares with one multiply and one fused multiply-add like the kernel */
+static int cmd_in_deadzone(const float* cmd, float deadzone) { return fmaf(cmd[1], cmd[1], cmd[0] * cmd[0]) < deadzone * deadzone; }
+
 static void update_command(H1v2Oracle* o, int ei) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
@@ -792,15 +796,23 @@ static void update_command(H1v2Oracle* o, int ei) {
   if (c->command_class == 0) {
     if (e->is_standing) e->cmd[0] = e->cmd[1] = e->cmd[2] = 0;
   } else {
-    /* UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96), velocity_deadzone == 0
-     * (C12/rsl_env_cfg.py:98): standing envs are not zeroed by the override; `norm(cmd_xy) < 0` is false for every env, so
-     * current_deadzone_count == 0 < n // 2 and randperm(n)[: n // 2] of all envs get cmd_xy = 0 on EVERY step (:62-70);
-     * restated per env as an independent draw with the same marginal probability (n // 2) / n.  Then the yaw-rate command
+    /* UniformVelocityCommandWithDeadzone._update_command (T/utils/mdp/commands.py:41-96): standing envs are not zeroed by the
+     * override.  Balancing (:62-83): the reference counts the envs whose norm(cmd_xy) is below the dead zone and moves exactly
+     * |n // 2 - count| envs across it, picked by torch.randperm: active ones get cmd_xy = 0, dead-zone ones a fresh command through
+     * _resample (new command and new time_left).  Restated per env: an independent draw with the probability that moves the same
+     * number in expectation, computed from the count at the end of the PREVIOUS step (the product runs one launch per step and
+     * has no process-wide count inside it).  With velocity_deadzone == 0 (C12/rsl_env_cfg.py:98) `norm < 0` never holds, the
+     * count stays 0 and every env loses its xy command with probability (n // 2) / n on EVERY step.  Then the yaw-rate command
      * changes sign with probability physics_dt / max_episode_length_s (:85-96). */
     float u[4];
     rng4(o->seed, c->env_id_offset + ei, o->step_counter, STREAM_CMD, 4, u);
-    const float dz_prob = (float)(o->n / 2) / (float)o->n;
-    if (u[0] < dz_prob) e->cmd[0] = e->cmd[1] = 0;
+    const int target = o->n / 2, cur = o->dz_prev < o->n ? o->dz_prev : o->n;
+    int in_dz = cmd_in_deadzone(e->cmd, c->velocity_deadzone);
+    if (cur < target) {
+      if (!in_dz && u[0] < (float)(target - cur) / (float)(o->n - cur)) e->cmd[0] = e->cmd[1] = 0;
+    } else if (cur > target) {
+      if (in_dz && u[0] < (float)(cur - target) / (float)cur) resample_command(o, ei, 6);
+    }
     if (u[1] < c->ang_vel_flip_prob) e->cmd[2] = -e->cmd[2];
   }
 }
@@ -1189,6 +1201,11 @@ static int step_impl(H1v2Oracle* o, const float* actions, float* obs, float* rew
   o->log[H1V2_LOG_NAN_RESETS] += (float)nbad;
   o->log[H1V2_LOG_MAX_ITERS] = (float)max_it;
   run_phase(proto, 1);
+  if (o->cfg.command_class == 1) { /* census for the next step's balancing */
+    int cnt = 0;
+    for (int i = 0; i < n; i++) cnt += cmd_in_deadzone(o->env[i].cmd, o->cfg.velocity_deadzone);
+    o->dz_prev = cnt;
+  }
   free(reset);
   free(bad);
   return 0;

@@ -141,7 +141,23 @@ for _ in range(2000):
     before = term.vel_command_b[:, 2].clone()
     term._update_command()
     flips += int((term.vel_command_b[:, 2] == -before).sum())
+# positive dead zone (the class default 0.1, the CaT cfg's 0.2): the balancing branch keeps exactly n // 2 envs inside.  _resample
+# belongs to the upstream base class (absent here); the stand-in redraws the command uniformly over the cfg ranges as upstream does.
+def _balanced_counts(deadzone, calls=30):
+    t = object.__new__(ref_commands.UniformVelocityCommandWithDeadzone)
+    t.cfg = term.cfg; t.velocity_deadzone = deadzone; t.dt, t.max_episode_length_s = PHYS_DT, EP_S
+    t.vel_command_b = torch.from_numpy(rng.uniform(-1, 1, (ND, 3)).astype(np.float32))
+    t._resample = lambda ids: t.vel_command_b.__setitem__(ids, torch.from_numpy(rng.uniform(-1, 1, (len(ids), 3)).astype(np.float32)))
+    counts = [int((torch.norm(t.vel_command_b[:, :2], dim=1) < deadzone).sum())]
+    for _ in range(calls):
+        t._update_command()
+        counts.append(int((torch.norm(t.vel_command_b[:, :2], dim=1) < deadzone).sum()))
+    return counts
+
+
+balanced = {str(dz): _balanced_counts(dz) for dz in (0.1, 0.2)}
 json.dump({"n_envs": ND, "calls": CALLS, "zero_xy_after_call": zero_xy, "yaw_flips": flips, "flip_trials": ND * (CALLS + 2000),
+           "in_deadzone_count_before_and_after_each_call": balanced,
            "standing_envs_yaw_untouched_by_zeroing": bool(torch.equal(term.vel_command_b[:64, 2].abs(), first[:64, 2].abs())),
            "physics_dt": PHYS_DT, "max_episode_length_s": EP_S},
           open(os.path.join(OUT, "deadzone_command.json"), "w"), indent=1)

@@ -115,7 +115,9 @@ def test_unsupported_cfg_is_rejected_loudly():
     with pytest.raises(NotImplementedError, match="history_step"):
         flatten_cfg(tree)
     tree = tasks.rsl_env_cfg(8)
-    tree.commands.base_velocity.velocity_deadzone = 0.1  # a positive dead zone balances a per-process count of envs: not in the kernel
+    tree.commands.base_velocity.velocity_deadzone = 0.1  # the class default (commands.py:104): supported, balanced per step
+    assert abs(flatten_cfg(tree).velocity_deadzone - 0.1) < 1e-7
+    tree.commands.base_velocity.velocity_deadzone = -0.1
     with pytest.raises(NotImplementedError, match="velocity_deadzone"):
         flatten_cfg(tree)
     tree = tasks.rsl_env_cfg(8)

@@ -214,6 +214,56 @@ def _deadzone_case(backend_cls, steps):
     return flips, trials
 
 
+def _balanced_case(backend_cls, deadzone):
+    """Positive dead zone: the reference's balancing keeps exactly n // 2 envs inside (golden: 2048 of 4096 after every call, from 30 / 126
+    before the first); the per-env restatement with the census of the previous step must settle at the same half, within the binomial
+    spread, from the first step on, and keep the envs it does not move untouched."""
+    import json
+    from h1v2_isaac_b200._capi import rsl_config
+    g = json.load(open(os.path.join(GOLD, "deadzone_command.json")))
+    ref = g["in_deadzone_count_before_and_after_each_call"][str(deadzone)]
+    n = g["n_envs"]
+    assert all(c == n // 2 for c in ref[1:]) and ref[0] < 0.05 * n
+    c = rsl_config(); c.velocity_deadzone = deadzone
+    b = backend_cls(c, n, seed=6)
+    b.observe()
+    rng = np.random.default_rng(7)
+    cmd = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    b.set_state({"command": cmd, "time_left": np.full((n, 1), 100.0, np.float32)})
+    a = np.zeros((n, 12), np.float32)
+    fracs, prev = [], cmd
+    for k in range(12):
+        done = b.step(a)
+        st = b.get_state(["command", "time_left"])
+        cur = st["command"]
+        inside = np.hypot(cur[:, 0], cur[:, 1]) < deadzone
+        fracs.append(float(inside[~done].mean()))
+        # an env is either untouched, zeroed (was outside), or redrawn with a fresh time_left (was inside)
+        was_inside = np.hypot(prev[:, 0], prev[:, 1]) < deadzone
+        same = (cur[:, :2] == prev[:, :2]).all(axis=1)
+        zeroed = ~same & (cur[:, 0] == 0) & (cur[:, 1] == 0)
+        redrawn = ~same & ~zeroed
+        ok = ~done
+        assert not (zeroed & was_inside & ok).any() or deadzone == 0
+        assert (was_inside | ~redrawn | ~ok).all() and (st["time_left"][redrawn & ok, 0] <= 8.0).all()
+        prev = cur
+    b.close()
+    sigma = 0.5 / np.sqrt(n)
+    assert abs(fracs[0] - (ref[0] / n + 0.5 * (1 - ref[0] / n))) < 5 * sigma, fracs  # half of the envs outside go in at once
+    assert all(abs(f - 0.5) < 6 * sigma for f in fracs[1:]), fracs
+
+
+@pytest.mark.parametrize("deadzone", [0.1, 0.2])
+def test_oracle_deadzone_balancing_against_reference_counts(deadzone):
+    _balanced_case(_OracleBackend, deadzone)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deadzone", [0.1, 0.2])
+def test_cuda_deadzone_balancing_against_reference_counts(deadzone):
+    _balanced_case(_GpuBackend, deadzone)
+
+
 def test_oracle_deadzone_command_against_reference_statistics():
     _deadzone_case(_OracleBackend, 14)
 

@@ -224,7 +224,7 @@ def test_c_abi_edge_cases(cfg):
                               ("command_class", 2, b"command_class")):
         c = cfg.copy(); setattr(c, field, value)
         assert lib.h1v2_create(C.byref(c), 8, 0, 1, C.byref(h)) != 0 and msg in lib.h1v2_last_error(), field
-    c = _capi.rsl_config(); c.velocity_deadzone = 0.1
+    c = _capi.rsl_config(); c.velocity_deadzone = -0.1
     assert lib.h1v2_create(C.byref(c), 8, 0, 1, C.byref(h)) != 0 and b"velocity_deadzone" in lib.h1v2_last_error()
     assert lib.h1v2_create(C.byref(cfg), 0, 0, 1, C.byref(h)) != 0
     assert lib.h1v2_create(C.byref(cfg), 8, 99, 1, C.byref(h)) != 0  # no such device

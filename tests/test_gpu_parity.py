@@ -195,7 +195,8 @@ def test_natural_command_resample_parity(cfg, task):
     sim.close()
 
 
-def test_tail_parity_rsl_task():
+@pytest.mark.parametrize("deadzone", [0.0, 0.2])
+def test_tail_parity_rsl_task(deadzone):
     """the resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (C12/rsl_env_cfg.py:44-540; tests/golden/
     rsl_cfg_resolved.json pins it to the reference's own cfg classes): IdealPD, action scale 0.25, history 6, scaled gyro / joint
     velocity, 16 reward terms incl. the second joint-set instances and contact_forces at 800 N, per-env friction 0.1..1.25, and
@@ -204,11 +205,15 @@ def test_tail_parity_rsl_task():
     from h1v2_isaac_b200._capi import rsl_config
     c = rsl_config()
     assert c.command_class == 1 and c.history_length == 6
+    c.velocity_deadzone = deadzone  # 0.2 = the CaT cfg's value: both balancing branches (zeroing and re-drawing) run
     w2 = [w * (1.5 if i % 2 else 0.5) for i, w in enumerate(c.rew_weight)]
     stats = _tail_parity(c, 2048, 40, 20, min_term=0, reweight=(20, w2))
-    # C12/rsl_env_cfg.py:98 velocity_deadzone = 0.0: every step half of ALL envs lose their xy command, so a command survives
-    # k steps with probability 2^-k -- the task as configured is in-place stepping and turning
-    assert stats["xy_zero_frac"][0] > 0.4 and stats["xy_zero_frac"][5] > 0.95 and stats["xy_zero_frac"][-1] > 0.99
+    if deadzone == 0.0:
+        # C12/rsl_env_cfg.py:98 velocity_deadzone = 0.0: every step half of ALL envs lose their xy command, so a command survives
+        # k steps with probability 2^-k -- the task as configured is in-place stepping and turning
+        assert stats["xy_zero_frac"][0] > 0.4 and stats["xy_zero_frac"][5] > 0.95 and stats["xy_zero_frac"][-1] > 0.99
+    else:  # balanced: about half of the envs keep a live xy command
+        assert all(0.4 < f < 0.6 for f in stats["xy_zero_frac"][1:])
     assert stats["yaw_flips"] > 0
 
 
@@ -252,7 +257,8 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
         if cfg.command_class == 1:  # dead-zone class: the zeroing and sign-flip draws are masks, compare them exactly
             assert np.array_equal(g["command"], o["command"]), f"dead-zone command, step {step}"
             stats["xy_zero_frac"].append(float(((g["command"][:, 0] == 0) & (g["command"][:, 1] == 0)).mean()))
-            same = ~(to | uo | resampled) & (prev["command"][:, 2] != 0)
+            redrawn = (g["command"][:, :2] != prev["command"][:, :2]).any(axis=1) & ~(g["command"][:, :2] == 0).all(axis=1)  # dead-zone re-activation
+            same = ~(to | uo | resampled | redrawn) & (prev["command"][:, 2] != 0)
             stats["yaw_flips"] += int((g["command"][same, 2] == -prev["command"][same, 2]).sum())
             assert np.all(np.abs(g["command"][same, 2]) == np.abs(prev["command"][same, 2]))
         lg, lo = sim.log_host(), orc.log()
