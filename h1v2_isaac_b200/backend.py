@@ -53,6 +53,10 @@ class H1v2Sim:
             p = C.c_void_p()
             self._check(self._lib.h1v2_get_log(self._h, C.byref(p)))
             self.log_buf = torch.as_tensor(_DevPtr(p.value, LOG_DIM), device=self.device)
+            self.cat_acc_buf = None
+            if self.cfg.cat_enable:  # sums behind Episode_Constraint_* (violation x100 [10], probability [10], count), device view
+                self._check(self._lib.h1v2_get_cat_log(self._h, C.byref(p)))
+                self.cat_acc_buf = torch.as_tensor(_DevPtr(p.value, 21), device=self.device)
 
     # ------------------------------------------------------------------
     def _check(self, rc: int):

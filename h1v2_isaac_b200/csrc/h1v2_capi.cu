@@ -333,6 +333,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   if (c.max_delay > 2 * c.decimation) return fail("config: max_delay exceeds two control steps");
   P.min_delay = c.min_delay; P.max_delay = c.max_delay;
   P.gravity = c.gravity;
+  P.mass_scales_inertia = c.mass_recompute_inertia;
   P.vel_limit = c.joint_vel_limit; P.runaway_vel = c.runaway_vel > 0.f ? c.runaway_vel : 3.0e38f;
   float Kf, Bf;
   kb_h(c.floss_solref, c.floss_solimp, c.sim_dt, &Kf, &Bf);
@@ -632,6 +633,11 @@ int h1v2_cat_debug(H1v2Handle* h, float* raw, float* probs, float* running_max) 
   if (raw) CK(cudaMemcpy(raw, h->cat.raw, cols, cudaMemcpyDeviceToHost));
   if (probs) CK(cudaMemcpy(probs, h->cat.probs, cols, cudaMemcpyDeviceToHost));
   if (running_max) CK(cudaMemcpy(running_max, h->cat.rmax + h->cat_parity * H1V2_CSTR_COLS, sizeof(float) * H1V2_CSTR_COLS, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev) {
+  if (!h || !acc_dev || !h->cfg.cat_enable) return fail("h1v2_get_cat_log: bad arguments");
+  *acc_dev = h->cat.logacc;
   return 0;
 }
 int h1v2_get_cat_log_host(H1v2Handle* h, float* out) {

@@ -127,6 +127,7 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   c->root_link_com[0] = -0.0004f; c->root_link_com[1] = 3.7e-05f; c->root_link_com[2] = -0.046864f;
   c->body_vel_at_com = 1;
   // Constraints-as-Terminations tail: off; parameters of config/h12_12dof/cat_env_cfg.py:336-431, ConstraintManager defaults
+  c->mass_recompute_inertia = 1;
   c->cat_enable = 0;
   c->cat_tau = 0.95f; c->cat_min_p = 0.0f;
   for (int t = 0; t < H1V2_NUM_CSTR; t++) c->cat_max_p[t] = 0.25f;

@@ -39,6 +39,7 @@ struct KParams {
   int min_delay, max_delay;
   // physics
   float gravity;
+  int mass_scales_inertia;       // added base mass rescales the base inertia (randomize_rigid_body_mass recompute_inertia)
   float vel_limit, runaway_vel;  // joint velocity clamp (<= 0: off); runaway-state guard
   float damping[18], armature[18];
   float floss[18], floss_D[18], floss_lim[18], floss_B;  // lim = R*frictionloss

@@ -195,6 +195,8 @@ typedef struct H1v2Config {
   float root_link_com[3];              /* COM of the root LINK (pelvis alone, h12_12dof.urdf:16 == h12_12dof.xml:67) in the pelvis frame:
                                           root_lin_vel_w/_b used by rewards and command metrics = v_origin + w x (R r) */
   int32_t body_vel_at_com;             /* 1: feet_slide reads the ankle_roll_link COM velocity (body_lin_vel_w), 0: link origin */
+  int32_t mass_recompute_inertia;      /* randomize_rigid_body_mass(recompute_inertia=...): 1 (isaaclab default) rescales the base inertia
+                                          with the mass, 0 (cat_env_cfg.py add_base_mass) adds the mass only */
   /* ---- Constraints-as-Terminations tail (utils/cat/constraint_manager.py, cat_env.py:147-153; cat_env_cfg.py:336-431) ---- */
   int32_t cat_enable;                  /* 1: h1v2_cat_step is available (keeps the per-env diagnostics buffer) */
   float cat_tau, cat_min_p;            /* ConstraintManager(tau=0.95, min_p=0.0) */
@@ -294,6 +296,9 @@ int h1v2_cat_debug(H1v2Handle* h, float* raw, float* probs, float* running_max);
 /* Episode_Constraint_violation/<term> (percent) and Episode_Constraint_probability/<term> of the envs reset in the last cat step that
  * reset any (constraint_manager.py:185-203): out[0..9] violation, out[10..19] probability, out[20] number of such envs.  Synchronises. */
 int h1v2_get_cat_log_host(H1v2Handle* h, float* out /*[2 * H1V2_NUM_CSTR + 1]*/);
+/* device pointer to the SUMS behind that log (float[2 * H1V2_NUM_CSTR + 1]: violation sums x100, probability sums, count of the
+ * envs reset in the last cat step), for callers that must not synchronise */
+int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev);
 
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);
