@@ -14,6 +14,10 @@ NUM_SLOT = 6
 OBS_TERM_DIM = 45
 MAX_HISTORY = 10
 LOG_DIM = 32
+NUM_CSTR, CSTR_COLS = 10, 56
+CSTR_NAMES = ["contact", "joint_position_limits", "joint_velocity_limits", "joint_torque_limits", "foot_contact_force", "no_move",
+              "base_orientation", "base_height", "foot_contact", "foot_clearance"]
+CSTR_COL0 = [0, 1, 13, 25, 37, 39, 51, 52, 53, 54, 56]  # first column of every term (and the end)
 
 REW_NAMES = [
     "termination_penalty", "track_lin_vel_xy_exp", "track_ang_vel_z_exp", "feet_air_time", "feet_slide",
@@ -59,6 +63,9 @@ class H1v2Config(C.Structure):
         ("mask_pos_limits_b", u32), ("mask_joint_dev_b", u32), ("mask_contact_forces_slots", u32), ("contact_forces_threshold", f32),
         ("command_class", i32), ("velocity_deadzone", f32), ("ang_vel_flip_prob", f32),
         ("root_link_com", f32 * 3), ("body_vel_at_com", i32),
+        ("mass_recompute_inertia", i32), ("cat_enable", i32), ("cat_tau", f32), ("cat_min_p", f32), ("cat_max_p", f32 * 10), ("cat_contact_slots", u32),
+        ("cat_foot_force_limit", f32), ("cat_no_move_deadzone", f32), ("cat_no_move_vel_limit", f32), ("cat_orientation_limit", f32),
+        ("cat_height", f32), ("cat_height_std", f32), ("cat_clearance_min_height", f32), ("cat_clearance_deadzone", f32),
         ("runaway_vel", f32), ("reserved", i32 * 8),
     ]
 
@@ -111,6 +118,11 @@ _SYMBOLS = {
     "h1v2_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_set_reward_weights": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_cat_step": (C.c_int, [C.c_void_p] * 7),
+    "h1v2_set_constraint_max_p": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_cat_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_get_cat_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_get_cat_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "h1v2_get_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_set_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

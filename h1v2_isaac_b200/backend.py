@@ -53,6 +53,10 @@ class H1v2Sim:
             p = C.c_void_p()
             self._check(self._lib.h1v2_get_log(self._h, C.byref(p)))
             self.log_buf = torch.as_tensor(_DevPtr(p.value, LOG_DIM), device=self.device)
+            self.cat_acc_buf = None
+            if self.cfg.cat_enable:  # sums behind Episode_Constraint_* (violation x100 [10], probability [10], count), device view
+                self._check(self._lib.h1v2_get_cat_log(self._h, C.byref(p)))
+                self.cat_acc_buf = torch.as_tensor(_DevPtr(p.value, 21), device=self.device)
 
     # ------------------------------------------------------------------
     def _check(self, rc: int):
@@ -88,6 +92,42 @@ class H1v2Sim:
         self._check(self._lib.h1v2_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(),
                                         trunc.data_ptr(), self._stream()))
         return obs, rew, term.view(torch.bool), trunc.view(torch.bool)
+
+    def cat_step(self, actions: torch.Tensor):
+        """Constraints-as-Terminations step (CaTEnv.step): -> obs, rew * (1 - p), dones (float: p, 1 on reset), truncated."""
+        a = actions
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
+            a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.shape != (self.num_envs, NJ):
+            raise ValueError(f"actions must be [{self.num_envs},{NJ}], got {tuple(a.shape)}")
+        obs = torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        rew = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        dones = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        trunc = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._check(self._lib.h1v2_cat_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dones.data_ptr(), trunc.data_ptr(), self._stream()))
+        return obs, rew, dones, trunc.view(torch.bool)
+
+    def set_constraint_max_p(self, max_p) -> None:
+        import numpy as np
+        p = np.ascontiguousarray(max_p, dtype=np.float32)
+        self._check(self._lib.h1v2_set_constraint_max_p(self._h, p.ctypes.data_as(C.POINTER(C.c_float))))
+        for i in range(p.size):
+            self.cfg.cat_max_p[i] = float(p[i])
+
+    def cat_debug(self):
+        """(raw [56,N], probs [56,N], running_max [56]) of the last cat step, host copies."""
+        import numpy as np
+        from ._capi import CSTR_COLS
+        raw = np.zeros((CSTR_COLS, self.num_envs), np.float32); probs = np.zeros_like(raw); rm = np.zeros(CSTR_COLS, np.float32)
+        self._check(self._lib.h1v2_cat_debug(self._h, raw.ctypes.data, probs.ctypes.data, rm.ctypes.data))
+        return raw, probs, rm
+
+    def cat_log_host(self):
+        import numpy as np
+        from ._capi import NUM_CSTR
+        out = np.zeros(2 * NUM_CSTR + 1, np.float32)
+        self._check(self._lib.h1v2_get_cat_log_host(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     def step_into(self, actions, obs, rew, term, trunc):
         """Same as step() with caller-provided output tensors (no allocation; used by bench.py and CUDA graphs)."""

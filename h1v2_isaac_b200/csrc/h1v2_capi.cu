@@ -12,6 +12,7 @@
 
 #include "../../include/h1v2_model_h12.h"
 #include "h1v2_step.cuh"
+#include "h1v2_cat.cuh"
 
 using namespace h1v2;
 
@@ -61,6 +62,12 @@ struct H1v2Handle {
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   cudaStream_t host_stream = nullptr;
+  // Constraints-as-Terminations tail (cfg.cat_enable)
+  CatState cat = {};
+  bool cat_first = true;
+  int cat_parity = 0;
+  uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
+  float cat_log[2 * H1V2_NUM_CSTR + 1] = {};
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -326,6 +333,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   if (c.max_delay > 2 * c.decimation) return fail("config: max_delay exceeds two control steps");
   P.min_delay = c.min_delay; P.max_delay = c.max_delay;
   P.gravity = c.gravity;
+  P.mass_scales_inertia = c.mass_recompute_inertia;
   P.vel_limit = c.joint_vel_limit; P.runaway_vel = c.runaway_vel > 0.f ? c.runaway_vel : 3.0e38f;
   float Kf, Bf;
   kb_h(c.floss_solref, c.floss_solimp, c.sim_dt, &Kf, &Bf);
@@ -442,7 +450,20 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &h->own_ep_len, N);
   int* lut_d = nullptr;
   rc |= dalloc(h, &lut_d, (size_t)h->P.obs_dim);
-  if (cfg->reserved[0]) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);
+  if (cfg->reserved[0] || cfg->cat_enable) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);  // the CaT tail reads the pre-reset values from it
+  if (cfg->cat_enable) {
+    CatState& T = h->cat;
+    rc |= dalloc(h, &T.raw, (size_t)H1V2_CSTR_COLS * N);
+    rc |= dalloc(h, &T.probs, (size_t)H1V2_CSTR_COLS * N);
+    rc |= dalloc(h, &T.rmax, (size_t)2 * H1V2_CSTR_COLS);
+    rc |= dalloc(h, &T.cmax, (size_t)H1V2_CSTR_COLS);
+    rc |= dalloc(h, &T.list, N);
+    rc |= dalloc(h, &T.count, (size_t)1);
+    rc |= dalloc(h, &T.swing, 2 * N);
+    rc |= dalloc(h, &T.sums, (size_t)2 * H1V2_NUM_CSTR * N);
+    rc |= dalloc(h, &T.logacc, (size_t)2 * H1V2_NUM_CSTR + 1);
+    rc |= dalloc(h, &h->cat_term, N);
+  }
   if (rc != 0) { h1v2_destroy(h); return -1; }
   S.ep_len = h->own_ep_len;
   {
@@ -562,6 +583,75 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
   if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
   if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static CatParams cat_params(const H1v2Handle* h) {
+  const H1v2Config& c = h->cfg;
+  CatParams C;
+  C.n = h->n; C.first = h->cat_first ? 1 : 0;
+  C.tau = c.cat_tau; C.min_p = c.cat_min_p;
+  for (int t = 0; t < H1V2_NUM_CSTR; t++) C.max_p[t] = c.cat_max_p[t];
+  C.contact_slots = c.cat_contact_slots;
+  C.foot_force_limit = c.cat_foot_force_limit; C.no_move_deadzone = c.cat_no_move_deadzone; C.no_move_vel_limit = c.cat_no_move_vel_limit;
+  C.orientation_limit = c.cat_orientation_limit; C.height = c.cat_height; C.height_std = c.cat_height_std;
+  C.clearance_min_height = c.cat_clearance_min_height; C.clearance_deadzone = c.cat_clearance_deadzone;
+  C.step_dt = h->P.step_dt; C.vel_limit = c.joint_vel_limit;
+  return C;
+}
+
+int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream) {
+  if (!h || !actions || !obs || !rew || !dones || !truncated) return fail("h1v2_cat_step: bad arguments");
+  if (!h->cfg.cat_enable) return fail("h1v2_cat_step: the handle was created without cfg.cat_enable");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (launch_step(h, true, actions, obs, rew, h->cat_term, truncated, st) != 0) return -1;
+  DeviceGuard guard(h->device);
+  const CatParams C = cat_params(h);
+  const int blocks = (h->n + 127) / 128;
+  cat_scan_kernel<<<1, 1024, 0, st>>>(h->S.diag, C, h->cat);
+  cat_raw_kernel<<<blocks, 128, 0, st>>>(h->P, h->S.diag, C, h->cat);
+  cat_apply_kernel<<<blocks, 128, 0, st>>>(h->S.diag, C, h->cat, h->cat_parity, rew, dones);
+  h->launches += 3;
+  h->cat_first = false;
+  h->cat_parity ^= 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+int h1v2_set_constraint_max_p(H1v2Handle* h, const float* max_p) {
+  if (!h || !max_p) return fail("h1v2_set_constraint_max_p: bad arguments");
+  for (int t = 0; t < H1V2_NUM_CSTR; t++) {
+    if (!(max_p[t] >= 0.f && max_p[t] <= 1.f)) return fail("h1v2_set_constraint_max_p: probabilities must be in [0, 1]");
+    h->cfg.cat_max_p[t] = max_p[t];
+  }
+  return 0;
+}
+int h1v2_cat_debug(H1v2Handle* h, float* raw, float* probs, float* running_max) {
+  if (!h || !h->cfg.cat_enable) return fail("h1v2_cat_debug: bad arguments");
+  DeviceGuard guard(h->device);
+  CK(cudaDeviceSynchronize());
+  const size_t cols = (size_t)H1V2_CSTR_COLS * h->n * sizeof(float);
+  if (raw) CK(cudaMemcpy(raw, h->cat.raw, cols, cudaMemcpyDeviceToHost));
+  if (probs) CK(cudaMemcpy(probs, h->cat.probs, cols, cudaMemcpyDeviceToHost));
+  if (running_max) CK(cudaMemcpy(running_max, h->cat.rmax + h->cat_parity * H1V2_CSTR_COLS, sizeof(float) * H1V2_CSTR_COLS, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev) {
+  if (!h || !acc_dev || !h->cfg.cat_enable) return fail("h1v2_get_cat_log: bad arguments");
+  *acc_dev = h->cat.logacc;
+  return 0;
+}
+int h1v2_get_cat_log_host(H1v2Handle* h, float* out) {
+  if (!h || !out || !h->cfg.cat_enable) return fail("h1v2_get_cat_log_host: bad arguments");
+  DeviceGuard guard(h->device);
+  CK(cudaDeviceSynchronize());
+  float acc[2 * H1V2_NUM_CSTR + 1];
+  CK(cudaMemcpy(acc, h->cat.logacc, sizeof(acc), cudaMemcpyDeviceToHost));
+  const float cnt = acc[2 * H1V2_NUM_CSTR];
+  if (cnt > 0.f) {  // upstream writes the keys only in steps with a reset; keep the last such values otherwise
+    for (int t = 0; t < 2 * H1V2_NUM_CSTR; t++) h->cat_log[t] = acc[t] / cnt;
+    h->cat_log[2 * H1V2_NUM_CSTR] = cnt;
+  }
+  for (int t = 0; t < 2 * H1V2_NUM_CSTR + 1; t++) out[t] = h->cat_log[t];
   return 0;
 }
 

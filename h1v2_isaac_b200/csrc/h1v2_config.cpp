@@ -126,6 +126,18 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
   // isaaclab 2.1.0 reports link velocities at the link's COM: pelvis link inertial origin, A/models/h12/h12_12dof.urdf:16 (== h12_12dof.xml:67)
   c->root_link_com[0] = -0.0004f; c->root_link_com[1] = 3.7e-05f; c->root_link_com[2] = -0.046864f;
   c->body_vel_at_com = 1;
+  // Constraints-as-Terminations tail: off; parameters of config/h12_12dof/cat_env_cfg.py:336-431, ConstraintManager defaults
+  c->mass_recompute_inertia = 1;
+  c->cat_enable = 0;
+  c->cat_tau = 0.95f; c->cat_min_p = 0.0f;
+  for (int t = 0; t < H1V2_NUM_CSTR; t++) c->cat_max_p[t] = 0.25f;
+  c->cat_max_p[H1V2_CSTR_CONTACT] = 1.0f;
+  c->cat_contact_slots = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 5);
+  c->cat_foot_force_limit = 750.0f;
+  c->cat_no_move_deadzone = 0.2f; c->cat_no_move_vel_limit = 6.0f;
+  c->cat_orientation_limit = 0.1f;
+  c->cat_height = 1.0f; c->cat_height_std = 0.05f;
+  c->cat_clearance_min_height = 0.1f; c->cat_clearance_deadzone = 0.2f;
   c->runaway_vel = 1000.0f;     // A/robots/h12.py:27-28 max_linear_velocity / max_angular_velocity
   return 0;
 }

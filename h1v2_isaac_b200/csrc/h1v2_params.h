@@ -39,6 +39,7 @@ struct KParams {
   int min_delay, max_delay;
   // physics
   float gravity;
+  int mass_scales_inertia;       // added base mass rescales the base inertia (randomize_rigid_body_mass recompute_inertia)
   float vel_limit, runaway_vel;  // joint velocity clamp (<= 0: off); runaway-state guard
   float damping[18], armature[18];
   float floss[18], floss_D[18], floss_lim[18], floss_B;  // lim = R*frictionloss
@@ -103,7 +104,8 @@ struct KState {
 #define H1V2_DIAG_DIM 168
 #define H1V2_DIAG_REW0 144
 // diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | (free 60..79)
-//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140 | reward_terms 144..165
+//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140
+//              | command before this step's update 141..143 | reward_terms 144..165 | episode length (pre-reset) 166 | reset flag 167
 #define FLAG_DELAY_FRESH 1
 #define FLAG_HIST_FRESH 2
 #define FLAG_LAG_SHIFT 2

@@ -350,7 +350,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   const V3 om0 = mulv(R0, mk3(rw[0], rw[1], rw[2]));
   const V3 acc0 = mk3(0.f, 0.f, P.gravity) + cross(v0, om0);  // root cacc: -gravity + free-joint cdof_dot * qvel
   const float m0 = P.root_mass + mass_add;
-  const RI I0 = body_inertia(R0, mulv(R0, ld3(P.root_ipos)), m0, P.root_inertia, m0 / P.root_mass);
+  const RI I0 = body_inertia(R0, mulv(R0, ld3(P.root_ipos)), m0, P.root_inertia, P.mass_scales_inertia ? m0 / P.root_mass : 1.f);
   float fs_root[6];  // first the bias force of the root link about O_r, then the smooth force of the root dofs
   {
     V3 an, al, vn, vl;

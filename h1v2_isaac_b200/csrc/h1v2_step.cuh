@@ -631,6 +631,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
         for (int t = 0; t < H1V2_NUM_REW; t++) dg[H1V2_DIAG_REW0 + t] = r[t];
         dg[86] = (float)max_it; dg[87] = (float)ncap; dg[88] = (float)sum_it;
+        // for the Constraints-as-Terminations tail: the command the mdp terms of this step read (before its update), the episode length
+        dg[141] = cmd.c[0]; dg[142] = cmd.c[1]; dg[143] = cmd.c[2];
+        dg[166] = (float)ep_len; dg[167] = reset ? 1.f : 0.f;
       }
     }
     // solver statistics

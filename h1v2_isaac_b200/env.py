@@ -17,7 +17,7 @@ import math
 import re
 from typing import Any
 
-from ._capi import H1v2Config, LOG_COUNT, LOG_ERR_XY, LOG_ERR_YAW, LOG_REW0, LOG_TERM_CONTACT, LOG_TERM_TIMEOUT, NJ, REW_NAMES, default_config
+from ._capi import CSTR_NAMES, H1v2Config, LOG_COUNT, LOG_ERR_XY, LOG_ERR_YAW, LOG_REW0, LOG_TERM_CONTACT, LOG_TERM_TIMEOUT, NJ, REW_NAMES, default_config
 
 # MJCF (leg-major) joint order of h12_12dof.xml:71-132 == A/robots/h12.py:40-53
 JOINT_NAMES = [f"{s}_{j}_joint" for s in ("left", "right") for j in ("hip_yaw", "hip_pitch", "hip_roll", "knee", "ankle_pitch", "ankle_roll")]
@@ -118,14 +118,51 @@ def reward_slots(cfg) -> dict[str, int]:
     return out
 
 
+def constraint_terms(cfg) -> dict[str, int]:
+    """cfg constraint term name -> kernel constraint index (utils/cat/constraints.py function name -> _capi.CSTR_NAMES)."""
+    out = {}
+    for n, t in _terms(_get(cfg, "constraints")):
+        f = _fname(t.func)
+        if f not in CSTR_NAMES:
+            raise NotImplementedError(f"constraints.{n}: constraints.{f} is not implemented in the CaT tail")
+        if CSTR_NAMES.index(f) in out.values():
+            raise NotImplementedError(f"constraints.{n}: constraints.{f} appears twice")
+        out[n] = CSTR_NAMES.index(f)
+    return out
+
+
+def constraint_curriculum(cfg) -> list[tuple[int, int, float]]:
+    """curriculums.modify_constraint_p terms (utils/cat/curriculums.py:20-42) -> [(constraint index, num_steps, init_max_p)]."""
+    out, terms = [], constraint_terms(cfg)
+    for n, t in _terms(_get(cfg, "curriculum")):
+        if _fname(t.func) == "modify_constraint_p":
+            p = t.params or {}
+            if p["term_name"] not in terms:
+                raise NotImplementedError(f"curriculum.{n}: constraint term {p['term_name']!r} does not exist")
+            out.append((terms[p["term_name"]], int(p["num_steps"]), float(p["init_max_p"])))
+    return out
+
+
+def constraint_max_p(schedule, base, common_step_counter: int) -> list[float]:
+    """max_p of every constraint at a step count: utils/cat/curriculums.py:27-34 for the scheduled terms, the cfg value otherwise."""
+    p = list(base)
+    for idx, num_steps, init in schedule:
+        progress = min(common_step_counter / num_steps, 1.0)
+        p[idx] = 1.0 / (20 + progress * (1.0 / init - 20))
+    return p
+
+
 def curriculum_schedule(cfg) -> list[tuple[int, float, int]]:
-    """CurriculumManager terms -> [(reward slot, weight, num_steps)].  Only mdp.modify_reward_weight is implemented
-    (C12/rsl_env_cfg.py:447-497): once common_step_counter > num_steps the term's weight becomes `weight`."""
+    """CurriculumManager terms -> [(reward slot, weight, num_steps)].  mdp.modify_reward_weight (C12/rsl_env_cfg.py:447-497): once
+    common_step_counter > num_steps the term's weight becomes `weight`; curriculums.modify_constraint_p is handled by
+    constraint_curriculum; anything else is refused."""
     out, slots = [], reward_slots(cfg)
     for n, t in _terms(_get(cfg, "curriculum")):
         f, p = _fname(t.func), (t.params or {})
+        if f == "modify_constraint_p":
+            continue
         if f != "modify_reward_weight":
-            raise NotImplementedError(f"curriculum.{n}: mdp.{f} is not implemented (only modify_reward_weight is)")
+            raise NotImplementedError(f"curriculum.{n}: mdp.{f} is not implemented (only modify_reward_weight and modify_constraint_p are)")
         if p["term_name"] not in slots:
             raise NotImplementedError(f"curriculum.{n}: reward term {p['term_name']!r} has no kernel slot")
         out.append((slots[p["term_name"]], float(p["weight"]), int(p["num_steps"])))
@@ -137,8 +174,36 @@ def flatten_cfg(cfg) -> H1v2Config:
     config/h12_12dof/rsl_env_cfg.py:44-540) -> H1v2Config."""
     c = default_config()  # rigid-body model, MuJoCo solver parameters; everything below is overwritten from the tree
     # managers the fused kernel does not have: refuse rather than silently drop them
-    if _get(cfg, "constraints") is not None:
-        raise NotImplementedError("constraints: the Constraints-as-Terminations manager (utils/cat) is not implemented in the fused kernel")
+    # ---- Constraints-as-Terminations manager (utils/cat/*; C12/cat_env_cfg.py:336-431) ----
+    cterms = constraint_terms(cfg)
+    constraint_curriculum(cfg)
+    if cterms:
+        c.cat_enable = 1
+        for t in range(len(CSTR_NAMES)):
+            c.cat_max_p[t] = 0.0  # a term the cfg does not hold never terminates
+        all_joints = list(range(NJ))
+        for n, idx in cterms.items():
+            t = getattr(cfg.constraints, n)
+            p, f = (t.params or {}), CSTR_NAMES[idx]
+            c.cat_max_p[idx] = float(t.max_p)
+            if f in ("joint_position_limits", "joint_velocity_limits", "joint_torque_limits", "no_move") and sorted(_match(_get(_get(p, "asset_cfg"), "joint_names"), JOINT_NAMES)) != all_joints:
+                raise NotImplementedError(f"constraints.{n}: must cover all 12 leg joints")
+            if f in ("foot_contact_force", "foot_contact") and _slot_mask(p, "asset_cfg") != 0b11:
+                raise NotImplementedError(f"constraints.{n}: bodies must be the two ankle_roll links")
+            if f == "contact":
+                c.cat_contact_slots = _slot_mask(p, "asset_cfg")
+            elif f == "foot_contact_force":
+                c.cat_foot_force_limit = float(p["limit"])
+            elif f == "no_move":
+                c.cat_no_move_deadzone, c.cat_no_move_vel_limit = float(p["velocity_deadzone"]), float(p["joint_vel_limit"])
+            elif f == "base_orientation":
+                c.cat_orientation_limit = float(p["limit"])
+            elif f == "base_height":
+                c.cat_height, c.cat_height_std = float(p["height"]), float(p["std"])
+            elif f == "foot_clearance":
+                c.cat_clearance_min_height, c.cat_clearance_deadzone = float(p["min_height"]), float(p["velocity_deadzone"])
+                if _slot_mask(p, "contact_asset_cfg") != 0b11:
+                    raise NotImplementedError(f"constraints.{n}: bodies must be the two ankle_roll links")
     curriculum_schedule(cfg)  # raises on anything but modify_reward_weight; the schedule itself is applied by the env, host side
     c.sim_dt = float(cfg.sim.dt)
     c.decimation = int(cfg.decimation)
@@ -355,8 +420,7 @@ def flatten_cfg(cfg) -> H1v2Config:
         elif f == "randomize_rigid_body_mass":
             if p.get("operation", "add") != "add":
                 raise NotImplementedError(f"events.{n}: only operation='add' is supported")
-            if p.get("recompute_inertia", True) is False:  # the kernel rescales the inertia with the mass (isaaclab 2.1.0 default)
-                raise NotImplementedError(f"events.{n}: recompute_inertia=False is not supported")
+            c.mass_recompute_inertia = int(bool(p.get("recompute_inertia", True)))
             c.mass_add_range[0], c.mass_add_range[1] = map(float, p["mass_distribution_params"])
         elif f == "apply_external_force_torque":
             if any(abs(float(v)) > 0 for v in tuple(p["force_range"]) + tuple(p["torque_range"])):
@@ -572,3 +636,47 @@ class H1v2ManagerBasedRLEnv:
             self.close()
         except Exception:
             pass
+
+
+class H1v2CaTEnv(H1v2ManagerBasedRLEnv):
+    """CaTEnv drop-in (packages/biped_tasks/biped_tasks/utils/cat/cat_env.py:28-275): the same fused step followed by the
+    Constraints-as-Terminations tail.  step(action) -> (obs_dict, reward * (1 - p), dones, time_outs, extras) where dones is a
+    FLOAT tensor (the termination probability p, 1 for the envs that reset), exactly what cat_env.py:193 returns."""
+
+    def __init__(self, cfg, render_mode: str | None = None, **kwargs):
+        super().__init__(cfg, render_mode, **kwargs)
+        if not self.kernel_cfg.cat_enable:
+            raise ValueError("H1v2CaTEnv needs a cfg with a `constraints` group (use H1v2ManagerBasedRLEnv otherwise)")
+        terms = constraint_terms(cfg)
+        self.constraint_manager = _NamesView(list(terms))
+        self._cstr_names, self._cstr_idx = list(terms), [terms[n] for n in terms]
+        self._cstr_schedule = constraint_curriculum(cfg)
+        self._cstr_base = list(self.kernel_cfg.cat_max_p)
+        self._cstr_log = None
+        if self._cstr_schedule:  # CurriculumManager.compute runs in the first _reset_idx, i.e. before the first step
+            self.sim.set_constraint_max_p(constraint_max_p(self._cstr_schedule, self._cstr_base, 0))
+
+    def step(self, action):
+        import torch
+        obs, rew, dones, truncated = self.sim.cat_step(action)
+        self._prev_action, self._last_action = self._last_action, action
+        self.common_step_counter += 1
+        if self._curriculum:
+            self._apply_curriculum()
+        if self._cstr_schedule:
+            self.sim.set_constraint_max_p(constraint_max_p(self._cstr_schedule, self._cstr_base, self.common_step_counter))
+        self.obs_buf = {"policy": obs}
+        self.reward_buf, self.reset_time_outs = rew, truncated
+        self.reset_buf = dones >= 1.0
+        self.reset_terminated = self.reset_buf & ~truncated
+        log = self._log_dict()
+        # Episode_Constraint_violation / _probability (constraint_manager.py:185-203): means over the envs that reset in this step,
+        # the last such values otherwise; computed on the device from the tail's accumulators, no host sync
+        acc = self.sim.cat_acc_buf
+        cur = acc[:20] / acc[20].clamp(min=1.0)
+        self._cstr_log = cur if self._cstr_log is None else torch.where(acc[20] > 0, cur, self._cstr_log)
+        for i, n in zip(self._cstr_idx, self._cstr_names):
+            log[f"Episode_Constraint_violation/{n}"] = self._cstr_log[i]
+            log[f"Episode_Constraint_probability/{n}"] = self._cstr_log[10 + i]
+        self.extras = {"log": log}
+        return self.obs_buf, rew, dones, truncated, self.extras

@@ -10,6 +10,10 @@ from __future__ import annotations
 
 TASK_ID = "Isaac-Velocity-Flat-H12_12dof-v0"
 RSL_TASK_ID = "Isaac-Velocity-Rsl-H12_12dof-v0"
+CAT_TASK_ID = "Isaac-Velocity-CaT-Flat-H12_12dof-v0"
+# reward term names of C12/cat_env_cfg.py:306-333 by kernel slot
+CAT_REW_NAMES = {14: "track_lin_vel_xy_exp", 15: "track_ang_vel_z_exp", 8: "dof_torques_l2", 9: "joint_acc_l2", 17: "joint_vel_l2", 10: "action_rate_l2",
+                 6: "joint_deviation_l1"}
 # reward term names of C12/rsl_env_cfg.py:278-407 by kernel slot (the Flat tree uses _capi.REW_NAMES)
 RSL_REW_NAMES = {14: "track_lin_vel_xy_exp", 15: "track_ang_vel_z_exp", 3: "feet_air_time", 4: "feet_slide", 11: "flat_orientation",
                  18: "base_height_l2", 8: "joint_torques_l2", 17: "joint_vel_l2", 9: "dof_acc_l2", 6: "joint_deviation_hip",
@@ -56,6 +60,31 @@ def rsl_play_env_cfg(num_envs: int = 100, device: str = "cuda:0"):
     c.cmd_lin_y[0] = c.cmd_lin_y[1] = 0.0
     c.cmd_ang_z[0] = c.cmd_ang_z[1] = 0.0
     return env_cfg_from_config(c, num_envs, device, rew_names=RSL_REW_NAMES, curriculum=RSL_CURRICULUM, curriculum_steps=24 * 5000)
+
+
+def cat_config():
+    """Resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (C12/__init__.py:63-71 -> C12/cat_env_cfg.py:522-557): the Rsl cfg's
+    observation / action / command format on the delayed-PD robot (A/robots/h12.py:18-114), a 7-term reward, base mass +0..6 kg
+    without inertia rescaling, command dead zone 0.2, and the ten constraints of :336-431.  Checked value by value against the
+    reference's own cfg class in tests/test_boundary.py (tests/golden/cat_cfg_resolved.json)."""
+    from ._capi import default_config, rsl_config
+    c, d = rsl_config(), default_config()
+    c.min_delay, c.max_delay = d.min_delay, d.max_delay                   # cat_env_cfg.py:44 H12_12DOF (DelayedPDActuatorCfg)
+    for i in range(len(c.rew_weight)):
+        c.rew_weight[i] = 0.0
+    for slot, w in ((14, 1.0), (15, 0.5), (8, -1.0e-5), (9, -2.5e-7), (17, -1.0e-3), (10, -0.01), (6, -0.1)):  # :306-333
+        c.rew_weight[slot] = w
+    c.base_height_target = d.base_height_target                            # no base_height_l2 term in this cfg
+    c.mask_joint_dev = 0b110101110101                                      # hip yaw + roll, ankle pitch + roll of both legs (:321-331)
+    c.mass_add_range[0], c.mass_add_range[1] = 0.0, 6.0                   # :241-250 add_base_mass, recompute_inertia=False
+    c.mass_recompute_inertia = 0
+    c.velocity_deadzone = 0.2                                              # :48,114
+    c.cat_enable = 1                                                       # :336-431, parameters = h1v2_default_config's cat_* defaults
+    return c
+
+
+def cat_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
+    return env_cfg_from_config(cat_config(), num_envs, device, rew_names=CAT_REW_NAMES)
 
 
 def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_names=None, curriculum=(), curriculum_steps=0):
@@ -179,16 +208,38 @@ def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_nam
             "position_range": tuple(c.reset_joint_pos_scale), "velocity_range": tuple(c.reset_joint_vel_scale)}))
     if c.mass_add_range[0] != 0.0 or c.mass_add_range[1] != 0.0:
         ev["add_base_mass"] = EventTermCfg(func=mdp.randomize_rigid_body_mass, mode="startup", params={
-            "mass_distribution_params": tuple(c.mass_add_range), "operation": "add"})
+            "mass_distribution_params": tuple(c.mass_add_range), "operation": "add", "recompute_inertia": bool(c.mass_recompute_inertia)})
     if c.push_enable:
         ev["push_robot"] = EventTermCfg(func=mdp.push_by_setting_velocity, mode="interval", interval_range_s=tuple(c.push_interval_s),
                                         params={"velocity_range": {"x": tuple(c.push_vel_xy), "y": tuple(c.push_vel_xy)}})
     perm = list(c.joint_perm)
     action = ienvs.JointPositionActionCfg(asset_name="robot", joint_names=[JOINT_NAMES[j] for j in perm], scale=c.action_scale,
                                           use_default_offset=True, preserve_order=True)
+    cons = None
+    if c.cat_enable:  # the ten ConstraintTerms of C12/cat_env_cfg.py:336-431 and their modify_constraint_p curriculum (:462-519)
+        import isaaclab_tasks.manager_based.locomotion.velocity.mdp as cmdp  # named stand-ins for utils/cat/constraints.py functions
+        from ._capi import CSTR_NAMES
+        robot_all = SceneEntityCfg("robot", joint_names=[".*"])
+        feet_s = SceneEntityCfg("contact_forces", body_names=SLOT_BODIES[:2])
+        cparams = {
+            "contact": {"asset_cfg": SceneEntityCfg("contact_forces", body_names=names(c.cat_contact_slots, SLOT_BODIES))},
+            "joint_position_limits": {"asset_cfg": robot_all}, "joint_velocity_limits": {"asset_cfg": robot_all}, "joint_torque_limits": {"asset_cfg": robot_all},
+            "foot_contact_force": {"limit": c.cat_foot_force_limit, "asset_cfg": feet_s},
+            "no_move": {"velocity_deadzone": c.cat_no_move_deadzone, "joint_vel_limit": c.cat_no_move_vel_limit, "asset_cfg": robot_all},
+            "base_orientation": {"limit": c.cat_orientation_limit, "asset_cfg": SceneEntityCfg("robot")},
+            "base_height": {"asset_cfg": SceneEntityCfg("robot"), "height": c.cat_height, "std": c.cat_height_std},
+            "foot_contact": {"asset_cfg": feet_s},
+            "foot_clearance": {"min_height": c.cat_clearance_min_height, "velocity_deadzone": c.cat_clearance_deadzone,
+                               "pos_asset_cfg": SceneEntityCfg("robot", body_names=SLOT_BODIES[:2]), "contact_asset_cfg": feet_s}}
+        cons = bag(**{n: Placeholder(func=getattr(cmdp, n), max_p=float(c.cat_max_p[i]), params=cparams[n]) for i, n in enumerate(CSTR_NAMES) if c.cat_max_p[i] > 0})
+        sched = {n: Placeholder(func=cmdp.modify_constraint_p, params={"term_name": n, "num_steps": 24 * 5000, "init_max_p": float(c.cat_max_p[i])})
+                 for i, n in enumerate(CSTR_NAMES) if i > 0 and c.cat_max_p[i] > 0}
+        cur = bag(**{**(cur.__dict__ if cur is not None else {}), **sched})
     cfg = ienvs.ManagerBasedRLEnvCfg(decimation=c.decimation, episode_length_s=c.episode_length_s, scene=scene,
                                      observations=bag(policy=policy), actions=bag(joint_pos=action), rewards=rewards,
                                      terminations=terminations, commands=commands, events=bag(**ev), curriculum=cur)
+    if cons is not None:
+        object.__setattr__(cfg, "constraints", cons)
     cfg.sim.dt = c.sim_dt
     cfg.sim.device = device
     cfg.sim.gravity = (0.0, 0.0, -c.gravity)
@@ -219,7 +270,7 @@ def register() -> bool:
     shims.install()
     import gymnasium as gym
     done = False
-    for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg"),
+    for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg"), (CAT_TASK_ID, "cat_env_cfg"),
                          (TASK_ID.replace("-v0", "-Play-v0"), "flat_play_env_cfg"), (RSL_TASK_ID.replace("-v0", "-Play-v0"), "rsl_play_env_cfg")):
         try:
             gym.spec(tid)
@@ -227,7 +278,7 @@ def register() -> bool:
         except Exception:
             pass
         # both ids use the same runner cfg (C12/__init__.py:47,91: rsl_rl_ppo_cfg:H12_12dof_FlatPPORunnerCfg)
-        gym.register(id=tid, entry_point="h1v2_isaac_b200.env:H1v2ManagerBasedRLEnv", disable_env_checker=True,
+        gym.register(id=tid, entry_point="h1v2_isaac_b200.env:" + ("H1v2CaTEnv" if tid == CAT_TASK_ID else "H1v2ManagerBasedRLEnv"), disable_env_checker=True,
                      kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}", "rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})
         done = True
     return done

@@ -49,6 +49,8 @@ extern "C" {
 #define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
 #define H1V2_MAX_HISTORY 10 /* the reference tasks use 10 (Flat), 6 (Rsl) and 1 (deploy) */
 #define H1V2_LOG_DIM 32      /* see h1v2_get_log */
+#define H1V2_NUM_CSTR 10     /* constraint terms of the CaT tail, order of H1V2_CSTR_* */
+#define H1V2_CSTR_COLS 56    /* their columns: 1 + 12 + 12 + 12 + 2 + 12 + 1 + 1 + 1 + 2 */
 #define H1V2_ACTION_ABS_MAX 1.0e6f /* an env whose action is non-finite or larger than this in magnitude is force-reset in that step
                                       (zero reward, terminated, counted in H1V2_LOG_NAN_RESETS), like a non-finite state */
 
@@ -76,6 +78,20 @@ enum {
   H1V2_REW_CONTACT_FORCES = 19,    /* contact_forces (own threshold and bodies)   rsl_env_cfg.py:395-404 */
   H1V2_REW_DOF_POS_LIMITS_B = 20,  /* second joint_pos_limits term (hips)         rsl_env_cfg.py:380-386 */
   H1V2_REW_JOINT_DEV_B = 21        /* second joint_deviation_l1 term (ankles)     rsl_env_cfg.py:358-372 */
+};
+
+/* constraint terms (utils/cat/constraints.py; parameters config/h12_12dof/cat_env_cfg.py:336-431) and their first column */
+enum {
+  H1V2_CSTR_CONTACT = 0,         /* contact                :86-99    col 0      */
+  H1V2_CSTR_JOINT_POS = 1,       /* joint_position_limits  :22-31    col 1..12  (MJCF joint order) */
+  H1V2_CSTR_JOINT_VEL = 2,       /* joint_velocity_limits  :34-43    col 13..24 */
+  H1V2_CSTR_JOINT_TORQUE = 3,    /* joint_torque_limits    :46-55    col 25..36 */
+  H1V2_CSTR_FOOT_FORCE = 4,      /* foot_contact_force     :161-168  col 37..38 */
+  H1V2_CSTR_NO_MOVE = 5,         /* no_move                :197-235  col 39..50 */
+  H1V2_CSTR_ORIENTATION = 6,     /* base_orientation       :102-108  col 51     */
+  H1V2_CSTR_HEIGHT = 7,          /* base_height            :256-272  col 52     */
+  H1V2_CSTR_FOOT_CONTACT = 8,    /* foot_contact           :171-194  col 53     */
+  H1V2_CSTR_CLEARANCE = 9        /* foot_clearance         :275-308  col 54..55 */
 };
 
 /* layout of the log vector returned by h1v2_get_log (all float):
@@ -179,6 +195,18 @@ typedef struct H1v2Config {
   float root_link_com[3];              /* COM of the root LINK (pelvis alone, h12_12dof.urdf:16 == h12_12dof.xml:67) in the pelvis frame:
                                           root_lin_vel_w/_b used by rewards and command metrics = v_origin + w x (R r) */
   int32_t body_vel_at_com;             /* 1: feet_slide reads the ankle_roll_link COM velocity (body_lin_vel_w), 0: link origin */
+  int32_t mass_recompute_inertia;      /* randomize_rigid_body_mass(recompute_inertia=...): 1 (isaaclab default) rescales the base inertia
+                                          with the mass, 0 (cat_env_cfg.py add_base_mass) adds the mass only */
+  /* ---- Constraints-as-Terminations tail (utils/cat/constraint_manager.py, cat_env.py:147-153; cat_env_cfg.py:336-431) ---- */
+  int32_t cat_enable;                  /* 1: h1v2_cat_step is available (keeps the per-env diagnostics buffer) */
+  float cat_tau, cat_min_p;            /* ConstraintManager(tau=0.95, min_p=0.0) */
+  float cat_max_p[H1V2_NUM_CSTR];      /* maximum termination probability per term (1.0 for contact, 0.25 for the rest) */
+  uint32_t cat_contact_slots;          /* contact: bit s = sensor slot s */
+  float cat_foot_force_limit;          /* 750 N */
+  float cat_no_move_deadzone, cat_no_move_vel_limit; /* 0.2, 6.0 rad/s */
+  float cat_orientation_limit;         /* 0.1 */
+  float cat_height, cat_height_std;    /* 1.0, 0.05 m */
+  float cat_clearance_min_height, cat_clearance_deadzone; /* 0.1 m, 0.2 */
   float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
                                           non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
   int32_t reserved[8];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
@@ -255,6 +283,22 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
  * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises.  (h1v2_step is CUDA-graph
  * capturable; a captured step keeps the parameter block of capture time, so re-capture after changing the weights.) */
 int h1v2_set_reward_weights(H1v2Handle* h, const float* weights);
+
+/* Constraints-as-Terminations step (CaTEnv.step, utils/cat/cat_env.py:95-193): h1v2_step followed by the constraint tail --
+ * rew is scaled by 1 - p, dones[N] (float) = p, and 1 for envs that reset; truncated as in h1v2_step.  Needs cfg.cat_enable.
+ * Four launches (step, dead-zone gather scan, constraint columns + their maxima over all envs, probabilities). */
+int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream);
+/* curriculums.modify_constraint_p (utils/cat/curriculums.py:20-42): new maximum probabilities, host array [H1V2_NUM_CSTR] */
+int h1v2_set_constraint_max_p(H1v2Handle* h, const float* max_p);
+/* host copies (synchronises): raw constraint columns and probabilities of the last cat step [H1V2_CSTR_COLS][N], the running
+ * column maxima [H1V2_CSTR_COLS]; NULL members are skipped */
+int h1v2_cat_debug(H1v2Handle* h, float* raw, float* probs, float* running_max);
+/* Episode_Constraint_violation/<term> (percent) and Episode_Constraint_probability/<term> of the envs reset in the last cat step that
+ * reset any (constraint_manager.py:185-203): out[0..9] violation, out[10..19] probability, out[20] number of such envs.  Synchronises. */
+int h1v2_get_cat_log_host(H1v2Handle* h, float* out /*[2 * H1V2_NUM_CSTR + 1]*/);
+/* device pointer to the SUMS behind that log (float[2 * H1V2_NUM_CSTR + 1]: violation sums x100, probability sums, count of the
+ * envs reset in the last cat step), for callers that must not synchronise */
+int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev);
 
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);

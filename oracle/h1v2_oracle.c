@@ -234,9 +234,11 @@ static void kinematics(const double* qpos, Kin* k) {
 }
 
 /* 6x6 spatial inertia of body b about the origin, world axes */
-static void body_inertia6(const Kin* k, int b, double mass_add, double I6[36]) {
+static void body_inertia6(const Kin* k, int b, double mass_add, int recompute_inertia, double I6[36]) {
   double m = h1v2_body_mass[b], scale = 1.0;
-  if (b == 0 && mass_add != 0.0) { scale = (m + mass_add) / m; m += mass_add; }
+  /* randomize_rigid_body_mass(operation="add"): the inertia tensor is rescaled with the mass unless recompute_inertia=False
+   * (C12/cat_env_cfg.py add_base_mass) */
+  if (b == 0 && mass_add != 0.0) { scale = recompute_inertia ? (m + mass_add) / m : 1.0; m += mass_add; }
   double c[3], off[3];
   matvec3(k->R[b], h1v2_body_ipos[b], off);
   for (int i = 0; i < 3; i++) c[i] = k->x[b][i] + off[i];
@@ -258,7 +260,7 @@ static void body_inertia6(const Kin* k, int b, double mass_add, double I6[36]) {
 
 static void mass_matrix(const H1v2Config* cfg, const Kin* k, double mass_add, double M[NV * NV]) {
   double Ic[NB][36];
-  for (int b = 0; b < NB; b++) body_inertia6(k, b, mass_add, Ic[b]);
+  for (int b = 0; b < NB; b++) body_inertia6(k, b, mass_add, cfg->mass_recompute_inertia, Ic[b]);
   for (int b = NB - 1; b >= 1; b--) {
     int p = h1v2_body_parent[b];
     for (int i = 0; i < 36; i++) Ic[p][i] += Ic[b][i];
@@ -325,7 +327,7 @@ static void rne_bias(const H1v2Config* cfg, const Kin* k, const double* qvel, do
   }
   for (int b = 0; b < NB; b++) {
     double I6[36], Ia[6], Iv[6], vf[6];
-    body_inertia6(k, b, mass_add, I6);
+    body_inertia6(k, b, mass_add, cfg->mass_recompute_inertia, I6);
     for (int r = 0; r < 6; r++) {
       Ia[r] = Iv[r] = 0;
       for (int c = 0; c < 6; c++) { Ia[r] += I6[6 * r + c] * cacc[b][c]; Iv[r] += I6[6 * r + c] * cvel[b][c]; }

@@ -14,13 +14,16 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "h1v2_isaac_b200", "shims"), os.path.jo
 import biped_tasks.tasks  # noqa: E402,F401  (runs the reference's gym.register calls)
 from isaaclab_tasks.utils import load_cfg_from_registry  # noqa: E402
 
-from h1v2_isaac_b200.env import config_to_dict, curriculum_schedule, flatten_cfg, reward_slots  # noqa: E402
+from h1v2_isaac_b200.env import config_to_dict, constraint_curriculum, constraint_terms, curriculum_schedule, flatten_cfg, reward_slots  # noqa: E402
 
-for TASK, name in (("Isaac-Velocity-Flat-H12_12dof-v0", "flat_cfg_resolved.json"), ("Isaac-Velocity-Rsl-H12_12dof-v0", "rsl_cfg_resolved.json")):
+for TASK, name in (("Isaac-Velocity-Flat-H12_12dof-v0", "flat_cfg_resolved.json"), ("Isaac-Velocity-Rsl-H12_12dof-v0", "rsl_cfg_resolved.json"),
+                   ("Isaac-Velocity-CaT-Flat-H12_12dof-v0", "cat_cfg_resolved.json")):
     env_cfg = load_cfg_from_registry(TASK, "env_cfg_entry_point")
-    agent_cfg = load_cfg_from_registry(TASK, "rsl_rl_cfg_entry_point")
-    out = {"task": TASK, "num_envs": env_cfg.scene.num_envs, "kernel_config": config_to_dict(flatten_cfg(env_cfg)), "agent": agent_cfg.to_dict(),
-           "reward_slots": reward_slots(env_cfg), "curriculum": curriculum_schedule(env_cfg)}
+    agent_cfg = load_cfg_from_registry(TASK, "rsl_rl_cfg_entry_point" if "CaT" not in TASK else "clean_rl_cfg_entry_point")
+    out = {"task": TASK, "num_envs": env_cfg.scene.num_envs, "kernel_config": config_to_dict(flatten_cfg(env_cfg)),
+           "agent": agent_cfg.to_dict() if hasattr(agent_cfg, "to_dict") else {k: v for k, v in vars(agent_cfg).items() if isinstance(v, (int, float, str, bool, list, tuple, type(None)))},
+           "reward_slots": reward_slots(env_cfg), "curriculum": curriculum_schedule(env_cfg),
+           "constraint_terms": constraint_terms(env_cfg), "constraint_curriculum": constraint_curriculum(env_cfg)}
     with open(os.path.join(ROOT, "tests", "golden", name), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote", name)

@@ -62,6 +62,31 @@ def test_self_contained_rsl_task_roundtrip():
     assert gym.spec(tasks.RSL_TASK_ID).kwargs["env_cfg_entry_point"]
 
 
+def test_cat_config_equals_reference_cfg_golden():
+    """tasks.cat_config / cat_env_cfg against the reference's own CaT cfg class (config/h12_12dof/cat_env_cfg.py:44-557, flattened in
+    tests/golden/cat_cfg_resolved.json): kernel config value by value, reward slots, the ten constraint terms and their
+    modify_constraint_p curriculum; the curriculum starts every scheduled term at max_p = 1 / 20 (curriculums.py:27-34)."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.env import (config_to_dict, constraint_curriculum, constraint_max_p, constraint_terms, flatten_cfg, reward_slots)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cat_cfg_resolved.json")))
+    tree = tasks.cat_env_cfg(16)
+    mine = config_to_dict(flatten_cfg(tree))
+    assert mine == config_to_dict(tasks.cat_config())
+    for k, v in gold["kernel_config"].items():
+        assert _close(mine[k], v), k
+    assert mine["cat_enable"] == 1 and mine["mass_recompute_inertia"] == 0 and abs(mine["velocity_deadzone"] - 0.2) < 1e-7
+    assert constraint_terms(tree) == gold["constraint_terms"] and reward_slots(tree) == gold["reward_slots"]
+    sched = constraint_curriculum(tree)
+    assert sorted(map(list, sched)) == sorted(gold["constraint_curriculum"]) and len(sched) == 9
+    p0 = constraint_max_p(sched, mine["cat_max_p"], 0)
+    assert p0[0] == 1.0 and all(abs(p - 0.05) < 1e-12 for p in p0[1:])
+    p1 = constraint_max_p(sched, mine["cat_max_p"], 10 ** 7)
+    assert all(abs(p - 0.25) < 1e-12 for p in p1[1:])
+    tasks.register()
+    import gymnasium as gym
+    assert gym.spec(tasks.CAT_TASK_ID).entry_point.endswith("H1v2CaTEnv")
+
+
 def test_self_contained_play_ids_equal_the_reference_play_cfgs():
     """tasks.flat_play_env_cfg / rsl_play_env_cfg against the reference's own Play cfg classes (C12/flat_env_cfg.py:51-66,
     C12/rsl_env_cfg.py:543-564), flattened in tests/golden/play_cfg_resolved.json: scene size, noise off, pushes and friction
@@ -148,6 +173,7 @@ def test_reference_cfg_tree_flattens_to_golden():
     again = json.load(open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json")))
     assert again == GOLD  # regenerating from the reference changes nothing
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json"))) == GOLD_RSL
+    assert json.load(open(os.path.join(ROOT, "tests", "golden", "cat_cfg_resolved.json")))["kernel_config"]["cat_enable"] == 1
     assert set(json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))) == {
         "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0"}
 
@@ -173,7 +199,7 @@ def test_unmodified_train_py_reaches_the_backend(tmp_path):
 def test_reference_variants_are_accepted_or_refused_by_name():
     """Which of the reference's H1-2 12-dof ids the backend takes: Flat and Flat-Play flatten, also with the
     H12_12DOF_IDEAL robot (IdealPD -> no delay line), and so do Rsl and Rsl-Play (dead-zone command class, second joint-set
-    terms, modify_reward_weight curriculum); CaT (constraint manager) and Rough (height scan, base_lin_vel) are refused with
+    terms, modify_reward_weight curriculum) and CaT (constraint manager); Rough (height scan, base_lin_vel) is refused with
     the name of the offending cfg entry, never approximated."""
     code = r'''
 import gymnasium as gym
@@ -203,7 +229,7 @@ import json; print("RESULT" + json.dumps(out))
     assert res["Isaac-Velocity-Flat-H12_12dof-v0"] == "ok corruption=1"
     assert res["Isaac-Velocity-Flat-H12_12dof-Play-v0"] == "ok corruption=0"
     assert res["ideal"] == "ok delays 0 0"
-    assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"].startswith("refused: constraints")
+    assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"] == "ok corruption=1"  # constraints group -> the CaT tail (h1v2_cat_step)
     assert res["Isaac-Velocity-Rsl-H12_12dof-v0"] == "ok corruption=1 class=1 H=6"
     assert res["Isaac-Velocity-Rsl-H12_12dof-Play-v0"] == "ok corruption=0 class=1 H=6"
     assert res["Isaac-Velocity-Rough-H12_12dof-v0"].startswith("refused: ")  # terrain curriculum, height scan, base_lin_vel
