@@ -129,34 +129,47 @@ __global__ void __launch_bounds__(128) cat_raw_kernel(const __grid_constant__ KP
   }
 }
 
+// term of every column (kCstrCol0 expanded), so that the column loop unrolls with compile-time term indices
+__host__ __device__ constexpr int cstr_term_of_col(int c) {
+  return c < 1 ? 0 : c < 13 ? 1 : c < 25 ? 2 : c < 37 ? 3 : c < 39 ? 4 : c < 51 ? 5 : c < 52 ? 6 : c < 53 ? 7 : c < 54 ? 8 : 9;
+}
+
 __global__ void __launch_bounds__(128) cat_apply_kernel(const float* __restrict__ diag, const CatParams C, const CatState T, int parity,
                                                        float* __restrict__ rew, float* __restrict__ dones) {
+  __shared__ float rm_s[H1V2_CSTR_COLS];
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = C.n;
-  const float* rm_old = T.rmax + parity * H1V2_CSTR_COLS;
-  float* rm_new = T.rmax + (parity ^ 1) * H1V2_CSTR_COLS;
+  if (threadIdx.x < H1V2_CSTR_COLS) {  // running maxima of this step, once per block (constraint_manager.py:59-62)
+    const int c = threadIdx.x;
+    const float cm = __int_as_float(T.cmax[c]);
+    const float rm = C.first ? cm : __fadd_rn(__fmul_rn(T.rmax[parity * H1V2_CSTR_COLS + c], C.tau), __fmul_rn(1.f - C.tau, cm));
+    rm_s[c] = rm;
+    if (blockIdx.x == 0) T.rmax[(parity ^ 1) * H1V2_CSTR_COLS + c] = rm;
+  }
+  __syncthreads();
   if (env >= N) return;
   const float* dg = diag + (size_t)env * H1V2_DIAG_DIM;
-  float p = 0.f;
   const bool reset = dg[167] != 0.f;
   const float inv_len = 1.f / fmaxf(dg[166], 1.f);
-#pragma unroll 1
+  float tmax[H1V2_NUM_CSTR];
+#pragma unroll
+  for (int t = 0; t < H1V2_NUM_CSTR; t++) tmax[t] = 0.f;
+#pragma unroll
+  for (int c = 0; c < H1V2_CSTR_COLS; c++) {  // independent loads: the compiler keeps them all in flight
+    const int t = cstr_term_of_col(c);
+    const float v = T.raw[(size_t)c * N + env];
+    float pc = 0.f;
+    if (v > 0.f) pc = C.min_p + fminf(fmaxf(__fdiv_rn(v, rm_s[c]), 0.f), 1.f) * (C.max_p[t] - C.min_p);  // :70-77
+    T.probs[(size_t)c * N + env] = pc;
+    tmax[t] = fmaxf(tmax[t], pc);
+  }
+  float p = 0.f;
+#pragma unroll
   for (int t = 0; t < H1V2_NUM_CSTR; t++) {
-    float tmax = 0.f;
-    for (int c = kCstrCol0[t]; c < kCstrCol0[t + 1]; c++) {
-      const float cm = __int_as_float(T.cmax[c]);
-      const float rm = C.first ? cm : __fadd_rn(__fmul_rn(rm_old[c], C.tau), __fmul_rn(1.f - C.tau, cm));  // constraint_manager.py:59-62
-      if (env == 0) rm_new[c] = rm;
-      const float v = T.raw[(size_t)c * N + env];
-      float pc = 0.f;
-      if (v > 0.f) pc = C.min_p + fminf(fmaxf(__fdiv_rn(v, rm), 0.f), 1.f) * (C.max_p[t] - C.min_p);  // :70-77
-      T.probs[(size_t)c * N + env] = pc;
-      tmax = fmaxf(tmax, pc);
-    }
-    p = fmaxf(p, tmax);
+    p = fmaxf(p, tmax[t]);
     // per-term episode statistics (constraint_manager.py:221-227) and their log on reset (:185-203)
-    float sv = T.sums[(size_t)t * N + env] + (tmax > 0.f ? 1.f : 0.f);
-    float sp = T.sums[(size_t)(H1V2_NUM_CSTR + t) * N + env] + tmax;
+    float sv = T.sums[(size_t)t * N + env] + (tmax[t] > 0.f ? 1.f : 0.f);
+    float sp = T.sums[(size_t)(H1V2_NUM_CSTR + t) * N + env] + tmax[t];
     if (reset) {
       atomicAdd(T.logacc + t, sv * inv_len * 100.f);
       atomicAdd(T.logacc + H1V2_NUM_CSTR + t, sp * inv_len);
