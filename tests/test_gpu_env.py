@@ -218,6 +218,9 @@ def test_c_abi_edge_cases(cfg):
     w = (C.c_float * _capi.NUM_REW)(*([float("nan")] + [0.0] * (_capi.NUM_REW - 1)))
     assert lib.h1v2_set_reward_weights(sim._h, w) != 0 and b"non-finite" in lib.h1v2_last_error()
     assert lib.h1v2_step(sim._h, None, None, None, None, None, None) != 0 and b"bad arguments" in lib.h1v2_last_error()
+    t = torch.zeros((n, 450), device="cuda")  # any valid device pointers: the call must be refused before it touches them
+    assert lib.h1v2_cat_step(sim._h, t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), None) != 0
+    assert b"cat_enable" in lib.h1v2_last_error()  # this handle has no constraint tail
     sim.close()
     h = C.c_void_p()
     for field, value, msg in (("history_length", 0, b"history_length"), ("history_length", 11, b"history_length"), ("max_delay", 9, b"delays"),
