@@ -459,6 +459,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
     rc |= dalloc(h, &T.cmax, (size_t)H1V2_CSTR_COLS);
     rc |= dalloc(h, &T.list, N);
     rc |= dalloc(h, &T.count, (size_t)1);
+    rc |= dalloc(h, &T.chunk_count, (N + 1023) / 1024);
     rc |= dalloc(h, &T.swing, 2 * N);
     rc |= dalloc(h, &T.sums, (size_t)2 * H1V2_NUM_CSTR * N);
     rc |= dalloc(h, &T.logacc, (size_t)2 * H1V2_NUM_CSTR + 1);
@@ -608,10 +609,12 @@ int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, f
   DeviceGuard guard(h->device);
   const CatParams C = cat_params(h);
   const int blocks = (h->n + 127) / 128;
-  cat_scan_kernel<<<1, 1024, 0, st>>>(h->S.diag, C, h->cat);
+  const int chunks = (h->n + 1023) / 1024;
+  cat_count_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
+  cat_scan_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
   cat_raw_kernel<<<blocks, 128, 0, st>>>(h->P, h->S.diag, C, h->cat);
   cat_apply_kernel<<<blocks, 128, 0, st>>>(h->S.diag, C, h->cat, h->cat_parity, rew, dones);
-  h->launches += 3;
+  h->launches += 4;
   h->cat_first = false;
   h->cat_parity ^= 1;
   CK(cudaGetLastError());

@@ -5,9 +5,10 @@
 //
 // Unlike the rest of the step this tail couples the envs of one process: every constraint column is normalised by a Polyak
 // average of its maximum over ALL envs of the current step, and no_move judges env i on the joints of another env (the
-// reference gathers the rows whose command is inside the dead zone and tiles that block over the batch).  So it is three small
+// reference gathers the rows whose command is inside the dead zone and tiles that block over the batch).  So it is four small
 // memory-bound launches over the values the step kernel left in its per-env diagnostics rows (csrc/h1v2_params.h):
-//   cat_scan_kernel   one block: ordered list of the envs whose whole command is inside the dead zone; clears the column maxima
+//   cat_count_kernel, cat_scan_kernel   ordered list of the envs whose whole command is inside the dead zone (two parallel passes
+//                     over chunks of 1024 envs); clears the column maxima and the log sums
 //   cat_raw_kernel    thread per env: the 56 raw constraint columns, their maxima (atomicMax), the swing-height tracker
 //   cat_apply_kernel  thread per env: running maxima, probabilities, p = max, reward *= 1 - p, dones, episode statistics, log
 #pragma once
@@ -29,6 +30,7 @@ struct CatState {
   int* cmax;      // [56]     this step's column maxima as float bits (all candidates are positive: clamp at 1e-6)
   int* list;      // [N]      envs whose command is inside the dead zone, ascending
   int* count;     // [1]
+  int* chunk_count;  // [ceil(N / 1024)] dead-zone members per chunk of 1024 envs
   float* swing;   // [2][N]   swing_max_height of foot_clearance
   float* sums;    // [2][10][N] per-term episode sums: violation count, probability
   float* logacc;  // [21]     sums over the envs reset in this step: violation[10], probability[10], count
@@ -37,28 +39,40 @@ __device__ __constant__ const int kCstrCol0[H1V2_NUM_CSTR + 1] = {0, 1, 13, 25, 
 
 __device__ __forceinline__ bool cmd_all_inside(const float* dg, float dz) { return fabsf(dg[141]) < dz && fabsf(dg[142]) < dz && fabsf(dg[143]) < dz; }
 
+// Ordered compaction in two parallel passes over chunks of 1024 envs: per-chunk counts, then every chunk places its own members
+// after the sum of the counts before it (the reference's boolean-mask gather keeps ascending env order, constraints.py:216-222).
+__global__ void __launch_bounds__(1024) cat_count_kernel(const float* __restrict__ diag, const CatParams C, const CatState T) {
+  const int tid = threadIdx.x, i = blockIdx.x * 1024 + tid;
+  if (blockIdx.x == 0) {
+    if (tid < H1V2_CSTR_COLS) T.cmax[tid] = __float_as_int(1e-6f);  // constraint.max(0).clamp(min=1e-6), constraint_manager.py:56
+    if (tid < 2 * H1V2_NUM_CSTR + 1) T.logacc[tid] = 0.f;
+  }
+  const bool f = i < C.n && cmd_all_inside(diag + (size_t)i * H1V2_DIAG_DIM, C.no_move_deadzone);
+  const int cnt = __syncthreads_count(f);
+  if (tid == 0) T.chunk_count[blockIdx.x] = cnt;
+}
+
 __global__ void __launch_bounds__(1024) cat_scan_kernel(const float* __restrict__ diag, const CatParams C, const CatState T) {
   __shared__ int warp_tot[32];
-  __shared__ int base;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid < H1V2_CSTR_COLS) T.cmax[tid] = __float_as_int(1e-6f);  // constraint.max(0).clamp(min=1e-6), constraint_manager.py:56
-  if (tid < 2 * H1V2_NUM_CSTR + 1) T.logacc[tid] = 0.f;
-  if (tid == 0) base = 0;
-  __syncthreads();
-  for (int start = 0; start < C.n; start += 1024) {
-    const int i = start + tid;
-    const bool f = i < C.n && cmd_all_inside(diag + (size_t)i * H1V2_DIAG_DIM, C.no_move_deadzone);
-    const unsigned m = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) warp_tot[w] = __popc(m);
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int k = 0; k < 32; k++) { const int t = warp_tot[k]; off += k < w ? t : 0; tot += t; }
-    if (f) T.list[base + off + __popc(m & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (tid == 0) base += tot;
-    __syncthreads();
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, i = blockIdx.x * 1024 + tid;
+  if (w == 0) {  // sum of the counts of the chunks before this one (and, in the last chunk, the total)
+    int b = 0;
+    for (int k = lane; k < (int)blockIdx.x; k += 32) b += T.chunk_count[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (lane == 0) {
+      base_s = b;
+      if (blockIdx.x == gridDim.x - 1) *T.count = b + T.chunk_count[blockIdx.x];
+    }
   }
-  if (tid == 0) *T.count = base;
+  const bool f = i < C.n && cmd_all_inside(diag + (size_t)i * H1V2_DIAG_DIM, C.no_move_deadzone);
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) warp_tot[w] = __popc(m);
+  __syncthreads();
+  int off = 0;
+  for (int k = 0; k < w; k++) off += warp_tot[k];
+  if (f) T.list[base_s + off + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // height of the ankle_roll_link origin above the ground (body_link_pos_w z, constraints.py:283)

@@ -286,7 +286,7 @@ int h1v2_set_reward_weights(H1v2Handle* h, const float* weights);
 
 /* Constraints-as-Terminations step (CaTEnv.step, utils/cat/cat_env.py:95-193): h1v2_step followed by the constraint tail --
  * rew is scaled by 1 - p, dones[N] (float) = p, and 1 for envs that reset; truncated as in h1v2_step.  Needs cfg.cat_enable.
- * Four launches (step, dead-zone gather scan, constraint columns + their maxima over all envs, probabilities). */
+ * Five launches (step, two passes of the dead-zone gather, constraint columns + their maxima over all envs, probabilities). */
 int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream);
 /* curriculums.modify_constraint_p (utils/cat/curriculums.py:20-42): new maximum probabilities, host array [H1V2_NUM_CSTR] */
 int h1v2_set_constraint_max_p(H1v2Handle* h, const float* max_p);
