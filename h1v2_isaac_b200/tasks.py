@@ -259,6 +259,15 @@ def default_agent_cfg():
                                        max_grad_norm=1.0))
 
 
+def cat_agent_cfg():
+    """CleanRL PPO cfg of the CaT id (values: config/h12_12dof/agents/clean_rl_ppo_cfg.py, schema utils/cleanrl/rl_cfg.py:11-38)."""
+    import types
+    return types.SimpleNamespace(
+        seed=42, save_interval=200, learning_rate=3.0e-4, num_steps=24, num_iterations=50000, gamma=0.99, gae_lambda=0.95, updates_epochs=5,
+        minibatch_size=16384, clip_coef=0.2, ent_coef=0.0081, vf_coef=2.0, max_grad_norm=1.0, norm_adv=True, clip_vloss=True, anneal_lr=True,
+        experiment_name="h12_12dof_flat", logger="tensorboard", wandb_project="h12_12dof_flat", load_run=".*", load_checkpoint="model_.*.pt")
+
+
 def ienvs_managers():
     import isaaclab.managers as m
     return m
@@ -279,6 +288,8 @@ def register() -> bool:
             pass
         # both ids use the same runner cfg (C12/__init__.py:47,91: rsl_rl_ppo_cfg:H12_12dof_FlatPPORunnerCfg)
         gym.register(id=tid, entry_point="h1v2_isaac_b200.env:" + ("H1v2CaTEnv" if tid == CAT_TASK_ID else "H1v2ManagerBasedRLEnv"), disable_env_checker=True,
-                     kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}", "rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})
+                     kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}",
+                             **({"clean_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:cat_agent_cfg"} if tid == CAT_TASK_ID  # C12/__init__.py:63-71
+                                else {"rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})})
         done = True
     return done

@@ -84,7 +84,9 @@ def test_cat_config_equals_reference_cfg_golden():
     assert all(abs(p - 0.25) < 1e-12 for p in p1[1:])
     tasks.register()
     import gymnasium as gym
-    assert gym.spec(tasks.CAT_TASK_ID).entry_point.endswith("H1v2CaTEnv")
+    assert gym.spec(tasks.CAT_TASK_ID).entry_point.endswith("H1v2CaTEnv") and "clean_rl_cfg_entry_point" in gym.spec(tasks.CAT_TASK_ID).kwargs
+    agent = vars(tasks.cat_agent_cfg())
+    assert agent == gold["agent"]  # the CleanRL PPO cfg of the reference (agents/clean_rl_ppo_cfg.py), value by value
 
 
 def test_self_contained_play_ids_equal_the_reference_play_cfgs():
