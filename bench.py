@@ -30,7 +30,12 @@ def algo_bytes_per_env_step(history: int) -> int:
     return 1222 + 360 * history
 
 
-TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-H12_12dof-v0"}
+TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-H12_12dof-v0", "cat": "Isaac-Velocity-CaT-Flat-H12_12dof-v0"}
+
+
+def task_config(task: str):
+    from h1v2_isaac_b200 import _capi, tasks
+    return {"flat": _capi.default_config, "rsl": _capi.rsl_config, "cat": tasks.cat_config}[task]()
 
 
 def parse():
@@ -40,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1] = 4096; configs[3] = 32768)")
-    ap.add_argument("--task", default="flat", choices=sorted(TASKS), help="flat = BASELINE's metric config (default); rsl = the SURVEY 8(f)1 variant, same kernel")
+    ap.add_argument("--task", default="flat", choices=sorted(TASKS), help="flat = BASELINE's metric config (default); rsl / cat = the SURVEY 8(f) variants (cat: fused step + constraint tail)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -140,8 +145,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from h1v2_isaac_b200._capi import default_config, rsl_config
-    cfg = rsl_config() if args.task == "rsl" else default_config()
+    cfg = task_config(args.task)
+    cfg.cat_enable = 0  # the CPU restatement of the constraint tail is numpy test infrastructure (oracle/cat_oracle.py), not timed here
     cb = cpu_baseline(cfg, args.seed, steps=max(1, args.steps) if args.steps <= 50 else None, warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": cb["steps"],
@@ -185,7 +190,8 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     n = args.envs
-    cfg = _capi.rsl_config() if args.task == "rsl" else default_config()
+    cfg = task_config(args.task)
+    is_cat = args.task == "cat"
     ALGO_BYTES_PER_ENV_STEP = algo_bytes_per_env_step(cfg.history_length)
     cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -200,10 +206,11 @@ def run_ours(args):
         pool = [sim.random_actions(i) for i in range(16)]  # synthetic N(0,1) actions, resident in HBM
         obs = torch.empty((n_envs, sim.obs_dim), device=dev)
         rew = torch.empty(n_envs, device=dev)
-        term = torch.empty(n_envs, dtype=torch.uint8, device=dev)
+        term = torch.empty(n_envs, dtype=torch.float32 if is_cat else torch.uint8, device=dev)  # CaT: float dones
         trunc = torch.empty(n_envs, dtype=torch.uint8, device=dev)
+        step_into = sim.cat_step_into if is_cat else sim.step_into
         for i in range(W):
-            sim.step_into(pool[i % 16], obs, rew, term, trunc)
+            step_into(pool[i % 16], obs, rew, term, trunc)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -213,7 +220,7 @@ def run_ours(args):
         for i in range(steps):
             flush.zero_()  # L2 flush between timed iterations (not timed)
             ev[i][0].record()
-            sim.step_into(pool[i % 16], obs, rew, term, trunc)
+            step_into(pool[i % 16], obs, rew, term, trunc)
             ev[i][1].record()
         torch.cuda.synchronize()
         if world > 1:
@@ -233,7 +240,7 @@ def run_ours(args):
 
     # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not is_cat:  # h1v2_step_host has no constraint tail: no host-buffer number for --task cat
         ha = [p.cpu().pin_memory() for p in pool[:4]]
         hobs = torch.empty((n, sim.obs_dim), dtype=torch.float32).pin_memory()
         hrew = torch.empty(n, dtype=torch.float32).pin_memory()

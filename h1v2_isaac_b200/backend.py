@@ -107,6 +107,10 @@ class H1v2Sim:
         self._check(self._lib.h1v2_cat_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dones.data_ptr(), trunc.data_ptr(), self._stream()))
         return obs, rew, dones, trunc.view(torch.bool)
 
+    def cat_step_into(self, actions, obs, rew, dones, trunc):
+        """cat_step() with caller-provided output tensors (dones float32 [N])."""
+        self._check(self._lib.h1v2_cat_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(), dones.data_ptr(), trunc.data_ptr(), self._stream()))
+
     def set_constraint_max_p(self, max_p) -> None:
         import numpy as np
         p = np.ascontiguousarray(max_p, dtype=np.float32)

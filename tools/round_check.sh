@@ -7,6 +7,7 @@ python bench.py > gpurun_out/${tag}_bench_4096.json 2> gpurun_out/${tag}_bench_4
 python bench.py --envs 32768 --no-big > gpurun_out/${tag}_bench_32768.json 2> gpurun_out/${tag}_bench_32768.err
 python bench.py --task rsl --no-cpu-baseline > gpurun_out/${tag}_bench_rsl_4096.json 2> gpurun_out/${tag}_bench_rsl_4096.err
 python bench.py --task rsl --envs 32768 --no-big --no-cpu-baseline > gpurun_out/${tag}_bench_rsl_32768.json 2> gpurun_out/${tag}_bench_rsl_32768.err
+python bench.py --task cat --no-cpu-baseline > gpurun_out/${tag}_bench_cat_4096.json 2> gpurun_out/${tag}_bench_cat_4096.err
 for n in 4096 32768; do
   ncu --set full --clock-control none --import-source on -k regex:step_kernel --launch-skip 30 --launch-count 1 -f -o gpurun_out/prof_${tag}_${n} python tools/prof_target.py $n 40 > gpurun_out/${tag}_ncu_${n}.log 2>&1
 done
