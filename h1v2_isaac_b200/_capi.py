@@ -107,6 +107,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libh1v2_b200.so")
 _SYMBOLS = {
     "h1v2_default_config": (C.c_int, [C.POINTER(H1v2Config)]),
     "h1v2_rsl_config": (C.c_int, [C.POINTER(H1v2Config)]),
+    "h1v2_cat_config": (C.c_int, [C.POINTER(H1v2Config)]),
     "h1v2_create": (C.c_int, [C.POINTER(H1v2Config), i32, i32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "h1v2_destroy": (None, [C.c_void_p]),
     "h1v2_last_error": (C.c_char_p, []),
@@ -171,4 +172,13 @@ def rsl_config() -> H1v2Config:
     rc = load_library().h1v2_rsl_config(C.byref(cfg))
     if rc != 0:
         raise RuntimeError("h1v2_rsl_config failed")
+    return cfg
+
+
+def cat_config() -> H1v2Config:
+    """Resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (config/h12_12dof/cat_env_cfg.py)."""
+    cfg = H1v2Config()
+    rc = load_library().h1v2_cat_config(C.byref(cfg))
+    if rc != 0:
+        raise RuntimeError("h1v2_cat_config failed")
     return cfg

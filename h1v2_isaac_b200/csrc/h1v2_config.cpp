@@ -199,3 +199,27 @@ extern "C" int h1v2_rsl_config(H1v2Config* c) {
   c->push_vel_xy[0] = -1.0f; c->push_vel_xy[1] = 1.0f;
   return 0;
 }
+
+// Resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (C12/__init__.py:63-71 -> C12/cat_env_cfg.py:528-565 H12_12dof_EnvCfg): the Rsl
+// cfg's observation / action / command format on the delayed-PD robot, a 7-term reward, and the Constraints-as-Terminations tail.
+extern "C" int h1v2_cat_config(H1v2Config* c) {
+  H1v2Config d;
+  if (h1v2_rsl_config(c) != 0 || h1v2_default_config(&d) != 0) return -1;
+  c->min_delay = d.min_delay; c->max_delay = d.max_delay;  // C12/cat_env_cfg.py:44 H12_12DOF (DelayedPDActuatorCfg, A/robots/h12.py:18-114)
+  for (int t = 0; t < H1V2_NUM_REW; t++) c->rew_weight[t] = 0.0f;
+  c->rew_weight[H1V2_REW_TRACK_LIN_XY_BASE] = 1.0f;   // :304-308
+  c->rew_weight[H1V2_REW_TRACK_ANG_Z_BASE] = 0.5f;    // :309-313
+  c->rew_weight[H1V2_REW_TORQUES] = -1.0e-5f;         // :316
+  c->rew_weight[H1V2_REW_DOF_ACC] = -2.5e-7f;         // :317
+  c->rew_weight[H1V2_REW_JOINT_VEL] = -1.0e-3f;       // :318
+  c->rew_weight[H1V2_REW_ACTION_RATE] = -0.01f;       // :319
+  c->rew_weight[H1V2_REW_JOINT_DEV_HIP] = -0.1f;      // :320-331 hip yaw + roll, ankle pitch + roll of both legs
+  c->mask_joint_dev = (1u << 0) | (1u << 2) | (1u << 4) | (1u << 5) | (1u << 6) | (1u << 8) | (1u << 10) | (1u << 11);
+  c->base_height_target = d.base_height_target;        // no base_height_l2 term in this cfg
+  c->mass_add_range[0] = 0.0f; c->mass_add_range[1] = 6.0f;  // :242-251 add_base_mass, recompute_inertia=False
+  c->mass_recompute_inertia = 0;
+  c->velocity_deadzone = 0.2f;                          // :48,114 VELOCITY_DEADZONE
+  c->cat_enable = 1;                                    // :336-431; the cat_* parameters are h1v2_default_config's
+  return 0;
+}
+

@@ -63,24 +63,10 @@ def rsl_play_env_cfg(num_envs: int = 100, device: str = "cuda:0"):
 
 
 def cat_config():
-    """Resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (C12/__init__.py:63-71 -> C12/cat_env_cfg.py:522-557): the Rsl cfg's
-    observation / action / command format on the delayed-PD robot (A/robots/h12.py:18-114), a 7-term reward, base mass +0..6 kg
-    without inertia rescaling, command dead zone 0.2, and the ten constraints of :336-431.  Checked value by value against the
-    reference's own cfg class in tests/test_boundary.py (tests/golden/cat_cfg_resolved.json)."""
-    from ._capi import default_config, rsl_config
-    c, d = rsl_config(), default_config()
-    c.min_delay, c.max_delay = d.min_delay, d.max_delay                   # cat_env_cfg.py:44 H12_12DOF (DelayedPDActuatorCfg)
-    for i in range(len(c.rew_weight)):
-        c.rew_weight[i] = 0.0
-    for slot, w in ((14, 1.0), (15, 0.5), (8, -1.0e-5), (9, -2.5e-7), (17, -1.0e-3), (10, -0.01), (6, -0.1)):  # :306-333
-        c.rew_weight[slot] = w
-    c.base_height_target = d.base_height_target                            # no base_height_l2 term in this cfg
-    c.mask_joint_dev = 0b110101110101                                      # hip yaw + roll, ankle pitch + roll of both legs (:321-331)
-    c.mass_add_range[0], c.mass_add_range[1] = 0.0, 6.0                   # :241-250 add_base_mass, recompute_inertia=False
-    c.mass_recompute_inertia = 0
-    c.velocity_deadzone = 0.2                                              # :48,114
-    c.cat_enable = 1                                                       # :336-431, parameters = h1v2_default_config's cat_* defaults
-    return c
+    """Resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0: h1v2_cat_config (csrc/h1v2_config.cpp cites C12/cat_env_cfg.py line by line);
+    checked value by value against the reference's own cfg class in tests/test_boundary.py (tests/golden/cat_cfg_resolved.json)."""
+    from ._capi import cat_config as _cat_config
+    return _cat_config()
 
 
 def cat_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):

@@ -256,6 +256,7 @@ typedef struct H1v2Handle H1v2Handle;
 
 int h1v2_default_config(H1v2Config* cfg); /* resolved cfg of Isaac-Velocity-Flat-H12_12dof-v0 */
 int h1v2_rsl_config(H1v2Config* cfg);     /* resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (config/h12_12dof/rsl_env_cfg.py:503-540) */
+int h1v2_cat_config(H1v2Config* cfg);     /* resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (config/h12_12dof/cat_env_cfg.py:528-565) */
 int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t seed, H1v2Handle** out);
 void h1v2_destroy(H1v2Handle* h);
 const char* h1v2_last_error(void);
