@@ -2,7 +2,7 @@
 # ncu launch list of a short bench run (B200_PROFILING.md: --metrics gpu__time_duration.sum --clock-control none), after the same
 # command has exited 0 without ncu.  Writes gpurun_out/<tag>_launches.csv and a per-kernel summary.
 tag=${1:-rX}
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-big"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-big ${2:+--task $2}"   # optional 2nd argument: flat / rsl / cat
 $CMD > gpurun_out/${tag}_launch_plain.log 2>&1 || { echo "bench failed without ncu"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_launch_ncu.log 2>&1
 python - "$tag" "$CMD" <<'PY'
