@@ -608,12 +608,12 @@ int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, f
   if (launch_step(h, true, actions, obs, rew, h->cat_term, truncated, st) != 0) return -1;
   DeviceGuard guard(h->device);
   const CatParams C = cat_params(h);
-  const int blocks = (h->n + 127) / 128;
+  const int blocks = (h->n + 63) / 64;  // small blocks: at 4096 envs the tail is latency-bound, spread it over more SMs
   const int chunks = (h->n + 1023) / 1024;
   cat_count_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
   cat_scan_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
-  cat_raw_kernel<<<blocks, 128, 0, st>>>(h->P, h->S.diag, C, h->cat);
-  cat_apply_kernel<<<blocks, 128, 0, st>>>(h->S.diag, C, h->cat, h->cat_parity, rew, dones);
+  cat_raw_kernel<<<blocks, 64, 0, st>>>(h->P, h->S.diag, C, h->cat);
+  cat_apply_kernel<<<blocks, 64, 0, st>>>(h->S.diag, C, h->cat, h->cat_parity, rew, dones);
   h->launches += 4;
   h->cat_first = false;
   h->cat_parity ^= 1;

@@ -89,7 +89,7 @@ __device__ __forceinline__ float foot_height(const KLeg& LG, const M3& R0, float
   return root_z + x.z;
 }
 
-__global__ void __launch_bounds__(128) cat_raw_kernel(const __grid_constant__ KParams P, const float* __restrict__ diag, const CatParams C, const CatState T) {
+__global__ void __launch_bounds__(64) cat_raw_kernel(const __grid_constant__ KParams P, const float* __restrict__ diag, const CatParams C, const CatState T) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = env < C.n;
   const float* dg = diag + (size_t)(valid ? env : 0) * H1V2_DIAG_DIM;
@@ -148,7 +148,7 @@ __host__ __device__ constexpr int cstr_term_of_col(int c) {
   return c < 1 ? 0 : c < 13 ? 1 : c < 25 ? 2 : c < 37 ? 3 : c < 39 ? 4 : c < 51 ? 5 : c < 52 ? 6 : c < 53 ? 7 : c < 54 ? 8 : 9;
 }
 
-__global__ void __launch_bounds__(128) cat_apply_kernel(const float* __restrict__ diag, const CatParams C, const CatState T, int parity,
+__global__ void __launch_bounds__(64) cat_apply_kernel(const float* __restrict__ diag, const CatParams C, const CatState T, int parity,
                                                        float* __restrict__ rew, float* __restrict__ dones) {
   __shared__ float rm_s[H1V2_CSTR_COLS];
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
