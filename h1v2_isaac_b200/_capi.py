@@ -66,7 +66,7 @@ class H1v2Config(C.Structure):
         ("mass_recompute_inertia", i32), ("cat_enable", i32), ("cat_tau", f32), ("cat_min_p", f32), ("cat_max_p", f32 * 10), ("cat_contact_slots", u32),
         ("cat_foot_force_limit", f32), ("cat_no_move_deadzone", f32), ("cat_no_move_vel_limit", f32), ("cat_orientation_limit", f32),
         ("cat_height", f32), ("cat_height_std", f32), ("cat_clearance_min_height", f32), ("cat_clearance_deadzone", f32),
-        ("runaway_vel", f32), ("reserved", i32 * 8),
+        ("runaway_vel", f32), ("solver_vel_tolerance", f32), ("reserved", i32 * 7),
     ]
 
     def copy(self) -> "H1v2Config":
@@ -142,7 +142,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("H1V2_LIB") or LIB_PATH  # H1V2_LIB: build variants under test (tools/diag_variants.py)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: the CUDA extension is the product and there is no fallback. "

@@ -25,8 +25,8 @@ class _DevPtr:
 
 class H1v2Sim:
     def __init__(self, num_envs: int, cfg: H1v2Config | None = None, device: str | torch.device = "cuda:0",
-                 seed: int = 42, diagnostics: bool = False):
-        self._lib = load_library()
+                 seed: int = 42, diagnostics: bool = False, lib_path: str | None = None):
+        self._lib = load_library(lib_path)  # lib_path: a build variant of the same ABI (tests: the double-precision build)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("H1v2Sim runs on CUDA devices only (no CPU fallback)")

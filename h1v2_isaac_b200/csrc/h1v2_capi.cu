@@ -84,9 +84,9 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
   const int64_t gid = P.env_id_offset + env;
   const unsigned long long step = S.counters[0];
   float4 r3 = S.root[3 * N + env];
-  float mu = r3.y, mass_add = r3.z, push_left = r3.w;
+  real mu = r3.y, mass_add = r3.z, push_left = r3.w;
   (void)startup;
-  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
+  real rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
   float4 tm;
   CmdState cmd;
   cmd.flags = 0; cmd.heading_target = 0.f;
@@ -349,7 +349,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   kb_h(c.contact_solref, c.contact_solimp, c.sim_dt, &P.contact_K, &P.contact_B);
   for (int k = 0; k < 5; k++) { P.limit_imp[k] = c.limit_solimp[k]; P.contact_imp[k] = c.contact_solimp[k]; }
   for (int s = 0; s < 6; s++) P.slot_tran[s] = (float)h1v2_slot_invweight_tran[s];
-  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance; P.ls_tol = c.solver_ls_tolerance > 0.f ? c.solver_ls_tolerance : 0.01f;
+  P.max_iters = c.solver_iterations; P.tol = c.solver_tolerance; P.step_tol = c.solver_step_tolerance; P.vel_tol = c.solver_vel_tolerance > 0.f ? c.solver_vel_tolerance / c.sim_dt : 3.0e38f; P.ls_tol = c.solver_ls_tolerance > 0.f ? c.solver_ls_tolerance : 0.01f;
   P.ls_max = c.reserved[1] > 0 ? c.reserved[1] : 6;  // reserved[1]: tuning knob for the line-search trip cap
   P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
   if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
@@ -530,7 +530,7 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
   DeviceGuard guard(h->device);
   const int threads = H1V2_BLOCK;
   const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
-  const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(float);
+  const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(real);
   if (!h->attr_set) {  // function attributes are per device: keep the flag with the handle, not with the process
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

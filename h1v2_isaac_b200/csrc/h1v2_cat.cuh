@@ -82,7 +82,7 @@ __device__ __forceinline__ float foot_height(const KLeg& LG, const M3& R0, float
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
     x = x + mulv(R, ld3(LG.pos[i]));
-    float s_, c_;
+    real s_, c_;
     sincos_lim(q[i], s_, c_);
     rotate_rt(R, joint_axis(i), s_, c_);
   }

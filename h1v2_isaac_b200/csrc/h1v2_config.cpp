@@ -59,6 +59,9 @@ extern "C" int h1v2_default_config(H1v2Config* c) {
                               // 30 when the friction range reaches below 0.3 (10x fewer non-converged solves at mu ~ 0.1, tools/diag_rand3.py)
   c->solver_tolerance = 1e-5f;  // on the scaled gradient norm; the fp32 noise floor of that norm is ~3e-6 (profiles/r1_notes.md), below it iterations only chase rounding
   c->solver_step_tolerance = 1e-3f;
+  c->solver_vel_tolerance = 2e-4f;  // rad/s per physics step: h * max_j |grad_j| * invweight0_j.  The gradient-norm test alone lets 2.3e-3 N m pass on a
+                                    // swinging ankle (1/invweight0 = 0.011 kg m^2): 1e-3 rad/s, the whole single-step tolerance; free on B200 (the residual of a
+                                    // converged Newton step is almost always far below both tests: 2.55 -> 2.55 iterations per substep, profiles/r2_notes.md)
   c->solver_ls_tolerance = 0.3f;  // MuJoCo default 0.01; 0.01..0.3 give the same Newton iteration histogram and parity on B200 (tools/diag_lstol.py), 0.3 is 5 % faster
   // observations: V/velocity_env_cfg.py:123-132 ; C12/flat_env_cfg.py:25-27
   c->history_length = 10;

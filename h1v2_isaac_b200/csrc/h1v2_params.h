@@ -49,6 +49,7 @@ struct KParams {
   int max_iters;
   float tol;  // on |grad| * scale
   float step_tol;
+  float vel_tol;  // second convergence test: h * max_j |grad_j| * invweight0_j below this (<= 0: off, stored as a huge number)
   int ls_max;    // line-search evaluations per Newton iteration (default 6, then the secant root of the bracket: measured on B200, iteration histogram and parity identical to 12; at <= 4 rare solves stall)
   float ls_tol;  // line-search tolerance on |phi'(alpha)| / |phi'(0)|  (MuJoCo opt.ls_tolerance = 0.01)
   float grad_scale;

@@ -46,10 +46,16 @@ namespace h1v2 {
 #ifndef U_EVJ
 #define U_EVJ 1
 #endif
+#ifndef H1V2_FINAL_MX
+#define H1V2_FINAL_MX 1  // rhs of the implicit update = M x (1) or f_smooth + J'f re-evaluated (0, round 1)
+#endif
+#ifndef U_PRO
+#define U_PRO 1  // once-per-substep joint loops (kinematics passes, smooth forces)
+#endif
 // shared-memory column of one thread: 6 joints x JSTRIDE floats, then MAXC contact points x PSTRIDE floats.
 // 220 floats per thread = 28160 B per warp: 8 warps per SM ((28160 + 1024 reserved) * 8 = 228 KB exactly).  Measured on
 // B200: throughput still grows linearly with resident warps at 7 per SM (tools: H1V2_SMEM_PAD experiment, profiles/r1_notes.md),
-// so every float here is worth keeping out: the link mass comes from the parameter block, the ABA 1/D shares a slot
+// so every real here is worth keeping out: the link mass comes from the parameter block, the ABA 1/D shares a slot
 // with the extra-diagonal / M-product scratch, and the active contact list holds 5 points.
 #define JSTRIDE 30
 #define F_W 0      // 3  joint axis (world)
@@ -72,13 +78,13 @@ namespace h1v2 {
 #define SMEM_FLOATS (PT_BASE + MAXC * PSTRIDE)
 
 struct Smem {
-  float* base;  // this thread's column
-  __device__ __forceinline__ float& jf(int j, int f) const { return base[(j * JSTRIDE + f) * H1V2_BLOCK]; }
-  __device__ __forceinline__ float& pf(int p, int f) const { return base[(PT_BASE + p * PSTRIDE + f) * H1V2_BLOCK]; }
+  real* base;  // this thread's column
+  __device__ __forceinline__ real& jf(int j, int f) const { return base[(j * JSTRIDE + f) * H1V2_BLOCK]; }
+  __device__ __forceinline__ real& pf(int p, int f) const { return base[(PT_BASE + p * PSTRIDE + f) * H1V2_BLOCK]; }
   __device__ __forceinline__ V3 jv(int j, int f) const { return mk3(jf(j, f), jf(j, f + 1), jf(j, f + 2)); }
   __device__ __forceinline__ void sjv(int j, int f, V3 v) const { jf(j, f) = v.x; jf(j, f + 1) = v.y; jf(j, f + 2) = v.z; }
   __device__ __forceinline__ V3 pv(int p, int f) const { return mk3(pf(p, f), pf(p, f + 1), pf(p, f + 2)); }
-  __device__ __forceinline__ RI ji(int j, float m) const {
+  __device__ __forceinline__ RI ji(int j, real m) const {
     RI I;
     I.m = m; I.mc = jv(j, F_I);
     I.xx = jf(j, F_I + 3); I.yy = jf(j, F_I + 4); I.zz = jf(j, F_I + 5); I.xy = jf(j, F_I + 6); I.xz = jf(j, F_I + 7); I.yz = jf(j, F_I + 8);
@@ -95,27 +101,27 @@ struct Smem {
 // fixed registers (~13 instructions and spills, profiles/r1g), the constant-mask one to a single SHFL.  The Newton loop
 // below is therefore warp-synchronous: every lane runs every trip, lanes whose solve is finished are masked by selects.
 #define FULL_MASK 0xffffffffu
-__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(FULL_MASK, v, 1); }
+__device__ __forceinline__ real pair_sum(real v) { return v + __shfl_xor_sync(FULL_MASK, v, 1); }
 __device__ __forceinline__ V3 pair_sum(V3 v) { return mk3(pair_sum(v.x), pair_sum(v.y), pair_sum(v.z)); }
 
 // MuJoCo getimpedance (solimp = d0, dmax, width, midpoint, power), margin 0
-__device__ __forceinline__ float impedance(const float* si, float pos) {
-  float dmin = fminf(fmaxf(si[0], 1e-4f), 0.9999f), dmax = fminf(fmaxf(si[1], 1e-4f), 0.9999f);
-  float width = si[2], mid = fminf(fmaxf(si[3], 1e-4f), 0.9999f), power = fmaxf(si[4], 1.f);
+__device__ __forceinline__ real impedance(const float* si, real pos) {
+  real dmin = r_min(r_max(si[0], 1e-4f), 0.9999f), dmax = r_min(r_max(si[1], 1e-4f), 0.9999f);
+  real width = si[2], mid = r_min(r_max(si[3], 1e-4f), 0.9999f), power = r_max(si[4], 1.f);
   if (dmin == dmax || width <= 1e-15f) return 0.5f * (dmin + dmax);
-  float x = fabsf(pos) / width;
+  real x = r_abs(pos) / width;
   if (x >= 1.f) return dmax;
   if (x == 0.f) return dmin;
-  float y;
+  real y;
   if (power == 1.f) y = x;
   else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else y = (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  else y = (x <= mid) ? r_pow(x, power) / r_pow(mid, power - 1.f) : 1.f - r_pow(1.f - x, power) / r_pow(1.f - mid, power - 1.f);
   return dmin + y * (dmax - dmin);
 }
 
 // general symmetric 6x6 in [ang;lin] order: aa (xx yy zz xy xz yz), al (row = ang, col = lin), ll (xx yy zz xy xz yz)
 struct K6 {
-  float aa[6], al[9], ll[6];
+  real aa[6], al[9], ll[6];
 };
 __device__ __forceinline__ void k6_zero(K6& K) {
 #pragma unroll
@@ -135,27 +141,27 @@ __device__ __forceinline__ void k6_add_rigid(K6& K, const RI& I) {
   K.ll[0] += I.m; K.ll[1] += I.m; K.ll[2] += I.m;
   K.al[1] -= I.mc.z; K.al[2] += I.mc.y; K.al[3] += I.mc.z; K.al[5] -= I.mc.x; K.al[6] -= I.mc.y; K.al[7] += I.mc.x;
 }
-__device__ __forceinline__ V3 sym3_mul(const float* s, V3 v) {
-  return mk3(fmaf(s[0], v.x, fmaf(s[3], v.y, s[4] * v.z)), fmaf(s[3], v.x, fmaf(s[1], v.y, s[5] * v.z)),
-             fmaf(s[4], v.x, fmaf(s[5], v.y, s[2] * v.z)));
+__device__ __forceinline__ V3 sym3_mul(const real* s, V3 v) {
+  return mk3(r_fma(s[0], v.x, r_fma(s[3], v.y, s[4] * v.z)), r_fma(s[3], v.x, r_fma(s[1], v.y, s[5] * v.z)),
+             r_fma(s[4], v.x, r_fma(s[5], v.y, s[2] * v.z)));
 }
 // (n,l) = K (w,u)
 __device__ __forceinline__ void k6_apply(const K6& K, V3 w, V3 u, V3& n, V3& l) {
-  n = sym3_mul(K.aa, w) + mk3(fmaf(K.al[0], u.x, fmaf(K.al[1], u.y, K.al[2] * u.z)), fmaf(K.al[3], u.x, fmaf(K.al[4], u.y, K.al[5] * u.z)),
-                              fmaf(K.al[6], u.x, fmaf(K.al[7], u.y, K.al[8] * u.z)));
-  l = sym3_mul(K.ll, u) + mk3(fmaf(K.al[0], w.x, fmaf(K.al[3], w.y, K.al[6] * w.z)), fmaf(K.al[1], w.x, fmaf(K.al[4], w.y, K.al[7] * w.z)),
-                              fmaf(K.al[2], w.x, fmaf(K.al[5], w.y, K.al[8] * w.z)));
+  n = sym3_mul(K.aa, w) + mk3(r_fma(K.al[0], u.x, r_fma(K.al[1], u.y, K.al[2] * u.z)), r_fma(K.al[3], u.x, r_fma(K.al[4], u.y, K.al[5] * u.z)),
+                              r_fma(K.al[6], u.x, r_fma(K.al[7], u.y, K.al[8] * u.z)));
+  l = sym3_mul(K.ll, u) + mk3(r_fma(K.al[0], w.x, r_fma(K.al[3], w.y, K.al[6] * w.z)), r_fma(K.al[1], w.x, r_fma(K.al[4], w.y, K.al[7] * w.z)),
+                              r_fma(K.al[2], w.x, r_fma(K.al[5], w.y, K.al[8] * w.z)));
 }
 // K -= (n;l)(n;l)' * s
-__device__ __forceinline__ void k6_rank1_sub(K6& K, V3 n, V3 l, float s) {
+__device__ __forceinline__ void k6_rank1_sub(K6& K, V3 n, V3 l, real s) {
   V3 ns = n * s, ls = l * s;
-  K.aa[0] = fmaf(-ns.x, n.x, K.aa[0]); K.aa[1] = fmaf(-ns.y, n.y, K.aa[1]); K.aa[2] = fmaf(-ns.z, n.z, K.aa[2]);
-  K.aa[3] = fmaf(-ns.x, n.y, K.aa[3]); K.aa[4] = fmaf(-ns.x, n.z, K.aa[4]); K.aa[5] = fmaf(-ns.y, n.z, K.aa[5]);
-  K.ll[0] = fmaf(-ls.x, l.x, K.ll[0]); K.ll[1] = fmaf(-ls.y, l.y, K.ll[1]); K.ll[2] = fmaf(-ls.z, l.z, K.ll[2]);
-  K.ll[3] = fmaf(-ls.x, l.y, K.ll[3]); K.ll[4] = fmaf(-ls.x, l.z, K.ll[4]); K.ll[5] = fmaf(-ls.y, l.z, K.ll[5]);
-  K.al[0] = fmaf(-ns.x, l.x, K.al[0]); K.al[1] = fmaf(-ns.x, l.y, K.al[1]); K.al[2] = fmaf(-ns.x, l.z, K.al[2]);
-  K.al[3] = fmaf(-ns.y, l.x, K.al[3]); K.al[4] = fmaf(-ns.y, l.y, K.al[4]); K.al[5] = fmaf(-ns.y, l.z, K.al[5]);
-  K.al[6] = fmaf(-ns.z, l.x, K.al[6]); K.al[7] = fmaf(-ns.z, l.y, K.al[7]); K.al[8] = fmaf(-ns.z, l.z, K.al[8]);
+  K.aa[0] = r_fma(-ns.x, n.x, K.aa[0]); K.aa[1] = r_fma(-ns.y, n.y, K.aa[1]); K.aa[2] = r_fma(-ns.z, n.z, K.aa[2]);
+  K.aa[3] = r_fma(-ns.x, n.y, K.aa[3]); K.aa[4] = r_fma(-ns.x, n.z, K.aa[4]); K.aa[5] = r_fma(-ns.y, n.z, K.aa[5]);
+  K.ll[0] = r_fma(-ls.x, l.x, K.ll[0]); K.ll[1] = r_fma(-ls.y, l.y, K.ll[1]); K.ll[2] = r_fma(-ls.z, l.z, K.ll[2]);
+  K.ll[3] = r_fma(-ls.x, l.y, K.ll[3]); K.ll[4] = r_fma(-ls.x, l.z, K.ll[4]); K.ll[5] = r_fma(-ls.y, l.z, K.ll[5]);
+  K.al[0] = r_fma(-ns.x, l.x, K.al[0]); K.al[1] = r_fma(-ns.x, l.y, K.al[1]); K.al[2] = r_fma(-ns.x, l.z, K.al[2]);
+  K.al[3] = r_fma(-ns.y, l.x, K.al[3]); K.al[4] = r_fma(-ns.y, l.y, K.al[4]); K.al[5] = r_fma(-ns.y, l.z, K.al[5]);
+  K.al[6] = r_fma(-ns.z, l.x, K.al[6]); K.al[7] = r_fma(-ns.z, l.y, K.al[7]); K.al[8] = r_fma(-ns.z, l.z, K.al[8]);
 }
 
 // K about O_s  ->  K about O_r, with O_s = O_r + d  (motion at O_s: u_s = u_r + w x d):  K_r = X' K_s X, X = [[1,0],[-[d]x,1]]
@@ -175,36 +181,36 @@ __device__ __forceinline__ void k6_shift(K6& K, V3 d) {
 // a_k = (0,mu,1) (0,-mu,1) (-mu,0,1) (mu,0,1)   (normal z, tangents y and -x: mju_makeFrame on the plane normal);
 // an edge is active where j_k < 0, with force -D*j_k along a_k.
 struct Edges {
-  float j0, j1, j2, j3;
+  real j0, j1, j2, j3;
 };
-__device__ __forceinline__ Edges point_edges(V3 e, float kap, float mu) {
+__device__ __forceinline__ Edges point_edges(V3 e, real kap, real mu) {
   Edges E;
-  E.j0 = fmaf(mu, e.y, e.z) + kap; E.j1 = fmaf(-mu, e.y, e.z) + kap;
-  E.j2 = fmaf(-mu, e.x, e.z) + kap; E.j3 = fmaf(mu, e.x, e.z) + kap;
+  E.j0 = r_fma(mu, e.y, e.z) + kap; E.j1 = r_fma(-mu, e.y, e.z) + kap;
+  E.j2 = r_fma(-mu, e.x, e.z) + kap; E.j3 = r_fma(mu, e.x, e.z) + kap;
   return E;
 }
 // contact force of the point (world axes)
-__device__ __forceinline__ V3 point_force(V3 e, float kap, float D, float mu) {
+__device__ __forceinline__ V3 point_force(V3 e, real kap, real D, real mu) {
   const Edges E = point_edges(e, kap, mu);
-  const float f0 = E.j0 < 0.f ? -D * E.j0 : 0.f, f1 = E.j1 < 0.f ? -D * E.j1 : 0.f;
-  const float f2 = E.j2 < 0.f ? -D * E.j2 : 0.f, f3 = E.j3 < 0.f ? -D * E.j3 : 0.f;
+  const real f0 = E.j0 < 0.f ? -D * E.j0 : 0.f, f1 = E.j1 < 0.f ? -D * E.j1 : 0.f;
+  const real f2 = E.j2 < 0.f ? -D * E.j2 : 0.f, f3 = E.j3 < 0.f ? -D * E.j3 : 0.f;
   return mk3(mu * (f3 - f2), mu * (f0 - f1), (f0 + f1) + (f2 + f3));
 }
 // 3x3 weight W = D * sum_active a a'  as  xx yy zz xz yz
-__device__ __forceinline__ void point_weight(V3 e, float kap, float D, float mu, float (&W)[5]) {
+__device__ __forceinline__ void point_weight(V3 e, real kap, real D, real mu, real (&W)[5]) {
   const Edges E = point_edges(e, kap, mu);
-  const float a0 = E.j0 < 0.f ? D : 0.f, a1 = E.j1 < 0.f ? D : 0.f, a2 = E.j2 < 0.f ? D : 0.f, a3 = E.j3 < 0.f ? D : 0.f;
+  const real a0 = E.j0 < 0.f ? D : 0.f, a1 = E.j1 < 0.f ? D : 0.f, a2 = E.j2 < 0.f ? D : 0.f, a3 = E.j3 < 0.f ? D : 0.f;
   W[0] = mu * mu * (a2 + a3);
   W[1] = mu * mu * (a0 + a1);
   W[2] = (a0 + a1) + (a2 + a3);
   W[3] = mu * (a3 - a2);
   W[4] = mu * (a0 - a1);
 }
-__device__ __forceinline__ V3 w5_mul(const float (&W)[5], V3 g) {
+__device__ __forceinline__ V3 w5_mul(const real (&W)[5], V3 g) {
   return mk3(W[0] * g.x + W[3] * g.z, W[1] * g.y + W[4] * g.z, W[3] * g.x + W[4] * g.y + W[2] * g.z);
 }
 // K += X' W X with X = [G | 1], G = -[r]x   (point velocity u = v_O + w x r)
-__device__ __forceinline__ void k6_add_point(K6& K, V3 r, const float (&W)[5]) {
+__device__ __forceinline__ void k6_add_point(K6& K, V3 r, const real (&W)[5]) {
   V3 g0 = mk3(0.f, -r.z, r.y), g1 = mk3(r.z, 0.f, -r.x), g2 = mk3(-r.y, r.x, 0.f);  // columns of G: e_j x r
   V3 w0 = w5_mul(W, g0), w1 = w5_mul(W, g1), w2 = w5_mul(W, g2);
   K.aa[0] += dot(g0, w0); K.aa[1] += dot(g1, w1); K.aa[2] += dot(g2, w2);
@@ -215,27 +221,27 @@ __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const float (&W)[5]) {
   K.ll[0] += W[0]; K.ll[1] += W[1]; K.ll[2] += W[2]; K.ll[4] += W[3]; K.ll[5] += W[4];
 }
 // line-search contribution of one contact point: d1 += D*jar*jv, d2 += D*jv^2 over the edges active at ea
-__device__ __forceinline__ void point_ls(V3 ea, V3 us, float kap, float D, float mu, float& d1, float& d2) {
+__device__ __forceinline__ void point_ls(V3 ea, V3 us, real kap, real D, real mu, real& d1, real& d2) {
   const Edges E = point_edges(ea, kap, mu);
-  const float v0 = fmaf(mu, us.y, us.z), v1 = fmaf(-mu, us.y, us.z), v2 = fmaf(-mu, us.x, us.z), v3 = fmaf(mu, us.x, us.z);
+  const real v0 = r_fma(mu, us.y, us.z), v1 = r_fma(-mu, us.y, us.z), v2 = r_fma(-mu, us.x, us.z), v3 = r_fma(mu, us.x, us.z);
   // branch-free: an inactive edge contributes min(j,0) = 0 to the first sum and a zeroed velocity to the second
-  const float w0 = E.j0 < 0.f ? v0 : 0.f, w1 = E.j1 < 0.f ? v1 : 0.f, w2 = E.j2 < 0.f ? v2 : 0.f, w3 = E.j3 < 0.f ? v3 : 0.f;
-  const float s1 = fmaf(E.j0, w0, fmaf(E.j1, w1, fmaf(E.j2, w2, E.j3 * w3)));
-  const float s2 = fmaf(w0, w0, fmaf(w1, w1, fmaf(w2, w2, w3 * w3)));
-  d1 = fmaf(D, s1, d1);
-  d2 = fmaf(D, s2, d2);
+  const real w0 = E.j0 < 0.f ? v0 : 0.f, w1 = E.j1 < 0.f ? v1 : 0.f, w2 = E.j2 < 0.f ? v2 : 0.f, w3 = E.j3 < 0.f ? v3 : 0.f;
+  const real s1 = r_fma(E.j0, w0, r_fma(E.j1, w1, r_fma(E.j2, w2, E.j3 * w3)));
+  const real s2 = r_fma(w0, w0, r_fma(w1, w1, r_fma(w2, w2, w3 * w3)));
+  d1 = r_fma(D, s1, d1);
+  d2 = r_fma(D, s2, d2);
 }
 // friction-loss row: force and activity (= D inside the quadratic zone) at residual jar.  The zone boundary R*fl is where
 // the linear force -D*jar reaches +-fl (D = 1/R), so the row is a clamp: no branches and no third constant.
-__device__ __forceinline__ float floss_force(float jar, float D, float fl, float& act) {
-  const float f = -D * jar;
-  act = fabsf(f) < fl ? D : 0.f;
-  return fminf(fmaxf(f, -fl), fl);
+__device__ __forceinline__ real floss_force(real jar, real D, real fl, real& act) {
+  const real f = -D * jar;
+  act = r_abs(f) < fl ? D : 0.f;
+  return r_min(r_max(f, -fl), fl);
 }
 
 struct SubOut {
   V3 F_foot, F_shin, F_torso, F_pelvis;  // net contact forces (torso/pelvis pair-summed, valid on both lanes)
-  float qacc[6];                         // joint accelerations of this leg after the implicit update
+  real qacc[6];                         // joint accelerations of this leg after the implicit update
   int iters, capped, overflow;
 };
 
@@ -244,13 +250,13 @@ struct SubOut {
 struct RootBasis {
   V3 c[3], rd[3];
 };
-__device__ __forceinline__ void root_project_force(const RootBasis& B, V3 n, V3 l, float (&out)[6]) {
+__device__ __forceinline__ void root_project_force(const RootBasis& B, V3 n, V3 l, real (&out)[6]) {
   out[0] = l.x; out[1] = l.y; out[2] = l.z;
 #pragma unroll
   for (int k = 0; k < 3; k++) out[3 + k] = dot(B.c[k], n) + dot(B.rd[k], l);
 }
 // A (packed lower 6x6) += S_r' K S_r
-__device__ __forceinline__ void root_project_k6(const RootBasis& B, const K6& K, float (&A)[21]) {
+__device__ __forceinline__ void root_project_k6(const RootBasis& B, const K6& K, real (&A)[21]) {
   A[TI(0, 0)] += K.ll[0]; A[TI(1, 1)] += K.ll[1]; A[TI(2, 2)] += K.ll[2];
   A[TI(1, 0)] += K.ll[3]; A[TI(2, 0)] += K.ll[4]; A[TI(2, 1)] += K.ll[5];
 #pragma unroll
@@ -263,25 +269,25 @@ __device__ __forceinline__ void root_project_k6(const RootBasis& B, const K6& K,
   }
 }
 // spatial "velocity" of the root body for generalized vector xr, about O_r + d
-__device__ __forceinline__ void root_motion(const RootBasis& B, const float (&xr)[6], V3 d, V3& a, V3& l) {
+__device__ __forceinline__ void root_motion(const RootBasis& B, const real (&xr)[6], V3 d, V3& a, V3& l) {
   a = fma3(B.c[0], xr[3], fma3(B.c[1], xr[4], B.c[2] * xr[5]));
   l = mk3(xr[0], xr[1], xr[2]) + cross(a, d);
 }
 
 // same about the pelvis origin itself (d = 0): rotation k is (c_k, 0)
-__device__ __forceinline__ void root_project_force0(const V3 (&c)[3], V3 n, V3 l, float (&out)[6]) {
+__device__ __forceinline__ void root_project_force0(const V3 (&c)[3], V3 n, V3 l, real (&out)[6]) {
   out[0] = l.x; out[1] = l.y; out[2] = l.z;
 #pragma unroll
   for (int k = 0; k < 3; k++) out[3 + k] = dot(c[k], n);
 }
-__device__ __forceinline__ void root_project_k60(const V3 (&c)[3], const K6& K, float (&A)[21]) {
+__device__ __forceinline__ void root_project_k60(const V3 (&c)[3], const K6& K, real (&A)[21]) {
   A[TI(0, 0)] += K.ll[0]; A[TI(1, 1)] += K.ll[1]; A[TI(2, 2)] += K.ll[2];
   A[TI(1, 0)] += K.ll[3]; A[TI(2, 0)] += K.ll[4]; A[TI(2, 1)] += K.ll[5];
 #pragma unroll
   for (int b = 0; b < 3; b++) {
     const V3 n = sym3_mul(K.aa, c[b]);
-    const V3 l = mk3(fmaf(K.al[0], c[b].x, fmaf(K.al[3], c[b].y, K.al[6] * c[b].z)), fmaf(K.al[1], c[b].x, fmaf(K.al[4], c[b].y, K.al[7] * c[b].z)),
-                     fmaf(K.al[2], c[b].x, fmaf(K.al[5], c[b].y, K.al[8] * c[b].z)));
+    const V3 l = mk3(r_fma(K.al[0], c[b].x, r_fma(K.al[3], c[b].y, K.al[6] * c[b].z)), r_fma(K.al[1], c[b].x, r_fma(K.al[4], c[b].y, K.al[7] * c[b].z)),
+                     r_fma(K.al[2], c[b].x, r_fma(K.al[5], c[b].y, K.al[8] * c[b].z)));
     A[TI(3 + b, 0)] += l.x; A[TI(3 + b, 1)] += l.y; A[TI(3 + b, 2)] += l.z;
 #pragma unroll
     for (int a = 0; a <= b; a++) A[TI(3 + b, 3 + a)] += dot(c[a], n);
@@ -291,23 +297,23 @@ __device__ __forceinline__ void root_project_k60(const V3 (&c)[3], const K6& K, 
 // joint axis in the link frame: hip_yaw z, hip_pitch y, hip_roll x, knee y, ankle_pitch y, ankle_roll x (h12_12dof.xml:71-96);
 // checked against the compiled model by build_params.  The index is warp-uniform, so the branches below do not diverge.
 __device__ __forceinline__ int joint_axis(int i) { return (0x146 >> (2 * i)) & 3; }
-__device__ __forceinline__ void rotate_rt(M3& R, int ax, float s, float c) {
+__device__ __forceinline__ void rotate_rt(M3& R, int ax, real s, real c) {
   if (ax == 2) rotate_sc<2>(R, s, c);
   else if (ax == 1) rotate_sc<1>(R, s, c);
   else rotate_sc<0>(R, s, c);
 }
 __device__ __forceinline__ V3 axis_rt(const M3& R, int ax) { return ax == 0 ? R.cx : (ax == 1 ? R.cy : R.cz); }
-__device__ __noinline__ float impedance_general(const float* si, float pos) { return impedance(si, pos); }
+__device__ __noinline__ real impedance_general(const float* si, real pos) { return impedance(si, pos); }
 // MuJoCo's default solimp (power 2, every geom and joint of h12_12dof.xml) inline; anything else out of line (powf paths)
-__device__ __forceinline__ float impedance_call(const float* si, float pos) {
+__device__ __forceinline__ real impedance_call(const float* si, real pos) {
   if (si[4] != 2.f || si[2] <= 1e-15f) return impedance_general(si, pos);
-  const float dmin = fminf(fmaxf(si[0], 1e-4f), 0.9999f), dmax = fminf(fmaxf(si[1], 1e-4f), 0.9999f);
-  const float mid = fminf(fmaxf(si[3], 1e-4f), 0.9999f);
+  const real dmin = r_min(r_max(si[0], 1e-4f), 0.9999f), dmax = r_min(r_max(si[1], 1e-4f), 0.9999f);
+  const real mid = r_min(r_max(si[3], 1e-4f), 0.9999f);
   if (dmin == dmax) return 0.5f * (dmin + dmax);
-  const float x = fabsf(pos) / si[2];
+  const real x = r_abs(pos) / si[2];
   if (x >= 1.f) return dmax;
   if (x == 0.f) return dmin;
-  const float y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  const real y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
   return dmin + y * (dmax - dmin);
 }
 
@@ -322,36 +328,36 @@ __device__ __forceinline__ float impedance_call(const float* si, float pos) {
 // "evaluate" and "solve" halves of an iteration that can be re-derived from the contact list (the contact
 // stiffness is accumulated straight into the articulated inertia during the tip->root sweep).
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, float (&rp)[3],
-                                     float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
-                                     const float (&tau)[6], const float mu, const float mass_add, float (&wl)[6], float (&wr)[6],
+__device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, real (&rp)[3],
+                                     real (&rq)[4], real (&rv)[3], real (&rw)[3], real (&q)[6], real (&qd)[6],
+                                     const real (&tau)[6], const real mu, const real mass_add, real (&wl)[6], real (&wr)[6],
                                      const bool use_warm, SubOut& out) {
-  extern __shared__ __align__(16) float smem_raw[];
+  extern __shared__ __align__(16) real smem_raw[];
   const Smem sm{smem_raw + tid};
   const KLeg& LG = P.leg[side];
-  const float h = P.h;
+  const real h = P.h;
   const int j0 = 6 * side;
   const V3 zero3 = mk3(0.f, 0.f, 0.f);
   // ---- stage the per-joint inputs in the column: q -> F_XQ, qd -> F_FLC, tau -> F_FS, warm start -> F_R ----
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const float lim = P.frc[j0 + j];
+    const real lim = P.frc[j0 + j];
     sm.jf(j, F_XQ) = q[j]; sm.jf(j, F_FLC) = qd[j];
-    sm.jf(j, F_FS) = lim > 0.f ? fminf(fmaxf(tau[j], -lim), lim) : tau[j];
+    sm.jf(j, F_FS) = lim > 0.f ? r_min(r_max(tau[j], -lim), lim) : tau[j];
     sm.jf(j, F_R) = use_warm ? wl[j] : 0.f;
   }
   // ---- root frame (about O_r = pelvis origin) ----
   {
-    float n = rsqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
+    real n = r_rsqrt(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
     rq[0] *= n; rq[1] *= n; rq[2] *= n; rq[3] *= n;
   }
   const M3 R0 = quat2mat(rq[0], rq[1], rq[2], rq[3]);
   const V3 v0 = mk3(rv[0], rv[1], rv[2]);
   const V3 om0 = mulv(R0, mk3(rw[0], rw[1], rw[2]));
   const V3 acc0 = mk3(0.f, 0.f, P.gravity) + cross(v0, om0);  // root cacc: -gravity + free-joint cdof_dot * qvel
-  const float m0 = P.root_mass + mass_add;
+  const real m0 = P.root_mass + mass_add;
   const RI I0 = body_inertia(R0, mulv(R0, ld3(P.root_ipos)), m0, P.root_inertia, P.mass_scales_inertia ? m0 / P.root_mass : 1.f);
-  float fs_root[6];  // first the bias force of the root link about O_r, then the smooth force of the root dofs
+  real fs_root[6];  // first the bias force of the root link about O_r, then the smooth force of the root dofs
   {
     V3 an, al, vn, vl;
     ri_apply(I0, zero3, acc0, an, al);
@@ -364,10 +370,10 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   {
     M3 R = R0;
     V3 x = zero3;
-#pragma unroll 1
+UNROLL(U_PRO)
     for (int i = 0; i < 6; i++) {
       x = x + mulv(R, ld3(LG.pos[i]));
-      float s, c;
+      real s, c;
       sincos_lim(sm.jf(i, F_XQ), s, c);
       sm.jf(i, F_G) = s; sm.jf(i, F_DG) = c;
       rotate_rt(R, joint_axis(i), s, c);
@@ -384,10 +390,10 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   {
     M3 R = R0;
     V3 x = zero3 - d, om = om0, vo = v0 + cross(om0, d), al = zero3, ao = acc0;
-#pragma unroll 1
+UNROLL(U_PRO)
     for (int i = 0; i < 6; i++) {
       const int ax = joint_axis(i);
-      const float qdi = sm.jf(i, F_FLC);
+      const real qdi = sm.jf(i, F_FLC);
       x = x + mulv(R, ld3(LG.pos[i]));
       const V3 wi = axis_rt(R, ax);
       const V3 ui = cross(x, wi);
@@ -410,46 +416,46 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   // ---- smooth forces: tau - bias - damping*v ; dof-row constants (friction loss, joint limits) ----
   {
     V3 fcn = zero3, fcl = zero3;
-#pragma unroll 1
+UNROLL(U_PRO)
     for (int j = 5; j >= 0; j--) {
       fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
       const int jj = j0 + j;
-      const float qj = sm.jf(j, F_XQ), qdj = sm.jf(j, F_FLC);
-      const float fs = sm.jf(j, F_FS) - (dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl)) - P.damping[6 + jj] * qdj;
+      const real qj = sm.jf(j, F_XQ), qdj = sm.jf(j, F_FLC);
+      const real fs = sm.jf(j, F_FS) - (dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl)) - P.damping[6 + jj] * qdj;
       sm.jf(j, F_FS) = fs;
       sm.jf(j, F_XQ) = 0.f; sm.jf(j, F_MA) = -fs; sm.jf(j, F_G) = 0.f;
       sm.jf(j, F_FLC) = P.floss_B * qdj;
-      const float dlo = qj - P.range_lo[jj], dhi = P.range_hi[jj] - qj;
-      const float sig = dlo < 0.f ? 1.f : (dhi < 0.f ? -1.f : 0.f);
-      float lc = 0.f, lD = 0.f;
+      const real dlo = qj - P.range_lo[jj], dhi = P.range_hi[jj] - qj;
+      const real sig = dlo < 0.f ? 1.f : (dhi < 0.f ? -1.f : 0.f);
+      real lc = 0.f, lD = 0.f;
       if (sig != 0.f) {
-        const float dist = dlo < 0.f ? dlo : dhi;
-        const float imp = impedance_call(P.limit_imp, dist);
+        const real dist = dlo < 0.f ? dlo : dhi;
+        const real imp = impedance_call(P.limit_imp, dist);
         lc = sig * P.limit_B * qdj + P.limit_K * imp * dist;
-        lD = sig / fmaxf(1e-15f, (1.f - imp) * P.limit_invw[jj] / imp);
+        lD = sig / r_max(1e-15f, (1.f - imp) * P.limit_invw[jj] / imp);
       }
       sm.jf(j, F_LIMC) = lc; sm.jf(j, F_LIMD) = lD;
     }
-    float bl[6];
+    real bl[6];
     root_project_force(RB, fcn, fcl, bl);
 #pragma unroll
     for (int k = 0; k < 6; k++) fs_root[k] = -(fs_root[k] + pair_sum(bl[k])) - P.damping[k] * (k < 3 ? rv[k] : rw[k - 3]);
   }
-  float rfl_c[3];  // friction-loss row offsets of the root dofs 3*side..3*side+2 owned by this lane
+  real rfl_c[3];  // friction-loss row offsets of the root dofs 3*side..3*side+2 owned by this lane
 #pragma unroll
   for (int k = 0; k < 3; k++) rfl_c[k] = P.floss_B * (side == 0 ? rv[k] : rw[k]);
   // ---- contact candidates -> compact active list, ordered foot | shin | torso | pelvis (feet, shins about O_s; root about O_r).
   //      Slot 3..5 of a point holds the row residual e = J x + B*velocity at the current iterate x (x = 0 here). ----
   int n_foot = 0, e_shin = 0, e_torso = 0, nact = 0, overflow = 0;
   {
-    const float pz = rp[2];
-    const float mu2 = mu * mu;
+    const real pz = rp[2];
+    const real mu2 = mu * mu;
     const int ncand = side == 0 ? 11 : 10;
 #pragma unroll 1
     for (int p = 0; p < ncand; p++) {
       V3 lp, xb, omb, vob;
       M3 Rb;
-      float rad, href;
+      real rad, href;
       int slot;
       if (p < 4) { lp = ld3(LG.foot_pt[p]); Rb = Rfoot; xb = zero3; omb = om_foot; vob = vo_foot; rad = 0.f; slot = side; href = pz + d.z; }
       else if (p < 6) { lp = ld3(LG.shin_pt[p - 4]); Rb = Rshin; xb = xshin; omb = om_shin; vob = vo_shin; rad = LG.shin_rad; slot = 2 + side; href = pz + d.z; }
@@ -458,18 +464,18 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
         lp = ld3(P.root_pt[rpi]); Rb = R0; xb = zero3; omb = om0; vob = v0; rad = P.root_rad[rpi]; slot = p < 10 ? 4 : 5; href = pz;
       }
       const V3 c = xb + mulv(Rb, lp);
-      const float dist = href + c.z - rad;
+      const real dist = href + c.z - rad;
       if (dist < 0.f) {
         if (nact < MAXC) {
           const V3 rc = mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
           const V3 vel = vob + cross(omb, rc);
-          const float imp = impedance_call(P.contact_imp, dist);
-          const float tr = P.slot_tran[slot];
-          const float Rn = fmaxf(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);
+          const real imp = impedance_call(P.contact_imp, dist);
+          const real tr = P.slot_tran[slot];
+          const real Rn = r_max(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);
           sm.pf(nact, 0) = rc.x; sm.pf(nact, 1) = rc.y; sm.pf(nact, 2) = rc.z;
           sm.pf(nact, 3) = P.contact_B * vel.x; sm.pf(nact, 4) = P.contact_B * vel.y; sm.pf(nact, 5) = P.contact_B * vel.z;
           sm.pf(nact, 6) = P.contact_K * imp * dist;
-          sm.pf(nact, 7) = 1.f / fmaxf(1e-15f, 2.f * mu2 * Rn);
+          sm.pf(nact, 7) = 1.f / r_max(1e-15f, 2.f * mu2 * Rn);
           nact++;
           n_foot += p < 4; e_shin += p < 6; e_torso += p < 10;
         } else {
@@ -480,7 +486,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
   }
 
   // ---- iterate state: per-joint scalars live in the shared-memory column, root 6-vectors in registers ----
-  float xr[6], Mar[6], jr[6], rr[6], Msr[6];
+  real xr[6], Mar[6], jr[6], rr[6], Msr[6];
   V3 Wl_f = zero3, Wl_s = zero3, F_torso = zero3, F_pelvis = zero3;  // net contact forces per body at the last evaluation
   int it = 0, capped = 0;
 #pragma unroll
@@ -499,17 +505,17 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
 #pragma unroll 1
   for (int trip = 0;; trip++) {
     const bool first = trip == 0;
-    float dg_own[3] = {0.f, 0.f, 0.f};  // extra Hessian diagonal of this lane's three root rows
+    real dg_own[3] = {0.f, 0.f, 0.f};  // extra Hessian diagonal of this lane's three root rows
     bool final_trip = false;            // this trip's solve is the lane's implicitfast update
     if (!first) {
       // ---- evaluate all rows at x: forces and gradient ----
-      float gr_own[6];
+      real gr_own[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) gr_own[k] = 0.f;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const int dk = 3 * side + k;
-        const float f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss[dk], dg_own[k]);
+        const real f = floss_force((side == 0 ? xr[k] : xr[3 + k]) + rfl_c[k], P.floss_D[dk], P.floss[dk], dg_own[k]);
         if (side == 0) gr_own[k] = f; else gr_own[3 + k] = f;
       }
       V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
@@ -519,8 +525,8 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
         const V3 r = sm.pv(p, 0);
         const V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
         const V3 mom = cross(r, Fp);
-        const float isf = p < n_foot ? 1.f : 0.f, iss = (p >= n_foot && p < e_shin) ? 1.f : 0.f, isr = p >= e_shin ? 1.f : 0.f;
-        const float ist = (p >= e_shin && p < e_torso) ? 1.f : 0.f;
+        const real isf = p < n_foot ? 1.f : 0.f, iss = (p >= n_foot && p < e_shin) ? 1.f : 0.f, isr = p >= e_shin ? 1.f : 0.f;
+        const real ist = (p >= e_shin && p < e_torso) ? 1.f : 0.f;
         Wn_f = fma3(mom, isf, Wn_f); Wl_f = fma3(Fp, isf, Wl_f);
         Wn_s = fma3(mom, iss, Wn_s); Wl_s = fma3(Fp, iss, Wl_s);
         Wn_r = fma3(mom, isr, Wn_r); Wl_r = fma3(Fp, isr, Wl_r);
@@ -529,7 +535,7 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
       F_pelvis = Wl_r - F_torso;
       const V3 Wn_leg = Wn_f + Wn_s, Wl_leg = Wl_f + Wl_s;  // wrench of the leg contacts about O_s
       {
-        float t6[6];
+        real t6[6];
         root_project_force(RB, Wn_leg, Wl_leg, t6);
 #pragma unroll
         for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
@@ -537,30 +543,32 @@ __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, co
 #pragma unroll
         for (int k = 0; k < 6; k++) gr_own[k] += t6[k];
       }
-      float gn2 = 0.f;
+      real gn2 = 0.f, gv = 0.f;
 UNROLL(U_EVJ)
       for (int j = 0; j < 6; j++) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
-        const float x = sm.jf(j, F_XQ);
-        float act;
-        float f = floss_force(x + sm.jf(j, F_FLC), flD[j], flF[j], act);
-        const float lD = sm.jf(j, F_LIMD);
-        const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
-        const float jar = fmaf(sig, x, sm.jf(j, F_LIMC));
-        const float la = (sig != 0.f && jar < 0.f) ? fabsf(lD) : 0.f;
+        const real x = sm.jf(j, F_XQ);
+        real act;
+        real f = floss_force(x + sm.jf(j, F_FLC), flD[j], flF[j], act);
+        const real lD = sm.jf(j, F_LIMD);
+        const real sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
+        const real jar = r_fma(sig, x, sm.jf(j, F_LIMC));
+        const real la = (sig != 0.f && jar < 0.f) ? r_abs(lD) : 0.f;
         f += sig * (-la * jar);
         const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
-        const float g = f + ((j >= 4) ? dot(wj, Wn_f) + dot(uj, Wl_f) : dot(wj, Wn_leg) + dot(uj, Wl_leg));
-        const float r = g - sm.jf(j, F_MA);
+        const real g = f + ((j >= 4) ? dot(wj, Wn_f) + dot(uj, Wl_f) : dot(wj, Wn_leg) + dot(uj, Wl_leg));
+        const real r = g - sm.jf(j, F_MA);
         sm.jf(j, F_G) = g; sm.jf(j, F_R) = r; sm.jf(j, F_DG) = act + la;
-        gn2 = fmaf(r, r, gn2);
+        gn2 = r_fma(r, r, gn2);
+        gv = r_max(gv, r_abs(r) * P.limit_invw[j0 + j]);  // ~ |(M^-1 grad)_j|: what this residual does to the joint's acceleration
       }
       F_torso = pair_sum(F_torso);
       F_pelvis = pair_sum(F_pelvis);
       gn2 = pair_sum(gn2);
+      gv = r_max(gv, __shfl_xor_sync(FULL_MASK, gv, 1));
 #pragma unroll
-      for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k]); rr[k] = jr[k] - Mar[k]; gn2 = fmaf(rr[k], rr[k], gn2); }
+      for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k]); rr[k] = jr[k] - Mar[k]; gn2 = r_fma(rr[k], rr[k], gn2); }
       if (mode == MODE_NEWTON) {
-        const bool conv = sqrtf(gn2) * P.grad_scale < P.tol;
+        const bool conv = r_sqrt(gn2) * P.grad_scale < P.tol && gv < P.vel_tol;
         if (conv || it >= P.max_iters) { capped = !conv; mode = MODE_FINAL; }
         else it++;
       }
@@ -568,16 +576,28 @@ UNROLL(U_EVJ)
       final_trip = mode == MODE_FINAL;
       if (!newton) {
         // implicitfast: (M + h*diag(damping)) qacc = f_smooth + J'f   (a done lane repeats this harmlessly)
+#if H1V2_FINAL_MX
+        // ... with f_smooth + J'f taken as M x, what it equals at the minimiser (grad = M x - f_smooth - J'f = 0), instead of
+        // re-evaluated from the rows.  The two differ by the residual gradient g: the re-evaluated form returns x - M^-1 g, i.e.
+        // it hands g (in stiff contact directions mostly fp32 noise of D * J x, or what a dropped negligible Newton step left)
+        // to the acceleration through M^-1 -- 1e-3 rad/s per step on a loaded ankle (0.0136 kg m^2) -- while the iterate itself
+        // is off by H^-1 g only, H = M + J'DJ >> M exactly where g is large (profiles/r2_notes.md, tools/diag_fp64.py)
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * P.damping[6 + j0 + j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_MA); }
+#pragma unroll
+        for (int k = 0; k < 6; k++) rr[k] = fs_root[k] + Mar[k];
+#else
 #pragma unroll 1
         for (int j = 0; j < 6; j++) { sm.jf(j, F_DG) = h * P.damping[6 + j0 + j]; sm.jf(j, F_R) = sm.jf(j, F_FS) + sm.jf(j, F_G); }
 #pragma unroll
         for (int k = 0; k < 6; k++) rr[k] = fs_root[k] + jr[k];
+#endif
       }
       // ---- ABA sweep 1 (tip -> root): articulated inertia and reduced rhs ----
       K6 IA;
       k6_zero(IA);
       V3 pn = zero3, pl = zero3;
-      const float Dk = newton ? 1.f : 0.f;  // contact stiffness enters the Newton Hessian only
+      const real Dk = newton ? 1.f : 0.f;  // contact stiffness enters the Newton Hessian only
 UNROLL(U_SWEEP1)
       for (int j = 5; j >= 0; j--) {
         k6_add_rigid(IA, sm.ji(j, LG.mass[j]));
@@ -585,7 +605,7 @@ UNROLL(U_SWEEP1)
           const int p1 = j == 5 ? n_foot : e_shin;
 #pragma unroll 1
           for (int p = j == 5 ? 0 : n_foot; p < p1; p++) {
-            float Wp[5];
+            real Wp[5];
             point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
             k6_add_point(IA, sm.pv(p, 0), Wp);
           }
@@ -593,12 +613,12 @@ UNROLL(U_SWEEP1)
         const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
         V3 n, l;
         k6_apply(IA, wj, uj, n, l);
-        const float dinv = 1.f / (dot(wj, n) + dot(uj, l) + arm[j] + sm.jf(j, F_DG));
-        const float t = sm.jf(j, F_R) - (dot(wj, pn) + dot(uj, pl));
+        const real dinv = 1.f / (dot(wj, n) + dot(uj, l) + arm[j] + sm.jf(j, F_DG));
+        const real t = sm.jf(j, F_R) - (dot(wj, pn) + dot(uj, pl));
         sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
         sm.jf(j, F_DINV) = dinv; sm.jf(j, F_R) = t;
         k6_rank1_sub(IA, n, l, dinv);
-        const float td = t * dinv;
+        const real td = t * dinv;
         pn = fma3(n, td, pn); pl = fma3(l, td, pl);
       }
       // ---- root block: both legs' hand-offs moved to the pelvis origin + own link + root contact points; 6x6 Cholesky on both lanes ----
@@ -611,7 +631,7 @@ UNROLL(U_SWEEP1)
         k6_add_rigid(IA, Ih);
 #pragma unroll 1
         for (int p = e_shin; p < nact; p++) {
-          float Wp[5];
+          real Wp[5];
           point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
           k6_add_point(IA, sm.pv(p, 0), Wp);
         }
@@ -620,22 +640,22 @@ UNROLL(U_SWEEP1)
 #pragma unroll
         for (int i = 0; i < 9; i++) IA.al[i] = pair_sum(IA.al[i]);
         pn = pair_sum(pn); pl = pair_sum(pl);
-        float A[21], g[6];
+        real A[21], g[6];
 #pragma unroll
         for (int i = 0; i < 21; i++) A[i] = 0.f;
         root_project_k60(c3, IA, A);
         root_project_force0(c3, pn, pl, g);
         // diagonal: armature, friction-loss curvature of the root rows (Newton) or h*damping (implicit update)
-        const float o0 = newton ? dg_own[0] : 0.f, o1 = newton ? dg_own[1] : 0.f, o2 = newton ? dg_own[2] : 0.f;
-        const float e0 = pair_sum(side == 0 ? o0 : 0.f), e1 = pair_sum(side == 0 ? o1 : 0.f), e2 = pair_sum(side == 0 ? o2 : 0.f);
-        const float e3 = pair_sum(side == 0 ? 0.f : o0), e4 = pair_sum(side == 0 ? 0.f : o1), e5 = pair_sum(side == 0 ? 0.f : o2);
-        const float ex[6] = {e0, e1, e2, e3, e4, e5};
+        const real o0 = newton ? dg_own[0] : 0.f, o1 = newton ? dg_own[1] : 0.f, o2 = newton ? dg_own[2] : 0.f;
+        const real e0 = pair_sum(side == 0 ? o0 : 0.f), e1 = pair_sum(side == 0 ? o1 : 0.f), e2 = pair_sum(side == 0 ? o2 : 0.f);
+        const real e3 = pair_sum(side == 0 ? 0.f : o0), e4 = pair_sum(side == 0 ? 0.f : o1), e5 = pair_sum(side == 0 ? 0.f : o2);
+        const real ex[6] = {e0, e1, e2, e3, e4, e5};
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           A[TI(k, k)] += P.armature[k] + (newton ? ex[k] : h * P.damping[k]);
           rr[k] -= g[k];
         }
-        float inva[6];
+        real inva[6];
         chol6(A, inva);
         fwd6(A, inva, rr);
         bwd6(A, inva, rr);
@@ -648,41 +668,41 @@ UNROLL(U_SWEEP1)
     Sl_r = mk3(rr[0], rr[1], rr[2]);
     Sa_f = Sa_r; Sl_f = Sl_r + cross(Sa_r, d);
     Sa_s = Sa_f; Sl_s = Sl_f;
-    float smax = 0.f;
+    real smax = 0.f;
 UNROLL(U_SWEEP2)
     for (int j = 0; j < 6; j++) {
-      float s = sm.jf(j, F_R);
+      real s = sm.jf(j, F_R);
       if (!first) {
         s = (s - (dot(sm.jv(j, F_X), Sa_f) + dot(sm.jv(j, F_X + 3), Sl_f))) * sm.jf(j, F_DINV);
         sm.jf(j, F_R) = s;
       }
-      smax = fmaxf(smax, fabsf(s));
+      smax = r_max(smax, r_abs(s));
       Sa_f = fma3(sm.jv(j, F_W), s, Sa_f); Sl_f = fma3(sm.jv(j, F_U), s, Sl_f);
       if (j == 3) { Sa_s = Sa_f; Sl_s = Sl_f; }
       V3 n, l;
       ri_apply(sm.ji(j, LG.mass[j]), Sa_f, Sl_f, n, l);
       sm.sjv(j, F_X, n); sm.sjv(j, F_X + 3, l);
     }
-    smax = fmaxf(smax, __shfl_xor_sync(FULL_MASK, smax, 1));
+    smax = r_max(smax, __shfl_xor_sync(FULL_MASK, smax, 1));
 #pragma unroll
-    for (int i = 0; i < 6; i++) smax = fmaxf(smax, fabsf(rr[i]));
+    for (int i = 0; i < 6; i++) smax = r_max(smax, r_abs(rr[i]));
     // what this lane does with the direction: Newton step with line search | unit step (trip 0) | nothing.
     // A Newton step that no longer moves the acceleration is dropped and the iterate accepted (J'f is current).
     bool search = !first && mode == MODE_NEWTON;
     if (search && smax < P.step_tol) { search = false; mode = MODE_FINAL; }
     // ---- M-product, tip -> root half:  Ms = M s  (stored in the F_DG slot) ; line-search scalars ----
-    float sMs = 0.f, sMa = 0.f, gs = 0.f;
+    real sMs = 0.f, sMa = 0.f, gs = 0.f;
     {
       V3 fcn = zero3, fcl = zero3;
 UNROLL(U_MPROD)
       for (int j = 5; j >= 0; j--) {
         fcn = fcn + sm.jv(j, F_X); fcl = fcl + sm.jv(j, F_X + 3);
-        const float s = sm.jf(j, F_R);
-        const float ms = dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl) + arm[j] * s;
+        const real s = sm.jf(j, F_R);
+        const real ms = dot(sm.jv(j, F_W), fcn) + dot(sm.jv(j, F_U), fcl) + arm[j] * s;
         sm.jf(j, F_DG) = ms;
-        sMs = fmaf(s, ms, sMs); sMa = fmaf(s, sm.jf(j, F_MA), sMa); gs = fmaf(s, sm.jf(j, F_G), gs);
+        sMs = r_fma(s, ms, sMs); sMa = r_fma(s, sm.jf(j, F_MA), sMa); gs = r_fma(s, sm.jf(j, F_G), gs);
       }
-      float bl[6], b0[6];
+      real bl[6], b0[6];
       root_project_force(RB, fcn, fcl, bl);
       V3 n0, f0;
       ri_apply(I0, Sa_r, Sl_r, n0, f0);
@@ -690,38 +710,38 @@ UNROLL(U_MPROD)
 #pragma unroll
       for (int k = 0; k < 6; k++) Msr[k] = b0[k] + pair_sum(bl[k]) + P.armature[k] * rr[k];
     }
-    float alpha = first ? 1.f : 0.f;
+    real alpha = first ? 1.f : 0.f;
     {
       // ---- exact line search along the direction (all lanes run the trips; only searching lanes move alpha) ----
       sMs = pair_sum(sMs); sMa = pair_sum(sMa); gs = pair_sum(gs);
 #pragma unroll
-      for (int k = 0; k < 6; k++) { sMs = fmaf(rr[k], Msr[k], sMs); sMa = fmaf(rr[k], Mar[k], sMa); gs = fmaf(rr[k], jr[k], gs); }
-      const float d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
-      float lo = 0.f, hi = 1e30f, dlo = d10, dhi = 0.f;  // bracket of the minimiser and phi' at its ends
+      for (int k = 0; k < 6; k++) { sMs = r_fma(rr[k], Msr[k], sMs); sMa = r_fma(rr[k], Mar[k], sMa); gs = r_fma(rr[k], jr[k], gs); }
+      const real d10 = sMa - gs;  // phi'(0) = grad . search  (< 0)
+      real lo = 0.f, hi = 1e30f, dlo = d10, dhi = 0.f;  // bracket of the minimiser and phi' at its ends
       if (search) alpha = 1.f;
 #pragma unroll 1
       for (int ls = 0; __any_sync(FULL_MASK, search); ls++) {
-        float d1 = 0.f, d2 = 0.f;
+        real d1 = 0.f, d2 = 0.f;
 UNROLL(U_LSJ)
         for (int j = 0; j < 6; j++) {
-          const float s = sm.jf(j, F_R);
-          const float xa = fmaf(alpha, s, sm.jf(j, F_XQ));
-          float act;
-          const float f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flF[j], act);
-          d1 = fmaf(-f, s, d1); d2 = fmaf(act * s, s, d2);
-          const float lD = sm.jf(j, F_LIMD);  // limit row, branch-free: lD = 0 (no row) or an inactive row weigh nothing
-          const float sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
-          const float jar = fmaf(sig, xa, sm.jf(j, F_LIMC));
-          const float lw = jar < 0.f ? fabsf(lD) : 0.f;
-          d1 = fmaf(lw * jar, sig * s, d1); d2 = fmaf(lw * s, s, d2);
+          const real s = sm.jf(j, F_R);
+          const real xa = r_fma(alpha, s, sm.jf(j, F_XQ));
+          real act;
+          const real f = floss_force(xa + sm.jf(j, F_FLC), flD[j], flF[j], act);
+          d1 = r_fma(-f, s, d1); d2 = r_fma(act * s, s, d2);
+          const real lD = sm.jf(j, F_LIMD);  // limit row, branch-free: lD = 0 (no row) or an inactive row weigh nothing
+          const real sig = lD > 0.f ? 1.f : (lD < 0.f ? -1.f : 0.f);
+          const real jar = r_fma(sig, xa, sm.jf(j, F_LIMC));
+          const real lw = jar < 0.f ? r_abs(lD) : 0.f;
+          d1 = r_fma(lw * jar, sig * s, d1); d2 = r_fma(lw * s, s, d2);
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           const int dk = 3 * side + k;
-          const float sk = side == 0 ? rr[k] : rr[3 + k], xk = side == 0 ? xr[k] : xr[3 + k];
-          float act;
-          const float f = floss_force(fmaf(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss[dk], act);
-          d1 = fmaf(-f, sk, d1); d2 = fmaf(act * sk, sk, d2);
+          const real sk = side == 0 ? rr[k] : rr[3 + k], xk = side == 0 ? xr[k] : xr[3 + k];
+          real act;
+          const real f = floss_force(r_fma(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss[dk], act);
+          d1 = r_fma(-f, sk, d1); d2 = r_fma(act * sk, sk, d2);
         }
 #pragma unroll 1
         for (int p = 0; p < nact; p++) {
@@ -731,19 +751,19 @@ UNROLL(U_LSJ)
           const V3 us = Sl + cross(Sa, r);
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
-        d1 = pair_sum(d1) + fmaf(alpha, sMs, sMa);
+        d1 = pair_sum(d1) + r_fma(alpha, sMs, sMa);
         d2 = pair_sum(d2) + sMs;
         if (search) {
-          if (fabsf(d1) <= P.ls_tol * fabsf(d10) || !(d2 > 0.f)) search = false;
+          if (r_abs(d1) <= P.ls_tol * r_abs(d10) || !(d2 > 0.f)) search = false;
           else {
             if (d1 < 0.f) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
             if (ls + 1 >= P.ls_max) {  // out of trips: phi' is monotone, take the secant root inside the bracket (regula falsi)
               if (hi < 1e29f) alpha = lo + (hi - lo) * (-dlo / (dhi - dlo));
               search = false;
             } else {
-              float nx = alpha - d1 / d2;
+              real nx = alpha - d1 / d2;
               if (!(nx > lo && nx < hi)) nx = hi < 1e29f ? 0.5f * (lo + hi) : 2.f * alpha;
-              if (fabsf(nx - alpha) <= 1e-4f * alpha) search = false;
+              if (r_abs(nx - alpha) <= 1e-4f * alpha) search = false;
               alpha = nx;
             }
           }
@@ -755,16 +775,16 @@ UNROLL(U_LSJ)
     const bool move = alpha != 0.f;
 #pragma unroll 1
     for (int j = 0; j < 6; j++) {
-      const float s = sm.jf(j, F_R);
+      const real s = sm.jf(j, F_R);
       if (move) {
-        sm.jf(j, F_XQ) = fmaf(alpha, s, sm.jf(j, F_XQ));
-        sm.jf(j, F_MA) = fmaf(alpha, sm.jf(j, F_DG), sm.jf(j, F_MA));
+        sm.jf(j, F_XQ) = r_fma(alpha, s, sm.jf(j, F_XQ));
+        sm.jf(j, F_MA) = r_fma(alpha, sm.jf(j, F_DG), sm.jf(j, F_MA));
       }
       if (final_trip) sm.jf(j, F_FS) = s;
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      if (move) { xr[i] = fmaf(alpha, rr[i], xr[i]); Mar[i] = fmaf(alpha, Msr[i], Mar[i]); }
+      if (move) { xr[i] = r_fma(alpha, rr[i], xr[i]); Mar[i] = r_fma(alpha, Msr[i], Mar[i]); }
       if (final_trip) wr[i] = rr[i];
     }
     if (move) {
@@ -783,27 +803,27 @@ UNROLL(U_LSJ)
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const float a = sm.jf(j, F_FS);
+    const real a = sm.jf(j, F_FS);
     out.qacc[j] = a; wl[j] = a;
-    qd[j] = fmaf(h, a, qd[j]);
-    if (P.vel_limit > 0.f) qd[j] = fminf(fmaxf(qd[j], -P.vel_limit), P.vel_limit);  // actuator velocity_limit (A/robots/h12.py:66)
-    q[j] = fmaf(h, qd[j], q[j]);
+    qd[j] = r_fma(h, a, qd[j]);
+    if (P.vel_limit > 0.f) qd[j] = r_min(r_max(qd[j], -P.vel_limit), P.vel_limit);  // actuator velocity_limit (A/robots/h12.py:66)
+    q[j] = r_fma(h, qd[j], q[j]);
   }
 #pragma unroll
-  for (int k = 0; k < 3; k++) { rv[k] = fmaf(h, wr[k], rv[k]); rw[k] = fmaf(h, wr[3 + k], rw[k]); rp[k] = fmaf(h, rv[k], rp[k]); }
+  for (int k = 0; k < 3; k++) { rv[k] = r_fma(h, wr[k], rv[k]); rw[k] = r_fma(h, wr[3 + k], rw[k]); rp[k] = r_fma(h, rv[k], rp[k]); }
   {
-    float wn = sqrtf(rw[0] * rw[0] + rw[1] * rw[1] + rw[2] * rw[2]);
-    float ang = wn * h, dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
+    real wn = r_sqrt(rw[0] * rw[0] + rw[1] * rw[1] + rw[2] * rw[2]);
+    real ang = wn * h, dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
     if (ang > 0.f) {
-      float s, c;
+      real s, c;
       sincos_lim(0.5f * ang, s, c);
       s /= wn;
       dw = c; dx = rw[0] * s; dy = rw[1] * s; dz = rw[2] * s;
     }
-    float a = rq[0], b = rq[1], c = rq[2], e = rq[3];
-    float nw = a * dw - b * dx - c * dy - e * dz, nx = a * dx + b * dw + c * dz - e * dy;
-    float ny = a * dy - b * dz + c * dw + e * dx, nz = a * dz + b * dy - c * dx + e * dw;
-    float n = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+    real a = rq[0], b = rq[1], c = rq[2], e = rq[3];
+    real nw = a * dw - b * dx - c * dy - e * dz, nx = a * dx + b * dw + c * dz - e * dy;
+    real ny = a * dy - b * dz + c * dw + e * dx, nz = a * dz + b * dy - c * dx + e * dw;
+    real n = r_rsqrt(nw * nw + nx * nx + ny * ny + nz * nz);
     rq[0] = nw * n; rq[1] = nx * n; rq[2] = ny * n; rq[3] = nz * n;
   }
   out.F_foot = Wl_f; out.F_shin = Wl_s; out.F_torso = F_torso; out.F_pelvis = F_pelvis;

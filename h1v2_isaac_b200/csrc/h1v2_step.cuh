@@ -11,9 +11,9 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 struct RootDerived {
   M3 R;
   V3 vb, vw, wb, ww, g;  // vb / vw: velocity of the root link's COM (base / world frame), as isaaclab's root_lin_vel_b / _w
-  float hx, hy;  // forward axis of the base projected on the ground, unnormalised: heading = atan2(hy, hx)
+  real hx, hy;  // forward axis of the base projected on the ground, unnormalised: heading = atan2(hy, hx)
 };
-__device__ __forceinline__ RootDerived root_derived(const KParams& P, const float (&rq)[4], const float (&rv)[3], const float (&rw)[3]) {
+__device__ __forceinline__ RootDerived root_derived(const KParams& P, const real (&rq)[4], const real (&rv)[3], const real (&rw)[3]) {
   RootDerived d;
   d.R = quat2mat(rq[0], rq[1], rq[2], rq[3]);
   d.wb = mk3(rw[0], rw[1], rw[2]);
@@ -29,8 +29,8 @@ __device__ __forceinline__ RootDerived root_derived(const KParams& P, const floa
 // world linear velocity of the ankle_roll_link origin of this lane's leg (body_lin_vel_w of the foot, feet_slide).
 // Rolled over the joints with q / qd staged in the lane's shared-memory column: call it while the column is free
 // (after the physics loop, before the history prefetch).
-__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const float (&q)[6], const float (&qd)[6], bool at_com) {
-  extern __shared__ __align__(16) float smem_raw[];
+__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const real (&q)[6], const real (&qd)[6], bool at_com) {
+  extern __shared__ __align__(16) real smem_raw[];
   const Smem sm{smem_raw + tid};
 #pragma unroll
   for (int j = 0; j < 6; j++) { sm.jf(j, F_XQ) = q[j]; sm.jf(j, F_FLC) = qd[j]; }
@@ -39,12 +39,12 @@ __device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const 
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
     const int ax = joint_axis(i);
-    const float qdi = sm.jf(i, F_FLC);
+    const real qdi = sm.jf(i, F_FLC);
     x = x + mulv(R, ld3(LG.pos[i]));
     const V3 wi = axis_rt(R, ax);
     om = fma3(wi, qdi, om);
     vo = fma3(cross(x, wi), qdi, vo);
-    float s_, c_;
+    real s_, c_;
     sincos_lim(sm.jf(i, F_XQ), s_, c_);
     rotate_rt(R, ax, s_, c_);
   }
@@ -72,25 +72,25 @@ __device__ __forceinline__ void resample_command(const KParams& P, CmdState& c, 
 }
 
 // reset of one env (reset_root_state_uniform, reset_joints_by_scale, manager resets); both lanes compute the root
-__device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, float (&rp)[3],
-                                          float (&rq)[4], float (&rv)[3], float (&rw)[3], float (&q)[6], float (&qd)[6],
-                                          float (&la)[6], float (&T1)[6], float (&T2)[6], float4& timers, CmdState& cmd,
-                                          float& push_left) {
+__device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gid, unsigned long long step, real (&rp)[3],
+                                          real (&rq)[4], real (&rv)[3], real (&rw)[3], real (&q)[6], real (&qd)[6],
+                                          real (&la)[6], real (&T1)[6], real (&T2)[6], float4& timers, CmdState& cmd,
+                                          real& push_left) {
   float u0[4], u1[4], u2[4], u3[4];
   rng4(P.key0, gid, step, STREAM_RESET, 0, u0);
   rng4(P.key0, gid, step, STREAM_RESET, 1, u1);
   rng4(P.key0, gid, step, STREAM_RESET, 2, u2);
   rng4(P.key0, gid, step, STREAM_RESET, 3, u3);
-  int lag = P.min_delay + (int)(u1[2] * (float)(P.max_delay - P.min_delay + 1));
+  int lag = P.min_delay + (int)(u1[2] * (real)(P.max_delay - P.min_delay + 1));
   lag = min(lag, P.max_delay);
   cmd.flags = FLAG_DELAY_FRESH | FLAG_HIST_FRESH | (lag << FLAG_LAG_SHIFT);
   timers = make_float4(0.f, 0.f, 0.f, 0.f);
   rp[0] = uni(u0[0], P.rp[0][0], P.rp[0][1]);
   rp[1] = uni(u0[1], P.rp[1][0], P.rp[1][1]);
   rp[2] = P.init_h + uni(u0[3], P.rp[2][0], P.rp[2][1]);
-  float roll = uni(u1[0], P.rp[3][0], P.rp[3][1]), pitch = uni(u1[1], P.rp[4][0], P.rp[4][1]);
-  float yaw = uni(u0[2], P.rp[5][0], P.rp[5][1]);
-  float sr, cr, sp, cp, sy, cy;
+  real roll = uni(u1[0], P.rp[3][0], P.rp[3][1]), pitch = uni(u1[1], P.rp[4][0], P.rp[4][1]);
+  real yaw = uni(u0[2], P.rp[5][0], P.rp[5][1]);
+  real sr, cr, sp, cp, sy, cy;
   sincos_lim(0.5f * roll, sr, cr); sincos_lim(0.5f * pitch, sp, cp); sincos_lim(0.5f * yaw, sy, cy);
   rq[0] = cy * cr * cp + sy * sr * sp;
   rq[1] = cy * sr * cp - sy * cr * sp;
@@ -109,9 +109,9 @@ __device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gi
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int k = 2 * b + e, j = 6 * side + k;
-      float spos = uni(uj[2 * e], P.rjp[0], P.rjp[1]);
-      float qq = P.q0[j] * spos;
-      q[k] = fminf(fmaxf(qq, P.soft_lo[j]), P.soft_hi[j]);
+      real spos = uni(uj[2 * e], P.rjp[0], P.rjp[1]);
+      real qq = P.q0[j] * spos;
+      q[k] = r_min(r_max(qq, P.soft_lo[j]), P.soft_hi[j]);
       qd[k] = 0.f;
     }
   }
@@ -130,14 +130,14 @@ __device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gi
 // Returns true when the env ends the step inside the command dead zone (class 1 only; counted for the next step's balancing).
 __device__ __forceinline__ bool update_command(const KParams& P, CmdState& c, const RootDerived& rd, int64_t gid,
                                                unsigned long long step, unsigned dz_prev) {
-  float ex = c.c[0] - rd.vb.x, ey = c.c[1] - rd.vb.y;
-  c.m_xy += sqrtf(ex * ex + ey * ey) / P.max_command_step;
-  c.m_yaw += fabsf(c.c[2] - rd.wb.z) / P.max_command_step;
+  real ex = c.c[0] - rd.vb.x, ey = c.c[1] - rd.vb.y;
+  c.m_xy += r_sqrt(ex * ex + ey * ey) / P.max_command_step;
+  c.m_yaw += r_abs(c.c[2] - rd.wb.z) / P.max_command_step;
   c.time_left -= P.step_dt;
   if (c.time_left <= 0.0f) resample_command(P, c, gid, step, 2);
   if (P.heading_cmd && (c.flags & FLAG_HEADING)) {
-    float err = wrap_to_pi(c.heading_target - atan2f(rd.hy, rd.hx));
-    c.c[2] = fminf(fmaxf(P.k_heading * err, P.c_wz[0]), P.c_wz[1]);
+    real err = wrap_to_pi(c.heading_target - r_atan2(rd.hy, rd.hx));
+    c.c[2] = r_min(r_max(P.k_heading * err, P.c_wz[0]), P.c_wz[1]);
   }
   if (P.cmd_class == 0) {
     if (c.flags & FLAG_STANDING) c.c[0] = c.c[1] = c.c[2] = 0.f;
@@ -158,9 +158,9 @@ __device__ __forceinline__ bool update_command(const KParams& P, CmdState& c, co
   const float dz2 = __fmul_rn(P.deadzone, P.deadzone);
   bool in_dz = __fmaf_rn(c.c[1], c.c[1], __fmul_rn(c.c[0], c.c[0])) < dz2;
   if (cur < target) {
-    if (!in_dz && u[0] < __fdiv_rn((float)(target - cur), (float)(P.n - cur))) c.c[0] = c.c[1] = 0.f;
+    if (!in_dz && u[0] < __fdiv_rn((real)(target - cur), (real)(P.n - cur))) c.c[0] = c.c[1] = 0.f;
   } else if (cur > target) {
-    if (in_dz && u[0] < __fdiv_rn((float)(cur - target), (float)cur)) resample_command(P, c, gid, step, 6);
+    if (in_dz && u[0] < __fdiv_rn((real)(cur - target), (real)cur)) resample_command(P, c, gid, step, 6);
   }
   if (u[1] < P.flip_prob) c.c[2] = -c.c[2];
   return __fmaf_rn(c.c[1], c.c[1], __fmul_rn(c.c[0], c.c[0])) < dz2;
@@ -174,7 +174,7 @@ __device__ __forceinline__ bool update_command(const KParams& P, CmdState& c, co
 // loads the emission was 27 % of the step, 76 % of it long-scoreboard stalls).
 __device__ __forceinline__ int hist_envs_per_chunk(int H, int epw) { return min(epw, (SMEM_FLOATS * H1V2_BLOCK) / (H * H1V2_HIST_STRIDE)); }
 __device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S, unsigned tid, unsigned bid, int e0) {
-  extern __shared__ __align__(16) float smem_raw[];
+  extern __shared__ __align__(16) real smem_raw[];
   const int lane = tid & 31;
   const int warp_env0 = (int)bid * P.epw;
   const int ne = min(hist_envs_per_chunk(P.H, P.epw), min(P.epw, P.n - warp_env0) - e0);
@@ -190,13 +190,13 @@ __device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S,
 // observation sample of this step -> history ring slot `head`; then the warp cooperatively emits the flattened rows
 __device__ __forceinline__ void emit_observation(const KParams& P, const KState& S, unsigned tid, unsigned bid, int env, int side, bool valid, int64_t gid,
                                                  unsigned long long step, int head, const RootDerived& rd, const CmdState& cmd,
-                                                 const float (&q)[6], const float (&qd)[6], const float (&la)[6], float* obs) {
-  extern __shared__ __align__(16) float smem_raw[];
+                                                 const real (&q)[6], const real (&qd)[6], const real (&la)[6], float* obs) {
+  extern __shared__ __align__(16) real smem_raw[];
   const int H = P.H;
   // ---- the sample: 18 values of this lane's leg, 9 root values on the env's first lane (noise: V/velocity_env_cfg.py:124-131) ----
-  float sv[18], s9[9];
+  real sv[18], s9[9];
   {
-    float nq[6] = {0, 0, 0, 0, 0, 0}, nv[6] = {0, 0, 0, 0, 0, 0};
+    real nq[6] = {0, 0, 0, 0, 0, 0}, nv[6] = {0, 0, 0, 0, 0, 0};
     if (P.corrupt) {
       float a[4], b[4], d[4];
       rng4(P.key0, gid, step, STREAM_OBS, 2 + 4 * side, a);
@@ -214,7 +214,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
       sv[6 + k] = (qd[k] + nv[k]) * P.s_v;
       sv[12 + k] = la[k] * P.s_a;
     }
-    float n0[3] = {0, 0, 0}, n1[3] = {0, 0, 0};
+    real n0[3] = {0, 0, 0}, n1[3] = {0, 0, 0};
     if (P.corrupt && side == 0) {
       float b0[4], b1[4];
       rng4(P.key0, gid, step, STREAM_OBS, 0, b0);
@@ -266,7 +266,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (my_e >= e0 && my_e < e0 + epc) {  // the new sample replaces the stale slot `head` of this env's copy
-      float* sl = smem_raw + (my_e - e0) * ring + head * H1V2_HIST_STRIDE;
+      float* sl = reinterpret_cast<float*>(smem_raw) + (my_e - e0) * ring + head * H1V2_HIST_STRIDE;
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const int i = P.inv_perm[6 * side + k];
@@ -283,7 +283,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     for (int e = e0; e < e1; e++) {
       const int env_e = warp_env0 + e;
       const bool fresh = (__shfl_sync(0xffffffffu, cmd.flags, 2 * e) & FLAG_HIST_FRESH) != 0;  // warp-uniform
-      const float* hsm = smem_raw + (e - e0) * ring;
+      const float* hsm = reinterpret_cast<const float*>(smem_raw) + (e - e0) * ring;
       float* orow = obs + (size_t)env_e * P.obs_dim + lane;
       const int sh = fresh ? 16 : 0;
 #pragma unroll
@@ -306,11 +306,11 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
 // Run by the 32 lanes of the LAST block of a step launch to finish (ticket counter S.done): one launch per control step.
 __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, unsigned t) {
   if (do_step) {
-    const float cnt = __ldcg(S.acc + H1V2_LOG_COUNT);
-    const float a = __ldcg(S.acc + t);  // t < 32 == H1V2_LOG_DIM
+    const real cnt = __ldcg(S.acc + H1V2_LOG_COUNT);
+    const real a = __ldcg(S.acc + t);  // t < 32 == H1V2_LOG_DIM
     if (t == H1V2_LOG_COUNT) S.log[t] = a;
     else if (t == H1V2_LOG_NAN_RESETS) S.log[t] += a;
-    else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (float)__float_as_int(a);
+    else if (t == H1V2_LOG_MAX_ITERS) S.log[t] = (real)__float_as_int(a);
     else if (t == H1V2_LOG_CAP_HITS || t == H1V2_LOG_SUM_ITERS || t == H1V2_LOG_CONTACT_OVERFLOW) S.log[t] = a;
     else if (cnt > 0.f) {
       const bool mean = (t >= H1V2_LOG_REW0 && t < H1V2_LOG_REW0 + H1V2_NUM_REW) || t == H1V2_LOG_ERR_XY || t == H1V2_LOG_ERR_YAW;
@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 
   // ---- load the physics state (coalesced 128-bit).  The actuator line and the command state are read AFTER the
   //      physics loop: whatever is live across substep() costs registers inside the Newton iteration. ----
-  float rp[3], rq[4], rv[3], rw[3], q[6], qd[6];
-  float mu, mass_add, push_left;
+  real rp[3], rq[4], rv[3], rw[3], q[6], qd[6];
+  real mu, mass_add, push_left;
   int flags0;
   {
     float4 r0 = S.root[env], r1 = S.root[N + env], r2 = S.root[2 * N + env], r3 = S.root[3 * N + env];
@@ -375,16 +375,16 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     asm volatile("prefetch.global.L1 [%0];" ::"l"(S.act + 4 * N2 + lidx));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)env * 12 + 6 * side));
   }
-  float wl[6], wr[6];
+  real wl[6], wr[6];
   {
     float4 w0 = S.warm[lidx], w1 = S.warm[N2 + lidx], w2 = S.warm[2 * N2 + lidx];
     wl[0] = w0.x; wl[1] = w0.y; wl[2] = w0.z; wl[3] = w0.w; wl[4] = w1.x; wl[5] = w1.y;
     wr[0] = w1.z; wr[1] = w1.w; wr[2] = w2.x; wr[3] = w2.y; wr[4] = w2.z; wr[5] = w2.w;
   }
-  float la[6], T1[6], T2[6];
+  real la[6], T1[6], T2[6];
   CmdState cmd;
-  float h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
-  float s_tau = 0.f, s_acc = 0.f;
+  real h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
+  real s_tau = 0.f, s_acc = 0.f;
   SubOut so;
   int max_it = 0, ncap = 0, sum_it = 0, novf = 0;
 
@@ -398,12 +398,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll 1
     for (int k = 0; k < P.decimation; k++) {
       const int age = lag - k;
-      float tau[6];
+      real tau[6];
       {
-        float T[6];
+        real T[6];
         if (age <= 0 || line_fresh) {
 #pragma unroll
-          for (int i = 0; i < 6; i++) T[i] = fmaf(P.action_scale, __ldg(actions + (size_t)env * 12 + P.inv_perm[6 * side + i]), P.q0[6 * side + i]);
+          for (int i = 0; i < 6; i++) T[i] = r_fma(P.action_scale, __ldg(actions + (size_t)env * 12 + P.inv_perm[6 * side + i]), P.q0[6 * side + i]);
         } else if (age <= P.decimation) {
           const float4 a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx];
           T[0] = a1.z; T[1] = a1.w; T[2] = a2.x; T[3] = a2.y; T[4] = a2.z; T[5] = a2.w;
@@ -415,9 +415,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 6; i++) {
           const int j = 6 * side + i;
-          const float t = P.kp[j] * (T[i] - q[i]) + P.kd[j] * (0.f - qd[i]);
-          tau[i] = fminf(fmaxf(t, -P.effort[j]), P.effort[j]);
-          if ((P.m_tau >> j) & 1u) s_tau = fmaf(tau[i], tau[i], s_tau);
+          const real t = P.kp[j] * (T[i] - q[i]) + P.kd[j] * (0.f - qd[i]);
+          tau[i] = r_min(r_max(t, -P.effort[j]), P.effort[j]);
+          if ((P.m_tau >> j) & 1u) s_tau = r_fma(tau[i], tau[i], s_tau);
         }
         if (S.diag && valid) {
           float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
@@ -428,22 +428,22 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters; novf += so.overflow;
-      if (valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);
+      if (S.diag && valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);  // iteration histogram: diagnostics handles only
       s_acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 6; i++) s_acc = fmaf(so.qacc[i], so.qacc[i], s_acc);
+      for (int i = 0; i < 6; i++) s_acc = r_fma(so.qacc[i], so.qacc[i], s_acc);
       if (S.diag && valid) {
         float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
 #pragma unroll
         for (int i = 0; i < 6; i++) dg[48 + 6 * side + i] = so.qacc[i];
       }
-      float nf = sqrtf(dot(so.F_foot, so.F_foot));
+      real nf = r_sqrt(dot(so.F_foot, so.F_foot));
       h_foot[0] = h_foot[1]; h_foot[1] = h_foot[2]; h_foot[2] = nf;
-      h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = sqrtf(dot(so.F_shin, so.F_shin));
-      h_torso[0] = h_torso[1]; h_torso[1] = h_torso[2]; h_torso[2] = sqrtf(dot(so.F_torso, so.F_torso));
-      h_pelvis[0] = h_pelvis[1]; h_pelvis[1] = h_pelvis[2]; h_pelvis[2] = sqrtf(dot(so.F_pelvis, so.F_pelvis));
+      h_shin[0] = h_shin[1]; h_shin[1] = h_shin[2]; h_shin[2] = r_sqrt(dot(so.F_shin, so.F_shin));
+      h_torso[0] = h_torso[1]; h_torso[1] = h_torso[2]; h_torso[2] = r_sqrt(dot(so.F_torso, so.F_torso));
+      h_pelvis[0] = h_pelvis[1]; h_pelvis[1] = h_pelvis[2]; h_pelvis[2] = r_sqrt(dot(so.F_pelvis, so.F_pelvis));
       {  // air / contact timers of the lane's foot (ContactSensor)
-        const float el = P.h;
+        const real el = P.h;
         const bool is_c = nf > P.contact_thr;
         const bool first_c = (tm.x > 0.f) && is_c, first_d = (tm.z > 0.f) && !is_c;
         tm.y = first_c ? tm.x + el : tm.y;
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   }
   if (DO_STEP) {
     // action manager bookkeeping: prev_action <- action ; action <- a ; shift the delay line
-    float prev[6];
+    real prev[6];
     {
       const bool line_fresh = (cmd.flags & FLAG_DELAY_FRESH) != 0;
 #pragma unroll
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         const int j = 6 * side + k;
         prev[k] = la[k];
         la[k] = __ldg(actions + (size_t)env * 12 + P.inv_perm[j]);
-        const float T0 = fmaf(P.action_scale, la[k], P.q0[j]);
+        const real T0 = r_fma(P.action_scale, la[k], P.q0[j]);
         T2[k] = line_fresh ? T0 : T1[k];
         T1[k] = T0;
       }
@@ -490,19 +490,19 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     // ---- non-finite / runaway guard ----
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !(fabsf(qd[k]) <= P.runaway_vel) || !(fabsf(la[k]) <= H1V2_ACTION_ABS_MAX);
+    for (int k = 0; k < 6; k++) bad |= !isfinite(q[k]) || !(r_abs(qd[k]) <= P.runaway_vel) || !(r_abs(la[k]) <= H1V2_ACTION_ABS_MAX);
 #pragma unroll
-    for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !(fabsf(rv[k]) <= P.runaway_vel) || !(fabsf(rw[k]) <= P.runaway_vel);
+    for (int k = 0; k < 3; k++) bad |= !isfinite(rp[k]) || !(r_abs(rv[k]) <= P.runaway_vel) || !(r_abs(rw[k]) <= P.runaway_vel);
     bad |= !isfinite(rq[0]) || !isfinite(rq[1]) || !isfinite(rq[2]) || !isfinite(rq[3]);
     bad = (__shfl_xor_sync(FULL_MASK, (int)bad, 1) | (int)bad) != 0;
 
     // ---- counters and terminations (C12/rough_env_cfg.py:95-109) ----
     int64_t ep_len = S.ep_len[env] + 1;
     const bool time_out = ep_len >= P.max_episode_length;
-    const float C_foot = fmaxf(h_foot[0], fmaxf(h_foot[1], h_foot[2]));
-    const float C_shin = fmaxf(h_shin[0], fmaxf(h_shin[1], h_shin[2]));
-    const float C_torso = fmaxf(h_torso[0], fmaxf(h_torso[1], h_torso[2]));
-    const float C_pelvis = fmaxf(h_pelvis[0], fmaxf(h_pelvis[1], h_pelvis[2]));
+    const real C_foot = r_max(h_foot[0], r_max(h_foot[1], h_foot[2]));
+    const real C_shin = r_max(h_shin[0], r_max(h_shin[1], h_shin[2]));
+    const real C_torso = r_max(h_torso[0], r_max(h_torso[1], h_torso[2]));
+    const real C_pelvis = r_max(h_pelvis[0], r_max(h_pelvis[1], h_pelvis[2]));
     int contact = (((P.m_illegal >> side) & 1u) && C_foot > P.contact_thr) || (((P.m_illegal >> (2 + side)) & 1u) && C_shin > P.contact_thr) ||
                   (((P.m_illegal >> 4) & 1u) && C_torso > P.contact_thr) || (((P.m_illegal >> 5) & 1u) && C_pelvis > P.contact_thr);
     contact = (__shfl_xor_sync(FULL_MASK, contact, 1) | contact) | (int)bad;
@@ -510,22 +510,22 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 
     // ---- rewards on the pre-reset state ----
     const RootDerived rd = root_derived(P, rq, rv, rw);
-    float r[H1V2_NUM_REW];
+    real r[H1V2_NUM_REW];
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) r[t] = 0.f;
     {
-      float s_lim = 0.f, s_dev = 0.f, s_lim_b = 0.f, s_dev_b = 0.f, s_vel = 0.f, s_da = 0.f;
+      real s_lim = 0.f, s_dev = 0.f, s_lim_b = 0.f, s_dev_b = 0.f, s_vel = 0.f, s_da = 0.f;
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const int j = 6 * side + k;
-        const float lim = -fminf(q[k] - P.soft_lo[j], 0.f) + fmaxf(q[k] - P.soft_hi[j], 0.f), dev = fabsf(q[k] - P.q0[j]);
+        const real lim = -r_min(q[k] - P.soft_lo[j], 0.f) + r_max(q[k] - P.soft_hi[j], 0.f), dev = r_abs(q[k] - P.q0[j]);
         if ((P.m_poslim >> j) & 1u) s_lim += lim;
         if ((P.m_dev >> j) & 1u) s_dev += dev;
         if ((P.m_poslim_b >> j) & 1u) s_lim_b += lim;
         if ((P.m_dev_b >> j) & 1u) s_dev_b += dev;
-        s_vel = fmaf(qd[k], qd[k], s_vel);
-        float da = la[k] - prev[k];
-        s_da = fmaf(da, da, s_da);
+        s_vel = r_fma(qd[k], qd[k], s_vel);
+        real da = la[k] - prev[k];
+        s_da = r_fma(da, da, s_da);
       }
       r[H1V2_REW_DOF_POS_LIMITS] = pair_sum(s_lim);
       r[H1V2_REW_JOINT_DEV_HIP] = pair_sum(s_dev);
@@ -536,64 +536,64 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       r[H1V2_REW_JOINT_VEL] = pair_sum(s_vel);
       r[H1V2_REW_ACTION_RATE] = pair_sum(s_da);
       r[H1V2_REW_TERMINATION] = contact ? 1.f : 0.f;
-      const float hn = rsqrtf(fmaxf(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));  // cos / sin of the heading without the angle itself
-      const float ch = rd.hx * hn, sh = rd.hy * hn;
-      float ex = cmd.c[0] - (ch * rd.vw.x + sh * rd.vw.y), ey = cmd.c[1] - (-sh * rd.vw.x + ch * rd.vw.y);
-      r[H1V2_REW_TRACK_LIN_XY_YAW] = expf(-(ex * ex + ey * ey) * P.inv_std2);
-      float ez = cmd.c[2] - rd.ww.z;
-      r[H1V2_REW_TRACK_ANG_Z_WORLD] = expf(-(ez * ez) * P.inv_std2);
+      const real hn = r_rsqrt(r_max(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));  // cos / sin of the heading without the angle itself
+      const real ch = rd.hx * hn, sh = rd.hy * hn;
+      real ex = cmd.c[0] - (ch * rd.vw.x + sh * rd.vw.y), ey = cmd.c[1] - (-sh * rd.vw.x + ch * rd.vw.y);
+      r[H1V2_REW_TRACK_LIN_XY_YAW] = r_exp(-(ex * ex + ey * ey) * P.inv_std2);
+      real ez = cmd.c[2] - rd.ww.z;
+      r[H1V2_REW_TRACK_ANG_Z_WORLD] = r_exp(-(ez * ez) * P.inv_std2);
       ex = cmd.c[0] - rd.vb.x; ey = cmd.c[1] - rd.vb.y;
-      r[H1V2_REW_TRACK_LIN_XY_BASE] = expf(-(ex * ex + ey * ey) * P.inv_std2);
+      r[H1V2_REW_TRACK_LIN_XY_BASE] = r_exp(-(ex * ex + ey * ey) * P.inv_std2);
       ez = cmd.c[2] - rd.wb.z;
-      r[H1V2_REW_TRACK_ANG_Z_BASE] = expf(-(ez * ez) * P.inv_std2);
-      const bool moving = sqrtf(cmd.c[0] * cmd.c[0] + cmd.c[1] * cmd.c[1]) > 0.1f;
+      r[H1V2_REW_TRACK_ANG_Z_BASE] = r_exp(-(ez * ez) * P.inv_std2);
+      const bool moving = r_sqrt(cmd.c[0] * cmd.c[0] + cmd.c[1] * cmd.c[1]) > 0.1f;
       // feet_air_time_positive_biped (V/mdp/rewards.py:38-62) and feet_air_time (:13-35)
       const int inc = tm.z > 0.f;
-      const float mode_t = inc ? tm.z : tm.x;
+      const real mode_t = inc ? tm.z : tm.x;
       const int inc_p = __shfl_xor_sync(FULL_MASK, inc, 1);
-      const float mode_p = __shfl_xor_sync(FULL_MASK, mode_t, 1);
+      const real mode_p = __shfl_xor_sync(FULL_MASK, mode_t, 1);
       const bool single = (inc + inc_p) == 1;
-      float mn = fminf(single ? mode_t : 0.f, single ? mode_p : 0.f);
-      mn = fminf(mn, P.air_thr);
+      real mn = r_min(single ? mode_t : 0.f, single ? mode_p : 0.f);
+      mn = r_min(mn, P.air_thr);
       r[H1V2_REW_FEET_AIR_BIPED] = moving ? mn : 0.f;
       const bool first = (tm.z > 0.f) && (tm.z < P.step_dt + 1e-8f);
-      float l2 = first ? (tm.y - P.air_thr) : 0.f;
+      real l2 = first ? (tm.y - P.air_thr) : 0.f;
       l2 = pair_sum(l2);
       r[H1V2_REW_FEET_AIR_L2] = moving ? l2 : 0.f;
-      float slide = (C_foot > P.contact_thr) ? sqrtf(fv.x * fv.x + fv.y * fv.y) : 0.f;
+      real slide = (C_foot > P.contact_thr) ? r_sqrt(fv.x * fv.x + fv.y * fv.y) : 0.f;
       r[H1V2_REW_FEET_SLIDE] = pair_sum(slide);
       r[H1V2_REW_ANG_VEL_XY] = rd.wb.x * rd.wb.x + rd.wb.y * rd.wb.y;
       r[H1V2_REW_FLAT_ORI] = rd.g.x * rd.g.x + rd.g.y * rd.g.y;
       r[H1V2_REW_LIN_VEL_Z] = rd.vb.z * rd.vb.z;
       r[H1V2_REW_BASE_HEIGHT] = (rp[2] - P.base_h) * (rp[2] - P.base_h);
-      float und = 0.f, cf = 0.f;
+      real und = 0.f, cf = 0.f;
       // undesired_contacts counts bodies above the sensor threshold; contact_forces (C12/rsl_env_cfg.py:395-404) sums the
       // excess of max_h |F| over its own threshold on its own bodies
       if ((P.m_undesired >> side) & 1u) und += C_foot > P.contact_thr;
       if ((P.m_undesired >> (2 + side)) & 1u) und += C_shin > P.contact_thr;
-      if ((P.m_cforce >> side) & 1u) cf += fmaxf(C_foot - P.cforce_thr, 0.f);
-      if ((P.m_cforce >> (2 + side)) & 1u) cf += fmaxf(C_shin - P.cforce_thr, 0.f);
+      if ((P.m_cforce >> side) & 1u) cf += r_max(C_foot - P.cforce_thr, 0.f);
+      if ((P.m_cforce >> (2 + side)) & 1u) cf += r_max(C_shin - P.cforce_thr, 0.f);
       if (side == 0) {
         if ((P.m_undesired >> 4) & 1u) und += C_torso > P.contact_thr;
         if ((P.m_undesired >> 5) & 1u) und += C_pelvis > P.contact_thr;
-        if ((P.m_cforce >> 4) & 1u) cf += fmaxf(C_torso - P.cforce_thr, 0.f);
-        if ((P.m_cforce >> 5) & 1u) cf += fmaxf(C_pelvis - P.cforce_thr, 0.f);
+        if ((P.m_cforce >> 4) & 1u) cf += r_max(C_torso - P.cforce_thr, 0.f);
+        if ((P.m_cforce >> 5) & 1u) cf += r_max(C_pelvis - P.cforce_thr, 0.f);
       }
       r[H1V2_REW_UNDESIRED_CONTACTS] = pair_sum(und);
       r[H1V2_REW_CONTACT_FORCES] = pair_sum(cf);
     }
-    float total = 0.f;
+    real total = 0.f;
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_REW; t++) {
-      float v = (P.w[t] == 0.f || bad) ? 0.f : P.w[t] * r[t] * P.step_dt;
+      real v = (P.w[t] == 0.f || bad) ? 0.f : P.w[t] * r[t] * P.step_dt;
       r[t] = v;
       total += v;
     }
     // episode sums: lane 0 owns float4 0..2 (terms 0..11), lane 1 owns float4 3..5 (terms 12..21 and two pads)
-    float es[12];
+    real es[12];
     const int ef0 = side == 0 ? 0 : 3, enf4 = 3;
     {
-      float rsel[12];
+      real rsel[12];
 #pragma unroll
       for (int i = 0; i < 12; i++) rsel[i] = side == 0 ? r[i] : (12 + i < H1V2_NUM_REW ? r[12 + i < H1V2_NUM_REW ? 12 + i : 0] : 0.f);
 #pragma unroll
@@ -630,10 +630,10 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         for (int i = 0; i < 3; i++) { dg[30 + i] = h_torso[i]; dg[33 + i] = h_pelvis[i]; }
 #pragma unroll
         for (int t = 0; t < H1V2_NUM_REW; t++) dg[H1V2_DIAG_REW0 + t] = r[t];
-        dg[86] = (float)max_it; dg[87] = (float)ncap; dg[88] = (float)sum_it;
+        dg[86] = (real)max_it; dg[87] = (real)ncap; dg[88] = (real)sum_it;
         // for the Constraints-as-Terminations tail: the command the mdp terms of this step read (before its update), the episode length
         dg[141] = cmd.c[0]; dg[142] = cmd.c[1]; dg[143] = cmd.c[2];
-        dg[166] = (float)ep_len; dg[167] = reset ? 1.f : 0.f;
+        dg[166] = (real)ep_len; dg[167] = reset ? 1.f : 0.f;
       }
     }
     // solver statistics
@@ -644,15 +644,15 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       int wo = __reduce_add_sync(0xffffffffu, valid ? novf : 0);  // per leg: each lane owns its own contact list
       if ((tid & 31) == 0) {
         atomicMax((int*)(S.acc + H1V2_LOG_MAX_ITERS), wm);
-        if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (float)wc);
-        atomicAdd(S.acc + H1V2_LOG_SUM_ITERS, (float)ws);
-        if (wo) atomicAdd(S.acc + H1V2_LOG_CONTACT_OVERFLOW, (float)wo);
+        if (wc) atomicAdd(S.acc + H1V2_LOG_CAP_HITS, (real)wc);
+        atomicAdd(S.acc + H1V2_LOG_SUM_ITERS, (real)ws);
+        if (wo) atomicAdd(S.acc + H1V2_LOG_CONTACT_OVERFLOW, (real)wo);
       }
     }
     // ---- reset (T/utils/cat/cat_env.py:195-248): log, then new state ----
     if (reset) {
       if (valid) {
-        const float inv = 1.f / P.max_episode_length_s;
+        const real inv = 1.f / P.max_episode_length_s;
         const int f0 = side == 0 ? 0 : 12, cnt = side == 0 ? 12 : H1V2_NUM_REW - 12;
 #pragma unroll
         for (int i = 0; i < 12; i++)

@@ -347,12 +347,18 @@ class OnPolicyRunner:
         stats = {"iteration": it, "fps": fps, "collection_time": collection_time, "learn_time": learn_time, **{f"loss/{k}": v for k, v in loss.items()},
                  "mean_noise_std": self.alg.policy.action_std.mean().item() if self.alg.policy.distribution is not None else float("nan"),
                  "lr": self.alg.lr}
-        if len(rewbuffer) > 0:
-            mr, ml = statistics.mean(rewbuffer), statistics.mean(lenbuffer)
-            if self.is_distributed:  # rollout statistics reduced over ranks once per iteration (north star)
-                t = torch.tensor([mr, ml, 1.0], device=self.device)
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        have = len(rewbuffer) > 0
+        mr, ml = (statistics.mean(rewbuffer), statistics.mean(lenbuffer)) if have else (0.0, 0.0)
+        if self.is_distributed:
+            # rollout statistics reduced over ranks once per iteration (north star).  EVERY rank takes part, whether or not an
+            # episode has finished on it yet: a rank with an empty buffer contributes zeros with weight 0 (a collective inside
+            # `if len(rewbuffer) > 0` would pair with the next collective of a rank that skipped it)
+            t = torch.tensor([mr, ml, 1.0] if have else [0.0, 0.0, 0.0], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            have = float(t[2]) > 0
+            if have:
                 mr, ml = (t[0] / t[2]).item(), (t[1] / t[2]).item()
+        if have:
             stats["mean_reward"], stats["mean_episode_length"] = mr, ml
         ep = {}
         if ep_infos:

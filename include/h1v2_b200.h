@@ -209,7 +209,11 @@ typedef struct H1v2Config {
   float cat_clearance_min_height, cat_clearance_deadzone; /* 0.1 m, 0.2 */
   float runaway_vel;                   /* an env whose root speed (m/s, rad/s) or joint speed exceeds this is treated like a
                                           non-finite one: zero reward, terminated, reset (PhysX caps at 1000, h12.py:27-28) */
-  int32_t reserved[8];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
+  float solver_vel_tolerance;          /* second convergence test of the Newton solver, rad/s (0 = off): h * max_j |grad_j| * invweight0_j, the joint-velocity
+                                          error a residual gradient leaves after the implicit update.  MuJoCo's own test (solver_tolerance, on
+                                          the gradient norm scaled by meaninertia * nv = 234) lets 2.3e-3 N m pass on an ankle of 0.0136 kg m^2:
+                                          8.5e-4 rad/s, the whole single-step tolerance of the north star (profiles/r2_notes.md) */
+  int32_t reserved[7];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
                                           [1] > 0: line-search evaluations per Newton iteration (default 6);
                                           [2] in {1,2,4,8,16}: envs per warp (default: chosen from n_envs); rest 0 */
 } H1v2Config;

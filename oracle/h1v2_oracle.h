@@ -27,6 +27,7 @@ int h1v2o_set_state(H1v2Oracle* o, const H1v2State* s);
 int h1v2o_get_episode_length(H1v2Oracle* o, int64_t* out);
 int h1v2o_set_episode_length(H1v2Oracle* o, const int64_t* in);
 int h1v2o_get_log(H1v2Oracle* o, float* out);
+int h1v2o_set_reward_weights(H1v2Oracle* o, const float* w);
 int h1v2o_solver_stats(H1v2Oracle* o, int32_t* iters, double* resid);
 int h1v2o_activation_margin(H1v2Oracle* o, double* contact, double* limit);
 

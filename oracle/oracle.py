@@ -20,9 +20,14 @@ _SO = os.path.join(_DIR, "_build", "libh1v2_oracle.so")
 _lib = None
 
 
+_SO_COUNTED = os.path.join(_DIR, "_build", "libh1v2_oracle_counted.so")
+_SRCS = [os.path.join(_DIR, "h1v2_oracle.c"), os.path.join(_DIR, "h1v2_oracle.h"), os.path.join(_DIR, "flopcount", "counted_double.h"),
+         os.path.join(_DIR, "..", "h1v2_isaac_b200", "csrc", "h1v2_config.cpp"), os.path.join(_DIR, "..", "include", "h1v2_b200.h")]
+
+
 def build(force: bool = False) -> str:
-    src = os.path.join(_DIR, "h1v2_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(f) for f in _SRCS if os.path.exists(f))
+    if force or not os.path.exists(_SO) or not os.path.exists(_SO_COUNTED) or min(os.path.getmtime(_SO), os.path.getmtime(_SO_COUNTED)) < newest:
         subprocess.check_call(["make", "-C", _DIR, "--quiet"])
     return _SO
 
@@ -62,8 +67,53 @@ def lib() -> C.CDLL:
         L.h1v2o_total_energy.restype = C.c_double
         L.h1v2o_wrap_to_pi.argtypes = [C.c_float]
         L.h1v2o_wrap_to_pi.restype = C.c_float
+        for f in ("h1v2_default_config", "h1v2_rsl_config", "h1v2_cat_config"):  # the oracle library's own copy (h1v2_config.cpp, host only)
+            getattr(L, f).argtypes = [C.POINTER(H1v2Config)]
         _lib = L
     return _lib
+
+
+def task_config(task: str = "flat") -> H1v2Config:
+    """Resolved cfg of the Flat / Rsl / CaT id from the ORACLE library (so that the reference arm of bench.py and the CPU tests
+    never load the CUDA library)."""
+    cfg = H1v2Config()
+    rc = getattr(lib(), {"flat": "h1v2_default_config", "rsl": "h1v2_rsl_config", "cat": "h1v2_cat_config"}[task])(C.byref(cfg))
+    assert rc == 0
+    return cfg
+
+
+def count_flops(cfg: H1v2Config, n_envs: int, steps: int, actions=None, settle: int = 0, seed: int = 3) -> dict:
+    """Exact double-precision operation counts of the oracle per env-step (the binding FLOP figure of the FP32
+    roofline).  Runs libh1v2_oracle_counted.so -- this file's source compiled with `double` replaced by a counting scalar
+    (flopcount/counted_double.h), outputs bit-identical to the plain build -- single-threaded.  actions: None = zero actions
+    (the double-support standing state once `settle` steps have passed), else a callable step -> [n,12] float32."""
+    global _lib, _SO
+    build()
+    saved = (_lib, _SO)
+    _lib, _SO = None, _SO_COUNTED
+    try:
+        L = lib()
+        L.h1v2o_flops_get.argtypes = [C.c_void_p]
+        orc = Oracle(cfg, n_envs, seed=seed, threads=1)
+        orc.observe()
+        zero = np.zeros((n_envs, NJ), np.float32)
+        for s in range(settle):
+            orc.step(zero if actions is None else actions(s))
+        L.h1v2o_flops_reset()
+        for s in range(steps):
+            orc.step(zero if actions is None else actions(settle + s))
+        c = np.zeros(7, np.uint64)
+        L.h1v2o_flops_get(_p(c))
+        it, _ = orc.solver_stats()
+        del orc
+    finally:
+        _lib, _SO = saved
+    per = c.astype(np.float64) / (n_envs * steps)
+    names = ["add", "mul", "div", "fma", "sqrt", "transcendental", "compare"]
+    out = {k: float(v) for k, v in zip(names, per)}
+    out["flops"] = float(per[0] + per[1] + per[2] + 2 * per[3] + per[4] + per[5])  # compares are not counted as flops
+    out["mean_newton_iters_last_substep"] = float(it.mean())
+    return out
 
 
 def _p(a: np.ndarray):

@@ -38,6 +38,11 @@ class OracleVecEnv:
         obs, rew, term, trunc = self.o.step(a.numpy().astype(np.float32))
         self._obs = torch.from_numpy(obs)
         rank, _ = H1v2ManagerBasedRLEnv._dist_info()
+        self.k = getattr(self, "k", 0) + 1
+        if rank == 0 and self.k == 2:
+            # an episode "finishes" on rank 0 only: the runner's reward / length reduction must not depend on every rank having
+            # a finished episode (a collective inside `if len(rewbuffer) > 0` would hang or pair with the wrong collective)
+            term = term.copy(); term[0] = True
         return self._obs, torch.from_numpy(rew), torch.from_numpy(term | trunc).long(), {
             "time_outs": torch.from_numpy(trunc), "observations": {"policy": self._obs},
             "log": {"Probe/rank_plus_one": torch.tensor(float(rank + 1))}}  # rank-dependent: the runner must log the mean over ranks
@@ -58,7 +63,7 @@ def main():
     runner.learn(2, init_at_random_ep_len=False)
     flat = torch.cat([p.detach().reshape(-1) for p in runner.alg.policy.parameters()])
     json.dump({"rank": rank, "world": runner.gpu_world_size, "param_sum": float(flat.double().sum()), "param_abs": float(flat.double().abs().sum()),
-               "lr": float(runner.alg.lr), "probe": runner.stats.get("episode/Probe/rank_plus_one"), "root_pos": first["root_pos"].tolist(), "command": first["command"].tolist()}, open(out_path, "w"))
+               "lr": float(runner.alg.lr), "mean_len": runner.stats.get("mean_episode_length"), "probe": runner.stats.get("episode/Probe/rank_plus_one"), "root_pos": first["root_pos"].tolist(), "command": first["command"].tolist()}, open(out_path, "w"))
 
 
 if __name__ == "__main__":

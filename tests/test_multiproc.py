@@ -40,6 +40,8 @@ def test_world_size_2_gloo(tmp_path, cfg):
     assert r[0]["lr"] == r[1]["lr"]
     # (3) rollout statistics: extras["log"] entries are reduced over ranks (rank r reports r + 1; both must log 1.5)
     assert r[0]["probe"] == pytest.approx(1.5) and r[1]["probe"] == pytest.approx(1.5)
+    # (4) episode statistics: only rank 0 saw an episode end, both ranks must have taken part in the reduction and log its length
+    assert r[0]["mean_len"] is not None and r[0]["mean_len"] == r[1]["mean_len"]
     # (1) the two shards are the two halves of one 32-env job
     from oracle.oracle import Oracle
     whole = Oracle(cfg, 32, seed=42, threads=2)
