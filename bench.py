@@ -6,7 +6,8 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl refere
                steps on synthetic N(0,1) actions resident in HBM, per-step CUDA events, L2 flushed between steps,
                max over ranks.  `e2e` is the same metric through h1v2_step_host (HOST buffers, copies inside).
   * reference: the reference's CPU path restated (oracle/h1v2_oracle.c, float64, MuJoCo-semantics physics at the Isaac
-               timing 5 ms x 4) on all host cores; a bounded sample of the same workload per step.
+               timing 5 ms x 4) on all host cores, on the SAME config as the GPU arm (env count, warm-up); it loads the
+               oracle library only (its own copy of the resolved configs), never libh1v2_b200.so.
 Workload = BASELINE.json configs[1]: Isaac-Velocity-Flat-H12_12dof-v0 step, 4096 envs, random actions (--envs overrides).
 """
 from __future__ import annotations
@@ -36,6 +37,13 @@ TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-
 def task_config(task: str):
     from h1v2_isaac_b200 import _capi, tasks
     return {"flat": _capi.default_config, "rsl": _capi.rsl_config, "cat": tasks.cat_config}[task]()
+
+
+def oracle_task_config(task: str):
+    """The same resolved configs from the ORACLE library (oracle/Makefile links its own h1v2_config.cpp): the reference arm and the
+    cpu_baseline leg must not load the CUDA library."""
+    from oracle.oracle import task_config as otc
+    return otc(task)
 
 
 def parse():
@@ -88,30 +96,31 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(cfg, seed: int, target_s: float = 12.0, steps: int | None = None, warmup: int = 2):
-    """Time the CPU restatement of the reference path on all host cores; bounded sample of the same workload."""
+def cpu_baseline(cfg, seed: int, n: int, target_s: float = 12.0, steps: int | None = None, warmup: int = 3, max_s: float = 150.0):
+    """Time the CPU restatement of the reference path on all host cores, on the workload's own env count; the number of timed
+    steps is bounded (steps=None: about target_s seconds; else `steps`, cut so that the run ends within max_s)."""
     import numpy as np
     from oracle.oracle import Oracle
 
     cores = os.cpu_count() or 1
-    n = 64 * cores
     orc = Oracle(cfg, n, seed=seed, threads=cores)
     orc.observe()
     rng = np.random.default_rng(0)
     acts = [rng.normal(size=(n, 12)).astype(np.float32) for _ in range(4)]
-    for i in range(warmup):
-        orc.step(acts[i % 4])
     t0 = time.perf_counter()
     orc.step(acts[0])
     one = time.perf_counter() - t0
-    k = steps if steps is not None else max(3, int(target_s / max(one, 1e-6)))
+    warmup = max(0, min(warmup - 1, int(0.2 * max_s / max(one, 1e-6))))
+    for i in range(warmup):
+        orc.step(acts[(i + 1) % 4])
+    k = max(3, int(target_s / max(one, 1e-6))) if steps is None else max(1, min(steps, int(max_s / max(one, 1e-6))))
     t0 = time.perf_counter()
     for i in range(k):
         orc.step(acts[i % 4])
     dt = time.perf_counter() - t0
     return {"value": n * k / dt, "unit": METRIC, "cores": cores, "kind": "port",
             "sample": f"{n} envs x {k} control steps (4 x 5 ms MuJoCo-semantics substeps + managers), float64 C oracle, {cores} pthreads",
-            "ms_per_step": dt / k * 1e3, "n_envs": n, "steps": k}
+            "ms_per_step": dt / k * 1e3, "n_envs": n, "steps": k, "warmup": warmup + 1}
 
 
 def cpu_baseline_sim2sim(cfg, seed: int, target_s: float = 4.0):
@@ -145,15 +154,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = task_config(args.task)
+    cfg = oracle_task_config(args.task)
     cfg.cat_enable = 0  # the CPU restatement of the constraint tail is numpy test infrastructure (oracle/cat_oracle.py), not timed here
-    cb = cpu_baseline(cfg, args.seed, steps=max(1, args.steps) if args.steps <= 50 else None, warmup=max(1, min(args.warmup, 3)))
+    cb = cpu_baseline(cfg, args.seed, args.envs, steps=max(1, args.steps), warmup=max(args.warmup, 3))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": cb["steps"],
-        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "warmup": cb["warmup"], "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": TASKS[args.task] + " physics+obs+reward step, random actions, CPU restatement of the MuJoCo sim2sim path (bounded sample)",
-                   "envs_per_step": cb["n_envs"], "decimation": 4, "sim_dt": 0.005},
+        "config": {"workload": f"{TASKS[args.task]} physics+obs+reward step, {args.envs} envs, random N(0,1) actions" + (" (BASELINE configs[1] when 4096)" if args.task == "flat" else ""),
+                   "envs_per_gpu": args.envs, "decimation": 4, "sim_dt": 0.005, "history": int(cfg.history_length),
+                   "engine": "CPU restatement of the MuJoCo sim2sim path (oracle/h1v2_oracle.c); mujoco itself is not installable here"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -239,38 +249,48 @@ def run_ours(args):
     logv = sim.log_host()
 
     # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
-    e2e = None
-    if not args.no_e2e and not is_cat:  # h1v2_step_host has no constraint tail: no host-buffer number for --task cat
-        ha = [p.cpu().pin_memory() for p in pool[:4]]
-        hobs = torch.empty((n, sim.obs_dim), dtype=torch.float32).pin_memory()
-        hrew = torch.empty(n, dtype=torch.float32).pin_memory()
-        hterm = torch.empty(n, dtype=torch.uint8).pin_memory()
-        htrunc = torch.empty(n, dtype=torch.uint8).pin_memory()
+    def e2e_run(sim_, pool_, n_envs):
+        ha = [p.cpu().pin_memory() for p in pool_[:4]]
+        hobs = torch.empty((n_envs, sim_.obs_dim), dtype=torch.float32).pin_memory()
+        hrew = torch.empty(n_envs, dtype=torch.float32).pin_memory()
+        hterm = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
+        htrunc = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
         Ke = max(10, min(K, 100))
-        for i in range(3):
-            sim.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)
+        for i in range(5):
+            sim_.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
-            sim.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)  # synchronises inside
+            sim_.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)  # synchronises inside
         dt = time.perf_counter() - t0
         td = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * Ke / float(td.item()), "unit": METRIC, "h2d_bytes_per_step": n * 12 * 4,
-               "d2h_bytes_per_step": n * (sim.obs_dim * 4 + 4 + 1 + 1), "steps": Ke, "timer": "host wall clock around synchronous h1v2_step_host calls"}
+        mode, threads = sim_.host_path_info()
+        # mode "assemble": only the new 45-float sample (a 192-byte slot) of every env crosses PCIe, host threads assemble the
+        # [N, obs_dim] rows in the caller's buffer; mode "rows": the kernel writes the rows themselves (zero-copy)
+        d2h = n_envs * ((48 * 4 if mode == 1 else sim_.obs_dim * 4) + 4 + 1 + 1)
+        return {"value": world * n_envs * Ke / float(td.item()), "unit": METRIC, "h2d_bytes_per_step": n_envs * 12 * 4, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "ms_per_step": float(td.item()) / Ke * 1e3, "timer": "host wall clock around synchronous h1v2_step_host calls, max over ranks",
+                "host_path": {"mode": "assemble" if mode == 1 else "rows", "host_threads": threads,
+                              "rows_bytes_written_by_host_threads_per_step": n_envs * sim_.obs_dim * 4 if mode == 1 else 0}}
+
+    e2e = None
+    if not args.no_e2e and not is_cat:  # h1v2_step_host has no constraint tail: no host-buffer number for --task cat
+        e2e = e2e_run(sim, pool, n)
 
     big = None
     if n != 32768 and not args.no_big:  # the north-star target is quoted at 32768 envs/GPU: report it beside configs[1]
         sim.close()
         sampler_b = ClockSampler(local) if rank == 0 else None  # clocks / throttle reasons of THIS timed region too
-        sim_b, _, ms_b, _ = timed(32768, max(20, K // 3))
+        sim_b, pool_b, ms_b, _ = timed(32768, max(20, K // 3))
         clocks_b = sampler_b.stop() if sampler_b else None
         kb = max(20, K // 3)
         big = {"envs_per_gpu": 32768, "value": world * 32768 * kb / (ms_b * 1e-3), "unit": METRIC, "ms_per_step": ms_b / kb, "steps": kb,
-               "clocks": clocks_b}
+               "clocks": clocks_b, "e2e": None if (args.no_e2e or is_cat) else e2e_run(sim_b, pool_b, 32768)}
         sim_b.close()
+    ppo = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,47 +300,60 @@ def run_ours(args):
         hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    achieved = ALGO_BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
+    hbm_achieved = ALGO_BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
     import ctypes as C
     fp = C.c_float(0.0)
-    load_library().h1v2_measure_fp32_peak(local, C.byref(fp))
+    load_library().h1v2_measure_fp32_peak(local, C.byref(fp))  # FFMA micro-benchmark on this GPU, outside every timed region
+    fp32_peak = float(fp.value)
     rf_path = os.path.join(ROOT, "profiles", "roofline.json")
     rf = json.load(open(rf_path)) if os.path.exists(rf_path) else {}
-    flops_per_env_step = rf.get("fp32_flops_per_env_step")
-    traffic = rf.get("dram_bytes_per_launch", {}).get(str(n))  # ncu dram read+write of one launch at this env count, else null
+    # FP32 work per env-step: the instrumented oracle's operation count on this workload, frozen in profiles/roofline.json
+    # (oracle/flopcount/count.py); the Flat id's count is used for every task
+    flops = rf.get("fp32_flops_per_env_step")
+    traffic = rf.get("dram_bytes_per_launch_l2_flushed", {}).get(str(n))  # ncu dram read+write of one launch after an L2 flush, else null
+    fp32_achieved = (flops * n / (ms_per_step * 1e-3) / 1e12) if flops else None
+    wi = rf.get("warp_instructions_per_env_step", {}).get(str(n)) or rf.get("warp_instructions_per_env_step", {}).get("32768")
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+
+    def fracs(ms, nn):
+        return {"roofline_fp32_frac": (flops * nn / (ms * 1e-3) / 1e12 / fp32_peak) if flops and fp32_peak > 0 else None,
+                "roofline_hbm_frac": ALGO_BYTES_PER_ENV_STEP * nn / (ms * 1e-3) / 1e9 / hbm_peak}
+
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{TASKS[args.task]} physics+obs+reward step, {n} envs/GPU, random N(0,1) actions" + (" (BASELINE configs[1] when 4096)" if args.task == "flat" else " (SURVEY 8(f)1 variant; not BASELINE's metric config)"),
+        "config": {"workload": f"{TASKS[args.task]} physics+obs+reward step, {n} envs/GPU, random N(0,1) actions" + (" (BASELINE configs[1] when 4096)" if args.task == "flat" else " (SURVEY 8(f) variant; not BASELINE's metric config)"),
                    "envs_per_gpu": n, "decimation": 4, "sim_dt": 0.005, "history": int(cfg.history_length), "obs_dim": sim.obs_dim, "parallelism": f"env-shard x{world}",
                    "l2": "flushed between timed steps (256 MiB write, untimed); per-step CUDA events summed"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                     "note": "the step kernel is FP32-issue bound, not HBM bound (SURVEY 8(d)); see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32", "peak": float(fp.value), "unit": "TFLOP/s", "peak_source": "h1v2_measure_fp32_peak (FFMA micro-benchmark, this run)",
-                          "flops_per_env_step": flops_per_env_step,
-                          "achieved": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12) if flops_per_env_step else None,
-                          "frac": (flops_per_env_step * n / (ms_per_step * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None},
-        "roofline_issue": (lambda wi, clk: {"bound": "warp-instruction issue", "unit": "G warp-instr/s", "peak": 148 * 4 * clk * 1e-3,
-                                             "achieved": wi * n / (ms_per_step * 1e-3) / 1e9, "frac": wi * n / (ms_per_step * 1e-3) / 1e9 / (148 * 4 * clk * 1e-3),
-                                             "warp_instructions_per_env_step": wi,
-                                             "note": "instruction count per env-step from the ncu capture at 32768 envs (profiles/roofline.json); peak = 148 SMs x 4 schedulers x SM clock"}
-                           )(rf.get("warp_instructions_per_env_step", {}).get("32768"), (clocks or {}).get("sm_mhz") or 1965.0)
-                          if rf.get("warp_instructions_per_env_step", {}).get("32768") else None,
-        "at_32768_envs_per_gpu": (dict(big, roofline_hbm_frac=ALGO_BYTES_PER_ENV_STEP * 32768 / (big["ms_per_step"] * 1e-3) / 1e9 / hbm_peak,
-                                       roofline_fp32_frac=(flops_per_env_step * 32768 / (big["ms_per_step"] * 1e-3) / 1e12 / float(fp.value)) if flops_per_env_step and fp.value > 0 else None)
-                                  if big else None),
+        # the step is bounded by the FP32 (non-tensor) pipe first, HBM second
+        "roofline": {"bound": "fp32", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": (fp32_achieved / fp32_peak) if fp32_achieved and fp32_peak > 0 else None, "traffic": traffic,
+                     "peak_source": "h1v2_measure_fp32_peak: FFMA micro-benchmark on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)",
+                     "flops_per_env_step": flops,
+                     "flops_source": "instrumented oracle (oracle/flopcount): exact add+mul+div+sqrt+transcendental count of the float64 restatement on this workload, profiles/roofline.json",
+                     "traffic_note": "dram bytes of one launch, ncu --set full capture taken after an L2 flush like the timed steps (null: no such capture for this env count)"},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP},
+        "roofline_issue": ({"bound": "warp-instruction issue", "unit": "G warp-instr/s", "peak": 148 * 4 * clk * 1e-3,
+                            "achieved": wi * n / (ms_per_step * 1e-3) / 1e9, "frac": wi * n / (ms_per_step * 1e-3) / 1e9 / (148 * 4 * clk * 1e-3),
+                            "warp_instructions_per_env_step": wi,
+                            "note": "instruction count per env-step from the ncu capture in profiles/roofline.json; peak = 148 SMs x 4 schedulers x SM clock"} if wi else None),
+        "at_32768_envs_per_gpu": (dict(big, **fracs(big["ms_per_step"], 32768)) if big else None),
         "solver": {"mean_newton_iters_per_substep": float(logv[_capi.LOG_SUM_ITERS]) / (4.0 * n), "max_iters_last_step": float(logv[_capi.LOG_MAX_ITERS]),
                    "cap_hits_last_step": float(logv[_capi.LOG_CAP_HITS]), "nan_resets": float(logv[_capi.LOG_NAN_RESETS])},
     }
+    if ppo is not None:
+        line["ppo"] = ppo
     if not args.no_cpu_baseline and world == 1:
         try:
-            cb = cpu_baseline(cfg, args.seed)
+            ocfg = oracle_task_config(args.task)
+            ocfg.cat_enable = 0
+            cb = cpu_baseline(ocfg, args.seed, n)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            line["cpu_baseline_sim2sim_1core"] = cpu_baseline_sim2sim(cfg, args.seed)
+            line["cpu_baseline_sim2sim_1core"] = cpu_baseline_sim2sim(ocfg, args.seed)
         except Exception as e:  # the checker library missing must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
     print(json.dumps(line), flush=True)

@@ -84,7 +84,7 @@ STATE_FIELDS = [
     ("episode_sums", NUM_REW, f32), ("obs_history", None, f32), ("friction", 1, f32), ("mass_add", 1, f32),
     ("push_time_left", 1, f32),
     ("slot_force", NUM_SLOT * 3, f32), ("slot_force_hist", NUM_SLOT * 3, f32), ("applied_torque", NJ, f32),
-    ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32), ("solver_iters", 2, f32),
+    ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32), ("solver_iters", 3, f32),
     ("pre_reset_qpos", 19, f32), ("pre_reset_qvel", 18, f32), ("pre_reset_timers", 8, f32),
 ]
 READ_ONLY_STATE = {"slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel", "solver_iters", "pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers"}
@@ -118,6 +118,7 @@ _SYMBOLS = {
     "h1v2_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "h1v2_host_path_info": (C.c_int, [C.c_void_p, C.POINTER(i32), C.POINTER(i32)]),
     "h1v2_set_reward_weights": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_cat_step": (C.c_int, [C.c_void_p] * 7),
     "h1v2_set_constraint_max_p": (C.c_int, [C.c_void_p, C.POINTER(f32)]),

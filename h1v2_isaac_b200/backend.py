@@ -144,6 +144,12 @@ class H1v2Sim:
             return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
         self._check(self._lib.h1v2_step_host(self._h, ptr(actions), ptr(obs), ptr(rew), ptr(term), ptr(trunc)))
 
+    def host_path_info(self):
+        """(mode, threads) of step_host: 0 = rows written by the kernel, 1 = samples over PCIe + host assembly, -1 = undecided."""
+        m, t = C.c_int32(-1), C.c_int32(0)
+        self._check(self._lib.h1v2_host_path_info(self._h, C.byref(m), C.byref(t)))
+        return int(m.value), int(t.value)
+
     def observe(self) -> torch.Tensor:
         obs = torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         self._check(self._lib.h1v2_observe(self._h, obs.data_ptr(), self._stream()))

@@ -7,8 +7,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define CPU_PAUSE() _mm_pause()
+#else
+#define CPU_PAUSE() ((void)0)
+#endif
 
 #include "../../include/h1v2_model_h12.h"
 #include "h1v2_step.cuh"
@@ -62,6 +72,18 @@ struct H1v2Handle {
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   cudaStream_t host_stream = nullptr;
+  // ordering of the host path after work queued through the stream-taking entry points
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_set = false;
+  cudaEvent_t order_ev = nullptr;
+  // host-assembly path of h1v2_step_host (see HostPool below)
+  float* h_sample = nullptr;      // pinned + mapped [N][48]: the step's new sample, written by the kernel (zero-copy)
+  float* h_sample_dev = nullptr;  // its device alias
+  float* h_ring = nullptr;        // host mirror of the history ring [N][H][48]
+  bool ring_valid = false;        // the mirror equals the device ring
+  uint64_t hist_launches = 0;     // step / observe launches so far == device counters[1] (the history head)
+  struct HostPool* pool = nullptr;
+  int host_mode = -1;             // -1 undecided, 0 full rows over PCIe (zero-copy / staged), 1 samples + host assembly
   // Constraints-as-Terminations tail (cfg.cat_enable)
   CatState cat = {};
   bool cat_first = true;
@@ -69,6 +91,10 @@ struct H1v2Handle {
   uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
   float cat_log[2 * H1V2_NUM_CSTR + 1] = {};
 };
+
+// Every stream-taking entry point notes its stream: h1v2_step_host runs on a private non-blocking stream and orders itself
+// after that work at entry (a C caller may do h1v2_reset(h, ids, n, NULL) and then h1v2_step_host).
+static inline void note_stream(H1v2Handle* h, cudaStream_t st) { h->last_stream = st; h->last_stream_set = true; }
 
 // ------------------------------------------------------------------------------------------------------
 // auxiliary kernels (not on the step path)
@@ -208,7 +234,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
       if (st.pre_reset_qpos) for (int k = 0; k < 19; k++) st.pre_reset_qpos[env * 19 + k] = dg[96 + k];
       if (st.pre_reset_qvel) for (int k = 0; k < 18; k++) st.pre_reset_qvel[env * 18 + k] = dg[115 + k];
       if (st.pre_reset_timers) for (int k = 0; k < 8; k++) st.pre_reset_timers[env * 8 + k] = dg[133 + k];
-      if (st.solver_iters) { st.solver_iters[env * 2] = dg[86]; st.solver_iters[env * 2 + 1] = dg[88]; }
+      if (st.solver_iters) { st.solver_iters[env * 3] = dg[86]; st.solver_iters[env * 3 + 1] = dg[88]; st.solver_iters[env * 3 + 2] = dg[89]; }
     }
     return;
   }
@@ -414,6 +440,103 @@ static T* mapped_alias(T* host) {
   return (T*)a.devicePointer;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Host side of h1v2_step_host, mode 1: the kernel ships only the NEW 45-float sample of every env (+ its first-push flag),
+// the term-major [N, 45 H] rows are assembled on the host from a host mirror of the history ring -- bit-identical to the rows
+// the kernel emits (observation_manager.py:335-355, circular_buffer.py:79-87,131-135).  9/10 of every row is history the
+// host already has; over PCIe go 192 B per env instead of 1.8 KB.  The old part of the rows (history slots head+1 .. head-1)
+// does not depend on the step in flight, so the pool writes it WHILE the kernel runs (phase 1); after the stream has
+// synchronised only the newest slot is scattered into the rows and the mirror (phase 2).
+// ------------------------------------------------------------------------------------------------------
+struct HostPool {
+  int nthreads = 1;
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv;
+  uint64_t gen = 0;  // guarded by m
+  bool stop = false;
+  std::atomic<uint64_t> phase2{0};
+  std::atomic<int> done{0};
+  // job (written by the caller before gen is advanced)
+  const float* sample = nullptr;
+  float* ring = nullptr;
+  float* obs = nullptr;
+  int n = 0, H = 0, head = 0;
+};
+static const int kTermOff[7] = {0, 3, 6, 9, 21, 33, 45};
+static inline void env_range(const HostPool* p, int t, int& a, int& b) {
+  const int per = (p->n + p->nthreads - 1) / p->nthreads;
+  a = std::min(p->n, t * per); b = std::min(p->n, a + per);
+}
+static void assemble_old(const HostPool* p, int t) {  // phase 1: history slots older than the step in flight
+  int a, b; env_range(p, t, a, b);
+  const int H = p->H, od = 45 * H;
+  for (int e = a; e < b; e++) {
+    const float* ring = p->ring + (size_t)e * H * H1V2_HIST_STRIDE;
+    float* row = p->obs + (size_t)e * od;
+    for (int hh = 0; hh + 1 < H; hh++) {
+      int sl = p->head + 1 + hh; sl = sl >= H ? sl - H : sl;
+      const float* src = ring + sl * H1V2_HIST_STRIDE;
+      for (int k = 0; k < 9; k++) row[(k / 3) * 3 * H + hh * 3 + (k % 3)] = src[k];
+      std::memcpy(row + 9 * H + hh * 12, src + 9, 48);
+      std::memcpy(row + 21 * H + hh * 12, src + 21, 48);
+      std::memcpy(row + 33 * H + hh * 12, src + 33, 48);
+    }
+  }
+}
+static void assemble_new(const HostPool* p, int t) {  // phase 2: the new sample; a first push fills the whole ring and row
+  int a, b; env_range(p, t, a, b);
+  const int H = p->H, od = 45 * H;
+  for (int e = a; e < b; e++) {
+    const float* s = p->sample + (size_t)e * H1V2_HIST_STRIDE;
+    float* ring = p->ring + (size_t)e * H * H1V2_HIST_STRIDE;
+    float* row = p->obs + (size_t)e * od;
+    const bool fresh = s[45] != 0.f;
+    for (int sl = fresh ? 0 : p->head; sl < (fresh ? H : p->head + 1); sl++) std::memcpy(ring + sl * H1V2_HIST_STRIDE, s, 45 * sizeof(float));
+    for (int hh = fresh ? 0 : H - 1; hh < H; hh++)
+      for (int tm = 0; tm < 6; tm++) {
+        const int d = kTermOff[tm + 1] - kTermOff[tm];
+        std::memcpy(row + kTermOff[tm] * H + hh * d, s + kTermOff[tm], d * sizeof(float));
+      }
+  }
+}
+static void pool_worker(HostPool* p, int t) {
+  uint64_t seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(p->m);
+      p->cv.wait(lk, [&] { return p->stop || p->gen != seen; });
+      if (p->stop) return;
+      seen = p->gen;
+    }
+    assemble_old(p, t);
+    while (p->phase2.load(std::memory_order_acquire) != seen) CPU_PAUSE();  // the kernel is in flight: < 1 ms
+    assemble_new(p, t);
+    p->done.fetch_add(1, std::memory_order_release);
+  }
+}
+static HostPool* pool_create() {
+  HostPool* p = new HostPool();
+  int nt = 0;
+  if (const char* e = std::getenv("H1V2_HOST_THREADS")) nt = std::atoi(e);
+  if (nt <= 0) {  // the box's cores shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE); at most 16 per handle
+    int ranks = 1;
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(e));
+    nt = (int)std::thread::hardware_concurrency() / ranks;
+  }
+  p->nthreads = std::max(1, std::min(nt, 16));
+  for (int t = 1; t < p->nthreads; t++) p->threads.emplace_back(pool_worker, p, t);
+  return p;
+}
+static void pool_destroy(HostPool* p) {
+  if (!p) return;
+  { std::lock_guard<std::mutex> lk(p->m); p->stop = true; }
+  p->cv.notify_all();
+  for (auto& t : p->threads) t.join();
+  delete p;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------------
@@ -478,6 +601,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
     S.lut = lut_d;
   }
   CKH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  CKH(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
   startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
   reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, 0);
   h->launches += 2;
@@ -495,6 +619,10 @@ void h1v2_destroy(H1v2Handle* h) {
   for (void* p : {(void*)h->d_act, (void*)h->d_obs, (void*)h->d_rew, (void*)h->d_term, (void*)h->d_trunc})
     if (p) cudaFree(p);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
+  pool_destroy(h->pool);
+  if (h->h_sample) cudaFreeHost(h->h_sample);
+  std::free(h->h_ring);
   delete h;
 }
 
@@ -521,13 +649,19 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
   const int cnt = env_ids ? n : h->n;
   if (cnt <= 0) return 0;
   reset_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(h->P, h->S, env_ids, cnt, 0);
+  note_stream(h, st);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
 
-static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st) {
+static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st,
+                       float* sample_out = nullptr) {
   DeviceGuard guard(h->device);
+  KState S = h->S;
+  S.sample_out = sample_out;
+  h->hist_launches += 1;  // every launch advances the history head (device counters[1])
+  if (!sample_out) { h->ring_valid = false; note_stream(h, st); }  // the host mirror of the ring misses this launch's sample
   const int threads = H1V2_BLOCK;
   const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
   const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(real);
@@ -538,9 +672,9 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     h->attr_set = true;
   }
   if (do_step)
-    step_kernel<true><<<blocks, threads, smem, st>>>(h->P, h->S, actions, obs, rew, term, trunc);
+    step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else  // the observe-only launch stages the history rings in the same shared-memory window
-    step_kernel<false><<<blocks, threads, smem, st>>>(h->P, h->S, nullptr, obs, nullptr, nullptr, nullptr);
+    step_kernel<false><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -560,30 +694,92 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
   if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step_host: bad arguments");
   DeviceGuard guard(h->device);
   const size_t N = (size_t)h->n, od = (size_t)h->P.obs_dim;
+  cudaStream_t st = h->host_stream;
+  if (h->last_stream_set) {  // order this step after whatever the stream-taking entry points queued on the caller's streams
+    CK(cudaEventRecord(h->order_ev, h->last_stream));
+    CK(cudaStreamWaitEvent(st, h->order_ev, 0));
+    h->last_stream_set = false;
+  }
+  if (h->host_mode < 0) {
+    // mode 1 (samples over PCIe + rows assembled by host threads) pays while the rows and the ring mirror stay cache-resident
+    // and the rank has cores to spare; otherwise mode 0: the kernel writes whole rows into the (pinned) caller buffer, the
+    // minimum-traffic way for the host memory system.  H1V2_HOST_PATH=rows|assemble overrides (measured: profiles/r2_notes.md).
+    h->pool = pool_create();
+    const char* e = std::getenv("H1V2_HOST_PATH");
+    if (e && !std::strcmp(e, "rows")) h->host_mode = 0;
+    else if (e && !std::strcmp(e, "assemble")) h->host_mode = 1;
+    // measured on the 16-core host of a B200 box (profiles/r2_e2e_modes.txt): 16 threads beat the row path at every size
+    // (4096 envs 0.258 vs 0.296 ms, 32768 envs 0.99 vs 1.43 ms), 8 threads up to 8192 envs, 4 threads never
+    else h->host_mode = (h->pool->nthreads >= 8 && N * od * sizeof(float) <= (size_t)h->pool->nthreads * (4u << 20)) ? 1 : 0;
+  }
   if (!h->d_act) {
     CK(cudaMalloc(&h->d_act, N * 12 * sizeof(float)));
-    CK(cudaMalloc(&h->d_obs, N * od * sizeof(float)));
     CK(cudaMalloc(&h->d_rew, N * sizeof(float)));
     CK(cudaMalloc(&h->d_term, N));
     CK(cudaMalloc(&h->d_trunc, N));
   }
-  cudaStream_t st = h->host_stream;
-  // Pinned caller buffers are written by the kernel itself (zero-copy over PCIe): the 1.8 KB observation row of an env
-  // leaves the GPU as soon as its warp has emitted it, overlapping the transfer with the rest of the step instead of
-  // serialising a 450-float-per-env D2H copy behind the kernel.  Pageable buffers take the staged path.
-  float* obs_dev = mapped_alias(obs);
   float* rew_dev = mapped_alias(rew);
   uint8_t* term_dev = mapped_alias(terminated);
   uint8_t* trunc_dev = mapped_alias(truncated);
   const float* act_dev = mapped_alias(const_cast<float*>(actions));
   if (!act_dev) { CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st)); act_dev = h->d_act; }
+  if (h->host_mode == 1) {
+    const int H = h->P.H;
+    const size_t ring_bytes = N * H * H1V2_HIST_STRIDE * sizeof(float);
+    if (!h->h_sample) {
+      CK(cudaHostAlloc(&h->h_sample, N * H1V2_HIST_STRIDE * sizeof(float), cudaHostAllocMapped));
+      CK(cudaHostGetDevicePointer(&h->h_sample_dev, h->h_sample, 0));
+      h->h_ring = (float*)std::aligned_alloc(64, (ring_bytes + 63) / 64 * 64);
+      if (!h->h_ring) return fail("h1v2_step_host: out of host memory");
+    }
+    if (!h->ring_valid) {  // first call, or the device path ran in between: fetch the ring once
+      CK(cudaMemcpyAsync(h->h_ring, h->S.hist, ring_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    HostPool* p = h->pool;
+    const int head = (int)((h->hist_launches + 1) % (uint64_t)H);  // the slot this launch writes (step_kernel: counters[1] + 1)
+    if (launch_step(h, true, act_dev, nullptr, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st,
+                    h->h_sample_dev) != 0) return -1;
+    if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
+    if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+    uint64_t gen;
+    {
+      std::lock_guard<std::mutex> lk(p->m);
+      p->sample = h->h_sample; p->ring = h->h_ring; p->obs = obs; p->n = h->n; p->H = H; p->head = head;
+      p->done.store(0, std::memory_order_relaxed);
+      gen = ++p->gen;
+    }
+    p->cv.notify_all();
+    assemble_old(p, 0);  // the caller's thread is worker 0
+    const cudaError_t e = cudaStreamSynchronize(st);
+    p->phase2.store(gen, std::memory_order_release);  // release the workers even on failure
+    if (e == cudaSuccess) assemble_new(p, 0);
+    while (p->done.load(std::memory_order_acquire) != p->nthreads - 1) CPU_PAUSE();
+    if (e != cudaSuccess) { h->ring_valid = false; return fail(std::string("h1v2_step_host: ") + cudaGetErrorString(e)); }
+    h->ring_valid = true;
+    return 0;
+  }
+  // mode 0.  Pinned caller buffers are written by the kernel itself (zero-copy over PCIe): the 1.8 KB observation row of an env
+  // leaves the GPU as soon as its warp has emitted it, overlapping the transfer with the rest of the step instead of
+  // serialising a 450-float-per-env D2H copy behind the kernel.  Pageable buffers take the staged path.
+  float* obs_dev = mapped_alias(obs);
+  if (!obs_dev && !h->d_obs) CK(cudaMalloc(&h->d_obs, N * od * sizeof(float)));
   if (launch_step(h, true, act_dev, obs_dev ? obs_dev : h->d_obs, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term,
                   trunc_dev ? trunc_dev : h->d_trunc, st) != 0) return -1;
+  h->last_stream_set = false;  // nothing of this launch is left in flight after the synchronise below
   if (!obs_dev) CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
   if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads) {
+  if (!h || !mode || !threads) return fail("h1v2_host_path_info: bad arguments");
+  *mode = h->host_mode;
+  *threads = h->pool ? h->pool->nthreads : 0;
   return 0;
 }
 
@@ -671,6 +867,7 @@ int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
   if (!h || !dst) return fail("h1v2_get_state: bad arguments");
   DeviceGuard guard(h->device);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *dst, 0);
+  note_stream(h, (cudaStream_t)cuda_stream);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -679,6 +876,8 @@ int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream) {
   if (!h || !src) return fail("h1v2_set_state: bad arguments");
   DeviceGuard guard(h->device);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *src, 1);
+  note_stream(h, (cudaStream_t)cuda_stream);
+  h->ring_valid = false;  // may have replaced the observation history
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -733,6 +932,7 @@ int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda
   if (!h || !actions) return fail("h1v2_random_actions: bad arguments");
   DeviceGuard guard(h->device);
   random_actions_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(h->P, actions, step);
+  note_stream(h, (cudaStream_t)cuda_stream);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;

@@ -97,6 +97,7 @@ struct KState {
   const int* lut;  // [obs_dim] (history index << 8) | offset in the 45-float sample, for the term-major flatten
   int64_t* ep_len; // [N] bound, owned by the caller
   float* diag;     // [N][H1V2_DIAG_DIM] or NULL
+  float* sample_out;  // [N][48] or NULL: this step's observation sample (45) | fresh flag at [45]; the host path of h1v2_step_host assembles the rows from it
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector
   unsigned long long* counters;  // [0] global step counter, [1] history head, [2] dead-zone census being taken, [3] census of the last step
@@ -105,7 +106,7 @@ struct KState {
 #define H1V2_DIAG_DIM 168
 #define H1V2_DIAG_REW0 144
 // diag layout: slot_force 0..17 | slot_hist 18..35 | applied_torque 36..47 | joint_acc 48..59 | (free 60..79)
-//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140
+//              | foot_vel 80..85 | newton iters 86 | cap hit 87 | iter sum 88 | contact-list overflow 89 | pre-reset qpos 96..114 | qvel 115..132 | timers 133..140
 //              | command before this step's update 141..143 | reward_terms 144..165 | episode length (pre-reset) 166 | reset flag 167
 #define FLAG_DELAY_FRESH 1
 #define FLAG_HIST_FRESH 2

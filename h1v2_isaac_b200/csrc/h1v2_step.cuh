@@ -279,6 +279,23 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     }
     __syncwarp();
     const int e1 = min(nenv, e0 + epc);
+    if (S.sample_out) {
+      // host path (h1v2_step_host): only what is NEW leaves the GPU -- the 45-float sample of every env of the chunk (+ the
+      // first-push flag), 192 B per env instead of the 1.8 KB row the host can assemble from its own copy of the ring.
+      // The warp's samples are one contiguous 16-byte-aligned range: coalesced float4 stores (zero-copy over PCIe when pinned).
+      const int nq = (e1 - e0) * (H1V2_HIST_STRIDE / 4);
+      float4* dst4 = reinterpret_cast<float4*>(S.sample_out + (size_t)(warp_env0 + e0) * H1V2_HIST_STRIDE);
+      for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int qi = q0 + lane;
+        const int e = min(qi / (H1V2_HIST_STRIDE / 4), e1 - e0 - 1), k4 = qi % (H1V2_HIST_STRIDE / 4);
+        const int fl = __shfl_sync(0xffffffffu, cmd.flags, 2 * (e0 + e));
+        if (qi < nq) {
+          float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem_raw) + e * ring + head * H1V2_HIST_STRIDE + 4 * k4);
+          if (k4 == H1V2_HIST_STRIDE / 4 - 1) v.y = (fl & FLAG_HIST_FRESH) ? 1.f : 0.f;  // float 45 of the slot (45..47 are padding)
+          dst4[qi] = v;
+        }
+      }
+    }
 #pragma unroll 1
     for (int e = e0; e < e1; e++) {
       const int env_e = warp_env0 + e;
@@ -609,6 +626,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       term[env] = (uint8_t)(contact != 0);
       trunc[env] = (uint8_t)time_out;
     }
+    const int novf_pair = novf + __shfl_xor_sync(FULL_MASK, novf, 1);
     if (S.diag && valid) {
       float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
       dg[3 * side + 0] = so.F_foot.x; dg[3 * side + 1] = so.F_foot.y; dg[3 * side + 2] = so.F_foot.z;
@@ -631,6 +649,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
         for (int t = 0; t < H1V2_NUM_REW; t++) dg[H1V2_DIAG_REW0 + t] = r[t];
         dg[86] = (real)max_it; dg[87] = (real)ncap; dg[88] = (real)sum_it;
+        dg[89] = (real)novf_pair;  // contact points dropped by either leg's full list
         // for the Constraints-as-Terminations tail: the command the mdp terms of this step read (before its update), the episode length
         dg[141] = cmd.c[0]; dg[142] = cmd.c[1]; dg[143] = cmd.c[2];
         dg[166] = (real)ep_len; dg[167] = reset ? 1.f : 0.f;

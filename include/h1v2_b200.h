@@ -250,7 +250,8 @@ typedef struct H1v2State {
   float* joint_acc;     /* [N,12] last substep */
   float* reward_terms;  /* [N,NUM_REW] weighted*dt value of every term in the last step */
   float* foot_vel;      /* [N,2,3] world linear velocity of the ankle_roll_link origins */
-  float* solver_iters;  /* [N,2] max and sum of Newton iterations over the substeps of the last step */
+  float* solver_iters;  /* [N,3] max and sum of Newton iterations over the substeps of the last step; contact points dropped because a leg's
+                           active list (5 entries) was full -- only possible with shin / torso / pelvis on the ground, i.e. in a terminating step */
   float* pre_reset_qpos;   /* [N,19] state after the physics substeps of the last step, BEFORE any reset */
   float* pre_reset_qvel;   /* [N,18] */
   float* pre_reset_timers; /* [N,2,4] */
@@ -283,6 +284,13 @@ int h1v2_step(H1v2Handle* h, const float* actions /*[N,12]*/, float* obs /*[N,ob
 /* Same with HOST buffers (pinned or pageable): H2D of actions and D2H of all outputs inside, synchronises. */
 int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                    uint8_t* truncated);
+/* How h1v2_step_host moves the observations (decided at its first call; H1V2_HOST_PATH=rows|assemble and
+ * H1V2_HOST_THREADS=<n> override): mode 0 "rows" = the kernel writes whole [N, obs_dim] rows into the caller's buffer
+ * (zero-copy over PCIe when it is pinned, staged otherwise); mode 1 "assemble" = only the step's new 45-float sample of
+ * every env crosses PCIe and `threads` host threads assemble the rows from a host mirror of the history ring while the
+ * kernel runs (bit-identical rows; tests/test_gpu_parity.py::test_step_host_matches_device_path).  -1 = not decided yet.
+ * The call orders itself after work queued earlier through the stream-taking entry points and synchronises before returning. */
+int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads);
 
 /* Replace the reward weights (CurriculumManager's modify_reward_weight, rsl_env_cfg.py:447-497).  Host array of
  * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises.  (h1v2_step is CUDA-graph

@@ -1249,7 +1249,7 @@ int h1v2o_get_state(H1v2Oracle* o, const H1v2State* s) {
   CPY_OUT(joint_acc, o->env[i].joint_acc[k], NJ, float)
   CPY_OUT(reward_terms, o->env[i].rew_terms[k], NREW, float)
   CPY_OUT(foot_vel, o->env[i].foot_vel[k / 3][k % 3], 6, float)
-  CPY_OUT(solver_iters, o->env[i].newton_iters, 2, float)
+  CPY_OUT(solver_iters, (k < 2 ? o->env[i].newton_iters : 0), 3, float) /* [2]: contact-list overflow, a kernel-only notion (the oracle's row list is unbounded) */
   CPY_OUT(pre_reset_qpos, 0.0f, 19, float)
   CPY_OUT(pre_reset_qvel, 0.0f, 18, float)
   CPY_OUT(pre_reset_timers, 0.0f, 8, float)

@@ -55,13 +55,14 @@ def test_reset_state_matches_oracle(cfg):
 @pytest.mark.parametrize("decimation,action_scale", [(1, 1.0), (1, 0.3), (4, 1.0)])
 def test_physics_parity_from_identical_states(cfg, decimation, action_scale):
     """(c): every control step starts from the SAME state on both sides (oracle re-synchronised to the GPU state).
-    decimation=1 is the single physics step of the north star; decimation=4 a whole control step (4 chained substeps).
-    Positions: 1e-4 rad / 1e-4 m on EVERY env.  Velocities: 99 % of env-steps within 5e-4 rad/s, 99.9 % within
-    1.5e-3 rad/s, all within 5e-3 rad/s.  The tail is the fp32 floor of this model, measured and explained in
-    DESIGN.md section 7: the pelvis height (~1 m) resolves 1e-7 m in fp32, MuJoCo's contact stiffness is ~7e5 N/m per
-    sole corner, so a hard landing (3-8 kN under N(0,1) actions) carries ~0.01 N m of pitch-moment noise on an ankle of
-    0.0136 kg m^2.  Envs within 2e-6 m (rad) of a contact (joint-limit) activation boundary at a substep start are
-    skipped: the soft contact switches on discontinuously at dist = 0, so float-vs-double rounding decides those."""
+    decimation=1 is the single physics step of the north star and is asserted LITERALLY: positions within 1e-4 rad / m and
+    velocities within 1e-3 rad/s (m/s) on EVERY kept env-step.  Measured on B200 over 785 k env-steps per seed
+    (tools/diag_fp64.py, profiles/r2_notes.md): max 8.5e-4 rad/s at action scale 1.0, 3.4e-4 at 0.3, q99.9 1.7e-4.  What is
+    left is fp32 rounding inside hard landings (2-3 kN on one foot): the SAME kernel source built in double agrees with the
+    oracle to 1.6e-4 (tests/test_gpu_fp64.py), and storing any single intermediate in float does not bring the error back.
+    decimation=4 chains four such substeps without re-synchronising, so the single-step budget compounds: bounded at 4e-3.
+    Envs within 2e-6 m (rad) of a contact (joint-limit) activation boundary at a substep start are skipped and counted:
+    the soft contact switches on discontinuously at dist = 0, so float-vs-double rounding of the distance decides those."""
     c = cfg.copy()
     c.decimation = decimation
     c.max_delay = min(c.max_delay, 2 * decimation)
@@ -71,23 +72,29 @@ def test_physics_parity_from_identical_states(cfg, decimation, action_scale):
     rng = np.random.default_rng(0)
     errs = {k: [] for k in PHYS}
     steps = 24 * (4 // decimation)
+    n_alive = n_boundary = 0
     for step in range(steps):
         a = (action_scale * rng.normal(size=(n, 12))).astype(np.float32)
         _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
         _, _, to, uo = orc.step(a)
         g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS)
         mc, ml = orc.activation_margin()
-        keep = ~(to | uo | tg.cpu().numpy()) & (mc > 2e-6) & (ml > 2e-6)
+        alive = ~(to | uo | tg.cpu().numpy())
+        keep = alive & (mc > 2e-6) & (ml > 2e-6)
+        n_alive += int(alive.sum()); n_boundary += int((alive & ~keep).sum())
         for k in PHYS:
             errs[k].append(np.abs(g[k][keep] - o[k][keep]).max(axis=1))
         _resync(sim, orc, g)
     e = {k: np.concatenate(v) for k, v in errs.items()}
-    print({k: (float(v.max()), float(np.quantile(v, 0.999)), float(np.quantile(v, 0.99))) for k, v in e.items()}, "env-steps", len(e["joint_pos"]))
-    assert len(e["joint_pos"]) > 0.7 * n * steps
+    print({k: (float(v.max()), float(np.quantile(v, 0.999)), float(np.quantile(v, 0.99))) for k, v in e.items()}, "env-steps", len(e["joint_pos"]),
+          f"excluded on an activation boundary: {n_boundary} of {n_alive} ({100.0 * n_boundary / max(n_alive, 1):.3f} %)")
+    assert len(e["joint_pos"]) > 0.7 * n * steps and n_boundary < 0.01 * n_alive
     for k in ("joint_pos", "root_pos", "root_quat"):
         assert e[k].max() < 1e-4, k
+    vmax = 1e-3 if decimation == 1 else 4e-3
     for k in ("joint_vel", "root_lin_vel", "root_ang_vel"):
-        assert np.quantile(e[k], 0.99) < 5e-4 and np.quantile(e[k], 0.999) < 1.5e-3 and e[k].max() < 5e-3, k
+        assert e[k].max() < vmax, (k, float(e[k].max()))
+        assert np.quantile(e[k], 0.99) < 5e-4 and np.quantile(e[k], 0.999) < 1e-3, k
     assert np.median(e["joint_vel"]) < 1e-4
 
 
@@ -100,13 +107,17 @@ def test_fall_contacts_and_termination_decisions_from_identical_states(cfg):
     torch, sim, orc = _mk(cfg, n, 41)
     sim.observe(); orc.observe()
     rng = np.random.default_rng(8)
-    n_fall_contacts = n_term = n_mismatch = n_steps = 0
+    n_fall_contacts = n_term = n_mismatch = n_steps = n_overflow = n_overflow_alive = 0
     worst = 0.0
     for step in range(48):
         a = rng.normal(size=(n, 12)).astype(np.float32)
         _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
         _, _, to, uo = orc.step(a)
-        g = _np(sim.get_state(SYNC + ["slot_force", "slot_force_hist"]))
+        g = _np(sim.get_state(SYNC + ["slot_force", "slot_force_hist", "solver_iters"]))
+        # a leg's active contact list holds 5 points (4 sole corners + 1): a dropped point is only acceptable in a step that
+        # terminates anyway (shin / torso / pelvis on the ground), where the state is thrown away
+        ovf = g["solver_iters"][:, 2] > 0
+        n_overflow += int(ovf.sum()); n_overflow_alive += int((ovf & ~tg.cpu().numpy()).sum())
         o = orc.get_state(["slot_force", "slot_force_hist"])
         mc, ml = orc.activation_margin()
         keep = (mc > 2e-6) & (ml > 2e-6)
@@ -123,6 +134,8 @@ def test_fall_contacts_and_termination_decisions_from_identical_states(cfg):
         n_mismatch += int((tg[keep] != to[keep])[decided].sum()); n_term += int(to.sum()); n_steps += int(keep.sum())
         _resync(sim, orc, g)
     print(f"fall-body force samples {n_fall_contacts}, worst error in units of (1 % + 0.5 N) {worst:.2f}, terminations {n_term}, decision mismatches {n_mismatch} of {n_steps}")
+    print(f"contact-list overflows {n_overflow}, of which in envs that did not terminate in that step: {n_overflow_alive}")
+    assert n_overflow_alive == 0
     assert n_fall_contacts > 300 and n_term > 100
     assert worst < 0.25  # measured 0.02: the fall-body forces agree to ~2e-4 relative
     assert n_mismatch == 0
@@ -376,24 +389,40 @@ def test_full_size_properties(cfg, task, n):
         assert torch.equal(obs_h[k], obs_a[k][half:]), k
 
 
+@pytest.mark.parametrize("mode", ["rows", "assemble"])
 @pytest.mark.parametrize("pinned", [True, False])
-def test_step_host_matches_device_path(cfg, pinned):
-    """The HOST-buffer entry point (what a non-torch caller binds) gives exactly the device path's results, both through
-    the zero-copy path (pinned buffers, written by the kernel over PCIe) and the staged one (pageable numpy buffers)."""
+def test_step_host_matches_device_path(cfg, pinned, mode, monkeypatch):
+    """The HOST-buffer entry point (what a non-torch caller binds) gives exactly the device path's results in both of its
+    modes -- "rows": the kernel writes whole observation rows into the caller's buffer (zero-copy over PCIe when pinned, staged
+    when pageable); "assemble": only the new 45-float sample crosses PCIe and host threads assemble the term-major rows from
+    a host mirror of the history ring -- and when it is mixed with the stream-taking entry points (a device-path step, an API
+    reset on the caller's stream, a state write): the host path orders itself after them and re-fetches the ring."""
     import torch
     from h1v2_isaac_b200.backend import H1v2Sim
+    monkeypatch.setenv("H1V2_HOST_PATH", mode)
     n = 1024
     s1, s2 = H1v2Sim(n, cfg, seed=4), H1v2Sim(n, cfg, seed=4)
     s1.observe(); s2.observe()
     pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
     hobs = pin(torch.empty((n, s1.obs_dim))); hrew = pin(torch.empty(n))
     ht = pin(torch.empty(n, dtype=torch.uint8)); hu = pin(torch.empty(n, dtype=torch.uint8))
-    for i in range(5):
+    ids = torch.tensor([1, 17, 500, 1023], device="cuda")
+    for i in range(14):
         a = s1.random_actions(i)
         o, r, t, u = s1.step(a)
+        if i == 5:  # a device-path step in between: the host mirror of the ring is stale afterwards
+            o2, r2, t2, u2 = s2.step(a)
+            assert torch.equal(o, o2)
+            continue
         s2.step_host(pin(a.cpu()), hobs, hrew, ht, hu)
-        assert torch.equal(o.cpu(), hobs) and torch.equal(r.cpu(), hrew) and torch.equal(t.cpu().to(torch.uint8), ht)
-        assert torch.equal(u.cpu().to(torch.uint8), hu)
+        assert torch.equal(o.cpu(), hobs), i
+        assert torch.equal(r.cpu(), hrew) and torch.equal(t.cpu().to(torch.uint8), ht) and torch.equal(u.cpu().to(torch.uint8), hu)
+        if i == 8:  # API reset of a few envs, queued on the caller's stream and NOT synchronised before the next host step
+            s1.reset(ids); s2.reset(ids)
+        if i == 10:  # state write (incl. the observation history) on the caller's stream
+            st = {k: v.clone() for k, v in s1.get_state(["obs_history", "joint_pos"]).items()}
+            st["obs_history"][::3] += 0.125
+            s1.set_state(st); s2.set_state(st)
     s1.close(); s2.close()
 
 

@@ -15,7 +15,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 ascale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 DEC = int(os.environ.get("DECIM", "1")); SEED = int(os.environ.get("SEED", "3"))
-F64 = os.path.join(ROOT, "h1v2_isaac_b200", "libh1v2_b200_f64.so")
+F64 = os.environ.get("F64LIB") or os.path.join(ROOT, "h1v2_isaac_b200", "libh1v2_b200_f64.so")
 PHYS = ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"]
 SYNC = PHYS + ["last_action", "target_hist", "lag", "fresh", "command", "heading_target", "time_left", "is_standing", "is_heading", "cmd_metrics",
                "feet_timers", "episode_sums", "obs_history", "friction", "mass_add", "push_time_left"]
