@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-big", action="store_true", help="skip the extra 32768-envs/GPU measurement")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO-loop measurement (BASELINE configs[2]/[3])")
     return ap.parse_args()
 
 
@@ -290,7 +291,54 @@ def run_ours(args):
         big = {"envs_per_gpu": 32768, "value": world * 32768 * kb / (ms_b * 1e-3), "unit": METRIC, "ms_per_step": ms_b / kb, "steps": kb,
                "clocks": clocks_b, "e2e": None if (args.no_e2e or is_cat) else e2e_run(sim_b, pool_b, 32768)}
         sim_b.close()
+    # ---- BASELINE configs[2] / [3]: the PPO loop of scripts/rsl_rl/train.py:120-141 on this backend (RslRlVecEnvWrapper ->
+    #      OnPolicyRunner.learn, random-init ActorCritic [512, 256, 128], 24 steps per env, 5 epochs x 4 mini-batches), with the
+    #      learner's NCCL collectives inside when N > 1: 20 gradient all-reduces (791 961 parameters, 3.17 MB) + 20 KL reductions
+    #      + the rollout-statistics reductions per iteration.  Reported beside the step metric, not instead of it.
+    def ppo_leg(n_envs, iters):
+        import contextlib
+        import tempfile
+        from h1v2_isaac_b200 import shims, tasks
+        shims.install()
+        tasks.register()
+        import gymnasium as gym
+        from isaaclab_rl.rsl_rl import RslRlVecEnvWrapper
+        from rsl_rl.runners import OnPolicyRunner
+        with contextlib.redirect_stdout(sys.stderr):  # the env and the runner print progress lines; stdout carries ONE JSON line
+            torch.manual_seed(args.seed + rank)
+            torch.backends.cuda.matmul.allow_tf32 = True  # as scripts/rsl_rl/train.py:70-73 sets them
+            torch.backends.cudnn.allow_tf32 = True
+            env = gym.make(TASKS["flat"], cfg=tasks.default_env_cfg(n_envs, device=f"cuda:{local}"))
+            agent = tasks.default_agent_cfg()
+            runner = OnPolicyRunner(RslRlVecEnvWrapper(env), agent.to_dict(), log_dir=tempfile.mkdtemp(prefix="h1v2_bench_ppo_"), device=f"cuda:{local}")
+            runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)  # warm-up: eager body + graph capture
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            runner.learn(num_learning_iterations=iters)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            td = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            T = runner.num_steps_per_env
+            col = sum(c for c, _ in runner.iteration_times) / len(runner.iteration_times)
+            lrn = sum(l for _, l in runner.iteration_times) / len(runner.iteration_times)
+            out = {"value": world * n_envs * T * iters / float(td.item()), "unit": METRIC, "envs_per_gpu": n_envs, "iterations": iters, "steps_per_env": T,
+                   "s_per_iteration": float(td.item()) / iters, "collection_s_per_iteration": col, "learn_s_per_iteration": lrn,
+                   "collection_ms_per_control_step": col / T * 1e3, "graph_rollout": bool(runner.graph_rollout),
+                   "policy": "random-init ActorCritic [512, 256, 128] ELU, fp32 parameters, TF32 matmul allowed (scripts/rsl_rl/train.py:70-73)", "mean_episode_length": runner.stats.get("mean_episode_length"),
+                   "collectives_per_iteration": (f"NCCL x{world}: 20 gradient all-reduces of {sum(p.numel() for p in runner.alg.policy.parameters())} parameters, 20 KL all-reduces, 2 rollout-statistics all-reduces" if world > 1 else "none (1 GPU)"),
+                   "timer": "host wall clock around OnPolicyRunner.learn, synchronised, max over ranks"}
+            env.close()
+        return out
+
     ppo = None
+    if not args.no_ppo and args.task == "flat":
+        ppo = ppo_leg(n, 4)
+        if big is not None:
+            big["ppo"] = ppo_leg(32768, 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

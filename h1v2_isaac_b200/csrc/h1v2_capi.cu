@@ -732,9 +732,12 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
       h->h_ring = (float*)std::aligned_alloc(64, (ring_bytes + 63) / 64 * 64);
       if (!h->h_ring) return fail("h1v2_step_host: out of host memory");
     }
-    if (!h->ring_valid) {  // first call, or the device path ran in between: fetch the ring once
+    if (!h->ring_valid) {  // first call, or the device path ran in between: fetch the ring once, and the head from the device
+      unsigned long long head_counter = 0;  // (a CUDA graph may have replayed steps this library never saw on the host)
       CK(cudaMemcpyAsync(h->h_ring, h->S.hist, ring_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&head_counter, h->S.counters + 1, sizeof(head_counter), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      h->hist_launches = head_counter;
     }
     HostPool* p = h->pool;
     const int head = (int)((h->hist_launches + 1) % (uint64_t)H);  // the slot this launch writes (step_kernel: counters[1] + 1)

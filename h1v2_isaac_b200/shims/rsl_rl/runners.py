@@ -150,7 +150,14 @@ class PPO:
                  entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01,
                  device="cpu", normalize_advantage_per_mini_batch=False, multi_gpu_cfg=None, **kwargs):
         self.policy, self.device = policy.to(device), device
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate)
+        # On CUDA the adaptive learning rate lives in a 0-d device tensor (Adam(capturable=True) reads it on the device), so the
+        # KL test of every mini-batch costs no host synchronisation; self.lr (float, for logs / checkpoints) is refreshed once per update().
+        self._lr_on_device = str(device).startswith("cuda")
+        if self._lr_on_device:
+            self.lr_t = torch.tensor(float(learning_rate), device=device)
+            self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.lr_t, capturable=True)
+        else:
+            self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate)
         self.epochs, self.nmb, self.clip, self.gamma, self.lam = num_learning_epochs, num_mini_batches, clip_param, gamma, lam
         self.vcoef, self.ecoef, self.lr, self.max_grad_norm = value_loss_coef, entropy_coef, learning_rate, max_grad_norm
         self.clip_v, self.schedule, self.desired_kl = use_clipped_value_loss, schedule, desired_kl
@@ -195,7 +202,7 @@ class PPO:
                 off += n
 
     def update(self):
-        mv = ms = me = 0.0
+        mv = ms = me = torch.zeros((), device=self.device)
         n = 0
         for obs, cobs, act, val, adv, ret, old_logp, old_mu, old_sigma in self.storage.mini_batches(self.nmb, self.epochs):
             self.policy.act(obs)
@@ -209,12 +216,18 @@ class PPO:
                     if self.multi_gpu:
                         dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
                         kl_mean /= self.multi_gpu["world_size"]
-                    if kl_mean > self.desired_kl * 2.0:
-                        self.lr = max(1e-5, self.lr / 1.5)
-                    elif 0.0 < kl_mean < self.desired_kl / 2.0:
-                        self.lr = min(1e-2, self.lr * 1.5)
-                    for g in self.opt.param_groups:
-                        g["lr"] = self.lr
+                    if self._lr_on_device:  # same rule as below, evaluated on the device
+                        down = (self.lr_t / 1.5).clamp(min=1e-5)
+                        up = (self.lr_t * 1.5).clamp(max=1e-2)
+                        self.lr_t.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down,
+                                                    torch.where((kl_mean > 0.0) & (kl_mean < self.desired_kl / 2.0), up, self.lr_t)))
+                    else:
+                        if kl_mean > self.desired_kl * 2.0:
+                            self.lr = max(1e-5, self.lr / 1.5)
+                        elif 0.0 < kl_mean < self.desired_kl / 2.0:
+                            self.lr = min(1e-2, self.lr * 1.5)
+                        for g in self.opt.param_groups:
+                            g["lr"] = self.lr
             ratio = torch.exp(logp - old_logp.squeeze(1))
             a = adv.squeeze(1)
             surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip, 1.0 + self.clip)).mean()
@@ -230,9 +243,107 @@ class PPO:
                 self.reduce_parameters()
             nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
             self.opt.step()
-            mv += vloss.item(); ms += surrogate.item(); me += ent.mean().item(); n += 1
+            mv = mv + vloss.detach(); ms = ms + surrogate.detach(); me = me + ent.mean().detach(); n += 1
         self.storage.clear()
-        return {"value_function": mv / n, "surrogate": ms / n, "entropy": me / n}
+        if self._lr_on_device:
+            self.lr = float(self.lr_t)  # the one host read of the update
+        return {"value_function": float(mv) / n, "surrogate": float(ms) / n, "entropy": float(me) / n}
+
+
+
+class _GraphRollout:
+    """The whole num_steps_per_env rollout of one iteration as ONE CUDA graph: per step the actor / critic
+    forward, the action sample, its log-probability, the fused env step (h1v2_step through H1v2Sim.step_into, which writes the
+    next observation straight into the rollout storage), the time-out bootstrap and the storage writes -- the same arithmetic as
+    PPO.act / env.step / PPO.process_env_step above, with the per-step Python, the wrapper dictionaries and the logging
+    synchronisations (nonzero / tolist) replaced by device-side accumulators read once per iteration.  Used when the env is this
+    package's CUDA backend without privileged observations, empirical normalisation or a pending curriculum change; otherwise (and
+    with H1V2_GRAPH_ROLLOUT=0) OnPolicyRunner.learn runs the eager loop.  The first iteration runs the same body eagerly (warm-up
+    of cuBLAS workspaces and kernel attributes), the graph is captured after it and replayed from the second iteration on."""
+
+    def __init__(self, runner):
+        self.r = runner
+        env, alg = runner.env, runner.alg
+        base = env.unwrapped
+        self.base, self.sim, self.alg, self.T = base, base.sim, alg, runner.num_steps_per_env
+        self.clip = getattr(env, "clip_actions", None)
+        self.bootstrap = not getattr(base, "cfg_is_finite_horizon", False)
+        dev, n = self.sim.device, self.sim.num_envs
+        self.obs_carry = torch.zeros((n, self.sim.obs_dim), device=dev)
+        self.rew = torch.zeros(n, device=dev)
+        self.term = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.cur_rew, self.cur_len = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.ep_stats = torch.zeros(3, device=dev)  # sum of returns, sum of lengths, count of the episodes that ended in this iteration
+        base._log_dict()  # builds the key list / gather index of extras["log"]
+        self.log_keys, self.log_index = list(base._log_keys), base._log_index
+        self.log_sum = torch.zeros(len(self.log_keys), device=dev)
+        self.graph = None
+        self.iterations = 0
+
+    @staticmethod
+    def supported(runner) -> bool:
+        if os.environ.get("H1V2_GRAPH_ROLLOUT", "1") == "0" or not str(runner.device).startswith("cuda"):
+            return False
+        base = getattr(runner.env, "unwrapped", None)
+        sim = getattr(base, "sim", None)
+        return (sim is not None and type(sim).__name__ == "H1v2Sim" and hasattr(sim, "step_into") and not runner.empirical_normalization
+                and runner.privileged is None and not getattr(base, "_curriculum", None) and not getattr(sim.cfg, "cat_enable", 0)
+                and torch.device(runner.device) == sim.device and type(runner.alg.policy).__name__ == "ActorCritic")
+
+    def _body(self):
+        st, pol, alg, sim = self.alg.storage, self.alg.policy, self.alg, self.sim
+        self.ep_stats.zero_(); self.log_sum.zero_()
+        st.obs[0].copy_(self.obs_carry)
+        for t in range(self.T):
+            obs = st.obs[t]
+            mean = pol.actor(obs)
+            value = pol.critic(obs)
+            std = pol.std.expand_as(mean)
+            act = mean + std * torch.randn_like(mean)  # = Normal(mean, std).sample() without torch.normal's host-side check of std (a sync: illegal in capture)
+            logp = (-((act - mean) ** 2) / (2 * std ** 2) - std.log() - 0.9189385332046727).sum(dim=-1)  # Normal(mean, std).log_prob(act).sum(-1)
+            st.critic_obs[t].copy_(obs); st.actions[t].copy_(act); st.values[t].copy_(value); st.logp[t].copy_(logp.view(-1, 1))
+            st.mu[t].copy_(mean); st.sigma[t].copy_(std)
+            a_env = act if self.clip is None else torch.clamp(act, -self.clip, self.clip)
+            nxt = st.obs[t + 1] if t + 1 < self.T else self.obs_carry
+            sim.step_into(a_env.contiguous(), nxt, self.rew, self.term, self.trunc)
+            done = (self.term | self.trunc)
+            r = self.rew + alg.gamma * value.squeeze(1) * self.trunc.float() if self.bootstrap else self.rew
+            st.rewards[t].copy_(r.view(-1, 1)); st.dones[t].copy_(done.view(-1, 1))
+            # logging accumulators (the eager loop's cur_reward_sum / cur_episode_length / ep_infos)
+            d = done.float()
+            self.cur_rew += self.rew; self.cur_len += 1.0
+            self.ep_stats[0] += (self.cur_rew * d).sum(); self.ep_stats[1] += (self.cur_len * d).sum(); self.ep_stats[2] += d.sum()
+            self.cur_rew *= 1.0 - d; self.cur_len *= 1.0 - d
+            self.log_sum += sim.log_buf[self.log_index]
+        st.step = self.T
+
+    def run(self, obs):
+        """One rollout starting from `obs` (only read in the first iteration; afterwards the carried observation is the env's own)."""
+        if self.iterations == 0:
+            self._body()
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.graph = g
+            self.graph.replay()
+            self.alg.storage.step = self.T
+        self.iterations += 1
+        base = self.base
+        base.common_step_counter += self.T
+        base.obs_buf = {"policy": self.obs_carry}
+        base.reward_buf, base.reset_terminated, base.reset_time_outs = self.rew, self.term.bool(), self.trunc.bool()
+        base.reset_buf = base.reset_terminated | base.reset_time_outs
+        return self.obs_carry
+
+    def stats(self):
+        """(episode statistics [sum_return, sum_length, count], {log key: mean over the steps}) -- the one host read of the rollout."""
+        ep = self.ep_stats.tolist()
+        lg = (self.log_sum / self.T).tolist()
+        return ep, dict(zip(self.log_keys, lg))
 
 
 class OnPolicyRunner:
@@ -305,9 +416,28 @@ class OnPolicyRunner:
             self.alg.broadcast_parameters()
         start = self.current_learning_iteration
         tot = start + num_learning_iterations
+        fast = getattr(self, "_fast", None)  # the captured rollout graph survives across learn() calls
+        if fast is None and _GraphRollout.supported(self):
+            fast = self._fast = _GraphRollout(self)
+        if fast is not None:
+            fast.obs_carry.copy_(obs)  # learn() starts from a freshly computed observation (env.get_observations above)
+        self.graph_rollout = fast is not None
+        self.iteration_times = []  # (collection_s, learn_s) of every iteration of this call
         for it in range(start, tot):
             t0 = time.time()
-            with torch.inference_mode():
+            if fast is not None:
+                with torch.inference_mode():
+                    obs = critic_obs = fast.run(obs)
+                    ep, log_means = fast.stats()  # synchronises: the collection time below is that of the finished rollout
+                    if self.log_dir is not None:
+                        ep_infos.append(log_means)
+                        if ep[2] > 0:  # mean return / length of the episodes that ended in this iteration
+                            rewbuffer.clear(); lenbuffer.clear()
+                            rewbuffer.append(ep[0] / ep[2]); lenbuffer.append(ep[1] / ep[2])
+                    t1 = time.time()
+                    self.alg.compute_returns(critic_obs)
+            else:
+              with torch.inference_mode():
                 for _ in range(self.num_steps_per_env):
                     actions = self.alg.act(obs, critic_obs)
                     obs, rewards, dones, infos = self.env.step(actions.to(self.env.device))
@@ -332,6 +462,7 @@ class OnPolicyRunner:
             loss = self.alg.update()
             t2 = time.time()
             self.current_learning_iteration = it
+            self.iteration_times.append((t1 - t0, t2 - t1))
             self._log(it, tot, t1 - t0, t2 - t1, loss, ep_infos, rewbuffer, lenbuffer)
             ep_infos.clear()
             if self.log_dir is not None and not self.disable_logs and it % self.save_interval == 0:

@@ -108,6 +108,42 @@ def test_rsl_rl_ppo_runs_on_the_backend(tmp_path):
     env.close()
 
 
+def test_graph_rollout_equals_the_eager_rollout(tmp_path, monkeypatch):
+    """The runner's CUDA-graph rollout (one graph per iteration: policy forward, sampling, h1v2_step, bootstrap, storage writes) against
+    the eager rsl_rl loop through RslRlVecEnvWrapper.step: the same seeds give the same rollout storage in the first iteration (the
+    graph path runs its body eagerly there), and the replayed graph keeps stepping the same env (step counter, episode lengths,
+    statistics), with finite losses."""
+    import torch
+    from h1v2_isaac_b200 import tasks
+    from isaaclab_rl.rsl_rl import RslRlVecEnvWrapper
+    from rsl_rl.runners import OnPolicyRunner
+    agent = tasks.default_agent_cfg()
+    store = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("H1V2_GRAPH_ROLLOUT", mode)
+        torch.manual_seed(7)
+        env = _make(512)
+        runner = OnPolicyRunner(RslRlVecEnvWrapper(env), agent.to_dict(), log_dir=str(tmp_path / mode), device="cuda:0")
+        runner.learn(num_learning_iterations=1, init_at_random_ep_len=True)
+        assert runner.graph_rollout == (mode == "1")
+        st = runner.alg.storage
+        store[mode] = {k: getattr(st, k).clone() for k in ("obs", "actions", "rewards", "dones", "values", "logp", "mu", "sigma")}
+        if mode == "1":
+            sim = env.unwrapped.sim
+            ep0 = env.unwrapped.episode_length_buf.clone()
+            runner.learn(num_learning_iterations=3)  # iterations 2.. replay the captured graph
+            assert runner.stats["iteration"] == 2 and all(torch.isfinite(p).all() for p in runner.alg.policy.parameters())
+            assert env.unwrapped.common_step_counter == 4 * 24
+            g = sim.get_state(["joint_pos"])["joint_pos"]
+            assert torch.isfinite(g).all() and not torch.equal(env.unwrapped.episode_length_buf, ep0)
+            assert not torch.equal(runner.alg.storage.obs, store["1"]["obs"])  # the replay wrote a new rollout
+            assert "episode/Episode_Reward/track_lin_vel_xy_exp" in runner.stats and runner.stats["mean_episode_length"] > 0
+        env.close()
+    for k in store["0"]:
+        a, b = store["0"][k].float(), store["1"][k].float()
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (k, float((a - b).abs().max()))
+
+
 def test_rank_shards_are_slices_of_one_job(cfg):
     """Multi-GPU sharding rule: a handle created with env_id_offset = r*n reproduces envs
     [r*n, (r+1)*n) of a single 2n-env handle bit for bit -- reset draws, noise, resamples -- with no exchange."""
