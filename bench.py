@@ -257,13 +257,16 @@ def run_ours(args):
         hterm = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
         htrunc = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
         Ke = max(10, min(K, 100))
+        if is_cat:  # h1v2_cat_step_host: float dones instead of the terminated flags
+            hterm = torch.empty(n_envs, dtype=torch.float32).pin_memory()
+        host_step = sim_.cat_step_host if is_cat else sim_.step_host
         for i in range(5):
-            sim_.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)
+            host_step(ha[i % 4], hobs, hrew, hterm, htrunc)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
-            sim_.step_host(ha[i % 4], hobs, hrew, hterm, htrunc)  # synchronises inside
+            host_step(ha[i % 4], hobs, hrew, hterm, htrunc)  # synchronises inside
         dt = time.perf_counter() - t0
         td = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
@@ -278,7 +281,7 @@ def run_ours(args):
                               "rows_bytes_written_by_host_threads_per_step": n_envs * sim_.obs_dim * 4 if mode == 1 else 0}}
 
     e2e = None
-    if not args.no_e2e and not is_cat:  # h1v2_step_host has no constraint tail: no host-buffer number for --task cat
+    if not args.no_e2e:
         e2e = e2e_run(sim, pool, n)
 
     big = None
@@ -289,7 +292,7 @@ def run_ours(args):
         clocks_b = sampler_b.stop() if sampler_b else None
         kb = max(20, K // 3)
         big = {"envs_per_gpu": 32768, "value": world * 32768 * kb / (ms_b * 1e-3), "unit": METRIC, "ms_per_step": ms_b / kb, "steps": kb,
-               "clocks": clocks_b, "e2e": None if (args.no_e2e or is_cat) else e2e_run(sim_b, pool_b, 32768)}
+               "clocks": clocks_b, "e2e": None if args.no_e2e else e2e_run(sim_b, pool_b, 32768)}
         sim_b.close()
     # ---- BASELINE configs[2] / [3]: the PPO loop of scripts/rsl_rl/train.py:120-141 on this backend (RslRlVecEnvWrapper ->
     #      OnPolicyRunner.learn, random-init ActorCritic [512, 256, 128], 24 steps per env, 5 epochs x 4 mini-batches), with the

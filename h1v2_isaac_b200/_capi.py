@@ -111,6 +111,7 @@ _SYMBOLS = {
     "h1v2_create": (C.c_int, [C.POINTER(H1v2Config), i32, i32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "h1v2_destroy": (None, [C.c_void_p]),
     "h1v2_last_error": (C.c_char_p, []),
+    "h1v2_check_guards": (i64, [C.c_void_p]),
     "h1v2_obs_dim": (C.c_int, [C.c_void_p]),
     "h1v2_num_envs": (C.c_int, [C.c_void_p]),
     "h1v2_bind_episode_length": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -121,6 +122,7 @@ _SYMBOLS = {
     "h1v2_host_path_info": (C.c_int, [C.c_void_p, C.POINTER(i32), C.POINTER(i32)]),
     "h1v2_set_reward_weights": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_cat_step": (C.c_int, [C.c_void_p] * 7),
+    "h1v2_cat_step_host": (C.c_int, [C.c_void_p] * 6),
     "h1v2_set_constraint_max_p": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_cat_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_get_cat_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),

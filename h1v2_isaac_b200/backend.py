@@ -144,6 +144,16 @@ class H1v2Sim:
             return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
         self._check(self._lib.h1v2_step_host(self._h, ptr(actions), ptr(obs), ptr(rew), ptr(term), ptr(trunc)))
 
+    def cat_step_host(self, actions, obs, rew, dones, trunc):
+        """h1v2_cat_step_host: the CaT step with HOST buffers (dones float32 [N])."""
+        def ptr(x):
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        self._check(self._lib.h1v2_cat_step_host(self._h, ptr(actions), ptr(obs), ptr(rew), ptr(dones), ptr(trunc)))
+
+    def check_guards(self) -> int:
+        """Guard bytes around the handle's device arrays that were overwritten (0 = no out-of-bounds store); synchronises."""
+        return int(self._lib.h1v2_check_guards(self._h))
+
     def host_path_info(self):
         """(mode, threads) of step_host: 0 = rows written by the kernel, 1 = samples over PCIe + host assembly, -1 = undecided."""
         m, t = C.c_int32(-1), C.c_int32(0)

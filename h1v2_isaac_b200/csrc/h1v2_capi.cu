@@ -66,7 +66,8 @@ struct H1v2Handle {
   uint64_t seed = 0;
   int64_t launches = 0;
   bool attr_set = false;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;       // base pointers (guard zone first)
+  std::vector<size_t> alloc_bytes;  // payload bytes between the guard zones
   int64_t* own_ep_len = nullptr;
   // staging for h1v2_step_host
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
@@ -85,10 +86,9 @@ struct H1v2Handle {
   struct HostPool* pool = nullptr;
   int host_mode = -1;             // -1 undecided, 0 full rows over PCIe (zero-copy / staged), 1 samples + host assembly
   // Constraints-as-Terminations tail (cfg.cat_enable)
-  CatState cat = {};
-  bool cat_first = true;
-  int cat_parity = 0;
+  CatState cat = {};            // all step-to-step CaT state lives on the device (graph-replayable)
   uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
+  float* d_dones = nullptr;     // staging of h1v2_cat_step_host
   float cat_log[2 * H1V2_NUM_CSTR + 1] = {};
 };
 
@@ -100,7 +100,7 @@ static inline void note_stream(H1v2Handle* h, cudaStream_t st) { h->last_stream 
 // auxiliary kernels (not on the step path)
 // ------------------------------------------------------------------------------------------------------
 __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, const int64_t* __restrict__ ids, int n_ids,
-                             int startup) {
+                             float* cat_sums) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gtid >> 1, side = gtid & 1;
   if (i >= n_ids) return;
@@ -111,7 +111,6 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
   const unsigned long long step = S.counters[0];
   float4 r3 = S.root[3 * N + env];
   real mu = r3.y, mass_add = r3.z, push_left = r3.w;
-  (void)startup;
   real rp[3], rq[4], rv[3], rw[3], q[6], qd[6], la[6], T1[6], T2[6];
   float4 tm;
   CmdState cmd;
@@ -126,6 +125,8 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
     S.cmd[N + env] = make_float4(cmd.time_left, 0.f, 0.f, __int_as_float(cmd.flags));
     S.ep_len[env] = 0;
     for (int k = 0; k < H1V2_EPSUM_F4; k++) S.epsum[(size_t)k * N + env] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cat_sums)  // _reset_idx -> constraint_manager.reset(env_ids) (constraint_manager.py:213-214): the per-term episode sums restart
+      for (int k = 0; k < 2 * H1V2_NUM_CSTR; k++) cat_sums[(size_t)k * N + env] = 0.f;
   }
   S.leg[lidx] = make_float4(q[0], q[1], q[2], q[3]);
   S.leg[N2 + lidx] = make_float4(q[4], q[5], qd[0], qd[1]);
@@ -419,15 +420,23 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   return 0;
 }
 
+// Every device array of a handle sits between two 256-byte guard zones filled with a pattern; h1v2_check_guards counts the guard
+// bytes that no longer hold it.  (compute-sanitizer is closed on the GPU pool this was developed on -- profiles/
+// r2_sanitizer_unavailable.txt -- so out-of-bounds stores are caught this way: tests/test_gpu_env.py.)
+static const size_t kGuard = 256;
+static const unsigned char kGuardByte = 0xA5;
 template <typename T>
 static int dalloc(H1v2Handle* h, T** p, size_t count) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+  unsigned char* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes + 2 * kGuard);
   if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  e = cudaMemset(q, 0, count * sizeof(T));
-  if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+  e = cudaMemset(q, kGuardByte, bytes + 2 * kGuard);
+  if (e == cudaSuccess) e = cudaMemset(q + kGuard, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(q); return fail(std::string("cudaMemset: ") + cudaGetErrorString(e)); }
   h->allocs.push_back(q);
-  *p = (T*)q;
+  h->alloc_bytes.push_back(bytes);
+  *p = (T*)(q + kGuard);
   return 0;
 }
 
@@ -573,20 +582,31 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   rc |= dalloc(h, &h->own_ep_len, N);
   int* lut_d = nullptr;
   rc |= dalloc(h, &lut_d, (size_t)h->P.obs_dim);
-  if (cfg->reserved[0] || cfg->cat_enable) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);  // the CaT tail reads the pre-reset values from it
+  if (cfg->reserved[0]) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);
   if (cfg->cat_enable) {
     CatState& T = h->cat;
-    rc |= dalloc(h, &T.raw, (size_t)H1V2_CSTR_COLS * N);
+    rc |= dalloc(h, &T.k.raw, (size_t)H1V2_CSTR_COLS * N);
+    rc |= dalloc(h, &T.k.qd, (size_t)12 * N);
+    rc |= dalloc(h, &T.k.aux, (size_t)2 * N);
+    rc |= dalloc(h, &T.k.dz, N);
+    rc |= dalloc(h, &T.k.cmax, (size_t)H1V2_CSTR_COLS);
+    rc |= dalloc(h, &T.k.list, N);
+    rc |= dalloc(h, &T.k.ctl, (size_t)4);
+    rc |= dalloc(h, &T.k.swing, 2 * N);
+    rc |= dalloc(h, &T.k.logacc, (size_t)2 * H1V2_NUM_CSTR + 1);
     rc |= dalloc(h, &T.probs, (size_t)H1V2_CSTR_COLS * N);
     rc |= dalloc(h, &T.rmax, (size_t)2 * H1V2_CSTR_COLS);
-    rc |= dalloc(h, &T.cmax, (size_t)H1V2_CSTR_COLS);
-    rc |= dalloc(h, &T.list, N);
-    rc |= dalloc(h, &T.count, (size_t)1);
-    rc |= dalloc(h, &T.chunk_count, (N + 1023) / 1024);
-    rc |= dalloc(h, &T.swing, 2 * N);
     rc |= dalloc(h, &T.sums, (size_t)2 * H1V2_NUM_CSTR * N);
-    rc |= dalloc(h, &T.logacc, (size_t)2 * H1V2_NUM_CSTR + 1);
     rc |= dalloc(h, &h->cat_term, N);
+    if (rc == 0) {  // column maxima start at their floor (constraint.max(0).clamp(min=1e-6)); the apply kernel restores it after every step
+      std::vector<float> floor_v(H1V2_CSTR_COLS, 1e-6f);
+      if (cudaMemcpy(T.k.cmax, floor_v.data(), sizeof(float) * H1V2_CSTR_COLS, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("cudaMemcpy: cat maxima");
+    }
+    T.k.contact_slots = cfg->cat_contact_slots;
+    T.k.foot_force_limit = cfg->cat_foot_force_limit; T.k.no_move_deadzone = cfg->cat_no_move_deadzone; T.k.no_move_vel_limit = cfg->cat_no_move_vel_limit;
+    T.k.orientation_limit = cfg->cat_orientation_limit; T.k.height = cfg->cat_height; T.k.height_std = cfg->cat_height_std;
+    T.k.clearance_min_height = cfg->cat_clearance_min_height; T.k.clearance_deadzone = cfg->cat_clearance_deadzone;
+    T.k.vel_limit = cfg->joint_vel_limit;
   }
   if (rc != 0) { h1v2_destroy(h); return -1; }
   S.ep_len = h->own_ep_len;
@@ -603,7 +623,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   CKH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   CKH(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
   startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
-  reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, 0);
+  reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, h->cat.sums);
   h->launches += 2;
   CKH(cudaGetLastError());
   CKH(cudaDeviceSynchronize());
@@ -616,7 +636,7 @@ void h1v2_destroy(H1v2Handle* h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
-  for (void* p : {(void*)h->d_act, (void*)h->d_obs, (void*)h->d_rew, (void*)h->d_term, (void*)h->d_trunc})
+  for (void* p : {(void*)h->d_act, (void*)h->d_obs, (void*)h->d_rew, (void*)h->d_term, (void*)h->d_trunc, (void*)h->d_dones})
     if (p) cudaFree(p);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
@@ -624,6 +644,23 @@ void h1v2_destroy(H1v2Handle* h) {
   if (h->h_sample) cudaFreeHost(h->h_sample);
   std::free(h->h_ring);
   delete h;
+}
+
+int64_t h1v2_check_guards(H1v2Handle* h) {
+  if (!h) return -1;
+  DeviceGuard guard(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) { fail("h1v2_check_guards: device error before the check"); return -1; }
+  int64_t bad = 0;
+  unsigned char buf[2 * 256];
+  for (size_t i = 0; i < h->allocs.size(); i++) {
+    const unsigned char* q = (const unsigned char*)h->allocs[i];
+    if (cudaMemcpy(buf, q, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(buf + kGuard, q + kGuard + h->alloc_bytes[i], kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fail("h1v2_check_guards: cudaMemcpy failed");
+      return -1;
+    }
+    for (size_t k = 0; k < 2 * kGuard; k++) bad += buf[k] != kGuardByte;
+  }
+  return bad;
 }
 
 int h1v2_obs_dim(const H1v2Handle* h) { return h ? h->P.obs_dim : -1; }
@@ -648,7 +685,7 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int cnt = env_ids ? n : h->n;
   if (cnt <= 0) return 0;
-  reset_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(h->P, h->S, env_ids, cnt, 0);
+  reset_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(h->P, h->S, env_ids, cnt, h->cat.sums);
   note_stream(h, st);
   h->launches += 1;
   CK(cudaGetLastError());
@@ -656,10 +693,11 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
 }
 
 static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st,
-                       float* sample_out = nullptr) {
+                       float* sample_out = nullptr, bool cat = false) {
   DeviceGuard guard(h->device);
   KState S = h->S;
   S.sample_out = sample_out;
+  if (cat) S.cat = h->cat.k;  // the step kernel also leaves the raw constraint columns and their maxima (h1v2_cat_step)
   h->hist_launches += 1;  // every launch advances the history head (device counters[1])
   if (!sample_out) { h->ring_valid = false; note_stream(h, st); }  // the host mirror of the ring misses this launch's sample
   const int threads = H1V2_BLOCK;
@@ -669,9 +707,13 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
-  if (do_step)
+  if (do_step && cat)
+    step_kernel<true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else  // the observe-only launch stages the history rings in the same shared-memory window
     step_kernel<false><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
@@ -690,8 +732,29 @@ int h1v2_step(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8
   return launch_step(h, true, actions, obs, rew, terminated, truncated, (cudaStream_t)cuda_stream);
 }
 
-int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated) {
-  if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step_host: bad arguments");
+}  // extern "C"
+
+static CatParams cat_params(const H1v2Handle* h) {
+  const H1v2Config& c = h->cfg;
+  CatParams C;
+  C.n = h->n;
+  C.tau = c.cat_tau; C.min_p = c.cat_min_p;
+  for (int t = 0; t < H1V2_NUM_CSTR; t++) C.max_p[t] = c.cat_max_p[t];
+  return C;
+}
+static int launch_cat(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* trunc, cudaStream_t st, float* sample_out) {
+  if (launch_step(h, true, actions, obs, rew, h->cat_term, trunc, st, sample_out, true) != 0) return -1;
+  DeviceGuard guard(h->device);
+  cat_apply_kernel<<<(h->n + 63) / 64, 64, 0, st>>>(cat_params(h), h->cat, rew, dones);  // small blocks: at 4096 envs the tail is latency-bound
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// dones != NULL: the Constraints-as-Terminations step (h1v2_cat_step_host); reward and dones are staged through device buffers
+// (the apply kernel rewrites the reward in place), `terminated` is unused
+static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, float* dones, uint8_t* truncated) {
+  const bool cat = dones != nullptr;
   DeviceGuard guard(h->device);
   const size_t N = (size_t)h->n, od = (size_t)h->P.obs_dim;
   cudaStream_t st = h->host_stream;
@@ -718,11 +781,24 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
     CK(cudaMalloc(&h->d_term, N));
     CK(cudaMalloc(&h->d_trunc, N));
   }
-  float* rew_dev = mapped_alias(rew);
-  uint8_t* term_dev = mapped_alias(terminated);
+  const float* act_dev_ = mapped_alias(const_cast<float*>(actions));
+  if (!act_dev_) { CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st)); act_dev_ = h->d_act; }
+  if (cat && !h->d_dones) CK(cudaMalloc(&h->d_dones, N * sizeof(float)));
+  float* rew_dev = cat ? nullptr : mapped_alias(rew);
+  uint8_t* term_dev = cat ? h->cat_term : mapped_alias(terminated);
   uint8_t* trunc_dev = mapped_alias(truncated);
-  const float* act_dev = mapped_alias(const_cast<float*>(actions));
-  if (!act_dev) { CK(cudaMemcpyAsync(h->d_act, actions, N * 12 * sizeof(float), cudaMemcpyHostToDevice, st)); act_dev = h->d_act; }
+  // one launch sequence for both flavours: the plain step, or the step + the constraint apply kernel
+  auto launch = [&](float* obs_arg, float* sample_arg) -> int {
+    if (cat) return launch_cat(h, act_dev_, obs_arg, h->d_rew, h->d_dones, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg);
+    return launch_step(h, true, act_dev_, obs_arg, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg);
+  };
+  auto copy_back = [&]() -> int {
+    if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (cat) CK(cudaMemcpyAsync(dones, h->d_dones, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
+    if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
   if (h->host_mode == 1) {
     const int H = h->P.H;
     const size_t ring_bytes = N * H * H1V2_HIST_STRIDE * sizeof(float);
@@ -741,11 +817,7 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
     }
     HostPool* p = h->pool;
     const int head = (int)((h->hist_launches + 1) % (uint64_t)H);  // the slot this launch writes (step_kernel: counters[1] + 1)
-    if (launch_step(h, true, act_dev, nullptr, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st,
-                    h->h_sample_dev) != 0) return -1;
-    if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
-    if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+    if (launch(nullptr, h->h_sample_dev) != 0 || copy_back() != 0) return -1;
     uint64_t gen;
     {
       std::lock_guard<std::mutex> lk(p->m);
@@ -768,15 +840,24 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
   // serialising a 450-float-per-env D2H copy behind the kernel.  Pageable buffers take the staged path.
   float* obs_dev = mapped_alias(obs);
   if (!obs_dev && !h->d_obs) CK(cudaMalloc(&h->d_obs, N * od * sizeof(float)));
-  if (launch_step(h, true, act_dev, obs_dev ? obs_dev : h->d_obs, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term,
-                  trunc_dev ? trunc_dev : h->d_trunc, st) != 0) return -1;
+  if (launch(obs_dev ? obs_dev : h->d_obs, nullptr) != 0) return -1;
   h->last_stream_set = false;  // nothing of this launch is left in flight after the synchronise below
   if (!obs_dev) CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (!term_dev) CK(cudaMemcpyAsync(terminated, h->d_term, N, cudaMemcpyDeviceToHost, st));
-  if (!trunc_dev) CK(cudaMemcpyAsync(truncated, h->d_trunc, N, cudaMemcpyDeviceToHost, st));
+  if (copy_back() != 0) return -1;
   CK(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" {
+
+int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated) {
+  if (!h || !actions || !obs || !rew || !terminated || !truncated) return fail("h1v2_step_host: bad arguments");
+  return step_host_impl(h, actions, obs, rew, terminated, nullptr, truncated);
+}
+int h1v2_cat_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated) {
+  if (!h || !actions || !obs || !rew || !dones || !truncated) return fail("h1v2_cat_step_host: bad arguments");
+  if (!h->cfg.cat_enable) return fail("h1v2_cat_step_host: the handle was created without cfg.cat_enable");
+  return step_host_impl(h, actions, obs, rew, nullptr, dones, truncated);
 }
 
 int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads) {
@@ -786,38 +867,10 @@ int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads) {
   return 0;
 }
 
-static CatParams cat_params(const H1v2Handle* h) {
-  const H1v2Config& c = h->cfg;
-  CatParams C;
-  C.n = h->n; C.first = h->cat_first ? 1 : 0;
-  C.tau = c.cat_tau; C.min_p = c.cat_min_p;
-  for (int t = 0; t < H1V2_NUM_CSTR; t++) C.max_p[t] = c.cat_max_p[t];
-  C.contact_slots = c.cat_contact_slots;
-  C.foot_force_limit = c.cat_foot_force_limit; C.no_move_deadzone = c.cat_no_move_deadzone; C.no_move_vel_limit = c.cat_no_move_vel_limit;
-  C.orientation_limit = c.cat_orientation_limit; C.height = c.cat_height; C.height_std = c.cat_height_std;
-  C.clearance_min_height = c.cat_clearance_min_height; C.clearance_deadzone = c.cat_clearance_deadzone;
-  C.step_dt = h->P.step_dt; C.vel_limit = c.joint_vel_limit;
-  return C;
-}
-
 int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream) {
   if (!h || !actions || !obs || !rew || !dones || !truncated) return fail("h1v2_cat_step: bad arguments");
   if (!h->cfg.cat_enable) return fail("h1v2_cat_step: the handle was created without cfg.cat_enable");
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  if (launch_step(h, true, actions, obs, rew, h->cat_term, truncated, st) != 0) return -1;
-  DeviceGuard guard(h->device);
-  const CatParams C = cat_params(h);
-  const int blocks = (h->n + 63) / 64;  // small blocks: at 4096 envs the tail is latency-bound, spread it over more SMs
-  const int chunks = (h->n + 1023) / 1024;
-  cat_count_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
-  cat_scan_kernel<<<chunks, 1024, 0, st>>>(h->S.diag, C, h->cat);
-  cat_raw_kernel<<<blocks, 64, 0, st>>>(h->P, h->S.diag, C, h->cat);
-  cat_apply_kernel<<<blocks, 64, 0, st>>>(h->S.diag, C, h->cat, h->cat_parity, rew, dones);
-  h->launches += 4;
-  h->cat_first = false;
-  h->cat_parity ^= 1;
-  CK(cudaGetLastError());
-  return 0;
+  return launch_cat(h, actions, obs, rew, dones, truncated, (cudaStream_t)cuda_stream, nullptr);
 }
 int h1v2_set_constraint_max_p(H1v2Handle* h, const float* max_p) {
   if (!h || !max_p) return fail("h1v2_set_constraint_max_p: bad arguments");
@@ -832,14 +885,18 @@ int h1v2_cat_debug(H1v2Handle* h, float* raw, float* probs, float* running_max) 
   DeviceGuard guard(h->device);
   CK(cudaDeviceSynchronize());
   const size_t cols = (size_t)H1V2_CSTR_COLS * h->n * sizeof(float);
-  if (raw) CK(cudaMemcpy(raw, h->cat.raw, cols, cudaMemcpyDeviceToHost));
+  if (raw) CK(cudaMemcpy(raw, h->cat.k.raw, cols, cudaMemcpyDeviceToHost));
   if (probs) CK(cudaMemcpy(probs, h->cat.probs, cols, cudaMemcpyDeviceToHost));
-  if (running_max) CK(cudaMemcpy(running_max, h->cat.rmax + h->cat_parity * H1V2_CSTR_COLS, sizeof(float) * H1V2_CSTR_COLS, cudaMemcpyDeviceToHost));
+  if (running_max) {
+    int ctl[4];
+    CK(cudaMemcpy(ctl, h->cat.k.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(running_max, h->cat.rmax + (ctl[1] & 1) * H1V2_CSTR_COLS, sizeof(float) * H1V2_CSTR_COLS, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev) {
   if (!h || !acc_dev || !h->cfg.cat_enable) return fail("h1v2_get_cat_log: bad arguments");
-  *acc_dev = h->cat.logacc;
+  *acc_dev = h->cat.k.logacc;
   return 0;
 }
 int h1v2_get_cat_log_host(H1v2Handle* h, float* out) {
@@ -847,7 +904,7 @@ int h1v2_get_cat_log_host(H1v2Handle* h, float* out) {
   DeviceGuard guard(h->device);
   CK(cudaDeviceSynchronize());
   float acc[2 * H1V2_NUM_CSTR + 1];
-  CK(cudaMemcpy(acc, h->cat.logacc, sizeof(acc), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(acc, h->cat.k.logacc, sizeof(acc), cudaMemcpyDeviceToHost));
   const float cnt = acc[2 * H1V2_NUM_CSTR];
   if (cnt > 0.f) {  // upstream writes the keys only in steps with a reset; keep the last such values otherwise
     for (int t = 0; t < 2 * H1V2_NUM_CSTR; t++) h->cat_log[t] = acc[t] / cnt;

@@ -83,6 +83,21 @@ struct KParams {
   int epw;  // envs per warp (1,2,4,8,16): lanes 2*epw..31 shadow the warp's first env (small-N mapping)
 };
 
+// --- Constraints-as-Terminations: what the step kernel leaves for the apply kernel (csrc/h1v2_cat.cuh).  raw == NULL: off ---
+struct KCat {
+  float* raw;      // [56][N] raw constraint columns of this step (the 12 no_move columns are filled in by the apply kernel's gather)
+  float* qd;       // [12][N] pre-reset joint velocities, MJCF order: what no_move gathers from another env
+  float* aux;      // [2][N]  pre-reset episode length | reset flag
+  unsigned short* dz;  // [warps of the step launch] bit p: env warp*epw + p has its whole command inside the no_move dead zone
+  int* cmax;       // [56]    this step's column maxima as float bits (candidates are positive: floor 1e-6)
+  int* list;       // [N]     dead-zone members in ascending env order (built by the step kernel's last block); ctl[0] = how many
+  int* ctl;        // [0] list length K  [1] apply launches done (running-maximum parity, first-step flag)  [2] apply ticket
+  float* swing;    // [2][N]  swing_max_height of foot_clearance
+  float* logacc;   // [21]    sums over the envs reset in this step: violation[10], probability[10], count
+  uint32_t contact_slots;
+  float foot_force_limit, no_move_deadzone, no_move_vel_limit, orientation_limit, height, height_std, clearance_min_height, clearance_deadzone, vel_limit;
+};
+
 // --- internal state, SoA of float4 so that every lane issues coalesced 128-bit accesses ---
 //   lane index l = 2*env + side (side 0 = left leg, 1 = right leg)
 struct KState {
@@ -97,6 +112,7 @@ struct KState {
   const int* lut;  // [obs_dim] (history index << 8) | offset in the 45-float sample, for the term-major flatten
   int64_t* ep_len; // [N] bound, owned by the caller
   float* diag;     // [N][H1V2_DIAG_DIM] or NULL
+  KCat cat;        // Constraints-as-Terminations outputs (raw == NULL unless launched by h1v2_cat_step)
   float* sample_out;  // [N][48] or NULL: this step's observation sample (45) | fresh flag at [45]; the host path of h1v2_step_host assembles the rows from it
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector

@@ -29,7 +29,7 @@ __device__ __forceinline__ RootDerived root_derived(const KParams& P, const real
 // world linear velocity of the ankle_roll_link origin of this lane's leg (body_lin_vel_w of the foot, feet_slide).
 // Rolled over the joints with q / qd staged in the lane's shared-memory column: call it while the column is free
 // (after the physics loop, before the history prefetch).
-__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const real (&q)[6], const real (&qd)[6], bool at_com) {
+__device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const M3& R0, V3 om0, V3 v0, const real (&q)[6], const real (&qd)[6], bool at_com, real& ankle_z) {
   extern __shared__ __align__(16) real smem_raw[];
   const Smem sm{smem_raw + tid};
 #pragma unroll
@@ -48,6 +48,7 @@ __device__ __forceinline__ V3 foot_velocity(const KLeg& LG, unsigned tid, const 
     sincos_lim(sm.jf(i, F_XQ), s_, c_);
     rotate_rt(R, ax, s_, c_);
   }
+  ankle_z = x.z;  // ankle_roll_link origin relative to the pelvis origin, world axes (foot_clearance's body_link_pos_w)
   if (at_com) x = x + mulv(R, ld3(LG.ipos[5]));  // body_lin_vel_w is the velocity of the link's COM (isaaclab ArticulationData)
   return vo + cross(om, x);
 }
@@ -319,9 +320,46 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   }
 }
 
+// Constraints-as-Terminations column maximum (constraint.max(0).clamp(min=1e-6), constraint_manager.py:56): reduce over the lanes
+// of the same side (xor 2..16 keeps the lane parity), then lanes 0 / 1 publish; positive floats order like their bit patterns.
+__device__ __forceinline__ void cat_col_max(int* cmax, int col, real v, bool valid, unsigned tid) {
+  float m = valid ? (float)v : -3.0e38f;
+#pragma unroll
+  for (int o = 2; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+  if ((tid & 31) < 2 && m > 1e-6f) atomicMax(cmax + col, __float_as_int(m));
+}
+
 // publishes the log vector, clears the accumulators, advances the step counter and the history head.
 // Run by the 32 lanes of the LAST block of a step launch to finish (ticket counter S.done): one launch per control step.
-__device__ __forceinline__ void finalize_step(const KState& S, bool do_step, unsigned t) {
+__device__ __forceinline__ void finalize_step(const KState& S, bool do_step, bool cat, unsigned t, int n, int epw) {
+  if (do_step && cat) {
+    // Constraints-as-Terminations: the ordered list of the envs whose command is inside the no_move dead zone (the reference's
+    // boolean-mask gather keeps ascending env order, constraints.py:216-222), from the per-warp member masks the blocks left: every lane
+    // takes a contiguous range of warps, counts, the warp scans the counts, every lane places its members.  Clears the log sums
+    // of the previous step (the apply kernel of THIS step accumulates into them next).
+    const KCat& T = S.cat;
+    if (t < 2 * H1V2_NUM_CSTR + 1) T.logacc[t] = 0.f;
+    const int nw = (n + epw - 1) / epw;  // warps of the step launch, one 16-bit member mask each
+    const int per = (nw + 31) / 32, a = min(nw, (int)t * per), b = min(nw, a + per);
+    int cnt = 0;
+    for (int i = a; i < b; i++) cnt += __popc((unsigned)__ldcg(T.dz + i));
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL_MASK, incl, o);
+      if ((int)t >= o) incl += v;
+    }
+    int w = incl - cnt;
+    for (int i = a; i < b; i++) {
+      unsigned m = (unsigned)__ldcg(T.dz + i);
+      while (m) {
+        const int p = __ffs(m) - 1;
+        m &= m - 1;
+        T.list[w++] = i * epw + p;
+      }
+    }
+    if (t == 31) T.ctl[0] = incl;
+  }
   if (do_step) {
     const real cnt = __ldcg(S.acc + H1V2_LOG_COUNT);
     const real a = __ldcg(S.acc + t);  // t < 32 == H1V2_LOG_DIM
@@ -347,7 +385,8 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, uns
   }
 }
 
-template <bool DO_STEP>
+// CAT: the Constraints-as-Terminations flavour (h1v2_cat_step) is its own instantiation, so the plain step carries none of its code
+template <bool DO_STEP, bool CAT = false>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
@@ -441,6 +480,15 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 6; i++) dg[36 + 6 * side + i] = tau[i];
         }
+        if (CAT && k == P.decimation - 1) {  // joint_torque_limits (constraints.py:55-66) on the applied torque of the last substep
+#pragma unroll
+          for (int i = 0; i < 6; i++) {  // unrolled: tau[] must stay in registers (no dynamically indexed locals in this kernel)
+            const int j = 6 * side + i;
+            const real v = r_abs(tau[i]) - P.effort[j];
+            if (valid) S.cat.raw[(size_t)(25 + j) * N + env] = v;
+            cat_col_max(S.cat.cmax, 25 + j, v, valid, tid);
+          }
+        }
       }
       substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
       use_warm = true;
@@ -471,9 +519,10 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     }
   }
   V3 fv = mk3(0.f, 0.f, 0.f);
+  real ankle_z = 0.f;
   if (DO_STEP) {
     const M3 Rn = quat2mat(rq[0], rq[1], rq[2], rq[3]);
-    fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd, P.foot_vel_com != 0);
+    fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd, P.foot_vel_com != 0, ankle_z);
     __syncwarp();  // every lane is done with its column before the asynchronous copy lands in it
   }
   hist_prefetch(P, S, tid, bid, 0);
@@ -626,6 +675,58 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       term[env] = (uint8_t)(contact != 0);
       trunc[env] = (uint8_t)time_out;
     }
+    if (CAT) {
+      // ---- Constraints-as-Terminations: the raw constraint columns of this step on the pre-reset state, coalesced [56][N], and their
+      //      maxima (T/utils/cat/constraints.py:22-308, parameters C12/cat_env_cfg.py:336-431).  The apply kernel turns them into
+      //      probabilities once the maxima of ALL envs are known; the 12 no_move columns need another env's joint velocities and are
+      //      gathered there -- their maxima are known here: the gather tiles the dead-zone members over the batch, so every member
+      //      appears (constraints.py:209-231). ----
+      const KCat& T = S.cat;
+      const real dzn = T.no_move_deadzone;
+      const bool in_dz = r_abs(cmd.c[0]) < dzn && r_abs(cmd.c[1]) < dzn && r_abs(cmd.c[2]) < dzn;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int j = 6 * side + k;
+        const real vp = r_max(P.soft_lo[j] - q[k], q[k] - P.soft_hi[j]);   // joint_position_limits :22-31
+        const real vv = r_abs(qd[k]) - T.vel_limit;                         // joint_velocity_limits :40-52
+        if (valid) { T.raw[(size_t)(1 + j) * N + env] = vp; T.raw[(size_t)(13 + j) * N + env] = vv; T.qd[(size_t)j * N + env] = qd[k]; }
+        cat_col_max(T.cmax, 1 + j, vp, valid, tid);
+        cat_col_max(T.cmax, 13 + j, vv, valid, tid);
+        cat_col_max(T.cmax, 39 + j, r_abs(qd[k]) - T.no_move_vel_limit, valid && in_dz, tid);  // no_move :209-231
+      }
+      const real vf = C_foot - T.foot_force_limit;                          // foot_contact_force :161-168
+      if (valid) T.raw[(size_t)(37 + side) * N + env] = vf;
+      cat_col_max(T.cmax, 37 + side, vf, valid, tid);
+      {                                                                      // foot_clearance :268-308
+        const real dzc = T.clearance_deadzone;
+        const real active = (r_abs(cmd.c[0]) > dzc || r_abs(cmd.c[1]) > dzc || r_abs(cmd.c[2]) > dzc) ? 1.f : 0.f;
+        const bool touchdown = tm.z > 0.f && tm.z < P.step_dt + 1.0e-8f;
+        const real sw = valid ? T.swing[(size_t)side * N + env] : 0.f;
+        const real vc = (T.clearance_min_height - sw) * (touchdown ? 1.f : 0.f) * active;
+        if (valid) { T.raw[(size_t)(54 + side) * N + env] = vc; T.swing[(size_t)side * N + env] = touchdown ? 0.f : r_max(sw, rp[2] + ankle_z); }
+        cat_col_max(T.cmax, 54 + side, vc, valid, tid);
+      }
+      int anyc = (((T.contact_slots >> side) & 1u) && C_foot > 1.0f) || (((T.contact_slots >> (2 + side)) & 1u) && C_shin > 1.0f) ||
+                 (((T.contact_slots >> 4) & 1u) && C_torso > 1.0f) || (((T.contact_slots >> 5) & 1u) && C_pelvis > 1.0f);
+      anyc |= __shfl_xor_sync(FULL_MASK, anyc, 1);
+      const int nfeet = (C_foot > 1.0f) + __shfl_xor_sync(FULL_MASK, (int)(C_foot > 1.0f), 1);
+      const real v0 = anyc ? 1.f : 0.f;                                                         // contact :86-99
+      const real v51 = r_sqrt(rd.g.x * rd.g.x + rd.g.y * rd.g.y) - T.orientation_limit;        // base_orientation :234-246
+      const real v52 = (rp[2] < T.height - T.height_std || rp[2] > T.height + T.height_std) ? 1.f : 0.f;  // base_height :249-266
+      const real v53 = (nfeet < 1 || nfeet > 2) ? 1.f : 0.f;                                    // foot_contact :171-193
+      if (valid && side == 0) {
+        T.raw[env] = v0; T.raw[(size_t)51 * N + env] = v51; T.raw[(size_t)52 * N + env] = v52; T.raw[(size_t)53 * N + env] = v53;
+        T.aux[env] = (float)ep_len; T.aux[(size_t)N + env] = reset ? 1.f : 0.f;
+      }
+      {  // dead-zone members of this warp as a bit mask (bit p = env warp_env0 + p): the even lanes' ballot bits, packed
+        unsigned m = __ballot_sync(FULL_MASK, in_dz && valid && side == 0) & 0x55555555u;
+        m = (m | (m >> 1)) & 0x33333333u; m = (m | (m >> 2)) & 0x0f0f0f0fu; m = (m | (m >> 4)) & 0x00ff00ffu; m = (m | (m >> 8)) & 0x0000ffffu;
+        if ((tid & 31) == 0) T.dz[bid] = (unsigned short)m;
+      }
+      const bool v0side = valid && side == 0;
+      cat_col_max(T.cmax, 0, v0, v0side, tid); cat_col_max(T.cmax, 51, v51, v0side, tid);
+      cat_col_max(T.cmax, 52, v52, v0side, tid); cat_col_max(T.cmax, 53, v53, v0side, tid);
+    }
     const int novf_pair = novf + __shfl_xor_sync(FULL_MASK, novf, 1);
     if (S.diag && valid) {
       float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
@@ -751,7 +852,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   ticket = __shfl_sync(FULL_MASK, ticket, 0);
   if (ticket == gridDim.x - 1) {
     __threadfence();
-    finalize_step(S, DO_STEP, tid);
+    finalize_step(S, DO_STEP, CAT, tid, P.n, P.epw);
   }
 }
 

@@ -73,6 +73,14 @@ def cat_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
     return env_cfg_from_config(cat_config(), num_envs, device, rew_names=CAT_REW_NAMES)
 
 
+def cat_play_env_cfg(num_envs: int = 100, device: str = "cuda:0"):
+    """Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0 (C12/cat_env_cfg.py:568-583): 100 envs, every command range (0, 0)."""
+    c = cat_config()
+    for r in (c.cmd_lin_x, c.cmd_lin_y, c.cmd_ang_z):
+        r[0] = r[1] = 0.0
+    return env_cfg_from_config(c, num_envs, device, rew_names=CAT_REW_NAMES)
+
+
 def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_names=None, curriculum=(), curriculum_steps=0):
     """Inverse of env.flatten_cfg: an H1v2Config -> a ManagerBasedRLEnvCfg-shaped tree built from the shim cfg classes."""
     from . import shims
@@ -266,16 +274,17 @@ def register() -> bool:
     import gymnasium as gym
     done = False
     for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg"), (CAT_TASK_ID, "cat_env_cfg"),
-                         (TASK_ID.replace("-v0", "-Play-v0"), "flat_play_env_cfg"), (RSL_TASK_ID.replace("-v0", "-Play-v0"), "rsl_play_env_cfg")):
+                         (TASK_ID.replace("-v0", "-Play-v0"), "flat_play_env_cfg"), (RSL_TASK_ID.replace("-v0", "-Play-v0"), "rsl_play_env_cfg"),
+                         (CAT_TASK_ID.replace("-v0", "-Play-v0"), "cat_play_env_cfg")):  # C12/__init__.py:76-82
         try:
             gym.spec(tid)
             continue
         except Exception:
             pass
         # both ids use the same runner cfg (C12/__init__.py:47,91: rsl_rl_ppo_cfg:H12_12dof_FlatPPORunnerCfg)
-        gym.register(id=tid, entry_point="h1v2_isaac_b200.env:" + ("H1v2CaTEnv" if tid == CAT_TASK_ID else "H1v2ManagerBasedRLEnv"), disable_env_checker=True,
+        gym.register(id=tid, entry_point="h1v2_isaac_b200.env:" + ("H1v2CaTEnv" if "CaT" in tid else "H1v2ManagerBasedRLEnv"), disable_env_checker=True,
                      kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}",
-                             **({"clean_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:cat_agent_cfg"} if tid == CAT_TASK_ID  # C12/__init__.py:63-71
+                             **({"clean_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:cat_agent_cfg"} if "CaT" in tid  # C12/__init__.py:63-82
                                 else {"rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})})
         done = True
     return done

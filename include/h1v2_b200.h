@@ -271,6 +271,9 @@ int h1v2_num_envs(const H1v2Handle* h);
 /* episode_length_buf: int64[N] device buffer owned by the caller, read and written by every step.  Binding copies the current
  * counters into it; NULL un-binds (the counters move back into the handle).  Synchronises the device (rare call). */
 int h1v2_bind_episode_length(H1v2Handle* h, int64_t* episode_length);
+/* Debug aid: every device array of the handle lies between two 256-byte guard zones; returns how many guard bytes have been
+ * overwritten (0 = no out-of-bounds store so far), -1 on error.  Synchronises the device. */
+int64_t h1v2_check_guards(H1v2Handle* h);
 
 /* Reset envs.  env_ids == NULL resets all.  No observation is produced (use h1v2_observe). */
 int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stream);
@@ -299,8 +302,13 @@ int h1v2_set_reward_weights(H1v2Handle* h, const float* weights);
 
 /* Constraints-as-Terminations step (CaTEnv.step, utils/cat/cat_env.py:95-193): h1v2_step followed by the constraint tail --
  * rew is scaled by 1 - p, dones[N] (float) = p, and 1 for envs that reset; truncated as in h1v2_step.  Needs cfg.cat_enable.
- * Five launches (step, two passes of the dead-zone gather, constraint columns + their maxima over all envs, probabilities). */
+ * Two launches: the fused step kernel also computes the raw constraint columns, their maxima over all envs and the ordered
+ * dead-zone list; one apply kernel turns them into probabilities (the maxima of ALL envs must be known first).  Every piece of
+ * step-to-step state (running maxima, their parity, the first-step flag) lives on the device: CUDA-graph capturable like
+ * h1v2_step (a captured step keeps the max_p of capture time). */
 int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream);
+/* Same with HOST buffers (the CaT flavour of h1v2_step_host: same two observation paths, synchronises). */
+int h1v2_cat_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated);
 /* curriculums.modify_constraint_p (utils/cat/curriculums.py:20-42): new maximum probabilities, host array [H1V2_NUM_CSTR] */
 int h1v2_set_constraint_max_p(H1v2Handle* h, const float* max_p);
 /* host copies (synchronises): raw constraint columns and probabilities of the last cat step [H1V2_CSTR_COLS][N], the running

@@ -28,9 +28,9 @@ for TASK, name in (("Isaac-Velocity-Flat-H12_12dof-v0", "flat_cfg_resolved.json"
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote", name)
 
-# the two Play ids (C12/flat_env_cfg.py:51-66, C12/rsl_env_cfg.py:543-564): flattened kernel config only
+# the three Play ids (C12/flat_env_cfg.py:51-66, C12/rsl_env_cfg.py:543-564, C12/cat_env_cfg.py:568-583): flattened kernel config only
 play = {}
-for TASK in ("Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0"):
+for TASK in ("Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0"):
     env_cfg = load_cfg_from_registry(TASK, "env_cfg_entry_point")
     play[TASK] = {"num_envs": env_cfg.scene.num_envs, "kernel_config": config_to_dict(flatten_cfg(env_cfg))}
 with open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json"), "w") as f:

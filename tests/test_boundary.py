@@ -98,13 +98,18 @@ def test_self_contained_play_ids_equal_the_reference_play_cfgs():
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))
     tasks.register()
     import gymnasium as gym
-    for tid, make in (("Isaac-Velocity-Flat-H12_12dof-Play-v0", tasks.flat_play_env_cfg), ("Isaac-Velocity-Rsl-H12_12dof-Play-v0", tasks.rsl_play_env_cfg)):
+    for tid, make in (("Isaac-Velocity-Flat-H12_12dof-Play-v0", tasks.flat_play_env_cfg), ("Isaac-Velocity-Rsl-H12_12dof-Play-v0", tasks.rsl_play_env_cfg),
+                      ("Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0", tasks.cat_play_env_cfg)):
         tree = make()
         mine = config_to_dict(flatten_cfg(tree))
         assert tree.scene.num_envs == gold[tid]["num_envs"]
         for k, v in gold[tid]["kernel_config"].items():
             assert _close(mine[k], v), (tid, k)
-        assert mine["enable_corruption"] == 0 and mine["push_enable"] == 0
+        if "CaT" in tid:  # C12/cat_env_cfg.py:568-583 only shrinks the scene and zeroes the command ranges
+            assert mine["cat_enable"] == 1 and mine["cmd_lin_x"] == [0.0, 0.0] and mine["cmd_ang_z"] == [0.0, 0.0]
+            assert gym.spec(tid).entry_point.endswith("H1v2CaTEnv")
+        else:
+            assert mine["enable_corruption"] == 0 and mine["push_enable"] == 0
         assert gym.spec(tid).kwargs["env_cfg_entry_point"]
 
 
@@ -177,7 +182,7 @@ def test_reference_cfg_tree_flattens_to_golden():
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json"))) == GOLD_RSL
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "cat_cfg_resolved.json")))["kernel_config"]["cat_enable"] == 1
     assert set(json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))) == {
-        "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0"}
+        "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0"}
 
 
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")

@@ -129,3 +129,51 @@ def test_cat_env_contract_and_constraint_curriculum():
         assert f"Episode_Constraint_violation/{nme}" in keys and f"Episode_Constraint_probability/{nme}" in keys
     assert abs(env.sim.cfg.cat_max_p[1] - 1.0 / (20 + (40 / 120000) * (4 - 20))) < 1e-6
     env.close(); twin.close()
+
+
+@pytest.mark.parametrize("mode", ["rows", "assemble"])
+def test_cat_step_host_and_graph_replay_match_the_device_path(mode, monkeypatch):
+    """h1v2_cat_step_host (HOST buffers, both observation paths) and a CUDA-graph replay of h1v2_cat_step give exactly what eager
+    device-path calls give: every piece of step-to-step CaT state (running maxima, their parity, the first-step flag, the
+    dead-zone list) lives on the device.  An API reset of some envs restarts their per-term episode statistics
+    (_reset_idx -> constraint_manager.reset, constraint_manager.py:185-214)."""
+    import torch
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.backend import H1v2Sim
+    monkeypatch.setenv("H1V2_HOST_PATH", mode)
+    c = tasks.cat_config()
+    n = 768
+    a_sim, b_sim, g_sim = (H1v2Sim(n, c, device="cuda:0", seed=9) for _ in range(3))
+    for s_ in (a_sim, b_sim, g_sim):
+        s_.observe()
+    hobs = torch.empty((n, a_sim.obs_dim)).pin_memory(); hrew = torch.empty(n).pin_memory()
+    hd = torch.empty(n).pin_memory(); hu = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # graph: static input / output tensors, two kernel launches captured
+    act_s = torch.zeros((n, 12), device="cuda")
+    gout = [torch.empty((n, g_sim.obs_dim), device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")]
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    graph = None
+    ids = torch.tensor([0, 3, 700], device="cuda")
+    for step in range(12):
+        act = torch.randn((n, 12), device="cuda", generator=gen) * (6.0 if step % 3 == 0 else 2.0)
+        o, r, d, u = a_sim.cat_step(act)
+        b_sim.cat_step_host(act.cpu().pin_memory(), hobs, hrew, hd, hu)
+        assert torch.equal(o.cpu(), hobs) and torch.equal(r.cpu(), hrew) and torch.equal(d.cpu(), hd) and torch.equal(u.cpu().to(torch.uint8), hu), step
+        act_s.copy_(act)
+        if step < 2:  # eager warm-up (function attributes), then capture once and replay
+            g_sim.cat_step_into(act_s, *gout)
+        else:
+            if graph is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    g_sim.cat_step_into(act_s, *gout)
+            graph.replay()
+        assert torch.equal(o, gout[0]) and torch.equal(r, gout[1]) and torch.equal(d, gout[2]) and torch.equal(u.to(torch.uint8), gout[3]), step
+        if step == 6:
+            for s_ in (a_sim, b_sim, g_sim):
+                s_.reset(ids)
+    la, lb = a_sim.cat_log_host(), b_sim.cat_log_host()
+    assert np.array_equal(la, lb)
+    for s_ in (a_sim, b_sim, g_sim):
+        s_.close()
