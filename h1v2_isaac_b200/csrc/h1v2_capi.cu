@@ -737,7 +737,7 @@ int h1v2_step(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8
 static CatParams cat_params(const H1v2Handle* h) {
   const H1v2Config& c = h->cfg;
   CatParams C;
-  C.n = h->n;
+  C.n = h->n; C.epw = h->P.epw; C.nmask = (h->n + h->P.epw - 1) / h->P.epw;
   C.tau = c.cat_tau; C.min_p = c.cat_min_p;
   for (int t = 0; t < H1V2_NUM_CSTR; t++) C.max_p[t] = c.cat_max_p[t];
   return C;

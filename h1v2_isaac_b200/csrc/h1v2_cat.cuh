@@ -9,8 +9,8 @@
 // launches per control step:
 //   step_kernel<true> (csrc/h1v2_step.cuh, with KState::cat set)  computes the raw constraint columns on the pre-reset state it
 //                     holds in registers, stores them coalesced [56][N], reduces their maxima (warp shuffle + one atomicMax per
-//                     column and warp), keeps the swing-height tracker, flags the dead-zone members; its last block orders
-//                     them into the gather list
+//                     column and warp), keeps the swing-height tracker, flags the dead-zone members (one bit mask per warp); its last block adds the
+//                     prefix sums that address them by rank
 //   cat_apply_kernel  thread per env: the no_move gather, running maxima, probabilities, p = max, reward *= 1 - p, dones,
 //                     per-term episode statistics, log; its last block advances the step parity and clears the maxima
 // All step-to-step state (running maxima, their parity, the first-step flag) lives on the device, so a captured CUDA graph of
@@ -21,7 +21,7 @@
 namespace h1v2 {
 
 struct CatParams {
-  int n;
+  int n, epw, nmask;  // envs, envs per warp of the step launch, number of member masks (= its warps)
   float tau, min_p, max_p[H1V2_NUM_CSTR];
 };
 struct CatState {
@@ -55,22 +55,39 @@ __global__ void __launch_bounds__(64) cat_apply_kernel(const CatParams C, const 
   if (env < N) {
     const bool reset = Kc.aux[(size_t)N + env] != 0.f;
     const float inv_len = 1.f / fmaxf(Kc.aux[env], 1.f);
+    // Two phases -- every load first, then the arithmetic and the stores: raw / probs / sums may alias as far as the compiler knows,
+    // so a load placed after a store waits for it; interleaved, the 56 columns were 56 serialised L2 round trips (25 us at 4096 envs).
+    float v[H1V2_CSTR_COLS], sv_[H1V2_NUM_CSTR], sp_[H1V2_NUM_CSTR];
     // no_move (constraints.py:209-231): env i is judged on the joint velocities of dead-zone member i mod K
     const int K = __ldcg(Kc.ctl);
-    const int src = K > 0 ? __ldcg(Kc.list + env % K) : env;
+    int src = env;
+    if (K > 0) {  // member number r of the ascending dead-zone list: first mask whose inclusive prefix exceeds r, then the bit inside it
+      const int r = env % K;
+      int lo = 0, hi = C.nmask - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldcg(Kc.list + mid) > r) hi = mid; else lo = mid + 1;
+      }
+      const unsigned m = (unsigned)__ldcg(Kc.dz + lo);
+      const int within = r - (__ldcg(Kc.list + lo) - __popc(m));
+      src = lo * C.epw + (int)__fns(m, 0, within + 1);
+    }
 #pragma unroll
-    for (int j = 0; j < 12; j++)
-      Kc.raw[(size_t)(39 + j) * N + env] = K > 0 ? fabsf(Kc.qd[(size_t)j * N + src]) - Kc.no_move_vel_limit : 0.f;
+    for (int c = 0; c < H1V2_CSTR_COLS; c++)
+      v[c] = (c >= 39 && c < 51) ? (K > 0 ? fabsf(__ldcg(Kc.qd + (size_t)(c - 39) * N + src)) - Kc.no_move_vel_limit : 0.f) : __ldcg(Kc.raw + (size_t)c * N + env);
+#pragma unroll
+    for (int t = 0; t < H1V2_NUM_CSTR; t++) { sv_[t] = T.sums[(size_t)t * N + env]; sp_[t] = T.sums[(size_t)(H1V2_NUM_CSTR + t) * N + env]; }
+    const float rew_in = rew[env];
     float tmax[H1V2_NUM_CSTR];
 #pragma unroll
     for (int t = 0; t < H1V2_NUM_CSTR; t++) tmax[t] = 0.f;
 #pragma unroll
-    for (int c = 0; c < H1V2_CSTR_COLS; c++) {  // independent loads: the compiler keeps them all in flight
+    for (int c = 0; c < H1V2_CSTR_COLS; c++) {
       const int t = cstr_term_of_col(c);
-      const float v = Kc.raw[(size_t)c * N + env];
       float pc = 0.f;
-      if (v > 0.f) pc = C.min_p + fminf(fmaxf(__fdiv_rn(v, rm_s[c]), 0.f), 1.f) * (C.max_p[t] - C.min_p);  // :70-77
+      if (v[c] > 0.f) pc = C.min_p + fminf(fmaxf(__fdiv_rn(v[c], rm_s[c]), 0.f), 1.f) * (C.max_p[t] - C.min_p);  // :70-77
       T.probs[(size_t)c * N + env] = pc;
+      if (c >= 39 && c < 51) Kc.raw[(size_t)c * N + env] = v[c];  // kept for h1v2_cat_debug
       tmax[t] = fmaxf(tmax[t], pc);
     }
     float p = 0.f;
@@ -78,8 +95,8 @@ __global__ void __launch_bounds__(64) cat_apply_kernel(const CatParams C, const 
     for (int t = 0; t < H1V2_NUM_CSTR; t++) {
       p = fmaxf(p, tmax[t]);
       // per-term episode statistics (constraint_manager.py:221-227) and their log on reset (:185-203)
-      float sv = T.sums[(size_t)t * N + env] + (tmax[t] > 0.f ? 1.f : 0.f);
-      float sp = T.sums[(size_t)(H1V2_NUM_CSTR + t) * N + env] + tmax[t];
+      float sv = sv_[t] + (tmax[t] > 0.f ? 1.f : 0.f);
+      float sp = sp_[t] + tmax[t];
       if (reset) {
         atomicAdd(Kc.logacc + t, sv * inv_len * 100.f);
         atomicAdd(Kc.logacc + H1V2_NUM_CSTR + t, sp * inv_len);
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(64) cat_apply_kernel(const CatParams C, const 
       T.sums[(size_t)(H1V2_NUM_CSTR + t) * N + env] = sp;
     }
     if (reset) atomicAdd(Kc.logacc + 2 * H1V2_NUM_CSTR, 1.f);
-    rew[env] *= 1.f - p;             // cat_env.py:152
+    rew[env] = rew_in * (1.f - p);   // cat_env.py:152
     dones[env] = reset ? 1.f : p;    // :153,167
   }
   // the last block to finish closes the step: parity / first-step flag advance, column maxima back to their floor

@@ -90,7 +90,7 @@ struct KCat {
   float* aux;      // [2][N]  pre-reset episode length | reset flag
   unsigned short* dz;  // [warps of the step launch] bit p: env warp*epw + p has its whole command inside the no_move dead zone
   int* cmax;       // [56]    this step's column maxima as float bits (candidates are positive: floor 1e-6)
-  int* list;       // [N]     dead-zone members in ascending env order (built by the step kernel's last block); ctl[0] = how many
+  int* list;       // [warps] inclusive prefix of the dead-zone member counts per warp mask (the step kernel's last block); ctl[0] = total K
   int* ctl;        // [0] list length K  [1] apply launches done (running-maximum parity, first-step flag)  [2] apply ticket
   float* swing;    // [2][N]  swing_max_height of foot_clearance
   float* logacc;   // [21]    sums over the envs reset in this step: violation[10], probability[10], count

@@ -322,40 +322,68 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
 
 // Constraints-as-Terminations column maximum (constraint.max(0).clamp(min=1e-6), constraint_manager.py:56): reduce over the lanes
 // of the same side (xor 2..16 keeps the lane parity), then lanes 0 / 1 publish; positive floats order like their bit patterns.
-__device__ __forceinline__ void cat_col_max(int* cmax, int col, real v, bool valid, unsigned tid) {
-  float m = valid ? (float)v : -3.0e38f;
+// Constraints-as-Terminations column maxima (constraint.max(0).clamp(min=1e-6), constraint_manager.py:56).  A candidate only
+// matters when it is positive, and positive floats order like their bit patterns: redux.sync (one instruction) over the lanes
+// of the same side; the result is then PUBLISHED BY DIFFERENT LANES FOR DIFFERENT COLUMNS (lane 2 i + side takes the i-th
+// column of its side), so a warp's 56 filtered atomics go out in two or three parallel rounds instead of 56 dependent round
+// trips of lanes 0 / 1 (24 us of a 0.84 ms step at 32768 envs).  All warps of a launch aim at the same 56 words: publish only what
+// beats the maximum seen so far (a stale read only costs a redundant atomic).
+struct CatMax {
+  unsigned v[3];   // this lane's column values of rounds 0..2 (bit patterns of max(value, 0))
+  int col[3];
+  int n;           // columns seen so far on this lane's side
+};
+__device__ __forceinline__ void cat_max_init(CatMax& M) { M.n = 0; M.v[0] = M.v[1] = M.v[2] = 0u; M.col[0] = M.col[1] = M.col[2] = 0; }
+__device__ __forceinline__ void cat_col_max(CatMax& M, int col, real v, bool valid, unsigned tid) {
+  const unsigned bits = (valid && v > 0.f) ? (unsigned)__float_as_int((float)v) : 0u;
+  const unsigned m = __reduce_max_sync((tid & 1) ? 0xaaaaaaaau : 0x55555555u, bits);
+  const int slot = M.n & 15, round = M.n >> 4;  // compile-time after unrolling
+  if ((int)((tid & 31) >> 1) == slot) { M.v[round] = m; M.col[round] = col; }
+  M.n++;
+}
+__device__ __forceinline__ void cat_max_publish(const CatMax& M, int* cmax) {
 #pragma unroll
-  for (int o = 2; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
-  if ((tid & 31) < 2 && m > 1e-6f) atomicMax(cmax + col, __float_as_int(m));
+  for (int r = 0; r < 3; r++)
+    if (M.v[r] > (unsigned)__float_as_int(1e-6f) && (int)M.v[r] > __ldcg(cmax + M.col[r])) atomicMax(cmax + M.col[r], (int)M.v[r]);
 }
 
 // publishes the log vector, clears the accumulators, advances the step counter and the history head.
 // Run by the 32 lanes of the LAST block of a step launch to finish (ticket counter S.done): one launch per control step.
 __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, bool cat, unsigned t, int n, int epw) {
   if (do_step && cat) {
-    // Constraints-as-Terminations: the ordered list of the envs whose command is inside the no_move dead zone (the reference's
-    // boolean-mask gather keeps ascending env order, constraints.py:216-222), from the per-warp member masks the blocks left: every lane
-    // takes a contiguous range of warps, counts, the warp scans the counts, every lane places its members.  Clears the log sums
-    // of the previous step (the apply kernel of THIS step accumulates into them next).
+    // Constraints-as-Terminations: the envs whose command is inside the no_move dead zone, in ascending env order (the reference's
+    // boolean-mask gather, constraints.py:216-222), are addressed by rank: the blocks left one member mask per warp, this block adds
+    // the inclusive prefix of their populations; the apply kernel finds member r by a binary search over the prefix and a bit select.
+    // Clears the log sums of the previous step (the apply kernel of THIS step accumulates into them next).
     const KCat& T = S.cat;
     if (t < 2 * H1V2_NUM_CSTR + 1) T.logacc[t] = 0.f;
     const int nw = (n + epw - 1) / epw;  // warps of the step launch, one 16-bit member mask each
+    // every lane takes a contiguous range of masks; loads are issued eight at a time (a dependent walk through global memory
+    // was a 30 us tail of this single warp at 32768 envs, profiles/r2_notes.md)
     const int per = (nw + 31) / 32, a = min(nw, (int)t * per), b = min(nw, a + per);
     int cnt = 0;
-    for (int i = a; i < b; i++) cnt += __popc((unsigned)__ldcg(T.dz + i));
+    for (int i0 = a; i0 < b; i0 += 8) {
+      unsigned m[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) m[k] = (i0 + k < b) ? (unsigned)__ldcg(T.dz + i0 + k) : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) cnt += __popc(m[k]);
+    }
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(FULL_MASK, incl, o);
       if ((int)t >= o) incl += v;
     }
-    int w = incl - cnt;
-    for (int i = a; i < b; i++) {
-      unsigned m = (unsigned)__ldcg(T.dz + i);
-      while (m) {
-        const int p = __ffs(m) - 1;
-        m &= m - 1;
-        T.list[w++] = i * epw + p;
+    int run = incl - cnt;
+    for (int i0 = a; i0 < b; i0 += 8) {
+      unsigned m[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) m[k] = (i0 + k < b) ? (unsigned)__ldcg(T.dz + i0 + k) : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        run += __popc(m[k]);
+        if (i0 + k < b) T.list[i0 + k] = run;  // members in the masks 0..i (inclusive prefix)
       }
     }
     if (t == 31) T.ctl[0] = incl;
@@ -481,13 +509,16 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           for (int i = 0; i < 6; i++) dg[36 + 6 * side + i] = tau[i];
         }
         if (CAT && k == P.decimation - 1) {  // joint_torque_limits (constraints.py:55-66) on the applied torque of the last substep
+          CatMax CM;
+          cat_max_init(CM);
 #pragma unroll
           for (int i = 0; i < 6; i++) {  // unrolled: tau[] must stay in registers (no dynamically indexed locals in this kernel)
             const int j = 6 * side + i;
             const real v = r_abs(tau[i]) - P.effort[j];
             if (valid) S.cat.raw[(size_t)(25 + j) * N + env] = v;
-            cat_col_max(S.cat.cmax, 25 + j, v, valid, tid);
+            cat_col_max(CM, 25 + j, v, valid, tid);
           }
+          cat_max_publish(CM, S.cat.cmax);
         }
       }
       substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
@@ -682,6 +713,8 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       //      gathered there -- their maxima are known here: the gather tiles the dead-zone members over the batch, so every member
       //      appears (constraints.py:209-231). ----
       const KCat& T = S.cat;
+      CatMax CM;
+      cat_max_init(CM);
       const real dzn = T.no_move_deadzone;
       const bool in_dz = r_abs(cmd.c[0]) < dzn && r_abs(cmd.c[1]) < dzn && r_abs(cmd.c[2]) < dzn;
 #pragma unroll
@@ -690,13 +723,13 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         const real vp = r_max(P.soft_lo[j] - q[k], q[k] - P.soft_hi[j]);   // joint_position_limits :22-31
         const real vv = r_abs(qd[k]) - T.vel_limit;                         // joint_velocity_limits :40-52
         if (valid) { T.raw[(size_t)(1 + j) * N + env] = vp; T.raw[(size_t)(13 + j) * N + env] = vv; T.qd[(size_t)j * N + env] = qd[k]; }
-        cat_col_max(T.cmax, 1 + j, vp, valid, tid);
-        cat_col_max(T.cmax, 13 + j, vv, valid, tid);
-        cat_col_max(T.cmax, 39 + j, r_abs(qd[k]) - T.no_move_vel_limit, valid && in_dz, tid);  // no_move :209-231
+        cat_col_max(CM, 1 + j, vp, valid, tid);
+        cat_col_max(CM, 13 + j, vv, valid, tid);
+        cat_col_max(CM, 39 + j, r_abs(qd[k]) - T.no_move_vel_limit, valid && in_dz, tid);  // no_move :209-231
       }
       const real vf = C_foot - T.foot_force_limit;                          // foot_contact_force :161-168
       if (valid) T.raw[(size_t)(37 + side) * N + env] = vf;
-      cat_col_max(T.cmax, 37 + side, vf, valid, tid);
+      cat_col_max(CM, 37 + side, vf, valid, tid);
       {                                                                      // foot_clearance :268-308
         const real dzc = T.clearance_deadzone;
         const real active = (r_abs(cmd.c[0]) > dzc || r_abs(cmd.c[1]) > dzc || r_abs(cmd.c[2]) > dzc) ? 1.f : 0.f;
@@ -704,7 +737,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         const real sw = valid ? T.swing[(size_t)side * N + env] : 0.f;
         const real vc = (T.clearance_min_height - sw) * (touchdown ? 1.f : 0.f) * active;
         if (valid) { T.raw[(size_t)(54 + side) * N + env] = vc; T.swing[(size_t)side * N + env] = touchdown ? 0.f : r_max(sw, rp[2] + ankle_z); }
-        cat_col_max(T.cmax, 54 + side, vc, valid, tid);
+        cat_col_max(CM, 54 + side, vc, valid, tid);
       }
       int anyc = (((T.contact_slots >> side) & 1u) && C_foot > 1.0f) || (((T.contact_slots >> (2 + side)) & 1u) && C_shin > 1.0f) ||
                  (((T.contact_slots >> 4) & 1u) && C_torso > 1.0f) || (((T.contact_slots >> 5) & 1u) && C_pelvis > 1.0f);
@@ -724,8 +757,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
         if ((tid & 31) == 0) T.dz[bid] = (unsigned short)m;
       }
       const bool v0side = valid && side == 0;
-      cat_col_max(T.cmax, 0, v0, v0side, tid); cat_col_max(T.cmax, 51, v51, v0side, tid);
-      cat_col_max(T.cmax, 52, v52, v0side, tid); cat_col_max(T.cmax, 53, v53, v0side, tid);
+      cat_col_max(CM, 0, v0, v0side, tid); cat_col_max(CM, 51, v51, v0side, tid);
+      cat_col_max(CM, 52, v52, v0side, tid); cat_col_max(CM, 53, v53, v0side, tid);
+      cat_max_publish(CM, T.cmax);
     }
     const int novf_pair = novf + __shfl_xor_sync(FULL_MASK, novf, 1);
     if (S.diag && valid) {

@@ -2,6 +2,7 @@
 import csv, re, subprocess, sys, collections, os, tempfile
 rep, so = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+KSEL = sys.argv[4] if len(sys.argv) > 4 else "step_kernelILb1ELb0"
 tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(so)} > /dev/null", shell=True, check=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "config" not in f][0]
@@ -10,7 +11,7 @@ amap, cur, insec = {}, None, False
 for l in dis:
     m = re.match(r"\s*\.section\s+\.text\.(\S+),", l)
     if m:
-        insec = "step_kernelILb1" in m.group(1)
+        insec = KSEL in m.group(1)
     if not insec:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)

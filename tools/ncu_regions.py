@@ -4,6 +4,7 @@ usage: python tools/ncu_regions.py <rep> <libh1v2_b200.so>"""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, so = sys.argv[1], sys.argv[2]
+KSEL = sys.argv[3] if len(sys.argv) > 3 else "step_kernelILb1ELb0"  # cubin section of the profiled instantiation (CaT: step_kernelILb1ELb1)
 CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "h1v2_isaac_b200", "csrc")
 
 
@@ -53,7 +54,7 @@ amap, chain, insec, fresh = {}, [], False, True
 for l in dis:
     m = re.match(r"\s*\.section\s+\.text\.(\S+),", l)
     if m:
-        insec = "step_kernelILb1" in m.group(1)
+        insec = KSEL in m.group(1)
     if not insec:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)

@@ -12,7 +12,10 @@ sim.observe()
 obs = torch.empty((n, sim.obs_dim), device='cuda'); rew = torch.empty(n, device='cuda')
 term = torch.empty(n, dtype=torch.uint8, device='cuda'); trunc = torch.empty(n, dtype=torch.uint8, device='cuda')
 acts = [sim.random_actions(i) for i in range(4)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda') if len(sys.argv) > 4 and sys.argv[4] == "flush" else None  # > 126 MB L2, like bench.py
 for i in range(steps):
+    if flush is not None:
+        flush.zero_()
     sim.step_into(acts[i % 4], obs, rew, term, trunc)
 torch.cuda.synchronize()
 print("done", float(rew.mean()))
