@@ -168,24 +168,47 @@ __device__ __forceinline__ bool update_command(const KParams& P, CmdState& c, co
 }
 
 // ---- history rings of the warp's 16 envs: global -> shared memory, asynchronously ----
-// The rings of consecutive envs are contiguous in HBM ([N][H][48] floats), so the warp's block is ONE contiguous range;
-// every lane issues 16-byte cp.async copies that need no registers and are all in flight at once.  The copy is started
-// right after the physics (the per-thread columns are dead by then) and awaited only when the observation is emitted,
-// so the HBM latency hides behind the reward / termination / reset / command code (profiles/r1k: with register-staged
+// The rings of consecutive envs are contiguous in HBM ([N][H][48] floats), so the warp's block is ONE contiguous, 16-byte
+// aligned range: a single bulk copy (cp.async.bulk, the 1-D TMA path: UBLKCP in SASS) issued by one lane moves up to 26.9 KB
+// with no registers and no per-lane instructions, and signals an mbarrier with the byte count when it has landed.  (Round 1
+// issued ~60 16-byte cp.async per lane, ~1 900 warp-instructions per step in a kernel bound by instruction issue.)  The copy
+// is started right after the physics (the per-thread columns are dead by then) and awaited only when the observation is
+// emitted, so the HBM latency hides behind the reward / termination / reset / command code (profiles/r1k: with register-staged
 // loads the emission was 27 % of the step, 76 % of it long-scoreboard stalls).
+// The mbarrier lives in the last 8 bytes of the (float-build) column window: a chunk of whole rings never reaches them
+// (7040 floats are not a multiple of the 48-float slot), and physics only uses them as lane 30/31's fifth contact point.
+#define H1V2_MBAR_OFFSET (SMEM_FLOATS * H1V2_BLOCK * 4 - 8)
 __device__ __forceinline__ int hist_envs_per_chunk(int H, int epw) { return min(epw, (SMEM_FLOATS * H1V2_BLOCK) / (H * H1V2_HIST_STRIDE)); }
-__device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S, unsigned tid, unsigned bid, int e0) {
+// chunk: 0 for the first copy of a launch (initialises the barrier), 1 for the second (H = 10 at 16 envs per warp: 14 + 2 rings)
+__device__ __forceinline__ void hist_prefetch(const KParams& P, const KState& S, unsigned tid, unsigned bid, int e0, int chunk) {
   extern __shared__ __align__(16) real smem_raw[];
   const int lane = tid & 31;
   const int warp_env0 = (int)bid * P.epw;
   const int ne = min(hist_envs_per_chunk(P.H, P.epw), min(P.epw, P.n - warp_env0) - e0);
-  const int nchunk = ne * P.H * (H1V2_HIST_STRIDE / 4);  // 16-byte pieces
+  const unsigned bytes = (unsigned)(ne * P.H * H1V2_HIST_STRIDE * 4);
   const float* src = S.hist + (size_t)(warp_env0 + e0) * P.H * H1V2_HIST_STRIDE;
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
-#pragma unroll 4
-  for (int c = lane; c < nchunk; c += 32)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 4 * c) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw), mbar = dst + H1V2_MBAR_OFFSET;
+  // every lane's earlier (generic-proxy) accesses to the window are ordered before the async-proxy writes of the copy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    if (chunk == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+  }
+}
+// wait until the bytes of copy `chunk` have landed (phase parity = chunk & 1); every lane waits for itself
+__device__ __forceinline__ void hist_wait(int chunk) {
+  extern __shared__ __align__(16) real smem_raw[];
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw) + H1V2_MBAR_OFFSET;
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(mbar), "r"((unsigned)(chunk & 1)) : "memory");
+  } while (!ok);
 }
 
 // observation sample of this step -> history ring slot `head`; then the warp cooperatively emits the flattened rows
@@ -263,8 +286,9 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   const int my_e = (int)(lane >> 1);
 #pragma unroll 1
   for (int e0 = 0; e0 < nenv; e0 += epc) {
-    if (e0 > 0) { __syncwarp(); hist_prefetch(P, S, tid, bid, e0); }  // H > 10 only: the rings do not fit at once
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (e0 > 0) { __syncwarp(); hist_prefetch(P, S, tid, bid, e0, 1); }  // H = 10 at 16 envs per warp: the 16 rings do not fit at once
+    __syncwarp();  // the barrier's initialisation by lane 0 is visible to every lane
+    hist_wait(e0 > 0 ? 1 : 0);
     __syncwarp();
     if (my_e >= e0 && my_e < e0 + epc) {  // the new sample replaces the stale slot `head` of this env's copy
       float* sl = reinterpret_cast<float*>(smem_raw) + (my_e - e0) * ring + head * H1V2_HIST_STRIDE;
@@ -556,7 +580,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     fv = foot_velocity(P.leg[side], tid, Rn, mulv(Rn, mk3(rw[0], rw[1], rw[2])), mk3(rv[0], rv[1], rv[2]), q, qd, P.foot_vel_com != 0, ankle_z);
     __syncwarp();  // every lane is done with its column before the asynchronous copy lands in it
   }
-  hist_prefetch(P, S, tid, bid, 0);
+  hist_prefetch(P, S, tid, bid, 0, 0);
   // ---- actuator line and command state ----
   {
     float4 a0 = S.act[lidx], a1 = S.act[N2 + lidx], a2 = S.act[2 * N2 + lidx], a3 = S.act[3 * N2 + lidx], a4 = S.act[4 * N2 + lidx];
