@@ -463,7 +463,8 @@ struct HostPool {
   std::vector<std::thread> threads;
   std::mutex m;
   std::condition_variable cv;
-  uint64_t gen = 0;  // guarded by m
+  std::atomic<uint64_t> gen{0};   // job generation; workers spin on it for a short while after a job (a caller in a step loop
+  std::atomic<int> sleepers{0};   // comes back within microseconds), then sleep on cv: no futex wake-up on the hot path
   bool stop = false;
   std::atomic<uint64_t> phase2{0};
   std::atomic<int> done{0};
@@ -513,12 +514,19 @@ static void assemble_new(const HostPool* p, int t) {  // phase 2: the new sample
 static void pool_worker(HostPool* p, int t) {
   uint64_t seen = 0;
   for (;;) {
-    {
-      std::unique_lock<std::mutex> lk(p->m);
-      p->cv.wait(lk, [&] { return p->stop || p->gen != seen; });
-      if (p->stop) return;
-      seen = p->gen;
+    bool got = false;
+    for (int spin = 0; spin < 20000 && !got; spin++) {  // ~100-200 us
+      got = p->gen.load(std::memory_order_acquire) != seen;
+      if (!got) CPU_PAUSE();
     }
+    if (!got) {
+      std::unique_lock<std::mutex> lk(p->m);
+      p->sleepers.fetch_add(1, std::memory_order_relaxed);
+      p->cv.wait(lk, [&] { return p->stop || p->gen.load(std::memory_order_acquire) != seen; });
+      p->sleepers.fetch_sub(1, std::memory_order_relaxed);
+      if (p->stop) return;
+    }
+    seen = p->gen.load(std::memory_order_acquire);
     assemble_old(p, t);
     while (p->phase2.load(std::memory_order_acquire) != seen) CPU_PAUSE();  // the kernel is in flight: < 1 ms
     assemble_new(p, t);
@@ -818,14 +826,14 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
     HostPool* p = h->pool;
     const int head = (int)((h->hist_launches + 1) % (uint64_t)H);  // the slot this launch writes (step_kernel: counters[1] + 1)
     if (launch(nullptr, h->h_sample_dev) != 0 || copy_back() != 0) return -1;
-    uint64_t gen;
+    p->sample = h->h_sample; p->ring = h->h_ring; p->obs = obs; p->n = h->n; p->H = H; p->head = head;
+    p->done.store(0, std::memory_order_relaxed);
+    const uint64_t gen = p->gen.load(std::memory_order_relaxed) + 1;
+    p->gen.store(gen, std::memory_order_release);  // publishes the job to the spinning workers
     {
-      std::lock_guard<std::mutex> lk(p->m);
-      p->sample = h->h_sample; p->ring = h->h_ring; p->obs = obs; p->n = h->n; p->H = H; p->head = head;
-      p->done.store(0, std::memory_order_relaxed);
-      gen = ++p->gen;
+      std::lock_guard<std::mutex> lk(p->m);  // a worker that went to sleep checks gen under this mutex: no lost wake-up
+      if (p->sleepers.load(std::memory_order_relaxed) > 0) p->cv.notify_all();
     }
-    p->cv.notify_all();
     assemble_old(p, 0);  // the caller's thread is worker 0
     const cudaError_t e = cudaStreamSynchronize(st);
     p->phase2.store(gen, std::memory_order_release);  // release the workers even on failure

@@ -128,9 +128,9 @@ class RolloutStorage:
             delta = self.rewards[t] + nt * gamma * nv - self.values[t]
             adv = delta + nt * gamma * lam * adv
             self.returns[t] = adv + self.values[t]
-        self.adv = self.returns - self.values
+        self.adv.copy_(self.returns - self.values)  # in place: the captured learner graph reads this tensor's storage
         if normalize:
-            self.adv = (self.adv - self.adv.mean()) / (self.adv.std() + 1e-8)
+            self.adv.copy_((self.adv - self.adv.mean()) / (self.adv.std() + 1e-8))
 
     def mini_batches(self, num_mini_batches, num_epochs):
         B = self.T * self.num_envs
@@ -201,54 +201,109 @@ class PPO:
                 p.grad.data.copy_(flat[off:off + n].view_as(p.grad.data))
                 off += n
 
+    def _minibatch_step(self, obs, cobs, act, val, adv, ret, old_logp, old_mu, old_sigma):
+        """One PPO mini-batch update (rsl-rl-lib 2.3.3 PPO.update body); returns the three detached loss statistics."""
+        self.policy.update_distribution(obs)  # upstream calls policy.act(obs) and discards the sample; torch.normal's host-side check of std cannot be captured
+        logp = self.policy.get_actions_log_prob(act)
+        value = self.policy.evaluate(cobs)
+        mu, sigma, ent = self.policy.action_mean, self.policy.action_std, self.policy.entropy
+        if self.desired_kl is not None and self.schedule == "adaptive":
+            with torch.inference_mode():
+                kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * sigma.square()) - 0.5, dim=-1)
+                kl_mean = kl.mean()
+                if self.multi_gpu:
+                    dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
+                    kl_mean /= self.multi_gpu["world_size"]
+                if self._lr_on_device:  # same rule as below, evaluated on the device
+                    down = (self.lr_t / 1.5).clamp(min=1e-5)
+                    up = (self.lr_t * 1.5).clamp(max=1e-2)
+                    self.lr_t.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down,
+                                                torch.where((kl_mean > 0.0) & (kl_mean < self.desired_kl / 2.0), up, self.lr_t)))
+                else:
+                    if kl_mean > self.desired_kl * 2.0:
+                        self.lr = max(1e-5, self.lr / 1.5)
+                    elif 0.0 < kl_mean < self.desired_kl / 2.0:
+                        self.lr = min(1e-2, self.lr * 1.5)
+                    for g in self.opt.param_groups:
+                        g["lr"] = self.lr
+        ratio = torch.exp(logp - old_logp.squeeze(1))
+        a = adv.squeeze(1)
+        surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip, 1.0 + self.clip)).mean()
+        if self.clip_v:
+            vc = val + (value - val).clamp(-self.clip, self.clip)
+            vloss = torch.max((value - ret).square(), (vc - ret).square()).mean()
+        else:
+            vloss = (ret - value).square().mean()
+        loss = surrogate + self.vcoef * vloss - self.ecoef * ent.mean()
+        self.opt.zero_grad()
+        loss.backward()
+        if self.multi_gpu:
+            self.reduce_parameters()
+        nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+        self.opt.step()
+        return vloss.detach(), surrogate.detach(), ent.mean().detach()
+
+    def _graph_update_ok(self) -> bool:
+        """The whole update (epochs x mini-batches of forward / backward / gradient clip / Adam, adaptive learning rate on the device) as
+        one CUDA graph: single GPU on CUDA by default (H1V2_GRAPH_LEARNER=0 turns it off, =1 also allows it with the NCCL gradient
+        all-reduce inside the capture)."""
+        flag = os.environ.get("H1V2_GRAPH_LEARNER", "")
+        return self._lr_on_device and flag != "0" and (self.multi_gpu is None or flag == "1")
+
     def update(self):
+        if self._graph_update_ok():
+            return self._update_graphed()
         mv = ms = me = torch.zeros((), device=self.device)
         n = 0
-        for obs, cobs, act, val, adv, ret, old_logp, old_mu, old_sigma in self.storage.mini_batches(self.nmb, self.epochs):
-            self.policy.act(obs)
-            logp = self.policy.get_actions_log_prob(act)
-            value = self.policy.evaluate(cobs)
-            mu, sigma, ent = self.policy.action_mean, self.policy.action_std, self.policy.entropy
-            if self.desired_kl is not None and self.schedule == "adaptive":
-                with torch.inference_mode():
-                    kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * sigma.square()) - 0.5, dim=-1)
-                    kl_mean = kl.mean()
-                    if self.multi_gpu:
-                        dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
-                        kl_mean /= self.multi_gpu["world_size"]
-                    if self._lr_on_device:  # same rule as below, evaluated on the device
-                        down = (self.lr_t / 1.5).clamp(min=1e-5)
-                        up = (self.lr_t * 1.5).clamp(max=1e-2)
-                        self.lr_t.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down,
-                                                    torch.where((kl_mean > 0.0) & (kl_mean < self.desired_kl / 2.0), up, self.lr_t)))
-                    else:
-                        if kl_mean > self.desired_kl * 2.0:
-                            self.lr = max(1e-5, self.lr / 1.5)
-                        elif 0.0 < kl_mean < self.desired_kl / 2.0:
-                            self.lr = min(1e-2, self.lr * 1.5)
-                        for g in self.opt.param_groups:
-                            g["lr"] = self.lr
-            ratio = torch.exp(logp - old_logp.squeeze(1))
-            a = adv.squeeze(1)
-            surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip, 1.0 + self.clip)).mean()
-            if self.clip_v:
-                vc = val + (value - val).clamp(-self.clip, self.clip)
-                vloss = torch.max((value - ret).square(), (vc - ret).square()).mean()
-            else:
-                vloss = (ret - value).square().mean()
-            loss = surrogate + self.vcoef * vloss - self.ecoef * ent.mean()
-            self.opt.zero_grad()
-            loss.backward()
-            if self.multi_gpu:
-                self.reduce_parameters()
-            nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
-            self.opt.step()
-            mv = mv + vloss.detach(); ms = ms + surrogate.detach(); me = me + ent.mean().detach(); n += 1
+        for batch in self.storage.mini_batches(self.nmb, self.epochs):
+            v, s_, e = self._minibatch_step(*batch)
+            mv = mv + v; ms = ms + s_; me = me + e; n += 1
         self.storage.clear()
         if self._lr_on_device:
             self.lr = float(self.lr_t)  # the one host read of the update
         return {"value_function": float(mv) / n, "surrogate": float(ms) / n, "entropy": float(me) / n}
 
+    def _update_graphed(self):
+        st = self.storage
+        B = st.T * st.num_envs
+        mb = B // self.nmb
+        nb = self.nmb * self.epochs
+        if getattr(self, "_gu", None) is None:
+            self._gu = {"idx": torch.zeros((nb, mb), dtype=torch.long, device=self.device), "stats": torch.zeros(3, device=self.device),
+                        "graph": None, "calls": 0, "stream": torch.cuda.Stream(device=self.device)}
+        G = self._gu
+        for ep in range(self.epochs):  # the same index stream as RolloutStorage.mini_batches: one permutation per epoch
+            G["idx"][ep * self.nmb:(ep + 1) * self.nmb].copy_(torch.randperm(self.nmb * mb, device=self.device).view(self.nmb, mb))
+
+        def body():
+            flat = lambda x: x.flatten(0, 1)  # noqa: E731
+            obs, cobs, act, val, ret, logp, adv, mu, sig = map(flat, (st.obs, st.critic_obs, st.actions, st.values, st.returns, st.logp, st.adv, st.mu, st.sigma))
+            G["stats"].zero_()
+            for i in range(nb):
+                b = G["idx"][i]
+                v, s_, e = self._minibatch_step(obs[b], cobs[b], act[b], val[b], adv[b], ret[b], logp[b], mu[b], sig[b])
+                G["stats"] += torch.stack((v, s_, e))
+
+        cur = torch.cuda.current_stream(self.device)
+        if G["calls"] == 0:  # first update: eagerly on a side stream (the warm-up torch asks for before capturing a backward pass)
+            G["stream"].wait_stream(cur)
+            with torch.cuda.stream(G["stream"]):
+                body()
+            cur.wait_stream(G["stream"])
+        else:
+            if G["graph"] is None:
+                torch.cuda.synchronize(self.device)
+                self.opt.zero_grad(set_to_none=True)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=G["stream"]):
+                    body()
+                G["graph"] = g
+            G["graph"].replay()
+        G["calls"] += 1
+        st.clear()
+        out = (G["stats"] / nb).tolist()  # the one host read of the update
+        self.lr = float(self.lr_t)
+        return {"value_function": out[0], "surrogate": out[1], "entropy": out[2]}
 
 
 class _GraphRollout:
