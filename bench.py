@@ -260,7 +260,7 @@ def run_ours(args):
         if is_cat:  # h1v2_cat_step_host: float dones instead of the terminated flags
             hterm = torch.empty(n_envs, dtype=torch.float32).pin_memory()
         host_step = sim_.cat_step_host if is_cat else sim_.step_host
-        for i in range(5):
+        for i in range(20):  # the first sixteen calls also time the two host paths against each other (h1v2_host_path_info)
             host_step(ha[i % 4], hobs, hrew, hterm, htrunc)
         if world > 1:
             dist.barrier()

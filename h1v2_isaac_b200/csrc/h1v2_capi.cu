@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -85,6 +86,8 @@ struct H1v2Handle {
   uint64_t hist_launches = 0;     // step / observe launches so far == device counters[1] (the history head)
   struct HostPool* pool = nullptr;
   int host_mode = -1;             // -1 undecided, 0 full rows over PCIe (zero-copy / staged), 1 samples + host assembly
+  int host_calib = -1;            // >= 0: calls made so far while both modes are being timed on this host (see step_host_impl)
+  double host_calib_t[2] = {1e30, 1e30};
   // Constraints-as-Terminations tail (cfg.cat_enable)
   CatState cat = {};            // all step-to-step CaT state lives on the device (graph-replayable)
   uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
@@ -779,10 +782,26 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
     const char* e = std::getenv("H1V2_HOST_PATH");
     if (e && !std::strcmp(e, "rows")) h->host_mode = 0;
     else if (e && !std::strcmp(e, "assemble")) h->host_mode = 1;
-    // measured on the 16-core host of a B200 box (profiles/r2_e2e_modes.txt): 16 threads beat the row path at every size
-    // (4096 envs 0.258 vs 0.296 ms, 32768 envs 0.99 vs 1.43 ms), 8 threads up to 8192 envs, 4 threads never
-    else h->host_mode = (h->pool->nthreads >= 8 && N * od * sizeof(float) <= (size_t)h->pool->nthreads * (4u << 20)) ? 1 : 0;
+    // Otherwise the handle measures: which path wins depends on the host (cores per rank, cache, memory bandwidth) as much as on
+    // the env count -- on the 16-core host of a B200 box 16 threads beat the row path at every size (4096 envs 0.258 vs 0.296 ms,
+    // 32768 envs 0.92 vs 1.40 ms), 8 threads up to 8192 envs, 4 threads never (profiles/r2_e2e_modes.txt).  Calls 0-7 run mode 1,
+    // calls 8-15 mode 0 (the first three of each are warm-up: ring fetch, page faults, thread wake-up), call 16 onwards the faster one.  Both modes
+    // return bit-identical results, so the caller sees nothing of it.
+    else if (h->pool->nthreads < 4) h->host_mode = 0;
+    else { h->host_mode = 1; h->host_calib = 0; }
   }
+  const auto t_call0 = std::chrono::steady_clock::now();
+  struct CalibGuard {  // times this call and advances the calibration when it returns
+    H1v2Handle* h; std::chrono::steady_clock::time_point t0;
+    ~CalibGuard() {
+      if (h->host_calib < 0) return;
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const int k = h->host_calib++, half = 8, warm = 3;  // per mode: 3 warm-up calls (thread wake-up, page faults, ring fetch), 5 timed
+      if (k % half >= warm) h->host_calib_t[k < half ? 1 : 0] = std::min(h->host_calib_t[k < half ? 1 : 0], dt);
+      if (k == half - 1) h->host_mode = 0;
+      if (k == 2 * half - 1) { h->host_mode = h->host_calib_t[1] <= h->host_calib_t[0] ? 1 : 0; h->host_calib = -1; }
+    }
+  } calib_guard{h, t_call0};
   if (!h->d_act) {
     CK(cudaMalloc(&h->d_act, N * 12 * sizeof(float)));
     CK(cudaMalloc(&h->d_rew, N * sizeof(float)));

@@ -292,6 +292,7 @@ int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, 
  * (zero-copy over PCIe when it is pinned, staged otherwise); mode 1 "assemble" = only the step's new 45-float sample of
  * every env crosses PCIe and `threads` host threads assemble the rows from a host mirror of the history ring while the
  * kernel runs (bit-identical rows; tests/test_gpu_parity.py::test_step_host_matches_device_path).  -1 = not decided yet.
+ * Without an override a handle with at least four host threads times both modes over its first sixteen calls and keeps the faster.
  * The call orders itself after work queued earlier through the stream-taking entry points and synchronises before returning. */
 int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads);
 
