@@ -312,7 +312,8 @@ class _GraphRollout:
     next observation straight into the rollout storage), the time-out bootstrap and the storage writes -- the same arithmetic as
     PPO.act / env.step / PPO.process_env_step above, with the per-step Python, the wrapper dictionaries and the logging
     synchronisations (nonzero / tolist) replaced by device-side accumulators read once per iteration.  Used when the env is this
-    package's CUDA backend without privileged observations, empirical normalisation or a pending curriculum change; otherwise (and
+    package's CUDA backend without privileged observations or empirical normalisation (a reward-weight curriculum is applied between
+    iterations and triggers a re-capture when it changes a weight); otherwise (and
     with H1V2_GRAPH_ROLLOUT=0) OnPolicyRunner.learn runs the eager loop.  The first iteration runs the same body eagerly (warm-up
     of cuBLAS workspaces and kernel attributes), the graph is captured after it and replayed from the second iteration on."""
 
@@ -343,7 +344,7 @@ class _GraphRollout:
         base = getattr(runner.env, "unwrapped", None)
         sim = getattr(base, "sim", None)
         return (sim is not None and type(sim).__name__ == "H1v2Sim" and hasattr(sim, "step_into") and not runner.empirical_normalization
-                and runner.privileged is None and not getattr(base, "_curriculum", None) and not getattr(sim.cfg, "cat_enable", 0)
+                and runner.privileged is None and not getattr(sim.cfg, "cat_enable", 0)
                 and torch.device(runner.device) == sim.device and type(runner.alg.policy).__name__ == "ActorCritic")
 
     def _body(self):
@@ -389,6 +390,13 @@ class _GraphRollout:
         self.iterations += 1
         base = self.base
         base.common_step_counter += self.T
+        if getattr(base, "_curriculum", None):
+            # mdp.modify_reward_weight terms that became due during this rollout (env.step applies them step by step; here once per
+            # iteration): the captured step kernel carries the reward weights of capture time, so a changed weight means a new capture
+            before = list(self.sim.cfg.rew_weight)
+            base._apply_curriculum()
+            if list(self.sim.cfg.rew_weight) != before:
+                self.graph = None
         base.obs_buf = {"policy": self.obs_carry}
         base.reward_buf, base.reset_terminated, base.reset_time_outs = self.rew, self.term.bool(), self.trunc.bool()
         base.reset_buf = base.reset_terminated | base.reset_time_outs
