@@ -66,7 +66,14 @@ class H1v2Config(C.Structure):
         ("mass_recompute_inertia", i32), ("cat_enable", i32), ("cat_tau", f32), ("cat_min_p", f32), ("cat_max_p", f32 * 10), ("cat_contact_slots", u32),
         ("cat_foot_force_limit", f32), ("cat_no_move_deadzone", f32), ("cat_no_move_vel_limit", f32), ("cat_orientation_limit", f32),
         ("cat_height", f32), ("cat_height_std", f32), ("cat_clearance_min_height", f32), ("cat_clearance_deadzone", f32),
-        ("runaway_vel", f32), ("solver_vel_tolerance", f32), ("reserved", i32 * 7),
+        ("runaway_vel", f32), ("solver_vel_tolerance", f32),
+        ("terrain_enable", i32), ("terrain_rows", i32), ("terrain_cols", i32), ("terrain_tile_size", f32), ("terrain_hscale", f32), ("terrain_vscale", f32),
+        ("terrain_level_min", i32), ("terrain_level_max", i32), ("terrain_level_step", i32), ("terrain_border_px", i32),
+        ("terrain_max_init_level", i32), ("terrain_curriculum", i32),
+        ("obs_base_lin_vel", i32), ("noise_lin_vel", f32), ("scale_lin_vel", f32),
+        ("obs_height_scan", i32), ("scan_size", f32 * 2), ("scan_resolution", f32), ("scan_offset", f32),
+        ("noise_height_scan", f32), ("scale_height_scan", f32), ("scan_clip", f32 * 2),
+        ("reserved", i32 * 7),
     ]
 
     def copy(self) -> "H1v2Config":
@@ -86,8 +93,9 @@ STATE_FIELDS = [
     ("slot_force", NUM_SLOT * 3, f32), ("slot_force_hist", NUM_SLOT * 3, f32), ("applied_torque", NJ, f32),
     ("joint_acc", NJ, f32), ("reward_terms", NUM_REW, f32), ("foot_vel", 6, f32), ("solver_iters", 3, f32),
     ("pre_reset_qpos", 19, f32), ("pre_reset_qvel", 18, f32), ("pre_reset_timers", 8, f32),
+    ("terrain_level", 1, i32), ("terrain_type", 1, i32),
 ]
-READ_ONLY_STATE = {"slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel", "solver_iters", "pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers"}
+READ_ONLY_STATE = {"terrain_type", "slot_force", "slot_force_hist", "applied_torque", "joint_acc", "reward_terms", "foot_vel", "solver_iters", "pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers"}
 
 
 class H1v2State(C.Structure):
@@ -108,6 +116,11 @@ _SYMBOLS = {
     "h1v2_default_config": (C.c_int, [C.POINTER(H1v2Config)]),
     "h1v2_rsl_config": (C.c_int, [C.POINTER(H1v2Config)]),
     "h1v2_cat_config": (C.c_int, [C.POINTER(H1v2Config)]),
+    "h1v2_rough_config": (C.c_int, [C.POINTER(H1v2Config)]),
+    "h1v2_terrain_dims": (C.c_int, [C.c_void_p, C.POINTER(i32)]),
+    "h1v2_get_terrain": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "h1v2_set_terrain": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "h1v2_get_terrain_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "h1v2_create": (C.c_int, [C.POINTER(H1v2Config), i32, i32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "h1v2_destroy": (None, [C.c_void_p]),
     "h1v2_last_error": (C.c_char_p, []),
@@ -176,6 +189,28 @@ def rsl_config() -> H1v2Config:
     if rc != 0:
         raise RuntimeError("h1v2_rsl_config failed")
     return cfg
+
+
+def rough_config() -> H1v2Config:
+    """Resolved cfg of Isaac-Velocity-Rough-H12_12dof-v0 (config/h12_12dof/rough_env_cfg.py, utils/mdp/terrains.py)."""
+    cfg = H1v2Config()
+    rc = load_library().h1v2_rough_config(C.byref(cfg))
+    if rc != 0:
+        raise RuntimeError("h1v2_rough_config failed")
+    return cfg
+
+
+def scan_count(size: float, resolution: float) -> int:
+    """Rays along one axis of a GridPatternCfg: len(torch.arange(-size / 2, size / 2 + 1e-9, resolution))."""
+    import math
+    return int(math.floor(size / resolution + 1e-4)) + 1  # 1e-4: the fp32 rounding of the config values (0.1f > 0.1)
+
+
+def obs_dim_of(cfg: H1v2Config) -> int:
+    if cfg.obs_base_lin_vel or cfg.obs_height_scan:
+        scan = scan_count(cfg.scan_size[0], cfg.scan_resolution) * scan_count(cfg.scan_size[1], cfg.scan_resolution) if cfg.obs_height_scan else 0
+        return (3 if cfg.obs_base_lin_vel else 0) + OBS_TERM_DIM + scan
+    return cfg.history_length * OBS_TERM_DIM
 
 
 def cat_config() -> H1v2Config:

@@ -53,6 +53,10 @@ class H1v2Sim:
             p = C.c_void_p()
             self._check(self._lib.h1v2_get_log(self._h, C.byref(p)))
             self.log_buf = torch.as_tensor(_DevPtr(p.value, LOG_DIM), device=self.device)
+            self.terrain_log_buf = None
+            if self.cfg.terrain_enable:  # [0] running sum, [1] Curriculum/terrain_levels after the last step (device view)
+                self._check(self._lib.h1v2_get_terrain_log(self._h, C.byref(p)))
+                self.terrain_log_buf = torch.as_tensor(_DevPtr(p.value, 2), device=self.device)
             self.cat_acc_buf = None
             if self.cfg.cat_enable:  # sums behind Episode_Constraint_* (violation x100 [10], probability [10], count), device view
                 self._check(self._lib.h1v2_get_cat_log(self._h, C.byref(p)))
@@ -149,6 +153,26 @@ class H1v2Sim:
         def ptr(x):
             return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
         self._check(self._lib.h1v2_cat_step_host(self._h, ptr(actions), ptr(obs), ptr(rew), ptr(dones), ptr(trunc)))
+
+    # ---- rough terrain (cfg.terrain_enable) ----
+    def terrain(self):
+        """Host copy of the height field [grid_x, grid_y] in metres (h1v2_get_terrain)."""
+        import numpy as np
+        d = (C.c_int32 * 2)()
+        self._check(self._lib.h1v2_terrain_dims(self._h, d))
+        out = np.zeros((d[0], d[1]), np.float32)
+        self._check(self._lib.h1v2_get_terrain(self._h, out.ctypes.data))
+        return out
+
+    def set_terrain(self, heights) -> None:
+        """Replace the generated height field, e.g. by the grid a real isaaclab TerrainGenerator produced (h1v2_set_terrain)."""
+        import numpy as np
+        d = (C.c_int32 * 2)()
+        self._check(self._lib.h1v2_terrain_dims(self._h, d))
+        a = np.ascontiguousarray(heights, dtype=np.float32)
+        if a.shape != (d[0], d[1]):
+            raise ValueError(f"terrain must be [{d[0]},{d[1]}], got {a.shape}")
+        self._check(self._lib.h1v2_set_terrain(self._h, a.ctypes.data))
 
     def check_guards(self) -> int:
         """Guard bytes around the handle's device arrays that were overwritten (0 = no out-of-bounds store); synchronises."""

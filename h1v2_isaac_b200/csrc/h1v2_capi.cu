@@ -93,6 +93,10 @@ struct H1v2Handle {
   uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
   float* d_dones = nullptr;     // staging of h1v2_cat_step_host
   float cat_log[2 * H1V2_NUM_CSTR + 1] = {};
+  // Rough id: height field and tile origins (device copies in S.terrain_h / S.terrain_oz)
+  bool rough = false;
+  float* d_terrain = nullptr;
+  float* d_origin_z = nullptr;
 };
 
 // Every stream-taking entry point notes its stream: h1v2_step_host runs on a private non-blocking stream and orders itself
@@ -118,6 +122,11 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
   float4 tm;
   CmdState cmd;
   cmd.flags = 0; cmd.heading_target = 0.f;
+  if (P.rough && side == 0) {  // (side 1's command state is discarded) the env keeps its terrain tile; _reset_idx runs the terrain-level curriculum on the state being left (curriculums.py:21-52)
+    const float4 r0 = S.root[env], c0 = S.cmd[env];
+    cmd.flags = __float_as_int(S.cmd[N + env].w) & FLAG_TERRAIN_MASK;
+    cmd.flags = terrain_curriculum(P, cmd.flags, r0.x, r0.y, c0.x, c0.y, gid, step);
+  }
   reset_env(P, side, gid, step, rp, rq, rv, rw, q, qd, la, T1, T2, tm, cmd, push_left);
   if (side == 0) {
     S.root[env] = make_float4(rp[0], rp[1], rp[2], rq[0]);
@@ -139,12 +148,20 @@ __global__ void reset_kernel(const __grid_constant__ KParams P, const KState S, 
   for (int k = 0; k < 3; k++) S.warm[(size_t)k * N2 + lidx] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__global__ void startup_kernel(const __grid_constant__ KParams P, const KState S, float fr_lo, float fr_hi, float ma_lo, float ma_hi) {
+__global__ void startup_kernel(const __grid_constant__ KParams P, const KState S, float fr_lo, float fr_hi, float ma_lo, float ma_hi, int max_init) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= P.n) return;
   float u[4];
   rng4(P.key0, P.env_id_offset + env, 0ull, STREAM_EVENT, 0, u);
   S.root[3 * P.n + env] = make_float4(0.f, uni(u[0], fr_lo, fr_hi), uni(u[1], ma_lo, ma_hi), 0.f);
+  if (P.rough) {
+    // TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols)) in fp32
+    float v[4];
+    rng4(P.key0, P.env_id_offset + env, 0ull, STREAM_EVENT, 3, v);
+    const int level = min((int)__fmul_rn(v[0], (float)(max_init + 1)), max_init);
+    const int type = min((int)floorf(__fdiv_rn((float)env, __fdiv_rn((float)P.n, (float)P.t_cols))), P.t_cols - 1);
+    S.cmd[P.n + env] = make_float4(0.f, 0.f, 0.f, __int_as_float((level << FLAG_LEVEL_SHIFT) | (type << FLAG_TYPE_SHIFT)));
+  }
 }
 
 __global__ void random_actions_kernel(const __grid_constant__ KParams P, float* __restrict__ actions, unsigned long long step) {
@@ -227,6 +244,8 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
     if (st.friction) st.friction[env] = root[13];
     if (st.mass_add) st.mass_add[env] = root[14];
     if (st.push_time_left) st.push_time_left[env] = root[15];
+    if (st.terrain_level) st.terrain_level[env] = (flags >> FLAG_LEVEL_SHIFT) & 255;
+    if (st.terrain_type) st.terrain_type[env] = (flags >> FLAG_TYPE_SHIFT) & 255;
     if (S.diag) {
       const float* dg = S.diag + (size_t)env * H1V2_DIAG_DIM;
       if (st.slot_force) for (int k = 0; k < 18; k++) st.slot_force[env * 18 + k] = dg[k];
@@ -262,6 +281,7 @@ __global__ void state_io_kernel(const __grid_constant__ KParams P, const KState 
   if (st.fresh) flags = (flags & ~3) | (st.fresh[env] & 3);
   if (st.is_standing) flags = (flags & ~FLAG_STANDING) | (st.is_standing[env] ? FLAG_STANDING : 0);
   if (st.is_heading) flags = (flags & ~FLAG_HEADING) | (st.is_heading[env] ? FLAG_HEADING : 0);
+  if (st.terrain_level && P.rough) flags = (flags & ~(255 << FLAG_LEVEL_SHIFT)) | (min(max(st.terrain_level[env], 0), P.t_rows - 1) << FLAG_LEVEL_SHIFT);
   if (st.command) { c[0].x = st.command[env * 3]; c[0].y = st.command[env * 3 + 1]; c[0].z = st.command[env * 3 + 2]; }
   if (st.heading_target) c[0].w = st.heading_target[env];
   if (st.time_left) c[1].x = st.time_left[env];
@@ -384,6 +404,38 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.grad_scale = (float)(1.0 / (H1V2_MEANINERTIA * 18.0));
   if (c.history_length < 1 || c.history_length > H1V2_MAX_HISTORY) return fail("config: history_length out of range");
   P.H = c.history_length; P.obs_dim = c.history_length * H1V2_OBS_TERM_DIM; P.corrupt = c.enable_corruption;
+  P.lut_dim = P.obs_dim;
+  P.rough = (c.terrain_enable || c.obs_base_lin_vel || c.obs_height_scan) ? 1 : 0;
+  if (P.rough) {
+    // Rough id (V/velocity_env_cfg.py:119-142): [base_lin_vel 3] | the 45 regular terms | [height_scan], no history
+    if (c.history_length != 1) return fail("config: base_lin_vel / height_scan / terrain need history_length 1 (the Rough id has no observation history)");
+    if (c.cat_enable) return fail("config: the Constraints-as-Terminations tail is not available on the rough-terrain instantiation");
+    P.lin_vel = c.obs_base_lin_vel ? 1 : 0; P.n_lv = c.noise_lin_vel; P.s_lv = c.scale_lin_vel;
+    P.lut_dim = (P.lin_vel ? 3 : 0) + H1V2_OBS_TERM_DIM;
+    P.obs_dim = P.lut_dim;
+    if (c.obs_height_scan) {
+      if (!(c.scan_resolution > 0.f) || !(c.scan_size[0] >= 0.f) || !(c.scan_size[1] >= 0.f)) return fail("config: bad height-scan pattern");
+      // len(torch.arange(-size/2, size/2 + 1e-9, res)); the 1e-4 absorbs the fp32 rounding of the config values (0.1f > 0.1)
+      P.scan_nx = (int)std::floor((double)c.scan_size[0] / (double)c.scan_resolution + 1e-4) + 1;
+      P.scan_ny = (int)std::floor((double)c.scan_size[1] / (double)c.scan_resolution + 1e-4) + 1;
+      if (P.scan_nx * P.scan_ny > H1V2_MAX_SCAN) return fail("config: too many height-scan rays");
+      P.scan_res = c.scan_resolution; P.scan_x0 = -0.5f * c.scan_size[0]; P.scan_y0 = -0.5f * c.scan_size[1];
+      P.scan_off = c.scan_offset; P.n_scan = c.noise_height_scan; P.s_scan = c.scale_height_scan; P.scan_lo = c.scan_clip[0]; P.scan_hi = c.scan_clip[1];
+      P.scan_col0 = P.lut_dim;
+      P.obs_dim += P.scan_nx * P.scan_ny;
+    }
+    if (c.terrain_enable) {
+      if (c.terrain_rows < 1 || c.terrain_rows > 255 || c.terrain_cols < 1 || c.terrain_cols > 255) return fail("config: terrain_rows / terrain_cols must be in 1..255");
+      if (!(c.terrain_tile_size > 0.f) || !(c.terrain_hscale > 0.f)) return fail("config: bad terrain tile size / horizontal scale");
+      P.t_rows = c.terrain_rows; P.t_cols = c.terrain_cols; P.t_curriculum = c.terrain_curriculum ? 1 : 0;
+      P.t_npx = (int)std::lround(c.terrain_tile_size / c.terrain_hscale);
+      P.t_tile = c.terrain_tile_size; P.t_half = 0.5f * c.terrain_tile_size; P.t_inv_hs = 1.0f / c.terrain_hscale;
+    } else {  // a plane under the rough instantiation: one flat tile
+      P.t_rows = P.t_cols = 1; P.t_curriculum = 0; P.t_npx = 2; P.t_tile = 8.f; P.t_half = 4.f; P.t_inv_hs = 0.25f;
+    }
+    P.t_gx = P.t_rows * P.t_npx + 1; P.t_gy = P.t_cols * P.t_npx + 1;
+    if ((size_t)P.t_gx * P.t_gy > ((size_t)1 << 28)) return fail("config: terrain grid too large");
+  }
   P.n_av = c.noise_ang_vel; P.n_g = c.noise_gravity; P.n_q = c.noise_joint_pos; P.n_v = c.noise_joint_vel;
   P.s_av = c.scale_ang_vel; P.s_g = c.scale_gravity; P.s_cmd = c.scale_cmd; P.s_q = c.scale_joint_pos; P.s_v = c.scale_joint_vel; P.s_a = c.scale_action;
   for (int t = 0; t < H1V2_NUM_REW; t++) P.w[t] = c.rew_weight[t];
@@ -557,6 +609,63 @@ static void pool_destroy(HostPool* p) {
   delete p;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Rough id: the height field.  Host-side generation of what upstream isaaclab builds from the reference's generator cfg
+// (packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:11-28): every tile a height field whose rim of border_px vertices is flat
+// and whose interior vertices hold independent uniform draws from {level_min .. level_max} * vscale (height_field/hf_terrains.py
+// random_uniform_terrain; the draws come from this backend's Philox stream 5, keyed by the grid row).
+// ------------------------------------------------------------------------------------------------------
+static void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+static void terrain_generate_host(const H1v2Config& c, const KParams& P, std::vector<float>& H) {
+  H.assign((size_t)P.t_gx * P.t_gy, 0.f);
+  if (!c.terrain_enable) return;
+  const int npx = P.t_npx, bp = c.terrain_border_px;
+  const int nlev = (c.terrain_level_max - c.terrain_level_min) / (c.terrain_level_step > 0 ? c.terrain_level_step : 1) + 1;
+  for (int i = 0; i < P.t_gx; i++)
+    for (int j0 = 0; j0 < P.t_gy; j0 += 4) {
+      uint32_t o[4];
+      philox_host((uint32_t)(j0 / 4), 0u, 5u /* STREAM_TERRAIN */, 0u, P.key0, (uint32_t)i, o);
+      for (int k = 0; k < 4 && j0 + k < P.t_gy; k++) {
+        const int j = j0 + k, a = i % npx, b = j % npx;
+        const bool rim = a < bp || a > npx - bp || b < bp || b > npx - bp || i == P.t_gx - 1 || j == P.t_gy - 1;
+        const float u = (float)(o[k] >> 8) * (1.0f / 16777216.0f);
+        int lev = (int)(u * (float)nlev);
+        if (lev > nlev - 1) lev = nlev - 1;
+        H[(size_t)i * P.t_gy + j] = rim ? 0.f : (float)(c.terrain_level_min + lev * c.terrain_level_step) * c.terrain_vscale;
+      }
+    }
+}
+// tile origin = tile centre at the highest vertex of the central 2 m x 2 m patch (height_field/utils.py height_field_to_mesh)
+static void terrain_origins_host(const H1v2Config& c, const KParams& P, const float* H, std::vector<float>& oz) {
+  oz.assign((size_t)P.t_rows * P.t_cols, 0.f);
+  if (!c.terrain_enable) return;
+  const int a1 = (int)((c.terrain_tile_size * 0.5f - 1.0f) / c.terrain_hscale), a2 = (int)((c.terrain_tile_size * 0.5f + 1.0f) / c.terrain_hscale);
+  for (int r = 0; r < P.t_rows; r++)
+    for (int q = 0; q < P.t_cols; q++) {
+      float m = -1e30f;
+      for (int a = a1; a < a2; a++)
+        for (int b = a1; b < a2; b++) m = std::fmax(m, H[(size_t)(r * P.t_npx + a) * P.t_gy + (q * P.t_npx + b)]);
+      oz[(size_t)r * P.t_cols + q] = m;
+    }
+}
+static int terrain_upload(H1v2Handle* h, const float* H) {
+  std::vector<float> oz;
+  terrain_origins_host(h->cfg, h->P, H, oz);
+  if (cudaMemcpy(h->d_terrain, H, sizeof(float) * (size_t)h->P.t_gx * h->P.t_gy, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->d_origin_z, oz.data(), sizeof(float) * oz.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("terrain upload: cudaMemcpy failed");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------------
@@ -594,6 +703,13 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   int* lut_d = nullptr;
   rc |= dalloc(h, &lut_d, (size_t)h->P.obs_dim);
   if (cfg->reserved[0]) rc |= dalloc(h, &S.diag, N * H1V2_DIAG_DIM);
+  h->rough = h->P.rough != 0;
+  if (h->rough) {
+    rc |= dalloc(h, &h->d_terrain, (size_t)h->P.t_gx * h->P.t_gy);
+    rc |= dalloc(h, &h->d_origin_z, (size_t)h->P.t_rows * h->P.t_cols);
+    rc |= dalloc(h, &S.tlog, (size_t)2);
+    S.terrain_h = h->d_terrain; S.terrain_oz = h->d_origin_z;
+  }
   if (cfg->cat_enable) {
     CatState& T = h->cat;
     rc |= dalloc(h, &T.k.raw, (size_t)H1V2_CSTR_COLS * N);
@@ -625,15 +741,26 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
     std::vector<int> lut(h->P.obs_dim);
     static const int off[7] = {0, 3, 6, 9, 21, 33, 45};
     int w = 0;
+    if (h->P.lin_vel)  // base_lin_vel leads the Rough id's row; it travels in floats 45..47 of the slot
+      for (int k = 45; k < 48; k++) lut[w++] = k;
     for (int t = 0; t < 6; t++)
       for (int hh = 0; hh < h->P.H; hh++)
         for (int k = off[t]; k < off[t + 1]; k++) lut[w++] = (hh << 8) | k;
     CKH(cudaMemcpy(lut_d, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
     S.lut = lut_d;
   }
+  if (h->rough) {
+    std::vector<float> H;
+    terrain_generate_host(*cfg, h->P, H);
+    if (terrain_upload(h, H.data()) != 0) { h1v2_destroy(h); return -1; }
+  }
   CKH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   CKH(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
-  startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
+  {
+    const int rows = h->P.t_rows, mi = cfg->terrain_max_init_level;
+    startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1],
+                                                  (mi < 0 || mi > rows - 1) ? rows - 1 : mi);
+  }
   reset_kernel<<<(2 * n_envs + 127) / 128, 128>>>(h->P, h->S, nullptr, n_envs, h->cat.sums);
   h->launches += 2;
   CKH(cudaGetLastError());
@@ -713,7 +840,13 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
   if (!sample_out) { h->ring_valid = false; note_stream(h, st); }  // the host mirror of the ring misses this launch's sample
   const int threads = H1V2_BLOCK;
   const int blocks = (h->n + h->P.epw - 1) / h->P.epw;  // one warp per block, epw envs per warp
-  const size_t smem = (size_t)SMEM_FLOATS * H1V2_BLOCK * sizeof(real);
+  const size_t smem = (size_t)(h->rough ? SMEM_FLOATS_ROUGH : SMEM_FLOATS) * H1V2_BLOCK * sizeof(real);
+  if (!h->attr_set && h->rough) {
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->attr_set = true;
+  }
   if (!h->attr_set) {  // function attributes are per device: keep the flag with the handle, not with the process
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -722,7 +855,11 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
-  if (do_step && cat)
+  if (h->rough && do_step)
+    step_kernel<true, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (h->rough)
+    step_kernel<false, false, true><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
+  else if (do_step && cat)
     step_kernel<true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
@@ -781,13 +918,13 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
     h->pool = pool_create();
     const char* e = std::getenv("H1V2_HOST_PATH");
     if (e && !std::strcmp(e, "rows")) h->host_mode = 0;
-    else if (e && !std::strcmp(e, "assemble")) h->host_mode = 1;
+    else if (e && !std::strcmp(e, "assemble") && !h->rough) h->host_mode = 1;
     // Otherwise the handle measures: which path wins depends on the host (cores per rank, cache, memory bandwidth) as much as on
     // the env count -- on the 16-core host of a B200 box 16 threads beat the row path at every size (4096 envs 0.258 vs 0.296 ms,
     // 32768 envs 0.92 vs 1.40 ms), 8 threads up to 8192 envs, 4 threads never (profiles/r2_e2e_modes.txt).  Calls 0-7 run mode 1,
     // calls 8-15 mode 0 (the first three of each are warm-up: ring fetch, page faults, thread wake-up), call 16 onwards the faster one.  Both modes
     // return bit-identical results, so the caller sees nothing of it.
-    else if (h->pool->nthreads < 4) h->host_mode = 0;
+    else if (h->rough || h->pool->nthreads < 4) h->host_mode = 0;  // the Rough id has no history to assemble: rows
     else { h->host_mode = 1; h->host_calib = 0; }
   }
   const auto t_call0 = std::chrono::steady_clock::now();
@@ -896,6 +1033,7 @@ int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads) {
 
 int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream) {
   if (!h || !actions || !obs || !rew || !dones || !truncated) return fail("h1v2_cat_step: bad arguments");
+  if (h->rough) return fail("h1v2_cat_step: not available on the rough-terrain instantiation");
   if (!h->cfg.cat_enable) return fail("h1v2_cat_step: the handle was created without cfg.cat_enable");
   return launch_cat(h, actions, obs, rew, dones, truncated, (cudaStream_t)cuda_stream, nullptr);
 }
@@ -948,6 +1086,31 @@ int h1v2_set_reward_weights(H1v2Handle* h, const float* weights) {
     h->cfg.rew_weight[t] = weights[t];
     h->P.w[t] = weights[t];  // the parameter block travels by value with every launch
   }
+  return 0;
+}
+int h1v2_terrain_dims(const H1v2Handle* h, int32_t dims[2]) {
+  if (!h || !dims || !h->rough) return fail("h1v2_terrain_dims: the handle has no terrain (cfg.terrain_enable)");
+  dims[0] = h->P.t_gx; dims[1] = h->P.t_gy;
+  return 0;
+}
+int h1v2_get_terrain(H1v2Handle* h, float* heights) {
+  if (!h || !heights || !h->rough) return fail("h1v2_get_terrain: the handle has no terrain (cfg.terrain_enable)");
+  DeviceGuard guard(h->device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(heights, h->d_terrain, sizeof(float) * (size_t)h->P.t_gx * h->P.t_gy, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int h1v2_set_terrain(H1v2Handle* h, const float* heights) {
+  if (!h || !heights || !h->rough) return fail("h1v2_set_terrain: the handle has no terrain (cfg.terrain_enable)");
+  DeviceGuard guard(h->device);
+  for (size_t i = 0, n = (size_t)h->P.t_gx * h->P.t_gy; i < n; i++)
+    if (!std::isfinite(heights[i])) return fail("h1v2_set_terrain: non-finite height");
+  CK(cudaDeviceSynchronize());
+  return terrain_upload(h, heights);
+}
+int h1v2_get_terrain_log(H1v2Handle* h, const float** log_dev) {
+  if (!h || !log_dev || !h->rough) return fail("h1v2_get_terrain_log: the handle has no terrain (cfg.terrain_enable)");
+  *log_dev = h->S.tlog;
   return 0;
 }
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {

@@ -226,3 +226,34 @@ extern "C" int h1v2_cat_config(H1v2Config* c) {
   return 0;
 }
 
+
+// Resolved cfg of Isaac-Velocity-Rough-H12_12dof-v0 (C12/__init__.py:17-26 -> C12/rough_env_cfg.py:65-125 H12_12dof_RoughEnvCfg on
+// V/velocity_env_cfg.py:280-324 LocomotionVelocityRoughEnvCfg).  Same robot, actuators and solver as the Flat id.
+// Terrain generator: the reference's in-tree cfg packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:11-28 (one HfRandomUniformTerrainCfg
+// sub-terrain); upstream isaaclab's ROUGH_TERRAINS_CFG of the same name also holds mesh stairs / boxes / slopes, which this backend refuses.
+extern "C" int h1v2_rough_config(H1v2Config* c) {
+  if (h1v2_default_config(c) != 0) return -1;
+  // rewards: C12/rough_env_cfg.py:18-62 (H12_12dof_Rewards) and :112-120 -- what C12/flat_env_cfg.py:35-44 overrides is undone here
+  c->rew_weight[H1V2_REW_TORQUES] = -1.5e-7f;            // :114
+  c->rew_weight[H1V2_REW_DOF_ACC] = -1.25e-7f;           // :116
+  c->rew_weight[H1V2_REW_FEET_AIR_BIPED] = 0.25f;        // :34-42
+  // commands: C12/rough_env_cfg.py:122-125
+  c->cmd_lin_y[0] = c->cmd_lin_y[1] = 0.0f;
+  // observations: V/velocity_env_cfg.py:119-142 -- base_lin_vel first, height_scan last, no history
+  c->history_length = 1;
+  c->obs_base_lin_vel = 1; c->noise_lin_vel = 0.1f; c->scale_lin_vel = 1.0f;                 // :123
+  c->obs_height_scan = 1;                                                                     // :133-138, sensor :61-68
+  c->scan_size[0] = 1.6f; c->scan_size[1] = 1.0f; c->scan_resolution = 0.1f;                  // GridPatternCfg(resolution=0.1, size=[1.6, 1.0])
+  c->scan_offset = 0.5f;                                                                      // mdp.height_scan(offset=0.5) [upstream default]
+  c->noise_height_scan = 0.1f; c->scale_height_scan = 1.0f; c->scan_clip[0] = -1.0f; c->scan_clip[1] = 1.0f;
+  // terrain: V/velocity_env_cfg.py:40-58 (generator, max_init_terrain_level 5) with T/utils/mdp/terrains.py:11-28
+  c->terrain_enable = 1;
+  c->terrain_rows = 10; c->terrain_cols = 20;            // num_rows, num_cols
+  c->terrain_tile_size = 8.0f;                           // size=(8.0, 8.0)
+  c->terrain_hscale = 0.1f; c->terrain_vscale = 0.005f;  // horizontal_scale, vertical_scale
+  c->terrain_level_min = 0; c->terrain_level_max = 4; c->terrain_level_step = 1;  // noise_range=(0.0, 0.02), noise_step=0.005 in units of 0.005
+  c->terrain_border_px = 3;                              // border_width=0.25 -> int(0.25 / 0.1) + 1
+  c->terrain_max_init_level = 5;
+  c->terrain_curriculum = 1;                             // V/velocity_env_cfg.py:275 terrain_levels_vel
+  return 0;
+}

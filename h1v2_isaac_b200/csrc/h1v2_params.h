@@ -80,6 +80,15 @@ struct KParams {
   uint32_t key0;
   int64_t env_id_offset;
   int n;
+  // Rough id (V/velocity_env_cfg.py:36-142, 270-276): observation layout and the height field
+  int lut_dim;   // entries of the flatten table: obs_dim on the flat ids; 48 on the Rough id (base_lin_vel | the 45 regular terms)
+  int rough;     // 1: the rough instantiation of the step kernel runs (terrain contacts, base_lin_vel, height scan)
+  int lin_vel;   // base_lin_vel leads the row; its three values travel in floats 45..47 of the sample slot
+  float n_lv, s_lv;
+  int scan_nx, scan_ny, scan_col0;  // height-scan rays along x / y (x fastest), first column of the scan in the row (0 rays: no scan)
+  float scan_res, scan_x0, scan_y0, scan_off, n_scan, s_scan, scan_lo, scan_hi;
+  int t_rows, t_cols, t_npx, t_gx, t_gy, t_curriculum;  // tiles, grid cells per tile side, grid vertices, terrain_levels_vel on / off
+  float t_inv_hs, t_half, t_tile;   // 1 / horizontal scale, half a tile, a tile
   int epw;  // envs per warp (1,2,4,8,16): lanes 2*epw..31 shadow the warp's first env (small-N mapping)
 };
 
@@ -113,6 +122,9 @@ struct KState {
   int64_t* ep_len; // [N] bound, owned by the caller
   float* diag;     // [N][H1V2_DIAG_DIM] or NULL
   KCat cat;        // Constraints-as-Terminations outputs (raw == NULL unless launched by h1v2_cat_step)
+  const float* terrain_h;   // [t_gx][t_gy] height field in metres (Rough id), second index fastest
+  const float* terrain_oz;  // [t_rows][t_cols] height of every tile's origin
+  float* tlog;              // [2] sum of the envs' terrain levels of the step in flight | mean level after the last step
   float* sample_out;  // [N][48] or NULL: this step's observation sample (45) | fresh flag at [45]; the host path of h1v2_step_host assembles the rows from it
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector
@@ -129,3 +141,7 @@ struct KState {
 #define FLAG_LAG_SHIFT 2
 #define FLAG_STANDING 32
 #define FLAG_HEADING 64
+// Rough id: the env's tile in the terrain grid, kept in the flag word (level = row, moved by the curriculum; type = column, fixed)
+#define FLAG_LEVEL_SHIFT 8
+#define FLAG_TYPE_SHIFT 16
+#define FLAG_TERRAIN_MASK 0x00ffff00

@@ -24,6 +24,7 @@
 #pragma once
 #include "h1v2_math.cuh"
 #include "h1v2_params.h"
+#include "h1v2_terrain.cuh"
 
 namespace h1v2 {
 
@@ -74,13 +75,16 @@ namespace h1v2 {
 #define F_FS 29    // 1  smooth force
 #define MAXC 5     // 4 sole corners + 1: any further point means shin / torso / pelvis on the ground, i.e. the env terminates this step
 #define PSTRIDE 8  // r (3) | row residual e (3) | K*imp*dist | 1/R   (owner link from the list position)
+#define PSTRIDE_ROUGH 11  // rough instantiation: + the contact normal (3); e is then held in the contact frame
 #define PT_BASE (6 * JSTRIDE)
 #define SMEM_FLOATS (PT_BASE + MAXC * PSTRIDE)
+#define SMEM_FLOATS_ROUGH (PT_BASE + MAXC * PSTRIDE_ROUGH)  // 235 floats per thread: 7 warps per SM
 
-struct Smem {
+template <int PS>
+struct SmemT {
   real* base;  // this thread's column
   __device__ __forceinline__ real& jf(int j, int f) const { return base[(j * JSTRIDE + f) * H1V2_BLOCK]; }
-  __device__ __forceinline__ real& pf(int p, int f) const { return base[(PT_BASE + p * PSTRIDE + f) * H1V2_BLOCK]; }
+  __device__ __forceinline__ real& pf(int p, int f) const { return base[(PT_BASE + p * PS + f) * H1V2_BLOCK]; }
   __device__ __forceinline__ V3 jv(int j, int f) const { return mk3(jf(j, f), jf(j, f + 1), jf(j, f + 2)); }
   __device__ __forceinline__ void sjv(int j, int f, V3 v) const { jf(j, f) = v.x; jf(j, f + 1) = v.y; jf(j, f + 2) = v.z; }
   __device__ __forceinline__ V3 pv(int p, int f) const { return mk3(pf(p, f), pf(p, f + 1), pf(p, f + 2)); }
@@ -95,6 +99,7 @@ struct Smem {
     jf(j, F_I + 3) = I.xx; jf(j, F_I + 4) = I.yy; jf(j, F_I + 5) = I.zz; jf(j, F_I + 6) = I.xy; jf(j, F_I + 7) = I.xz; jf(j, F_I + 8) = I.yz;
   }
 };
+typedef SmemT<PSTRIDE> Smem;
 
 // Sum over the two lanes of an env.  ALWAYS executed by the whole, converged warp with the constant full mask: a shuffle
 // with a per-pair register mask compiles to a BSSY / WARPSYNC.COLLECTIVE / SHFL / ENDCOLLECTIVE / BSYNC sequence through
@@ -220,6 +225,24 @@ __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const real (&W)[5]) {
   K.al[6] += w2.x; K.al[7] += w2.y; K.al[8] += w2.z;
   K.ll[0] += W[0]; K.ll[1] += W[1]; K.ll[2] += W[2]; K.ll[4] += W[3]; K.ll[5] += W[4];
 }
+// the same for a point whose weight W is given in its contact frame (axes ax, ay, n): K += X' (L W L') X
+__device__ __forceinline__ void k6_add_point_rot(K6& K, V3 r, const real (&W)[5], V3 n) {
+  V3 ax, ay;
+  contact_axes(n, ax, ay);
+  // columns of Ww = L W L':  Ww e_k = L (W (L' e_k)),  L' e_k = (ax_k, ay_k, n_k)
+  const V3 w0 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.x, ay.x, n.x)));
+  const V3 w1 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.y, ay.y, n.y)));
+  const V3 w2 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.z, ay.z, n.z)));
+  // Ww g_j over the columns g_j = e_j x r of G
+  const V3 g0 = mk3(0.f, -r.z, r.y), g1 = mk3(r.z, 0.f, -r.x), g2 = mk3(-r.y, r.x, 0.f);
+  const V3 v0 = fma3(w1, g0.y, w2 * g0.z), v1 = fma3(w0, g1.x, w2 * g1.z), v2 = fma3(w0, g2.x, w1 * g2.y);
+  K.aa[0] += dot(g0, v0); K.aa[1] += dot(g1, v1); K.aa[2] += dot(g2, v2);
+  K.aa[3] += dot(g0, v1); K.aa[4] += dot(g0, v2); K.aa[5] += dot(g1, v2);
+  K.al[0] += v0.x; K.al[1] += v0.y; K.al[2] += v0.z;
+  K.al[3] += v1.x; K.al[4] += v1.y; K.al[5] += v1.z;
+  K.al[6] += v2.x; K.al[7] += v2.y; K.al[8] += v2.z;
+  K.ll[0] += w0.x; K.ll[1] += w1.y; K.ll[2] += w2.z; K.ll[3] += w0.y; K.ll[4] += w0.z; K.ll[5] += w1.z;
+}
 // line-search contribution of one contact point: d1 += D*jar*jv, d2 += D*jv^2 over the edges active at ea
 __device__ __forceinline__ void point_ls(V3 ea, V3 us, real kap, real D, real mu, real& d1, real& d2) {
   const Edges E = point_edges(ea, kap, mu);
@@ -328,12 +351,15 @@ __device__ __forceinline__ real impedance_call(const float* si, real pos) {
 // "evaluate" and "solve" halves of an iteration that can be re-derived from the contact list (the contact
 // stiffness is accumulated straight into the articulated inertia during the tip->root sweep).
 // ----------------------------------------------------------------------------------------------------------
+// ROUGH: contacts against the height field of the Rough id (terrain height and triangle normal under every candidate, residuals
+// held in the contact frame) -- its own instantiation, the plane kernel carries none of that code.
+template <bool ROUGH>
 __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, real (&rp)[3],
                                      real (&rq)[4], real (&rv)[3], real (&rw)[3], real (&q)[6], real (&qd)[6],
                                      const real (&tau)[6], const real mu, const real mass_add, real (&wl)[6], real (&wr)[6],
-                                     const bool use_warm, SubOut& out) {
+                                     const bool use_warm, SubOut& out, const float* __restrict__ terrain_h, const TerrainEnv& te) {
   extern __shared__ __align__(16) real smem_raw[];
-  const Smem sm{smem_raw + tid};
+  const SmemT<ROUGH ? PSTRIDE_ROUGH : PSTRIDE> sm{smem_raw + tid};
   const KLeg& LG = P.leg[side];
   const real h = P.h;
   const int j0 = 6 * side;
@@ -464,11 +490,25 @@ UNROLL(U_PRO)
         lp = ld3(P.root_pt[rpi]); Rb = R0; xb = zero3; omb = om0; vob = v0; rad = P.root_rad[rpi]; slot = p < 10 ? 4 : 5; href = pz;
       }
       const V3 c = xb + mulv(Rb, lp);
-      const real dist = href + c.z - rad;
+      real dist = href + c.z - rad;
+      V3 nrm = mk3(0.f, 0.f, 1.f);
+      if (ROUGH) {  // point / sphere against the plane of the triangle under it
+        real ht, gx, gy;
+        terrain_sample(P, terrain_h, te, rp[0] + c.x + (p < 6 ? d.x : 0.f), rp[1] + c.y + (p < 6 ? d.y : 0.f), ht, gx, gy);
+        const real s = r_rsqrt(r_fma(gx, gx, r_fma(gy, gy, 1.f)));
+        nrm = mk3(-gx * s, -gy * s, s);
+        dist = (href + c.z - ht) * s - rad;
+      }
       if (dist < 0.f) {
         if (nact < MAXC) {
-          const V3 rc = mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
-          const V3 vel = vob + cross(omb, rc);
+          const V3 rc = ROUGH ? c - nrm * (rad + 0.5f * dist) : mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
+          V3 vel = vob + cross(omb, rc);
+          if (ROUGH) {
+            V3 ax, ay;
+            contact_axes(nrm, ax, ay);
+            vel = to_contact(ax, ay, nrm, vel);
+            sm.pf(nact, 8) = nrm.x; sm.pf(nact, 9) = nrm.y; sm.pf(nact, 10) = nrm.z;
+          }
           const real imp = impedance_call(P.contact_imp, dist);
           const real tr = P.slot_tran[slot];
           const real Rn = r_max(1e-15f, (1.f - imp) * (tr + mu2 * tr) / imp);
@@ -523,7 +563,13 @@ UNROLL(U_PRO)
 #pragma unroll 1
       for (int p = 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
-        const V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
+        V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
+        if (ROUGH) {  // contact frame -> world
+          const V3 n = sm.pv(p, 8);
+          V3 ax, ay;
+          contact_axes(n, ax, ay);
+          Fp = from_contact(ax, ay, n, Fp);
+        }
         const V3 mom = cross(r, Fp);
         const real isf = p < n_foot ? 1.f : 0.f, iss = (p >= n_foot && p < e_shin) ? 1.f : 0.f, isr = p >= e_shin ? 1.f : 0.f;
         const real ist = (p >= e_shin && p < e_torso) ? 1.f : 0.f;
@@ -607,7 +653,8 @@ UNROLL(U_SWEEP1)
           for (int p = j == 5 ? 0 : n_foot; p < p1; p++) {
             real Wp[5];
             point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
-            k6_add_point(IA, sm.pv(p, 0), Wp);
+            if (ROUGH) k6_add_point_rot(IA, sm.pv(p, 0), Wp, sm.pv(p, 8));
+            else k6_add_point(IA, sm.pv(p, 0), Wp);
           }
         }
         const V3 wj = sm.jv(j, F_W), uj = sm.jv(j, F_U);
@@ -633,7 +680,8 @@ UNROLL(U_SWEEP1)
         for (int p = e_shin; p < nact; p++) {
           real Wp[5];
           point_weight(sm.pv(p, 3), sm.pf(p, 6), Dk * sm.pf(p, 7), mu, Wp);
-          k6_add_point(IA, sm.pv(p, 0), Wp);
+          if (ROUGH) k6_add_point_rot(IA, sm.pv(p, 0), Wp, sm.pv(p, 8));
+          else k6_add_point(IA, sm.pv(p, 0), Wp);
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) { IA.aa[i] = pair_sum(IA.aa[i]); IA.ll[i] = pair_sum(IA.ll[i]); }
@@ -748,7 +796,13 @@ UNROLL(U_LSJ)
           const V3 r = sm.pv(p, 0);
           const bool isf = p < n_foot, iss = p < e_shin;
           const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
-          const V3 us = Sl + cross(Sa, r);
+          V3 us = Sl + cross(Sa, r);
+          if (ROUGH) {
+            const V3 n = sm.pv(p, 8);
+            V3 ax, ay;
+            contact_axes(n, ax, ay);
+            us = to_contact(ax, ay, n, us);
+          }
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
         d1 = pair_sum(d1) + r_fma(alpha, sMs, sMa);
@@ -793,7 +847,14 @@ UNROLL(U_LSJ)
         const V3 r = sm.pv(p, 0);
         const bool isf = p < n_foot, iss = p < e_shin;
         const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
-        const V3 e = fma3(Sl + cross(Sa, r), alpha, sm.pv(p, 3));
+        V3 us = Sl + cross(Sa, r);
+        if (ROUGH) {
+          const V3 n = sm.pv(p, 8);
+          V3 ax, ay;
+          contact_axes(n, ax, ay);
+          us = to_contact(ax, ay, n, us);
+        }
+        const V3 e = fma3(us, alpha, sm.pv(p, 3));
         sm.pf(p, 3) = e.x; sm.pf(p, 4) = e.y; sm.pf(p, 5) = e.z;
       }
     }

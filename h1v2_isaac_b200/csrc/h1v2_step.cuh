@@ -84,7 +84,7 @@ __device__ __forceinline__ void reset_env(const KParams& P, int side, int64_t gi
   rng4(P.key0, gid, step, STREAM_RESET, 3, u3);
   int lag = P.min_delay + (int)(u1[2] * (real)(P.max_delay - P.min_delay + 1));
   lag = min(lag, P.max_delay);
-  cmd.flags = FLAG_DELAY_FRESH | FLAG_HIST_FRESH | (lag << FLAG_LAG_SHIFT);
+  cmd.flags = (cmd.flags & FLAG_TERRAIN_MASK) | FLAG_DELAY_FRESH | FLAG_HIST_FRESH | (lag << FLAG_LAG_SHIFT);  // the env keeps its terrain tile
   timers = make_float4(0.f, 0.f, 0.f, 0.f);
   rp[0] = uni(u0[0], P.rp[0][0], P.rp[0][1]);
   rp[1] = uni(u0[1], P.rp[1][0], P.rp[1][1]);
@@ -250,6 +250,18 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     s9[3] = (rd.g.x + n1[0]) * P.s_g; s9[4] = (rd.g.y + n1[1]) * P.s_g; s9[5] = (rd.g.z + n1[2]) * P.s_g;
     s9[6] = cmd.c[0] * P.s_cmd; s9[7] = cmd.c[1] * P.s_cmd; s9[8] = cmd.c[2] * P.s_cmd;
   }
+  // Rough id: base_lin_vel (V/velocity_env_cfg.py:123) travels in floats 45..47 of the slot; the flatten table puts it first
+  real slv[3] = {0.f, 0.f, 0.f};
+  if (P.lin_vel) {
+    real nl[3] = {0.f, 0.f, 0.f};
+    if (P.corrupt && side == 0) {
+      float b[4];
+      rng4(P.key0, gid, step, STREAM_OBS, 10, b);
+#pragma unroll
+      for (int i = 0; i < 3; i++) nl[i] = uni(b[i], -P.n_lv, P.n_lv);
+    }
+    slv[0] = (rd.vb.x + nl[0]) * P.s_lv; slv[1] = (rd.vb.y + nl[1]) * P.s_lv; slv[2] = (rd.vb.z + nl[2]) * P.s_lv;
+  }
   if (valid) {  // ring slot `head` in HBM
     float* slot = S.hist + ((size_t)env * H + head) * H1V2_HIST_STRIDE;
 #pragma unroll
@@ -260,6 +272,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     if (side == 0) {
 #pragma unroll
       for (int k = 0; k < 9; k++) slot[k] = s9[k];
+      if (P.lin_vel) { slot[45] = slv[0]; slot[46] = slv[1]; slot[47] = slv[2]; }
     }
   }
   // ---- cooperative flatten from the shared-memory copy: term-major, oldest -> newest inside each term block
@@ -268,13 +281,13 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   // env, so it is decoded once (packed: regular offset | offset in the newest slot << 16; -1 = beyond obs_dim). ----
   const int lane = tid & 31;
   const int warp_env0 = (int)bid * P.epw;
-  const int npass = (P.obs_dim + 31) >> 5;
+  const int npass = (P.lut_dim + 31) >> 5;
   int off[H1V2_OBS_MAXPASS];
 #pragma unroll
   for (int i = 0; i < H1V2_OBS_MAXPASS; i++) {
     const int idx = lane + 32 * i;
     off[i] = -1;
-    if (i < npass && idx < P.obs_dim) {
+    if (i < npass && idx < P.lut_dim) {
       const int hk = __ldg(S.lut + idx);
       const int hh = hk >> 8, k = hk & 255;
       int sl = head + 1 + hh;
@@ -300,6 +313,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
       if (side == 0) {
 #pragma unroll
         for (int k = 0; k < 9; k++) sl[k] = s9[k];
+        if (P.lin_vel) { sl[45] = slv[0]; sl[46] = slv[1]; sl[47] = slv[2]; }
       }
     }
     __syncwarp();
@@ -344,6 +358,53 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   }
 }
 
+// Rough id: height_scan (V/velocity_env_cfg.py:61-68,133-138; upstream mdp.height_scan = sensor z - hit z - offset).  The warp walks its
+// envs; for each, the lanes share the env's pose (shuffles from its first lane) and cast the GridPattern rays -- x fastest, "xy"
+// indexing, about the scanner body (torso_link = the pelvis frame: fixed joint), rotated by the base yaw only -- straight down onto
+// the height field: one terrain lookup per ray.  Four consecutive rays share one Philox draw.  Noise, then clip, then scale.
+template <bool ROUGH>
+__device__ __forceinline__ void emit_height_scan(const KParams& P, const KState& S, unsigned tid, unsigned bid, unsigned long long step,
+                                                 const real (&rp)[3], const RootDerived& rd, int flags, float* obs) {
+  const int lane = tid & 31;
+  const int warp_env0 = (int)bid * P.epw, nenv = min(P.epw, P.n - warp_env0);
+  const int nrays = P.scan_nx * P.scan_ny, ngrp = (nrays + 3) >> 2;
+  const real hn = r_rsqrt(r_max(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));
+  const real my_c = rd.hx * hn, my_s = rd.hy * hn;
+#pragma unroll 1
+  for (int e = 0; e < nenv; e++) {
+    const real px = __shfl_sync(FULL_MASK, rp[0], 2 * e), py = __shfl_sync(FULL_MASK, rp[1], 2 * e), pz = __shfl_sync(FULL_MASK, rp[2], 2 * e);
+    const real cy = __shfl_sync(FULL_MASK, my_c, 2 * e), sy = __shfl_sync(FULL_MASK, my_s, 2 * e);
+    const int fl = __shfl_sync(FULL_MASK, flags, 2 * e);
+    TerrainEnv te;
+    te.i0 = te.j0 = 0; te.oz = 0.f;
+    if (ROUGH) te = terrain_env(P, S.terrain_oz, fl);
+    const int64_t gid = P.env_id_offset + warp_env0 + e;
+    float* orow = obs + (size_t)(warp_env0 + e) * P.obs_dim + P.scan_col0;
+#pragma unroll 1
+    for (int g = lane; g < ngrp; g += 32) {
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (P.corrupt) {
+        rng4(P.key0, gid, step, STREAM_OBS, 16 + g, nz);
+#pragma unroll
+        for (int k = 0; k < 4; k++) nz[k] = uni(nz[k], -P.n_scan, P.n_scan);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int r = 4 * g + k;
+        if (r < nrays) {
+          const int iy = r / P.scan_nx, ix = r - iy * P.scan_nx;
+          const real gx = r_fma((real)ix, P.scan_res, P.scan_x0), gy = r_fma((real)iy, P.scan_res, P.scan_y0);
+          real h = 0.f, g0, g1;
+          if (ROUGH) terrain_sample(P, S.terrain_h, te, px + cy * gx - sy * gy, py + sy * gx + cy * gy, h, g0, g1);
+          float v = (float)(pz - h - P.scan_off) + nz[k];
+          v = fminf(fmaxf(v, P.scan_lo), P.scan_hi) * P.s_scan;
+          if (obs) orow[r] = v;
+        }
+      }
+    }
+  }
+}
+
 // Constraints-as-Terminations column maximum (constraint.max(0).clamp(min=1e-6), constraint_manager.py:56): reduce over the lanes
 // of the same side (xor 2..16 keeps the lane parity), then lanes 0 / 1 publish; positive floats order like their bit patterns.
 // Constraints-as-Terminations column maxima (constraint.max(0).clamp(min=1e-6), constraint_manager.py:56).  A candidate only
@@ -374,6 +435,10 @@ __device__ __forceinline__ void cat_max_publish(const CatMax& M, int* cmax) {
 // publishes the log vector, clears the accumulators, advances the step counter and the history head.
 // Run by the 32 lanes of the LAST block of a step launch to finish (ticket counter S.done): one launch per control step.
 __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, bool cat, unsigned t, int n, int epw) {
+  if (S.tlog && do_step && t == 0) {  // Curriculum/terrain_levels: mean level over all envs (V/mdp/curriculums.py:52)
+    S.tlog[1] = __ldcg(S.tlog) / (float)n;
+    S.tlog[0] = 0.f;
+  }
   if (do_step && cat) {
     // Constraints-as-Terminations: the envs whose command is inside the no_move dead zone, in ascending env order (the reference's
     // boolean-mask gather, constraints.py:216-222), are addressed by rank: the blocks left one member mask per warp, this block adds
@@ -438,7 +503,8 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, boo
 }
 
 // CAT: the Constraints-as-Terminations flavour (h1v2_cat_step) is its own instantiation, so the plain step carries none of its code
-template <bool DO_STEP, bool CAT = false>
+// ROUGH: the Rough id's flavour (height-field contacts, base_lin_vel, height scan, terrain-level curriculum), its own instantiation too
+template <bool DO_STEP, bool CAT = false, bool ROUGH = false>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
@@ -489,6 +555,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     wl[0] = w0.x; wl[1] = w0.y; wl[2] = w0.z; wl[3] = w0.w; wl[4] = w1.x; wl[5] = w1.y;
     wr[0] = w1.z; wr[1] = w1.w; wr[2] = w2.x; wr[3] = w2.y; wr[4] = w2.z; wr[5] = w2.w;
   }
+  TerrainEnv te;
+  te.i0 = te.j0 = 0; te.oz = 0.f;
+  if (ROUGH) te = terrain_env(P, S.terrain_oz, flags0);
   real la[6], T1[6], T2[6];
   CmdState cmd;
   real h_foot[3] = {0, 0, 0}, h_shin[3] = {0, 0, 0}, h_torso[3] = {0, 0, 0}, h_pelvis[3] = {0, 0, 0};
@@ -545,7 +614,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           cat_max_publish(CM, S.cat.cmax);
         }
       }
-      substep(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so);
+      substep<ROUGH>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
       use_warm = true;
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters; novf += so.overflow;
       if (S.diag && valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);  // iteration histogram: diagnostics handles only
@@ -844,6 +913,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           if (bad) atomicAdd(S.acc + H1V2_LOG_NAN_RESETS, 1.f);
         }
       }
+      // CurriculumManager.compute(env_ids) comes first in _reset_idx (cat_env.py:197-200): the terrain level moves on the state and the
+      // command the episode ended with
+      if (ROUGH) cmd.flags = terrain_curriculum(P, cmd.flags, (float)rp[0], (float)rp[1], cmd.c[0], cmd.c[1], gid, step);
       reset_env(P, side, gid, step, rp, rq, rv, rw, q, qd, la, T1, T2, tm, cmd, push_left);
 #pragma unroll
       for (int i = 0; i < 12; i++) es[i] = 0.f;
@@ -878,6 +950,13 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     }
   }
   emit_observation(P, S, tid, bid, env, side, valid, gid, step, head, rd, cmd, q, qd, la, obs);
+  if (ROUGH) {
+    if (P.scan_nx > 0) emit_height_scan<true>(P, S, tid, bid, step, rp, rd, cmd.flags, obs);
+    if (DO_STEP) {  // terrain level census of the step (after the resets)
+      const int lv = __reduce_add_sync(FULL_MASK, (valid && side == 0) ? ((cmd.flags >> FLAG_LEVEL_SHIFT) & 255) : 0);
+      if ((tid & 31) == 0) atomicAdd(S.tlog, (float)lv);
+    }
+  }
   cmd.flags &= ~FLAG_HIST_FRESH;
 
   // ---- store state ----

@@ -40,6 +40,8 @@ REW_FUNC_SLOT = {
 # the second term of the cfg goes to the kernel's second slot of that function
 REW_FUNC_SLOT_B = {"joint_pos_limits": 20, "joint_deviation_l1": 21}
 OBS_LAYOUT = ["base_ang_vel", "projected_gravity", "generated_commands", "joint_pos_rel", "joint_vel_rel", "last_action"]
+# the Rough id's row (V/velocity_env_cfg.py:119-142): base_lin_vel first, height_scan last, no history
+OBS_LAYOUT_ROUGH = ["base_lin_vel"] + OBS_LAYOUT + ["height_scan"]
 
 
 def _get(obj, name, default=None):
@@ -159,10 +161,10 @@ def curriculum_schedule(cfg) -> list[tuple[int, float, int]]:
     out, slots = [], reward_slots(cfg)
     for n, t in _terms(_get(cfg, "curriculum")):
         f, p = _fname(t.func), (t.params or {})
-        if f == "modify_constraint_p":
+        if f in ("modify_constraint_p", "terrain_levels_vel"):  # the terrain-level curriculum runs inside the kernel's reset (flatten_cfg)
             continue
         if f != "modify_reward_weight":
-            raise NotImplementedError(f"curriculum.{n}: mdp.{f} is not implemented (only modify_reward_weight and modify_constraint_p are)")
+            raise NotImplementedError(f"curriculum.{n}: mdp.{f} is not implemented (only modify_reward_weight, modify_constraint_p and terrain_levels_vel are)")
         if p["term_name"] not in slots:
             raise NotImplementedError(f"curriculum.{n}: reward term {p['term_name']!r} has no kernel slot")
         out.append((slots[p["term_name"]], float(p["weight"]), int(p["num_steps"])))
@@ -270,11 +272,17 @@ def flatten_cfg(cfg) -> H1v2Config:
     pol = cfg.observations.policy
     terms = _terms(pol)
     got = [_fname(t.func) for _, t in terms]
-    if got != OBS_LAYOUT:
-        raise NotImplementedError(f"observations.policy: the fused kernel emits {OBS_LAYOUT}; the cfg asks for {got}")
+    rough_obs = got != OBS_LAYOUT
+    if rough_obs:
+        lead, tail = got[:1] == ["base_lin_vel"], got[-1:] == ["height_scan"]
+        if got[int(lead):len(got) - int(tail)] != OBS_LAYOUT:
+            raise NotImplementedError(f"observations.policy: the fused kernel emits {OBS_LAYOUT}, optionally led by base_lin_vel and ended by height_scan; the cfg asks for {got}")
+        c.obs_base_lin_vel, c.obs_height_scan = int(lead), int(tail)
     if not _get(pol, "concatenate_terms", True):
         raise NotImplementedError("observations.policy.concatenate_terms=False is not supported")
     c.history_length = int(_get(pol, "history_length", 0) or 1)
+    if rough_obs and c.history_length != 1:
+        raise NotImplementedError("observations.policy: base_lin_vel / height_scan cannot be combined with an observation history")
     if int(_get(pol, "history_step", 1) or 1) != 1:  # T/utils/history/observation_manager.py:441-451 (the CaT cfg sets 1)
         raise NotImplementedError("observations.policy.history_step != 1 is not supported")
     if _get(pol, "flatten_history_dim", True) is False:
@@ -284,20 +292,24 @@ def flatten_cfg(cfg) -> H1v2Config:
         if th not in (None, 0, c.history_length):
             raise NotImplementedError(f"observations.policy.{n}.history_length differs from the group's")
     c.enable_corruption = int(bool(_get(pol, "enable_corruption", False)))
-    noise, scale = [], []
+    noise, scale = {}, {}
     for n, t in terms:
+        f = _fname(t.func)
         nz = _get(t, "noise")
         if nz is None:
-            noise.append(0.0)
+            noise[f] = 0.0
         else:
             lo, hi = float(nz.n_min), float(nz.n_max)
             if abs(lo + hi) > 1e-12:
                 raise NotImplementedError(f"observations.policy.{n}: only symmetric additive uniform noise is supported")
-            noise.append(hi)
-        if _get(t, "clip") is not None:
+            noise[f] = hi
+        clip = _get(t, "clip")
+        if f == "height_scan":
+            c.scan_clip[0], c.scan_clip[1] = (float(clip[0]), float(clip[1])) if clip is not None else (-3.0e38, 3.0e38)
+        elif clip is not None:
             raise NotImplementedError(f"observations.policy.{n}.clip is not supported")
         sc = _get(t, "scale")
-        scale.append(1.0 if sc is None else float(sc))
+        scale[f] = 1.0 if sc is None else float(sc)
     for n, t in terms:  # joint-indexed terms must list the joints in the action's order (one permutation in the kernel)
         ac = _get(_get(t, "params"), "asset_cfg")
         names = _get(ac, "joint_names")
@@ -312,10 +324,66 @@ def flatten_cfg(cfg) -> H1v2Config:
             jo = [i for i in BREADTH_FIRST if i in sel]
         if _fname(t.func) in ("joint_pos_rel", "joint_vel_rel") and list(jo) != list(order):
             raise NotImplementedError(f"observations.policy.{n}: joint order differs from the action term's")
-    if noise[2] or noise[5]:
+    if noise["generated_commands"] or noise["last_action"]:
         raise NotImplementedError("observations.policy: noise on commands / last_action is not supported")
-    c.noise_ang_vel, c.noise_gravity, c.noise_joint_pos, c.noise_joint_vel = noise[0], noise[1], noise[3], noise[4]
-    c.scale_ang_vel, c.scale_gravity, c.scale_cmd, c.scale_joint_pos, c.scale_joint_vel, c.scale_action = scale
+    c.noise_ang_vel, c.noise_gravity, c.noise_joint_pos, c.noise_joint_vel = noise["base_ang_vel"], noise["projected_gravity"], noise["joint_pos_rel"], noise["joint_vel_rel"]
+    c.scale_ang_vel, c.scale_gravity, c.scale_cmd, c.scale_joint_pos, c.scale_joint_vel, c.scale_action = (scale[f] for f in OBS_LAYOUT)
+    if c.obs_base_lin_vel:
+        c.noise_lin_vel, c.scale_lin_vel = noise["base_lin_vel"], scale["base_lin_vel"]
+    if c.obs_height_scan:  # V/velocity_env_cfg.py:61-68,133-138: RayCasterCfg on the torso (= pelvis frame), GridPattern, yaw-aligned
+        hs = dict(terms)[[n for n, t in terms if _fname(t.func) == "height_scan"][0]]
+        sensor = _get(cfg.scene, _get(_get(hs.params, "sensor_cfg"), "name", "height_scanner"))
+        if sensor is None:
+            raise NotImplementedError("observations.policy.height_scan: the scene has no such ray caster")
+        body = str(_get(sensor, "prim_path", "")).rsplit("/", 1)[-1]
+        if body not in ("torso_link", "pelvis", "base"):  # torso_link is welded to the pelvis at zero offset (h12_12dof.urdf:394-400)
+            raise NotImplementedError(f"scene.height_scanner: attached to {body!r}; only the pelvis / torso_link frame is supported")
+        if not _get(sensor, "attach_yaw_only", False):
+            raise NotImplementedError("scene.height_scanner: attach_yaw_only=False is not supported")
+        off = _get(_get(sensor, "offset"), "pos", (0.0, 0.0, 0.0))
+        if abs(float(off[0])) > 1e-9 or abs(float(off[1])) > 1e-9:
+            raise NotImplementedError("scene.height_scanner: a horizontal sensor offset is not supported")
+        pat = _get(sensor, "pattern_cfg")
+        if type(pat).__name__ != "GridPatternCfg" or _get(pat, "ordering", "xy") != "xy" or tuple(_get(pat, "direction", (0.0, 0.0, -1.0))) != (0.0, 0.0, -1.0):
+            raise NotImplementedError("scene.height_scanner: only a downward GridPatternCfg with 'xy' ordering is supported")
+        c.scan_size[0], c.scan_size[1], c.scan_resolution = float(pat.size[0]), float(pat.size[1]), float(pat.resolution)
+        c.scan_offset = float(_get(hs.params, "offset", 0.5))  # mdp.height_scan(env, sensor_cfg, offset=0.5) [UPSTREAM default]
+        c.noise_height_scan, c.scale_height_scan = noise["height_scan"], scale["height_scan"]
+
+    # ---- terrain (V/velocity_env_cfg.py:40-58, utils/mdp/terrains.py:11-28) and its curriculum (V/mdp/curriculums.py:21-52) ----
+    terrain = _get(cfg.scene, "terrain")
+    ttype = _get(terrain, "terrain_type", "plane")
+    if ttype == "generator":
+        gen = _get(terrain, "terrain_generator")
+        subs = dict(_get(gen, "sub_terrains") or {})
+        if len(subs) != 1 or type(next(iter(subs.values()))).__name__ != "HfRandomUniformTerrainCfg":
+            raise NotImplementedError("scene.terrain.terrain_generator: exactly one HfRandomUniformTerrainCfg sub-terrain is supported "
+                                      f"(utils/mdp/terrains.py:11-28); got {[type(v).__name__ for v in subs.values()]}")
+        sub = next(iter(subs.values()))
+        if abs(float(gen.size[0]) - float(gen.size[1])) > 1e-9:
+            raise NotImplementedError("scene.terrain.terrain_generator.size: tiles must be square")
+        if _get(sub, "downsampled_scale") not in (None, float(gen.horizontal_scale)):
+            raise NotImplementedError("scene.terrain.terrain_generator: downsampled_scale is not supported")
+        c.terrain_enable = 1
+        c.terrain_rows, c.terrain_cols = int(gen.num_rows), int(gen.num_cols)
+        c.terrain_tile_size = float(gen.size[0])
+        hs_, vs_ = float(gen.horizontal_scale), float(gen.vertical_scale)  # python doubles, as upstream's int() conversions see them
+        c.terrain_hscale, c.terrain_vscale = hs_, vs_
+        # hf_terrains.random_uniform_terrain [UPSTREAM]: int(noise / vertical_scale) on both ends and the step
+        c.terrain_level_min, c.terrain_level_max = int(float(sub.noise_range[0]) / vs_), int(float(sub.noise_range[1]) / vs_)
+        c.terrain_level_step = max(1, int(float(sub.noise_step) / vs_))
+        bw = float(_get(sub, "border_width", 0.0))
+        c.terrain_border_px = int(bw / hs_) + 1 if bw > 0 else 0  # height_field/utils.py height_field_to_mesh
+        mil = _get(terrain, "max_init_terrain_level")
+        c.terrain_max_init_level = -1 if mil is None else int(mil)
+        cur_terms = [_fname(t.func) for _, t in _terms(_get(cfg, "curriculum"))]
+        c.terrain_curriculum = int("terrain_levels_vel" in cur_terms and bool(_get(gen, "curriculum", False)))
+    elif ttype != "plane":
+        raise NotImplementedError(f"scene.terrain.terrain_type={ttype!r} is not supported (plane, or generator with a random-rough height field)")
+    elif "terrain_levels_vel" in [_fname(t.func) for _, t in _terms(_get(cfg, "curriculum"))]:
+        raise NotImplementedError("curriculum: terrain_levels_vel needs terrain_type='generator'")
+    if c.terrain_enable and cterms:
+        raise NotImplementedError("constraints: the Constraints-as-Terminations tail is not available on generated terrain")
 
     # ---- rewards (rough_env_cfg.py:18-62,112-120; flat_env_cfg.py:35-44; V/velocity_env_cfg.py:225-257) ----
     for i in range(len(REW_NAMES)):
@@ -474,7 +542,9 @@ class _ObservationManagerView:
     def __init__(self, env):
         self._env = env
         self.group_obs_dim = {"policy": (env.sim.obs_dim,)}
-        self.active_terms = {"policy": ["base_ang_vel", "projected_gravity", "velocity_commands", "joint_pos", "joint_vel", "actions"]}
+        k = env.kernel_cfg
+        self.active_terms = {"policy": (["base_lin_vel"] if k.obs_base_lin_vel else []) + ["base_ang_vel", "projected_gravity", "velocity_commands", "joint_pos",
+                                        "joint_vel", "actions"] + (["height_scan"] if k.obs_height_scan else [])}
 
     def compute(self):
         """ObservationManager.compute(): appends to the history like upstream (observation_manager.py:318-355)."""
@@ -622,7 +692,10 @@ class H1v2ManagerBasedRLEnv:
                 "Metrics/base_velocity/error_vel_xy", "Metrics/base_velocity/error_vel_yaw"]
             idx = [LOG_REW0 + s for s in self._rew_slots] + [LOG_TERM_TIMEOUT, LOG_TERM_CONTACT, LOG_ERR_XY, LOG_ERR_YAW]
             self._log_index = torch.tensor(idx, dtype=torch.long, device=self.device)
-        return dict(zip(self._log_keys, self.sim.log_buf[self._log_index].unbind(0)))
+        log = dict(zip(self._log_keys, self.sim.log_buf[self._log_index].unbind(0)))
+        if self.kernel_cfg.terrain_enable and self.kernel_cfg.terrain_curriculum:  # CurriculumManager: mdp.terrain_levels_vel returns the mean level
+            log["Curriculum/terrain_levels"] = self.sim.terrain_log_buf[1].clone()
+        return log
 
     def render(self, recompute: bool = False):
         return None

@@ -295,12 +295,130 @@ class SimulationCfg:
 
 
 make_lenient("isaaclab.sim", SimulationCfg=SimulationCfg)
-make_lenient("isaaclab.sensors")
-make_lenient("isaaclab.sensors.patterns")
-make_lenient("isaaclab.terrains")
+
+
+# ---------------------------------------------------------------- terrains / ray caster (cfg classes the Rough id's flatten_cfg reads)
+@configclass
+class SubTerrainBaseCfg:
+    """isaaclab.terrains.SubTerrainBaseCfg / HfTerrainBaseCfg fields [UPSTREAM 2.1.0]."""
+    function = None
+    proportion: float = 1.0
+    size: tuple = (10.0, 10.0)
+    flat_patch_sampling = None
+    border_width: float = 0.0
+    horizontal_scale: float = 0.1
+    vertical_scale: float = 0.005
+    slope_threshold = None
+
+
+@configclass
+class HfRandomUniformTerrainCfg(SubTerrainBaseCfg):
+    """height_field/hf_terrains_cfg.py [UPSTREAM]; used by packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:20-25."""
+    noise_range: tuple = MISSING
+    noise_step: float = MISSING
+    downsampled_scale = None
+
+
+@configclass
+class TerrainGeneratorCfg:
+    """isaaclab.terrains.TerrainGeneratorCfg [UPSTREAM]; instantiated by utils/mdp/terrains.py:11-28."""
+    seed = None
+    curriculum: bool = False
+    size: tuple = MISSING
+    border_width: float = 0.0
+    border_height: float = 1.0
+    num_rows: int = 1
+    num_cols: int = 1
+    color_scheme: str = "none"
+    horizontal_scale: float = 0.1
+    vertical_scale: float = 0.005
+    slope_threshold = 0.75
+    sub_terrains: dict = MISSING
+    difficulty_range: tuple = (0.0, 1.0)
+    use_cache: bool = False
+    cache_dir: str = "/tmp/isaaclab/terrains"
+
+
+@configclass
+class TerrainImporterCfg:
+    """isaaclab.terrains.TerrainImporterCfg [UPSTREAM]; instantiated by V/velocity_env_cfg.py:40-58."""
+    class_type = None
+    collision_group: int = -1
+    prim_path: str = MISSING
+    num_envs: int = 1
+    terrain_type: str = "generator"
+    terrain_generator = None
+    usd_path = None
+    env_spacing = None
+    visual_material = None
+    physics_material = None
+    max_init_terrain_level = None
+    debug_vis: bool = False
+
+
+@configclass
+class GridPatternCfg:
+    """isaaclab.sensors.patterns.GridPatternCfg [UPSTREAM]: rays over torch.arange(-size/2, size/2 + 1e-9, resolution), "xy" ordering."""
+    func = None
+    resolution: float = MISSING
+    size: tuple = MISSING
+    direction: tuple = (0.0, 0.0, -1.0)
+    ordering: str = "xy"
+
+
+@configclass
+class RayCasterCfg:
+    """isaaclab.sensors.RayCasterCfg [UPSTREAM]; instantiated by V/velocity_env_cfg.py:61-68."""
+
+    @configclass
+    class OffsetCfg:
+        pos: tuple = (0.0, 0.0, 0.0)
+        rot: tuple = (1.0, 0.0, 0.0, 0.0)
+
+    class_type = None
+    prim_path: str = MISSING
+    update_period: float = 0.0
+    history_length: int = 0
+    debug_vis: bool = False
+    mesh_prim_paths: list = MISSING
+    offset: OffsetCfg = OffsetCfg()
+    attach_yaw_only: bool = MISSING
+    pattern_cfg = MISSING
+    max_distance: float = 1e6
+    drift_range: tuple = (0.0, 0.0)
+    visualizer_cfg = None
+
+
+make_lenient("isaaclab.sensors", RayCasterCfg=RayCasterCfg)
+make_lenient("isaaclab.sensors.patterns", GridPatternCfg=GridPatternCfg)
+make_lenient("isaaclab.sensors.ray_caster", RayCasterCfg=RayCasterCfg)
+make_lenient("isaaclab.terrains", TerrainImporterCfg=TerrainImporterCfg, TerrainGeneratorCfg=TerrainGeneratorCfg, HfRandomUniformTerrainCfg=HfRandomUniformTerrainCfg)
 make_lenient("isaaclab.terrains.config")
-make_lenient("isaaclab.terrains.config.rough")
-make_lenient("isaaclab.terrains.terrain_generator_cfg")
+make_lenient("isaaclab.terrains.terrain_generator_cfg", TerrainGeneratorCfg=TerrainGeneratorCfg)
+
+
+class _RoughTerrainsModule(type(_me)):
+    """isaaclab.terrains.config.rough: ROUGH_TERRAINS_CFG resolves, at first use, to the reference's OWN in-tree generator cfg of
+    that name (packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:11-28, one random-rough height field) -- upstream's cfg of the
+    same name also holds mesh stairs / boxes / slopes, which the B200 backend does not simulate (flatten_cfg refuses them by name).
+    Without biped_tasks, the same values come from h1v2_isaac_b200.tasks."""
+
+    def __getattr__(self, name):
+        if name != "ROUGH_TERRAINS_CFG":
+            raise AttributeError(name)
+        try:
+            import importlib
+            cfg = importlib.import_module("biped_tasks.utils.mdp.terrains").ROUGH_TERRAINS_CFG
+        except Exception:  # noqa: BLE001
+            from h1v2_isaac_b200.tasks import rough_terrains_cfg
+            cfg = rough_terrains_cfg()
+        setattr(self, name, cfg)
+        return cfg
+
+
+_rough = _RoughTerrainsModule("isaaclab.terrains.config.rough")
+sys.modules[_rough.__name__] = _rough
+sys.modules["isaaclab.terrains.config"].rough = _rough
 
 
 # ---------------------------------------------------------------- app

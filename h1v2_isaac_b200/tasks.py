@@ -11,6 +11,7 @@ from __future__ import annotations
 TASK_ID = "Isaac-Velocity-Flat-H12_12dof-v0"
 RSL_TASK_ID = "Isaac-Velocity-Rsl-H12_12dof-v0"
 CAT_TASK_ID = "Isaac-Velocity-CaT-Flat-H12_12dof-v0"
+ROUGH_TASK_ID = "Isaac-Velocity-Rough-H12_12dof-v0"
 # reward term names of C12/cat_env_cfg.py:306-333 by kernel slot
 CAT_REW_NAMES = {14: "track_lin_vel_xy_exp", 15: "track_ang_vel_z_exp", 8: "dof_torques_l2", 9: "joint_acc_l2", 17: "joint_vel_l2", 10: "action_rate_l2",
                  6: "joint_deviation_l1"}
@@ -60,6 +61,45 @@ def rsl_play_env_cfg(num_envs: int = 100, device: str = "cuda:0"):
     c.cmd_lin_y[0] = c.cmd_lin_y[1] = 0.0
     c.cmd_ang_z[0] = c.cmd_ang_z[1] = 0.0
     return env_cfg_from_config(c, num_envs, device, rew_names=RSL_REW_NAMES, curriculum=RSL_CURRICULUM, curriculum_steps=24 * 5000)
+
+
+def rough_terrains_cfg(c=None):
+    """The reference's in-tree terrain generator cfg (packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:11-28) rebuilt from the
+    resolved kernel config, for machines without biped_tasks."""
+    from . import shims
+    shims.install()
+    from isaaclab.terrains import HfRandomUniformTerrainCfg, TerrainGeneratorCfg
+    if c is None:
+        from ._capi import rough_config
+        c = rough_config()
+    hs, vs = float(c.terrain_hscale), float(c.terrain_vscale)
+    return TerrainGeneratorCfg(
+        size=(c.terrain_tile_size, c.terrain_tile_size), border_width=20.0, num_rows=c.terrain_rows, num_cols=c.terrain_cols, horizontal_scale=hs,
+        vertical_scale=vs, slope_threshold=0.75, use_cache=False, curriculum=bool(c.terrain_curriculum),
+        sub_terrains={"random_rough": HfRandomUniformTerrainCfg(
+            proportion=1.0, noise_range=(c.terrain_level_min * vs, c.terrain_level_max * vs), noise_step=c.terrain_level_step * vs,
+            border_width=(c.terrain_border_px - 0.5) * hs if c.terrain_border_px > 0 else 0.0)})
+
+
+def rough_env_cfg(num_envs: int = 4096, device: str = "cuda:0"):
+    """Isaac-Velocity-Rough-H12_12dof-v0 (C12/rough_env_cfg.py:65-125) with the in-tree terrain generator cfg."""
+    from ._capi import rough_config
+    return env_cfg_from_config(rough_config(), num_envs, device)
+
+
+def rough_play_env_cfg(num_envs: int = 50, device: str = "cuda:0"):
+    """Isaac-Velocity-Rough-H12_12dof-Play-v0 (C12/rough_env_cfg.py:128-156): 50 envs, 40 s episodes, 5 x 5 tiles without curriculum and
+    envs spread over all levels, forward command 1 m/s, heading 0, no observation noise."""
+    from ._capi import rough_config
+    c = rough_config()
+    c.episode_length_s = 40.0
+    c.terrain_max_init_level = -1
+    c.terrain_rows = c.terrain_cols = 5
+    c.terrain_curriculum = 0
+    c.cmd_lin_x[0] = c.cmd_lin_x[1] = 1.0
+    c.cmd_heading[0] = c.cmd_heading[1] = 0.0
+    c.enable_corruption = 0
+    return env_cfg_from_config(c, num_envs, device)
 
 
 def cat_config():
@@ -127,7 +167,19 @@ def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_nam
         soft_joint_pos_limit_factor=c.soft_limit_factor, actuators=actuators)
     scene = InteractiveSceneCfg(num_envs=num_envs, env_spacing=c.env_spacing)
     object.__setattr__(scene, "robot", robot)
-    object.__setattr__(scene, "terrain", Placeholder(terrain_type="plane", physics_material=Placeholder(static_friction=1.0, dynamic_friction=1.0)))
+    ground = Placeholder(static_friction=1.0, dynamic_friction=1.0)
+    if c.terrain_enable:  # V/velocity_env_cfg.py:40-58
+        from isaaclab.terrains import TerrainImporterCfg
+        object.__setattr__(scene, "terrain", TerrainImporterCfg(
+            prim_path="/World/ground", terrain_type="generator", terrain_generator=rough_terrains_cfg(c),
+            max_init_terrain_level=(None if c.terrain_max_init_level < 0 else c.terrain_max_init_level), physics_material=ground))
+    else:
+        object.__setattr__(scene, "terrain", Placeholder(terrain_type="plane", physics_material=ground))
+    if c.obs_height_scan:  # V/velocity_env_cfg.py:61-68, C12/rough_env_cfg.py:74-75
+        from isaaclab.sensors import RayCasterCfg, patterns
+        object.__setattr__(scene, "height_scanner", RayCasterCfg(
+            prim_path="{ENV_REGEX_NS}/Robot/torso_link", offset=RayCasterCfg.OffsetCfg(pos=(0.0, 0.0, 20.0)), attach_yaw_only=True,
+            pattern_cfg=patterns.GridPatternCfg(resolution=c.scan_resolution, size=[c.scan_size[0], c.scan_size[1]]), mesh_prim_paths=["/World/ground"]))
 
     def obs(func, n=0.0, s=1.0, joints=False):
         t = ObservationTermCfg(func=func, noise=Unoise(n_min=-n, n_max=n) if n else None, scale=None if s == 1.0 else s)
@@ -135,16 +187,25 @@ def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_nam
             t.params = {"asset_cfg": SceneEntityCfg("robot", joint_names=[JOINT_NAMES[j] for j in c.joint_perm], preserve_order=True)}
         return t
 
-    policy = ObservationGroupCfg(concatenate_terms=True, enable_corruption=bool(c.enable_corruption), history_length=c.history_length)
-    for k, v in (("base_ang_vel", obs(mdp.base_ang_vel, c.noise_ang_vel, c.scale_ang_vel)),
+    rough_obs = bool(c.obs_base_lin_vel or c.obs_height_scan)
+    policy = ObservationGroupCfg(concatenate_terms=True, enable_corruption=bool(c.enable_corruption), history_length=(0 if rough_obs else c.history_length))
+    lead, tail = [], []
+    if c.obs_base_lin_vel:  # V/velocity_env_cfg.py:123
+        lead = [("base_lin_vel", obs(mdp.base_lin_vel, c.noise_lin_vel, c.scale_lin_vel))]
+    if c.obs_height_scan:   # V/velocity_env_cfg.py:133-138
+        t = obs(mdp.height_scan, c.noise_height_scan, c.scale_height_scan)
+        t.params = {"sensor_cfg": SceneEntityCfg("height_scanner")}
+        t.clip = (c.scan_clip[0], c.scan_clip[1])
+        tail = [("height_scan", t)]
+    for k, v in lead + [("base_ang_vel", obs(mdp.base_ang_vel, c.noise_ang_vel, c.scale_ang_vel)),
                  ("projected_gravity", obs(mdp.projected_gravity, c.noise_gravity, c.scale_gravity)),
                  ("velocity_commands", obs(mdp.generated_commands, 0.0, c.scale_cmd)),
                  ("joint_pos", obs(mdp.joint_pos_rel, c.noise_joint_pos, c.scale_joint_pos, True)),
                  ("joint_vel", obs(mdp.joint_vel_rel, c.noise_joint_vel, c.scale_joint_vel, True)),
-                 ("actions", obs(mdp.last_action, 0.0, c.scale_action))):
+                 ("actions", obs(mdp.last_action, 0.0, c.scale_action))] + tail:
         object.__setattr__(policy, k, v)
-    policy.__configclass_fields__ = lambda: ["concatenate_terms", "enable_corruption", "history_length", "base_ang_vel", "projected_gravity",
-                                             "velocity_commands", "joint_pos", "joint_vel", "actions"]
+    policy.__configclass_fields__ = lambda: ["concatenate_terms", "enable_corruption", "history_length"] + [k for k, _ in lead] + [
+        "base_ang_vel", "projected_gravity", "velocity_commands", "joint_pos", "joint_vel", "actions"] + [k for k, _ in tail]
 
     feet = SceneEntityCfg("contact_forces", body_names=SLOT_BODIES[:2])
     rew_params = {
@@ -177,6 +238,9 @@ def env_cfg_from_config(c, num_envs: int = 4096, device: str = "cuda:0", rew_nam
     rewards = bag(**rew)
     cur = bag(**{n: ienvs_managers().CurriculumTermCfg(func=mdp.modify_reward_weight, params={
         "term_name": n, "weight": rew[n].weight, "num_steps": curriculum_steps}) for n in curriculum}) if curriculum else None
+
+    if c.terrain_enable and c.terrain_curriculum:  # V/velocity_env_cfg.py:275
+        cur = bag(**{**(cur.__dict__ if cur is not None else {}), "terrain_levels": ienvs_managers().CurriculumTermCfg(func=lmdp.terrain_levels_vel)})
 
     terminations = bag(
         time_out=TerminationTermCfg(func=mdp.time_out, time_out=True),
@@ -274,6 +338,7 @@ def register() -> bool:
     import gymnasium as gym
     done = False
     for tid, env_cfg in ((TASK_ID, "default_env_cfg"), (RSL_TASK_ID, "rsl_env_cfg"), (CAT_TASK_ID, "cat_env_cfg"),
+                         (ROUGH_TASK_ID, "rough_env_cfg"), (ROUGH_TASK_ID.replace("-v0", "-Play-v0"), "rough_play_env_cfg"),  # C12/__init__.py:17-36
                          (TASK_ID.replace("-v0", "-Play-v0"), "flat_play_env_cfg"), (RSL_TASK_ID.replace("-v0", "-Play-v0"), "rsl_play_env_cfg"),
                          (CAT_TASK_ID.replace("-v0", "-Play-v0"), "cat_play_env_cfg")):  # C12/__init__.py:76-82
         try:

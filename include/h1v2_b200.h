@@ -1,6 +1,7 @@
 /*
  * h1v2_b200.h -- C-ABI of the B200-native batched simulation backend for the Unitree H1-2
- * velocity-tracking tasks  Isaac-Velocity-Flat-H12_12dof-v0  and  Isaac-Velocity-Rsl-H12_12dof-v0.
+ * velocity-tracking tasks  Isaac-Velocity-Flat-H12_12dof-v0,  Isaac-Velocity-Rsl-H12_12dof-v0,
+ * Isaac-Velocity-CaT-Flat-H12_12dof-v0  and  Isaac-Velocity-Rough-H12_12dof-v0.
  *
  * The reference (olivier-stasse/h1v2-Isaac) has no FFI of its own: its seam is the Python
  * ManagerBasedRLEnv.step contract.  Each entry point below names the reference interface it replaces
@@ -16,6 +17,12 @@
  *                            packages/biped_assets/biped_assets/robots/h12.py:18-114
  *   h1v2_rsl_config    <- resolved cfg of the Rsl id
  *                            .../velocity/config/h12_12dof/rsl_env_cfg.py:44-540, robots/h12.py:117-206
+ *   h1v2_rough_config  <- resolved cfg of the Rough id
+ *                            .../velocity/config/h12_12dof/rough_env_cfg.py:65-125, .../velocity/velocity_env_cfg.py:36-324,
+ *                            packages/biped_tasks/biped_tasks/utils/mdp/terrains.py:11-28
+ *   h1v2_get_terrain /
+ *   h1v2_set_terrain   <- TerrainImporter / TerrainGenerator height field (upstream isaaclab; cfg utils/mdp/terrains.py:11-28)
+ *   h1v2_get_terrain_log <- CurriculumManager: mdp.terrain_levels_vel   .../velocity/mdp/curriculums.py:21-52
  *   h1v2_set_reward_weights <- CurriculumManager: mdp.modify_reward_weight   rsl_env_cfg.py:447-497
  *   h1v2_step          <- ManagerBasedRLEnv.step(action)         utils/cat/cat_env.py:95-193
  *   h1v2_step_host     <- same call with HOST buffers (what a non-torch caller binds; used for e2e timing)
@@ -47,6 +54,7 @@ extern "C" {
 #define H1V2_NUM_REW 22      /* reward-term slots (union of the Flat / base / Rsl cfgs) */
 #define H1V2_NUM_SLOT 6      /* contact-sensor bodies: 0,1 feet L/R; 2,3 knee_link L/R; 4 torso_link; 5 pelvis */
 #define H1V2_OBS_TERM_DIM 45 /* ang_vel 3 | proj_g 3 | cmd 3 | q-q0 12 | qd 12 | last_action 12 */
+#define H1V2_MAX_SCAN 256   /* most height-scan rays per env (the Rough id has 17 x 11 = 187) */
 #define H1V2_MAX_HISTORY 10 /* the reference tasks use 10 (Flat), 6 (Rsl) and 1 (deploy) */
 #define H1V2_LOG_DIM 32      /* see h1v2_get_log */
 #define H1V2_NUM_CSTR 10     /* constraint terms of the CaT tail, order of H1V2_CSTR_* */
@@ -213,6 +221,23 @@ typedef struct H1v2Config {
                                           error a residual gradient leaves after the implicit update.  MuJoCo's own test (solver_tolerance, on
                                           the gradient norm scaled by meaninertia * nv = 234) lets 2.3e-3 N m pass on an ankle of 0.0136 kg m^2:
                                           8.5e-4 rad/s, the whole single-step tolerance of the north star (profiles/r2_notes.md) */
+  /* ---- rough terrain (velocity_env_cfg.py:40-68, utils/mdp/terrains.py:11-28, mdp/curriculums.py:21-52); all 0 on the flat ids ---- */
+  int32_t terrain_enable;              /* 1: generated height field instead of the plane; positions are relative to the env's tile origin */
+  int32_t terrain_rows, terrain_cols;  /* curriculum levels x terrain types: 10 x 20 tiles */
+  float terrain_tile_size;             /* 8 m (square tiles) */
+  float terrain_hscale, terrain_vscale;/* 0.1 m grid, 0.005 m height unit */
+  int32_t terrain_level_min, terrain_level_max, terrain_level_step; /* HfRandomUniformTerrainCfg noise_range / noise_step in height
+                                          units, as upstream's int() conversions give them: 0, 4, 1 (0 .. 0.02 m in 5 mm steps) */
+  int32_t terrain_border_px;           /* flat rim of every tile in grid cells: int(border_width / hscale) + 1 = 3 */
+  int32_t terrain_max_init_level;      /* TerrainImporterCfg.max_init_terrain_level = 5 (< 0: rows - 1) */
+  int32_t terrain_curriculum;          /* 1: mdp.terrain_levels_vel moves an env's level on every reset */
+  int32_t obs_base_lin_vel;            /* 1: base_lin_vel leads the observation (velocity_env_cfg.py:123) */
+  float noise_lin_vel, scale_lin_vel;  /* 0.1, 1 */
+  int32_t obs_height_scan;             /* 1: height_scan ends the observation (velocity_env_cfg.py:133-138): GridPattern rays about the
+                                          scanner body (torso_link == pelvis frame, fixed joint), yaw-aligned */
+  float scan_size[2], scan_resolution; /* 1.6 x 1.0 m at 0.1 m -> 17 x 11 = 187 rays, x fastest */
+  float scan_offset;                   /* mdp.height_scan offset 0.5: value = sensor z - hit z - offset */
+  float noise_height_scan, scale_height_scan, scan_clip[2]; /* 0.1, 1, (-1, 1): noise, then clip, then scale (ObservationManager order) */
   int32_t reserved[7];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
                                           [1] > 0: line-search evaluations per Newton iteration (default 6);
                                           [2] in {1,2,4,8,16}: envs per warp (default: chosen from n_envs); rest 0 */
@@ -255,6 +280,9 @@ typedef struct H1v2State {
   float* pre_reset_qpos;   /* [N,19] state after the physics substeps of the last step, BEFORE any reset */
   float* pre_reset_qvel;   /* [N,18] */
   float* pre_reset_timers; /* [N,2,4] */
+  /* rough terrain (terrain_enable): the env's curriculum level (row of the tile grid; get and set) and its terrain type (column; get only) */
+  int32_t* terrain_level;  /* [N] */
+  int32_t* terrain_type;   /* [N] */
 } H1v2State;
 
 typedef struct H1v2Handle H1v2Handle;
@@ -262,6 +290,8 @@ typedef struct H1v2Handle H1v2Handle;
 int h1v2_default_config(H1v2Config* cfg); /* resolved cfg of Isaac-Velocity-Flat-H12_12dof-v0 */
 int h1v2_rsl_config(H1v2Config* cfg);     /* resolved cfg of Isaac-Velocity-Rsl-H12_12dof-v0 (config/h12_12dof/rsl_env_cfg.py:503-540) */
 int h1v2_cat_config(H1v2Config* cfg);     /* resolved cfg of Isaac-Velocity-CaT-Flat-H12_12dof-v0 (config/h12_12dof/cat_env_cfg.py:528-565) */
+int h1v2_rough_config(H1v2Config* cfg);   /* resolved cfg of Isaac-Velocity-Rough-H12_12dof-v0 (config/h12_12dof/rough_env_cfg.py:65-125) with the
+                                             reference's in-tree terrain generator cfg (utils/mdp/terrains.py:11-28) */
 int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t seed, H1v2Handle** out);
 void h1v2_destroy(H1v2Handle* h);
 const char* h1v2_last_error(void);
@@ -322,6 +352,17 @@ int h1v2_get_cat_log_host(H1v2Handle* h, float* out /*[2 * H1V2_NUM_CSTR + 1]*/)
  * envs reset in the last cat step), for callers that must not synchronise */
 int h1v2_get_cat_log(H1v2Handle* h, const float** acc_dev);
 
+/* Rough terrain (cfg.terrain_enable).  The height field is a grid of [rows * px + 1][cols * px + 1] vertices (px = tile_size / hscale,
+ * second index fastest, metres) triangulated like isaaclab's convert_height_field_to_mesh (cell diagonal from (i, j) to (i+1, j+1));
+ * vertex (i, j) sits at x = i * hscale - rows * tile / 2, y = j * hscale - cols * tile / 2; outside the grid the ground is flat at 0
+ * (the 20 m border).  h1v2_create generates it from the seed (uniform levels on the interior vertices of every tile, flat tile rims:
+ * HfRandomUniformTerrainCfg); h1v2_set_terrain replaces it with the caller's grid, e.g. the one a real isaaclab TerrainGenerator made.
+ * Both take / fill HOST arrays and synchronise.  dims = {grid_x, grid_y}. */
+int h1v2_terrain_dims(const H1v2Handle* h, int32_t dims[2]);
+int h1v2_get_terrain(H1v2Handle* h, float* heights);
+int h1v2_set_terrain(H1v2Handle* h, const float* heights);
+/* device pointer to float[2]: [1] = Curriculum/terrain_levels, the mean level over all envs after the last step (curriculums.py:52) */
+int h1v2_get_terrain_log(H1v2Handle* h, const float** log_dev);
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream);
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);
 /* device pointer to the float[H1V2_LOG_DIM] log vector (valid for the handle's lifetime, updated by step) */

@@ -86,6 +86,7 @@ void h1v2o_rng4(uint64_t seed, int64_t env_gid, uint64_t step, uint32_t stream, 
 #define STREAM_RESET 1u
 #define STREAM_CMD 2u
 #define STREAM_EVENT 3u
+#define STREAM_TERRAIN 5u
 #define STREAM_ACTIONS 7u
 
 static inline float uni(float u, float lo, float hi) { return fmaf(hi - lo, u, lo); } /* fused, like the kernel: draws are bit-identical */
@@ -104,6 +105,7 @@ typedef struct {
   int64_t ep_len;
   double friction, mass_add;
   float push_left;
+  int level, type; /* rough terrain: row (curriculum level) and column (terrain type) of the env's tile */
   /* diagnostics */
   double slot_force[NSLOT][3], slot_hist[NSLOT][3], applied_tau[NJ], joint_acc[NJ], rew_terms[NREW], foot_vel[2][3];
   double slot_hist_diag[NSLOT][3]; /* slot_hist as the terminations / rewards of the last step saw it (before any reset cleared it) */
@@ -111,6 +113,7 @@ typedef struct {
   double newton_resid;
   double min_abs_dist; /* smallest |signed distance| of any contact candidate at a substep start during the last step */
   double min_limit_dist; /* same for joint-limit activation */
+  double min_tri_margin; /* rough terrain: distance (cells) of a contact candidate near the ground to a triangle boundary of the height field */
 } OEnv;
 
 struct H1v2Oracle {
@@ -125,6 +128,11 @@ struct H1v2Oracle {
   int max_newton_iters;
   int nthreads;
   int dz_prev; /* envs inside the command dead zone at the end of the previous step (UniformVelocityCommandWithDeadzone balancing) */
+  /* rough terrain (cfg.terrain_enable): height grid [gx][gy] in metres, tile-origin heights [rows][cols] */
+  float* terrain;
+  float* origin_z;
+  int gx, gy, npx;
+  float terrain_level_mean;
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -372,8 +380,97 @@ static void kb_from_solref(const float* solref, const float* solimp, double dt, 
   *B = 2.0 / (bd > MINVAL ? bd : MINVAL);
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rough terrain.  Restates what upstream isaaclab builds from the reference's generator cfg (T/utils/mdp/terrains.py:11-28 through
+ * V/velocity_env_cfg.py:40-58): a grid of rows x cols square tiles (terrain_generator.py curriculum layout: row = difficulty level,
+ * column = terrain type), every tile a height field of tile/hscale + 1 vertices per side whose rim of border_px vertices is flat and
+ * whose interior vertices hold independent uniform draws from {level_min, level_min + step, .. level_max} * vscale
+ * (height_field/hf_terrains.py random_uniform_terrain with downsampled_scale == horizontal_scale; the @height_field_to_mesh decorator
+ * adds the rim), meshed by convert_height_field_to_mesh: every cell is split along the diagonal (i,j) -> (i+1,j+1).  The mesh is
+ * centred on the world origin; around it lies the flat border at z = 0 (terrain_generator.py _add_terrain_border).  The tile origin
+ * is the tile centre at the highest vertex of the central 2 m x 2 m patch (height_field/utils.py).  [UPSTREAM, from memory of
+ * isaaclab 2.1.0; the draws themselves come from this backend's Philox stream, not numpy's generator.] */
+static int terrain_npx(const H1v2Config* c) { return (int)lroundf(c->terrain_tile_size / c->terrain_hscale); }
+
+static void terrain_origin_heights(H1v2Oracle* o) {
+  const H1v2Config* c = &o->cfg;
+  const int npx = o->npx;
+  const int a1 = (int)((c->terrain_tile_size * 0.5f - 1.0f) / c->terrain_hscale), a2 = (int)((c->terrain_tile_size * 0.5f + 1.0f) / c->terrain_hscale);
+  for (int r = 0; r < c->terrain_rows; r++)
+    for (int q = 0; q < c->terrain_cols; q++) {
+      float m = -1e30f;
+      for (int a = a1; a < a2; a++)
+        for (int b = a1; b < a2; b++) {
+          float h = o->terrain[(size_t)(r * npx + a) * o->gy + (q * npx + b)];
+          if (h > m) m = h;
+        }
+      o->origin_z[r * c->terrain_cols + q] = m;
+    }
+}
+
+static void terrain_generate(H1v2Oracle* o) {
+  const H1v2Config* c = &o->cfg;
+  const int npx = o->npx, bp = c->terrain_border_px;
+  const int nlev = (c->terrain_level_max - c->terrain_level_min) / (c->terrain_level_step > 0 ? c->terrain_level_step : 1) + 1;
+  for (int i = 0; i < o->gx; i++)
+    for (int j0 = 0; j0 < o->gy; j0 += 4) {
+      float u[4];
+      rng4(o->seed, (int64_t)i, (uint64_t)(j0 / 4), STREAM_TERRAIN, 0, u);
+      for (int k = 0; k < 4 && j0 + k < o->gy; k++) {
+        const int j = j0 + k, a = i % npx, b = j % npx;
+        /* rim vertices of a tile (shared with its neighbour) are flat; the last grid line belongs to the last tile's rim */
+        const int rim = a < bp || a > npx - bp || b < bp || b > npx - bp || i == o->gx - 1 || j == o->gy - 1;
+        int lev = (int)(u[k] * (float)nlev);
+        if (lev > nlev - 1) lev = nlev - 1;
+        o->terrain[(size_t)i * o->gy + j] = rim ? 0.0f : (float)(c->terrain_level_min + lev * c->terrain_level_step) * c->terrain_vscale;
+      }
+    }
+  terrain_origin_heights(o);
+}
+
+/* height (relative to the tile origin's z) and unit normal of the terrain under the point (lx, ly) given relative to the origin of tile
+ * (level, type).  margin: distance (in cells) of the point from the nearest cell edge or diagonal, where the triangle changes */
+static void terrain_query(const H1v2Oracle* o, int level, int type, double lx, double ly, double* h, double n[3], double* margin) {
+  const H1v2Config* c = &o->cfg;
+  const double half = (double)(0.5f * c->terrain_tile_size), inv = (double)(1.0f / c->terrain_hscale); /* the fp32 constants the kernel holds */
+  const double oz = o->origin_z[level * c->terrain_cols + type];
+  double a = (lx + half) * inv, b = (ly + half) * inv;
+  double fa = floor(a), fb = floor(b);
+  long i = (long)level * o->npx + (long)fa, j = (long)type * o->npx + (long)fb;
+  double u = a - fa, v = b - fb;
+  n[0] = 0; n[1] = 0; n[2] = 1;
+  if (margin) *margin = 1.0;
+  if (i < 0 || j < 0 || i >= o->gx - 1 || j >= o->gy - 1) { *h = -oz; return; } /* the flat border around the tiles */
+  const float* H = o->terrain;
+  double h00 = H[(size_t)i * o->gy + j], h10 = H[(size_t)(i + 1) * o->gy + j], h01 = H[(size_t)i * o->gy + j + 1], h11 = H[(size_t)(i + 1) * o->gy + j + 1];
+  double dx, dy;
+  if (v >= u) { dx = h11 - h01; dy = h01 - h00; } else { dx = h10 - h00; dy = h11 - h10; }
+  *h = h00 + u * dx + v * dy - oz;
+  double gx = dx * inv, gy = dy * inv, s = 1.0 / sqrt(1.0 + gx * gx + gy * gy);
+  n[0] = -gx * s; n[1] = -gy * s; n[2] = s;
+  if (margin) {
+    double m = fmin(fmin(u, 1 - u), fmin(v, 1 - v));
+    *margin = fmin(m, fabs(u - v));
+  }
+}
+
+/* contact frame from the normal, MuJoCo mju_makeFrame: t1 = the y axis (z if the normal is within 30 deg of y) made orthogonal to n,
+ * t2 = n x t1.  On the plane: t1 = y, t2 = -x. */
+static void contact_frame(const double n[3], double t1[3], double t2[3]) {
+  double y[3] = {0, 0, 0};
+  if (n[1] < 0.5 && n[1] > -0.5) y[1] = 1; else y[2] = 1;
+  double d = dot3(n, y), nn = 0;
+  for (int i = 0; i < 3; i++) { t1[i] = y[i] - n[i] * d; nn += t1[i] * t1[i]; }
+  nn = sqrt(nn);
+  for (int i = 0; i < 3; i++) t1[i] /= nn;
+  cross3(n, t1, t2);
+}
+
 typedef struct {
   int n;
+  double dirv[MAXROW][3]; /* world direction of a contact row's force: n +- mu t */
+  double min_tri_margin;  /* rough terrain: smallest distance (cells) of an active or nearly active contact point to a triangle boundary */
   double J[MAXROW][NV];
   double aref[MAXROW], R[MAXROW], D[MAXROW], floss[MAXROW];
   int type[MAXROW];  /* 0 friction-loss (two-sided box), 1 unilateral (limit / pyramid edge) */
@@ -395,11 +492,12 @@ static double row_eval(const Rows* r, int i, double jar, double* force, int* act
   *force = 0; *active = 0; return 0;
 }
 
-static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows* r) {
+static void build_rows(const H1v2Oracle* o, const Kin* k, const OEnv* e, Rows* r) {
+  const H1v2Config* cfg = &o->cfg;
   const double dt = cfg->sim_dt;
   const double* qvel = e->qvel;
   r->n = 0;
-  r->min_abs_dist = 1e30; r->min_limit_dist = 1e30;
+  r->min_abs_dist = 1e30; r->min_limit_dist = 1e30; r->min_tri_margin = 1.0;
   double K, B;
   /* (a) dof friction loss */
   kb_from_solref(cfg->floss_solref, cfg->floss_solimp, dt, &K, &B);
@@ -444,10 +542,16 @@ static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows*
     double off[3], ctr[3];
     matvec3(k->R[b], &h1v2_coll[c][1], off);
     for (int i = 0; i < 3; i++) ctr[i] = k->x[b][i] + off[i];
-    double dist = ctr[2] - rad;
+    double nrm[3] = {0, 0, 1}, hterr = 0, tri = 1.0;
+    if (cfg->terrain_enable) terrain_query(o, e->level, e->type, ctr[0], ctr[1], &hterr, nrm, &tri);
+    /* point / sphere against the plane of the triangle under it: distance along the plane normal */
+    double dist = cfg->terrain_enable ? (ctr[2] - hterr) * nrm[2] - rad : ctr[2] - rad;
     if (fabs(dist) < r->min_abs_dist) r->min_abs_dist = fabs(dist);
+    if (dist < 0.02 && tri < r->min_tri_margin) r->min_tri_margin = tri;
     if (dist >= 0) continue;
-    double p[3] = {ctr[0], ctr[1], 0.5 * dist}; /* midway between the surfaces */
+    double p[3] = {ctr[0], ctr[1], 0.5 * dist}; /* midway between the surfaces: centre - n (rad + dist / 2) */
+    if (cfg->terrain_enable)
+      for (int i = 0; i < 3; i++) p[i] = ctr[i] - nrm[i] * (rad + 0.5 * dist);
     /* translational jacobian of the body-fixed point at p: v = v_O + w x p */
     double Jp[3][NV];
     for (int d = 0; d < NV; d++) {
@@ -461,13 +565,31 @@ static void build_rows(const H1v2Config* cfg, const Kin* k, const OEnv* e, Rows*
     double dA = tran + mu * mu * tran;
     double R0 = fmax(MINVAL, (1 - imp) * dA / imp);
     double Rpy = fmax(MINVAL, 2 * mu * mu * R0);
-    /* edges: n + mu*t1, n - mu*t1, n + mu*t2, n - mu*t2 with n=z, t1=y, t2=-x (mju_makeFrame) */
-    static const double ex[4] = {0, 0, -1, 1}, ey[4] = {1, -1, 0, 0};
+    /* edges: n + mu*t1, n - mu*t1, n + mu*t2, n - mu*t2 (mju_makeFrame; on the plane n = z, t1 = y, t2 = -x) */
+    if (!cfg->terrain_enable) { /* the plane: the arithmetic of the flat ids, operation for operation (profiles/roofline.json counts it) */
+      static const double ex[4] = {0, 0, -1, 1}, ey[4] = {1, -1, 0, 0};
+      for (int ed = 0; ed < 4; ed++) {
+        int i = r->n++;
+        double vel = 0;
+        for (int d = 0; d < NV; d++) {
+          r->J[i][d] = Jp[2][d] + mu * (ex[ed] * Jp[0][d] + ey[ed] * Jp[1][d]);
+          vel += r->J[i][d] * qvel[d];
+        }
+        r->aref[i] = -B * vel - K * imp * dist;
+        r->R[i] = Rpy; r->D[i] = 1.0 / Rpy; r->floss[i] = 0; r->type[i] = 1; r->coll[i] = c; r->edge[i] = ed;
+      }
+      continue;
+    }
+    double t1[3], t2[3];
+    contact_frame(nrm, t1, t2);
     for (int ed = 0; ed < 4; ed++) {
       int i = r->n++;
+      const double* t = ed < 2 ? t1 : t2;
+      const double sg = (ed & 1) ? -1.0 : 1.0;
+      for (int a = 0; a < 3; a++) r->dirv[i][a] = nrm[a] + mu * sg * t[a];
       double vel = 0;
       for (int d = 0; d < NV; d++) {
-        r->J[i][d] = Jp[2][d] + mu * (ex[ed] * Jp[0][d] + ey[ed] * Jp[1][d]);
+        r->J[i][d] = r->dirv[i][0] * Jp[0][d] + r->dirv[i][1] * Jp[1][d] + r->dirv[i][2] * Jp[2][d];
         vel += r->J[i][d] * qvel[d];
       }
       r->aref[i] = -B * vel - K * imp * dist;
@@ -603,23 +725,28 @@ static void physics_substep(const H1v2Oracle* o, OEnv* e, const double ctrl[NJ])
   memcpy(qacc_s, fs, sizeof(fs));
   chol_solve(L, NV, qacc_s);
   static _Thread_local Rows rows;
-  build_rows(cfg, &k, e, &rows);
+  build_rows(o, &k, e, &rows);
   if (rows.min_abs_dist < e->min_abs_dist) e->min_abs_dist = rows.min_abs_dist;
+  if (rows.min_tri_margin < e->min_tri_margin) e->min_tri_margin = rows.min_tri_margin;
   if (rows.min_limit_dist < e->min_limit_dist) e->min_limit_dist = rows.min_limit_dist;
   double qacc[NV];
   solve_constraints(o, M, qacc_s, &rows, qacc, &e->newton_iters, &e->newton_resid);
   /* constraint force and per-slot net contact force */
   double fc[NV] = {0};
   memset(e->slot_force, 0, sizeof(e->slot_force));
-  static const double ex[4] = {0, 0, -1, 1}, ey[4] = {1, -1, 0, 0};
   for (int i = 0; i < rows.n; i++) {
     for (int d = 0; d < NV; d++) fc[d] += rows.J[i][d] * rows.force[i];
-    if (rows.coll[i] >= 0) {
+    if (rows.coll[i] >= 0) { /* pyramid edge force f along n +- mu t */
       int slot = (int)h1v2_coll[rows.coll[i]][5];
-      double f = rows.force[i], mu = e->friction;
-      e->slot_force[slot][0] += f * mu * ex[rows.edge[i]];
-      e->slot_force[slot][1] += f * mu * ey[rows.edge[i]];
-      e->slot_force[slot][2] += f;
+      if (cfg->terrain_enable) {
+        for (int a = 0; a < 3; a++) e->slot_force[slot][a] += rows.force[i] * rows.dirv[i][a];
+      } else { /* the plane: n = z, t1 = y, t2 = -x */
+        static const double ex[4] = {0, 0, -1, 1}, ey[4] = {1, -1, 0, 0};
+        double f = rows.force[i], mu = e->friction;
+        e->slot_force[slot][0] += f * mu * ex[rows.edge[i]];
+        e->slot_force[slot][1] += f * mu * ey[rows.edge[i]];
+        e->slot_force[slot][2] += f;
+      }
     }
   }
   /* implicitfast: (M + h*diag(damping)) qacc = qfrc_smooth + qfrc_constraint */
@@ -688,10 +815,32 @@ static void resample_command(H1v2Oracle* o, int ei, uint32_t block0) {
   e->is_standing = v[1] <= c->rel_standing_envs;
 }
 
+/* mdp.terrain_levels_vel (V/mdp/curriculums.py:21-52) + TerrainImporter.update_env_origins [UPSTREAM]: evaluated in _reset_idx on the
+ * state the episode ended in.  fp32 like the torch tensors it runs on; the position is relative to the env origin already. */
+static void terrain_curriculum(H1v2Oracle* o, int ei) {
+  OEnv* e = &o->env[ei];
+  const H1v2Config* c = &o->cfg;
+  if (!c->terrain_enable || !c->terrain_curriculum) return;
+  const float x = (float)e->qpos[0], y = (float)e->qpos[1];
+  const float dist = sqrtf(fmaf(y, y, x * x));
+  const float cn = sqrtf(fmaf(e->cmd[1], e->cmd[1], e->cmd[0] * e->cmd[0]));
+  const int up = dist > c->terrain_tile_size * 0.5f;
+  const int down = (dist < cn * c->episode_length_s * 0.5f) && !up;
+  int lev = e->level + up - down;
+  if (lev >= c->terrain_rows) { /* robots that solve the last level are sent to a random one */
+    float u[4];
+    rng4(o->seed, c->env_id_offset + ei, o->step_counter, STREAM_RESET, 10, u);
+    lev = (int)(u[0] * (float)c->terrain_rows);
+    if (lev > c->terrain_rows - 1) lev = c->terrain_rows - 1;
+  } else if (lev < 0) lev = 0;
+  e->level = lev;
+}
+
 static void reset_env(H1v2Oracle* o, int ei) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
   const int64_t gid = c->env_id_offset + ei;
+  terrain_curriculum(o, ei); /* CurriculumManager.compute(env_ids) runs first in _reset_idx (cat_env.py:197-200) */
   float u0[4], u1[4], u2[4], u3[4];
   rng4(o->seed, gid, o->step_counter, STREAM_RESET, 0, u0);
   rng4(o->seed, gid, o->step_counter, STREAM_RESET, 1, u1);
@@ -819,6 +968,10 @@ static void update_command(H1v2Oracle* o, int ei) {
   }
 }
 
+/* rays along one axis of a GridPatternCfg: len(torch.arange(-size/2, size/2 + 1e-9, resolution)); the 1e-4 absorbs the fp32 rounding of the
+ * config values (0.1f > 0.1) */
+static int scan_count(float size, float res) { return (int)floor((double)size / (double)res + 1e-4) + 1; }
+
 static void compute_obs(H1v2Oracle* o, int ei, float* obs_out) {
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
@@ -860,6 +1013,46 @@ static void compute_obs(H1v2Oracle* o, int ei, float* obs_out) {
     s[21 + i] = (float)((e->qvel[6 + j] + n_v[j]) * c->scale_joint_vel);
     s[33 + i] = e->last_action[i] * c->scale_action;
   }
+  if (c->obs_base_lin_vel || c->obs_height_scan) {
+    /* Rough id (V/velocity_env_cfg.py:119-142): base_lin_vel | the 45 terms above | height_scan, no history */
+    e->fresh &= ~2;
+    memcpy(e->hist[0], s, sizeof(s));
+    if (!obs_out) return;
+    int w = 0;
+    if (c->obs_base_lin_vel) {
+      float n_lv[3] = {0, 0, 0};
+      if (c->enable_corruption) {
+        float b[4];
+        rng4(o->seed, c->env_id_offset + ei, o->step_counter, STREAM_OBS, 10, b);
+        for (int i = 0; i < 3; i++) n_lv[i] = uni(b[i], -c->noise_lin_vel, c->noise_lin_vel);
+      }
+      for (int i = 0; i < 3; i++) obs_out[w++] = (float)((vb[i] + n_lv[i]) * c->scale_lin_vel);
+    }
+    for (int k = 0; k < H1V2_OBS_TERM_DIM; k++) obs_out[w++] = s[k];
+    if (c->obs_height_scan) {
+      /* mdp.height_scan [UPSTREAM]: sensor.data.pos_w.z - ray_hits_w.z - offset over a GridPattern (x fastest, "xy" indexing) cast
+       * straight down from the scanner body (torso_link: the pelvis frame, fixed joint h12_12dof.urdf:394-400), attach_yaw_only */
+      const int nx = scan_count(c->scan_size[0], c->scan_resolution), ny = scan_count(c->scan_size[1], c->scan_resolution);
+      const double cy = cos(heading), sy = sin(heading);
+      for (int r = 0; r < nx * ny; r++) {
+        const int ix = r % nx, iy = r / nx;
+        const double gx = (double)((float)ix * c->scan_resolution - 0.5f * c->scan_size[0]), gy = (double)((float)iy * c->scan_resolution - 0.5f * c->scan_size[1]);
+        const double lx = e->qpos[0] + cy * gx - sy * gy, ly = e->qpos[1] + sy * gx + cy * gy;
+        double h = 0, nrm[3];
+        if (c->terrain_enable) terrain_query(o, e->level, e->type, lx, ly, &h, nrm, NULL);
+        float v = (float)(e->qpos[2] - h - c->scan_offset);
+        if (c->enable_corruption) {
+          float b[4];
+          rng4(o->seed, c->env_id_offset + ei, o->step_counter, STREAM_OBS, 16 + (uint32_t)(r / 4), b);
+          v += uni(b[r % 4], -c->noise_height_scan, c->noise_height_scan);
+        }
+        if (v < c->scan_clip[0]) v = c->scan_clip[0];
+        if (v > c->scan_clip[1]) v = c->scan_clip[1];
+        obs_out[w++] = v * c->scale_height_scan;
+      }
+    }
+    return;
+  }
   /* history append: first push after a reset fills every slot (circular_buffer.py:131-135) */
   if (e->fresh & 2) {
     for (int h = 0; h < H; h++) memcpy(e->hist[h], s, sizeof(s));
@@ -896,7 +1089,7 @@ static void step_env(H1v2Oracle* o, int ei, const float* action, float* rew_out,
   OEnv* e = &o->env[ei];
   const H1v2Config* c = &o->cfg;
   const float step_dt = c->sim_dt * (float)c->decimation;
-  e->min_abs_dist = 1e30; e->min_limit_dist = 1e30;
+  e->min_abs_dist = 1e30; e->min_limit_dist = 1e30; e->min_tri_margin = 1.0;
   /* -- action manager: process_action -- */
   float prev_action[NJ];
   memcpy(prev_action, e->last_action, sizeof(prev_action));
@@ -1084,14 +1277,52 @@ int h1v2o_create(const H1v2Config* cfg, int32_t n_envs, uint64_t seed, H1v2Oracl
     o->env[i].friction = (double)uni(u[0], cfg->friction_range[0], cfg->friction_range[1]);
     o->env[i].mass_add = (double)uni(u[1], cfg->mass_add_range[0], cfg->mass_add_range[1]);
   }
+  if (cfg->terrain_enable) {
+    o->npx = terrain_npx(cfg);
+    o->gx = cfg->terrain_rows * o->npx + 1; o->gy = cfg->terrain_cols * o->npx + 1;
+    o->terrain = (float*)calloc((size_t)o->gx * o->gy, sizeof(float));
+    o->origin_z = (float*)calloc((size_t)cfg->terrain_rows * cfg->terrain_cols, sizeof(float));
+    terrain_generate(o);
+    /* TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols)) in fp32 */
+    const int max_init = cfg->terrain_max_init_level < 0 || cfg->terrain_max_init_level > cfg->terrain_rows - 1 ? cfg->terrain_rows - 1 : cfg->terrain_max_init_level;
+    for (int i = 0; i < n_envs; i++) {
+      float u[4];
+      rng4(seed, cfg->env_id_offset + i, 0, STREAM_EVENT, 3, u);
+      int lev = (int)(u[0] * (float)(max_init + 1));
+      o->env[i].level = lev > max_init ? max_init : lev;
+      int ty = (int)floorf((float)i / ((float)n_envs / (float)cfg->terrain_cols));
+      o->env[i].type = ty > cfg->terrain_cols - 1 ? cfg->terrain_cols - 1 : ty;
+    }
+  }
   o->step_counter = 0;
   for (int i = 0; i < n_envs; i++) reset_env(o, i);
   *out = o;
   return 0;
 }
-void h1v2o_destroy(H1v2Oracle* o) { if (o) { free(o->env); free(o); } }
+void h1v2o_destroy(H1v2Oracle* o) { if (o) { free(o->terrain); free(o->origin_z); free(o->env); free(o); } }
 void h1v2o_set_threads(H1v2Oracle* o, int n) { o->nthreads = n > 0 ? n : 1; }
-int h1v2o_obs_dim(const H1v2Oracle* o) { return o->cfg.history_length * H1V2_OBS_TERM_DIM; }
+int h1v2o_obs_dim(const H1v2Oracle* o) {
+  const H1v2Config* c = &o->cfg;
+  if (c->obs_base_lin_vel || c->obs_height_scan)
+    return (c->obs_base_lin_vel ? 3 : 0) + H1V2_OBS_TERM_DIM + (c->obs_height_scan ? scan_count(c->scan_size[0], c->scan_resolution) * scan_count(c->scan_size[1], c->scan_resolution) : 0);
+  return c->history_length * H1V2_OBS_TERM_DIM;
+}
+int h1v2o_terrain_dims(const H1v2Oracle* o, int32_t dims[2]) { dims[0] = o->gx; dims[1] = o->gy; return o->terrain ? 0 : -1; }
+int h1v2o_get_terrain(const H1v2Oracle* o, float* out) { if (!o->terrain) return -1; memcpy(out, o->terrain, sizeof(float) * (size_t)o->gx * o->gy); return 0; }
+int h1v2o_set_terrain(H1v2Oracle* o, const float* in) {
+  if (!o->terrain) return -1;
+  memcpy(o->terrain, in, sizeof(float) * (size_t)o->gx * o->gy);
+  terrain_origin_heights(o);
+  return 0;
+}
+float h1v2o_terrain_level_mean(const H1v2Oracle* o) { return o->terrain_level_mean; }
+/* height (relative to the origin of tile (level, type)) and normal under a point given relative to that origin */
+int h1v2o_terrain_query(const H1v2Oracle* o, int level, int type, double lx, double ly, double* h, double* n) {
+  if (!o->terrain) return -1;
+  terrain_query(o, level, type, lx, ly, h, n, NULL);
+  return 0;
+}
+int h1v2o_tri_margin(H1v2Oracle* o, double* out) { for (int i = 0; i < o->n; i++) out[i] = o->env[i].min_tri_margin; return 0; }
 int64_t h1v2o_max_episode_length(const H1v2Oracle* o) { return o->max_episode_length; }
 
 int h1v2o_reset(H1v2Oracle* o, const int64_t* env_ids, int32_t n) {
@@ -1203,6 +1434,11 @@ static int step_impl(H1v2Oracle* o, const float* actions, float* obs, float* rew
   o->log[H1V2_LOG_NAN_RESETS] += (float)nbad;
   o->log[H1V2_LOG_MAX_ITERS] = (float)max_it;
   run_phase(proto, 1);
+  if (o->cfg.terrain_enable) { /* Curriculum/terrain_levels: mean level over all envs (curriculums.py:52) */
+    double sum = 0;
+    for (int i = 0; i < n; i++) sum += o->env[i].level;
+    o->terrain_level_mean = (float)(sum / n);
+  }
   if (o->cfg.command_class == 1) { /* census for the next step's balancing */
     int cnt = 0;
     for (int i = 0; i < n; i++) cnt += cmd_in_deadzone(o->env[i].cmd, o->cfg.velocity_deadzone);
@@ -1253,6 +1489,8 @@ int h1v2o_get_state(H1v2Oracle* o, const H1v2State* s) {
   CPY_OUT(pre_reset_qpos, 0.0f, 19, float)
   CPY_OUT(pre_reset_qvel, 0.0f, 18, float)
   CPY_OUT(pre_reset_timers, 0.0f, 8, float)
+  CPY_OUT(terrain_level, o->env[i].level, 1, int32_t)
+  CPY_OUT(terrain_type, o->env[i].type, 1, int32_t)
   return 0;
 }
 
@@ -1285,6 +1523,7 @@ int h1v2o_set_state(H1v2Oracle* o, const H1v2State* s) {
   CPY_IN(friction, o->env[i].friction, 1)
   CPY_IN(mass_add, o->env[i].mass_add, 1)
   CPY_IN(push_time_left, o->env[i].push_left, 1)
+  CPY_IN(terrain_level, o->env[i].level, 1)
   return 0;
 }
 int h1v2o_get_episode_length(H1v2Oracle* o, int64_t* out) { for (int i = 0; i < o->n; i++) out[i] = o->env[i].ep_len; return 0; }
@@ -1325,6 +1564,7 @@ void h1v2o_physics_step(const H1v2Config* cfg, double* qpos, double* qvel, const
   H1v2Oracle o;
   memset(&o, 0, sizeof(o));
   o.cfg = *cfg;
+  o.cfg.terrain_enable = 0; /* raw plane physics: this helper owns no height field */
   o.max_newton_iters = 100;
   OEnv e;
   memset(&e, 0, sizeof(e));

@@ -30,6 +30,13 @@ int h1v2o_get_log(H1v2Oracle* o, float* out);
 int h1v2o_set_reward_weights(H1v2Oracle* o, const float* w);
 int h1v2o_solver_stats(H1v2Oracle* o, int32_t* iters, double* resid);
 int h1v2o_activation_margin(H1v2Oracle* o, double* contact, double* limit);
+/* rough terrain */
+int h1v2o_terrain_dims(const H1v2Oracle* o, int32_t dims[2]);
+int h1v2o_get_terrain(const H1v2Oracle* o, float* out);
+int h1v2o_set_terrain(H1v2Oracle* o, const float* in);
+float h1v2o_terrain_level_mean(const H1v2Oracle* o);
+int h1v2o_terrain_query(const H1v2Oracle* o, int level, int type, double lx, double ly, double* h, double* n);
+int h1v2o_tri_margin(H1v2Oracle* o, double* out);
 
 /* building blocks for known-answer tests */
 void h1v2o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -67,7 +67,14 @@ def lib() -> C.CDLL:
         L.h1v2o_total_energy.restype = C.c_double
         L.h1v2o_wrap_to_pi.argtypes = [C.c_float]
         L.h1v2o_wrap_to_pi.restype = C.c_float
-        for f in ("h1v2_default_config", "h1v2_rsl_config", "h1v2_cat_config"):  # the oracle library's own copy (h1v2_config.cpp, host only)
+        L.h1v2o_terrain_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.h1v2o_get_terrain.argtypes = [C.c_void_p, C.c_void_p]
+        L.h1v2o_set_terrain.argtypes = [C.c_void_p, C.c_void_p]
+        L.h1v2o_terrain_level_mean.argtypes = [C.c_void_p]
+        L.h1v2o_terrain_level_mean.restype = C.c_float
+        L.h1v2o_terrain_query.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.h1v2o_tri_margin.argtypes = [C.c_void_p, C.c_void_p]
+        for f in ("h1v2_default_config", "h1v2_rsl_config", "h1v2_cat_config", "h1v2_rough_config"):  # the oracle library's own copy (h1v2_config.cpp, host only)
             getattr(L, f).argtypes = [C.POINTER(H1v2Config)]
         _lib = L
     return _lib
@@ -77,7 +84,7 @@ def task_config(task: str = "flat") -> H1v2Config:
     """Resolved cfg of the Flat / Rsl / CaT id from the ORACLE library (so that the reference arm of bench.py and the CPU tests
     never load the CUDA library)."""
     cfg = H1v2Config()
-    rc = getattr(lib(), {"flat": "h1v2_default_config", "rsl": "h1v2_rsl_config", "cat": "h1v2_cat_config"}[task])(C.byref(cfg))
+    rc = getattr(lib(), {"flat": "h1v2_default_config", "rsl": "h1v2_rsl_config", "cat": "h1v2_cat_config", "rough": "h1v2_rough_config"}[task])(C.byref(cfg))
     assert rc == 0
     return cfg
 
@@ -229,6 +236,32 @@ class Oracle:
         l = np.zeros(self.n, np.float64)
         lib().h1v2o_activation_margin(self._h, _p(c), _p(l))
         return c, l
+
+    # ---- rough terrain ----
+    def terrain(self) -> np.ndarray:
+        d = np.zeros(2, np.int32)
+        assert lib().h1v2o_terrain_dims(self._h, _p(d)) == 0, "no terrain (cfg.terrain_enable)"
+        out = np.zeros((int(d[0]), int(d[1])), np.float32)
+        lib().h1v2o_get_terrain(self._h, _p(out))
+        return out
+
+    def set_terrain(self, heights):
+        a = np.ascontiguousarray(heights, dtype=np.float32)
+        assert lib().h1v2o_set_terrain(self._h, _p(a)) == 0
+
+    def terrain_level_mean(self) -> float:
+        return float(lib().h1v2o_terrain_level_mean(self._h))
+
+    def terrain_query(self, level: int, ttype: int, lx: float, ly: float):
+        h = np.zeros(1)
+        n = np.zeros(3)
+        assert lib().h1v2o_terrain_query(self._h, level, ttype, lx, ly, _p(h), _p(n)) == 0
+        return float(h[0]), n
+
+    def tri_margin(self) -> np.ndarray:
+        out = np.zeros(self.n, np.float64)
+        lib().h1v2o_tri_margin(self._h, _p(out))
+        return out
 
     def solver_stats(self):
         it = np.zeros(self.n, np.int32)

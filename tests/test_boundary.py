@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "flat_cfg_resolved.json")))
 GOLD_RSL = json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json")))
+GOLD_ROUGH = json.load(open(os.path.join(ROOT, "tests", "golden", "rough_cfg_resolved.json")))
+GOLD_PLAY = json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))
 has_ref = os.path.isdir(os.path.join(REF, "packages", "biped_tasks"))
 
 
@@ -45,6 +47,60 @@ def test_rsl_config_equals_reference_cfg_golden():
     assert len(GOLD_RSL["curriculum"]) == 12
     for slot, weight, num_steps in GOLD_RSL["curriculum"]:
         assert num_steps == 24 * 5000 and _close(weight, mine["rew_weight"][slot])
+
+
+def test_rough_config_equals_reference_cfg_golden():
+    """h1v2_rough_config (C restatement of config/h12_12dof/rough_env_cfg.py:65-125 on velocity_env_cfg.py:36-324 with the in-tree terrain
+    generator cfg utils/mdp/terrains.py:11-28) == the reference's own Rough cfg tree flattened, value by value: 10 x 20 tiles of 8 m at
+    0.1 m / 5 mm, levels 0..4, rim 3 cells, max init level 5, terrain_levels_vel on; base_lin_vel + 45 + 17 x 11 height scan, no history;
+    and the Play id (rough_env_cfg.py:128-156) equals tasks.rough_play_env_cfg."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200._capi import obs_dim_of, rough_config
+    from h1v2_isaac_b200.env import config_to_dict, flatten_cfg, reward_slots
+    mine = config_to_dict(rough_config())
+    gold = GOLD_ROUGH["kernel_config"]
+    assert set(mine) == set(gold)
+    for k in gold:
+        assert _close(mine[k], gold[k]), k
+    assert mine["terrain_enable"] == 1 and mine["terrain_rows"] == 10 and mine["terrain_cols"] == 20 and mine["terrain_curriculum"] == 1
+    assert obs_dim_of(rough_config()) == 3 + 45 + 17 * 11 == 235
+    # the self-contained trees invert flatten_cfg, with the reference's reward term names
+    tree = tasks.rough_env_cfg(32)
+    assert config_to_dict(flatten_cfg(tree)) == mine
+    assert reward_slots(tree) == GOLD_ROUGH["reward_slots"]
+    play = config_to_dict(flatten_cfg(tasks.rough_play_env_cfg()))
+    gp = GOLD_PLAY["Isaac-Velocity-Rough-H12_12dof-Play-v0"]
+    assert gp["num_envs"] == 50 and set(play) == set(gp["kernel_config"])
+    for k in play:
+        assert _close(play[k], gp["kernel_config"][k]), k
+
+
+def test_flatten_refuses_what_the_rough_kernel_cannot_do():
+    """Terrain / scanner settings outside the built path raise NotImplementedError naming the entry (never approximated): upstream's mesh
+    sub-terrains, a second sub-terrain, a scanner that is not yaw-aligned, height_scan on a history cfg."""
+    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200.env import flatten_cfg
+    from h1v2_isaac_b200.shims._lenient import Placeholder
+
+    class MeshPyramidStairsTerrainCfg(Placeholder):
+        pass
+
+    t = tasks.rough_env_cfg(16)
+    t.scene.terrain.terrain_generator.sub_terrains["pyramid_stairs"] = MeshPyramidStairsTerrainCfg(proportion=0.2)
+    with pytest.raises(NotImplementedError, match="HfRandomUniformTerrainCfg"):
+        flatten_cfg(t)
+    t = tasks.rough_env_cfg(16)
+    t.scene.height_scanner.attach_yaw_only = False
+    with pytest.raises(NotImplementedError, match="attach_yaw_only"):
+        flatten_cfg(t)
+    t = tasks.rough_env_cfg(16)
+    t.observations.policy.history_length = 5
+    with pytest.raises(NotImplementedError, match="history"):
+        flatten_cfg(t)
+    t = tasks.rough_env_cfg(16)
+    t.scene.terrain.terrain_type = "usd"
+    with pytest.raises(NotImplementedError, match="terrain_type"):
+        flatten_cfg(t)
 
 
 def test_self_contained_rsl_task_roundtrip():
@@ -182,7 +238,9 @@ def test_reference_cfg_tree_flattens_to_golden():
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "rsl_cfg_resolved.json"))) == GOLD_RSL
     assert json.load(open(os.path.join(ROOT, "tests", "golden", "cat_cfg_resolved.json")))["kernel_config"]["cat_enable"] == 1
     assert set(json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))) == {
-        "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0"}
+        "Isaac-Velocity-Flat-H12_12dof-Play-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-CaT-Flat-H12_12dof-Play-v0",
+        "Isaac-Velocity-Rough-H12_12dof-Play-v0"}
+    assert json.load(open(os.path.join(ROOT, "tests", "golden", "rough_cfg_resolved.json"))) == GOLD_ROUGH
 
 
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
@@ -206,8 +264,8 @@ def test_unmodified_train_py_reaches_the_backend(tmp_path):
 def test_reference_variants_are_accepted_or_refused_by_name():
     """Which of the reference's H1-2 12-dof ids the backend takes: Flat and Flat-Play flatten, also with the
     H12_12DOF_IDEAL robot (IdealPD -> no delay line), and so do Rsl and Rsl-Play (dead-zone command class, second joint-set
-    terms, modify_reward_weight curriculum) and CaT (constraint manager); Rough (height scan, base_lin_vel) is refused with
-    the name of the offending cfg entry, never approximated."""
+    terms, modify_reward_weight curriculum), CaT (constraint manager) and Rough (height field, height scan, base_lin_vel, terrain
+    curriculum)."""
     code = r'''
 import gymnasium as gym
 import biped_tasks.tasks
@@ -219,7 +277,7 @@ for tid in ("Isaac-Velocity-Flat-H12_12dof-v0", "Isaac-Velocity-Flat-H12_12dof-P
             "Isaac-Velocity-Rsl-H12_12dof-v0", "Isaac-Velocity-Rsl-H12_12dof-Play-v0", "Isaac-Velocity-Rough-H12_12dof-v0"):
     cfg = load_cfg_from_registry(tid, "env_cfg_entry_point")
     try:
-        c = flatten_cfg(cfg); out[tid] = "ok corruption=%d" % c.enable_corruption + (" class=%d H=%d" % (c.command_class, c.history_length) if "Rsl" in tid else "")
+        c = flatten_cfg(cfg); out[tid] = "ok corruption=%d" % c.enable_corruption + (" class=%d H=%d" % (c.command_class, c.history_length) if "Rsl" in tid else "") + (" terrain=%dx%d scan=%d" % (c.terrain_rows, c.terrain_cols, c.obs_height_scan) if "Rough" in tid else "")
     except NotImplementedError as e:
         out[tid] = "refused: " + str(e)[:40]
 cfg = load_cfg_from_registry("Isaac-Velocity-Flat-H12_12dof-v0", "env_cfg_entry_point")
@@ -239,7 +297,7 @@ import json; print("RESULT" + json.dumps(out))
     assert res["Isaac-Velocity-CaT-Flat-H12_12dof-v0"] == "ok corruption=1"  # constraints group -> the CaT tail (h1v2_cat_step)
     assert res["Isaac-Velocity-Rsl-H12_12dof-v0"] == "ok corruption=1 class=1 H=6"
     assert res["Isaac-Velocity-Rsl-H12_12dof-Play-v0"] == "ok corruption=0 class=1 H=6"
-    assert res["Isaac-Velocity-Rough-H12_12dof-v0"].startswith("refused: ")  # terrain curriculum, height scan, base_lin_vel
+    assert res["Isaac-Velocity-Rough-H12_12dof-v0"] == "ok corruption=1 terrain=10x20 scan=1"
 
 
 @pytest.mark.skipif(not has_ref, reason="reference tree not present (GPU box)")
