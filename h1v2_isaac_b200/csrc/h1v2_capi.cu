@@ -155,11 +155,12 @@ __global__ void startup_kernel(const __grid_constant__ KParams P, const KState S
   rng4(P.key0, P.env_id_offset + env, 0ull, STREAM_EVENT, 0, u);
   S.root[3 * P.n + env] = make_float4(0.f, uni(u[0], fr_lo, fr_hi), uni(u[1], ma_lo, ma_hi), 0.f);
   if (P.rough) {
-    // TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols)) in fp32
+    // TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols))
     float v[4];
     rng4(P.key0, P.env_id_offset + env, 0ull, STREAM_EVENT, 3, v);
     const int level = min((int)__fmul_rn(v[0], (float)(max_init + 1)), max_init);
-    const int type = min((int)floorf(__fdiv_rn((float)env, __fdiv_rn((float)P.n, (float)P.t_cols))), P.t_cols - 1);
+    // torch.div(arange(n), n / cols, rounding_mode="floor"): fp32 divisor, exact floor (1024 / fp32(204.8) = 4.99999993 -> 4)
+    const int type = min((int)floor((double)env / (double)(float)((double)P.n / (double)P.t_cols)), P.t_cols - 1);
     S.cmd[P.n + env] = make_float4(0.f, 0.f, 0.f, __int_as_float((level << FLAG_LEVEL_SHIFT) | (type << FLAG_TYPE_SHIFT)));
   }
 }

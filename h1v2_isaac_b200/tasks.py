@@ -317,6 +317,13 @@ def default_agent_cfg():
                                        max_grad_norm=1.0))
 
 
+def rough_agent_cfg():
+    """rsl_rl runner cfg of the Rough id (config/h12_12dof/agents/rsl_rl_ppo_cfg.py:10-37): the Flat cfg's values, experiment h12_12dof_rough."""
+    a = default_agent_cfg()
+    a.experiment_name = "h12_12dof_rough"
+    return a
+
+
 def cat_agent_cfg():
     """CleanRL PPO cfg of the CaT id (values: config/h12_12dof/agents/clean_rl_ppo_cfg.py, schema utils/cleanrl/rl_cfg.py:11-38)."""
     import types
@@ -350,6 +357,6 @@ def register() -> bool:
         gym.register(id=tid, entry_point="h1v2_isaac_b200.env:" + ("H1v2CaTEnv" if "CaT" in tid else "H1v2ManagerBasedRLEnv"), disable_env_checker=True,
                      kwargs={"env_cfg_entry_point": f"h1v2_isaac_b200.tasks:{env_cfg}",
                              **({"clean_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:cat_agent_cfg"} if "CaT" in tid  # C12/__init__.py:63-82
-                                else {"rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:default_agent_cfg"})})
+                                else {"rsl_rl_cfg_entry_point": "h1v2_isaac_b200.tasks:" + ("rough_agent_cfg" if "Rough" in tid else "default_agent_cfg")})})
         done = True
     return done

@@ -1283,14 +1283,16 @@ int h1v2o_create(const H1v2Config* cfg, int32_t n_envs, uint64_t seed, H1v2Oracl
     o->terrain = (float*)calloc((size_t)o->gx * o->gy, sizeof(float));
     o->origin_z = (float*)calloc((size_t)cfg->terrain_rows * cfg->terrain_cols, sizeof(float));
     terrain_generate(o);
-    /* TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols)) in fp32 */
+    /* TerrainImporter._compute_env_origins_curriculum [UPSTREAM]: level = randint(0, max_init_level + 1), type = floor(i / (n / cols)) */
     const int max_init = cfg->terrain_max_init_level < 0 || cfg->terrain_max_init_level > cfg->terrain_rows - 1 ? cfg->terrain_rows - 1 : cfg->terrain_max_init_level;
     for (int i = 0; i < n_envs; i++) {
       float u[4];
       rng4(seed, cfg->env_id_offset + i, 0, STREAM_EVENT, 3, u);
       int lev = (int)(u[0] * (float)(max_init + 1));
       o->env[i].level = lev > max_init ? max_init : lev;
-      int ty = (int)floorf((float)i / ((float)n_envs / (float)cfg->terrain_cols));
+      /* torch.div(arange(n), n / cols, rounding_mode="floor"): the divisor is the fp32 value of the python double, the floor is exact
+       * (c10 div_floor_floating works through fmod): 1024 / fp32(204.8) is 4.99999993 -> 4, where a rounded fp32 division says 5 */
+      int ty = (int)floor((double)i / (double)(float)((double)n_envs / (double)cfg->terrain_cols));
       o->env[i].type = ty > cfg->terrain_cols - 1 ? cfg->terrain_cols - 1 : ty;
     }
   }

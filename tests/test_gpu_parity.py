@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 PHYS = ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"]
 SYNC = PHYS + ["last_action", "target_hist", "lag", "fresh", "command", "heading_target", "time_left", "is_standing",
                "is_heading", "cmd_metrics", "feet_timers", "episode_sums", "obs_history", "friction", "mass_add",
-               "push_time_left"]
+               "push_time_left", "terrain_level"]
 POST = ["pre_reset_qpos", "pre_reset_qvel", "pre_reset_timers", "slot_force_hist", "applied_torque", "joint_acc", "foot_vel"]
 
 
@@ -240,6 +240,7 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
     n_term = n_trunc = n_resample = 0
     stats = {"xy_zero_frac": [], "yaw_flips": 0}
     prev = _np(sim.get_state(["time_left", "command"]))
+    prev_level = _np(sim.get_state(["terrain_level"]))["terrain_level"]
     for step in range(steps):
         if reweight is not None and step == reweight[0]:
             sim.set_reward_weights(reweight[1]); orc.set_reward_weights(reweight[1])
@@ -259,6 +260,11 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
         assert np.array_equal(g["time_left"], o["time_left"]), "command resample mask (time_left is float32 on both sides)"
         assert np.array_equal(sim.episode_length_buf.cpu().numpy(), orc.episode_length)
         assert np.array_equal(g["feet_timers"], o["feet_timers"]), "contact-sensor air/contact timers"
+        assert np.array_equal(g["terrain_level"], o["terrain_level"]), f"terrain level after the resets of step {step}"
+        if cfg.terrain_enable:
+            stats.setdefault("level_moves", 0)
+            stats["level_moves"] += int((g["terrain_level"] != prev_level).sum()); prev_level = g["terrain_level"].copy()
+            assert abs(float(sim.terrain_log_buf[1]) - orc.terrain_level_mean()) < 1e-4
         # (a) values
         np.testing.assert_allclose(g["reward_terms"], o["reward_terms"], rtol=1e-5, atol=2e-7, err_msg=f"reward terms, step {step}")
         np.testing.assert_allclose(rg, ro, rtol=1e-5, atol=1e-6)

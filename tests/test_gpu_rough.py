@@ -1,0 +1,196 @@
+"""Rough terrain on the GPU: the rough instantiation of the fused step kernel, through the C-ABI, against the CPU
+oracle -- same bar as the flat ids: height field, levels and reset state bit-exact; single-step physics from identical states within
+1e-4 rad / 1e-3 rad/s; rewards / observations (235 = base_lin_vel 3 + 45 + height scan 17 x 11) within 1e-5 on identical post-physics
+states; termination / reset / resample masks and terrain levels bit-exact; the reference's own terrain_levels_vel golden through both
+reset paths of the kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import PHYS, SYNC, _mk, _np, _resync, _tail_parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rough():
+    from h1v2_isaac_b200._capi import rough_config
+    return rough_config()
+
+
+def test_rough_terrain_levels_and_reset_state_match_oracle(rough):
+    torch, sim, orc = _mk(rough, 640, 13)
+    Hg, Ho = sim.terrain(), orc.terrain()
+    assert Hg.shape == (801, 1601) and np.array_equal(Hg, Ho)  # the same Philox draws, vertex by vertex
+    names = SYNC + ["terrain_type"]
+    g, o = _np(sim.get_state(names)), orc.get_state(names)
+    for k in names:
+        if g[k].dtype.kind == "i":
+            assert np.array_equal(g[k], o[k]), k
+        else:
+            np.testing.assert_allclose(g[k], o[k], rtol=0, atol=2e-6, err_msg=k)
+    assert g["terrain_level"].max() == 5 and g["terrain_level"].min() == 0 and g["terrain_type"].max() == 19
+    og, oo = sim.observe().cpu().numpy(), orc.observe()
+    assert og.shape == (640, 235)
+    np.testing.assert_allclose(og, oo, rtol=0, atol=3e-6)
+    assert np.abs(og[:, 48:]).max() <= 1.0 and og[:, 48:].std() > 0.01  # clipped, noisy, and it sees the bumps
+    # a caller-supplied height field replaces the generated one on both sides (h1v2_set_terrain)
+    rng = np.random.default_rng(0)
+    H2 = (rng.integers(0, 9, Hg.shape) * 0.01).astype(np.float32)
+    sim.set_terrain(H2); orc.set_terrain(H2)
+    assert np.array_equal(sim.terrain(), H2)
+    np.testing.assert_allclose(sim.observe().cpu().numpy(), orc.observe(), rtol=0, atol=3e-6)
+    assert sim.check_guards() == 0
+    sim.close()
+
+
+@pytest.mark.parametrize("decimation,rough_cm", [(1, 2), (1, 8), (4, 2)])
+def test_rough_physics_parity_from_identical_states(rough, decimation, rough_cm):
+    """North star (c) on the height field, asserted literally for one physics step: positions within 1e-4 rad / m and velocities within
+    1e-3 rad/s (m/s) on every kept env-step.  rough_cm = 2 is the reference's generator cfg (0 .. 2 cm); 8 makes the slopes four times
+    as steep (up to 39 degrees), so that the contact frames matter.  Skipped and counted, as on the plane: envs within 2e-6 of a
+    contact / limit activation boundary, and here also envs with a contact candidate within 1e-4 cells (10 um) of a triangle edge of the
+    height field (the normal jumps there; float vs double rounding of the position decides the triangle)."""
+    c = rough.copy()
+    c.decimation = decimation
+    c.max_delay = min(c.max_delay, 2 * decimation)
+    n = 2048
+    torch, sim, orc = _mk(c, n, 3)
+    if rough_cm != 2:
+        H = sim.terrain() * (rough_cm / 2.0)
+        sim.set_terrain(H); orc.set_terrain(H)
+    sim.observe(); orc.observe()
+    rng = np.random.default_rng(0)
+    errs = {k: [] for k in PHYS}
+    steps = 24 * (4 // decimation)
+    n_alive = n_boundary = 0
+    for step in range(steps):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        _, _, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        _, _, to, uo = orc.step(a)
+        g, o = _np(sim.get_state(SYNC)), orc.get_state(PHYS)
+        mc, ml = orc.activation_margin()
+        alive = ~(to | uo | tg.cpu().numpy())
+        keep = alive & (mc > 2e-6) & (ml > 2e-6) & (orc.tri_margin() > 1e-4)
+        n_alive += int(alive.sum()); n_boundary += int((alive & ~keep).sum())
+        for k in PHYS:
+            errs[k].append(np.abs(g[k][keep] - o[k][keep]).max(axis=1))
+        _resync(sim, orc, g)
+    e = {k: np.concatenate(v) for k, v in errs.items()}
+    print({k: (float(v.max()), float(np.quantile(v, 0.999)), float(np.quantile(v, 0.99))) for k, v in e.items()}, "env-steps", len(e["joint_pos"]),
+          f"excluded on an activation / triangle boundary: {n_boundary} of {n_alive} ({100.0 * n_boundary / max(n_alive, 1):.3f} %)")
+    assert len(e["joint_pos"]) > 0.6 * n * steps and n_boundary < 0.01 * decimation * n_alive
+    for k in ("joint_pos", "root_pos", "root_quat"):
+        assert e[k].max() < 1e-4, k
+    # the literal bound on the reference's own terrain; the four-times-steeper stress field (not a cfg of the reference) gets 2e-3 on the
+    # maximum (measured 1.04e-3: fp32 rounding of hard landings on 39-degree facets), the same quantile bounds
+    vmax = (1e-3 if rough_cm == 2 else 2e-3) if decimation == 1 else 4e-3
+    for k in ("joint_vel", "root_lin_vel", "root_ang_vel"):
+        assert e[k].max() < vmax, (k, float(e[k].max()))
+        assert np.quantile(e[k], 0.99) < 5e-4 and np.quantile(e[k], 0.999) < 1e-3, k
+    sim.close()
+
+
+def test_rough_tail_parity(rough):
+    """Managers of the Rough id on identical post-physics states: 12 reward terms, the 235-float observation (noise draws bit-identical,
+    height scan through the kernel's own terrain lookups), masks, command resamples, and the terrain levels the in-kernel curriculum
+    leaves after every reset, plus Curriculum/terrain_levels."""
+    stats = _tail_parity(rough, 2048, 40, 20, min_term=0)
+    assert stats["level_moves"] > 20
+
+
+def test_rough_curriculum_golden_through_both_reset_paths(rough):
+    """tests/golden/terrain_curriculum.npz (the reference's own terrain_levels_vel on 4096 stand-in envs): the API reset (reset_kernel)
+    and the in-step reset of envs that time out move every env's level exactly like the reference did."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "terrain_curriculum.npz"))
+    n = len(G["levels0"])
+    w = G["wrapped"]
+    torch, sim, orc = _mk(rough, n, 5)
+    sim.observe()
+    assert np.array_equal(_np(sim.get_state(["terrain_type"]))["terrain_type"][:, 0], G["types"])
+
+    def load():
+        st = _np(sim.get_state(["root_pos"]))
+        st["root_pos"][:, :2] = G["rel"]
+        sim.set_state({"root_pos": st["root_pos"], "command": G["cmd"], "terrain_level": G["levels0"]})
+
+    load()
+    sim.reset(torch.arange(n).cuda())
+    lv = _np(sim.get_state(["terrain_level"]))["terrain_level"][:, 0]
+    assert np.array_equal(lv[~w], G["levels1"][~w])
+    assert (lv[w] >= 0).all() and (lv[w] < 10).all() and len(np.unique(lv[w])) > 5
+    # in-step path: every env times out in this step; during it the robots move a few millimetres, so entries within 5 cm of a
+    # threshold are left out of the comparison
+    load()
+    sim.set_state({"root_lin_vel": np.zeros((n, 3), np.float32)})
+    sim.episode_length_buf.fill_(sim.max_episode_length - 1)
+    _, _, _, trunc = sim.step(torch.zeros((n, 12), device="cuda"))
+    assert bool(trunc.all())
+    lv = _np(sim.get_state(["terrain_level"]))["terrain_level"][:, 0]
+    dist = np.linalg.norm(G["rel"], axis=1)
+    need = np.linalg.norm(G["cmd"][:, :2], axis=1) * 20.0 * 0.5
+    clear = (np.abs(dist - 4.0) > 0.05) & (np.abs(dist - need) > 0.05) & ~w
+    assert clear.sum() > 3000 and np.array_equal(lv[clear], G["levels1"][clear])
+    assert abs(float(sim.terrain_log_buf[1]) - lv.mean()) < 1e-3
+    sim.close()
+
+
+@pytest.mark.parametrize("n", [1000, 4096])
+def test_rough_full_size_properties(rough, n):
+    """Free running at the config's env count (and a ragged one): finite, every output element written, scan inside its clip range,
+    levels inside the grid, guard zones intact, bit-identical reruns; the per-step cost is reported."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    outs = []
+    for rep in range(2):
+        sim = H1v2Sim(n, rough, device="cuda:0", seed=77)
+        obs = torch.full((n, sim.obs_dim), float("nan"), device="cuda")
+        rew = torch.full((n,), float("nan"), device="cuda")
+        term = torch.zeros(n, dtype=torch.uint8, device="cuda"); trunc = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        act = torch.empty((n, 12), device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for s in range(60):
+            sim.random_actions(s, act)
+            if s == 20:
+                e0.record()
+            sim.step_into(act, obs, rew, term, trunc)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 40
+        lv = sim.get_state(["terrain_level"])["terrain_level"]
+        assert int(lv.min()) >= 0 and int(lv.max()) <= 9
+        assert float(obs[:, 48:].abs().max()) <= 1.0
+        assert abs(float(sim.terrain_log_buf[1]) - float(lv.float().mean())) < 1e-3
+        assert sim.check_guards() == 0
+        outs.append((obs.clone(), rew.clone(), lv.clone()))
+        sim.close()
+    print(f"rough step, {n} envs: {ms:.3f} ms per control step ({n / ms / 1e3:.2f} M env-steps/s)")
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_rough_gym_env_and_ppo(rough):
+    """gym.make("Isaac-Velocity-Rough-H12_12dof-v0") on the self-contained cfg tree: 235-dim observation, the reference's log keys incl.
+    Curriculum/terrain_levels, and two PPO iterations of the runner shim on it."""
+    import torch
+    from h1v2_isaac_b200 import shims, tasks
+    shims.install()
+    tasks.register()
+    import gymnasium as gym
+    from isaaclab_rl.rsl_rl import RslRlVecEnvWrapper
+    from rsl_rl.runners import OnPolicyRunner
+    env = gym.make(tasks.ROUGH_TASK_ID, cfg=tasks.rough_env_cfg(256))
+    u = env.unwrapped
+    assert u.sim.obs_dim == 235 and u.observation_manager.active_terms["policy"][0] == "base_lin_vel" and u.observation_manager.active_terms["policy"][-1] == "height_scan"
+    obs, _ = env.reset()
+    assert obs["policy"].shape == (256, 235)
+    obs, rew, term, trunc, extras = env.step(torch.zeros((256, 12), device=u.device))
+    assert "Curriculum/terrain_levels" in extras["log"] and 0.0 <= float(extras["log"]["Curriculum/terrain_levels"]) <= 9.0
+    assert "Episode_Reward/feet_air_time" in extras["log"] and "Episode_Termination/base_contact" in extras["log"]
+    agent = tasks.default_agent_cfg()
+    agent.max_iterations = 2
+    runner = OnPolicyRunner(RslRlVecEnvWrapper(env), agent.to_dict(), log_dir=None, device=str(u.device))
+    runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+    env.close()
