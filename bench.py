@@ -27,16 +27,19 @@ METRIC = "env-steps/sec"
 # algorithmic HBM bytes per env-step of the fused kernel: action 48, root r+w 128, leg 192,
 # actuator line 320, command 64, timers 64, warm start 192, episode sums 192, episode length 16, reward+flags 6 = 1222,
 # plus per history slot H: ring read (H-1)x180 + ring write 180 + observation write 180 H = 360 H  (H = 10: 4822)
-def algo_bytes_per_env_step(history: int) -> int:
+def algo_bytes_per_env_step(history: int, obs_dim: int | None = None) -> int:
+    if obs_dim is not None and obs_dim != 45 * history:  # Rough id: no history ring to read; one 192-byte slot and the 235-float row are written
+        return 1222 + 192 + 4 * obs_dim
     return 1222 + 360 * history
 
 
-TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-H12_12dof-v0", "cat": "Isaac-Velocity-CaT-Flat-H12_12dof-v0"}
+TASKS = {"flat": "Isaac-Velocity-Flat-H12_12dof-v0", "rsl": "Isaac-Velocity-Rsl-H12_12dof-v0", "cat": "Isaac-Velocity-CaT-Flat-H12_12dof-v0",
+         "rough": "Isaac-Velocity-Rough-H12_12dof-v0"}
 
 
 def task_config(task: str):
     from h1v2_isaac_b200 import _capi, tasks
-    return {"flat": _capi.default_config, "rsl": _capi.rsl_config, "cat": tasks.cat_config}[task]()
+    return {"flat": _capi.default_config, "rsl": _capi.rsl_config, "cat": tasks.cat_config, "rough": _capi.rough_config}[task]()
 
 
 def oracle_task_config(task: str):
@@ -53,7 +56,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1] = 4096; configs[3] = 32768)")
-    ap.add_argument("--task", default="flat", choices=sorted(TASKS), help="flat = BASELINE's metric config (default); rsl / cat = the SURVEY 8(f) variants (cat: fused step + constraint tail)")
+    ap.add_argument("--task", default="flat", choices=sorted(TASKS), help="flat = BASELINE's metric config (default); rsl / cat / rough = the SURVEY 8(f) variants (cat: fused step + constraint tail; rough: height-field terrain, height scan)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -127,7 +130,7 @@ def cpu_baseline(cfg, seed: int, n: int, target_s: float = 12.0, steps: int | No
 def cpu_baseline_sim2sim(cfg, seed: int, target_s: float = 4.0):
     """BASELINE.md B0 -- the reference's literal CPU configuration (scripts/deploy/sim2sim.py:46-54, deploy/config.yaml:7-8):
     ONE env on ONE core, MuJoCo-semantics step at 1 ms x 20 substeps per 50 Hz control step, PD in the loop, random-init
-    450->512->256->128->12 ELU policy on torch-CPU.  Engine: the float64 C oracle (mujoco is not installable here)."""
+    obs_dim->512->256->128->12 ELU policy on torch-CPU (obs_dim 450 on the Flat id).  Engine: the float64 C oracle (mujoco is not installable here)."""
     import numpy as np
     import torch
     from oracle.oracle import Oracle
@@ -137,7 +140,7 @@ def cpu_baseline_sim2sim(cfg, seed: int, target_s: float = 4.0):
     orc = Oracle(c, 1, seed=seed, threads=1)
     torch.manual_seed(0)
     torch.set_num_threads(1)
-    pi = torch.nn.Sequential(torch.nn.Linear(450, 512), torch.nn.ELU(), torch.nn.Linear(512, 256), torch.nn.ELU(),
+    pi = torch.nn.Sequential(torch.nn.Linear(orc.obs_dim, 512), torch.nn.ELU(), torch.nn.Linear(512, 256), torch.nn.ELU(),
                              torch.nn.Linear(256, 128), torch.nn.ELU(), torch.nn.Linear(128, 12))
     obs = orc.observe()
     k, t0 = 0, time.perf_counter()
@@ -203,7 +206,7 @@ def run_ours(args):
     n = args.envs
     cfg = task_config(args.task)
     is_cat = args.task == "cat"
-    ALGO_BYTES_PER_ENV_STEP = algo_bytes_per_env_step(cfg.history_length)
+    ALGO_BYTES_PER_ENV_STEP = algo_bytes_per_env_step(cfg.history_length, _capi.obs_dim_of(cfg))
     cfg.env_id_offset = rank * n  # envs shard across ranks; the Philox key uses the global env id
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     W, K = max(args.warmup, 3), args.steps

@@ -227,12 +227,13 @@ __device__ __forceinline__ void k6_add_point(K6& K, V3 r, const real (&W)[5]) {
 }
 // the same for a point whose weight W is given in its contact frame (axes ax, ay, n): K += X' (L W L') X
 __device__ __forceinline__ void k6_add_point_rot(K6& K, V3 r, const real (&W)[5], V3 n) {
+  const CFrame cf = cframe(n);
   V3 ax, ay;
-  contact_axes(n, ax, ay);
+  contact_axes(cf, ax, ay);
   // columns of Ww = L W L':  Ww e_k = L (W (L' e_k)),  L' e_k = (ax_k, ay_k, n_k)
-  const V3 w0 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.x, ay.x, n.x)));
-  const V3 w1 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.y, ay.y, n.y)));
-  const V3 w2 = from_contact(ax, ay, n, w5_mul(W, mk3(ax.z, ay.z, n.z)));
+  const V3 w0 = from_contact(cf, w5_mul(W, mk3(ax.x, ay.x, n.x)));
+  const V3 w1 = from_contact(cf, w5_mul(W, mk3(ax.y, ay.y, n.y)));
+  const V3 w2 = from_contact(cf, w5_mul(W, mk3(ax.z, ay.z, n.z)));
   // Ww g_j over the columns g_j = e_j x r of G
   const V3 g0 = mk3(0.f, -r.z, r.y), g1 = mk3(r.z, 0.f, -r.x), g2 = mk3(-r.y, r.x, 0.f);
   const V3 v0 = fma3(w1, g0.y, w2 * g0.z), v1 = fma3(w0, g1.x, w2 * g1.z), v2 = fma3(w0, g2.x, w1 * g2.y);
@@ -504,9 +505,7 @@ UNROLL(U_PRO)
           const V3 rc = ROUGH ? c - nrm * (rad + 0.5f * dist) : mk3(c.x, c.y, 0.5f * dist - href);  // midway between the surfaces
           V3 vel = vob + cross(omb, rc);
           if (ROUGH) {
-            V3 ax, ay;
-            contact_axes(nrm, ax, ay);
-            vel = to_contact(ax, ay, nrm, vel);
+            vel = to_contact(cframe(nrm), vel);
             sm.pf(nact, 8) = nrm.x; sm.pf(nact, 9) = nrm.y; sm.pf(nact, 10) = nrm.z;
           }
           const real imp = impedance_call(P.contact_imp, dist);
@@ -564,12 +563,7 @@ UNROLL(U_PRO)
       for (int p = 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
         V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
-        if (ROUGH) {  // contact frame -> world
-          const V3 n = sm.pv(p, 8);
-          V3 ax, ay;
-          contact_axes(n, ax, ay);
-          Fp = from_contact(ax, ay, n, Fp);
-        }
+        if (ROUGH) Fp = from_contact(cframe(sm.pv(p, 8)), Fp);  // contact frame -> world
         const V3 mom = cross(r, Fp);
         const real isf = p < n_foot ? 1.f : 0.f, iss = (p >= n_foot && p < e_shin) ? 1.f : 0.f, isr = p >= e_shin ? 1.f : 0.f;
         const real ist = (p >= e_shin && p < e_torso) ? 1.f : 0.f;
@@ -797,12 +791,7 @@ UNROLL(U_LSJ)
           const bool isf = p < n_foot, iss = p < e_shin;
           const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
           V3 us = Sl + cross(Sa, r);
-          if (ROUGH) {
-            const V3 n = sm.pv(p, 8);
-            V3 ax, ay;
-            contact_axes(n, ax, ay);
-            us = to_contact(ax, ay, n, us);
-          }
+          if (ROUGH) us = to_contact(cframe(sm.pv(p, 8)), us);
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
         d1 = pair_sum(d1) + r_fma(alpha, sMs, sMa);
@@ -848,12 +837,7 @@ UNROLL(U_LSJ)
         const bool isf = p < n_foot, iss = p < e_shin;
         const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
         V3 us = Sl + cross(Sa, r);
-        if (ROUGH) {
-          const V3 n = sm.pv(p, 8);
-          V3 ax, ay;
-          contact_axes(n, ax, ay);
-          us = to_contact(ax, ay, n, us);
-        }
+        if (ROUGH) us = to_contact(cframe(sm.pv(p, 8)), us);
         const V3 e = fma3(us, alpha, sm.pv(p, 3));
         sm.pf(p, 3) = e.x; sm.pf(p, 4) = e.y; sm.pf(p, 5) = e.z;
       }

@@ -358,49 +358,85 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   }
 }
 
-// Rough id: height_scan (V/velocity_env_cfg.py:61-68,133-138; upstream mdp.height_scan = sensor z - hit z - offset).  The warp walks its
-// envs; for each, the lanes share the env's pose (shuffles from its first lane) and cast the GridPattern rays -- x fastest, "xy"
-// indexing, about the scanner body (torso_link = the pelvis frame: fixed joint), rotated by the base yaw only -- straight down onto
-// the height field: one terrain lookup per ray.  Four consecutive rays share one Philox draw.  Noise, then clip, then scale.
+// Rough id: height_scan (V/velocity_env_cfg.py:61-68,133-138; upstream mdp.height_scan = sensor z - hit z - offset): GridPattern rays --
+// x fastest, "xy" indexing -- about the scanner body (torso_link = the pelvis frame: fixed joint), rotated by the base yaw only, cast
+// straight down onto the height field: one terrain lookup per ray.  Noise, then clip, then scale.
+// The envs of the warp leave their scan frame (position, yaw, tile) in shared memory (the per-thread columns are dead by now); the
+// (env, group of four consecutive rays) pairs are then dealt round-robin to the 32 lanes, so that no lane idles and the lookups of
+// several groups are in flight together (the first version walked env by env: 11 % of the instructions but 24 % of the step's
+// stall samples, all of it exposed L2 latency; profiles/r3_regions_rough_32768.txt).  Four rays share one Philox draw.
+#define SCAN_FRAME 8  // px py pz cos sin | i0 j0 (int bits) | oz
 template <bool ROUGH>
 __device__ __forceinline__ void emit_height_scan(const KParams& P, const KState& S, unsigned tid, unsigned bid, unsigned long long step,
                                                  const real (&rp)[3], const RootDerived& rd, int flags, float* obs) {
+  extern __shared__ __align__(16) real smem_raw[];
+  float* fr = reinterpret_cast<float*>(smem_raw);
   const int lane = tid & 31;
   const int warp_env0 = (int)bid * P.epw, nenv = min(P.epw, P.n - warp_env0);
   const int nrays = P.scan_nx * P.scan_ny, ngrp = (nrays + 3) >> 2;
-  const real hn = r_rsqrt(r_max(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));
-  const real my_c = rd.hx * hn, my_s = rd.hy * hn;
-#pragma unroll 1
-  for (int e = 0; e < nenv; e++) {
-    const real px = __shfl_sync(FULL_MASK, rp[0], 2 * e), py = __shfl_sync(FULL_MASK, rp[1], 2 * e), pz = __shfl_sync(FULL_MASK, rp[2], 2 * e);
-    const real cy = __shfl_sync(FULL_MASK, my_c, 2 * e), sy = __shfl_sync(FULL_MASK, my_s, 2 * e);
-    const int fl = __shfl_sync(FULL_MASK, flags, 2 * e);
+  __syncwarp();  // every lane is done with the history window
+  if ((lane & 1) == 0 && (lane >> 1) < nenv) {
+    const real hn = r_rsqrt(r_max(rd.hx * rd.hx + rd.hy * rd.hy, 1e-30f));
+    float* f = fr + (lane >> 1) * SCAN_FRAME;
+    f[0] = (float)rp[0]; f[1] = (float)rp[1]; f[2] = (float)rp[2]; f[3] = (float)(rd.hx * hn); f[4] = (float)(rd.hy * hn);
     TerrainEnv te;
     te.i0 = te.j0 = 0; te.oz = 0.f;
-    if (ROUGH) te = terrain_env(P, S.terrain_oz, fl);
-    const int64_t gid = P.env_id_offset + warp_env0 + e;
-    float* orow = obs + (size_t)(warp_env0 + e) * P.obs_dim + P.scan_col0;
+    if (ROUGH) te = terrain_env(P, S.terrain_oz, flags);
+    f[5] = __int_as_float(te.i0); f[6] = __int_as_float(te.j0); f[7] = (float)te.oz;
+  }
+  __syncwarp();
+  const int nitem = nenv * ngrp;
+  const float inv_ngrp = 1.0f / (float)ngrp, inv_nx = 1.0f / (float)P.scan_nx;
 #pragma unroll 1
-    for (int g = lane; g < ngrp; g += 32) {
-      float nz[4] = {0.f, 0.f, 0.f, 0.f};
-      if (P.corrupt) {
-        rng4(P.key0, gid, step, STREAM_OBS, 16 + g, nz);
-#pragma unroll
-        for (int k = 0; k < 4; k++) nz[k] = uni(nz[k], -P.n_scan, P.n_scan);
-      }
+  for (int it = lane; it < nitem; it += 32) {
+    const int e = (int)(((float)it + 0.5f) * inv_ngrp), g = it - e * ngrp;  // exact for these small integers
+    const float* f = fr + e * SCAN_FRAME;
+    const real px = f[0], py = f[1], pz = f[2], cy = f[3], sy = f[4];
+    TerrainEnv te;
+    te.i0 = __float_as_int(f[5]); te.j0 = __float_as_int(f[6]); te.oz = f[7];
+    // all sixteen loads of the group's four lookups are issued before anything consumes them, and the Philox rounds (inlined here: a
+    // call would fence the loads) run while they are in flight
+    real hv[4];
+    if (ROUGH) {
+      float c00[4], c01[4], c10[4], c11[4];
+      real uu[4], vv[4];
+      bool in[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int r = 4 * g + k;
-        if (r < nrays) {
-          const int iy = r / P.scan_nx, ix = r - iy * P.scan_nx;
-          const real gx = r_fma((real)ix, P.scan_res, P.scan_x0), gy = r_fma((real)iy, P.scan_res, P.scan_y0);
-          real h = 0.f, g0, g1;
-          if (ROUGH) terrain_sample(P, S.terrain_h, te, px + cy * gx - sy * gy, py + sy * gx + cy * gy, h, g0, g1);
-          float v = (float)(pz - h - P.scan_off) + nz[k];
-          v = fminf(fmaxf(v, P.scan_lo), P.scan_hi) * P.s_scan;
-          if (obs) orow[r] = v;
-        }
+        const int iy = (int)(((float)r + 0.5f) * inv_nx), ix = r - iy * P.scan_nx;
+        const real gx = r_fma((real)ix, P.scan_res, P.scan_x0), gy = r_fma((real)iy, P.scan_res, P.scan_y0);
+        const real a = (px + cy * gx - sy * gy + P.t_half) * P.t_inv_hs, b = (py + sy * gx + cy * gy + P.t_half) * P.t_inv_hs;
+        const real fa = r_floor(a), fb = r_floor(b);
+        const int i = te.i0 + (int)fa, j = te.j0 + (int)fb;
+        uu[k] = a - fa; vv[k] = b - fb;
+        in[k] = i >= 0 && j >= 0 && i < P.t_gx - 1 && j < P.t_gy - 1;
+        const float* p = S.terrain_h + (in[k] ? (size_t)i * P.t_gy + j : 0);
+        c00[k] = __ldg(p); c01[k] = __ldg(p + 1); c10[k] = __ldg(p + P.t_gy); c11[k] = __ldg(p + P.t_gy + 1);
       }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {  // terrain_sample's arithmetic (h1v2_terrain.cuh), on the values loaded above
+        const bool upper = vv[k] >= uu[k];
+        const real dx = upper ? c11[k] - c01[k] : c10[k] - c00[k], dy = upper ? c01[k] - c00[k] : c11[k] - c10[k];
+        hv[k] = in[k] ? r_fma(uu[k], dx, r_fma(vv[k], dy, (real)c00[k])) - te.oz : -te.oz;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) hv[k] = 0.f;
+    }
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (P.corrupt) {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), STREAM_OBS, (uint32_t)(16 + g), P.key0, (uint32_t)(P.env_id_offset + warp_env0 + e), o);
+#pragma unroll
+      for (int k = 0; k < 4; k++) nz[k] = uni((float)(o[k] >> 8) * (1.0f / 16777216.0f), -P.n_scan, P.n_scan);
+    }
+    float* orow = obs + (size_t)(warp_env0 + e) * P.obs_dim + P.scan_col0 + 4 * g;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float v = (float)(pz - hv[k] - P.scan_off) + nz[k];
+      v = fminf(fmaxf(v, P.scan_lo), P.scan_hi) * P.s_scan;
+      if (obs && 4 * g + k < nrays) orow[k] = v;
     }
   }
 }

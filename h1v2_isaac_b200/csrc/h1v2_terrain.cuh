@@ -41,18 +41,41 @@ __device__ __forceinline__ void terrain_sample(const KParams& P, const float* __
     gx = dx * P.t_inv_hs; gy = dy * P.t_inv_hs;
   }
 }
-// Axes of the contact frame in the order the plane code uses them (local x, y, z = -t2, t1, n of MuJoCo's mju_makeFrame: t1 is the
-// world y axis -- z when the normal is within 30 degrees of y -- made orthogonal to the normal, t2 = n x t1; on the plane x, y, z).
-__device__ __forceinline__ void contact_axes(V3 n, V3& ax, V3& ay) {
-  const bool usey = r_abs(n.y) < 0.5f;
-  const real d = usey ? n.y : n.z;
-  V3 t = mk3(0.f, usey ? 1.f : 0.f, usey ? 0.f : 1.f) - n * d;
-  t = t * r_rsqrt(dot(t, t));
-  ay = t;
-  ax = cross(t, n);
+// Contact frame of MuJoCo's mju_makeFrame in the axis order the plane code uses (local x, y, z = -t2, t1, n; on the plane x, y, z):
+// t1 = (e - n d) / sqrt(1 - d^2) with e the world y axis (z when the normal is within 30 degrees of y) and d = n . e, t2 = n x t1, so
+// -t2 = t1 x n = (e x n) / sqrt(1 - d^2).  Only the normal is stored per contact point; the closed forms below rebuild what each
+// use needs (a dot product with n, one component of n x v, two scalings) instead of the axes themselves.
+struct CFrame {
+  V3 n;
+  real d, inv;
+  bool usey;
+};
+__device__ __forceinline__ CFrame cframe(V3 n) {
+  CFrame f;
+  f.n = n; f.usey = r_abs(n.y) < 0.5f;
+  f.d = f.usey ? n.y : n.z;
+  f.inv = r_rsqrt(r_fma(-f.d, f.d, 1.f));
+  return f;
 }
-__device__ __forceinline__ V3 to_contact(V3 ax, V3 ay, V3 n, V3 v) { return mk3(dot(ax, v), dot(ay, v), dot(n, v)); }
-__device__ __forceinline__ V3 from_contact(V3 ax, V3 ay, V3 n, V3 v) { return fma3(ax, v.x, fma3(ay, v.y, n * v.z)); }
+__device__ __forceinline__ V3 to_contact(const CFrame& f, V3 v) {  // (ax . v, ay . v, n . v)
+  const real nv = dot(f.n, v);
+  const real ev = f.usey ? v.y : v.z;
+  const real cx = f.usey ? r_fma(f.n.z, v.x, -f.n.x * v.z) : r_fma(f.n.x, v.y, -f.n.y * v.x);  // (e x n) . v
+  return mk3(cx * f.inv, r_fma(-f.d, nv, ev) * f.inv, nv);
+}
+__device__ __forceinline__ V3 from_contact(const CFrame& f, V3 w) {  // ax w.x + ay w.y + n w.z
+  const real a = w.x * f.inv, b = w.y * f.inv;
+  V3 r = f.n * r_fma(-b, f.d, w.z);
+  r.x += f.usey ? a * f.n.z : -a * f.n.y;
+  r.y += f.usey ? b : a * f.n.x;
+  r.z += f.usey ? -a * f.n.x : b;
+  return r;
+}
+__device__ __forceinline__ void contact_axes(const CFrame& f, V3& ax, V3& ay) {
+  ax = f.usey ? mk3(f.n.z * f.inv, 0.f, -f.n.x * f.inv) : mk3(-f.n.y * f.inv, f.n.x * f.inv, 0.f);
+  const V3 t = mk3(0.f, f.usey ? 1.f : 0.f, f.usey ? 0.f : 1.f) - f.n * f.d;
+  ay = t * f.inv;
+}
 
 // mdp.terrain_levels_vel (V/mdp/curriculums.py:21-52) + TerrainImporter.update_env_origins: on reset, an env that walked further than
 // half a tile moves one level up, one that covered less than half the distance its command asked for moves one down; past the last

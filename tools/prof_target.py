@@ -3,11 +3,11 @@ import sys
 sys.path.insert(0, '/root/repo')
 import torch
 from h1v2_isaac_b200.backend import H1v2Sim
-from h1v2_isaac_b200._capi import default_config, rsl_config
+from h1v2_isaac_b200._capi import default_config, rough_config, rsl_config
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 task = sys.argv[3] if len(sys.argv) > 3 else "flat"
-sim = H1v2Sim(n, rsl_config() if task == "rsl" else default_config(), seed=1)
+sim = H1v2Sim(n, {"rsl": rsl_config, "rough": rough_config}.get(task, default_config)(), seed=1)
 sim.observe()
 obs = torch.empty((n, sim.obs_dim), device='cuda'); rew = torch.empty(n, device='cuda')
 term = torch.empty(n, dtype=torch.uint8, device='cuda'); trunc = torch.empty(n, dtype=torch.uint8, device='cuda')
