@@ -263,7 +263,7 @@ def run_ours(args):
         if is_cat:  # h1v2_cat_step_host: float dones instead of the terminated flags
             hterm = torch.empty(n_envs, dtype=torch.float32).pin_memory()
         host_step = sim_.cat_step_host if is_cat else sim_.step_host
-        for i in range(20):  # the first sixteen calls also time the two host paths against each other (h1v2_host_path_info)
+        for i in range(48):  # the first forty calls also time the host paths against each other (h1v2_host_path_info)
             host_step(ha[i % 4], hobs, hrew, hterm, htrunc)
         if world > 1:
             dist.barrier()
@@ -275,13 +275,14 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         mode, threads = sim_.host_path_info()
-        # mode "assemble": only the new 45-float sample (a 192-byte slot) of every env crosses PCIe, host threads assemble the
-        # [N, obs_dim] rows in the caller's buffer; mode "rows": the kernel writes the rows themselves (zero-copy)
-        d2h = n_envs * ((48 * 4 if mode == 1 else sim_.obs_dim * 4) + 4 + 1 + 1)
+        n_rows = sim_.host_path_rows()
+        # "assemble": only the new 45-float sample (a 192-byte slot) of an env crosses PCIe, host threads assemble its [obs_dim] row in the
+        # caller's buffer; "rows": the kernel writes the rows themselves (zero-copy); "hybrid": rows for the first n_rows envs, samples for the rest
+        d2h = n_rows * sim_.obs_dim * 4 + (n_envs - n_rows) * 48 * 4 + n_envs * (4 + 1 + 1)
         return {"value": world * n_envs * Ke / float(td.item()), "unit": METRIC, "h2d_bytes_per_step": n_envs * 12 * 4, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": float(td.item()) / Ke * 1e3, "timer": "host wall clock around synchronous h1v2_step_host calls, max over ranks",
-                "host_path": {"mode": "assemble" if mode == 1 else "rows", "host_threads": threads,
-                              "rows_bytes_written_by_host_threads_per_step": n_envs * sim_.obs_dim * 4 if mode == 1 else 0}}
+                "host_path": {"mode": ("rows" if mode == 0 else ("assemble" if n_rows == 0 else "hybrid")), "host_threads": threads, "envs_with_rows_over_pcie": n_rows,
+                              "rows_bytes_written_by_host_threads_per_step": (n_envs - n_rows) * sim_.obs_dim * 4 if mode == 1 else 0}}
 
     e2e = None
     if not args.no_e2e:

@@ -133,6 +133,7 @@ _SYMBOLS = {
     "h1v2_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "h1v2_host_path_info": (C.c_int, [C.c_void_p, C.POINTER(i32), C.POINTER(i32)]),
+    "h1v2_host_path_rows": (C.c_int, [C.c_void_p]),
     "h1v2_set_reward_weights": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_cat_step": (C.c_int, [C.c_void_p] * 7),
     "h1v2_cat_step_host": (C.c_int, [C.c_void_p] * 6),

@@ -184,6 +184,10 @@ class H1v2Sim:
         self._check(self._lib.h1v2_host_path_info(self._h, C.byref(m), C.byref(t)))
         return int(m.value), int(t.value)
 
+    def host_path_rows(self) -> int:
+        """Envs whose rows the kernel writes into the caller's buffer itself (N: mode rows; 0..N in mode assemble, > 0 = hybrid)."""
+        return int(self._lib.h1v2_host_path_rows(self._h))
+
     def observe(self) -> torch.Tensor:
         obs = torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         self._check(self._lib.h1v2_observe(self._h, obs.data_ptr(), self._stream()))

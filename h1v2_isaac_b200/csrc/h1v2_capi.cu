@@ -85,9 +85,15 @@ struct H1v2Handle {
   bool ring_valid = false;        // the mirror equals the device ring
   uint64_t hist_launches = 0;     // step / observe launches so far == device counters[1] (the history head)
   struct HostPool* pool = nullptr;
-  int host_mode = -1;             // -1 undecided, 0 full rows over PCIe (zero-copy / staged), 1 samples + host assembly
-  int host_calib = -1;            // >= 0: calls made so far while both modes are being timed on this host (see step_host_impl)
-  double host_calib_t[2] = {1e30, 1e30};
+  int host_mode = -1;             // -1 undecided, 0 full rows over PCIe (zero-copy / staged), 1 samples + host assembly (of the envs >= host_rows)
+  int host_rows = 0;              // mode 1: envs [0, host_rows) still get their rows from the kernel over PCIe (a multiple of epw) -- the hybrid
+  cudaEvent_t host_ev = nullptr;   // end of the last streaming host step: the stream-taking entry points wait for it (order_after_host)
+  bool host_pending = false;
+  unsigned* h_flags = nullptr;     // pinned + mapped [blocks]: per-warp completion words of the step in flight (written by the kernel)
+  unsigned* h_flags_dev = nullptr;
+  unsigned host_seq = 0;
+  int host_calib = -1;            // >= 0: calls made so far while the candidates are being timed on this host (see step_host_impl)
+  double host_calib_t[5] = {1e30, 1e30, 1e30, 1e30, 1e30};
   // Constraints-as-Terminations tail (cfg.cat_enable)
   CatState cat = {};            // all step-to-step CaT state lives on the device (graph-replayable)
   uint8_t* cat_term = nullptr;  // scratch for the step kernel's terminated flags (h1v2_cat_step reports dones instead)
@@ -102,6 +108,11 @@ struct H1v2Handle {
 // Every stream-taking entry point notes its stream: h1v2_step_host runs on a private non-blocking stream and orders itself
 // after that work at entry (a C caller may do h1v2_reset(h, ids, n, NULL) and then h1v2_step_host).
 static inline void note_stream(H1v2Handle* h, cudaStream_t st) { h->last_stream = st; h->last_stream_set = true; }
+// ... and the other way round: a host step in streaming mode returns when all its outputs are in the caller's memory, while the last
+// block's bookkeeping may still be running on the private stream; work queued on another stream afterwards waits for it.
+static inline void order_after_host(H1v2Handle* h, cudaStream_t st) {
+  if (h->host_pending && st != h->host_stream) cudaStreamWaitEvent(st, h->host_ev, 0);
+}
 
 // ------------------------------------------------------------------------------------------------------
 // auxiliary kernels (not on the step path)
@@ -529,13 +540,23 @@ struct HostPool {
   float* ring = nullptr;
   float* obs = nullptr;
   int n = 0, H = 0, head = 0;
+  int e0 = 0;  // first env the pool assembles (the envs below it get their rows from the kernel)
+  // streaming hand-over (flags != NULL): the kernel raises flags[w] = seq once warp w's outputs are in host memory; the workers take the new
+  // slot of an env as soon as its warp has reported instead of waiting for the whole launch
+  const volatile unsigned* flags = nullptr;
+  unsigned seq = 0;
+  int epw = 16;
+  std::atomic<int> failed{0};
 };
 static const int kTermOff[7] = {0, 3, 6, 9, 21, 33, 45};
 static inline void env_range(const HostPool* p, int t, int& a, int& b) {
-  const int per = (p->n + p->nthreads - 1) / p->nthreads;
-  a = std::min(p->n, t * per); b = std::min(p->n, a + per);
+  const int cnt = p->n - p->e0, per = (cnt + p->nthreads - 1) / p->nthreads;
+  a = p->e0 + std::min(cnt, t * per); b = std::min(p->n, a + per);
 }
-static void assemble_old(const HostPool* p, int t) {  // phase 1: history slots older than the step in flight
+// phase 1: history slots older than the step in flight, slot by slot.  (Measured on the B200 box's 16-core host and not kept: writing
+// term-major doubles the time of this phase -- 42 vs 20 us at 4096 envs -- and non-temporal row stores make a 32768-env step 20 %
+// slower, 1.23 vs 1.01 ms.)
+static void assemble_old(const HostPool* p, int t) {
   int a, b; env_range(p, t, a, b);
   const int H = p->H, od = 45 * H;
   for (int e = a; e < b; e++) {
@@ -551,8 +572,36 @@ static void assemble_old(const HostPool* p, int t) {  // phase 1: history slots 
     }
   }
 }
+// spin until warp w of the launch in flight has reported; false after ~2 s (a faulted kernel never reports)
+static bool wait_flag(HostPool* p, int w) {
+  if (p->flags[w] == p->seq) return true;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spin = 1;; spin++) {
+    if (p->flags[w] == p->seq) return true;
+    if (p->failed.load(std::memory_order_relaxed)) return false;
+    CPU_PAUSE();
+    if ((spin & 0xffff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) {
+      p->failed.store(1, std::memory_order_relaxed);
+      return false;
+    }
+  }
+}
+static void assemble_new_range(const HostPool* p, int a, int b);
+static void assemble_new_streaming(HostPool* p, int t) {  // the new slot of every env of the range, warp by warp as the kernel reports them
+  int a, b; env_range(p, t, a, b);
+  for (int e = a; e < b;) {
+    const int w = e / p->epw, e1 = std::min(b, (w + 1) * p->epw);
+    if (!wait_flag(p, w)) return;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    assemble_new_range(p, e, e1);
+    e = e1;
+  }
+}
 static void assemble_new(const HostPool* p, int t) {  // phase 2: the new sample; a first push fills the whole ring and row
   int a, b; env_range(p, t, a, b);
+  assemble_new_range(p, a, b);
+}
+static void assemble_new_range(const HostPool* p, int a, int b) {
   const int H = p->H, od = 45 * H;
   for (int e = a; e < b; e++) {
     const float* s = p->sample + (size_t)e * H1V2_HIST_STRIDE;
@@ -584,8 +633,11 @@ static void pool_worker(HostPool* p, int t) {
     }
     seen = p->gen.load(std::memory_order_acquire);
     assemble_old(p, t);
-    while (p->phase2.load(std::memory_order_acquire) != seen) CPU_PAUSE();  // the kernel is in flight: < 1 ms
-    assemble_new(p, t);
+    if (p->flags) assemble_new_streaming(p, t);
+    else {
+      while (p->phase2.load(std::memory_order_acquire) != seen) CPU_PAUSE();  // the kernel is in flight: < 1 ms
+      assemble_new(p, t);
+    }
     p->done.fetch_add(1, std::memory_order_release);
   }
 }
@@ -757,6 +809,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   }
   CKH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   CKH(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+  CKH(cudaEventCreateWithFlags(&h->host_ev, cudaEventDisableTiming));
   {
     const int rows = h->P.t_rows, mi = cfg->terrain_max_init_level;
     startup_kernel<<<(n_envs + 127) / 128, 128>>>(h->P, h->S, cfg->friction_range[0], cfg->friction_range[1], cfg->mass_add_range[0], cfg->mass_add_range[1],
@@ -779,8 +832,10 @@ void h1v2_destroy(H1v2Handle* h) {
     if (p) cudaFree(p);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
+  if (h->host_ev) cudaEventDestroy(h->host_ev);
   pool_destroy(h->pool);
   if (h->h_sample) cudaFreeHost(h->h_sample);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
   std::free(h->h_ring);
   delete h;
 }
@@ -824,6 +879,7 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int cnt = env_ids ? n : h->n;
   if (cnt <= 0) return 0;
+  order_after_host(h, st);
   reset_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(h->P, h->S, env_ids, cnt, h->cat.sums);
   note_stream(h, st);
   h->launches += 1;
@@ -832,10 +888,13 @@ int h1v2_reset(H1v2Handle* h, const int64_t* env_ids, int32_t n, void* cuda_stre
 }
 
 static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc, cudaStream_t st,
-                       float* sample_out = nullptr, bool cat = false) {
+                       float* sample_out = nullptr, bool cat = false, int n_rows = 0, unsigned* host_flags = nullptr, unsigned host_seq = 0) {
   DeviceGuard guard(h->device);
   KState S = h->S;
   S.sample_out = sample_out;
+  S.n_rows = n_rows;
+  S.host_flags = host_flags; S.host_seq = host_seq;
+  order_after_host(h, st);
   if (cat) S.cat = h->cat.k;  // the step kernel also leaves the raw constraint columns and their maxima (h1v2_cat_step)
   h->hist_launches += 1;  // every launch advances the history head (device counters[1])
   if (!sample_out) { h->ring_valid = false; note_stream(h, st); }  // the host mirror of the ring misses this launch's sample
@@ -891,8 +950,8 @@ static CatParams cat_params(const H1v2Handle* h) {
   for (int t = 0; t < H1V2_NUM_CSTR; t++) C.max_p[t] = c.cat_max_p[t];
   return C;
 }
-static int launch_cat(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* trunc, cudaStream_t st, float* sample_out) {
-  if (launch_step(h, true, actions, obs, rew, h->cat_term, trunc, st, sample_out, true) != 0) return -1;
+static int launch_cat(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* trunc, cudaStream_t st, float* sample_out, int n_rows = 0) {
+  if (launch_step(h, true, actions, obs, rew, h->cat_term, trunc, st, sample_out, true, n_rows) != 0) return -1;
   DeviceGuard guard(h->device);
   cat_apply_kernel<<<(h->n + 63) / 64, 64, 0, st>>>(cat_params(h), h->cat, rew, dones);  // small blocks: at 4096 envs the tail is latency-bound
   h->launches += 1;
@@ -912,34 +971,64 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
     CK(cudaStreamWaitEvent(st, h->order_ev, 0));
     h->last_stream_set = false;
   }
+  float* obs_dev = mapped_alias(obs);  // device alias of a pinned caller buffer, else NULL
+  // candidates of the calibration: {mode, fraction of the envs whose rows the kernel writes over PCIe}
+  static const struct { int mode; float frac; } kCand[5] = {{1, 0.f}, {0, 1.f}, {1, 0.25f}, {1, 0.5f}, {1, 0.75f}};
+  const int epw = h->P.epw;
+  auto rows_for = [&](float frac) { return std::min(h->n, (int)std::lround(frac * h->n / epw) * epw); };
+  auto set_rows = [&](int r) { if (r != h->host_rows) { h->host_rows = r; h->ring_valid = false; } };  // the mirror is only kept for the assembled envs
   if (h->host_mode < 0) {
-    // mode 1 (samples over PCIe + rows assembled by host threads) pays while the rows and the ring mirror stay cache-resident
-    // and the rank has cores to spare; otherwise mode 0: the kernel writes whole rows into the (pinned) caller buffer, the
-    // minimum-traffic way for the host memory system.  H1V2_HOST_PATH=rows|assemble overrides (measured: profiles/r2_notes.md).
+    // Three ways to bring the [N, 45 H] rows into the caller's buffer.  "rows": the kernel writes them (zero-copy over PCIe when the
+    // buffer is pinned) -- PCIe-bound at large N (59 MB per step at 32768 envs).  "assemble": only the new 45-float sample of every
+    // env crosses PCIe, host threads assemble the rows from a host mirror of the ring -- bound by the cores' memory bandwidth.
+    // "hybrid": the kernel writes the rows of the first envs while the host threads assemble those of the rest: PCIe DMA and the
+    // cores work concurrently.  Which wins depends on the host (cores per rank, cache, memory bandwidth, PCIe) as much as on the env
+    // count, so a handle with a pinned buffer and at least four host threads measures: five candidates (assemble, rows, hybrid at
+    // 1/4, 1/2, 3/4) x eight calls each (three warm-up: ring fetch, page faults, thread wake-up), from call 40 onwards the fastest.
+    // All of them return bit-identical results, so the caller sees nothing of it.  H1V2_HOST_PATH=rows|assemble|hybrid
+    // (H1V2_HOST_ROWS_FRAC, default 0.5) overrides.
     h->pool = pool_create();
     const char* e = std::getenv("H1V2_HOST_PATH");
     if (e && !std::strcmp(e, "rows")) h->host_mode = 0;
     else if (e && !std::strcmp(e, "assemble") && !h->rough) h->host_mode = 1;
-    // Otherwise the handle measures: which path wins depends on the host (cores per rank, cache, memory bandwidth) as much as on
-    // the env count -- on the 16-core host of a B200 box 16 threads beat the row path at every size (4096 envs 0.258 vs 0.296 ms,
-    // 32768 envs 0.92 vs 1.40 ms), 8 threads up to 8192 envs, 4 threads never (profiles/r2_e2e_modes.txt).  Calls 0-7 run mode 1,
-    // calls 8-15 mode 0 (the first three of each are warm-up: ring fetch, page faults, thread wake-up), call 16 onwards the faster one.  Both modes
-    // return bit-identical results, so the caller sees nothing of it.
+    else if (e && !std::strcmp(e, "hybrid") && !h->rough && obs_dev) {
+      const char* f = std::getenv("H1V2_HOST_ROWS_FRAC");
+      h->host_mode = 1;
+      set_rows(rows_for(f ? std::min(1.f, std::max(0.f, (float)std::atof(f))) : 0.5f));
+    }
     else if (h->rough || h->pool->nthreads < 4) h->host_mode = 0;  // the Rough id has no history to assemble: rows
     else { h->host_mode = 1; h->host_calib = 0; }
   }
+  if (h->host_mode == 1 && h->host_rows > 0 && !obs_dev) set_rows(0);  // a pageable buffer cannot take the kernel's rows directly
   const auto t_call0 = std::chrono::steady_clock::now();
   struct CalibGuard {  // times this call and advances the calibration when it returns
-    H1v2Handle* h; std::chrono::steady_clock::time_point t0;
+    H1v2Handle* h; std::chrono::steady_clock::time_point t0; bool hybrid_ok; int r25, r50, r75;
     ~CalibGuard() {
       if (h->host_calib < 0) return;
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      const int k = h->host_calib++, half = 8, warm = 3;  // per mode: 3 warm-up calls (thread wake-up, page faults, ring fetch), 5 timed
-      if (k % half >= warm) h->host_calib_t[k < half ? 1 : 0] = std::min(h->host_calib_t[k < half ? 1 : 0], dt);
-      if (k == half - 1) h->host_mode = 0;
-      if (k == 2 * half - 1) { h->host_mode = h->host_calib_t[1] <= h->host_calib_t[0] ? 1 : 0; h->host_calib = -1; }
+      const int per = 8, warm = 3, ncand = hybrid_ok ? 5 : 2;
+      const int k = h->host_calib++, c = k / per;
+      if (k % per >= warm) h->host_calib_t[c] = std::min(h->host_calib_t[c], dt);
+      const int rows_of[5] = {0, 0, r25, r50, r75};
+      auto apply = [&](int cand) {
+        h->host_mode = kCand[cand].mode;
+        const int r = kCand[cand].mode == 1 ? rows_of[cand] : 0;
+        if (r != h->host_rows) { h->host_rows = r; h->ring_valid = false; }
+      };
+      if ((k + 1) % per == 0) {
+        if (c + 1 < ncand) apply(c + 1);
+        else {
+          int best = 0;
+          for (int i = 1; i < ncand; i++) if (h->host_calib_t[i] < h->host_calib_t[best]) best = i;
+          if (std::getenv("H1V2_HOST_DEBUG"))
+            std::fprintf(stderr, "[h1v2 host path] calibration (ms): assemble %.4f rows %.4f hybrid 1/4 %.4f 1/2 %.4f 3/4 %.4f -> candidate %d\n", h->host_calib_t[0] * 1e3,
+                         h->host_calib_t[1] * 1e3, h->host_calib_t[2] * 1e3, h->host_calib_t[3] * 1e3, h->host_calib_t[4] * 1e3, best);
+          apply(best);
+          h->host_calib = -1;
+        }
+      }
     }
-  } calib_guard{h, t_call0};
+  } calib_guard{h, t_call0, obs_dev != nullptr, rows_for(0.25f), rows_for(0.5f), rows_for(0.75f)};
   if (!h->d_act) {
     CK(cudaMalloc(&h->d_act, N * 12 * sizeof(float)));
     CK(cudaMalloc(&h->d_rew, N * sizeof(float)));
@@ -953,9 +1042,12 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
   uint8_t* term_dev = cat ? h->cat_term : mapped_alias(terminated);
   uint8_t* trunc_dev = mapped_alias(truncated);
   // one launch sequence for both flavours: the plain step, or the step + the constraint apply kernel
-  auto launch = [&](float* obs_arg, float* sample_arg) -> int {
-    if (cat) return launch_cat(h, act_dev_, obs_arg, h->d_rew, h->d_dones, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg);
-    return launch_step(h, true, act_dev_, obs_arg, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg);
+  // streaming hand-over: possible when every output of the step kernel lands in mapped host memory (pinned buffers, no constraint tail)
+  const bool stream_out = !cat && rew_dev && term_dev && trunc_dev && h->host_mode == 1 && !std::getenv("H1V2_HOST_NO_STREAMING");
+  auto launch = [&](float* obs_arg, float* sample_arg, int n_rows) -> int {
+    if (cat) return launch_cat(h, act_dev_, obs_arg, h->d_rew, h->d_dones, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg, n_rows);
+    return launch_step(h, true, act_dev_, obs_arg, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg, false, n_rows,
+                       stream_out ? h->h_flags_dev : nullptr, h->host_seq);
   };
   auto copy_back = [&]() -> int {
     if (!rew_dev) CK(cudaMemcpyAsync(rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -972,6 +1064,10 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
       CK(cudaHostGetDevicePointer(&h->h_sample_dev, h->h_sample, 0));
       h->h_ring = (float*)std::aligned_alloc(64, (ring_bytes + 63) / 64 * 64);
       if (!h->h_ring) return fail("h1v2_step_host: out of host memory");
+      const size_t nblk = (N + h->P.epw - 1) / h->P.epw;
+      CK(cudaHostAlloc(&h->h_flags, (nblk + 1) * sizeof(unsigned), cudaHostAllocMapped));  // one word per warp + one for the launch's bookkeeping
+      CK(cudaHostGetDevicePointer(&h->h_flags_dev, h->h_flags, 0));
+      std::memset(h->h_flags, 0, (nblk + 1) * sizeof(unsigned));
     }
     if (!h->ring_valid) {  // first call, or the device path ran in between: fetch the ring once, and the head from the device
       unsigned long long head_counter = 0;  // (a CUDA graph may have replayed steps this library never saw on the host)
@@ -982,8 +1078,11 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
     }
     HostPool* p = h->pool;
     const int head = (int)((h->hist_launches + 1) % (uint64_t)H);  // the slot this launch writes (step_kernel: counters[1] + 1)
-    if (launch(nullptr, h->h_sample_dev) != 0 || copy_back() != 0) return -1;
-    p->sample = h->h_sample; p->ring = h->h_ring; p->obs = obs; p->n = h->n; p->H = H; p->head = head;
+    // hybrid: the envs below host_rows get their rows from the kernel (zero-copy into the pinned caller buffer), the pool takes the rest
+    if (stream_out && ++h->host_seq == 0) h->host_seq = 1;  // 0 is what the flag words start with
+    if (launch(h->host_rows > 0 ? obs_dev : nullptr, h->h_sample_dev, h->host_rows) != 0 || copy_back() != 0) return -1;
+    p->sample = h->h_sample; p->ring = h->h_ring; p->obs = obs; p->n = h->n; p->H = H; p->head = head; p->e0 = h->host_rows;
+    p->flags = stream_out ? h->h_flags : nullptr; p->seq = h->host_seq; p->epw = h->P.epw; p->failed.store(0, std::memory_order_relaxed);
     p->done.store(0, std::memory_order_relaxed);
     const uint64_t gen = p->gen.load(std::memory_order_relaxed) + 1;
     p->gen.store(gen, std::memory_order_release);  // publishes the job to the spinning workers
@@ -991,11 +1090,51 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
       std::lock_guard<std::mutex> lk(p->m);  // a worker that went to sleep checks gen under this mutex: no lost wake-up
       if (p->sleepers.load(std::memory_order_relaxed) > 0) p->cv.notify_all();
     }
+    static const bool dbg = std::getenv("H1V2_HOST_DEBUG") != nullptr;  // breakdown of a call: tools/diag_e2e.py
+    static double acc[5] = {0, 0, 0, 0, 0};
+    static int nacc = 0;
+    const auto t1 = std::chrono::steady_clock::now();
     assemble_old(p, 0);  // the caller's thread is worker 0
-    const cudaError_t e = cudaStreamSynchronize(st);
-    p->phase2.store(gen, std::memory_order_release);  // release the workers even on failure
-    if (e == cudaSuccess) assemble_new(p, 0);
-    while (p->done.load(std::memory_order_acquire) != p->nthreads - 1) CPU_PAUSE();
+    const auto t2 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaSuccess;
+    auto t3 = t2, t4 = t2;
+    if (stream_out) {
+      // warp by warp as the kernel reports them; the rows the kernel wrote itself (hybrid) are complete once their warps have reported
+      assemble_new_streaming(p, 0);
+      t3 = std::chrono::steady_clock::now();
+      for (int w = 0; w < (h->host_rows + h->P.epw - 1) / h->P.epw && wait_flag(p, w); w++) {}
+      t4 = std::chrono::steady_clock::now();
+      while (p->done.load(std::memory_order_acquire) != p->nthreads - 1) CPU_PAUSE();
+      wait_flag(p, (h->n + h->P.epw - 1) / h->P.epw);  // the last block's bookkeeping (log vector, counters) has been published too
+      // Every warp and the last block have reported: all outputs are in the caller's memory, all device-side state of the step is
+      // written; what is left of the launch is the kernel's exit.  Waiting for the stream here would cost the driver's completion
+      // latency (~20 us) for nothing anyone can see; the stream-taking entry points still order themselves after this launch
+      // (order_after_host).  A kernel that faulted never reports: the timeout above ends the wait, the synchronise then names the error.
+      if (p->failed.load(std::memory_order_relaxed)) {
+        e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaErrorLaunchTimeout;
+      } else {
+        e = cudaEventRecord(h->host_ev, st);
+        h->host_pending = e == cudaSuccess;
+      }
+    } else {
+      e = cudaStreamSynchronize(st);
+      t3 = std::chrono::steady_clock::now();
+      p->phase2.store(gen, std::memory_order_release);  // release the workers even on failure
+      if (e == cudaSuccess) assemble_new(p, 0);
+      t4 = std::chrono::steady_clock::now();
+      while (p->done.load(std::memory_order_acquire) != p->nthreads - 1) CPU_PAUSE();
+    }
+    if (dbg) {
+      const auto t5 = std::chrono::steady_clock::now();
+      auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+      acc[0] += us(t_call0, t1); acc[1] += us(t1, t2); acc[2] += us(t2, t3); acc[3] += us(t3, t4); acc[4] += us(t4, t5);
+      if (++nacc == 100) {
+        std::fprintf(stderr, "[h1v2 host path] per call: enqueue %.1f us | old slots (worker 0) %.1f | wait for the stream (streaming: new slots as the warps report) %.1f | new slot (streaming: row warps) %.1f | pool + final sync %.1f\n",
+                     acc[0] / 100, acc[1] / 100, acc[2] / 100, acc[3] / 100, acc[4] / 100);
+        nacc = 0; acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = 0;
+      }
+    }
     if (e != cudaSuccess) { h->ring_valid = false; return fail(std::string("h1v2_step_host: ") + cudaGetErrorString(e)); }
     h->ring_valid = true;
     return 0;
@@ -1003,9 +1142,8 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
   // mode 0.  Pinned caller buffers are written by the kernel itself (zero-copy over PCIe): the 1.8 KB observation row of an env
   // leaves the GPU as soon as its warp has emitted it, overlapping the transfer with the rest of the step instead of
   // serialising a 450-float-per-env D2H copy behind the kernel.  Pageable buffers take the staged path.
-  float* obs_dev = mapped_alias(obs);
   if (!obs_dev && !h->d_obs) CK(cudaMalloc(&h->d_obs, N * od * sizeof(float)));
-  if (launch(obs_dev ? obs_dev : h->d_obs, nullptr) != 0) return -1;
+  if (launch(obs_dev ? obs_dev : h->d_obs, nullptr, 0) != 0) return -1;
   h->last_stream_set = false;  // nothing of this launch is left in flight after the synchronise below
   if (!obs_dev) CK(cudaMemcpyAsync(obs, h->d_obs, N * od * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (copy_back() != 0) return -1;
@@ -1031,6 +1169,7 @@ int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads) {
   *threads = h->pool ? h->pool->nthreads : 0;
   return 0;
 }
+int h1v2_host_path_rows(const H1v2Handle* h) { return h ? (h->host_mode == 0 ? h->n : (h->host_mode == 1 ? h->host_rows : -1)) : -1; }
 
 int h1v2_cat_step(H1v2Handle* h, const float* actions, float* obs, float* rew, float* dones, uint8_t* truncated, void* cuda_stream) {
   if (!h || !actions || !obs || !rew || !dones || !truncated) return fail("h1v2_cat_step: bad arguments");
@@ -1117,6 +1256,7 @@ int h1v2_get_terrain_log(H1v2Handle* h, const float** log_dev) {
 int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
   if (!h || !dst) return fail("h1v2_get_state: bad arguments");
   DeviceGuard guard(h->device);
+  order_after_host(h, (cudaStream_t)cuda_stream);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *dst, 0);
   note_stream(h, (cudaStream_t)cuda_stream);
   h->launches += 1;
@@ -1126,6 +1266,7 @@ int h1v2_get_state(H1v2Handle* h, const H1v2State* dst, void* cuda_stream) {
 int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream) {
   if (!h || !src) return fail("h1v2_set_state: bad arguments");
   DeviceGuard guard(h->device);
+  order_after_host(h, (cudaStream_t)cuda_stream);
   state_io_kernel<<<(h->n + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(h->P, h->S, *src, 1);
   note_stream(h, (cudaStream_t)cuda_stream);
   h->ring_valid = false;  // may have replaced the observation history
@@ -1182,6 +1323,7 @@ int h1v2_measure_fp32_peak(int32_t device, float* tflops) {
 int h1v2_random_actions(H1v2Handle* h, float* actions, uint64_t step, void* cuda_stream) {
   if (!h || !actions) return fail("h1v2_random_actions: bad arguments");
   DeviceGuard guard(h->device);
+  order_after_host(h, (cudaStream_t)cuda_stream);
   random_actions_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(h->P, actions, step);
   note_stream(h, (cudaStream_t)cuda_stream);
   h->launches += 1;

@@ -125,6 +125,9 @@ struct KState {
   const float* terrain_h;   // [t_gx][t_gy] height field in metres (Rough id), second index fastest
   const float* terrain_oz;  // [t_rows][t_cols] height of every tile's origin
   float* tlog;              // [2] sum of the envs' terrain levels of the step in flight | mean level after the last step
+  int n_rows;         // host path (sample_out != NULL): envs [0, n_rows) get their observation ROWS written (into `obs`), the rest only their sample
+  unsigned* host_flags;  // host path: [blocks of the launch] mapped host words; a warp stores host_seq there once its outputs are in the caller's memory
+  unsigned host_seq;
   float* sample_out;  // [N][48] or NULL: this step's observation sample (45) | fresh flag at [45]; the host path of h1v2_step_host assembles the rows from it
   float* acc;      // [H1V2_LOG_DIM] log accumulators (atomics)
   float* log;      // [H1V2_LOG_DIM] published log vector

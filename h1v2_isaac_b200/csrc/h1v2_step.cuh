@@ -297,6 +297,10 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
   }
   const int nenv = min(P.epw, P.n - warp_env0), epc = hist_envs_per_chunk(H, P.epw), ring = H * H1V2_HIST_STRIDE;
   const int my_e = (int)(lane >> 1);
+  // host path (h1v2_step_host): the warps of envs [0, n_rows) write whole rows (PCIe DMA into the caller's pinned buffer), the others
+  // only their new sample (host threads assemble those rows meanwhile): the two halves of the host's work run concurrently
+  const bool warp_samples = S.sample_out != nullptr && warp_env0 >= S.n_rows;
+  if (warp_samples) obs = nullptr;
 #pragma unroll 1
   for (int e0 = 0; e0 < nenv; e0 += epc) {
     if (e0 > 0) { __syncwarp(); hist_prefetch(P, S, tid, bid, e0, 1); }  // H = 10 at 16 envs per warp: the 16 rings do not fit at once
@@ -318,7 +322,7 @@ __device__ __forceinline__ void emit_observation(const KParams& P, const KState&
     }
     __syncwarp();
     const int e1 = min(nenv, e0 + epc);
-    if (S.sample_out) {
+    if (warp_samples) {
       // host path (h1v2_step_host): only what is NEW leaves the GPU -- the 45-float sample of every env of the chunk (+ the
       // first-push flag), 192 B per env instead of the 1.8 KB row the host can assemble from its own copy of the ring.
       // The warp's samples are one contiguous 16-byte-aligned range: coalesced float4 stores (zero-copy over PCIe when pinned).
@@ -994,6 +998,14 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     }
   }
   cmd.flags &= ~FLAG_HIST_FRESH;
+  if (S.host_flags) {
+    // host path (h1v2_step_host): everything this warp owes the caller -- reward, flags, sample or row -- has been stored into mapped
+    // host memory; make it visible system-wide, then raise the warp's flag: the host threads pick the envs up warp by warp while the
+    // rest of the grid is still running, instead of waiting for the whole launch
+    __threadfence_system();
+    __syncwarp();
+    if ((tid & 31) == 0) *((volatile unsigned*)S.host_flags + bid) = S.host_seq;
+  }
 
   // ---- store state ----
   if (valid) {
@@ -1026,6 +1038,11 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   if (ticket == gridDim.x - 1) {
     __threadfence();
     finalize_step(S, DO_STEP, CAT, tid, P.n, P.epw);
+    if (S.host_flags) {  // host path: the launch's bookkeeping (log vector, counters) is done too -- the word after the warps' flags
+      __threadfence_system();
+      __syncwarp();
+      if ((tid & 31) == 0) *((volatile unsigned*)S.host_flags + gridDim.x) = S.host_seq;
+    }
   }
 }
 

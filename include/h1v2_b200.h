@@ -317,14 +317,19 @@ int h1v2_step(H1v2Handle* h, const float* actions /*[N,12]*/, float* obs /*[N,ob
 /* Same with HOST buffers (pinned or pageable): H2D of actions and D2H of all outputs inside, synchronises. */
 int h1v2_step_host(H1v2Handle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                    uint8_t* truncated);
-/* How h1v2_step_host moves the observations (decided at its first call; H1V2_HOST_PATH=rows|assemble and
- * H1V2_HOST_THREADS=<n> override): mode 0 "rows" = the kernel writes whole [N, obs_dim] rows into the caller's buffer
- * (zero-copy over PCIe when it is pinned, staged otherwise); mode 1 "assemble" = only the step's new 45-float sample of
- * every env crosses PCIe and `threads` host threads assemble the rows from a host mirror of the history ring while the
- * kernel runs (bit-identical rows; tests/test_gpu_parity.py::test_step_host_matches_device_path).  -1 = not decided yet.
- * Without an override a handle with at least four host threads times both modes over its first sixteen calls and keeps the faster.
+/* How h1v2_step_host moves the observations (decided at its first calls; H1V2_HOST_PATH=rows|assemble|hybrid, H1V2_HOST_ROWS_FRAC=<0..1> and
+ * H1V2_HOST_THREADS=<n> override): mode 0 "rows" = the kernel writes whole [N, obs_dim] rows into the caller's buffer (zero-copy over PCIe when it
+ * is pinned, staged otherwise); mode 1 "assemble" = only the step's new 45-float sample of an env crosses PCIe and `threads` host threads
+ * assemble its row from a host mirror of the history ring while the kernel runs -- for ALL envs, or ("hybrid") for the envs from
+ * h1v2_host_path_rows() upwards while the kernel writes the rows of the envs below it, so that PCIe DMA and the cores' memory bandwidth work
+ * concurrently.  Bit-identical rows in every case (tests/test_gpu_parity.py::test_step_host_matches_device_path).  -1 = not decided yet.
+ * Without an override a handle with a pinned observation buffer and at least four host threads times five candidates (assemble, rows, hybrid
+ * at 1/4, 1/2, 3/4) over its first forty calls and keeps the fastest.  With pinned buffers the kernel raises one flag per warp in mapped host
+ * memory once that warp's outputs are in the caller's buffers: the host threads take the envs over warp by warp while the rest of the grid runs.
  * The call orders itself after work queued earlier through the stream-taking entry points and synchronises before returning. */
 int h1v2_host_path_info(const H1v2Handle* h, int32_t* mode, int32_t* threads);
+/* envs whose observation rows the kernel itself writes into the caller's buffer: N in mode 0, 0 .. N in mode 1 (> 0: hybrid), -1 undecided */
+int h1v2_host_path_rows(const H1v2Handle* h);
 
 /* Replace the reward weights (CurriculumManager's modify_reward_weight, rsl_env_cfg.py:447-497).  Host array of
  * H1V2_NUM_REW floats; takes effect from the next step enqueued after the call.  Never synchronises.  (h1v2_step is CUDA-graph
