@@ -13,15 +13,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 F64 = os.path.join(ROOT, "h1v2_isaac_b200", "libh1v2_b200_f64.so")
 PHYS = ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"]
 SYNC = PHYS + ["last_action", "target_hist", "lag", "fresh", "command", "heading_target", "time_left", "is_standing", "is_heading", "cmd_metrics",
-               "feet_timers", "episode_sums", "obs_history", "friction", "mass_add", "push_time_left"]
+               "feet_timers", "episode_sums", "obs_history", "friction", "mass_add", "push_time_left", "terrain_level"]
 
 
-def _run(cfg, lib, n, steps, seed=3):
+def _run(cfg, lib, n, steps, seed=3, terrain_scale=1.0):
     import torch
     from h1v2_isaac_b200.backend import H1v2Sim
     from oracle.oracle import Oracle
     sim = H1v2Sim(n, cfg, device="cuda:0", seed=seed, diagnostics=True, lib_path=lib)
     orc = Oracle(cfg, n, seed=seed, threads=16)
+    if terrain_scale != 1.0:
+        H = orc.terrain() * np.float32(terrain_scale)
+        sim.set_terrain(H); orc.set_terrain(H)
     sim.observe(); orc.observe()
     rng = np.random.default_rng(seed)
     errs = {k: [] for k in PHYS}
@@ -33,6 +36,8 @@ def _run(cfg, lib, n, steps, seed=3):
         o = orc.get_state(PHYS)
         mc, ml = orc.activation_margin()
         keep = ~(to | uo | tg.cpu().numpy()) & (mc > 2e-6) & (ml > 2e-6)
+        if cfg.terrain_enable:  # a contact candidate within 10 um of a triangle edge of the height field: the normal jumps there
+            keep &= orc.tri_margin() > 1e-4
         for k in PHYS:
             errs[k].append(np.abs(g[k][keep] - o[k][keep]).max(axis=1))
         orc.set_state({k: g[k] for k in SYNC}); orc.episode_length = sim.episode_length_buf.cpu().numpy()
@@ -55,3 +60,23 @@ def test_double_build_of_the_same_kernel_matches_the_oracle(cfg):
     assert e64["joint_pos"].max() < 2e-6 and e64["root_pos"].max() < 1e-6
     # the float product on the same states: within the north star's single-step tolerance, and its tail is rounding
     assert e32["joint_vel"].max() < 1e-3 and np.quantile(e32["joint_vel"], 0.99) > 1.5 * np.quantile(e64["joint_vel"], 0.99)
+
+
+def test_double_build_of_the_rough_kernel_matches_the_oracle():
+    """The rough instantiation (height-field contacts in the triangle's frame, closed-form frame transforms) built in double against the
+    oracle's frame-general pyramid rows, on the reference's terrain and on a field four times as steep: the algorithm is the oracle's
+    (the contact frame, the rotated point weights, the residuals kept in the contact frame); what the float product adds is rounding."""
+    from h1v2_isaac_b200._capi import rough_config
+    assert os.path.exists(F64)
+    c = rough_config()
+    c.decimation = 1
+    c.max_delay = 2
+    for scale in (1.0, 4.0):
+        e64 = _run(c, F64, 2048, 48, terrain_scale=scale)
+        e32 = _run(c, None, 2048, 48, terrain_scale=scale)
+        for name, e in (("double build", e64), ("float product", e32)):
+            print(f"terrain x{scale}", name, {k: (float(v.max()), float(np.quantile(v, 0.999)), float(np.quantile(v, 0.99))) for k, v in e.items()})
+        assert e64["joint_vel"].max() < 3e-4 and np.quantile(e64["joint_vel"], 0.99) < 5e-5
+        assert e64["root_ang_vel"].max() < 3e-5 and e64["root_lin_vel"].max() < 1e-5
+        assert e64["joint_pos"].max() < 2e-6 and e64["root_pos"].max() < 1e-6
+        assert e32["joint_vel"].max() < (1e-3 if scale == 1.0 else 2e-3)
