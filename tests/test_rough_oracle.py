@@ -212,3 +212,41 @@ def test_slope_contacts_live_in_the_slope_frame(rough):
             worst = max(worst, float(ratio.max())); sliding += int((ratio > 0.98).sum())
     assert k >= 20, "the robots fell before the test saw anything"
     assert worst <= 1.0 + 1e-6 and sliding > 0, (worst, sliding)
+
+
+def test_play_cfg_of_the_rough_id_runs_on_the_oracle():
+    """Isaac-Velocity-Rough-H12_12dof-Play-v0 (C12/rough_env_cfg.py:128-156): 50 envs on 5 x 5 tiles, every level populated from the start
+    (max_init_terrain_level None), no curriculum, no observation noise, forward command 1 m/s with heading 0."""
+    import json
+    from h1v2_isaac_b200._capi import H1v2Config
+    from oracle.oracle import Oracle, task_config
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "play_cfg_resolved.json")))["Isaac-Velocity-Rough-H12_12dof-Play-v0"]
+    c = task_config("rough")
+    for k, v in gold["kernel_config"].items():  # the reference's own Play cfg, flattened
+        cur = getattr(c, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                if hasattr(cur[i], "__len__"):
+                    for j, y in enumerate(x):
+                        cur[i][j] = y
+                else:
+                    cur[i] = x
+        else:
+            setattr(c, k, v)
+    assert isinstance(c, H1v2Config) and c.terrain_rows == 5 and c.terrain_cols == 5 and c.terrain_curriculum == 0 and c.enable_corruption == 0
+    n = gold["num_envs"]
+    orc = Oracle(c, n, seed=1)
+    assert orc.terrain().shape == (5 * 80 + 1, 5 * 80 + 1)
+    st = orc.get_state(["terrain_level", "terrain_type", "command"])
+    assert set(np.unique(st["terrain_level"])) == {0, 1, 2, 3, 4} and np.array_equal(st["terrain_type"][:, 0], np.arange(n) // 10)
+    moving = np.abs(st["command"]).sum(axis=1) > 0  # 2 % of the envs stand (rel_standing_envs)
+    assert moving.sum() >= n - 3 and np.allclose(st["command"][moving, 0], 1.0) and np.all(st["command"][:, 1] == 0)
+    lv0 = st["terrain_level"].copy()
+    obs = orc.observe()
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        obs2, rew, term, trunc = orc.step(rng.normal(size=(n, 12)).astype(np.float32))
+    assert term.sum() + trunc.sum() >= 0 and np.isfinite(obs2).all()
+    assert np.array_equal(orc.get_state(["terrain_level"])["terrain_level"], lv0)  # resets happened (random actions), levels did not move
+    # no corruption: two observations of the same state are identical
+    assert np.array_equal(orc.observe()[:, :48], orc.observe()[:, :48])
