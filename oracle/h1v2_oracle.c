@@ -1,6 +1,6 @@
 /*
  * h1v2_oracle.c -- CPU restatement (float64) of the hot path of olivier-stasse/h1v2-Isaac:
- * one ManagerBasedRLEnv.step of Isaac-Velocity-Flat-H12_12dof-v0 with MuJoCo-semantics physics.
+ * one ManagerBasedRLEnv.step of Isaac-Velocity-Flat-H12_12dof-v0 (and its Rsl / Rough siblings) with MuJoCo-semantics physics.
  *
  * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product (h1v2_isaac_b200/) never links or calls it.
@@ -28,6 +28,11 @@
  *   terminations .............. C12/rough_env_cfg.py:95-109 ; T/utils/cat/constraints.py:86-99 (idiom)
  *   commands .................. V/velocity_env_cfg.py:90-104 ; T/utils/mdp/commands.py:47-59
  *   reset events .............. C12/rough_env_cfg.py:78-92 ; V/velocity_env_cfg.py:176-209
+ *   rough terrain (Rough id) .. V/velocity_env_cfg.py:40-68,119-142,270-276 ; T/utils/mdp/terrains.py:11-28 (generator cfg) ;
+ *                               V/mdp/curriculums.py:21-52 (terrain_levels_vel; pinned by tests/golden/terrain_curriculum.npz, produced by
+ *                               the reference's own function) ; upstream isaaclab 2.1.0 terrain generator / height-field mesher /
+ *                               RayCaster / mdp.height_scan [from memory: SURVEY App. B]; the physics of the rough scene has no
+ *                               external target at all (the reference's MuJoCo model is flat)
  *
  * Deliberately written with dense, generic algorithms (13-body tree loops, dense 18x18 Cholesky, explicit
  * constraint-row lists) so that it shares no structure with the CUDA kernel it checks.
