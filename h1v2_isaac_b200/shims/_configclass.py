@@ -58,9 +58,12 @@ def configclass(cls=None, **kwargs):
         user_post_init = cls.__dict__.get("__post_init__")
 
         def __init__(self, **kw):
-            for name, default in _fields_of(type(self)).items():
+            fields = _fields_of(type(self))
+            for name, default in fields.items():
                 object.__setattr__(self, name, copy.deepcopy(default))
             for k, v in kw.items():
+                if k not in fields:  # upstream's configclass is a dataclass: a misspelled field is a TypeError at construction, not a silent attribute
+                    raise TypeError(f"{type(self).__name__}.__init__() got an unexpected keyword argument '{k}'")
                 setattr(self, k, v)
             post = getattr(self, "__post_init__", None)
             if post is not None:

@@ -365,3 +365,24 @@ def test_deploy_config_matches_the_env_yaml_the_reference_ships(tmp_path):
     assert [(o["name"], o.get("scale") or 1) for o in mine["observations"]] == [(o["name"], o.get("scale") or 1) for o in shipped["observations"]]
     assert mine["joints"] == shipped["joints"][:12]
     assert all(not j["enabled"] for j in shipped["joints"][12:])
+
+
+def test_shim_cfg_classes_reject_misspelled_fields():
+    """The shim's configclass is as strict as upstream's dataclass-based one: a misspelled constructor keyword raises instead of becoming a
+    silent attribute that flatten_cfg would never read (round-1 review: lenient placeholders)."""
+    from h1v2_isaac_b200 import shims
+    shims.install()
+    from isaaclab.managers import RewardTermCfg
+    from isaaclab.sensors import RayCasterCfg, patterns
+    from isaaclab.terrains import HfRandomUniformTerrainCfg, TerrainGeneratorCfg
+    with pytest.raises(TypeError, match="wieght"):
+        RewardTermCfg(func=None, wieght=1.0)
+    with pytest.raises(TypeError, match="noise_rnage"):
+        HfRandomUniformTerrainCfg(noise_rnage=(0.0, 0.02), noise_step=0.005)
+    with pytest.raises(TypeError, match="num_row"):
+        TerrainGeneratorCfg(size=(8.0, 8.0), num_row=10, sub_terrains={})
+    with pytest.raises(TypeError, match="resolutoin"):
+        patterns.GridPatternCfg(resolutoin=0.1, size=[1.6, 1.0])
+    ok = RayCasterCfg(prim_path="{ENV_REGEX_NS}/Robot/torso_link", offset=RayCasterCfg.OffsetCfg(pos=(0.0, 0.0, 20.0)), attach_yaw_only=True,
+                      pattern_cfg=patterns.GridPatternCfg(resolution=0.1, size=[1.6, 1.0]), mesh_prim_paths=["/World/ground"])
+    assert ok.offset.pos == (0.0, 0.0, 20.0) and ok.pattern_cfg.ordering == "xy"
