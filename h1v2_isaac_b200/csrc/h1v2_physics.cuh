@@ -47,6 +47,15 @@ namespace h1v2 {
 #ifndef U_EVJ
 #define U_EVJ 1
 #endif
+#ifndef U_EVP
+#define U_EVP 1  // contact-point loops of the Newton trip: evaluate | line search | step (tools/build_variants.sh experiments)
+#endif
+#ifndef U_LSP
+#define U_LSP 1
+#endif
+#ifndef U_STP
+#define U_STP 1
+#endif
 #ifndef H1V2_FINAL_MX
 #define H1V2_FINAL_MX 1  // rhs of the implicit update = M x (1) or f_smooth + J'f re-evaluated (0, round 1)
 #endif
@@ -559,7 +568,7 @@ UNROLL(U_PRO)
       }
       V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
       Wl_f = Wl_s = F_torso = zero3;
-#pragma unroll 1
+UNROLL(U_EVP)
       for (int p = 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
         V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
@@ -785,7 +794,7 @@ UNROLL(U_LSJ)
           const real f = floss_force(r_fma(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss[dk], act);
           d1 = r_fma(-f, sk, d1); d2 = r_fma(act * sk, sk, d2);
         }
-#pragma unroll 1
+UNROLL(U_LSP)
         for (int p = 0; p < nact; p++) {
           const V3 r = sm.pv(p, 0);
           const bool isf = p < n_foot, iss = p < e_shin;
@@ -831,7 +840,7 @@ UNROLL(U_LSJ)
       if (final_trip) wr[i] = rr[i];
     }
     if (move) {
-#pragma unroll 1
+UNROLL(U_STP)
       for (int p = 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
         const bool isf = p < n_foot, iss = p < e_shin;
