@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from test_gpu_parity import PHYS, SYNC, _mk, _np, _resync, _tail_parity
+from test_gpu_parity import PHYS, SYNC, _mk, _np, _randomised, _resync, _tail_parity
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -99,6 +99,45 @@ def test_rough_tail_parity(rough):
     leaves after every reset, plus Curriculum/terrain_levels."""
     stats = _tail_parity(rough, 2048, 40, 20, min_term=0)
     assert stats["level_moves"] > 20
+
+
+def test_rough_tail_parity_with_randomised_events(rough):
+    """BASELINE configs[4] on the height field: interval pushes, per-env friction 0.3..1.25 and +-5 kg of base mass (the Rough cfg itself
+    switches pushes and the mass event off, C12/rough_env_cfg.py:78-79) -- managers, masks and terrain levels as in the nominal case."""
+    stats = _tail_parity(_randomised(rough), 1024, 30, 10, min_term=0)
+    assert stats["level_moves"] > 5
+
+
+def test_rough_bounded_divergence_free_running(rough):
+    """300 free-running control steps of kernel and oracle under the zero action (no re-synchronisation): finite, no force-reset, the two
+    populations stay statistically together (mean reward per step, terrain levels), individual trajectories may separate."""
+    n = 256
+    c = rough.copy()
+    c.enable_corruption = 0
+    torch, sim, orc = _mk(c, n, 9)
+    sim.observe(); orc.observe()
+    a = np.zeros((n, 12), np.float32)
+    at = torch.from_numpy(a).cuda()
+    rg_sum = ro_sum = 0.0
+    dq = []
+    for step in range(300):
+        og, rg, tg, _ = sim.step(at)
+        oo, ro, to, _ = orc.step(a)
+        rg_sum += float(rg.mean()); ro_sum += float(ro.mean())
+        if step in (0, 4, 24):
+            g, o = _np(sim.get_state(["joint_pos"])), orc.get_state(["joint_pos"])
+            dq.append(float(np.median(np.abs(g["joint_pos"] - o["joint_pos"]).max(1))))
+        if step == 0:
+            np.testing.assert_allclose(og.cpu().numpy()[:, 48:], oo[:, 48:], rtol=0, atol=2e-5)  # the scan after one step of both physics
+    assert torch.isfinite(og).all()
+    from h1v2_isaac_b200._capi import LOG_NAN_RESETS
+    assert sim.log_host()[LOG_NAN_RESETS] == 0
+    lg, lo = float(sim.terrain_log_buf[1]), orc.terrain_level_mean()
+    print("median max-joint divergence after 1/5/25 steps:", dq, " mean reward/step gpu", rg_sum / 300, "oracle", ro_sum / 300, " mean terrain level gpu", lg, "oracle", lo)
+    assert dq[0] < 1e-5 and dq[1] < 1e-4
+    assert abs(rg_sum - ro_sum) / 300 < 0.05 * max(abs(ro_sum) / 300, 0.01) + 0.02
+    assert abs(lg - lo) < 0.5
+    sim.close()
 
 
 def test_rough_curriculum_golden_through_both_reset_paths(rough):
