@@ -26,7 +26,8 @@ for n in [int(x) for x in %r.split(',')]:
             e0.record()
             for i in range(100): sim.step_into(acts[i %% 8], obs, rew, term, trunc)
             e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1) / 100)
-        out.append(f"n={n} epw={epw}: {best:.4f} ms ({n / best / 1e3:.1f} M/s) rew {float(rew.mean()):.5f}")
+        lg = sim.log_host()
+        out.append(f"n={n} epw={epw}: {best:.4f} ms ({n / best / 1e3:.1f} M/s) rew {float(rew.mean()):.5f} iters/substep {lg[30] / (4 * n):.3f} max {lg[28]:.0f}")
         sim.close()
 print(' | '.join(out))
 """ % (ROOT, ns, epws)
