@@ -334,6 +334,9 @@ class _GraphRollout:
         base._log_dict()  # builds the key list / gather index of extras["log"]
         self.log_keys, self.log_index = list(base._log_keys), base._log_index
         self.log_sum = torch.zeros(len(self.log_keys), device=dev)
+        # Rough id: Curriculum/terrain_levels (mdp.terrain_levels_vel returns the mean level) comes from the kernel's own two-float log
+        self.terrain_log = self.sim.terrain_log_buf if getattr(base.kernel_cfg, "terrain_curriculum", 0) else None
+        self.terrain_sum = torch.zeros((), device=dev)
         self.graph = None
         self.iterations = 0
 
@@ -349,7 +352,7 @@ class _GraphRollout:
 
     def _body(self):
         st, pol, alg, sim = self.alg.storage, self.alg.policy, self.alg, self.sim
-        self.ep_stats.zero_(); self.log_sum.zero_()
+        self.ep_stats.zero_(); self.log_sum.zero_(); self.terrain_sum.zero_()
         st.obs[0].copy_(self.obs_carry)
         for t in range(self.T):
             obs = st.obs[t]
@@ -372,6 +375,8 @@ class _GraphRollout:
             self.ep_stats[0] += (self.cur_rew * d).sum(); self.ep_stats[1] += (self.cur_len * d).sum(); self.ep_stats[2] += d.sum()
             self.cur_rew *= 1.0 - d; self.cur_len *= 1.0 - d
             self.log_sum += sim.log_buf[self.log_index]
+            if self.terrain_log is not None:
+                self.terrain_sum += self.terrain_log[1]
         st.step = self.T
 
     def run(self, obs):
@@ -406,7 +411,10 @@ class _GraphRollout:
         """(episode statistics [sum_return, sum_length, count], {log key: mean over the steps}) -- the one host read of the rollout."""
         ep = self.ep_stats.tolist()
         lg = (self.log_sum / self.T).tolist()
-        return ep, dict(zip(self.log_keys, lg))
+        out = dict(zip(self.log_keys, lg))
+        if self.terrain_log is not None:
+            out["Curriculum/terrain_levels"] = float(self.terrain_sum) / self.T
+        return ep, out
 
 
 class OnPolicyRunner:
@@ -575,9 +583,10 @@ class OnPolicyRunner:
             for k, v in self.stats.items():
                 if isinstance(v, (int, float)):
                     self.writer.add_scalar(k, v, it)
+        terrain = self.stats.get("episode/Curriculum/terrain_levels")
         print(f"[rsl_rl shim] it {it + 1}/{tot}  steps/s {fps}  collect {collection_time:.3f}s learn {learn_time:.3f}s  "
               f"reward {stats.get('mean_reward', float('nan')):.3f}  len {stats.get('mean_episode_length', float('nan')):.1f}  "
-              f"vloss {loss['value_function']:.4f}  lr {self.alg.lr:.2e}", flush=True)
+              f"vloss {loss['value_function']:.4f}  lr {self.alg.lr:.2e}" + (f"  terrain level {terrain:.2f}" if terrain is not None else ""), flush=True)
 
     def save(self, path: str, infos=None):
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
