@@ -19,10 +19,23 @@ def _act(name: str):
     return {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}[name]()
 
 
+class _AlignedLinear(nn.Linear):
+    """nn.Linear whose matmul sees an input width that is a multiple of 8 on CUDA: same parameters and state_dict as nn.Linear, the
+    input and the weight are zero-padded on the fly (the extra products are exact zeros).  The policy's first layer has 450 inputs
+    (45 x 10 history): with K % 4 != 0 cuBLAS falls back to the unaligned TF32 kernels (cutlass_80 ... align1), which were 22 % of the
+    PPO loop's GPU time at 4096 envs (profiles/r3_ppo_launches_summary.txt); padded to 456 the aligned sm_100 kernels run."""
+
+    def forward(self, x):
+        pad = (-self.in_features) % 8
+        if pad and x.is_cuda:
+            return nn.functional.linear(nn.functional.pad(x, (0, pad)), nn.functional.pad(self.weight, (0, pad)), self.bias)
+        return nn.functional.linear(x, self.weight, self.bias)
+
+
 def _mlp(i, hidden, o, act):
     layers, d = [], i
     for h in hidden:
-        layers += [nn.Linear(d, h), _act(act)]
+        layers += [(_AlignedLinear if d % 8 else nn.Linear)(d, h), _act(act)]
         d = h
     layers.append(nn.Linear(d, o))
     return nn.Sequential(*layers)
