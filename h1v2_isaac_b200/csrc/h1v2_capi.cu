@@ -1049,7 +1049,8 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
   uint8_t* trunc_dev = mapped_alias(truncated);
   // one launch sequence for both flavours: the plain step, or the step + the constraint apply kernel
   // streaming hand-over: possible when every output of the step kernel lands in mapped host memory (pinned buffers, no constraint tail)
-  const bool stream_out = !cat && rew_dev && term_dev && trunc_dev && h->host_mode == 1 && !std::getenv("H1V2_HOST_NO_STREAMING");
+  static const bool no_streaming = std::getenv("H1V2_HOST_NO_STREAMING") != nullptr;  // diagnostics: the round-2 hand-over (synchronise, then the new slots)
+  const bool stream_out = !cat && rew_dev && term_dev && trunc_dev && h->host_mode == 1 && !no_streaming;
   auto launch = [&](float* obs_arg, float* sample_arg, int n_rows) -> int {
     if (cat) return launch_cat(h, act_dev_, obs_arg, h->d_rew, h->d_dones, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg, n_rows);
     return launch_step(h, true, act_dev_, obs_arg, rew_dev ? rew_dev : h->d_rew, term_dev ? term_dev : h->d_term, trunc_dev ? trunc_dev : h->d_trunc, st, sample_arg, false, n_rows,
