@@ -108,10 +108,16 @@ struct H1v2Handle {
 // Every stream-taking entry point notes its stream: h1v2_step_host runs on a private non-blocking stream and orders itself
 // after that work at entry (a C caller may do h1v2_reset(h, ids, n, NULL) and then h1v2_step_host).
 static inline void note_stream(H1v2Handle* h, cudaStream_t st) { h->last_stream = st; h->last_stream_set = true; }
-// ... and the other way round: a host step in streaming mode returns when all its outputs are in the caller's memory, while the last
-// block's bookkeeping may still be running on the private stream; work queued on another stream afterwards waits for it.
+// ... and the other way round: a host step in streaming mode returns when all its outputs are in the caller's memory and the last block
+// has published the launch's bookkeeping; what is left on the private stream is the kernel's exit.  Work queued on another stream
+// afterwards waits for the event recorded behind that launch.  The caller's stream may be capturing a CUDA graph: there the wait
+// has to be an external-event node (cudaEventWaitExternal) -- a plain wait on an event recorded outside the capture, or any host-side
+// synchronisation, invalidates the capture.
 static inline void order_after_host(H1v2Handle* h, cudaStream_t st) {
-  if (h->host_pending && st != h->host_stream) cudaStreamWaitEvent(st, h->host_ev, 0);
+  if (!h->host_pending || st == h->host_stream) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  cudaStreamWaitEvent(st, h->host_ev, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault);
 }
 
 // ------------------------------------------------------------------------------------------------------

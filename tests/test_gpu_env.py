@@ -114,7 +114,8 @@ def test_graph_rollout_equals_the_eager_rollout(tmp_path, monkeypatch):
     graph path runs its body eagerly there), and the replayed graph keeps stepping the same env (step counter, episode lengths,
     statistics), with finite losses."""
     import torch
-    from h1v2_isaac_b200 import tasks
+    from h1v2_isaac_b200 import shims, tasks
+    shims.install()  # (also when this test runs on its own)
     from isaaclab_rl.rsl_rl import RslRlVecEnvWrapper
     from rsl_rl.runners import OnPolicyRunner
     agent = tasks.default_agent_cfg()
@@ -398,6 +399,41 @@ def test_step_is_cuda_graph_capturable(cfg):
         graph.replay()
         ob, rb, tb, ub = b.step(acts[k])
         assert torch.equal(obs, ob) and torch.equal(rew, rb) and torch.equal(term.bool(), tb) and torch.equal(trunc.bool(), ub), k
+    a.close(); b.close()
+
+
+def test_graph_capture_right_after_a_streaming_host_step(cfg, monkeypatch):
+    """A host-buffer step in streaming mode (per-warp flags, no stream synchronise on the way out) followed at once by the capture of a
+    device-path step on another stream: the capture must not see an external event wait, and the replays continue the same trajectory."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    monkeypatch.setenv("H1V2_HOST_PATH", "assemble")
+    n = 1024
+    a, b = H1v2Sim(n, cfg, device="cuda:0", seed=21), H1v2Sim(n, cfg, device="cuda:0", seed=21)
+    a.observe(); b.observe()
+    hobs = torch.empty((n, a.obs_dim)).pin_memory(); hrew = torch.empty(n).pin_memory()
+    ht = torch.empty(n, dtype=torch.uint8).pin_memory(); hu = torch.empty(n, dtype=torch.uint8).pin_memory()
+    obs = torch.empty((n, a.obs_dim), device="cuda"); rew = torch.empty(n, device="cuda")
+    term = torch.empty(n, dtype=torch.uint8, device="cuda"); trunc = torch.empty(n, dtype=torch.uint8, device="cuda")
+    act = torch.zeros((n, 12), device="cuda")
+    a.step_into(a.random_actions(0), obs, rew, term, trunc); b.step(b.random_actions(0))  # sets the kernel attributes outside capture
+    for i in range(1, 4):
+        x = a.random_actions(i)
+        a.step_host(x.cpu().pin_memory(), hobs, hrew, ht, hu)
+        ob, rb, tb, ub = b.step(x)
+        assert torch.equal(ob.cpu(), hobs)
+    assert a.host_path_info()[0] == 1
+    graph, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            a.step_into(act, obs, rew, term, trunc)
+    torch.cuda.current_stream().wait_stream(s)
+    for i in range(4, 8):
+        act.copy_(a.random_actions(i))
+        graph.replay()
+        ob, rb, tb, ub = b.step(act)
+        assert torch.equal(obs, ob) and torch.equal(rew, rb) and torch.equal(term.bool(), tb), i
     a.close(); b.close()
 
 
