@@ -210,6 +210,32 @@ def test_rough_full_size_properties(rough, n):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n", [1, 17, 33])
+def test_rough_tiny_and_ragged_env_counts(rough, n):
+    """One env, and env counts that leave a warp partly empty under every envs-per-warp mapping: levels / types, the reset observation,
+    and ten injected-state steps (observation incl. the scan, reward, masks, levels) against the oracle; guard zones intact."""
+    torch, sim, orc = _mk(rough, n, 31)
+    names = SYNC + ["terrain_type"]
+    g, o = _np(sim.get_state(names)), orc.get_state(names)
+    assert np.array_equal(g["terrain_level"], o["terrain_level"]) and np.array_equal(g["terrain_type"], o["terrain_type"])
+    np.testing.assert_allclose(sim.observe().cpu().numpy(), orc.observe(), rtol=0, atol=3e-6)
+    rng = np.random.default_rng(n)
+    from test_gpu_parity import POST
+    for step in range(10):
+        a = rng.normal(size=(n, 12)).astype(np.float32)
+        og, rg, tg, ug = sim.step(torch.from_numpy(a).cuda())
+        g = _np(sim.get_state(SYNC + POST))
+        oo, ro, to, uo = orc.step_injected(a, {k: v for k, v in g.items() if k != "foot_vel"})
+        o = orc.get_state(SYNC)
+        assert np.array_equal(tg.cpu().numpy(), to) and np.array_equal(ug.cpu().numpy(), uo)
+        assert np.array_equal(g["terrain_level"], o["terrain_level"])
+        np.testing.assert_allclose(og.cpu().numpy(), oo, rtol=1e-5, atol=2e-6, err_msg=f"observation, step {step}")
+        np.testing.assert_allclose(rg.cpu().numpy(), ro, rtol=1e-5, atol=1e-6)
+        _resync(sim, orc, g)
+    assert sim.check_guards() == 0
+    sim.close()
+
+
 def test_rough_gym_env_and_ppo(rough):
     """gym.make("Isaac-Velocity-Rough-H12_12dof-v0") on the self-contained cfg tree: 235-dim observation, the reference's log keys incl.
     Curriculum/terrain_levels, and two PPO iterations of the runner shim on it."""
