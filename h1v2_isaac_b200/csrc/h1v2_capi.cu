@@ -1292,6 +1292,12 @@ int h1v2_get_log(H1v2Handle* h, const float** log_dev) {
   *log_dev = h->S.log;
   return 0;
 }
+#ifdef H1V2_WARPCLOCK
+// diagnostic variant only (not declared in the header, not in the product library): tools/diag_warpclock.py
+extern "C" int h1v2_debug_warpclock(unsigned long long* out, int nwarps) {
+  return cudaMemcpyFromSymbol(out, h1v2::g_warpclock, sizeof(unsigned long long) * 4 * (size_t)nwarps) == cudaSuccess ? 0 : -1;
+}
+#endif
 int h1v2_debug_iter_hist(H1v2Handle* h, float* hist32) {
   if (!h || !hist32) return fail("h1v2_debug_iter_hist: bad arguments");
   DeviceGuard guard(h->device);

@@ -276,6 +276,9 @@ struct SubOut {
   V3 F_foot, F_shin, F_torso, F_pelvis;  // net contact forces (torso/pelvis pair-summed, valid on both lanes)
   real qacc[6];                         // joint accelerations of this leg after the implicit update
   int iters, capped, overflow;
+#ifdef H1V2_WARPCLOCK
+  int trips, lstrips;  // diagnostic variant only (tools/diag_warpclock.py): warp-synchronous trips of the Newton loop / line search
+#endif
 };
 
 // root-joint-space projection helpers.  Root dofs seen from reference point O_s = O_r + d:
@@ -550,8 +553,14 @@ UNROLL(U_PRO)
   // trip and is MODE_DONE afterwards; done lanes keep running on frozen state (all their writes are selects).
   enum { MODE_NEWTON = 1, MODE_FINAL = 2, MODE_DONE = 3 };
   int mode = MODE_NEWTON;
+#ifdef H1V2_WARPCLOCK
+  out.trips = 0; out.lstrips = 0;
+#endif
 #pragma unroll 1
   for (int trip = 0;; trip++) {
+#ifdef H1V2_WARPCLOCK
+    out.trips++;
+#endif
     const bool first = trip == 0;
     real dg_own[3] = {0.f, 0.f, 0.f};  // extra Hessian diagonal of this lane's three root rows
     bool final_trip = false;            // this trip's solve is the lane's implicitfast update
@@ -772,6 +781,9 @@ UNROLL(U_MPROD)
       if (search) alpha = 1.f;
 #pragma unroll 1
       for (int ls = 0; __any_sync(FULL_MASK, search); ls++) {
+#ifdef H1V2_WARPCLOCK
+        out.lstrips++;
+#endif
         real d1 = 0.f, d2 = 0.f;
 UNROLL(U_LSJ)
         for (int j = 0; j < 6; j++) {

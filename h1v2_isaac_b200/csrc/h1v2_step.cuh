@@ -544,6 +544,10 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, boo
 
 // CAT: the Constraints-as-Terminations flavour (h1v2_cat_step) is its own instantiation, so the plain step carries none of its code
 // ROUGH: the Rough id's flavour (height-field contacts, base_lin_vel, height scan, terrain-level curriculum), its own instantiation too
+#ifdef H1V2_WARPCLOCK
+// diagnostic variant only: per warp {globaltimer at entry, clock64 cycles of the physics loop, of the whole kernel, trips | lstrips << 32}
+__device__ unsigned long long g_warpclock[4 * 16384];
+#endif
 template <bool DO_STEP, bool CAT = false, bool ROUGH = false>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
@@ -555,6 +559,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
   // lane pair p of warp w owns env w*epw + p for p < epw; the remaining lanes shadow the warp's first env (their work is
   // bit-identical to it, so they never lengthen the warp's Newton loop) and store nothing
+#ifdef H1V2_WARPCLOCK
+  unsigned long long wc_g0, wc_c1 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wc_g0));
+  const long long wc_c0 = clock64();
+  int wc_trips = 0, wc_ls = 0;
+#endif
   const int side = tid & 1;
   const int slot = (int)(tid >> 1);
   const int warp_env0 = (int)bid * P.epw;
@@ -656,6 +666,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
       substep<ROUGH>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
       use_warm = true;
+#ifdef H1V2_WARPCLOCK
+      wc_trips += so.trips; wc_ls += so.lstrips;
+#endif
       max_it = max(max_it, so.iters); ncap += so.capped; sum_it += so.iters; novf += so.overflow;
       if (S.diag && valid && side == 0) atomicAdd(S.acc + H1V2_LOG_DIM + min(so.iters, 31), 1.f);  // iteration histogram: diagnostics handles only
       s_acc = 0.f;
@@ -682,6 +695,9 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
       }
     }
   }
+#ifdef H1V2_WARPCLOCK
+  wc_c1 = clock64() - wc_c0;
+#endif
   V3 fv = mk3(0.f, 0.f, 0.f);
   real ankle_z = 0.f;
   if (DO_STEP) {
@@ -1030,6 +1046,12 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
     S.warm[N2 + lidx] = make_float4(wl[4], wl[5], wr[0], wr[1]);
     S.warm[2 * N2 + lidx] = make_float4(wr[2], wr[3], wr[4], wr[5]);
   }
+#ifdef H1V2_WARPCLOCK
+  if (DO_STEP && tid == 0 && bid < 16384) {
+    g_warpclock[4 * bid] = wc_g0; g_warpclock[4 * bid + 1] = wc_c1; g_warpclock[4 * bid + 2] = clock64() - wc_c0;
+    g_warpclock[4 * bid + 3] = (unsigned long long)wc_trips | ((unsigned long long)wc_ls << 32);
+  }
+#endif
   // ---- the last block to get here finalizes the step ----
   __threadfence();
   unsigned ticket = 0;
