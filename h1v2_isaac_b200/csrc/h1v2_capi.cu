@@ -67,6 +67,7 @@ struct H1v2Handle {
   uint64_t seed = 0;
   int64_t launches = 0;
   bool attr_set = false;
+  bool no_quad = false;             // cfg.reserved[3] != 0: 8-env warps run the plain instantiation (A/B switch of the mirror-lane split)
   std::vector<void*> allocs;       // base pointers (guard zone first)
   std::vector<size_t> alloc_bytes;  // payload bytes between the guard zones
   int64_t* own_ep_len = nullptr;
@@ -743,6 +744,7 @@ int h1v2_create(const H1v2Config* cfg, int32_t n_envs, int32_t device, uint64_t 
   H1v2Handle* h = new H1v2Handle();
   h->cfg = *cfg; h->n = n_envs; h->device = device; h->seed = seed;
   if (build_params(*cfg, n_envs, seed, h->P) != 0) { delete h; return -1; }
+  h->no_quad = cfg->reserved[3] != 0;
   const size_t N = (size_t)n_envs;
   KState& S = h->S;
   int rc = 0;
@@ -919,6 +921,8 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
   if (h->rough && do_step)
@@ -927,6 +931,8 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     step_kernel<false, false, true><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
   else if (do_step && cat)
     step_kernel<true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (do_step && h->P.epw == 8 && !h->no_quad)
+    step_kernel<true, false, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else  // the observe-only launch stages the history rings in the same shared-memory window

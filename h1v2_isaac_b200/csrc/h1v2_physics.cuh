@@ -117,6 +117,12 @@ typedef SmemT<PSTRIDE> Smem;
 #define FULL_MASK 0xffffffffu
 __device__ __forceinline__ real pair_sum(real v) { return v + __shfl_xor_sync(FULL_MASK, v, 1); }
 __device__ __forceinline__ V3 pair_sum(V3 v) { return mk3(pair_sum(v.x), pair_sum(v.y), pair_sum(v.z)); }
+// QUAD instantiation (8 envs per warp): lanes 16..31 mirror lanes 0..15 bit for bit (same env, same leg, same shared-memory
+// column) instead of idling, and the loops whose iterations are independent -- the rows and contact points of the line
+// search -- are dealt to the two mirrors by parity; this sum over the mirror pair closes them.  Addition commutes, so both
+// mirrors hold the same bits afterwards and stay mirrors.
+template <bool QUAD>
+__device__ __forceinline__ real mirror_sum(real v) { return QUAD ? v + __shfl_xor_sync(FULL_MASK, v, 16) : v; }
 
 // MuJoCo getimpedance (solimp = d0, dmax, width, midpoint, power), margin 0
 __device__ __forceinline__ real impedance(const float* si, real pos) {
@@ -366,13 +372,15 @@ __device__ __forceinline__ real impedance_call(const float* si, real pos) {
 // ----------------------------------------------------------------------------------------------------------
 // ROUGH: contacts against the height field of the Rough id (terrain height and triangle normal under every candidate, residuals
 // held in the contact frame) -- its own instantiation, the plane kernel carries none of that code.
-template <bool ROUGH>
+template <bool ROUGH, bool QUAD>
 __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, real (&rp)[3],
                                      real (&rq)[4], real (&rv)[3], real (&rw)[3], real (&q)[6], real (&qd)[6],
                                      const real (&tau)[6], const real mu, const real mass_add, real (&wl)[6], real (&wr)[6],
                                      const bool use_warm, SubOut& out, const float* __restrict__ terrain_h, const TerrainEnv& te) {
   extern __shared__ __align__(16) real smem_raw[];
-  const SmemT<ROUGH ? PSTRIDE_ROUGH : PSTRIDE> sm{smem_raw + tid};
+  const SmemT<ROUGH ? PSTRIDE_ROUGH : PSTRIDE> sm{smem_raw + (QUAD ? (tid & 15u) : tid)};
+  const int q0 = QUAD ? (int)(tid >> 4) : 0;  // first iteration of a dealt loop; its stride is QS
+  constexpr int QS = QUAD ? 2 : 1;
   const KLeg& LG = P.leg[side];
   const real h = P.h;
   const int j0 = 6 * side;
@@ -577,8 +585,19 @@ UNROLL(U_PRO)
       }
       V3 Wn_f = zero3, Wn_s = zero3, Wn_r = zero3, Wl_r = zero3;
       Wl_f = Wl_s = F_torso = zero3;
+      if (QUAD) {  // the sole points (the common case) dealt to the mirrors; shin / torso / pelvis points below by both
+#pragma unroll 1
+        for (int p = q0; p < n_foot; p += 2) {
+          const V3 r = sm.pv(p, 0);
+          V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
+          if (ROUGH) Fp = from_contact(cframe(sm.pv(p, 8)), Fp);
+          Wn_f = Wn_f + cross(r, Fp); Wl_f = Wl_f + Fp;
+        }
+        Wn_f = mk3(mirror_sum<QUAD>(Wn_f.x), mirror_sum<QUAD>(Wn_f.y), mirror_sum<QUAD>(Wn_f.z));
+        Wl_f = mk3(mirror_sum<QUAD>(Wl_f.x), mirror_sum<QUAD>(Wl_f.y), mirror_sum<QUAD>(Wl_f.z));
+      }
 UNROLL(U_EVP)
-      for (int p = 0; p < nact; p++) {
+      for (int p = (QUAD) ? n_foot : 0; p < nact; p++) {
         const V3 r = sm.pv(p, 0);
         V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
         if (ROUGH) Fp = from_contact(cframe(sm.pv(p, 8)), Fp);  // contact frame -> world
@@ -603,7 +622,7 @@ UNROLL(U_EVP)
       }
       real gn2 = 0.f, gv = 0.f;
 UNROLL(U_EVJ)
-      for (int j = 0; j < 6; j++) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
+      for (int j = q0; j < 6; j += QS) {  // joint rows (friction loss, limit) + J'f of the contacts: gradient g - (M x - f)
         const real x = sm.jf(j, F_XQ);
         real act;
         real f = floss_force(x + sm.jf(j, F_FLC), flD[j], flF[j], act);
@@ -619,10 +638,12 @@ UNROLL(U_EVJ)
         gn2 = r_fma(r, r, gn2);
         gv = r_max(gv, r_abs(r) * P.limit_invw[j0 + j]);  // ~ |(M^-1 grad)_j|: what this residual does to the joint's acceleration
       }
+      if (QUAD) __syncwarp();  // the mirror's joints are in the shared column
       F_torso = pair_sum(F_torso);
       F_pelvis = pair_sum(F_pelvis);
-      gn2 = pair_sum(gn2);
+      gn2 = mirror_sum<QUAD>(pair_sum(gn2));
       gv = r_max(gv, __shfl_xor_sync(FULL_MASK, gv, 1));
+      if (QUAD) gv = r_max(gv, __shfl_xor_sync(FULL_MASK, gv, 16));
 #pragma unroll
       for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k]); rr[k] = jr[k] - Mar[k]; gn2 = r_fma(rr[k], rr[k], gn2); }
       if (mode == MODE_NEWTON) {
@@ -786,7 +807,7 @@ UNROLL(U_MPROD)
 #endif
         real d1 = 0.f, d2 = 0.f;
 UNROLL(U_LSJ)
-        for (int j = 0; j < 6; j++) {
+        for (int j = q0; j < 6; j += QS) {
           const real s = sm.jf(j, F_R);
           const real xa = r_fma(alpha, s, sm.jf(j, F_XQ));
           real act;
@@ -798,6 +819,7 @@ UNROLL(U_LSJ)
           const real lw = jar < 0.f ? r_abs(lD) : 0.f;
           d1 = r_fma(lw * jar, sig * s, d1); d2 = r_fma(lw * s, s, d2);
         }
+        if (!QUAD || q0 == 0) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           const int dk = 3 * side + k;
@@ -806,8 +828,9 @@ UNROLL(U_LSJ)
           const real f = floss_force(r_fma(alpha, sk, xk) + rfl_c[k], P.floss_D[dk], P.floss[dk], act);
           d1 = r_fma(-f, sk, d1); d2 = r_fma(act * sk, sk, d2);
         }
+        }
 UNROLL(U_LSP)
-        for (int p = 0; p < nact; p++) {
+        for (int p = q0; p < nact; p += QS) {
           const V3 r = sm.pv(p, 0);
           const bool isf = p < n_foot, iss = p < e_shin;
           const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
@@ -815,8 +838,8 @@ UNROLL(U_LSP)
           if (ROUGH) us = to_contact(cframe(sm.pv(p, 8)), us);
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
-        d1 = pair_sum(d1) + r_fma(alpha, sMs, sMa);
-        d2 = pair_sum(d2) + sMs;
+        d1 = mirror_sum<QUAD>(pair_sum(d1)) + r_fma(alpha, sMs, sMa);
+        d2 = mirror_sum<QUAD>(pair_sum(d2)) + sMs;
         if (search) {
           if (r_abs(d1) <= P.ls_tol * r_abs(d10) || !(d2 > 0.f)) search = false;
           else {
@@ -838,7 +861,7 @@ UNROLL(U_LSP)
     //      A lane that just took its implicit update keeps the result: qacc -> F_FS, root part -> wr. ----
     const bool move = alpha != 0.f;
 #pragma unroll 1
-    for (int j = 0; j < 6; j++) {
+    for (int j = q0; j < 6; j += QS) {
       const real s = sm.jf(j, F_R);
       if (move) {
         sm.jf(j, F_XQ) = r_fma(alpha, s, sm.jf(j, F_XQ));
@@ -853,7 +876,7 @@ UNROLL(U_LSP)
     }
     if (move) {
 UNROLL(U_STP)
-      for (int p = 0; p < nact; p++) {
+      for (int p = q0; p < nact; p += QS) {
         const V3 r = sm.pv(p, 0);
         const bool isf = p < n_foot, iss = p < e_shin;
         const V3 Sa = isf ? Sa_f : (iss ? Sa_s : Sa_r), Sl = isf ? Sl_f : (iss ? Sl_s : Sl_r);
@@ -864,6 +887,7 @@ UNROLL(U_STP)
       }
     }
     if (final_trip) mode = MODE_DONE;
+    if (QUAD) __syncwarp();  // both mirrors' halves of the step are in the shared column
     if (__all_sync(FULL_MASK, mode == MODE_DONE)) break;
   }
   // ---- integrate (semi-implicit Euler; quaternion on SO(3) with the body-frame angular velocity) ----

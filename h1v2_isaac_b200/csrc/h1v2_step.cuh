@@ -548,7 +548,9 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, boo
 // diagnostic variant only: per warp {globaltimer at entry, clock64 cycles of the physics loop, of the whole kernel, trips | lstrips << 32}
 __device__ unsigned long long g_warpclock[4 * 16384];
 #endif
-template <bool DO_STEP, bool CAT = false, bool ROUGH = false>
+// QUAD: the instantiation for 8 envs per warp (2049..4144 envs on a B200, BASELINE configs[1]): lanes 16..31 mirror lanes 0..15
+// instead of shadowing the warp's first env, and share the independent loops of the Newton trip with them (h1v2_physics.cuh)
+template <bool DO_STEP, bool CAT = false, bool ROUGH = false, bool QUAD = false>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
@@ -566,10 +568,11 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   int wc_trips = 0, wc_ls = 0;
 #endif
   const int side = tid & 1;
-  const int slot = (int)(tid >> 1);
+  const int slot = QUAD ? (int)((tid >> 1) & 7u) : (int)(tid >> 1);
   const int warp_env0 = (int)bid * P.epw;
-  const bool valid = slot < P.epw && warp_env0 + slot < P.n;
-  const int env = valid ? warp_env0 + slot : min(warp_env0, P.n - 1);
+  const bool in_range = (QUAD || slot < P.epw) && warp_env0 + slot < P.n;
+  const bool valid = in_range && (!QUAD || tid < 16u);  // a mirror lane computes everything and stores nothing
+  const int env = in_range ? warp_env0 + slot : min(warp_env0, P.n - 1);
   const int lidx = 2 * env + side;
   const int N = P.n, N2 = 2 * P.n;
   const int64_t gid = P.env_id_offset + env;
@@ -664,7 +667,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           cat_max_publish(CM, S.cat.cmax);
         }
       }
-      substep<ROUGH>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
+      substep<ROUGH, QUAD>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
       use_warm = true;
 #ifdef H1V2_WARPCLOCK
       wc_trips += so.trips; wc_ls += so.lstrips;

@@ -240,7 +240,8 @@ typedef struct H1v2Config {
   float noise_height_scan, scale_height_scan, scan_clip[2]; /* 0.1, 1, (-1, 1): noise, then clip, then scale (ObservationManager order) */
   int32_t reserved[7];                 /* [0] != 0: keep per-env diagnostics of the last step (get_state's read-only fields);
                                           [1] > 0: line-search evaluations per Newton iteration (default 6);
-                                          [2] in {1,2,4,8,16}: envs per warp (default: chosen from n_envs); rest 0 */
+                                          [2] in {1,2,4,8,16}: envs per warp (default: chosen from n_envs);
+                                          [3] != 0: 8-env warps run the plain instantiation instead of the mirror-lane one; rest 0 */
 } H1v2Config;
 
 /* Natural-layout state exchange (row-major, env-major).  NULL members are skipped.

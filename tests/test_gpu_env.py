@@ -165,6 +165,39 @@ def test_rank_shards_are_slices_of_one_job(cfg):
     whole.close(); shard.close()
 
 
+def test_mirror_lane_instantiation_is_deterministic_and_agrees_to_rounding(cfg):
+    """8 envs per warp (2073..4144 envs on a B200) run the mirror-lane instantiation: lanes 16..31 hold the same env, leg and
+    shared-memory column as lanes 0..15 and take every other iteration of the independent loops of the Newton trip, so the row
+    sums are associated differently from the plain kernel's.  It must be deterministic (two handles: bit-identical), must not
+    depend on where an env sits in its warp, and one control step from the same state differs from the plain kernel's by
+    rounding only (the oracle parity of this instantiation: tests/test_gpu_parity.py, epw = 8 cases)."""
+    import torch
+    from h1v2_isaac_b200.backend import H1v2Sim
+    n = 203
+    cq = cfg.copy(); cq.reserved[2] = 8
+    cp = cfg.copy(); cp.reserved[2] = 8; cp.reserved[3] = 1
+    q1, q2, pl = H1v2Sim(n, cq, device="cuda:0", seed=9), H1v2Sim(n, cq, device="cuda:0", seed=9), H1v2Sim(n, cp, device="cuda:0", seed=9)
+    cs = cq.copy(); cs.env_id_offset = 3
+    shifted = H1v2Sim(n - 3, cs, device="cuda:0", seed=9)  # the global envs 3..n-1 at other lane positions
+    assert torch.equal(q1.observe(), pl.observe()) and torch.equal(q1.observe(), q2.observe())
+    assert torch.equal(q1.observe()[3:], shifted.observe())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for it in range(12):
+        a = torch.randn((n, 12), device="cuda", generator=g)
+        o1, o2 = q1.step(a), q2.step(a)
+        for x, y in zip(o1, o2):
+            assert torch.equal(x, y)
+        for x, y in zip(o1, shifted.step(a[3:].contiguous())):
+            assert torch.equal(x[3:], y)
+        if it == 0:
+            op = pl.step(a)
+            assert float((o1[0] - op[0]).abs().max()) < 1e-4 and float((o1[1] - op[1]).abs().max()) < 1e-5
+            assert torch.equal(o1[2], op[2]) and torch.equal(o1[3], op[3])
+    assert q1.check_guards() == 0
+    for s_ in (q1, q2, pl, shifted):
+        s_.close()
+
+
 def test_envs_per_warp_mapping_is_bit_identical(cfg):
     """The small-N mapping (fewer envs per warp, spare lanes shadowing the warp's first env) must not change a single bit
     of any env's trajectory: same arithmetic per env, only the grouping into warps differs."""
@@ -174,6 +207,7 @@ def test_envs_per_warp_mapping_is_bit_identical(cfg):
     sims = []
     for epw in (16, 8, 4, 1):
         c = cfg.copy(); c.reserved[2] = epw
+        c.reserved[3] = 1  # 8 per warp: the plain instantiation (the mirror-lane one sums in another order: next test)
         sims.append(H1v2Sim(n, c, device="cuda:0", seed=9))
     obs0 = [s.observe() for s in sims]
     for o in obs0[1:]:
