@@ -913,6 +913,8 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute((step_kernel<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
   if (!h->attr_set) {  // function attributes are per device: keep the flag with the handle, not with the process
@@ -923,15 +925,22 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
-  if (h->rough && do_step)
+  const bool quad = h->P.epw == 8 && !h->no_quad;  // 8 envs per warp: the mirror-lane instantiations
+  if (h->rough && do_step && quad)
+    step_kernel<true, false, true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (h->rough && do_step)
     step_kernel<true, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (h->rough)
     step_kernel<false, false, true><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
+  else if (do_step && cat && quad)
+    step_kernel<true, true, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step && cat)
     step_kernel<true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
-  else if (do_step && h->P.epw == 8 && !h->no_quad)
+  else if (do_step && quad)
     step_kernel<true, false, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);

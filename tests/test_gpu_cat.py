@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 ILLEGAL, FEET = [2, 3, 4, 5], [0, 1]
 
 
-def test_cat_tail_matches_the_pinned_oracle():
+@pytest.mark.parametrize("epw", [0, 8])  # 8: the mirror-lane instantiation of the CaT step (8 envs per warp, what 4096 envs run)
+def test_cat_tail_matches_the_pinned_oracle(epw):
     import torch
     from h1v2_isaac_b200._capi import CSTR_COL0, CSTR_NAMES, rsl_config
     from h1v2_isaac_b200.backend import H1v2Sim
@@ -17,6 +18,7 @@ def test_cat_tail_matches_the_pinned_oracle():
     c = rsl_config()
     c.cat_enable = 1
     c.velocity_deadzone = 0.2  # the CaT cfg's command dead zone (cat_env_cfg.py:48,114)
+    c.reserved[2] = epw
     n = 1024
     cat, twin = H1v2Sim(n, c, device="cuda:0", seed=21), H1v2Sim(n, c, device="cuda:0", seed=21, diagnostics=True)
     cat.observe(); twin.observe()

@@ -46,14 +46,15 @@ def test_rough_terrain_levels_and_reset_state_match_oracle(rough):
     sim.close()
 
 
-@pytest.mark.parametrize("decimation,rough_cm", [(1, 2), (1, 8), (4, 2)])
-def test_rough_physics_parity_from_identical_states(rough, decimation, rough_cm):
+@pytest.mark.parametrize("decimation,rough_cm,epw", [(1, 2, 0), (1, 8, 0), (4, 2, 0), (1, 8, 8)])  # epw 8: the mirror-lane instantiation
+def test_rough_physics_parity_from_identical_states(rough, decimation, rough_cm, epw):
     """North star (c) on the height field, asserted literally for one physics step: positions within 1e-4 rad / m and velocities within
     1e-3 rad/s (m/s) on every kept env-step.  rough_cm = 2 is the reference's generator cfg (0 .. 2 cm); 8 makes the slopes four times
     as steep (up to 39 degrees), so that the contact frames matter.  Skipped and counted, as on the plane: envs within 2e-6 of a
     contact / limit activation boundary, and here also envs with a contact candidate within 1e-4 cells (10 um) of a triangle edge of the
     height field (the normal jumps there; float vs double rounding of the position decides the triangle)."""
     c = rough.copy()
+    c.reserved[2] = epw
     c.decimation = decimation
     c.max_delay = min(c.max_delay, 2 * decimation)
     n = 2048
