@@ -318,7 +318,7 @@ def run_ours(args):
             env = gym.make(TASKS["flat"], cfg=tasks.default_env_cfg(n_envs, device=f"cuda:{local}"))
             agent = tasks.default_agent_cfg()
             runner = OnPolicyRunner(RslRlVecEnvWrapper(env), agent.to_dict(), log_dir=tempfile.mkdtemp(prefix="h1v2_bench_ppo_"), device=f"cuda:{local}")
-            runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)  # warm-up: eager body + graph capture
+            runner.learn(num_learning_iterations=3, init_at_random_ep_len=True)  # warm-up: eager body, graph capture, first plain replay (uploads the graphs)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
