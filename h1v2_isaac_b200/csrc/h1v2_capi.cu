@@ -488,6 +488,9 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int epw = 1;
     while (epw < 16 && 2 * ((n + epw - 1) / epw) > 7 * sms) epw *= 2;
+    // 8 per warp runs the mirror-lane instantiation (10 % cheaper trips): it stays ahead of 16 per warp up to ~4.75 warps per SM
+    // (profiles/r4_notes.md: 5120 envs 0.2255 vs 0.2357 ms, 6144 envs 0.2389 vs 0.2379)
+    if (epw == 16 && 4 * ((n + 7) / 8) <= 19 * sms && c.reserved[3] == 0) epw = 8;
     if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) epw = c.reserved[2];
     P.epw = epw;
   }

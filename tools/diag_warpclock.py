@@ -12,7 +12,7 @@ from h1v2_isaac_b200._capi import default_config
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 lib = _capi.load_library()
 lib.h1v2_debug_warpclock.argtypes = [C.c_void_p, C.c_int]
-for name, cap, epw in (("cap12", 12, 0), ("cap6", 6, 0), ("cap4", 4, 0), ("cap12 epw16", 12, 16)):
+for name, cap, epw in (("cap12", 12, 0), ("cap6", 6, 0)):
     cfg = default_config(); cfg.solver_iterations = cap; cfg.reserved[2] = epw
     sim = H1v2Sim(n, cfg, seed=1); sim.observe()
     acts = [sim.random_actions(i) for i in range(8)]
