@@ -419,6 +419,9 @@ def test_step_host_matches_device_path(cfg, pinned, mode, monkeypatch):
     else:
         monkeypatch.setenv("H1V2_HOST_PATH", mode)
     n = 1024
+    cfg = cfg.copy()
+    if mode in ("assemble", "hybrid"):  # 8 envs per warp = the mirror-lane instantiation 4096 envs run (lanes 16..31 store nothing, raise no flag twice)
+        cfg.reserved[2] = 8
     s1, s2 = H1v2Sim(n, cfg, seed=4), H1v2Sim(n, cfg, seed=4)
     s1.observe(); s2.observe()
     pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)

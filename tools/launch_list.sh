@@ -17,7 +17,7 @@ for r in rows[1:]:
 tot = sum(v for _, v in agg.values())
 with open(f"gpurun_out/{tag}_launches_summary.txt", "w") as f:
     f.write(f"# ncu launch list of `{cmd}` (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)\n")
-    f.write("# kernel | launches | total us | share   (fma_peak_kernel = the FP32-peak micro-benchmark, outside every timed region; one step = ONE step_kernel<1,0> launch; CaT: step_kernel<1,1> + cat_apply_kernel)\n")
+    f.write("# kernel | launches | total us | share   (fma_peak_kernel = the FP32-peak micro-benchmark, outside every timed region; one step = ONE step_kernel<1,0,0,Q> launch, Q = 1: the mirror-lane instantiation of 8 envs per warp; CaT: step_kernel<1,1,0,Q> + cat_apply_kernel)\n")
     for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k} | {n} | {v:.1f} | {100 * v / tot:.1f}%\n")
 print(open(f"gpurun_out/{tag}_launches_summary.txt").read())
