@@ -295,11 +295,13 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
     return stats
 
 
-def test_bounded_divergence_over_1000_steps(cfg):
+@pytest.mark.parametrize("epw", [0, 8])  # 8: the mirror-lane instantiation
+def test_bounded_divergence_over_1000_steps(cfg, epw):
     """(c) free-running: 1000 control steps of both implementations under a stabilising (zero) action stay statistically
     together and finite; individual trajectories are allowed to separate (contact dynamics are chaotic)."""
     n = 256
     c = cfg.copy()
+    c.reserved[2] = epw
     c.enable_corruption = 0
     torch, sim, orc = _mk(c, n, 9)
     sim.observe(); orc.observe()
