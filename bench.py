@@ -344,7 +344,9 @@ def run_ours(args):
                    "policy": "random-init ActorCritic [512, 256, 128] ELU, fp32 parameters, TF32 matmul allowed (scripts/rsl_rl/train.py:70-73)", "mean_episode_length": runner.stats.get("mean_episode_length"),
                    "collectives_per_iteration": (f"NCCL x{world}: 20 gradient all-reduces of {sum(p.numel() for p in runner.alg.policy.parameters())} parameters, 20 KL all-reduces, 2 rollout-statistics all-reduces" if world > 1 else "none (1 GPU)"),
                    "timer": "host wall clock around OnPolicyRunner.learn, synchronised, max over ranks"}
+            runner.release_graphs()  # captured graphs (with NCCL work inside when H1V2_GRAPH_LEARNER=1) go before the process group does
             env.close()
+            del runner
         return out
 
     ppo = None

@@ -258,10 +258,11 @@ class PPO:
 
     def _graph_update_ok(self) -> bool:
         """The whole update (epochs x mini-batches of forward / backward / gradient clip / Adam, adaptive learning rate on the device) as
-        one CUDA graph: single GPU on CUDA by default (H1V2_GRAPH_LEARNER=0 turns it off, =1 also allows it with the NCCL gradient
-        all-reduce inside the capture)."""
+        one CUDA graph, on CUDA by default (H1V2_GRAPH_LEARNER=0 turns it off).  On several GPUs the NCCL gradient / KL all-reduces are
+        inside the capture (2 GPUs, 4096 envs each: learn 76 -> 38 ms per iteration, profiles/r4_notes.md); the runner drops its graphs at
+        interpreter exit, before the process group goes away (OnPolicyRunner.release_graphs)."""
         flag = os.environ.get("H1V2_GRAPH_LEARNER", "")
-        return self._lr_on_device and flag != "0" and (self.multi_gpu is None or flag == "1")
+        return self._lr_on_device and flag != "0"
 
     def update(self):
         if self._graph_update_ok():
@@ -444,6 +445,11 @@ class OnPolicyRunner:
             self.alg_cfg.pop(k, None)
         policy = ActorCritic(num_obs, num_critic, self.env.num_actions, **self.policy_cfg).to(self.device)
         self.alg = PPO(policy, device=self.device, multi_gpu_cfg=self.multi_gpu_cfg, **self.alg_cfg)
+        if self.is_distributed:  # captured graphs hold NCCL work: they must be gone before the communicator is torn down at exit
+            import atexit
+            import weakref
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref().release_graphs())
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
         self.empirical_normalization = self.cfg.get("empirical_normalization", False)
         if self.empirical_normalization:
@@ -553,6 +559,17 @@ class OnPolicyRunner:
                 self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
         if self.log_dir is not None and not self.disable_logs:
             self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+
+    def release_graphs(self):
+        """Drop the captured rollout / update graphs.  With H1V2_GRAPH_LEARNER=1 on several GPUs the update graph carries the NCCL gradient
+        all-reduces: it has to be gone before the process group is destroyed (a communicator with live captured work does not tear down)."""
+        import gc
+        self._fast = None
+        if getattr(self.alg, "_gu", None) is not None:
+            self.alg._gu = None
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def _log(self, it, tot, collection_time, learn_time, loss, ep_infos, rewbuffer, lenbuffer):
         steps = self.num_steps_per_env * self.env.num_envs * self.gpu_world_size
