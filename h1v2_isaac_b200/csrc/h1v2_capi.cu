@@ -96,8 +96,7 @@ struct H1v2Handle {
   unsigned host_seq = 0;
   int host_calib = -1;            // >= 0: calls made so far while the candidates are being timed on this host (see step_host_impl)
   double host_calib_t[5] = {1e30, 1e30, 1e30, 1e30, 1e30};
-  double host_calib_s[5][5] = {};  // the five timed calls of every candidate: the MEDIAN decides (with N ranks on one host the fastest call is the
-                                   // one in which the other ranks' host threads happened to be idle -- not what the steady state looks like)
+  double host_calib_s[5][5] = {};  // the five timed calls of every candidate
   double host_chosen_t = 0.0, host_ema = 0.0;  // watchdog: calibrated time of the chosen candidate, running mean of the calls since
   int host_since = 0, host_recal = 0;          // calls since the calibration ended; re-calibrations so far (at most two)
   // Constraints-as-Terminations tail (cfg.cat_enable)
@@ -487,7 +486,8 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.n = n;
   // envs per warp: 16 fills the lanes; with few envs, fewer per warp shorten every warp's Newton loop (it runs as long as
   // its slowest env).  Measured on B200 (tools/diag_epw.py): best is the smallest group that keeps the grid within ~3.5
-  // warps per SM (4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16).  reserved[2] overrides.
+  // warps per SM (round 1: 4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16); since the mirror-lane instantiation
+  // 8 per warp from 519 to 5624 envs.  reserved[2] overrides.
   {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -496,6 +496,8 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
     // 8 per warp runs the mirror-lane instantiation (10 % cheaper trips): it stays ahead of 16 per warp up to ~4.75 warps per SM
     // (profiles/r4_notes.md: 5120 envs 0.2255 vs 0.2357 ms, 6144 envs 0.2389 vs 0.2379)
     if (epw == 16 && 4 * ((n + 7) / 8) <= 19 * sms && c.reserved[3] == 0) epw = 8;
+    // ... and ahead of 2 / 4 per warp below that (1024 envs: 0.1850 vs 0.1908 ms, 2048 envs: 0.1912 vs 0.2059); one env per warp keeps <= 518 envs
+    if ((epw == 2 || epw == 4) && c.reserved[3] == 0) epw = 8;
     if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) epw = c.reserved[2];
     P.epw = epw;
   }
@@ -1052,11 +1054,14 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
       const int k = h->host_calib++, c = k / per;
       if (k % per >= warm) {
         h->host_calib_s[c][k % per - warm] = dt;
-        if (k % per == per - 1) {  // median of the five
+        if (k % per == per - 1) {
+          // the FASTEST of the five decides.  (The median was tried: the first candidate is timed right after the handle's first calls -- first
+          // touch of the caller's rows by the host threads, thread wake-up -- and lost to a worse one on an otherwise idle host:
+          // profiles/r4_notes.md.  What the fastest call cannot see -- other ranks' host threads in the steady state -- is the watchdog's job.)
           double v[5];
           for (int i = 0; i < 5; i++) v[i] = h->host_calib_s[c][i];
           std::sort(v, v + 5);
-          h->host_calib_t[c] = v[2];
+          h->host_calib_t[c] = v[0];
         }
       }
       const int rows_of[5] = {0, 0, r25, r50, r75};
@@ -1069,7 +1074,7 @@ static int step_host_impl(H1v2Handle* h, const float* actions, float* obs, float
         if (c + 1 < ncand) apply(c + 1);
         else {
           // the plain assemble path is the default; another candidate has to beat it by a margin the timing noise of five calls does not
-          // reach (rows: 5 %, a hybrid split: 2 %); the times are medians of five calls
+          // reach (rows: 5 %, a hybrid split: 2 %)
           int best = 0;
           double tb = h->host_calib_t[0];
           for (int i = 1; i < ncand; i++) {

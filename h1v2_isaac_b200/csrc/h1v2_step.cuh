@@ -548,7 +548,7 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, boo
 // diagnostic variant only: per warp {globaltimer at entry, clock64 cycles of the physics loop, of the whole kernel, trips | lstrips << 32}
 __device__ unsigned long long g_warpclock[4 * 16384];
 #endif
-// QUAD: the instantiation for 8 envs per warp (2049..4144 envs on a B200, BASELINE configs[1]): lanes 16..31 mirror lanes 0..15
+// QUAD: the instantiation for 8 envs per warp (519..5624 envs on a B200, BASELINE configs[1]): lanes 16..31 mirror lanes 0..15
 // instead of shadowing the warp's first env, and share the independent loops of the Newton trip with them (h1v2_physics.cuh)
 template <bool DO_STEP, bool CAT = false, bool ROUGH = false, bool QUAD = false>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,

@@ -166,7 +166,7 @@ def test_rank_shards_are_slices_of_one_job(cfg):
 
 
 def test_mirror_lane_instantiation_is_deterministic_and_agrees_to_rounding(cfg):
-    """8 envs per warp (2073..4144 envs on a B200) run the mirror-lane instantiation: lanes 16..31 hold the same env, leg and
+    """8 envs per warp (519..5624 envs on a B200) run the mirror-lane instantiation: lanes 16..31 hold the same env, leg and
     shared-memory column as lanes 0..15 and take every other iteration of the independent loops of the Newton trip, so the row
     sums are associated differently from the plain kernel's.  It must be deterministic (two handles: bit-identical), must not
     depend on where an env sits in its warp, and one control step from the same state differs from the plain kernel's by
