@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final pass of the third session: parity suite, bench lines of every id, reference arm, ncu launch list of the bench command
+# Final pass of a session (run under gpurun from the repo root): parity suite, bench lines of every id, reference arm, ncu launch list of the bench command
 tag=r4
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/${tag}_tests.log
 python bench.py > gpurun_out/${tag}_bench_4096.json 2> gpurun_out/${tag}_bench_4096.err
