@@ -1,7 +1,8 @@
 """CPU restatement (numpy, float32 like the reference's torch code) of the Constraints-as-Terminations tail -- SURVEY.md 8(f) rank 3.
 
-TEST INFRASTRUCTURE, like everything under oracle/: only tests/ may import it.  There is no CUDA counterpart yet; this file is the
-pinned specification the kernels of the CaT variant will be checked against.  Pinned by
+TEST INFRASTRUCTURE, like everything under oracle/: only tests/ may import it.  It is the pinned specification the CUDA path of the CaT
+variant (the constraint columns inside step_kernel<.., CAT> + cat_apply_kernel, csrc/h1v2_cat.cuh; h1v2_cat_step) is checked against in
+tests/test_gpu_cat.py.  Pinned by
 tests/golden/cat_sequence.npz, which tests/golden/make_cat_goldens.py produced by running the reference's own functions.
 
 Reference (paths relative to packages/biped_tasks/biped_tasks/):
