@@ -487,7 +487,7 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   // envs per warp: 16 fills the lanes; with few envs, fewer per warp shorten every warp's Newton loop (it runs as long as
   // its slowest env).  Measured on B200 (tools/diag_epw.py): best is the smallest group that keeps the grid within ~3.5
   // warps per SM (round 1: 4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16); since the mirror-lane instantiation
-  // 8 per warp from 519 to 5624 envs.  reserved[2] overrides.
+  // 4 per warp (four mirrors per lane) up to 2368 envs, 8 per warp (two mirrors) up to 5624.  reserved[2] overrides.
   {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -496,8 +496,10 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
     // 8 per warp runs the mirror-lane instantiation (10 % cheaper trips): it stays ahead of 16 per warp up to ~4.75 warps per SM
     // (profiles/r4_notes.md: 5120 envs 0.2255 vs 0.2357 ms, 6144 envs 0.2389 vs 0.2379)
     if (epw == 16 && 4 * ((n + 7) / 8) <= 19 * sms && c.reserved[3] == 0) epw = 8;
-    // ... and ahead of 2 / 4 per warp below that (1024 envs: 0.1850 vs 0.1908 ms, 2048 envs: 0.1912 vs 0.2059); one env per warp keeps <= 518 envs
-    if ((epw == 2 || epw == 4) && c.reserved[3] == 0) epw = 8;
+    // ... and below one warp per scheduler at 4 per warp (2368 envs), 4 per warp with FOUR mirrors per lane is ahead of everything else
+    // (profiles/r4_notes.md: 2048 envs 0.1784 ms against 0.1911 at 8 and 0.2053 plain; 1024: 0.1699 / 0.1847 / 0.1973; 256: 0.1610 against 0.1703
+    // at one env per warp), above it 8 per warp (2560 envs: 0.1926 against 0.2015)
+    if (c.reserved[3] == 0 && epw < 16) epw = (n + 3) / 4 <= 4 * sms ? 4 : 8;
     if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) epw = c.reserved[2];
     P.epw = epw;
   }
@@ -923,8 +925,10 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute((step_kernel<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute((step_kernel<true, false, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute((step_kernel<true, false, true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, 2>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, true, 4>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
   if (!h->attr_set) {  // function attributes are per device: keep the flag with the handle, not with the process
@@ -933,25 +937,36 @@ static int launch_step(H1v2Handle* h, bool do_step, const float* actions, float*
     CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((step_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute((step_kernel<true, false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaFuncSetAttribute((step_kernel<true, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute((step_kernel<true, true, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, 2>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, false, false, 4>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, 2>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((step_kernel<true, true, false, 4>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_set = true;
   }
-  const bool quad = h->P.epw == 8 && !h->no_quad;  // 8 envs per warp: the mirror-lane instantiations
+  const bool quad = h->P.epw == 8 && !h->no_quad;  // 8 envs per warp: the mirror-lane instantiations (two mirrors per lane)
+  const bool octo = h->P.epw == 4 && !h->no_quad;  // 4 envs per warp: four mirrors per lane
   if (h->rough && do_step && quad)
-    step_kernel<true, false, true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+    step_kernel<true, false, true, 2><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (h->rough && do_step && octo)
+    step_kernel<true, false, true, 4><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (h->rough && do_step)
     step_kernel<true, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (h->rough)
     step_kernel<false, false, true><<<blocks, threads, smem, st>>>(h->P, S, nullptr, obs, nullptr, nullptr, nullptr);
   else if (do_step && cat && quad)
-    step_kernel<true, true, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+    step_kernel<true, true, false, 2><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (do_step && cat && octo)
+    step_kernel<true, true, false, 4><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step && cat)
     step_kernel<true, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step && quad)
-    step_kernel<true, false, false, true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+    step_kernel<true, false, false, 2><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
+  else if (do_step && octo)
+    step_kernel<true, false, false, 4><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else if (do_step)
     step_kernel<true><<<blocks, threads, smem, st>>>(h->P, S, actions, obs, rew, term, trunc);
   else  // the observe-only launch stages the history rings in the same shared-memory window

@@ -121,8 +121,18 @@ __device__ __forceinline__ V3 pair_sum(V3 v) { return mk3(pair_sum(v.x), pair_su
 // column) instead of idling, and the loops whose iterations are independent -- the rows and contact points of the line
 // search -- are dealt to the two mirrors by parity; this sum over the mirror pair closes them.  Addition commutes, so both
 // mirrors hold the same bits afterwards and stay mirrors.
-template <bool QUAD>
-__device__ __forceinline__ real mirror_sum(real v) { return QUAD ? v + __shfl_xor_sync(FULL_MASK, v, 16) : v; }
+// NM = mirrors per lane: 1 (plain, 16 envs per warp), 2 (8 envs per warp, lanes l and l+16), 4 (4 envs per warp: l, l+8, l+16, l+24 -- the
+// two butterfly stages add symmetric pairs, so all four end with the same bits too).
+template <int NM>
+__device__ __forceinline__ real mirror_sum(real v) {
+  if (NM == 4) v = v + __shfl_xor_sync(FULL_MASK, v, 8);
+  return NM > 1 ? v + __shfl_xor_sync(FULL_MASK, v, 16) : v;
+}
+template <int NM>
+__device__ __forceinline__ real mirror_max(real v) {
+  if (NM == 4) v = r_max(v, __shfl_xor_sync(FULL_MASK, v, 8));
+  return NM > 1 ? r_max(v, __shfl_xor_sync(FULL_MASK, v, 16)) : v;
+}
 
 // MuJoCo getimpedance (solimp = d0, dmax, width, midpoint, power), margin 0
 __device__ __forceinline__ real impedance(const float* si, real pos) {
@@ -372,15 +382,16 @@ __device__ __forceinline__ real impedance_call(const float* si, real pos) {
 // ----------------------------------------------------------------------------------------------------------
 // ROUGH: contacts against the height field of the Rough id (terrain height and triangle normal under every candidate, residuals
 // held in the contact frame) -- its own instantiation, the plane kernel carries none of that code.
-template <bool ROUGH, bool QUAD>
+template <bool ROUGH, int NM>
 __device__ __forceinline__ void substep(const KParams& P, const unsigned tid, const int side, real (&rp)[3],
                                      real (&rq)[4], real (&rv)[3], real (&rw)[3], real (&q)[6], real (&qd)[6],
                                      const real (&tau)[6], const real mu, const real mass_add, real (&wl)[6], real (&wr)[6],
                                      const bool use_warm, SubOut& out, const float* __restrict__ terrain_h, const TerrainEnv& te) {
   extern __shared__ __align__(16) real smem_raw[];
-  const SmemT<ROUGH ? PSTRIDE_ROUGH : PSTRIDE> sm{smem_raw + (QUAD ? (tid & 15u) : tid)};
-  const int q0 = QUAD ? (int)(tid >> 4) : 0;  // first iteration of a dealt loop; its stride is QS
-  constexpr int QS = QUAD ? 2 : 1;
+  constexpr bool QUAD = NM > 1;  // mirror-lane instantiation
+  const SmemT<ROUGH ? PSTRIDE_ROUGH : PSTRIDE> sm{smem_raw + (NM == 4 ? (tid & 7u) : NM == 2 ? (tid & 15u) : tid)};
+  const int q0 = NM == 4 ? (int)(tid >> 3) : NM == 2 ? (int)(tid >> 4) : 0;  // first iteration of a dealt loop; its stride is QS
+  constexpr int QS = NM;
   const KLeg& LG = P.leg[side];
   const real h = P.h;
   const int j0 = 6 * side;
@@ -587,14 +598,14 @@ UNROLL(U_PRO)
       Wl_f = Wl_s = F_torso = zero3;
       if (QUAD) {  // the sole points (the common case) dealt to the mirrors; shin / torso / pelvis points below by both
 #pragma unroll 1
-        for (int p = q0; p < n_foot; p += 2) {
+        for (int p = q0; p < n_foot; p += QS) {
           const V3 r = sm.pv(p, 0);
           V3 Fp = point_force(sm.pv(p, 3), sm.pf(p, 6), sm.pf(p, 7), mu);
           if (ROUGH) Fp = from_contact(cframe(sm.pv(p, 8)), Fp);
           Wn_f = Wn_f + cross(r, Fp); Wl_f = Wl_f + Fp;
         }
-        Wn_f = mk3(mirror_sum<QUAD>(Wn_f.x), mirror_sum<QUAD>(Wn_f.y), mirror_sum<QUAD>(Wn_f.z));
-        Wl_f = mk3(mirror_sum<QUAD>(Wl_f.x), mirror_sum<QUAD>(Wl_f.y), mirror_sum<QUAD>(Wl_f.z));
+        Wn_f = mk3(mirror_sum<NM>(Wn_f.x), mirror_sum<NM>(Wn_f.y), mirror_sum<NM>(Wn_f.z));
+        Wl_f = mk3(mirror_sum<NM>(Wl_f.x), mirror_sum<NM>(Wl_f.y), mirror_sum<NM>(Wl_f.z));
       }
 UNROLL(U_EVP)
       for (int p = (QUAD) ? n_foot : 0; p < nact; p++) {
@@ -641,9 +652,9 @@ UNROLL(U_EVJ)
       if (QUAD) __syncwarp();  // the mirror's joints are in the shared column
       F_torso = pair_sum(F_torso);
       F_pelvis = pair_sum(F_pelvis);
-      gn2 = mirror_sum<QUAD>(pair_sum(gn2));
+      gn2 = mirror_sum<NM>(pair_sum(gn2));
       gv = r_max(gv, __shfl_xor_sync(FULL_MASK, gv, 1));
-      if (QUAD) gv = r_max(gv, __shfl_xor_sync(FULL_MASK, gv, 16));
+      gv = mirror_max<NM>(gv);
 #pragma unroll
       for (int k = 0; k < 6; k++) { jr[k] = pair_sum(gr_own[k]); rr[k] = jr[k] - Mar[k]; gn2 = r_fma(rr[k], rr[k], gn2); }
       if (mode == MODE_NEWTON) {
@@ -838,8 +849,8 @@ UNROLL(U_LSP)
           if (ROUGH) us = to_contact(cframe(sm.pv(p, 8)), us);
           point_ls(fma3(us, alpha, sm.pv(p, 3)), us, sm.pf(p, 6), sm.pf(p, 7), mu, d1, d2);
         }
-        d1 = mirror_sum<QUAD>(pair_sum(d1)) + r_fma(alpha, sMs, sMa);
-        d2 = mirror_sum<QUAD>(pair_sum(d2)) + sMs;
+        d1 = mirror_sum<NM>(pair_sum(d1)) + r_fma(alpha, sMs, sMa);
+        d2 = mirror_sum<NM>(pair_sum(d2)) + sMs;
         if (search) {
           if (r_abs(d1) <= P.ls_tol * r_abs(d10) || !(d2 > 0.f)) search = false;
           else {

@@ -548,9 +548,10 @@ __device__ __forceinline__ void finalize_step(const KState& S, bool do_step, boo
 // diagnostic variant only: per warp {globaltimer at entry, clock64 cycles of the physics loop, of the whole kernel, trips | lstrips << 32}
 __device__ unsigned long long g_warpclock[4 * 16384];
 #endif
-// QUAD: the instantiation for 8 envs per warp (519..5624 envs on a B200, BASELINE configs[1]): lanes 16..31 mirror lanes 0..15
+// NM > 1: the mirror-lane instantiations -- NM = 2 for 8 envs per warp (2369..5624 envs on a B200, BASELINE configs[1]): lanes 16..31 mirror lanes 0..15;
+// NM = 4 for 4 envs per warp (<= 2368 envs): lanes l, l+8, l+16, l+24 --
 // instead of shadowing the warp's first env, and share the independent loops of the Newton trip with them (h1v2_physics.cuh)
-template <bool DO_STEP, bool CAT = false, bool ROUGH = false, bool QUAD = false>
+template <bool DO_STEP, bool CAT = false, bool ROUGH = false, int NM = 1>
 __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant__ KParams P, const KState S, const float* __restrict__ actions,
                                                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ term,
                                                   uint8_t* __restrict__ trunc) {
@@ -568,10 +569,11 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
   int wc_trips = 0, wc_ls = 0;
 #endif
   const int side = tid & 1;
-  const int slot = QUAD ? (int)((tid >> 1) & 7u) : (int)(tid >> 1);
+  constexpr bool QUAD = NM > 1;  // NM mirrors per lane: 2 at 8 envs per warp, 4 at 4 envs per warp
+  const int slot = QUAD ? (int)((tid >> 1) & (16u / NM - 1u)) : (int)(tid >> 1);
   const int warp_env0 = (int)bid * P.epw;
   const bool in_range = (QUAD || slot < P.epw) && warp_env0 + slot < P.n;
-  const bool valid = in_range && (!QUAD || tid < 16u);  // a mirror lane computes everything and stores nothing
+  const bool valid = in_range && (!QUAD || tid < 32u / NM);  // a mirror lane computes everything and stores nothing
   const int env = in_range ? warp_env0 + slot : min(warp_env0, P.n - 1);
   const int lidx = 2 * env + side;
   const int N = P.n, N2 = 2 * P.n;
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(H1V2_BLOCK) step_kernel(const __grid_constant_
           cat_max_publish(CM, S.cat.cmax);
         }
       }
-      substep<ROUGH, QUAD>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
+      substep<ROUGH, NM>(P, tid, side, rp, rq, rv, rw, q, qd, tau, mu, mass_add, wl, wr, use_warm, so, S.terrain_h, te);
       use_warm = true;
 #ifdef H1V2_WARPCLOCK
       wc_trips += so.trips; wc_ls += so.lstrips;

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 ILLEGAL, FEET = [2, 3, 4, 5], [0, 1]
 
 
-@pytest.mark.parametrize("epw", [16, 8])  # 16: the plain instantiation of the CaT step; 8: the mirror-lane one (8 envs per warp, what 4096 envs run)
+@pytest.mark.parametrize("epw", [16, 8, 4])  # 16: the plain instantiation of the CaT step; 8 / 4: the mirror-lane ones (two mirrors per lane: what 4096 envs run; four: <= 2368 envs)
 def test_cat_tail_matches_the_pinned_oracle(epw):
     import torch
     from h1v2_isaac_b200._capi import CSTR_COL0, CSTR_NAMES, rsl_config

@@ -165,8 +165,9 @@ def test_rank_shards_are_slices_of_one_job(cfg):
     whole.close(); shard.close()
 
 
-def test_mirror_lane_instantiation_is_deterministic_and_agrees_to_rounding(cfg):
-    """8 envs per warp (519..5624 envs on a B200) run the mirror-lane instantiation: lanes 16..31 hold the same env, leg and
+@pytest.mark.parametrize("epw", [8, 4])
+def test_mirror_lane_instantiation_is_deterministic_and_agrees_to_rounding(cfg, epw):
+    """8 envs per warp (2369..5624 envs on a B200; 4 per warp with four mirrors per lane below that) run the mirror-lane instantiation: lanes 16..31 hold the same env, leg and
     shared-memory column as lanes 0..15 and take every other iteration of the independent loops of the Newton trip, so the row
     sums are associated differently from the plain kernel's.  It must be deterministic (two handles: bit-identical), must not
     depend on where an env sits in its warp, and one control step from the same state differs from the plain kernel's by
@@ -174,8 +175,8 @@ def test_mirror_lane_instantiation_is_deterministic_and_agrees_to_rounding(cfg):
     import torch
     from h1v2_isaac_b200.backend import H1v2Sim
     n = 203
-    cq = cfg.copy(); cq.reserved[2] = 8
-    cp = cfg.copy(); cp.reserved[2] = 8; cp.reserved[3] = 1
+    cq = cfg.copy(); cq.reserved[2] = epw
+    cp = cfg.copy(); cp.reserved[2] = epw; cp.reserved[3] = 1
     q1, q2, pl = H1v2Sim(n, cq, device="cuda:0", seed=9), H1v2Sim(n, cq, device="cuda:0", seed=9), H1v2Sim(n, cp, device="cuda:0", seed=9)
     cs = cq.copy(); cs.env_id_offset = 3
     shifted = H1v2Sim(n - 3, cs, device="cuda:0", seed=9)  # the global envs 3..n-1 at other lane positions

@@ -52,7 +52,7 @@ def test_reset_state_matches_oracle(cfg):
         np.testing.assert_allclose(g[k], o[k], rtol=0, atol=2e-6, err_msg=k)
 
 
-@pytest.mark.parametrize("decimation,action_scale,epw", [(1, 1.0, 16), (1, 0.3, 16), (4, 1.0, 16), (1, 1.0, 8), (4, 1.0, 8)])
+@pytest.mark.parametrize("decimation,action_scale,epw", [(1, 1.0, 16), (1, 0.3, 16), (4, 1.0, 16), (1, 1.0, 8), (4, 1.0, 8), (1, 1.0, 4), (4, 1.0, 4)])
 def test_physics_parity_from_identical_states(cfg, decimation, action_scale, epw):
     """(c): every control step starts from the SAME state on both sides (oracle re-synchronised to the GPU state).
     decimation=1 is the single physics step of the north star and is asserted LITERALLY: positions within 1e-4 rad / m and
@@ -64,8 +64,9 @@ def test_physics_parity_from_identical_states(cfg, decimation, action_scale, epw
     Envs within 2e-6 m (rad) of a contact (joint-limit) activation boundary at a substep start are skipped and counted:
     the soft contact switches on discontinuously at dist = 0, so float-vs-double rounding of the distance decides those.
     epw = 16: the plain instantiation with every lane pair on its own env (what >= 5625 envs, e.g. the 32768 of the north star, run).
-    epw = 8: the mirror-lane instantiation 519..5624 envs run (BASELINE configs[1], 4096 envs): lanes 16..31 mirror lanes 0..15
-    and take every other row / sole point of the gradient evaluation, the line search and the step."""
+    epw = 8: the mirror-lane instantiation 2369..5624 envs run (BASELINE configs[1], 4096 envs): lanes 16..31 mirror lanes 0..15
+    and take every other row / sole point of the gradient evaluation, the line search and the step.  epw = 4: four mirrors per
+    lane (lanes l, l+8, l+16, l+24), what <= 2368 envs run."""
     c = cfg.copy()
     c.reserved[2] = epw
     c.decimation = decimation
@@ -297,7 +298,7 @@ def _tail_parity(cfg, n, steps, min_events, min_term=None, reweight=None):
     return stats
 
 
-@pytest.mark.parametrize("epw", [16, 8])  # 16: the plain instantiation (>= 5625 envs); 8: the mirror-lane one (519..5624 envs)
+@pytest.mark.parametrize("epw", [16, 8, 4])  # 16: the plain instantiation (>= 5625 envs); 8 / 4: the mirror-lane ones (two / four mirrors per lane)
 def test_bounded_divergence_over_1000_steps(cfg, epw):
     """(c) free-running: 1000 control steps of both implementations under a stabilising (zero) action stay statistically
     together and finite; individual trajectories are allowed to separate (contact dynamics are chaotic)."""
@@ -395,7 +396,7 @@ def test_full_size_properties(cfg, task, n):
         assert torch.equal(b1[:, :-1], b0[:, 1:])
     assert int(ep_a.max()) <= 12
     # sharding: the second half of the envs simulated on its own (rank 1 of 2) reproduces the same trajectories
-    # (bit for bit between handles on the same kernel instantiation: 519..5624 envs run the mirror-lane one, whose row sums are
+    # (bit for bit between handles on the same kernel instantiation: <= 5624 envs run the mirror-lane ones, whose row sums are
     # associated differently -- for that size the whole job is re-run on the plain instantiation, cfg.reserved[3] = 1)
     half = n // 2
     obs_w = obs_a if n != 4096 else run(0, n, steps=3, plain=1)[0]

@@ -46,7 +46,7 @@ def test_rough_terrain_levels_and_reset_state_match_oracle(rough):
     sim.close()
 
 
-@pytest.mark.parametrize("decimation,rough_cm,epw", [(1, 2, 16), (1, 8, 16), (4, 2, 16), (1, 8, 8)])  # epw 16: the plain instantiation, 8: the mirror-lane one
+@pytest.mark.parametrize("decimation,rough_cm,epw", [(1, 2, 16), (1, 8, 16), (4, 2, 16), (1, 8, 8), (1, 8, 4)])  # epw 16: the plain instantiation, 8 / 4: the mirror-lane ones
 def test_rough_physics_parity_from_identical_states(rough, decimation, rough_cm, epw):
     """North star (c) on the height field, asserted literally for one physics step: positions within 1e-4 rad / m and velocities within
     1e-3 rad/s (m/s) on every kept env-step.  rough_cm = 2 is the reference's generator cfg (0 .. 2 cm); 8 makes the slopes four times
