@@ -117,9 +117,10 @@ typedef SmemT<PSTRIDE> Smem;
 #define FULL_MASK 0xffffffffu
 __device__ __forceinline__ real pair_sum(real v) { return v + __shfl_xor_sync(FULL_MASK, v, 1); }
 __device__ __forceinline__ V3 pair_sum(V3 v) { return mk3(pair_sum(v.x), pair_sum(v.y), pair_sum(v.z)); }
-// QUAD instantiation (8 envs per warp): lanes 16..31 mirror lanes 0..15 bit for bit (same env, same leg, same shared-memory
-// column) instead of idling, and the loops whose iterations are independent -- the rows and contact points of the line
-// search -- are dealt to the two mirrors by parity; this sum over the mirror pair closes them.  Addition commutes, so both
+// Mirror-lane instantiations (fewer than 16 envs per warp): the lanes that would idle MIRROR the working ones bit for bit (same
+// env, same leg, same shared-memory column), and the loops whose iterations are independent -- joint rows of the gradient
+// evaluation, sole points, rows and contact points of the line search, the step -- are dealt to the mirrors round-robin (same
+// instruction stream, different index: no divergence); this sum over the mirrors closes them.  Addition commutes, so all
 // mirrors hold the same bits afterwards and stay mirrors.
 // NM = mirrors per lane: 1 (plain, 16 envs per warp), 2 (8 envs per warp, lanes l and l+16), 4 (4 envs per warp: l, l+8, l+16, l+24 -- the
 // two butterfly stages add symmetric pairs, so all four end with the same bits too).
