@@ -145,6 +145,7 @@ _SYMBOLS = {
     "h1v2_set_state": (C.c_int, [C.c_void_p, C.POINTER(H1v2State), C.c_void_p]),
     "h1v2_get_log": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "h1v2_get_log_host": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
+    "h1v2_envs_per_warp": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "h1v2_debug_iter_hist": (C.c_int, [C.c_void_p, C.POINTER(f32)]),
     "h1v2_launch_count": (i64, [C.c_void_p]),
     "h1v2_measure_fp32_peak": (C.c_int, [i32, C.POINTER(f32)]),

@@ -351,6 +351,24 @@ static void kb_h(const float* solref, const float* solimp, double dt, float* K, 
   *B = (float)(2.0 / std::fmax(1e-15, dmax * tc));
 }
 
+// envs per warp: 16 fills the lanes; with few envs, fewer per warp shorten every warp's Newton loop (it runs as long as
+// its slowest env).  Measured on B200 (tools/diag_epw.py): the plain kernel is best at the smallest group that keeps the grid within
+// ~3.5 warps per SM (round 1: 4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16).  The mirror-lane
+// instantiations (lanes that would idle mirror the working ones and share the independent loops of the Newton trip) move that:
+// below one warp per scheduler at 4 per warp (2368 envs on 148 SMs) 4 per warp with FOUR mirrors per lane is ahead of everything else
+// (profiles/r4_notes.md: 2048 envs 0.1784 ms against 0.1911 at 8 and 0.2053 plain; 1024: 0.1699 / 0.1847 / 0.1973; 256: 0.1610
+// against 0.1703 at one env per warp), then 8 per warp with two mirrors up to ~4.75 warps per SM (5624 envs; 5120 envs: 0.2255
+// against 0.2357 ms at 16 per warp, 6144 envs: 0.2389 against 0.2379), 16 per warp above.  cfg.reserved[2] overrides the result.
+extern "C" int h1v2_envs_per_warp(int n_envs, int sms, int plain) {
+  const int n = n_envs < 1 ? 1 : n_envs;
+  if (sms < 1) sms = 148;
+  int epw = 1;
+  while (epw < 16 && 2 * ((n + epw - 1) / epw) > 7 * sms) epw *= 2;
+  if (plain) return epw;
+  if ((n + 3) / 4 <= 4 * sms) return 4;
+  return 4 * ((n + 7) / 8) <= 19 * sms ? 8 : 16;
+}
+
 static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   std::memset(&P, 0, sizeof(P));
   static const int axis_expect[6] = {2, 1, 0, 1, 1, 0};
@@ -484,24 +502,11 @@ static int build_params(const H1v2Config& c, int n, uint64_t seed, KParams& P) {
   P.key0 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
   P.env_id_offset = c.env_id_offset;
   P.n = n;
-  // envs per warp: 16 fills the lanes; with few envs, fewer per warp shorten every warp's Newton loop (it runs as long as
-  // its slowest env).  Measured on B200 (tools/diag_epw.py): best is the smallest group that keeps the grid within ~3.5
-  // warps per SM (round 1: 4096 envs: 8 per warp, 0.309 ms vs 0.330; 2048: 4; 1024: 2; >= 8192: 16); since the mirror-lane instantiation
-  // 4 per warp (four mirrors per lane) up to 2368 envs, 8 per warp (two mirrors) up to 5624.  reserved[2] overrides.
   {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int epw = 1;
-    while (epw < 16 && 2 * ((n + epw - 1) / epw) > 7 * sms) epw *= 2;
-    // 8 per warp runs the mirror-lane instantiation (10 % cheaper trips): it stays ahead of 16 per warp up to ~4.75 warps per SM
-    // (profiles/r4_notes.md: 5120 envs 0.2255 vs 0.2357 ms, 6144 envs 0.2389 vs 0.2379)
-    if (epw == 16 && 4 * ((n + 7) / 8) <= 19 * sms && c.reserved[3] == 0) epw = 8;
-    // ... and below one warp per scheduler at 4 per warp (2368 envs), 4 per warp with FOUR mirrors per lane is ahead of everything else
-    // (profiles/r4_notes.md: 2048 envs 0.1784 ms against 0.1911 at 8 and 0.2053 plain; 1024: 0.1699 / 0.1847 / 0.1973; 256: 0.1610 against 0.1703
-    // at one env per warp), above it 8 per warp (2560 envs: 0.1926 against 0.2015)
-    if (c.reserved[3] == 0 && epw < 16) epw = (n + 3) / 4 <= 4 * sms ? 4 : 8;
-    if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) epw = c.reserved[2];
-    P.epw = epw;
+    P.epw = h1v2_envs_per_warp(n, sms, c.reserved[3] != 0);
+    if (c.reserved[2] == 1 || c.reserved[2] == 2 || c.reserved[2] == 4 || c.reserved[2] == 8 || c.reserved[2] == 16) P.epw = c.reserved[2];
   }
   return 0;
 }

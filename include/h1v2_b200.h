@@ -374,6 +374,10 @@ int h1v2_set_state(H1v2Handle* h, const H1v2State* src, void* cuda_stream);
 /* device pointer to the float[H1V2_LOG_DIM] log vector (valid for the handle's lifetime, updated by step) */
 int h1v2_get_log(H1v2Handle* h, const float** log_dev);
 int h1v2_get_log_host(H1v2Handle* h, float* log_host /*[H1V2_LOG_DIM]*/);
+/* Envs per warp the step launch of an n_envs handle uses on a GPU with `sms` multiprocessors (host-only, no device needed): 4 (four mirror lanes per
+ * lane, up to one warp per scheduler), 8 (two mirrors, up to ~4.75 warps per SM), 16 above; plain != 0: the rule of the plain instantiation
+ * (cfg.reserved[3]).  cfg.reserved[2] overrides it per handle.  DESIGN.md section 3. */
+int h1v2_envs_per_warp(int n_envs, int sms, int plain);
 /* cumulative histogram of Newton iterations per (env,substep) solve since creation: hist32[k] = #solves with k iterations */
 int h1v2_debug_iter_hist(H1v2Handle* h, float* hist32);
 /* number of kernels launched by this handle since creation (for bench.py's gpu_launches) */

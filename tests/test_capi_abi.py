@@ -26,6 +26,20 @@ def test_library_exports_every_declared_symbol():
         assert s in _capi._SYMBOLS, f"{s} has no ctypes binding"
 
 
+def test_envs_per_warp_rule():
+    """Host logic of the launch geometry (h1v2_envs_per_warp, no device needed): on a 148-SM B200 up to 2368 envs run 4 envs per warp (four mirror
+    lanes per lane, at most one warp per scheduler), up to 5624 envs 8 per warp (two mirrors; BASELINE configs[1] = 4096), 16 above (the north
+    star's 32768); the plain instantiations keep round 1's rule (smallest group within 3.5 warps per SM)."""
+    from h1v2_isaac_b200 import _capi
+    lib = _capi.load_library()
+    f = lambda n, plain=0, sms=148: lib.h1v2_envs_per_warp(n, sms, plain)
+    assert [f(n) for n in (1, 3, 256, 1024, 2048, 2368)] == [4] * 6
+    assert [f(n) for n in (2369, 4096, 5120, 5624)] == [8] * 4
+    assert [f(n) for n in (5625, 8192, 32768, 65536)] == [16] * 4
+    assert [f(n, 1) for n in (256, 518, 519, 1024, 2048, 4096, 8192, 32768)] == [1, 1, 2, 2, 4, 8, 16, 16]
+    assert f(4096, 0, 74) == 16 and f(1184, 0, 74) == 4 and f(0) == 4 and f(4096, 0, 0) == 8  # half the SMs; degenerate arguments
+
+
 def test_struct_layout_matches_c(tmp_path):
     from h1v2_isaac_b200 import _capi
     src = tmp_path / "sz.c"
