@@ -6,6 +6,7 @@ There is no fallback: constructing H1v2Sim without the built library or without 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -35,6 +36,8 @@ class H1v2Sim:
         self.cfg = (cfg or default_config()).copy()
         if diagnostics:
             self.cfg.reserved[0] = 1
+        if os.environ.get("H1V2_PLAIN_KERNEL") == "1":  # A/B switch: the plain instantiations instead of the mirror-lane ones (cfg.reserved[3])
+            self.cfg.reserved[3] = 1
         self.num_envs = int(num_envs)
         self._h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()

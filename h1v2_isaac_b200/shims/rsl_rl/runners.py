@@ -20,14 +20,17 @@ def _act(name: str):
 
 
 class _AlignedLinear(nn.Linear):
-    """nn.Linear whose matmul sees an input width that is a multiple of 8 on CUDA: same parameters and state_dict as nn.Linear, the
-    input and the weight are zero-padded on the fly (the extra products are exact zeros).  The policy's first layer has 450 inputs
-    (45 x 10 history): with K % 4 != 0 cuBLAS falls back to the unaligned TF32 kernels (cutlass_80 ... align1), which were 22 % of the
-    PPO loop's GPU time at 4096 envs (profiles/r3_ppo_launches_summary.txt); padded to 456 the aligned sm_100 kernels run."""
+    """nn.Linear whose matmul CAN see an input width that is a multiple of 8 on CUDA (H1V2_KPAD=1): same parameters and state_dict as
+    nn.Linear, the input and the weight are zero-padded on the fly (the extra products are exact zeros).  The policy's first layer has
+    450 inputs (45 x 10 history): with K % 4 != 0 cuBLAS falls back to the unaligned TF32 kernels (cutlass_80 ... align1), which were
+    22 % of the PPO loop's GPU time at 4096 envs (profiles/r3_ppo_launches_summary.txt); padded to 456 the aligned sm_100 kernels run
+    (learn 42 -> 34 ms per iteration at 4096 envs).  OFF by default: with it the reference's unmodified train.py learns the Flat id three
+    times more slowly (mean episode length 116 instead of 939 after 300 iterations, same kernel, same seed; profiles/r4_notes.md section 8)
+    -- the aligned TF32 kernels evidently do not give the first layer the gradient the unaligned ones do; not understood yet."""
 
     def forward(self, x):
         pad = (-self.in_features) % 8
-        if pad and x.is_cuda:
+        if pad and x.is_cuda and os.environ.get("H1V2_KPAD") == "1":
             return nn.functional.linear(nn.functional.pad(x, (0, pad)), nn.functional.pad(self.weight, (0, pad)), self.bias)
         return nn.functional.linear(x, self.weight, self.bias)
 
